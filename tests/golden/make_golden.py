@@ -1,0 +1,205 @@
+"""Generate tests/golden/hebb_golden.npz + makehebbian_golden.json from the LIVE reference.
+
+Run ONLY in the build container (needs /root/reference, which is not on the GPU
+box):  python tests/golden/make_golden.py
+The reference modules are imported unchanged under an alias; nothing is copied.
+Each case stores the inputs (x, W, bias, hyper-parameters) and what the
+reference produced (y, argmax winners, delta_w, grad after local_update, W
+after N optimiser steps), so both the oracle and the CUDA path can be checked
+on a box without the reference.
+"""
+import importlib.util
+import io
+import json
+import os
+import sys
+import contextlib
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = os.environ.get('HEBB_REFERENCE', '/root/reference')
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+
+
+def load_reference():
+    """Import the reference 'hebb' package under the alias 'ref_hebb'."""
+    spec = importlib.util.spec_from_file_location(
+        'ref_hebb', os.path.join(REF, 'hebb', '__init__.py'),
+        submodule_search_locations=[os.path.join(REF, 'hebb')])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules['ref_hebb'] = mod
+    spec.loader.exec_module(mod)
+    mk = importlib.import_module('ref_hebb.makehebbian')
+    return mod, mk
+
+
+CONV_CASES = [
+    # name, nd, B, Cin, Cout, kernel, stride, padding, spatial, k, bias
+    ('c2d_3x3_p1_k1',      2, 2, 3, 8, 3, 1, 1, (12, 12), 1.0, False),
+    ('c2d_3x3_p1_k50',     2, 2, 3, 8, 3, 1, 1, (12, 12), 50.0, False),
+    ('c2d_c1_config1',     2, 2, 3, 64, 3, 1, 1, (32, 32), 3.0, False),
+    ('c2d_16_16',          2, 2, 16, 16, 3, 1, 1, (20, 24), 50.0, False),
+    ('c2d_1x1',            2, 3, 24, 12, 1, 1, 0, (9, 7), 5.0, True),
+    ('c2d_stride2_nopad',  2, 2, 3, 16, 3, 2, 0, (15, 15), 10.0, False),
+    ('c2d_asym_pad',       2, 1, 4, 6, (3, 3), 1, (2, 1), (8, 10), 2.0, True),
+    ('c2d_rect_kernel',    2, 2, 5, 7, (1, 3), 1, (0, 1), (6, 9), 20.0, False),
+    ('c3d_3x3x3_p1',       3, 2, 1, 8, 3, 1, 1, (6, 8, 10), 50.0, False),
+    ('c3d_8_16',           3, 1, 8, 16, 3, 1, 1, (6, 6, 6), 50.0, False),
+    ('c3d_40ch_chunked',   3, 1, 40, 8, 3, 1, 1, (4, 5, 6), 1.0, False),   # > PARALLEL_CHANNELS
+    ('c3d_1x1x1',          3, 2, 6, 4, 1, 1, 0, (3, 4, 5), 7.0, True),
+]
+
+CONVT_CASES = [
+    ('t2d_2x2_s2',  2, 2, 6, 4, 2, 2, (5, 7), 50.0),
+    ('t2d_k1',      2, 2, 6, 4, 2, 2, (5, 7), 1.0),
+    ('t3d_2x2x2_s2', 3, 2, 8, 4, 2, 2, (3, 4, 5), 50.0),
+    ('t3d_40co',    3, 1, 6, 40, 2, 2, (2, 3, 3), 5.0),    # > PARALLEL_CHANNELS out channels
+]
+
+
+def main():
+    ref, mk = load_reference()
+    out = {}
+    meta = {}
+    g = torch.Generator().manual_seed(20261018)
+
+    def rnd(*shape, scale=1.0):
+        return torch.randn(*shape, generator=g) * scale
+
+    for (name, nd, B, Cin, Cout, kernel, stride, padding, spatial, k, bias) in CONV_CASES:
+        cls = ref.HebbianConv2d if nd == 2 else ref.HebbianConv3d
+        layer = cls(Cin, Cout, kernel, stride=stride, padding=padding, bias=bias,
+                    w_nrm=True, mode='swta', k=k, patchwise=True, alpha=1.)
+        with torch.no_grad():
+            layer.weight.copy_(rnd(*layer.weight.shape, scale=0.3))
+            if bias:
+                layer.bias.copy_(rnd(Cout, scale=0.1))
+        layer.train()
+        x = rnd(B, Cin, *spatial)
+        y = layer(x)
+        dw1 = layer.delta_w.clone()
+        y2 = layer(x * 0.5)          # second forward: delta_w must accumulate
+        dw2 = layer.delta_w.clone()
+        layer.local_update()
+        grad = layer.weight.grad.clone()
+        out[name + '/x'] = x.numpy()
+        out[name + '/w'] = layer.weight.detach().numpy()
+        out[name + '/b'] = layer.bias.detach().numpy()
+        out[name + '/y'] = y.detach().numpy()
+        out[name + '/win'] = y.argmax(dim=1).numpy().astype(np.int32)
+        out[name + '/dw1'] = dw1.numpy()
+        out[name + '/dw2'] = dw2.numpy()
+        out[name + '/grad'] = grad.numpy()
+        assert float(layer.delta_w.abs().max()) == 0.0
+        meta[name] = dict(kind='conv', nd=nd, B=B, Cin=Cin, Cout=Cout, kernel=kernel, stride=stride,
+                          padding=padding, spatial=list(spatial), k=k, bias=bias)
+
+    # zero-norm filter + eval()/alpha==0 produce no update
+    layer = ref.HebbianConv2d(3, 4, 3, padding=1, bias=False, k=5., alpha=1.)
+    with torch.no_grad():
+        layer.weight.copy_(rnd(*layer.weight.shape))
+        layer.weight[2].zero_()
+    x = rnd(2, 3, 6, 6)
+    layer.train()
+    y = layer(x)
+    out['zero_row/x'], out['zero_row/w'] = x.numpy(), layer.weight.detach().numpy()
+    out['zero_row/y'], out['zero_row/dw1'] = y.detach().numpy(), layer.delta_w.clone().numpy()
+    meta['zero_row'] = dict(kind='conv', nd=2, B=2, Cin=3, Cout=4, kernel=3, stride=1, padding=1,
+                            spatial=[6, 6], k=5., bias=False)
+
+    for (name, nd, B, Cin, Cout, kernel, stride, spatial, k) in CONVT_CASES:
+        cls = ref.HebbianConvTranspose2d if nd == 2 else ref.HebbianConvTranspose3d
+        layer = cls(Cin, Cout, kernel, stride=stride, padding=0, bias=False,
+                    w_nrm=True, mode='swta_t', k=k, patchwise=True, alpha=1.)
+        with torch.no_grad():
+            layer.weight.copy_(rnd(*layer.weight.shape, scale=0.3))
+        layer.train()
+        x = rnd(B, Cin, *spatial)
+        y = layer(x)
+        dw1 = layer.delta_w.clone()
+        layer.local_update()
+        out[name + '/x'] = x.numpy()
+        out[name + '/w'] = layer.weight.detach().contiguous().numpy()     # (Cin, Cout, k...)
+        out[name + '/y'] = y.detach().numpy()
+        out[name + '/win'] = y.argmax(dim=1).numpy().astype(np.int32)
+        out[name + '/dw1'] = dw1.contiguous().numpy()
+        out[name + '/grad'] = layer.weight.grad.contiguous().numpy()
+        meta[name] = dict(kind='convT', nd=nd, B=B, Cin=Cin, Cout=Cout, kernel=kernel, stride=stride,
+                          spatial=list(spatial), k=k)
+
+    # multi-step drift: config-1-like layer driven by SGD and Adam for 100 steps
+    for opt_name in ('sgd', 'adam'):
+        layer = ref.HebbianConv2d(3, 16, 3, padding=1, bias=False, k=10., alpha=1.)
+        with torch.no_grad():
+            layer.weight.copy_(rnd(*layer.weight.shape, scale=0.3))
+        w0 = layer.weight.detach().clone()
+        xs = rnd(4, 2, 3, 10, 10)
+        opt = (torch.optim.SGD([layer.weight], lr=1e-3) if opt_name == 'sgd'
+               else torch.optim.Adam([layer.weight], lr=1e-3))
+        layer.train()
+        w_after1 = None
+        for step in range(100):
+            opt.zero_grad()
+            layer(xs[step % 4])
+            layer.local_update()
+            opt.step()
+            if step == 0:
+                w_after1 = layer.weight.detach().clone()
+        out[f'drift_{opt_name}/xs'] = xs.numpy()
+        out[f'drift_{opt_name}/w0'] = w0.numpy()
+        out[f'drift_{opt_name}/w1'] = w_after1.numpy()
+        out[f'drift_{opt_name}/w100'] = layer.weight.detach().numpy()
+        meta[f'drift_{opt_name}'] = dict(kind='drift', opt=opt_name, lr=1e-3, k=10., steps=100)
+
+    np.savez_compressed(os.path.join(HERE, 'hebb_golden.npz'), **out)
+
+    # ---- makehebbian structure on the reference test's toy net (tests/test_makehebbian.py:5-39)
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.down = nn.Sequential(nn.Conv2d(3, 16, 3, stride=2), nn.BatchNorm2d(16), nn.ReLU())
+            self.up = nn.Sequential(nn.ConvTranspose2d(16, 20, 3, stride=2), nn.BatchNorm2d(20), nn.ReLU())
+            self.clf = nn.Sequential(mk.FlattenLast(2), nn.Linear(20, 16), nn.BatchNorm1d(16), nn.ReLU(),
+                                     nn.Dropout(0.5), nn.Linear(16, 10))
+
+        def forward(self, x):
+            return self.clf(self.up(self.down(x)))
+
+    def describe(net):
+        mods = {n: type(m).__name__ for n, m in net.named_modules()}
+        params = {n: [list(p.shape), bool(p.requires_grad), list(p.stride())] for n, p in net.named_parameters()}
+        bufs = {n: list(b.shape) for n, b in net.named_buffers()}
+        hp = {n: dict(mode=m.mode, k=m.k, alpha=m.alpha, w_nrm=m.w_nrm, patchwise=m.patchwise,
+                      kernel_size=list(m.kernel_size), stride=list(m.stride),
+                      padding=(m.padding if isinstance(m.padding, int) else list(m.padding)))
+              for n, m in net.named_modules() if hasattr(m, 'local_update')}
+        return dict(modules=mods, params=params, buffers=bufs, hebb=hp,
+                    state_keys=list(net.state_dict().keys()))
+
+    structures = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = mk.makehebbian(Net(), exclude=['clf.5'], hebb_params={})
+        structures['toy_default_params'] = describe(net)
+        net = mk.makehebbian(Net(), exclude=['clf.5'],
+                             hebb_params={'mode': 'swta_t', 'k': 50., 'w_nrm': True, 'alpha': 1.})
+        structures['toy_swta_t'] = describe(net)
+        net = mk.makehebbian(Net(), exclude=None, hebb_params=None)
+        structures['toy_none'] = describe(net)
+    structures['adjust'] = {
+        'swta_t': mk.adjust_hebbian_params({'mode': 'swta_t', 'k': 3}),
+        'hpca_t': mk.adjust_hebbian_params({'mode': 'hpca_t'}),
+        'swta': mk.adjust_hebbian_params({'mode': 'swta'}),
+        'none': mk.adjust_hebbian_params({'k': 2}),
+    }
+    structures['default_hebb_params'] = {k: (v if not isinstance(v, nn.Module) else type(v).__name__)
+                                         for k, v in mk.default_hebb_params.items()}
+    with open(os.path.join(HERE, 'makehebbian_golden.json'), 'w') as f:
+        json.dump(dict(meta=meta, structures=structures), f, indent=1, sort_keys=True)
+    print('wrote', len(out), 'arrays;', os.path.getsize(os.path.join(HERE, 'hebb_golden.npz')) // 1024, 'KiB')
+
+
+if __name__ == '__main__':
+    main()
