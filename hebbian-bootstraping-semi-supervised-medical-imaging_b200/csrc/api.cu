@@ -1,0 +1,174 @@
+// C-ABI entry points of libhebb_sm100.so (see include/hebb_sm100.h).
+#include "common.cuh"
+#include <mutex>
+
+namespace hebb {
+
+thread_local int g_last_cuda_error = 0;
+unsigned long long g_launches = 0;
+
+static int g_dev_checked = 0;   // 0 unknown, 1 ok, -1 bad
+static int g_num_sms = 148;
+static int g_sm_major = 0, g_sm_minor = 0;
+static std::mutex g_mu;
+
+static void probe_device() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_dev_checked) return;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { (void)cudaGetLastError(); g_dev_checked = -1; return; }
+  int dev = 0;
+  cudaDeviceProp p;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+    (void)cudaGetLastError(); g_dev_checked = -1; return;
+  }
+  g_sm_major = p.major; g_sm_minor = p.minor; g_num_sms = p.multiProcessorCount;
+  g_dev_checked = (p.major == 10) ? 1 : -1;
+}
+
+int device_ok() { if (!g_dev_checked) probe_device(); return g_dev_checked == 1 ? HEBB_OK : HEBB_EARCH; }
+int num_sms() { if (!g_dev_checked) probe_device(); return g_num_sms; }
+
+int resolve_geo(const HebbDesc* d, Geo* g) {
+  if (!d || !g) return HEBB_EARG;
+  if (d->nd != 2 && d->nd != 3) return HEBB_ESHAPE;
+  if (d->B <= 0 || d->Cin <= 0 || d->Cout <= 0) return HEBB_ESHAPE;
+  for (int i = 0; i < 3; ++i) {
+    if (d->in[i] <= 0 || d->k[i] <= 0 || d->stride[i] <= 0 || d->pad_lo[i] < 0 || d->pad_hi[i] < 0) return HEBB_ESHAPE;
+  }
+  if (d->nd == 2 && (d->in[0] != 1 || d->k[0] != 1 || d->stride[0] != 1 || d->pad_lo[0] || d->pad_hi[0])) return HEBB_ESHAPE;
+  g->nd = d->nd; g->B = d->B; g->Cin = d->Cin; g->Cout = d->Cout;
+  g->iD = d->in[0]; g->iH = d->in[1]; g->iW = d->in[2];
+  g->kD = d->k[0]; g->kH = d->k[1]; g->kW = d->k[2];
+  g->sD = d->stride[0]; g->sH = d->stride[1]; g->sW = d->stride[2];
+  g->pD = d->pad_lo[0]; g->pH = d->pad_lo[1]; g->pW = d->pad_lo[2];
+  g->qD = d->pad_hi[0]; g->qH = d->pad_hi[1]; g->qW = d->pad_hi[2];
+  g->transposed = d->transposed ? 1 : 0;
+  const int xD = g->iD + g->pD + g->qD, xH = g->iH + g->pH + g->qH, xW = g->iW + g->pW + g->qW;
+  if (!g->transposed) {
+    if (xD < g->kD || xH < g->kH || xW < g->kW) return HEBB_ESHAPE;
+    g->oD = (xD - g->kD) / g->sD + 1; g->oH = (xH - g->kH) / g->sH + 1; g->oW = (xW - g->kW) / g->sW + 1;
+  } else {
+    g->oD = (xD - 1) * g->sD + g->kD; g->oH = (xH - 1) * g->sH + g->kH; g->oW = (xW - 1) * g->sW + g->kW;
+  }
+  g->taps = g->kD * g->kH * g->kW;
+  g->K = g->Cin * g->taps;
+  g->inS = (long long)g->iD * g->iH * g->iW;
+  g->outS = (long long)g->oD * g->oH * g->oW;
+  // index arithmetic in the kernels is 32-bit within one image and 64-bit across the batch
+  if (g->inS * g->Cin >= (1LL << 31) || g->outS * g->Cout >= (1LL << 31)) return HEBB_ESHAPE;
+  if ((long long)xD * xH * xW >= (1LL << 30)) return HEBB_ESHAPE;
+  return HEBB_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace hebb
+
+using namespace hebb;
+
+extern "C" {
+
+int hebb_query(int* sm_major, int* sm_minor, int* n_sms) {
+  const int ok = device_ok();
+  if (sm_major) *sm_major = g_sm_major;
+  if (sm_minor) *sm_minor = g_sm_minor;
+  if (n_sms) *n_sms = g_num_sms;
+  return ok;
+}
+
+const char* hebb_status_str(int s) {
+  switch (s) {
+    case HEBB_OK: return "ok";
+    case HEBB_EARCH: return "no sm_100 (B200) CUDA device: this library has no other backend";
+    case HEBB_ESHAPE: return "unsupported or inconsistent layer geometry";
+    case HEBB_EALIGN: return "pointer must be 16-byte aligned";
+    case HEBB_EWS: return "workspace missing or smaller than hebb_workspace_bytes()";
+    case HEBB_ECUDA: return "CUDA runtime error (see hebb_last_cuda_error)";
+    case HEBB_EARG: return "null pointer or invalid enum argument";
+    case HEBB_EKERNEL: return "kernel watchdog reported an internal error";
+    default: return "unknown hebb status";
+  }
+}
+
+int hebb_last_cuda_error(void) { return g_last_cuda_error; }
+
+unsigned long long hebb_debug_launch_count(void) { return g_launches; }
+
+const char* hebb_version(void) { return "hebb_sm100 0.1 (sm_100a; fp32 CUDA-core + tcgen05 bf16/bf16x3)"; }
+
+int hebb_out_shape(const HebbDesc* d, int32_t out[3]) {
+  Geo g;
+  HEBB_TRY(resolve_geo(d, &g));
+  if (!out) return HEBB_EARG;
+  out[0] = g.oD; out[1] = g.oH; out[2] = g.oW;
+  return HEBB_OK;
+}
+
+static bool use_tc(const Geo& g, int prec) {
+  return prec != HEBB_PREC_FP32 && !g.transposed && tc_supported(g);
+}
+
+int hebb_workspace_bytes(const HebbDesc* d, int prec, size_t* bytes) {
+  Geo g;
+  HEBB_TRY(resolve_geo(d, &g));
+  if (!bytes) return HEBB_EARG;
+  if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
+  *bytes = use_tc(g, prec) ? tc_workspace_bytes(g, prec) : simt_workspace_bytes(g);
+  return HEBB_OK;
+}
+
+int hebb_uses_tensor_cores(const HebbDesc* d, int prec) {
+  Geo g;
+  if (resolve_geo(d, &g) != HEBB_OK) return 0;
+  return use_tc(g, prec) ? 1 : 0;
+}
+
+int hebb_wnorm(const float* W, float* Wn, float* inv_norm, int64_t rows, int64_t row_stride, int64_t mid,
+               int64_t mid_stride, int64_t inner, void* stream) {
+  HEBB_TRY(device_ok());
+  if (!W || (!Wn && !inv_norm)) return HEBB_EARG;
+  if (rows < 0 || mid <= 0 || inner <= 0) return HEBB_ESHAPE;
+  return launch_wnorm(W, Wn, inv_norm, rows, row_stride, mid, mid_stride, inner, (cudaStream_t)stream);
+}
+
+int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const float* bias, float kinv,
+                        float* y, int32_t* winner, float* delta_w, void* ws, size_t ws_bytes,
+                        unsigned flags, int prec, void* stream) {
+  HEBB_TRY(device_ok());
+  Geo g;
+  HEBB_TRY(resolve_geo(d, &g));
+  if (g.transposed) return HEBB_EARG;
+  if (!x || !W || !y) return HEBB_EARG;
+  if ((flags & HEBB_F_UPDATE) && !delta_w) return HEBB_EARG;
+  if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
+  if (!aligned16(ws)) return HEBB_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(g, prec)) return tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, st);
+  return simt_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, st);
+}
+
+int hebb_convT_swta_step(const HebbDesc* d, const float* x, const float* W, const float* bias, float kinv,
+                         float* y, int32_t* winner, float* delta_w, void* ws, size_t ws_bytes,
+                         unsigned flags, int prec, void* stream) {
+  HEBB_TRY(device_ok());
+  Geo g;
+  HEBB_TRY(resolve_geo(d, &g));
+  if (!g.transposed) return HEBB_EARG;
+  if (!x || !W || !y) return HEBB_EARG;
+  if ((flags & HEBB_F_UPDATE) && !delta_w) return HEBB_EARG;
+  if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
+  if (!aligned16(ws)) return HEBB_EALIGN;
+  return simt_convT_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, (cudaStream_t)stream);
+}
+
+int hebb_local_update_multi(int n, float* const* grad, float* const* dw, const int64_t* numel,
+                            const float* alpha, const int32_t* has_grad, void* stream) {
+  HEBB_TRY(device_ok());
+  if (n < 0) return HEBB_EARG;
+  if (n == 0) return HEBB_OK;
+  if (!grad || !dw || !numel || !alpha || !has_grad) return HEBB_EARG;
+  return launch_local_update_multi(n, grad, dw, numel, alpha, has_grad, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Shared declarations of libhebb_sm100: status codes, geometry, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "hebb_sm100.h"
+
+namespace hebb {
+
+// Thread-local record of the last failing CUDA runtime call (hebb_last_cuda_error()).
+extern thread_local int g_last_cuda_error;
+// Number of kernels this library has launched in this process (hebb_debug_launch_count()).
+extern unsigned long long g_launches;
+#define HEBB_LAUNCHED() (++::hebb::g_launches)
+
+#define HEBB_CUDA_TRY(expr)                                   \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) {                                  \
+      ::hebb::g_last_cuda_error = (int)_e;                    \
+      return HEBB_ECUDA;                                      \
+    }                                                         \
+  } while (0)
+
+#define HEBB_TRY(expr)               \
+  do {                               \
+    int _s = (expr);                 \
+    if (_s != HEBB_OK) return _s;    \
+  } while (0)
+
+// Geometry of one layer, resolved from HebbDesc (device-friendly POD).
+struct Geo {
+  int nd, B, Cin, Cout;
+  int iD, iH, iW;     // unpadded input extent
+  int kD, kH, kW;
+  int sD, sH, sW;
+  int pD, pH, pW;     // pad_lo
+  int qD, qH, qW;     // pad_hi
+  int oD, oH, oW;     // output extent
+  int taps;           // kD*kH*kW
+  int K;              // Cin*taps (conv) — length of one filter
+  long long inS, outS;  // spatial sizes
+  int transposed;
+};
+
+int resolve_geo(const HebbDesc* d, Geo* g);
+int device_ok();          // HEBB_OK iff current device is sm_100
+int num_sms();
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- elementwise stage (elementwise.cu) ----
+int launch_wnorm(const float* W, float* Wn, float* inv, long long rows, long long row_stride,
+                 long long mid, long long mid_stride, long long inner, cudaStream_t st);
+int launch_local_update_multi(int n, float* const* grad, float* const* dw, const int64_t* numel,
+                              const float* alpha, const int32_t* has_grad, cudaStream_t st);
+// delta_w[c,j] += H[c*(K+1)+j] - H[c*(K+1)+K] * W[c,j]
+int launch_finalize_conv(const float* H, const float* W, float* delta_w, int Cout, int K, cudaStream_t st);
+// transposed: see simt_path.cu
+int launch_finalize_convT(const float* H, const float* W, float* delta_w, int Cin, int Cout, int taps,
+                          cudaStream_t st);
+
+// ---- fp32 CUDA-core path (simt_path.cu) ----
+size_t simt_workspace_bytes(const Geo& g);
+int simt_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y,
+                   int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags,
+                   cudaStream_t st);
+int simt_convT_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y,
+                    int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags,
+                    cudaStream_t st);
+
+// ---- tcgen05 path (tc_path.cu) ----
+bool tc_supported(const Geo& g);
+size_t tc_workspace_bytes(const Geo& g, int prec);
+int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y,
+                 int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
+                 cudaStream_t st);
+
+}  // namespace hebb

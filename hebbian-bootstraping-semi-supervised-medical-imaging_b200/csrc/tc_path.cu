@@ -1,0 +1,854 @@
+// tcgen05 / TMEM path of the Hebbian convolution (stride-1 convs, Cout % 16 == 0, Cout <= 256).
+//
+// Both contractions are "shift GEMMs" over ONE packed copy of the activations, so no patch
+// matrix (hebb/hebb.py:105-106, hebb/hebb3d.py:92-101) is ever built:
+//
+//   packed activations  Xp[hl][c8][p][8]  bf16   p = b*Qimg + (d*HP + h)*WP + w  over the ZERO-PADDED
+//                                                 image (halo materialised once, 2 B/elem), channels in
+//                                                 chunks of 8 (one 16-byte vector per position)
+//   packed responses    Rp[hl][c8][p][8]  bf16   same position index, r = softmax_c(k*y), 0 where p is
+//                                                 not a real output pixel
+//   output pixel p, tap (kd,kh,kw)  ->  input position p + (kd*HP + kh)*WP + kw          (stride 1)
+//
+//   forward  D[p, co]        = sum_tap sum_ci Xp[ci][p + shift(tap)] * W[co][ci][tap]
+//            A = 128 consecutive positions x 16 channels, K-major, SWIZZLE_NONE: a tap is just a
+//            16-byte-granular start-address offset into the staged segment; B = packed weights.
+//   dW       H[tap][ci, co]  = sum_p Xp[ci][p + shift(tap)] * Rp[co][p]
+//            A = channels x 16 positions (MN-major), B = channels x 16 positions (MN-major).
+//
+// hl = 0/1 are the hi / lo halves of the bf16x3 split (v = hi + lo up to 2^-17); a product is
+// hi*hi + hi*lo + lo*hi accumulated in fp32 in TMEM.
+//
+// Every global->shared transfer is a 1-D bulk async copy (TMA engine) of a contiguous byte
+// range completing on an mbarrier; one thread issues tcgen05.mma; 4 warps run the epilogue
+// out of TMEM (bias, y store, winner, softmax, bf16 split of r, column sums of r).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace hebb {
+
+using namespace ptx;
+
+constexpr int kMaxTaps = 27;
+constexpr int kSmemLimit = 227 * 1024;
+
+// -------------------------------------------------------------------------------------
+// Packing kernels
+// -------------------------------------------------------------------------------------
+struct PackGeo {
+  int B, Cin, iD, iH, iW, pD, pH, pW, HP, WP, plane, Qimg, CC;
+  long long PA;   // positions per chunk plane (incl. zero slack)
+  long long PTOT; // B*Qimg
+};
+
+__global__ void __launch_bounds__(256)
+pack_x_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __restrict__ xlo, const __grid_constant__ PackGeo g) {
+  const long long total = (long long)g.CC * g.PA;
+  const long long iHW = (long long)g.iH * g.iW;
+  const long long inS = (long long)g.iD * iHW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx / g.PA);
+    const long long p = idx - (long long)c8 * g.PA;
+    uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+    if (p < g.PTOT) {
+      const int b = (int)(p / g.Qimg);
+      int q = (int)(p - (long long)b * g.Qimg);
+      const int d = q / g.plane; q -= d * g.plane;
+      const int hh = q / g.WP;
+      const int w = q - hh * g.WP;
+      const int id = d - g.pD, ih = hh - g.pH, iw = w - g.pW;
+      if ((unsigned)id < (unsigned)g.iD && (unsigned)ih < (unsigned)g.iH && (unsigned)iw < (unsigned)g.iW) {
+        const float* src = x + ((long long)b * g.Cin + c8 * 8) * inS + (long long)id * iHW + (long long)ih * g.iW + iw;
+        __nv_bfloat16 vh[8], vl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = (c8 * 8 + i < g.Cin) ? __ldg(src + (long long)i * inS) : 0.f;
+          split_bf16(v, vh[i], vl[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h[i] = pack_bf16x2(vh[2 * i], vh[2 * i + 1]); l[i] = pack_bf16x2(vl[2 * i], vl[2 * i + 1]); }
+      }
+    }
+    xhi[idx] = make_uint4(h[0], h[1], h[2], h[3]);
+    if (xlo) xlo[idx] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// Wp[slab][tap][hl][c2][co] (uint4 = 8 input channels) : the forward B operand, K-major.
+__global__ void __launch_bounds__(256)
+pack_w_kernel(const float* __restrict__ W, uint4* __restrict__ wp, int Cin, int Cout, int taps, int NSLAB, int HL) {
+  const long long total = (long long)NSLAB * taps * HL * 2 * Cout;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long t = idx;
+    const int co = (int)(t % Cout); t /= Cout;
+    const int c2 = (int)(t % 2); t /= 2;
+    const int hl = (int)(t % HL); t /= HL;
+    const int tap = (int)(t % taps); t /= taps;
+    const int slab = (int)t;
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat16 e[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int ci = (slab * 2 + c2) * 8 + 2 * i + j;
+        const float v = ci < Cin ? __ldg(W + ((long long)co * Cin + ci) * taps + tap) : 0.f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        e[j] = hl ? lo : hi;
+      }
+      o[i] = pack_bf16x2(e[0], e[1]);
+    }
+    wp[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// Forward shift-GEMM + fused soft-WTA epilogue
+// -------------------------------------------------------------------------------------
+struct FwdParams {
+  const uint4* xp[2];
+  const uint4* wp;
+  uint4* rp[2];
+  float* y; int32_t* winner; const float* inv; const float* bias; float* rsum; int* err;
+  int Cout, CC, NSLAB, taps, nseg, HL;
+  long long PA, PR, PTOT;      // positions per chunk plane in Xp / Rp; real positions B*Qimg
+  int MB, TILE_M, ntiles, SEGLEN;
+  int XST, WST, NACC;
+  int WP, plane, Qimg, oD, oH, oW;
+  float kinv; int write_r;
+  int seg_base[4]; int seg_tap_begin[5]; int tap_off[kMaxTaps];
+  uint32_t x_stage_bytes, w_stage_bytes, off_w, off_misc;
+  uint32_t tmem_cols;
+};
+
+template <int CH>
+__device__ __forceinline__ float lane_col_sum(float (&v)[CH], int lane) {
+  // returns in lane l the sum over the 32 lanes of v[l % CH]
+  if (CH == 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+  }
+#pragma unroll
+  for (int off = CH / 2; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int CH> struct TmemLd;
+template <> struct TmemLd<32> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[32]) { tmem_ld32(a, v); } };
+template <> struct TmemLd<16> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) { tmem_ld16(a, v); } };
+
+template <int CH>
+__global__ void __launch_bounds__(192, 1)
+fwd_swta_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  // misc region: [inv Cout][bias Cout][rs 4*Cout] floats, then barriers, then tmem ptr
+  float* s_inv = reinterpret_cast<float*>(smem + p.off_misc);
+  float* s_bias = s_inv + p.Cout;
+  float* s_rs = s_bias + p.Cout;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rs + 4 * p.Cout);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t x_full = bar0, x_empty = x_full + 8 * p.XST;
+  const uint32_t w_full = x_empty + 8 * p.XST, w_empty = w_full + 8 * p.WST;
+  const uint32_t t_full = w_empty + 8 * p.WST, t_empty = t_full + 8 * p.NACC;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * p.XST + 2 * p.WST + 2 * p.NACC);
+
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+    s_inv[i] = p.inv ? p.inv[i] : 1.f;
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 4 * p.Cout; i += blockDim.x) s_rs[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.XST; ++i) { mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 1); }
+    for (int i = 0; i < p.WST; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
+    for (int i = 0; i < p.NACC; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(s_tmem), p.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================== producer: bulk copies =====================
+    if (lane == 0) {
+      int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const long long p0 = (long long)tile * p.TILE_M;
+        for (int slab = 0; slab < p.NSLAB; ++slab) {
+          for (int seg = 0; seg < p.nseg; ++seg) {
+            mbar_wait(x_empty + 8 * xs, xph ^ 1, p.err, 1);
+            mbar_expect_tx(x_full + 8 * xs, p.x_stage_bytes);
+            const uint32_t dst = sbase + xs * p.x_stage_bytes;
+            for (int hl = 0; hl < p.HL; ++hl)
+              for (int c = 0; c < 2; ++c)
+                bulk_g2s(dst + (hl * 2 + c) * p.SEGLEN * 16,
+                         p.xp[hl] + (long long)(slab * 2 + c) * p.PA + p0 + p.seg_base[seg],
+                         p.SEGLEN * 16, x_full + 8 * xs);
+            if (++xs == p.XST) { xs = 0; xph ^= 1; }
+            for (int tap = p.seg_tap_begin[seg]; tap < p.seg_tap_begin[seg + 1]; ++tap) {
+              mbar_wait(w_empty + 8 * ws, wph ^ 1, p.err, 2);
+              mbar_expect_tx(w_full + 8 * ws, p.w_stage_bytes);
+              bulk_g2s(sbase + p.off_w + ws * p.w_stage_bytes,
+                       p.wp + (long long)(slab * p.taps + tap) * p.HL * 2 * p.Cout, p.w_stage_bytes,
+                       w_full + 8 * ws);
+              if (++ws == p.WST) { ws = 0; wph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, p.Cout, 0, 0);
+      const uint64_t a_hi64 = smem_desc_hi(p.SEGLEN * 16, 128);   // LBO: chunk stride, SBO: 8 positions
+      const uint64_t b_hi64 = smem_desc_hi(p.Cout * 16, 128);
+      int xs = 0, ws = 0, acc = 0; uint32_t xph = 0, wph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * p.MB * p.Cout;
+        bool first = true;
+        for (int slab = 0; slab < p.NSLAB; ++slab) {
+          for (int seg = 0; seg < p.nseg; ++seg) {
+            mbar_wait(x_full + 8 * xs, xph, p.err, 4);
+            tc_fence_after();
+            const uint32_t xa = sbase + xs * p.x_stage_bytes;
+            for (int tap = p.seg_tap_begin[seg]; tap < p.seg_tap_begin[seg + 1]; ++tap) {
+              mbar_wait(w_full + 8 * ws, wph, p.err, 5);
+              tc_fence_after();
+              const uint32_t wa = sbase + p.off_w + ws * p.w_stage_bytes;
+              const uint64_t bh = smem_desc(b_hi64, wa);
+              const uint64_t bl = smem_desc(b_hi64, wa + 2 * p.Cout * 16);
+              for (int j = 0; j < p.MB; ++j) {
+                const uint32_t a0 = xa + (j * 128 + p.tap_off[tap]) * 16;
+                const uint64_t ah = smem_desc(a_hi64, a0);
+                const uint32_t d = d0 + j * p.Cout;
+                if (p.HL == 2) {
+                  const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
+                  umma_bf16(d, ah, bl, idesc, first ? 0u : 1u);
+                  umma_bf16(d, al, bh, idesc, 1u);
+                  umma_bf16(d, ah, bh, idesc, 1u);
+                } else {
+                  umma_bf16(d, ah, bh, idesc, first ? 0u : 1u);
+                }
+              }
+              first = false;
+              umma_commit(w_empty + 8 * ws);
+              if (++ws == p.WST) { ws = 0; wph ^= 1; }
+            }
+            umma_commit(x_empty + 8 * xs);
+            if (++xs == p.XST) { xs = 0; xph ^= 1; }
+          }
+        }
+        umma_commit(t_full + 8 * acc);
+        if (++acc == p.NACC) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    const int ew = warp - 2;
+    const int row = quad * 32 + lane;
+    const long long outS = (long long)p.oD * p.oH * p.oW;
+    const int oHW = p.oH * p.oW;
+    const int C8 = p.Cout / 8;
+    float* my_rs = s_rs + ew * p.Cout;
+    int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      mbar_wait(t_full + 8 * acc, aph, p.err, 6);
+      tc_fence_after();
+      for (int j = 0; j < p.MB; ++j) {
+        const long long pp = (long long)tile * p.TILE_M + j * 128 + row;
+        const int b = (int)(pp / p.Qimg);
+        int q = (int)(pp - (long long)b * p.Qimg);
+        const int od = q / p.plane; q -= od * p.plane;
+        const int oh = q / p.WP;
+        const int ow = q - oh * p.WP;
+        const bool valid = (od < p.oD) && (oh < p.oH) && (ow < p.oW) && (pp < p.PTOT);
+        const long long s = (long long)od * oHW + (long long)oh * p.oW + ow;
+        float* yb = p.y + (long long)b * p.Cout * outS + s;
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.MB * p.Cout + j * p.Cout;
+        float mx = -INFINITY, best = -INFINITY;
+        int bi = 0;
+        uint32_t v[CH];
+        for (int c0 = 0; c0 < p.Cout; c0 += CH) {
+          TmemLd<CH>::ld(ta + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const float f = fmaf(__uint_as_float(v[i]), s_inv[c0 + i], s_bias[c0 + i]);
+            if (valid) yb[(long long)(c0 + i) * outS] = f;
+            mx = fmaxf(mx, f * p.kinv);
+            if (f > best) { best = f; bi = c0 + i; }
+          }
+        }
+        if (p.winner && valid) p.winner[(long long)b * outS + s] = bi;
+        if (p.write_r) {
+          float sum = 0.f;
+          for (int c0 = 0; c0 < p.Cout; c0 += CH) {
+            TmemLd<CH>::ld(ta + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const float f = fmaf(__uint_as_float(v[i]), s_inv[c0 + i], s_bias[c0 + i]);
+              sum += __expf(fmaf(f, p.kinv, -mx));
+            }
+          }
+          const float rinv = valid ? (1.f / sum) : 0.f;
+          for (int c0 = 0; c0 < p.Cout; c0 += CH) {
+            TmemLd<CH>::ld(ta + c0, v);
+            tmem_ld_wait();
+            float rr[CH];
+#pragma unroll
+            for (int g8 = 0; g8 < CH / 8; ++g8) {
+              uint32_t oh4[4], ol4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat16 h2[2], l2[2];
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                  const int c = g8 * 8 + i * 2 + k2;
+                  const float f = fmaf(__uint_as_float(v[c]), s_inv[c0 + c], s_bias[c0 + c]);
+                  const float r = __expf(fmaf(f, p.kinv, -mx)) * rinv;
+                  split_bf16(r, h2[k2], l2[k2]);
+                  rr[c] = __bfloat162float(h2[k2]) + (p.HL == 2 ? __bfloat162float(l2[k2]) : 0.f);
+                }
+                oh4[i] = pack_bf16x2(h2[0], h2[1]);
+                ol4[i] = pack_bf16x2(l2[0], l2[1]);
+              }
+              const long long ridx = (long long)(c0 / 8 + g8) * p.PR + pp;
+              if (pp < p.PR) {
+                p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+                if (p.HL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+              }
+            }
+            const float cs = lane_col_sum<CH>(rr, lane);
+            if (lane < CH) my_rs[c0 + lane] += cs;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+      if (++acc == p.NACC) { acc = 0; aph ^= 1; }
+    }
+    __syncwarp();
+    if (p.write_r)
+      for (int c = lane; c < p.Cout; c += 32) atomicAdd(p.rsum + c, my_rs[c]);
+    (void)C8;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// -------------------------------------------------------------------------------------
+// dW shift-GEMM:  Hpart[split][tap][ci][co] = sum_{p in split} Xp[ci][p+shift(tap)] * Rp[co][p]
+// -------------------------------------------------------------------------------------
+struct DwParams {
+  const uint4* xp[2];
+  const uint4* rp[2];
+  float* hpart; int* err;
+  int Cin, Cout, CC, C8, taps, HL;
+  long long PA, PR;
+  int BLK, SEGLEN, total_blocks, blocks_per_split, PS;
+  int ngrp; int grp_base[9]; int grp_tap_begin[10]; int tap_off[kMaxTaps];
+  int CM, n_cin_tiles, CN, n_cout_tiles, ST, CinP;
+  uint32_t stage_bytes, x_bytes, off_bar, tmem_cols;
+};
+
+__global__ void __launch_bounds__(192, 1)
+dw_swta_kernel(const __grid_constant__ DwParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  const uint32_t full = smem_u32(bars), empty = full + 8 * p.ST, done = empty + 8 * p.ST;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * p.ST + 1);
+
+  // output tile fastest: CTAs that stream the same positions run side by side (L2 reuse)
+  int task = blockIdx.x;
+  const int out_tiles = p.ngrp * p.n_cin_tiles * p.n_cout_tiles;
+  const int split = task / out_tiles; task -= split * out_tiles;
+  const int cout_tile = task % p.n_cout_tiles; task /= p.n_cout_tiles;
+  const int cin_tile = task % p.n_cin_tiles; task /= p.n_cin_tiles;
+  const int grp = task;
+  const int cm_chunks = min(p.CM / 8, p.CC - cin_tile * (p.CM / 8));
+  const int N = min(p.CN, p.Cout - cout_tile * p.CN);
+  const int rn_chunks = N / 8;
+  const int tap_b = p.grp_tap_begin[grp], tap_e = p.grp_tap_begin[grp + 1];
+  const int blk_b = min(split * p.blocks_per_split, p.total_blocks);
+  const int blk_e = min(blk_b + p.blocks_per_split, p.total_blocks);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.ST; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(s_tmem), p.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t r_off = p.x_bytes;                 // R region follows X region inside a stage
+  const uint32_t x_hl_stride = cm_chunks * p.SEGLEN * 16;
+  const uint32_t r_hl_stride = (p.CN / 8) * p.BLK * 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      const uint32_t bytes = p.HL * (cm_chunks * p.SEGLEN + rn_chunks * p.BLK) * 16;
+      for (int blk = blk_b; blk < blk_e; ++blk) {
+        const long long p0 = (long long)blk * p.BLK;
+        mbar_wait(empty + 8 * st, ph ^ 1, p.err, 11);
+        mbar_expect_tx(full + 8 * st, bytes);
+        const uint32_t dst = sbase + st * p.stage_bytes;
+        for (int hl = 0; hl < p.HL; ++hl) {
+          for (int c = 0; c < cm_chunks; ++c)
+            bulk_g2s(dst + hl * x_hl_stride + c * p.SEGLEN * 16,
+                     p.xp[hl] + (long long)(cin_tile * (p.CM / 8) + c) * p.PA + p0 + p.grp_base[grp],
+                     p.SEGLEN * 16, full + 8 * st);
+          for (int c = 0; c < rn_chunks; ++c)
+            bulk_g2s(dst + r_off + hl * r_hl_stride + c * p.BLK * 16,
+                     p.rp[hl] + (long long)(cout_tile * (p.CN / 8) + c) * p.PR + p0, p.BLK * 16, full + 8 * st);
+        }
+        if (++st == p.ST) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(p.CM, N, 1, 1);
+      const uint64_t a_hi64 = smem_desc_hi(128, p.SEGLEN * 16);   // MN-major: LBO = next 8 positions, SBO = next chunk
+      const uint64_t b_hi64 = smem_desc_hi(128, p.BLK * 16);
+      int st = 0; uint32_t ph = 0;
+      const int ksteps = p.BLK / 16;
+      for (int blk = blk_b; blk < blk_e; ++blk) {
+        mbar_wait(full + 8 * st, ph, p.err, 12);
+        tc_fence_after();
+        const uint32_t xa = sbase + st * p.stage_bytes;
+        const uint32_t ra = xa + r_off;
+        const uint32_t accum0 = (blk == blk_b) ? 0u : 1u;
+        for (int tap = tap_b; tap < tap_e; ++tap) {
+          const uint32_t d = tmem_base + (tap - tap_b) * p.CN;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t a0 = xa + (ks * 16 + p.tap_off[tap]) * 16;
+            const uint32_t b0 = ra + ks * 256;
+            const uint64_t ah = smem_desc(a_hi64, a0), bh = smem_desc(b_hi64, b0);
+            const uint32_t acc = (ks == 0) ? accum0 : 1u;
+            if (p.HL == 2) {
+              const uint64_t al = smem_desc(a_hi64, a0 + x_hl_stride), bl = smem_desc(b_hi64, b0 + r_hl_stride);
+              umma_bf16(d, ah, bl, idesc, acc);
+              umma_bf16(d, al, bh, idesc, 1u);
+              umma_bf16(d, ah, bh, idesc, 1u);
+            } else {
+              umma_bf16(d, ah, bh, idesc, acc);
+            }
+          }
+        }
+        umma_commit(empty + 8 * st);
+        if (++st == p.ST) { st = 0; ph ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int quad = warp & 3;
+    mbar_wait(done, 0, p.err, 13);
+    tc_fence_after();
+    int row; bool row_ok;
+    if (p.CM == 128) { row = quad * 32 + lane; row_ok = true; }
+    else { row = quad * 16 + (lane & 15); row_ok = lane < 16; }    // M=64: D row r lives in lane (r%16)+32*(r/16)
+    const int ci = cin_tile * p.CM + row;
+    const bool st_ok = row_ok && ci < p.Cin;
+    const bool have = blk_e > blk_b;
+    for (int tap = tap_b; tap < tap_e; ++tap) {
+      const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (tap - tap_b) * p.CN;
+      float* dst = p.hpart + (((long long)split * p.taps + tap) * p.CinP + ci) * p.Cout + cout_tile * p.CN;
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(ta + c0, v);
+        tmem_ld_wait();
+        if (st_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 o;
+            o.x = have ? __uint_as_float(v[4 * i + 0]) : 0.f; o.y = have ? __uint_as_float(v[4 * i + 1]) : 0.f;
+            o.z = have ? __uint_as_float(v[4 * i + 2]) : 0.f; o.w = have ? __uint_as_float(v[4 * i + 3]) : 0.f;
+            *reinterpret_cast<float4*>(dst + c0 + 4 * i) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// delta_w[co][ci][t] += sum_s Hpart[s][t][ci][co] - rsum[co] * W[co][ci][t]
+__global__ void __launch_bounds__(256)
+tc_finalize_kernel(const float* __restrict__ hpart, const float* __restrict__ rsum, const float* __restrict__ W,
+                   float* __restrict__ dw, int PS, int taps, int Cin, int CinP, int Cout) {
+  const long long n = (long long)taps * Cin * Cout;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % Cout);
+    long long t2 = idx / Cout;
+    const int ci = (int)(t2 % Cin);
+    const int t = (int)(t2 / Cin);
+    float acc = 0.f;
+    for (int s = 0; s < PS; ++s) acc += hpart[(((long long)s * taps + t) * CinP + ci) * Cout + co];
+    const long long wi = ((long long)co * Cin + ci) * taps + t;
+    dw[wi] += acc - rsum[co] * W[wi];
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// Host-side planning
+// -------------------------------------------------------------------------------------
+static int round_up_i(long long v, int a) { return (int)((v + a - 1) / a * a); }
+__host__ __device__ static inline uint32_t pow2_cols(int c) { uint32_t r = 32; while ((int)r < c) r <<= 1; return r; }
+
+struct Plan {
+  // geometry of the packed position space
+  int HP, WP, plane, Qimg, CC, NSLAB, C8;
+  long long PTOT, PR, PA;
+  int maxshift;
+  // forward
+  int f_HL, MB, TILE_M, f_SEGLEN, XST, WST, NACC, f_nseg, f_ntiles;
+  uint32_t f_x_stage, f_w_stage, f_off_w, f_off_misc, f_smem, f_tmem;
+  // dW
+  int d_HL, BLK, d_SEGLEN, d_by_kh, ngrp, CM, n_cin_tiles, CN, n_cout_tiles, PS, total_blocks, blocks_per_split, ST, CinP;
+  uint32_t d_stage, d_x_bytes, d_off_bar, d_smem, d_tmem;
+  // workspace carve (byte offsets)
+  size_t o_inv, o_rsum, o_err, o_xp[2], o_rp[2], o_wp, o_hpart, total;
+  bool ok;
+};
+
+static bool plan_layer(const Geo& g, int prec, Plan* P) {
+  Plan& q = *P;
+  q.ok = false;
+  if (g.transposed || g.sD != 1 || g.sH != 1 || g.sW != 1) return false;
+  if (g.Cout % 16 || g.Cout > 256 || g.taps > kMaxTaps) return false;
+  if (g.kD > 3 || g.kH > 9 || g.kW > 9) return false;
+  q.HP = g.iH + g.pH + g.qH; q.WP = g.iW + g.pW + g.qW;
+  const int xD = g.iD + g.pD + g.qD;
+  q.plane = q.HP * q.WP;
+  const long long qimg = (long long)xD * q.plane;
+  if (qimg * g.B >= (1LL << 31)) return false;
+  q.Qimg = (int)qimg;
+  q.PTOT = qimg * g.B;
+  q.NSLAB = (g.Cin + 15) / 16; q.CC = q.NSLAB * 2; q.C8 = g.Cout / 8;
+  q.maxshift = ((g.kD - 1) * q.HP + (g.kH - 1)) * q.WP + (g.kW - 1);
+  const int sms = num_sms();
+
+  // ---------------- forward ----------------
+  q.f_HL = 2;                                   // forward is always split (exact winners)
+  const int halo = (g.kH - 1) * q.WP + (g.kW - 1);
+  q.f_nseg = g.kD;
+  q.f_w_stage = (uint32_t)q.f_HL * 2 * g.Cout * 16;
+  const uint32_t misc = (uint32_t)(6 * g.Cout * 4 + 8 * 64 + 64);
+  bool found = false;
+  for (int mb = 4; mb >= 1 && !found; mb >>= 1) {
+    if (mb * g.Cout > 256 && !(mb == 1)) continue;
+    // do not make tiles so large that the grid cannot fill the machine
+    if (mb > 1 && cdiv(q.PTOT, 128LL * mb) < 2LL * sms) continue;
+    const int seglen = round_up_i(128 * mb + halo, 8);
+    const uint32_t xst = (uint32_t)q.f_HL * 2 * seglen * 16;
+    for (int nx = 3; nx >= 2 && !found; --nx) {
+      for (int nw = 8; nw >= 2 && !found; nw >>= 1) {
+        const uint32_t tot = nx * xst + nw * q.f_w_stage + misc + 256;
+        if (tot <= (uint32_t)kSmemLimit - 1024) {
+          q.MB = mb; q.TILE_M = 128 * mb; q.f_SEGLEN = seglen; q.XST = nx; q.WST = nw;
+          q.f_x_stage = xst; found = true;
+        }
+      }
+    }
+  }
+  if (!found) return false;
+  q.NACC = (2 * q.MB * g.Cout <= 512) ? 2 : 1;
+  q.f_tmem = pow2_cols(q.NACC * q.MB * g.Cout);
+  q.f_off_w = q.XST * q.f_x_stage;
+  q.f_off_misc = q.f_off_w + q.WST * q.f_w_stage;
+  q.f_smem = q.f_off_misc + misc;
+
+  // ---------------- dW ----------------
+  q.d_HL = (prec == HEBB_PREC_BF16) ? 1 : 2;
+  q.CM = (q.CC * 8 <= 64) ? 64 : 128;
+  q.n_cin_tiles = (int)cdiv(q.CC * 8, q.CM);
+  q.CinP = q.n_cin_tiles * q.CM;
+  const int cm_chunks = (q.CC < q.CM / 8) ? q.CC : q.CM / 8;
+  found = false;
+  for (int by_kh = 0; by_kh <= 1 && !found; ++by_kh) {
+    const int gtaps = by_kh ? g.kW : g.kH * g.kW;
+    const int ghalo = by_kh ? (g.kW - 1) : halo;
+    int cn = (512 / gtaps) / 16 * 16;
+    if (cn > g.Cout) cn = g.Cout;
+    if (cn > 256) cn = 256;
+    if (cn < 16) continue;
+    for (int blk = 1024; blk >= 128 && !found; blk >>= 1) {
+      if (!by_kh && ghalo > blk) continue;              // halo dominates: regroup by kernel row instead
+      const int seglen = round_up_i(blk + ghalo, 8);
+      const uint32_t xb = (uint32_t)q.d_HL * cm_chunks * seglen * 16;
+      const uint32_t rb = (uint32_t)q.d_HL * (cn / 8) * blk * 16;
+      for (int st = 3; st >= 2 && !found; --st) {
+        // the A descriptor always spans CM/8 chunks: the rows past cm_chunks read whatever
+        // follows in shared memory (discarded rows) but must stay inside the allocation
+        const uint32_t ring = st * (xb + rb);
+        const uint32_t last_read = (st - 1) * (xb + rb) + (q.d_HL - 1) * cm_chunks * seglen * 16 +
+                                   (uint32_t)(q.CM / 8) * seglen * 16 + 256;
+        uint32_t tot = ring > last_read ? ring : last_read;
+        tot += 8 * 16 + 64;
+        if (tot <= (uint32_t)kSmemLimit - 1024) {
+          q.d_by_kh = by_kh; q.BLK = blk; q.d_SEGLEN = seglen; q.ST = st; q.CN = cn;
+          q.d_x_bytes = xb; q.d_stage = xb + rb;
+          q.d_off_bar = (tot - (8 * 16 + 64) + 127) / 128 * 128;
+          q.d_smem = q.d_off_bar + 8 * 16 + 64;
+          found = true;
+        }
+      }
+    }
+  }
+  if (!found) return false;
+  q.ngrp = q.d_by_kh ? g.kD * g.kH : g.kD;
+  q.n_cout_tiles = (int)cdiv(g.Cout, q.CN);
+  q.d_tmem = pow2_cols((q.d_by_kh ? g.kW : g.kH * g.kW) * q.CN);
+
+  // packed position space: multiples of both tile sizes
+  const int big = q.TILE_M > q.BLK ? q.TILE_M : q.BLK;
+  q.PR = (q.PTOT + big - 1) / big * big;
+  q.PA = (q.PR + q.maxshift + 16 + 7) / 8 * 8;
+  q.f_ntiles = (int)(q.PR / q.TILE_M);
+  q.total_blocks = (int)(q.PR / q.BLK);
+  const int out_tiles = q.ngrp * q.n_cin_tiles * q.n_cout_tiles;
+  int ps = (sms + out_tiles - 1) / out_tiles;
+  if (ps > q.total_blocks) ps = q.total_blocks;
+  if (ps < 1) ps = 1;
+  q.blocks_per_split = (int)cdiv(q.total_blocks, ps);
+  q.PS = (int)cdiv(q.total_blocks, q.blocks_per_split);
+
+  // ---------------- workspace ----------------
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  q.o_inv = take(sizeof(float) * g.Cout);
+  q.o_rsum = take(sizeof(float) * g.Cout);
+  q.o_err = take(256);
+  q.o_xp[0] = take((size_t)q.CC * q.PA * 16);
+  q.o_xp[1] = take((size_t)q.CC * q.PA * 16);
+  q.o_rp[0] = take((size_t)q.C8 * q.PR * 16);
+  q.o_rp[1] = take((size_t)q.C8 * q.PR * 16);
+  q.o_wp = take((size_t)q.NSLAB * g.taps * q.f_HL * 2 * g.Cout * 16);
+  q.o_hpart = take((size_t)q.PS * g.taps * q.CinP * g.Cout * sizeof(float));
+  q.total = off;
+  q.ok = true;
+  return true;
+}
+
+bool tc_supported(const Geo& g) {
+  Plan P;
+  return plan_layer(g, HEBB_PREC_BF16X3, &P);
+}
+
+size_t tc_workspace_bytes(const Geo& g, int prec) {
+  Plan P;
+  if (!plan_layer(g, prec, &P)) return 0;
+  return P.total;
+}
+
+static unsigned ew_grid(long long n) {
+  long long gx = cdiv(n, 256);
+  const long long cap = (long long)num_sms() * 16;
+  return (unsigned)(gx > cap ? cap : (gx < 1 ? 1 : gx));
+}
+
+int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y,
+                 int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
+                 cudaStream_t st) {
+  Plan P;
+  if (!plan_layer(g, prec, &P)) return HEBB_ESHAPE;
+  if (!ws || ws_bytes < P.total) return HEBB_EWS;
+  char* base = static_cast<char*>(ws);
+  float* inv = reinterpret_cast<float*>(base + P.o_inv);
+  float* rsum = reinterpret_cast<float*>(base + P.o_rsum);
+  int* err = reinterpret_cast<int*>(base + P.o_err);
+  uint4* xp0 = reinterpret_cast<uint4*>(base + P.o_xp[0]);
+  uint4* xp1 = reinterpret_cast<uint4*>(base + P.o_xp[1]);
+  uint4* rp0 = reinterpret_cast<uint4*>(base + P.o_rp[0]);
+  uint4* rp1 = reinterpret_cast<uint4*>(base + P.o_rp[1]);
+  uint4* wp = reinterpret_cast<uint4*>(base + P.o_wp);
+  float* hpart = reinterpret_cast<float*>(base + P.o_hpart);
+  const bool upd = (flags & HEBB_F_UPDATE) != 0;
+
+  // profiling aid: HEBB_F_ONLY_* re-run one stage on the scratch left by a preceding full call
+  const unsigned only = flags & (HEBB_F_ONLY_PACK | HEBB_F_ONLY_FWD | HEBB_F_ONLY_DW);
+  const bool do_pack = !only || (only & HEBB_F_ONLY_PACK);
+  const bool do_fwd = !only || (only & HEBB_F_ONLY_FWD);
+  const bool do_dw = upd && (!only || (only & HEBB_F_ONLY_DW));
+  if (do_fwd) HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, (P.o_xp[0] - P.o_rsum), st));   // rsum + err word
+  if ((flags & HEBB_F_WNRM) && do_pack) HEBB_TRY(launch_wnorm(W, nullptr, inv, g.Cout, g.K, 1, 0, g.K, st));
+
+  PackGeo pg;
+  pg.B = g.B; pg.Cin = g.Cin; pg.iD = g.iD; pg.iH = g.iH; pg.iW = g.iW; pg.pD = g.pD; pg.pH = g.pH; pg.pW = g.pW;
+  pg.HP = P.HP; pg.WP = P.WP; pg.plane = P.plane; pg.Qimg = P.Qimg; pg.CC = P.CC; pg.PA = P.PA; pg.PTOT = P.PTOT;
+  if (do_pack) {
+    pack_x_kernel<<<ew_grid((long long)P.CC * P.PA), 256, 0, st>>>(x, xp0, xp1, pg);
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  }
+  if (do_pack) {
+    const long long n = (long long)P.NSLAB * g.taps * P.f_HL * 2 * g.Cout;
+    pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL);
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  }
+
+  // ---- forward ----
+  FwdParams f;
+  f.xp[0] = xp0; f.xp[1] = xp1; f.wp = wp; f.rp[0] = rp0; f.rp[1] = rp1;
+  f.y = y; f.winner = winner; f.inv = (flags & HEBB_F_WNRM) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = err;
+  f.Cout = g.Cout; f.CC = P.CC; f.NSLAB = P.NSLAB; f.taps = g.taps; f.nseg = P.f_nseg; f.HL = P.f_HL;
+  f.PA = P.PA; f.PR = P.PR; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
+  f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC;
+  f.WP = P.WP; f.plane = P.plane; f.Qimg = P.Qimg; f.oD = g.oD; f.oH = g.oH; f.oW = g.oW;
+  f.kinv = kinv; f.write_r = upd ? 1 : 0;
+  for (int s = 0; s < 4; ++s) f.seg_base[s] = s * P.plane;
+  for (int s = 0; s <= 4; ++s) f.seg_tap_begin[s] = (s <= g.kD ? s : g.kD) * g.kH * g.kW;
+  for (int t = 0; t < kMaxTaps; ++t) f.tap_off[t] = 0;
+  for (int kd = 0, t = 0; kd < g.kD; ++kd)
+    for (int kh = 0; kh < g.kH; ++kh)
+      for (int kw = 0; kw < g.kW; ++kw, ++t) f.tap_off[t] = kh * P.WP + kw;
+  f.x_stage_bytes = P.f_x_stage; f.w_stage_bytes = P.f_w_stage; f.off_w = P.f_off_w; f.off_misc = P.f_off_misc;
+  f.tmem_cols = P.f_tmem;
+  const int fgrid = P.f_ntiles < num_sms() ? P.f_ntiles : num_sms();
+  if (!do_fwd) {
+  } else if (g.Cout % 32 == 0) {
+    HEBB_CUDA_TRY(cudaFuncSetAttribute(fwd_swta_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    fwd_swta_kernel<32><<<fgrid, 192, kSmemLimit, st>>>(f);
+  } else {
+    HEBB_CUDA_TRY(cudaFuncSetAttribute(fwd_swta_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    fwd_swta_kernel<16><<<fgrid, 192, kSmemLimit, st>>>(f);
+  }
+  if (do_fwd) { HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED(); }
+  if (!do_dw) return HEBB_OK;
+
+  // ---- dW ----
+  DwParams d;
+  d.xp[0] = xp0; d.xp[1] = xp1; d.rp[0] = rp0; d.rp[1] = rp1; d.hpart = hpart; d.err = err;
+  d.Cin = g.Cin; d.Cout = g.Cout; d.CC = P.CC; d.C8 = P.C8; d.taps = g.taps; d.HL = P.d_HL;
+  d.PA = P.PA; d.PR = P.PR; d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
+  d.blocks_per_split = P.blocks_per_split; d.PS = P.PS; d.ngrp = P.ngrp;
+  for (int i = 0; i < 9; ++i) d.grp_base[i] = 0;
+  for (int i = 0; i < 10; ++i) d.grp_tap_begin[i] = g.taps;
+  for (int t = 0; t < kMaxTaps; ++t) d.tap_off[t] = 0;
+  if (P.d_by_kh) {
+    for (int kd = 0, gi = 0; kd < g.kD; ++kd)
+      for (int kh = 0; kh < g.kH; ++kh, ++gi) {
+        d.grp_base[gi] = kd * P.plane + kh * P.WP;
+        d.grp_tap_begin[gi] = gi * g.kW;
+        for (int kw = 0; kw < g.kW; ++kw) d.tap_off[gi * g.kW + kw] = kw;
+      }
+  } else {
+    for (int kd = 0; kd < g.kD; ++kd) {
+      d.grp_base[kd] = kd * P.plane;
+      d.grp_tap_begin[kd] = kd * g.kH * g.kW;
+      for (int kh = 0; kh < g.kH; ++kh)
+        for (int kw = 0; kw < g.kW; ++kw) d.tap_off[(kd * g.kH + kh) * g.kW + kw] = kh * P.WP + kw;
+    }
+  }
+  d.grp_tap_begin[P.ngrp] = g.taps;
+  d.CM = P.CM; d.n_cin_tiles = P.n_cin_tiles; d.CN = P.CN; d.n_cout_tiles = P.n_cout_tiles; d.ST = P.ST; d.CinP = P.CinP;
+  d.stage_bytes = P.d_stage; d.x_bytes = P.d_x_bytes; d.off_bar = P.d_off_bar; d.tmem_cols = P.d_tmem;
+  const int dgrid = P.ngrp * P.n_cin_tiles * P.n_cout_tiles * P.PS;
+  HEBB_CUDA_TRY(cudaFuncSetAttribute(dw_swta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  dw_swta_kernel<<<dgrid, 192, kSmemLimit, st>>>(d);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  {
+    const long long n = (long long)g.taps * g.Cin * g.Cout;
+    tc_finalize_kernel<<<ew_grid(n), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS, g.taps, g.Cin, P.CinP, g.Cout);
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  }
+  return HEBB_OK;
+}
+
+// -------------------------------------------------------------------------------------
+// Descriptor probe (tests/test_umma_probe.py): one CTA, raw images, raw descriptors.
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const uint8_t* __restrict__ a_img, int a_bytes, const uint8_t* __restrict__ b_img, int b_bytes,
+                  uint64_t a_hi, uint32_t a_start, uint32_t a_step, uint64_t b_hi, uint32_t b_start,
+                  uint32_t b_step, uint32_t idesc, int ksteps, int m, int n, float* __restrict__ d_out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sa = smem_u32(smem);
+  const uint32_t b_off = (uint32_t)((a_bytes + 1023) / 1024 * 1024);
+  for (int i = threadIdx.x; i < a_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+  for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem + b_off)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  const uint32_t cols = pow2_cols(n);
+  if (warp == 0) { tmem_alloc(smem_u32(&s_tmem), cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = s_tmem;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < ksteps; ++k)
+      umma_bf16(tb, smem_desc(a_hi, sa + a_start + k * a_step), smem_desc(b_hi, sa + b_off + b_start + k * b_step),
+                idesc, k ? 1u : 0u);
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+  tc_fence_after();
+  // dump all 128 lanes x n columns; the host maps lanes to rows (M=64 uses lanes (r%16)+32*(r/16))
+  const uint32_t ta = tb + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(ta + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (c0 + i < n) d_out[(long long)(warp * 32 + lane) * n + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, cols);
+  (void)m;
+}
+
+}  // namespace hebb
+
+extern "C" int hebb_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
+                                     uint64_t a_desc_hi, uint32_t a_start, uint32_t a_step,
+                                     uint64_t b_desc_hi, uint32_t b_start, uint32_t b_step, uint32_t idesc,
+                                     int ksteps, int m, int n, float* d_out, void* stream) {
+  using namespace hebb;
+  HEBB_TRY(device_ok());
+  if (!a_img || !b_img || !d_out) return HEBB_EARG;
+  if (a_bytes % 16 || b_bytes % 16 || n % 8 || n < 8 || n > 256 || (m != 64 && m != 128)) return HEBB_ESHAPE;
+  const size_t smem = (size_t)((a_bytes + 1023) / 1024 * 1024) + b_bytes + 1024;
+  if (smem > (size_t)kSmemLimit) return HEBB_ESHAPE;
+  HEBB_CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
+      static_cast<const uint8_t*>(a_img), a_bytes, static_cast<const uint8_t*>(b_img), b_bytes, a_desc_hi, a_start,
+      a_step, b_desc_hi, b_start, b_step, idesc, ksteps, m, n, d_out);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}

@@ -1,0 +1,285 @@
+"""Dimension-agnostic implementation behind HebbianConv{2,3}d / HebbianConvTranspose{2,3}d.
+
+The public classes in hebb.py / hebb3d.py keep the reference's constructor signatures,
+attributes, state_dict keys and method names (reference hebb/hebb.py:16-277,
+hebb/hebb3d.py:15-305); everything numerical is a call into libhebb_sm100.so.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native
+
+
+def normalize(x, dim=None):
+    """x / ||x||_2 over `dim` with zero norms mapped to 1 (reference hebb/hebb.py:10-13).
+
+    CUDA float32 tensors whose reduced dims are every dim but the first are normalised by the
+    hebb_wnorm kernel; anything else (other dims, other dtypes, CPU tensors — this function is
+    also a plain utility in the reference) is evaluated with ordinary tensor ops.
+    """
+    nd = x.dim()
+    dims = tuple(range(nd)) if dim is None else tuple(d % nd for d in (dim if isinstance(dim, (tuple, list)) else (dim,)))
+    if (x.is_cuda and x.dtype == torch.float32 and nd >= 2 and dims == tuple(range(1, nd))
+            and not (torch.is_grad_enabled() and x.requires_grad)):
+        lay = _dense_layout(x)
+        if lay is not None:
+            return _native.wnorm(x.detach(), *lay)
+    nrm = (x ** 2).sum(dim=dims, keepdim=True) ** 0.5
+    nrm = torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+    return x / nrm
+
+
+def _dense_layout(w: torch.Tensor):
+    """(rows,row_stride,mid,mid_stride,inner) for hebb_wnorm, or None if w is neither contiguous
+    nor the transposed (dim0<->dim1) view of a contiguous buffer."""
+    if w.is_contiguous():
+        inner = w[0].numel()
+        return (w.shape[0], inner, 1, 0, inner)
+    base = w.transpose(0, 1)
+    if base.is_contiguous() and w.storage_offset() == base.storage_offset():
+        taps = math.prod(w.shape[2:]) if w.dim() > 2 else 1
+        return (w.shape[0], taps, w.shape[1], w.shape[0] * taps, taps)
+    return None
+
+
+def _ntuple(v, n):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
+
+
+class _HebbFn(torch.autograd.Function):
+    """Forward = the sm_100 kernels.  Backward (only reached when back-prop gradients are wanted,
+    i.e. alpha < 1 or a trainable layer upstream) differentiates the same formula with stock ATen
+    convolution-backward — SURVEY.md §8(f) row 3 lists native dgrad/wgrad as a later step."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer, update):
+        ctx.layer = layer
+        ctx.save_for_backward(x, weight, bias)
+        return layer._launch(x, weight, bias, update)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, bias = ctx.saved_tensors
+        layer = ctx.layer
+        need = ctx.needs_input_grad
+        with torch.enable_grad():
+            xx = x.detach().requires_grad_(need[0])
+            ww = weight.detach().requires_grad_(need[1])
+            bb = bias.detach().requires_grad_(need[2]) if bias is not None else None
+            yy = layer._aten_formula(xx, ww, bb)
+            wanted = [t for t, n in ((xx, need[0]), (ww, need[1]), (bb, need[2])) if n and t is not None]
+            got = list(torch.autograd.grad(yy, wanted, gy, allow_unused=True))
+        out = []
+        for t, n in ((xx, need[0]), (ww, need[1]), (bb, need[2])):
+            out.append(got.pop(0) if (n and t is not None) else None)
+        return out[0], out[1], out[2], None, None
+
+
+class _HebbianConvNd(nn.Module):
+    """Shared body.  Sub-classes set `_nd` and `_transposed`."""
+
+    MODE_SWTA = 'swta'
+    MODE_HPCA = 'hpca'
+    MODE_CONTRASTIVE = 'contrastive'
+    _nd = 2
+    _transposed = False
+
+    def _setup(self, in_channels, out_channels, kernel_size, stride, padding, bias, w_nrm, act,
+               mode, k, patchwise, contrast, uniformity, alpha):
+        nd = self._nd
+        self.mode = mode
+        self.out_channels = out_channels
+        self.in_channels = in_channels
+        self.kernel_size = _ntuple(kernel_size, nd)
+        self.padding = padding
+        self.stride = _ntuple(stride, nd)
+        self.weight = nn.Parameter(torch.empty((out_channels, in_channels, *self.kernel_size)), requires_grad=True)
+        nn.init.xavier_normal_(self.weight)
+        self.w_nrm = w_nrm
+        self.bias = nn.Parameter(torch.zeros(out_channels), requires_grad=bias)
+        self.act = act
+        self.register_buffer('delta_w', torch.zeros_like(self.weight))
+        self.k = k
+        self.patchwise = patchwise
+        self.contrast = contrast
+        self.uniformity = uniformity
+        self.alpha = alpha
+        if self._transposed:
+            # the reference keeps (Cin, Cout, k...) VIEWS of (Cout, Cin, k...) storage (hebb.py:222-224)
+            with torch.no_grad():
+                self.weight.transpose_(0, 1)
+                self.delta_w.transpose_(0, 1)
+        # --- not part of the reference API ---
+        self.prec = None              # None -> library default (hebb.set_precision / HEBB_PREC)
+        self.record_winners = False   # when True the last forward's argmax map is kept in .winners
+        self.winners = None
+        self._desc_cache = {}
+
+    # ------------------------------------------------------------------ geometry
+    def _pad_list(self):
+        nd = self._nd
+        p = self.padding
+        if isinstance(p, int):
+            return [p] * (2 * nd)
+        p = list(p)
+        if len(p) == nd:
+            out = []
+            for v in p:
+                out += [v, v]
+            return out
+        return p
+
+    def _pad_lo_hi(self):
+        """(lo, hi) per spatial axis in (D,)H,W order, as F.pad would apply self._pad_list()."""
+        nd = self._nd
+        lst = self._pad_list()
+        if len(lst) % 2 or len(lst) > 2 * nd:
+            raise RuntimeError(f'padding {self.padding!r} pads non-spatial dims; unsupported by the sm_100 Hebbian layer')
+        lo, hi = [0] * nd, [0] * nd
+        for i in range(len(lst) // 2):          # pair i pads dim -(i+1)
+            lo[nd - 1 - i], hi[nd - 1 - i] = int(lst[2 * i]), int(lst[2 * i + 1])
+        if min(lo + hi) < 0:
+            raise RuntimeError('negative padding is not supported by the sm_100 Hebbian layer')
+        return lo, hi
+
+    def _desc(self, x_shape, pad):
+        key = (tuple(x_shape), pad)
+        d = self._desc_cache.get(key)
+        if d is None:
+            lo, hi = self._pad_lo_hi() if pad else ([0] * self._nd, [0] * self._nd)
+            d = _native.make_desc(self._nd, x_shape[0], self.in_channels, self.out_channels, x_shape[2:],
+                                  self.kernel_size, self.stride, lo, hi, self._transposed)
+            d._out = _native.out_shape(d)
+            if len(self._desc_cache) > 16:
+                self._desc_cache.clear()
+            self._desc_cache[key] = d
+        return d
+
+    # ------------------------------------------------------------------ storage helpers
+    def _raw(self, t):
+        """The contiguous (Cout, Cin, k...) tensor that shares (or mirrors) t's storage."""
+        if not self._transposed:
+            return (t if t.is_contiguous() else None)
+        b = t.transpose(0, 1)
+        return b if b.is_contiguous() else None
+
+    # ------------------------------------------------------------------ kernels
+    def _launch(self, x, weight, bias, update, pad=True, w_nrm=None):
+        if x.dim() != self._nd + 2:
+            raise RuntimeError(f'expected a {self._nd + 2}-D input, got {tuple(x.shape)}')
+        if not x.is_cuda:
+            raise RuntimeError('Hebbian layers of this package run on CUDA (sm_100) only: move the model and '
+                               'its inputs to the GPU; there is no CPU fallback')
+        x = x.detach()
+        if x.dtype != torch.float32:
+            raise RuntimeError(f'input must be float32, got {x.dtype}')
+        if not x.is_contiguous():
+            x = x.contiguous()
+        w = self._raw(weight.detach())
+        tmp_w = w is None
+        if tmp_w:   # unusual strides (e.g. after a user re-assignment): work on a dense copy
+            w = (weight.detach().transpose(0, 1) if self._transposed else weight.detach()).contiguous()
+        desc = self._desc(x.shape, pad)
+        y = torch.empty((x.shape[0], self.out_channels, *desc._out), dtype=torch.float32, device=x.device)
+        win = None
+        if self.record_winners:
+            win = torch.empty((x.shape[0], *desc._out), dtype=torch.int32, device=x.device)
+        flags = _native.F_WNRM if (self.w_nrm if w_nrm is None else w_nrm) else 0
+        dw = None
+        tmp_dw = None
+        if update:
+            flags |= _native.F_UPDATE
+            dw = self._raw(self.delta_w)
+            if dw is None:
+                tmp_dw = torch.zeros_like(w)
+                dw = tmp_dw
+        b = bias.detach() if bias is not None else None
+        _native.conv_step(desc, x, w, b, float(self.k), y, win, dw, flags, _native.parse_prec(self.prec))
+        if tmp_dw is not None:
+            self.delta_w += tmp_dw.transpose(0, 1) if self._transposed else tmp_dw
+        self.winners = win
+        return y
+
+    def _aten_formula(self, x, w, b):
+        """The reference formula with stock ops; used ONLY to differentiate (see _HebbFn.backward)."""
+        x = F.pad(x, self._pad_list())
+        if self.w_nrm:
+            nrm = (w ** 2).sum(dim=tuple(range(1, w.dim())), keepdim=True) ** 0.5
+            w = w / torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+        if self._transposed:
+            op = torch.conv_transpose2d if self._nd == 2 else torch.conv_transpose3d
+        else:
+            op = torch.conv2d if self._nd == 2 else torch.conv3d
+        return op(x, w, bias=b, stride=self.stride)
+
+    # ------------------------------------------------------------------ reference API
+    def apply_weights(self, x, w):
+        """conv / conv_transpose of an already padded x with the given weights (no normalisation)."""
+        return self._launch(x, w, self.bias, update=False, pad=False, w_nrm=False)
+
+    def compute_activation(self, x):
+        """y = act(conv(x, W/|W|)) for an already padded x."""
+        return self.act(self._launch(x, self.weight, self.bias, update=False, pad=False))
+
+    def pad(self, x):
+        return F.pad(x, self._pad_list())
+
+    def _check_mode(self):
+        valid = [self.MODE_SWTA, self.MODE_HPCA, self.MODE_CONTRASTIVE]
+        if self._transposed:
+            valid += [self.MODE_SWTA_T, self.MODE_HPCA_T]
+        if self.mode not in valid:
+            raise NotImplementedError("Learning mode {} unavailable for {} layer".format(self.mode, self.__class__.__name__))
+        native = self.MODE_SWTA_T if self._transposed else self.MODE_SWTA
+        if self.mode != native or not self.patchwise:
+            raise NotImplementedError(
+                "Learning mode {} (patchwise={}) of {} is not built into libhebb_sm100 yet; the sm_100 library "
+                "implements the pretraining path ('{}', patchwise=True) and has no PyTorch fallback".format(
+                    self.mode, self.patchwise, self.__class__.__name__, native))
+
+    def forward(self, x):
+        update = bool(self.training and self.alpha != 0)
+        if update:
+            self._check_mode()
+        w = self.weight
+        if self.alpha == 1:
+            w = w.detach()       # (1 - alpha) * grad == 0 in local_update(): no need to back-prop into W
+        b = self.bias
+        if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
+            y = _HebbFn.apply(x, w, b, self, update)
+        else:
+            y = self._launch(x, w, b, update)
+        return self.act(y)
+
+    def compute_update(self, x, y):
+        """Accumulate the plasticity update for an already padded x into delta_w (y is recomputed
+        on chip; the argument is accepted for signature compatibility)."""
+        self._check_mode()
+        self._launch(x, self.weight, self.bias, update=True, pad=False)
+
+    @torch.no_grad()
+    def local_update(self):
+        """weight.grad = (1 - alpha) * weight.grad - alpha * delta_w ; delta_w = 0  (hebb.py:174-192)."""
+        dw = self.delta_w
+        had = self.weight.grad is not None
+        if not dw.is_cuda:
+            raise RuntimeError('local_update(): the layer must live on a CUDA device (no CPU fallback)')
+        if not had:
+            self.weight.grad = torch.empty_like(dw)           # same (possibly transposed) strides as delta_w
+        g = self.weight.grad
+        if g.stride() != dw.stride() or _dense_layout(dw) is None:
+            g = g.contiguous() if had else g
+            new = torch.empty_like(dw, memory_format=torch.contiguous_format)
+            d2 = dw.contiguous()
+            if had:
+                new.copy_(g)
+            _native.local_update_multi([new], [d2], [self.alpha], [had])
+            self.weight.grad = new
+            dw.zero_()
+            return
+        _native.local_update_multi([g], [dw], [self.alpha], [had])

@@ -1,0 +1,230 @@
+"""ctypes binding of libhebb_sm100.so (C ABI in include/hebb_sm100.h).
+
+PyTorch is used here only for device memory and streams.  There is no CPU path:
+if the shared library cannot be loaded, or no sm_100 device is present, every
+compute entry raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'libhebb_sm100.so')
+
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+_PREC_NAMES = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'fp32x3': PREC_BF16X3, 'bf16': PREC_BF16}
+F_UPDATE, F_WNRM = 1, 2
+F_ONLY_PACK, F_ONLY_FWD, F_ONLY_DW = 0x100, 0x200, 0x400
+
+EXPORTS = [
+    'hebb_query', 'hebb_status_str', 'hebb_last_cuda_error', 'hebb_version', 'hebb_out_shape',
+    'hebb_workspace_bytes', 'hebb_wnorm', 'hebb_conv_swta_step', 'hebb_convT_swta_step',
+    'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
+]
+
+
+class HebbDesc(ctypes.Structure):
+    _fields_ = [('nd', ctypes.c_int32), ('B', ctypes.c_int32), ('Cin', ctypes.c_int32), ('Cout', ctypes.c_int32),
+                ('inp', ctypes.c_int32 * 3), ('k', ctypes.c_int32 * 3), ('stride', ctypes.c_int32 * 3),
+                ('pad_lo', ctypes.c_int32 * 3), ('pad_hi', ctypes.c_int32 * 3), ('transposed', ctypes.c_int32)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+_default_prec = _PREC_NAMES.get(os.environ.get('HEBB_PREC', 'bf16x3').lower(), PREC_BF16X3)
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f'{_LIB_PATH} not found: build it with `python build.py` (or __graft_entry__.build()). '
+                'The Hebbian layers have no CPU or PyTorch fallback.')
+        lib = ctypes.CDLL(_LIB_PATH)
+        vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+        lib.hebb_query.argtypes = [ctypes.POINTER(i32)] * 3
+        lib.hebb_status_str.restype = ctypes.c_char_p
+        lib.hebb_status_str.argtypes = [i32]
+        lib.hebb_version.restype = ctypes.c_char_p
+        lib.hebb_out_shape.argtypes = [ctypes.POINTER(HebbDesc), ctypes.POINTER(ctypes.c_int32 * 3)]
+        lib.hebb_workspace_bytes.argtypes = [ctypes.POINTER(HebbDesc), i32, ctypes.POINTER(ctypes.c_size_t)]
+        lib.hebb_wnorm.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, vp]
+        step = [ctypes.POINTER(HebbDesc), vp, vp, vp, f32, vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_uint, i32, vp]
+        lib.hebb_conv_swta_step.argtypes = step
+        lib.hebb_convT_swta_step.argtypes = step
+        lib.hebb_local_update_multi.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
+                                                ctypes.POINTER(f32), ctypes.POINTER(ctypes.c_int32), vp]
+        lib.hebb_debug_umma_probe.argtypes = [vp, i32, vp, i32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
+                                              ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                              i32, i32, i32, vp, vp]
+        lib.hebb_debug_launch_count.restype = ctypes.c_ulonglong
+        lib.hebb_uses_tensor_cores.argtypes = [ctypes.POINTER(HebbDesc), i32]
+        for name in EXPORTS:
+            getattr(lib, name)      # fail loudly if a declared symbol is missing
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = ''):
+    if status != 0:
+        lib = load()
+        msg = lib.hebb_status_str(status).decode()
+        extra = ''
+        if status == -5:
+            extra = f' (cudaError {lib.hebb_last_cuda_error()})'
+        raise RuntimeError(f'libhebb_sm100: {what}: {msg}{extra}')
+
+
+def parse_prec(p) -> int:
+    if p is None:
+        return _default_prec
+    if isinstance(p, str):
+        try:
+            return _PREC_NAMES[p.lower()]
+        except KeyError:
+            raise ValueError(f'unknown precision {p!r}; use one of {sorted(_PREC_NAMES)}')
+    return int(p)
+
+
+def prec_name(p: int) -> str:
+    return {PREC_FP32: 'fp32', PREC_BF16X3: 'bf16x3', PREC_BF16: 'bf16'}[int(p)]
+
+
+def set_default_precision(p):
+    """'fp32' (CUDA-core exact order), 'bf16x3' (tcgen05 3-pass split, default) or 'bf16'."""
+    global _default_prec
+    _default_prec = parse_prec(p)
+
+
+def get_default_precision() -> int:
+    return _default_prec
+
+
+def make_desc(nd: int, B: int, Cin: int, Cout: int, inp: Sequence[int], k: Sequence[int], stride: Sequence[int],
+              pad_lo: Sequence[int], pad_hi: Sequence[int], transposed: bool) -> HebbDesc:
+    def three(v, fill):
+        v = list(v)
+        return [fill] * (3 - len(v)) + v
+    d = HebbDesc()
+    d.nd, d.B, d.Cin, d.Cout = nd, B, Cin, Cout
+    d.inp[:] = three(inp, 1)
+    d.k[:] = three(k, 1)
+    d.stride[:] = three(stride, 1)
+    d.pad_lo[:] = three(pad_lo, 0)
+    d.pad_hi[:] = three(pad_hi, 0)
+    d.transposed = 1 if transposed else 0
+    return d
+
+
+def out_shape(desc: HebbDesc):
+    out = (ctypes.c_int32 * 3)()
+    check(load().hebb_out_shape(ctypes.byref(desc), ctypes.byref(out)), 'out_shape')
+    return list(out)[3 - desc.nd:]
+
+
+def workspace_bytes(desc: HebbDesc, prec: int) -> int:
+    n = ctypes.c_size_t(0)
+    check(load().hebb_workspace_bytes(ctypes.byref(desc), prec, ctypes.byref(n)), 'workspace_bytes')
+    return int(n.value)
+
+
+# One scratch buffer per device, shared by every layer (layers of a network run back to back on
+# one stream, so their scratch never overlaps in time).  Grown on demand, never shrunk.
+_ws = {}
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            # a stream may still be using the old buffer; let the caching allocator order it
+            buf.record_stream(torch.cuda.current_stream(device))
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def release_workspaces():
+    _ws.clear()
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor: the sm_100 Hebbian library has no CPU fallback')
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'{name} must be float32 (got {t.dtype})')
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def conv_step(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w, flags: int, prec: int):
+    """Launch hebb_conv_swta_step / hebb_convT_swta_step (by desc.transposed) on the current stream."""
+    lib = load()
+    _require_cuda(x, 'x'); _require_cuda(W, 'weight')
+    nbytes = workspace_bytes(desc, prec)
+    ws = workspace(x.device, nbytes)
+    fn = lib.hebb_convT_swta_step if desc.transposed else lib.hebb_conv_swta_step
+    st = fn(ctypes.byref(desc), x.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None,
+            float(kinv), y.data_ptr(), winner.data_ptr() if winner is not None else None,
+            delta_w.data_ptr() if delta_w is not None else None, ws.data_ptr(), ws.numel(),
+            int(flags), int(prec), _stream_ptr(x.device))
+    check(st, 'conv_swta_step')
+
+
+def wnorm(W: torch.Tensor, rows: int, row_stride: int, mid: int, mid_stride: int, inner: int,
+          want_inv: bool = False):
+    """normalize() over the raw storage addressing described in hebb_sm100.h."""
+    _require_cuda(W, 'weight')
+    out = torch.empty_strided(W.shape, W.stride(), dtype=W.dtype, device=W.device)
+    inv = torch.empty(rows, dtype=torch.float32, device=W.device) if want_inv else None
+    check(load().hebb_wnorm(W.data_ptr(), out.data_ptr(), inv.data_ptr() if inv is not None else None,
+                            rows, row_stride, mid, mid_stride, inner, _stream_ptr(W.device)), 'wnorm')
+    return (out, inv) if want_inv else out
+
+
+def local_update_multi(grads, dws, alphas, has_grad):
+    """grad_i = (1-a_i) grad_i - a_i dw_i  (or -a_i dw_i), dw_i = 0, for all i in ONE launch."""
+    n = len(dws)
+    if n == 0:
+        return
+    lib = load()
+    vp = ctypes.c_void_p
+    g = (vp * n)(*[t.data_ptr() for t in grads])
+    d = (vp * n)(*[t.data_ptr() for t in dws])
+    ne = (ctypes.c_int64 * n)(*[t.numel() for t in dws])
+    al = (ctypes.c_float * n)(*[float(a) for a in alphas])
+    hg = (ctypes.c_int32 * n)(*[1 if h else 0 for h in has_grad])
+    check(lib.hebb_local_update_multi(n, g, d, ne, al, hg, _stream_ptr(dws[0].device)), 'local_update_multi')
+
+
+def launch_count() -> int:
+    return int(load().hebb_debug_launch_count())
+
+
+def uses_tensor_cores(desc: HebbDesc, prec: int) -> bool:
+    return bool(load().hebb_uses_tensor_cores(ctypes.byref(desc), int(prec)))
+
+
+def query():
+    lib = load()
+    a, b, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    st = lib.hebb_query(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return st, a.value, b.value, c.value

@@ -1,0 +1,141 @@
+/*
+ * hebb_sm100.h — C ABI of libhebb_sm100.so: the B200 (sm_100a) implementation of the
+ * reference's Hebbian-convolution hot path (forward + soft-WTA plasticity update).
+ *
+ * The reference exposes NO FFI: its seam is the Python class (hebb/hebb.py, hebb/hebb3d.py).
+ * Each entry point below names the reference lines it replaces.  The Python drop-in
+ * (hebbian-bootstraping-semi-supervised-medical-imaging_b200/hebb/) binds these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory unless it says "host";
+ *  - tensors are fp32, contiguous NCHW / NCDHW unless a stride argument says otherwise;
+ *  - the library never allocates, frees or keeps device memory: scratch comes in through
+ *    (ws, ws_bytes) sized by hebb_workspace_bytes(); delta_w is read-modify-write (+=);
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*), never syncs;
+ *  - return value: 0 on success, a negative hebb_status otherwise; no C++ exception crosses;
+ *  - there is no CPU path: without an sm_100 device every compute call returns HEBB_EARCH.
+ */
+#ifndef HEBB_SM100_H_
+#define HEBB_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum hebb_status {
+  HEBB_OK = 0,
+  HEBB_EARCH = -1,   /* no CUDA device, or device is not sm_100 */
+  HEBB_ESHAPE = -2,  /* unsupported / inconsistent shape */
+  HEBB_EALIGN = -3,  /* pointer not aligned as required (16 B) */
+  HEBB_EWS = -4,     /* workspace missing or too small */
+  HEBB_ECUDA = -5,   /* a CUDA runtime call failed; see hebb_last_cuda_error() */
+  HEBB_EARG = -6,    /* null pointer / bad enum */
+  HEBB_EKERNEL = -7  /* a kernel reported an internal error (watchdog) */
+} hebb_status;
+
+/* Operand precision of the two contractions.  State it per run (BASELINE.json north_star).
+ *  FP32   : CUDA-core fp32 FMA implicit GEMM (exact-order fp32; parity anchor, any shape)
+ *  BF16X3 : tcgen05 kind::f16, every operand split hi+lo bf16, 3 MMAs per product
+ *           (hi*hi + hi*lo + lo*hi), fp32 accumulate in TMEM  -> meets the 1e-4 bar
+ *  BF16   : tcgen05 kind::f16, single-pass bf16 operands on the dW contraction, split
+ *           (3-pass) forward so winner indices stay exact            -> meets the 1e-2 bar */
+typedef enum hebb_prec { HEBB_PREC_FP32 = 0, HEBB_PREC_BF16X3 = 1, HEBB_PREC_BF16 = 2 } hebb_prec;
+
+/* Geometry of one Hebbian (transposed) convolution.  nd==2 uses the last two entries of
+ * every 3-array (index 0 is the depth axis and must be size 1 / kernel 1 / stride 1 / pad 0).
+ * pad_lo/pad_hi are the zero halo the reference's pad() really applies per axis
+ * (hebb/hebb.py:83-85, hebb/hebb3d.py:82-84 — note its tuple form pads W with padding[0]). */
+typedef struct HebbDesc {
+  int32_t nd;          /* 2 or 3 */
+  int32_t B, Cin, Cout;
+  int32_t in[3];       /* unpadded input extent  (D, H, W) */
+  int32_t k[3];        /* kernel extent          (kd, kh, kw) */
+  int32_t stride[3];
+  int32_t pad_lo[3];
+  int32_t pad_hi[3];
+  int32_t transposed;  /* 0: y = conv(x, W[Cout,Cin,k]);  1: y = convT(x, W[Cin,Cout,k]) */
+} HebbDesc;
+
+/* flags for hebb_conv_swta_step / hebb_convT_swta_step */
+#define HEBB_F_UPDATE 1u   /* also accumulate the plasticity update into delta_w */
+#define HEBB_F_WNRM   2u   /* divide each filter by its L2 norm (w_nrm=True) */
+/* Profiling aids (tensor-core path only): re-run ONE stage of the step on the scratch a
+ * preceding full call with the same arguments left in `ws`; outputs are rewritten. */
+#define HEBB_F_ONLY_PACK 0x100u   /* filter norms + bf16 packing of x and W */
+#define HEBB_F_ONLY_FWD  0x200u   /* forward shift-GEMM + soft-WTA epilogue */
+#define HEBB_F_ONLY_DW   0x400u   /* dW shift-GEMM + decay/accumulate (needs HEBB_F_UPDATE) */
+
+/* Device / build query.  Pointers may be NULL.  Returns HEBB_EARCH when no sm_100 device. */
+int hebb_query(int* sm_major, int* sm_minor, int* num_sms);
+const char* hebb_status_str(int status);
+/* cudaError_t of the last failing runtime call seen by this thread (0 if none). */
+int hebb_last_cuda_error(void);
+const char* hebb_version(void);
+
+/* Output extent (D,H,W) of the layer described by d. */
+int hebb_out_shape(const HebbDesc* d, int32_t out[3]);
+
+/* Scratch bytes needed by the *_step calls for this geometry and precision. */
+int hebb_workspace_bytes(const HebbDesc* d, int prec, size_t* bytes);
+
+/* a1  normalize()  hebb/hebb.py:10-13, hebb/hebb3d.py:9-12.
+ * Treats W as rows x (mid x inner): element (r,m,i) lives at r*row_stride + m*mid_stride + i.
+ * Wn[...] = W[...] / ||W_r||_2 (norm 0 -> divide by 1), same addressing.  inv_norm (nullable)
+ * receives 1/||W_r|| (1 for zero rows).  Conv weight [Cout,Cin,k..]: rows=Cout,
+ * row_stride=Cin*taps, mid=1, inner=Cin*taps.  Transposed view [Cin,Cout,k..] of a
+ * [Cout,Cin,k..] buffer (hebb.py:222-224): rows=Cin, row_stride=taps, mid=Cout,
+ * mid_stride=Cin*taps, inner=taps. */
+int hebb_wnorm(const float* W, float* Wn, float* inv_norm, int64_t rows, int64_t row_stride,
+               int64_t mid, int64_t mid_stride, int64_t inner, void* stream);
+
+/* a2+a3+a5 (+a4+a6+a7 with HEBB_F_UPDATE): one HebbianConv{2,3}d.forward in SWTA/patchwise
+ * mode — hebb/hebb.py:87-115, hebb/hebb3d.py:86-125.
+ *   y[B,Cout,out..]      = conv(zero_pad(x), W/||W||, bias, stride)          (overwritten)
+ *   winner[B,out..]      = argmax_c y (lowest index wins ties); nullable      (overwritten)
+ *   delta_w[Cout,Cin,k..] += sum_p r[c,p] X[p,:] - (sum_p r[c,p]) W[c,:],  r = softmax_c(kinv*y)
+ * W is the UN-normalised weight; bias is nullable. */
+int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const float* bias,
+                        float kinv, float* y, int32_t* winner, float* delta_w,
+                        void* ws, size_t ws_bytes, unsigned flags, int prec, void* stream);
+
+/* a9: one HebbianConvTranspose{2,3}d.forward in swta_t/patchwise mode —
+ * hebb/hebb.py:226-264, hebb/hebb3d.py:250-289.  W and delta_w are the CONTIGUOUS
+ * [Cout,Cin,k..] buffers underneath the reference's transposed (Cin,Cout,k..) view; the
+ * normalisation is per input channel (the view's leading dim).  Padding must be 0. */
+int hebb_convT_swta_step(const HebbDesc* d, const float* x, const float* W, const float* bias,
+                         float kinv, float* y, int32_t* winner, float* delta_w,
+                         void* ws, size_t ws_bytes, unsigned flags, int prec, void* stream);
+
+/* a8  local_update() for n layers in one launch — hebb/hebb.py:174-192.
+ * For i<n:  grad[i][j] = has_grad[i] ? (1-alpha[i])*grad[i][j] - alpha[i]*dw[i][j]
+ *                                    : -alpha[i]*dw[i][j];   dw[i][j] = 0.
+ * The four arrays are HOST arrays of length n; grad[i]/dw[i] are device pointers with the
+ * same (dense) memory layout, numel[i] elements each. */
+int hebb_local_update_multi(int n, float* const* grad, float* const* dw, const int64_t* numel,
+                            const float* alpha, const int32_t* has_grad, void* stream);
+
+/* ---- exported for tests and profiling ---- */
+
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
+unsigned long long hebb_debug_launch_count(void);
+
+/* 1 if (d, prec) runs on the tcgen05 kernels, 0 if on the CUDA-core kernels. */
+int hebb_uses_tensor_cores(const HebbDesc* d, int prec);
+
+/* One CTA: copy two raw operand images to shared memory, issue `ksteps` tcgen05.mma
+ * (kind::f16, bf16 in, fp32 out) with descriptors {hi | (start + i*step) >> 4}, and dump
+ * TMEM lanes 0..127 x n columns to d_out[128][n].  Pins the SWIZZLE_NONE descriptor
+ * semantics the shift-GEMM kernels rely on (tests/test_umma_probe.py). */
+int hebb_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
+                          uint64_t a_desc_hi, uint32_t a_start, uint32_t a_step,
+                          uint64_t b_desc_hi, uint32_t b_start, uint32_t b_step,
+                          uint32_t idesc, int ksteps, int m, int n, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEBB_SM100_H_ */

@@ -198,7 +198,62 @@ def main():
                                          for k, v in mk.default_hebb_params.items()}
     with open(os.path.join(HERE, 'makehebbian_golden.json'), 'w') as f:
         json.dump(dict(meta=meta, structures=structures), f, indent=1, sort_keys=True)
+    network_goldens(mk)
     print('wrote', len(out), 'arrays;', os.path.getsize(os.path.join(HERE, 'hebb_golden.npz')) // 1024, 'KiB')
+
+
+def _load_file(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def layer_digest(t, n=48):
+    t = t.detach().contiguous().reshape(-1).double()
+    idx = torch.linspace(0, t.numel() - 1, min(n, t.numel())).long()
+    return dict(sum=float(t.sum()), abssum=float(t.abs().sum()), norm=float(t.norm()),
+                idx=idx.tolist(), val=t[idx].tolist())
+
+
+def network_goldens(mk):
+    """Whole-network fixtures: the reference's unet (2-D) and UNet3D (3-D, init_features=4) after
+    makehebbian, one training-mode forward + local_update on a small seeded input, dropout off,
+    weights from workloads.deterministic_state_.  Also the state_dict key/shape lists that
+    tests/test_workloads.py compares the restated topologies with."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import workloads
+    with contextlib.redirect_stdout(io.StringIO()):
+        r2 = _load_file(os.path.join(REF, 'models/networks_2d/unet.py'), 'ref_unet2d')
+        r3 = _load_file(os.path.join(REF, 'models/networks_3d/unet3d.py'), 'ref_unet3d')
+        full2, full3 = r2.unet(3, 2), r3.unet3d(1, 2)
+    keys = {'unet2d': [[n, list(v.shape)] for n, v in full2.state_dict().items()],
+            'unet3d': [[n, list(v.shape)] for n, v in full3.state_dict().items()]}
+    with open(os.path.join(HERE, 'workload_state_keys.json'), 'w') as f:
+        json.dump(keys, f)
+
+    res = {}
+    hp = {'mode': 'swta_t', 'k': 50., 'w_nrm': True, 'alpha': 1.}
+    cases = [('unet2d', lambda: r2.unet(3, 2), workloads.EXCLUDE_2D, (2, 3, 32, 32)),
+             ('unet3d_f4', lambda: r3.UNet3D(1, 2, init_features=4), workloads.EXCLUDE_3D, (2, 1, 16, 16, 16))]
+    for name, ctor, excl, shape in cases:
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = ctor()
+            mk.makehebbian(net, exclude=excl, hebb_params=hp)
+        workloads.deterministic_state_(net)
+        workloads.disable_dropout_(net)
+        net.train()
+        x = torch.randn(*shape, generator=torch.Generator().manual_seed(77))
+        out = net(x)
+        layers = {}
+        for n, m in net.named_modules():
+            if hasattr(m, 'local_update'):
+                layers[n] = dict(kind=type(m).__name__, delta_w=layer_digest(m.delta_w))
+                m.local_update()
+                layers[n]['grad'] = layer_digest(m.weight.grad)
+        res[name] = dict(shape=list(shape), out=layer_digest(out, 256), layers=layers)
+    with open(os.path.join(HERE, 'network_golden.json'), 'w') as f:
+        json.dump(res, f)
 
 
 if __name__ == '__main__':

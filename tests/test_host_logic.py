@@ -1,0 +1,179 @@
+"""CPU-side tests: the C-ABI library loads and exports what include/hebb_sm100.h declares,
+makehebbian() reproduces the reference's module surgery (fixtures from the live reference),
+the restated workload networks match the reference's, and the drop-in refuses CPU tensors."""
+import ctypes
+import io
+import contextlib
+import json
+import os
+import re
+
+import pytest
+import torch
+import torch.nn as nn
+
+import hebb
+from hebb import _native
+from hebb.makehebbian import (makehebbian, UnsqueezeLast, FlattenLast, adjust_hebbian_params,
+                              default_hebb_params, init_weights)
+import workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'hebb_sm100.h')).read()
+    declared = set(re.findall(r'\b(hebb_[a-z_A-Z0-9]+)\s*\(', header))
+    declared -= {'hebb_status', 'hebb_prec'}
+    assert {'hebb_conv_swta_step', 'hebb_convT_swta_step', 'hebb_local_update_multi', 'hebb_wnorm'} <= declared
+    lib = ctypes.CDLL(_native.lib_path())
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in hebb_sm100.h but not exported'
+    assert set(_native.EXPORTS) <= declared
+    assert b'sm_100' in _native.load().hebb_version()
+    assert _native.load().hebb_status_str(-1).decode().startswith('no sm_100')
+
+
+def test_geometry_queries_need_no_gpu():
+    d = _native.make_desc(2, 8, 3, 64, (128, 128), (3, 3), (1, 1), (1, 1), (1, 1), False)
+    assert _native.out_shape(d) == [128, 128]
+    assert _native.workspace_bytes(d, _native.PREC_FP32) > 0
+    assert _native.workspace_bytes(d, _native.PREC_BF16X3) > 0
+    d3 = _native.make_desc(3, 2, 8, 4, (3, 4, 5), (2, 2, 2), (2, 2, 2), (0, 0, 0), (0, 0, 0), True)
+    assert _native.out_shape(d3) == [6, 8, 10]
+    bad = _native.make_desc(2, 1, 3, 8, (2, 2), (3, 3), (1, 1), (0, 0), (0, 0), False)
+    with pytest.raises(RuntimeError):
+        _native.out_shape(bad)
+
+
+def test_no_cpu_fallback():
+    layer = hebb.HebbianConv2d(3, 8, 3, padding=1, alpha=1.)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        layer(torch.randn(1, 3, 8, 8))
+    with pytest.raises(RuntimeError):
+        layer.local_update()
+
+
+class Net(nn.Module):   # the reference test's toy net (tests/test_makehebbian.py:5-39)
+    def __init__(self):
+        super().__init__()
+        self.down = nn.Sequential(nn.Conv2d(3, 16, 3, stride=2), nn.BatchNorm2d(16), nn.ReLU())
+        self.up = nn.Sequential(nn.ConvTranspose2d(16, 20, 3, stride=2), nn.BatchNorm2d(20), nn.ReLU())
+        self.clf = nn.Sequential(FlattenLast(2), nn.Linear(20, 16), nn.BatchNorm1d(16), nn.ReLU(),
+                                 nn.Dropout(0.5), nn.Linear(16, 10))
+
+    def forward(self, x):
+        return self.clf(self.up(self.down(x)))
+
+
+def describe(net):
+    mods = {n: type(m).__name__ for n, m in net.named_modules()}
+    params = {n: [list(p.shape), bool(p.requires_grad), list(p.stride())] for n, p in net.named_parameters()}
+    bufs = {n: list(b.shape) for n, b in net.named_buffers()}
+    hp = {n: dict(mode=m.mode, k=m.k, alpha=m.alpha, w_nrm=m.w_nrm, patchwise=m.patchwise,
+                  kernel_size=list(m.kernel_size), stride=list(m.stride),
+                  padding=(m.padding if isinstance(m.padding, int) else list(m.padding)))
+          for n, m in net.named_modules() if hasattr(m, 'local_update')}
+    return dict(modules=mods, params=params, buffers=bufs, hebb=hp, state_keys=list(net.state_dict().keys()))
+
+
+@pytest.mark.parametrize('case,kwargs', [
+    ('toy_default_params', dict(exclude=['clf.5'], hebb_params={})),
+    ('toy_swta_t', dict(exclude=['clf.5'], hebb_params={'mode': 'swta_t', 'k': 50., 'w_nrm': True, 'alpha': 1.})),
+    ('toy_none', dict(exclude=None, hebb_params=None)),
+])
+def test_makehebbian_matches_reference_structure(golden_meta, case, kwargs):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        net = makehebbian(Net(), **kwargs)
+    got = json.loads(json.dumps(describe(net)))
+    want = golden_meta['structures'][case]
+    for key in ('modules', 'params', 'buffers', 'hebb', 'state_keys'):
+        assert got[key] == want[key], key
+    assert buf.getvalue().startswith('Layers excluded from conversion to Hebbian:')
+
+
+def test_makehebbian_helpers(golden_meta):
+    want = golden_meta['structures']['adjust']
+    assert adjust_hebbian_params({'mode': 'swta_t', 'k': 3}) == want['swta_t']
+    assert adjust_hebbian_params({'mode': 'hpca_t'}) == want['hpca_t']
+    assert adjust_hebbian_params({'mode': 'swta'}) == want['swta']
+    assert adjust_hebbian_params({'k': 2}) == want['none']
+    dflt = {k: (v if not isinstance(v, nn.Module) else type(v).__name__) for k, v in default_hebb_params.items()}
+    assert dflt == golden_meta['structures']['default_hebb_params']
+    with pytest.raises(NotImplementedError):
+        init_weights(nn.Conv2d(1, 1, 1), 'bogus')
+    with pytest.raises(RuntimeError, match='Dilation'):
+        makehebbian(nn.Sequential(nn.Conv2d(1, 1, 3, dilation=2)))
+    with pytest.raises(RuntimeError, match='Grouped'):
+        makehebbian(nn.Sequential(nn.Conv3d(2, 2, 3, groups=2)))
+    x = torch.randn(4, 5)
+    assert UnsqueezeLast(2)(x).shape == (4, 5, 1, 1)
+    assert FlattenLast(2)(torch.randn(4, 5, 2, 3)).shape == (4, 30)
+
+
+def test_layer_api_surface():
+    l2 = hebb.HebbianConv2d(3, 8, 3, stride=1, padding=1, bias=False, w_nrm=True, mode='swta', k=5, alpha=1.)
+    assert list(l2.state_dict().keys()) == ['weight', 'bias', 'delta_w']
+    assert l2.weight.shape == (8, 3, 3, 3) and l2.delta_w.shape == (8, 3, 3, 3)
+    assert l2.bias.requires_grad is False and l2.kernel_size == (3, 3) and l2.stride == (1, 1)
+    for attr in ('mode', 'in_channels', 'out_channels', 'padding', 'w_nrm', 'act', 'k', 'patchwise',
+                 'contrast', 'uniformity', 'alpha'):
+        assert hasattr(l2, attr)
+    assert hebb.HebbianConv2d.MODE_SWTA == 'swta' and hebb.HebbianConvTranspose3d.MODE_SWTA_T == 'swta_t'
+    t3 = hebb.HebbianConvTranspose3d(4, 6, 2, stride=2)
+    assert t3.mode == 'swta_t' and t3.weight.shape == (4, 6, 2, 2, 2)
+    assert t3.weight.stride() == (8, 32, 4, 2, 1) and not t3.weight.is_contiguous()
+    l2.mode = 'bogus'
+    l2.train()
+    with pytest.raises(NotImplementedError, match='Learning mode bogus unavailable'):
+        l2._check_mode()
+    # padding quirk of hebb.py:84: tuple (p0, p1) pads W with p0 and H with p1
+    q = hebb.HebbianConv2d(1, 1, 3, padding=(2, 1))
+    assert q._pad_lo_hi() == ([1, 2], [1, 2])
+    assert q.pad(torch.zeros(1, 1, 4, 4)).shape == (1, 1, 6, 8)
+    # normalize() stays a general utility on CPU tensors
+    w = torch.tensor([[3., 4.], [0., 0.]])
+    assert torch.allclose(hebb.normalize(w, dim=1), torch.tensor([[0.6, 0.8], [0., 0.]]))
+
+
+def test_state_dict_round_trip_with_reference_layout():
+    """Reference checkpoints store the transposed layers' (Cin, Cout, ...) view contiguously."""
+    net = makehebbian(Net(), exclude=['clf.5'], hebb_params={'mode': 'swta_t', 'k': 5., 'alpha': 1.})
+    sd = {k: torch.randn_like(v) if v.is_floating_point() else v.clone() for k, v in net.state_dict().items()}
+    net.load_state_dict(sd)
+    assert torch.equal(net.up[0].weight.detach(), sd['up.0.weight'])
+    assert net.up[0].weight.stride() == (9, 144, 3, 1)       # still the transposed view of (Cout,Cin,..)
+
+
+def test_workload_topologies_match_reference():
+    keys = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'workload_state_keys.json')))
+    n2 = workloads.unet2d(3, 2)
+    n3 = workloads.unet3d(1, 2, init_features=8)
+    assert [[n, list(v.shape)] for n, v in n2.state_dict().items()] == keys['unet2d']
+    got3 = [n for n, _ in n3.state_dict().items()]
+    assert got3 == [n for n, _ in keys['unet3d']]
+    with contextlib.redirect_stdout(io.StringIO()):
+        makehebbian(n2, exclude=workloads.EXCLUDE_2D, hebb_params={'mode': 'swta_t', 'k': 50., 'alpha': 1.})
+        makehebbian(n3, exclude=workloads.EXCLUDE_3D, hebb_params={'mode': 'swta_t', 'k': 50., 'alpha': 1.})
+    h2 = [m for m in n2.modules() if hasattr(m, 'local_update')]
+    h3 = [m for m in n3.modules() if hasattr(m, 'local_update')]
+    assert len(h2) == 22 and all(type(m).__name__ == 'HebbianConv2d' and m.mode == 'swta' for m in h2)
+    assert len(h3) == 22 and sum(type(m).__name__ == 'HebbianConvTranspose3d' for m in h3) == 4
+    assert all(p.requires_grad for p in n2.out_conv.parameters())
+    assert not any(p.requires_grad for n, p in n2.named_parameters() if 'out_conv' not in n and p.dim() == 1)
+
+
+def test_flatten_delta_w_keeps_shapes_and_aliases():
+    from hebb.step import flatten_delta_w, hebbian_layers
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = makehebbian(Net(), exclude=['clf.5'], hebb_params={'mode': 'swta_t', 'k': 5., 'alpha': 1.})
+    before = {n: (tuple(b.shape), b.stride()) for n, b in net.named_buffers() if n.endswith('delta_w')}
+    keys = list(net.state_dict().keys())
+    flat = flatten_delta_w(net)
+    after = {n: (tuple(b.shape), b.stride()) for n, b in net.named_buffers() if n.endswith('delta_w')}
+    assert before == after and keys == list(net.state_dict().keys())
+    flat.fill_(2.0)
+    assert all(float(m.delta_w.min()) == 2.0 for m in hebbian_layers(net))
+    net.up[0].delta_w.zero_()
+    assert float(flat.sum()) < 2.0 * flat.numel()

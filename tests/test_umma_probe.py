@@ -1,0 +1,87 @@
+"""Pins the shared-memory descriptor semantics the tensor-core kernels rely on: SWIZZLE_NONE
+K-major and MN-major operands whose start address is shifted by whole 16-byte position slots."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from hebb import _native
+
+pytestmark = pytest.mark.gpu
+
+
+def desc_hi(lbo, sbo):
+    return ((lbo >> 4) & 0x3FFF) << 16 | ((sbo >> 4) & 0x3FFF) << 32 | (1 << 46)
+
+
+def idesc(m, n, a_mn, b_mn):
+    return (1 << 4) | (1 << 7) | (1 << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((m >> 4) << 24)
+
+
+def bf16_round(a):
+    t = torch.from_numpy(a.astype(np.float32)).to(torch.bfloat16)
+    return t
+
+
+def to_u16(t):
+    return t.view(torch.int16).numpy().view(np.uint16)
+
+
+def run_probe(a_img, b_img, a_hi, a_start, a_step, b_hi, b_start, b_step, idc, ksteps, m, n):
+    lib = _native.load()
+    a = torch.from_numpy(a_img.view(np.int16).copy()).cuda()
+    b = torch.from_numpy(b_img.view(np.int16).copy()).cuda()
+    out = torch.zeros(128, n, dtype=torch.float32, device='cuda')
+    st = lib.hebb_debug_umma_probe(a.data_ptr(), a.numel() * 2, b.data_ptr(), b.numel() * 2,
+                                   ctypes.c_uint64(a_hi), a_start, a_step, ctypes.c_uint64(b_hi), b_start, b_step,
+                                   idc, ksteps, m, n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _native.check(st, 'probe')
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize('shift', [0, 1, 3, 8, 13])
+def test_k_major_shifted_rows(shift):
+    """Forward-kernel operand form: A[position, channel], rows 16 B apart, tap = start offset."""
+    rng = np.random.default_rng(shift)
+    M, N, K, rows = 128, 32, 32, 128 + 16
+    A = bf16_round(rng.standard_normal((rows, K)))
+    B = bf16_round(rng.standard_normal((N, K)))
+    a_img = np.zeros((K // 8, rows, 8), np.uint16)      # [chunk][row][8]
+    b_img = np.zeros((K // 8, N, 8), np.uint16)
+    Au, Bu = to_u16(A), to_u16(B)
+    for c in range(K // 8):
+        a_img[c] = Au[:, c * 8:(c + 1) * 8]
+        b_img[c] = Bu[:, c * 8:(c + 1) * 8]
+    lbo_a, lbo_b = rows * 16, N * 16
+    d = run_probe(a_img.reshape(-1), b_img.reshape(-1), desc_hi(lbo_a, 128), shift * 16, 2 * lbo_a,
+                  desc_hi(lbo_b, 128), 0, 2 * lbo_b, idesc(M, N, 0, 0), K // 16, M, N)
+    want = A.float().numpy()[shift:shift + M].astype(np.float64) @ B.float().numpy().astype(np.float64).T
+    assert np.abs(d - want).max() < 1e-3 * np.abs(want).max()
+
+
+@pytest.mark.parametrize('m', [64, 128])
+@pytest.mark.parametrize('shift', [0, 1, 5, 8])
+def test_mn_major_shifted_positions(m, shift):
+    """dW-kernel operand form: A[channel, position] and B[channel, position], positions 16 B apart."""
+    rng = np.random.default_rng(100 + shift + m)
+    N, K, pos = 48, 64, 64 + 16
+    A = bf16_round(rng.standard_normal((m, pos)))        # [ci][position]
+    B = bf16_round(rng.standard_normal((N, K)))          # [co][position]
+    Au, Bu = to_u16(A), to_u16(B)
+    a_img = np.zeros((m // 8, pos, 8), np.uint16)        # [chunk][position][8 channels]
+    b_img = np.zeros((N // 8, K, 8), np.uint16)
+    for c in range(m // 8):
+        a_img[c] = Au[c * 8:(c + 1) * 8, :].T
+    for c in range(N // 8):
+        b_img[c] = Bu[c * 8:(c + 1) * 8, :].T
+    d = run_probe(a_img.reshape(-1), b_img.reshape(-1), desc_hi(128, pos * 16), shift * 16, 256,
+                  desc_hi(128, K * 16), 0, 256, idesc(m, N, 1, 1), K // 16, m, N)
+    want = A.float().numpy()[:, shift:shift + K].astype(np.float64) @ B.float().numpy().astype(np.float64).T
+    if m == 128:
+        got = d
+    else:                                               # M=64: row r lives in lane (r%16) + 32*(r/16)
+        lanes = [(r % 16) + 32 * (r // 16) for r in range(64)]
+        got = d[lanes]
+    assert np.abs(got - want).max() < 1e-3 * np.abs(want).max()
