@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark of the Hebbian pretraining step (BASELINE.json metric) — see DESIGN.md §Measurement.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU (weak scaling)
+
+A "step" is one Hebbian pretraining step of the reference loop (pretrain_hebbian_unsup_2d.py:181-196):
+zero_grad -> forward through the makehebbian()-converted UNet (22 Hebbian layers: conv forward +
+soft-WTA update) -> Dice loss + backward on the excluded head -> local_update -> optimizer.step().
+Default workload = BASELINE.json configs[1]: 2-D UNet, synthetic GlaS-shaped 64 x 3 x 256 x 256 per GPU.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'hebbian-bootstraping-semi-supervised-medical-imaging_b200')
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+import workloads  # noqa: E402
+
+HEBB_PARAMS = {'mode': 'swta_t', 'k': 50., 'w_nrm': True, 'alpha': 1.}   # reproduce_*_2d.sh:18-27 (K=50)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c4'])
+    ap.add_argument('--prec', default=os.environ.get('HEBB_PREC', 'bf16x3'), choices=['fp32', 'bf16x3', 'bf16'])
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (0 = the workload default)')
+    ap.add_argument('--cpu-sample-batch', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-layer-profile', action='store_true')
+    ap.add_argument('--layers-out', default='', help='write the per-layer stage timings to this JSON file')
+    return ap.parse_args()
+
+
+WORKLOADS = {
+    # name: (description, default per-GPU batch, cpu sample batch)
+    'c1': ('single HebbianConv2d 3->64 k3 soft-WTA, 8x3x128x128', 8, 8),
+    'c2': ('2D UNet Hebbian pretraining, synthetic GlaS 256x256 RGB', 64, 4),
+    'c4': ('3D UNet Hebbian pretraining, synthetic LA 96x96x80', 8, 1),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=float(d['hbm_gbs']), tf=float(d['bf16_tflops']), tf_sustained=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])),
+                    source='measured')
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, source='fallback')
+
+
+# ------------------------------------------------------------------------------------------
+def build_model(workload, impl_ours, device):
+    """Returns (model, make_batch(batch, seed, device), criterion)."""
+    if workload == 'c1':
+        if impl_ours:
+            import hebb
+            torch.manual_seed(0)
+            layer = hebb.HebbianConv2d(3, 64, 3, stride=1, padding=1, bias=False, w_nrm=True, mode='swta', k=3.,
+                                       patchwise=True, alpha=1.)
+        else:
+            from oracle import hebb_oracle as O
+            torch.manual_seed(0)
+            layer = O.OracleHebbConv(2, 3, 64, 3, stride=1, padding=1, bias=False, w_nrm=True, k=3., alpha=1.)
+
+        def batch(b, seed, dev):
+            g = torch.Generator().manual_seed(seed)
+            return torch.randn(b, 3, 128, 128, generator=g).to(dev), None
+        return layer.to(device).train(), batch, None
+    if workload == 'c2':
+        net, excl = workloads.unet2d(3, 2), workloads.EXCLUDE_2D
+
+        def batch(b, seed, dev):
+            return workloads.glas_batch(b, 256, seed=seed, device=dev)
+    else:
+        net, excl = workloads.unet3d(1, 2), workloads.EXCLUDE_3D
+
+        def batch(b, seed, dev):
+            return workloads.la_batch(b, (96, 96, 80), seed=seed, device=dev)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if impl_ours:
+            from hebb.makehebbian import makehebbian
+            makehebbian(net, exclude=excl, hebb_params=dict(HEBB_PARAMS))
+        else:
+            from oracle import hebb_oracle as O
+            O.oracle_makehebbian(net, exclude=excl, k=HEBB_PARAMS['k'], alpha=HEBB_PARAMS['alpha'])
+    workloads.init_weights_like_reference(net)            # init_weights_unet(model,'kaiming') after surgery
+    return net.to(device).train(), batch, workloads.dice_loss
+
+
+def reference_step(model, opt, crit, x, m):
+    """The reference loop body, verbatim in structure (pretrain_hebbian_unsup_2d.py:181-196)."""
+    opt.zero_grad()
+    out = model(x)
+    loss = None
+    if crit is not None:
+        loss = crit(out, m)
+        loss.backward()
+    for mod in model.modules():
+        if hasattr(mod, 'local_update'):
+            mod.local_update()
+    opt.step()
+    return loss
+
+
+def time_cpu_port(workload, sample_batch, steps, warmup):
+    """The oracle (a CPU port of the reference algorithm) on the host cores: samples/s."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, make_batch, crit = build_model(workload, False, 'cpu')
+    lr = 1e-6 if workload != 'c4' else 1e-5
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    x, m = make_batch(sample_batch, 0, 'cpu')
+    for _ in range(warmup):
+        reference_step(model, opt, crit, x, m)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        reference_step(model, opt, crit, x, m)
+    dt = time.perf_counter() - t0
+    return dict(value=sample_batch * steps / dt, ms_per_step=dt / steps * 1e3, cores=cores,
+                sample=f'{steps} step(s) of batch {sample_batch} (same shapes as the GPU workload), {warmup} warm-up')
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith('nvmlClocksThrottleReason') or n.startswith('nvmlClocksEventReason'):
+                v = getattr(nv, n)
+                if isinstance(v, int) and v:
+                    names[v] = n.replace('nvmlClocksThrottleReason', '').replace('nvmlClocksEventReason', '')
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit and bit & (bit - 1) == 0:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._th = threading.Thread(target=self._run, daemon=True)
+            self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._th is not None:
+            self._th.join(2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        bad = {'HwSlowdown', 'HwThermalSlowdown', 'SwThermalSlowdown'}
+        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(r for r in self.reasons if r not in ('None', 'GpuIdle', 'All')),
+                    rejected=bool(bad & self.reasons))
+
+
+# ------------------------------------------------------------------------------------------
+def profile_layers(model, x, flush):
+    """Per-layer, per-stage CUDA-event timings of the tensor-core path (pack / forward / dW), taken in
+    one extra forward pass by re-running each stage alone (HEBB_F_ONLY_*) on the layer's real input."""
+    from hebb import _native
+    rows = []
+
+    def hook(mod, inp, out):
+        xin = inp[0].detach().contiguous()
+        desc = mod._desc(xin.shape, True)
+        prec = _native.parse_prec(mod.prec)
+        tc = (not mod._transposed) and _native.uses_tensor_cores(desc, prec)
+        g = dict(kind=type(mod).__name__, Cin=mod.in_channels, Cout=mod.out_channels, k=list(mod.kernel_size),
+                 x=list(xin.shape), y=list(out.shape), tensor_cores=bool(tc))
+        P = out.numel() // mod.out_channels
+        K = mod.in_channels * int(torch.tensor(mod.kernel_size).prod())
+        if mod._transposed:
+            P = xin.numel() // mod.in_channels
+            K = mod.in_channels
+            g['flops_one_contraction'] = 2.0 * P * mod.out_channels * K * int(torch.tensor(mod.kernel_size).prod())
+        else:
+            g['flops_one_contraction'] = 2.0 * P * mod.out_channels * K
+        g['bytes_min'] = 4.0 * (xin.numel() + out.numel()) + 12.0 * mod.weight.numel()
+        w = mod._raw(mod.weight.detach())
+        scratch_dw = torch.zeros_like(w)
+        yb = torch.empty_like(out)
+        base = _native.F_WNRM | _native.F_UPDATE
+        stages = [('full', 0)] + ([('pack', _native.F_ONLY_PACK), ('fwd', _native.F_ONLY_FWD), ('dw', _native.F_ONLY_DW)] if tc else [])
+        for name, fl in stages:
+            best = None
+            for rep in range(3):
+                flush()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _native.conv_step(desc, xin, w, mod.bias.detach(), float(mod.k), yb, None, scratch_dw, base | fl, prec)
+                e1.record()
+                e1.synchronize()
+                t = e0.elapsed_time(e1)
+                best = t if best is None else min(best, t)
+            g[name + '_ms'] = best
+        rows.append(g)
+
+    hs = [m.register_forward_hook(hook) for m in model.modules() if hasattr(m, 'local_update')]
+    was = model.training
+    model.eval()              # the hook drives the update stages itself; keep delta_w untouched
+    with torch.no_grad():
+        model(x)
+    model.train(was)
+    for h in hs:
+        h.remove()
+    return rows
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from hebb import _native
+    from hebb.step import HebbianStepper
+    import hebb
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    hebb.set_precision(args.prec)
+    desc, dflt_b, cpu_b = WORKLOADS[args.workload]
+    B = args.batch or dflt_b
+    cpu_b = args.cpu_sample_batch or cpu_b
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = time_cpu_port(args.workload, cpu_b, 2 if args.workload != 'c4' else 1, 1 if args.workload != 'c4' else 0)
+
+    torch.manual_seed(1234)
+    model, make_batch, crit = build_model(args.workload, True, dev)
+    lr = 1e-6 if args.workload != 'c4' else 1e-5
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    stepper = HebbianStepper(model, opt, crit)
+    x_host, m_host = make_batch(B, 100 + rank, 'cpu')
+    x_pin = x_host.pin_memory()
+    m_pin = m_host.pin_memory() if m_host is not None else None
+    x = x_pin.to(dev)
+    m = m_pin.to(dev) if m_pin is not None else None
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def flush():
+        flush_buf.fill_(1)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        stepper.step(x, m)
+    sync_all()
+
+    # ---- value: inputs resident in HBM ----
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n0 = _native.launch_count()
+    with ClockSampler(local) as clk:
+        sync_all()
+        t_wall0 = time.perf_counter()
+        for e0, e1 in evs:
+            flush()
+            e0.record()
+            stepper.step(x, m)
+            e1.record()
+        sync_all()
+        t_wall = time.perf_counter() - t_wall0
+    launches = _native.launch_count() - n0
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = B * world * args.steps / (dev_ms / 1e3)
+
+    # ---- e2e: host (pinned) inputs in, loss out, every step ----
+    sync_all()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        x.copy_(x_pin, non_blocking=True)
+        if m is not None:
+            m.copy_(m_pin, non_blocking=True)
+        out, loss = stepper.step(x, m)
+        last = float(loss.item()) if loss is not None else float(out.flatten()[0].item())
+    s1.record()
+    sync_all()
+    t = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = B * world * args.steps / (e2e_ms / 1e3)
+    h2d = x_pin.numel() * x_pin.element_size() + (m_pin.numel() * m_pin.element_size() if m_pin is not None else 0)
+
+    # ---- roofline of the dominant kernel class (per-layer stage timings) ----
+    roof, rows = None, []
+    pk = peaks()
+    if rank == 0 and not args.no_layer_profile:
+        if args.workload == 'c1':
+            class _W(torch.nn.Module):
+                def __init__(s, l):
+                    super().__init__(); s.l = l
+
+                def forward(s, z):
+                    return s.l(z)
+            rows = profile_layers(_W(model), x, flush)
+        else:
+            rows = profile_layers(model, x, flush)
+        tc_rows = [r for r in rows if r['tensor_cores']]
+        tot = {s: sum(r[s + '_ms'] for r in tc_rows) for s in ('pack', 'fwd', 'dw')} if tc_rows else {}
+        if tot:
+            dom = max(tot, key=tot.get)
+            fl = sum(r['flops_one_contraction'] for r in tc_rows)
+            if dom in ('fwd', 'dw'):
+                ach = fl / (tot[dom] / 1e3) / 1e12
+                roof = dict(bound='tensor', kernel={'fwd': 'fwd_swta_kernel', 'dw': 'dw_swta_kernel'}[dom], achieved=ach,
+                            peak=pk['tf'], unit='TFLOP/s', frac=ach / pk['tf'], traffic=None,
+                            peak_source=pk['source'] + ' bf16 burst', launches_per_step=len(tc_rows),
+                            note=f'algorithmic 2*P*Cout*K flops of the {len(tc_rows)} tensor-core layers / summed CUDA-event time of that '
+                                 f'stage ({args.prec}: {"3 MMAs per product" if (args.prec == "bf16x3" or dom == "fwd") else "1 MMA per product"})',
+                            stage_ms=tot)
+            else:
+                by = sum(4.0 * torch.tensor(r['x']).prod().item() * 1.5 for r in tc_rows)
+                ach = by / (tot[dom] / 1e3) / 1e9
+                roof = dict(bound='hbm', kernel='pack_x_kernel', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'],
+                            traffic=None, peak_source=pk['source'], stage_ms=tot)
+        if args.layers_out:
+            with open(args.layers_out, 'w') as f:
+                json.dump(dict(workload=args.workload, prec=args.prec, batch=B, layers=rows), f, indent=1)
+
+    if rank == 0:
+        line = {
+            'metric': 'hebbian_pretrain_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16x3': 'bf16x3 (fp32-equivalent split)', 'bf16': 'bf16'}[args.prec],
+            'data': 'synthetic',
+            'config': {'workload': f'{args.workload}: {desc}', 'per_gpu_batch': B, 'global_batch': B * world,
+                       'hebb_params': HEBB_PARAMS if args.workload != 'c1' else {'mode': 'swta', 'k': 3.0, 'alpha': 1.0},
+                       'optimizer': f'adam lr={lr}', 'precision_mode': args.prec, 'l2': 'flushed between timed steps (256 MB fill)',
+                       'parallelism': f'dp{world} (batch shards, one all-reduce of delta_w per step)'},
+            'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                    'ms_per_step': e2e_ms / args.steps, 'last_loss': last},
+            'gpu_launches': int(launches),
+            'clocks': clk.summary(),
+            'wall_s_timed_region': t_wall,
+            'roofline': roof,
+            'cpu_baseline': (dict(value=cpu['value'], unit='samples/s', cores=cpu['cores'], kind='port', sample=cpu['sample'],
+                                  ms_per_step=cpu['ms_per_step']) if cpu else None),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's algorithm on the box's host cores (oracle port: /root/reference is not on the box)."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    desc, dflt_b, cpu_b = WORKLOADS[args.workload]
+    cpu_b = args.cpu_sample_batch or cpu_b
+    r = time_cpu_port(args.workload, cpu_b, args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': 'hebbian_pretrain_samples_per_sec', 'value': r['value'], 'unit': 'samples/s',
+        'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{args.workload}: {desc}', 'per_step_sample_batch': cpu_b,
+                   'note': 'CPU PyTorch restatement of the reference path (oracle/), all host threads'},
+        'cpu_baseline': {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
+        'e2e': {'value': r['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

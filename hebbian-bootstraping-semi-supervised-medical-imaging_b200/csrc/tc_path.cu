@@ -114,6 +114,7 @@ struct FwdParams {
   uint4* rp[2];
   float* y; int32_t* winner; const float* inv; const float* bias; float* rsum; int* err;
   int Cout, CC, NSLAB, taps, nseg, HL;
+  int RHL;                     // 1: r is consumed as single bf16 (hi only), 2: hi + lo
   long long PA, PR, PTOT;      // positions per chunk plane in Xp / Rp; real positions B*Qimg
   int MB, TILE_M, ntiles, SEGLEN;
   int XST, WST, NACC;
@@ -327,7 +328,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                   const float f = fmaf(__uint_as_float(v[c]), s_inv[c0 + c], s_bias[c0 + c]);
                   const float r = __expf(fmaf(f, p.kinv, -mx)) * rinv;
                   split_bf16(r, h2[k2], l2[k2]);
-                  rr[c] = __bfloat162float(h2[k2]) + (p.HL == 2 ? __bfloat162float(l2[k2]) : 0.f);
+                  rr[c] = __bfloat162float(h2[k2]) + (p.RHL == 2 ? __bfloat162float(l2[k2]) : 0.f);
                 }
                 oh4[i] = pack_bf16x2(h2[0], h2[1]);
                 ol4[i] = pack_bf16x2(l2[0], l2[1]);
@@ -335,7 +336,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               const long long ridx = (long long)(c0 / 8 + g8) * p.PR + pp;
               if (pp < p.PR) {
                 p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
-                if (p.HL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+                if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
               }
             }
             const float cs = lane_col_sum<CH>(rr, lane);
@@ -720,7 +721,7 @@ int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias
   FwdParams f;
   f.xp[0] = xp0; f.xp[1] = xp1; f.wp = wp; f.rp[0] = rp0; f.rp[1] = rp1;
   f.y = y; f.winner = winner; f.inv = (flags & HEBB_F_WNRM) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = err;
-  f.Cout = g.Cout; f.CC = P.CC; f.NSLAB = P.NSLAB; f.taps = g.taps; f.nseg = P.f_nseg; f.HL = P.f_HL;
+  f.Cout = g.Cout; f.CC = P.CC; f.NSLAB = P.NSLAB; f.taps = g.taps; f.nseg = P.f_nseg; f.HL = P.f_HL; f.RHL = P.d_HL;
   f.PA = P.PA; f.PR = P.PR; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
   f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC;
   f.WP = P.WP; f.plane = P.plane; f.Qimg = P.Qimg; f.oD = g.oD; f.oH = g.oH; f.oW = g.oW;

@@ -17,15 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NET = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'network_golden.json')))
 
 
-def digest_err(t, dg):
-    t = t.detach().contiguous().reshape(-1).double()
-    idx = torch.tensor(dg['idx'])
-    val = torch.tensor(dg['val'], dtype=torch.float64)
-    scale = max(dg['norm'] / max(t.numel(), 1) ** 0.5, 1e-30)
-    e_samples = float((t[idx] - val).abs().max() / scale)
-    e_norm = abs(float(t.norm()) - dg['norm']) / max(dg['norm'], 1e-30)
-    e_sum = abs(float(t.sum()) - dg['sum']) / max(dg['abssum'], 1e-30)
-    return max(e_samples, e_norm, e_sum)
+from helpers import digest_err  # noqa: E402
 
 
 def build_oracle_net(name):
