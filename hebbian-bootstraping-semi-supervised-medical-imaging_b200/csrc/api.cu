@@ -106,7 +106,7 @@ int hebb_out_shape(const HebbDesc* d, int32_t out[3]) {
 }
 
 static bool use_tc(const Geo& g, int prec) {
-  return prec != HEBB_PREC_FP32 && !g.transposed && tc_supported(g);
+  return prec != HEBB_PREC_FP32 && !g.transposed && tc_supported(g, prec);
 }
 
 int hebb_workspace_bytes(const HebbDesc* d, int prec, size_t* bytes) {
@@ -122,6 +122,13 @@ int hebb_uses_tensor_cores(const HebbDesc* d, int prec) {
   Geo g;
   if (resolve_geo(d, &g) != HEBB_OK) return 0;
   return use_tc(g, prec) ? 1 : 0;
+}
+
+int hebb_debug_plan(const HebbDesc* d, int prec, int* out, int n) {
+  Geo g;
+  if (resolve_geo(d, &g) != HEBB_OK || !out) return 0;
+  if (!use_tc(g, prec)) return 0;
+  return tc_describe_plan(g, prec, out, n);
 }
 
 int hebb_wnorm(const float* W, float* Wn, float* inv_norm, int64_t rows, int64_t row_stride, int64_t mid,

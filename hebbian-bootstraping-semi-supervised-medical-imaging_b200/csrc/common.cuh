@@ -71,8 +71,9 @@ int simt_convT_step(const Geo& g, const float* x, const float* W, const float* b
                     cudaStream_t st);
 
 // ---- tcgen05 path (tc_path.cu) ----
-bool tc_supported(const Geo& g);
+bool tc_supported(const Geo& g, int prec);
 size_t tc_workspace_bytes(const Geo& g, int prec);
+int tc_describe_plan(const Geo& g, int prec, int* out, int n);
 int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y,
                  int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
                  cudaStream_t st);

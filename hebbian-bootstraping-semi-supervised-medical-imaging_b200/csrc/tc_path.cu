@@ -153,7 +153,7 @@ template <int CH>
 __global__ void __launch_bounds__(192, 1)
 fwd_swta_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   // misc region: [inv Cout][bias Cout][rs 4*Cout] floats, then barriers, then tmem ptr
@@ -186,7 +186,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
 
   if (warp == 0) {
     // ===================== producer: bulk copies =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const long long p0 = (long long)tile * p.TILE_M;
@@ -215,7 +215,9 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the (warp-uniform) loop nest; only the elected lane issues tcgen05.mma /
+    // commit.  Keeping control flow uniform lets ptxas keep descriptors in uniform registers.
+    {
       const uint32_t idesc = idesc_bf16(128, p.Cout, 0, 0);
       const uint64_t a_hi64 = smem_desc_hi(p.SEGLEN * 16, 128);   // LBO: chunk stride, SBO: 8 positions
       const uint64_t b_hi64 = smem_desc_hi(p.Cout * 16, 128);
@@ -224,11 +226,10 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
         mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * p.MB * p.Cout;
-        bool first = true;
+        uint32_t accum = 0u;
         for (int slab = 0; slab < p.NSLAB; ++slab) {
           for (int seg = 0; seg < p.nseg; ++seg) {
             mbar_wait(x_full + 8 * xs, xph, p.err, 4);
-            tc_fence_after();
             const uint32_t xa = sbase + xs * p.x_stage_bytes;
             for (int tap = p.seg_tap_begin[seg]; tap < p.seg_tap_begin[seg + 1]; ++tap) {
               mbar_wait(w_full + 8 * ws, wph, p.err, 5);
@@ -236,28 +237,34 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               const uint32_t wa = sbase + p.off_w + ws * p.w_stage_bytes;
               const uint64_t bh = smem_desc(b_hi64, wa);
               const uint64_t bl = smem_desc(b_hi64, wa + 2 * p.Cout * 16);
-              for (int j = 0; j < p.MB; ++j) {
-                const uint32_t a0 = xa + (j * 128 + p.tap_off[tap]) * 16;
-                const uint64_t ah = smem_desc(a_hi64, a0);
-                const uint32_t d = d0 + j * p.Cout;
-                if (p.HL == 2) {
-                  const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
-                  umma_bf16(d, ah, bl, idesc, first ? 0u : 1u);
-                  umma_bf16(d, al, bh, idesc, 1u);
-                  umma_bf16(d, ah, bh, idesc, 1u);
-                } else {
-                  umma_bf16(d, ah, bh, idesc, first ? 0u : 1u);
+              const uint32_t a_tap = xa + p.tap_off[tap] * 16;
+              if (elect_one()) {
+                for (int j = 0; j < p.MB; ++j) {
+                  const uint32_t a0 = a_tap + j * 2048;
+                  const uint64_t ah = smem_desc(a_hi64, a0);
+                  const uint32_t d = d0 + j * p.Cout;
+                  if (p.HL == 2) {
+                    const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
+                    umma_bf16(d, ah, bl, idesc, accum);
+                    umma_bf16(d, al, bh, idesc, 1u);
+                    umma_bf16(d, ah, bh, idesc, 1u);
+                  } else {
+                    umma_bf16(d, ah, bh, idesc, accum);
+                  }
                 }
+                umma_commit(w_empty + 8 * ws);
               }
-              first = false;
-              umma_commit(w_empty + 8 * ws);
+              __syncwarp();
+              accum = 1u;
               if (++ws == p.WST) { ws = 0; wph ^= 1; }
             }
-            umma_commit(x_empty + 8 * xs);
+            if (elect_one()) umma_commit(x_empty + 8 * xs);
+            __syncwarp();
             if (++xs == p.XST) { xs = 0; xph ^= 1; }
           }
         }
-        umma_commit(t_full + 8 * acc);
+        if (elect_one()) umma_commit(t_full + 8 * acc);
+        __syncwarp();
         if (++acc == p.NACC) { acc = 0; aph ^= 1; }
       }
     }
@@ -377,7 +384,7 @@ struct DwParams {
 __global__ void __launch_bounds__(192, 1)
 dw_swta_kernel(const __grid_constant__ DwParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
@@ -413,7 +420,7 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   const uint32_t r_hl_stride = (p.CN / 8) * p.BLK * 16;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0; uint32_t ph = 0;
       const uint32_t bytes = p.HL * (cm_chunks * p.SEGLEN + rn_chunks * p.BLK) * 16;
       for (int blk = blk_b; blk < blk_e; ++blk) {
@@ -434,7 +441,7 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = idesc_bf16(p.CM, N, 1, 1);
       const uint64_t a_hi64 = smem_desc_hi(128, p.SEGLEN * 16);   // MN-major: LBO = next 8 positions, SBO = next chunk
       const uint64_t b_hi64 = smem_desc_hi(128, p.BLK * 16);
@@ -446,27 +453,32 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
         const uint32_t xa = sbase + st * p.stage_bytes;
         const uint32_t ra = xa + r_off;
         const uint32_t accum0 = (blk == blk_b) ? 0u : 1u;
-        for (int tap = tap_b; tap < tap_e; ++tap) {
-          const uint32_t d = tmem_base + (tap - tap_b) * p.CN;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t a0 = xa + (ks * 16 + p.tap_off[tap]) * 16;
-            const uint32_t b0 = ra + ks * 256;
-            const uint64_t ah = smem_desc(a_hi64, a0), bh = smem_desc(b_hi64, b0);
-            const uint32_t acc = (ks == 0) ? accum0 : 1u;
-            if (p.HL == 2) {
-              const uint64_t al = smem_desc(a_hi64, a0 + x_hl_stride), bl = smem_desc(b_hi64, b0 + r_hl_stride);
-              umma_bf16(d, ah, bl, idesc, acc);
-              umma_bf16(d, al, bh, idesc, 1u);
-              umma_bf16(d, ah, bh, idesc, 1u);
-            } else {
-              umma_bf16(d, ah, bh, idesc, acc);
+        if (elect_one()) {
+          for (int tap = tap_b; tap < tap_e; ++tap) {
+            const uint32_t d = tmem_base + (tap - tap_b) * p.CN;
+            const uint32_t a_tap = xa + p.tap_off[tap] * 16;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t a0 = a_tap + ks * 256;
+              const uint32_t b0 = ra + ks * 256;
+              const uint64_t ah = smem_desc(a_hi64, a0), bh = smem_desc(b_hi64, b0);
+              const uint32_t acc = (ks == 0) ? accum0 : 1u;
+              if (p.HL == 2) {
+                const uint64_t al = smem_desc(a_hi64, a0 + x_hl_stride), bl = smem_desc(b_hi64, b0 + r_hl_stride);
+                umma_bf16(d, ah, bl, idesc, acc);
+                umma_bf16(d, al, bh, idesc, 1u);
+                umma_bf16(d, ah, bh, idesc, 1u);
+              } else {
+                umma_bf16(d, ah, bh, idesc, acc);
+              }
             }
           }
+          umma_commit(empty + 8 * st);
         }
-        umma_commit(empty + 8 * st);
+        __syncwarp();
         if (++st == p.ST) { st = 0; ph ^= 1; }
       }
-      umma_commit(done);
+      if (elect_one()) umma_commit(done);
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
@@ -590,43 +602,65 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   q.f_smem = q.f_off_misc + misc;
 
   // ---------------- dW ----------------
+  // Search (tap grouping, cin tile, cout tile, positions per stage, stages) for the cheapest plan that
+  // fits shared memory and TMEM.  Cost model (cycles per SM): a SWIZZLE_NONE MN-major tcgen05.mma costs
+  // ~135 cycles however small it is (measured, profiles/umma_rate_r1.txt) or N/2 when math-bound; staged
+  // bytes arrive at ~40 B/cycle/SM from L2.
   q.d_HL = (prec == HEBB_PREC_BF16) ? 1 : 2;
-  q.CM = (q.CC * 8 <= 64) ? 64 : 128;
-  q.n_cin_tiles = (int)cdiv(q.CC * 8, q.CM);
-  q.CinP = q.n_cin_tiles * q.CM;
-  const int cm_chunks = (q.CC < q.CM / 8) ? q.CC : q.CM / 8;
+  const int hl3 = (q.d_HL == 2) ? 3 : 1;
+  double best_cost = 1e300;
   found = false;
-  for (int by_kh = 0; by_kh <= 1 && !found; ++by_kh) {
+  for (int by_kh = 0; by_kh <= 1; ++by_kh) {
     const int gtaps = by_kh ? g.kW : g.kH * g.kW;
     const int ghalo = by_kh ? (g.kW - 1) : halo;
-    int cn = (512 / gtaps) / 16 * 16;
-    if (cn > g.Cout) cn = g.Cout;
-    if (cn > 256) cn = 256;
-    if (cn < 16) continue;
-    for (int blk = 1024; blk >= 128 && !found; blk >>= 1) {
-      if (!by_kh && ghalo > blk) continue;              // halo dominates: regroup by kernel row instead
-      const int seglen = round_up_i(blk + ghalo, 8);
-      const uint32_t xb = (uint32_t)q.d_HL * cm_chunks * seglen * 16;
-      const uint32_t rb = (uint32_t)q.d_HL * (cn / 8) * blk * 16;
-      for (int st = 3; st >= 2 && !found; --st) {
-        // the A descriptor always spans CM/8 chunks: the rows past cm_chunks read whatever
-        // follows in shared memory (discarded rows) but must stay inside the allocation
-        const uint32_t ring = st * (xb + rb);
-        const uint32_t last_read = (st - 1) * (xb + rb) + (q.d_HL - 1) * cm_chunks * seglen * 16 +
-                                   (uint32_t)(q.CM / 8) * seglen * 16 + 256;
-        uint32_t tot = ring > last_read ? ring : last_read;
-        tot += 8 * 16 + 64;
-        if (tot <= (uint32_t)kSmemLimit - 1024) {
-          q.d_by_kh = by_kh; q.BLK = blk; q.d_SEGLEN = seglen; q.ST = st; q.CN = cn;
-          q.d_x_bytes = xb; q.d_stage = xb + rb;
-          q.d_off_bar = (tot - (8 * 16 + 64) + 127) / 128 * 128;
-          q.d_smem = q.d_off_bar + 8 * 16 + 64;
-          found = true;
+    const int ngrp = by_kh ? g.kD * g.kH : g.kD;
+    if (by_kh && g.kH == 1) continue;
+    for (int cm = 128; cm >= 64; cm -= 64) {
+      if (cm == 128 && q.CC * 8 <= 64) continue;
+      const int cm_chunks = (q.CC < cm / 8) ? q.CC : cm / 8;
+      const int n_cin = (int)cdiv(q.CC * 8, cm);
+      const int cn_opts[7] = {256, 128, 64, 48, 32, 16, g.Cout};
+      for (int ci = 0; ci < 7; ++ci) {
+        const int cn = cn_opts[ci];
+        if (cn > g.Cout || cn > 256 || gtaps * cn > 512 || cn % 16) continue;
+        const int n_cout = (int)cdiv(g.Cout, cn);
+        for (int blk = 1024; blk >= 64; blk >>= 1) {
+          const int seglen = round_up_i(blk + ghalo, 8);
+          const uint32_t xb = (uint32_t)q.d_HL * cm_chunks * seglen * 16;
+          const uint32_t rb = (uint32_t)q.d_HL * (cn / 8) * blk * 16;
+          for (int st = 3; st >= 2; --st) {
+            // the A descriptor always spans cm/8 chunks: rows past cm_chunks read whatever follows in
+            // shared memory (discarded rows) but must stay inside the allocation
+            const uint64_t ring = (uint64_t)st * (xb + rb);
+            const uint64_t last_read = (uint64_t)(st - 1) * (xb + rb) + (uint64_t)(q.d_HL - 1) * cm_chunks * seglen * 16 +
+                                       (uint64_t)(cm / 8) * seglen * 16 + 256;
+            uint64_t tot = ring > last_read ? ring : last_read;
+            tot = (tot + 127) / 128 * 128 + 8 * 16 + 64;
+            if (tot > (uint64_t)kSmemLimit - 1024) continue;
+            const double mma = (cn / 2.0 > 135.0) ? cn / 2.0 : 135.0;
+            const double t_mma = (double)gtaps * (blk / 16) * hl3 * mma;
+            const double t_ld = (double)q.d_HL * 16.0 * ((double)cm_chunks * seglen + (cn / 8.0) * blk) / 40.0;
+            const double per_blk = (t_mma > t_ld ? t_mma : t_ld) + 800.0 + (st == 2 ? 0.15 * t_ld : 0.0);
+            const double out_tiles = (double)ngrp * n_cin * n_cout;
+            const double blocks = (double)cdiv(q.PTOT, blk);
+            double waves = out_tiles / sms;               // how unevenly the tasks fill the SMs
+            waves = waves < 1.0 ? 1.0 : waves;
+            const double cost = blocks * per_blk * out_tiles / sms + 30000.0 * waves + 4.0 * gtaps * cn * waves;
+            if (cost < best_cost) {
+              best_cost = cost; found = true;
+              q.d_by_kh = by_kh; q.BLK = blk; q.d_SEGLEN = seglen; q.ST = st; q.CN = cn; q.CM = cm;
+              q.d_x_bytes = xb; q.d_stage = xb + rb;
+              q.d_off_bar = (uint32_t)(tot - (8 * 16 + 64));
+              q.d_smem = (uint32_t)tot;
+            }
+          }
         }
       }
     }
   }
   if (!found) return false;
+  q.n_cin_tiles = (int)cdiv(q.CC * 8, q.CM);
+  q.CinP = q.n_cin_tiles * q.CM;
   q.ngrp = q.d_by_kh ? g.kD * g.kH : g.kD;
   q.n_cout_tiles = (int)cdiv(g.Cout, q.CN);
   q.d_tmem = pow2_cols((q.d_by_kh ? g.kW : g.kH * g.kW) * q.CN);
@@ -661,15 +695,26 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   return true;
 }
 
-bool tc_supported(const Geo& g) {
+bool tc_supported(const Geo& g, int prec) {
   Plan P;
-  return plan_layer(g, HEBB_PREC_BF16X3, &P);
+  return plan_layer(g, prec, &P);
 }
 
 size_t tc_workspace_bytes(const Geo& g, int prec) {
   Plan P;
   if (!plan_layer(g, prec, &P)) return 0;
   return P.total;
+}
+
+int tc_describe_plan(const Geo& g, int prec, int* o, int n) {
+  Plan P;
+  if (!plan_layer(g, prec, &P)) return 0;
+  const int v[] = {P.MB, P.f_SEGLEN, P.XST, P.WST, P.NACC, (int)P.f_tmem, P.f_ntiles, (int)P.f_smem,
+                   P.d_by_kh, P.CM, P.CN, P.BLK, P.ST, P.d_SEGLEN, P.ngrp, P.n_cin_tiles, P.n_cout_tiles, P.PS,
+                   P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20)};
+  const int m = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < n && i < m; ++i) o[i] = v[i];
+  return m;
 }
 
 static unsigned ew_grid(long long n) {
@@ -834,6 +879,47 @@ umma_probe_kernel(const uint8_t* __restrict__ a_img, int a_bytes, const uint8_t*
   (void)m;
 }
 
+
+// MMA issue-rate microbenchmark: every CTA issues `iters` rounds of `per_round` tcgen05.mma from operands
+// already resident in (uninitialised) shared memory and reports elapsed SM cycles of the whole sequence.
+__global__ void __launch_bounds__(128, 1)
+umma_rate_kernel(uint64_t a_hi, uint32_t a_step, uint64_t b_hi, uint32_t b_step, uint32_t b_off, uint32_t idesc,
+                 int per_round, int iters, int n, long long* __restrict__ cycles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t sa = smem_u32(smem);
+  // finite contents (zeros) so no NaN handling paths are exercised
+  for (int i = threadIdx.x; i < (int)(b_off * 2 / 16); i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  const uint32_t cols = pow2_cols(n);
+  if (warp == 0) { tmem_alloc(smem_u32(&s_tmem), cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = s_tmem;
+  if (__shfl_sync(0xffffffffu, warp, 0) == 0) {
+    const long long t0 = clock64();
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+        for (int k = 0; k < per_round; ++k)
+          umma_bf16(tb, smem_desc(a_hi, sa + k * a_step), smem_desc(b_hi, sa + b_off + k * b_step), idesc, 1u);
+        umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bar), ph, nullptr, 0);
+      ph ^= 1;
+    }
+    if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, cols);
+}
+
 }  // namespace hebb
 
 extern "C" int hebb_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
@@ -851,5 +937,19 @@ extern "C" int hebb_debug_umma_probe(const void* a_img, int a_bytes, const void*
       static_cast<const uint8_t*>(a_img), a_bytes, static_cast<const uint8_t*>(b_img), b_bytes, a_desc_hi, a_start,
       a_step, b_desc_hi, b_start, b_step, idesc, ksteps, m, n, d_out);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
+extern "C" int hebb_debug_umma_rate(uint64_t a_desc_hi, uint32_t a_step, uint64_t b_desc_hi, uint32_t b_step,
+                                    uint32_t region_bytes, uint32_t idesc, int per_round, int iters, int n, int ctas,
+                                    long long* cycles, void* stream) {
+  using namespace hebb;
+  HEBB_TRY(device_ok());
+  if (!cycles || region_bytes % 1024 || region_bytes * 2 + 1024 > (uint32_t)kSmemLimit) return HEBB_EARG;
+  const size_t smem = (size_t)region_bytes * 2 + 1024;
+  HEBB_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(a_desc_hi, a_step, b_desc_hi, b_step, region_bytes, idesc,
+                                                             per_round, iters, n, cycles);
+  HEBB_CUDA_TRY(cudaGetLastError());
   return HEBB_OK;
 }

@@ -25,6 +25,7 @@ EXPORTS = [
     'hebb_query', 'hebb_status_str', 'hebb_last_cuda_error', 'hebb_version', 'hebb_out_shape',
     'hebb_workspace_bytes', 'hebb_wnorm', 'hebb_conv_swta_step', 'hebb_convT_swta_step',
     'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
+    'hebb_debug_umma_rate', 'hebb_debug_plan',
 ]
 
 
@@ -72,6 +73,8 @@ def load():
         lib.hebb_debug_umma_probe.argtypes = [vp, i32, vp, i32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
                                               ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                               i32, i32, i32, vp, vp]
+        lib.hebb_debug_umma_rate.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
+                                             ctypes.c_uint32, ctypes.c_uint32, i32, i32, i32, i32, vp, vp]
         lib.hebb_debug_launch_count.restype = ctypes.c_ulonglong
         lib.hebb_uses_tensor_cores.argtypes = [ctypes.POINTER(HebbDesc), i32]
         for name in EXPORTS:
@@ -213,6 +216,16 @@ def local_update_multi(grads, dws, alphas, has_grad):
     al = (ctypes.c_float * n)(*[float(a) for a in alphas])
     hg = (ctypes.c_int32 * n)(*[1 if h else 0 for h in has_grad])
     check(lib.hebb_local_update_multi(n, g, d, ne, al, hg, _stream_ptr(dws[0].device)), 'local_update_multi')
+
+
+PLAN_FIELDS = ['MB', 'f_SEGLEN', 'XST', 'WST', 'NACC', 'f_tmem', 'f_tiles', 'f_smem', 'by_kh', 'CM', 'CN', 'BLK', 'ST',
+               'd_SEGLEN', 'ngrp', 'n_cin', 'n_cout', 'PS', 'blocks', 'd_tmem', 'd_smem', 'd_HL', 'ws_MiB']
+
+
+def plan(desc: HebbDesc, prec: int):
+    out = (ctypes.c_int * 32)()
+    n = load().hebb_debug_plan(ctypes.byref(desc), int(prec), out, 32)
+    return dict(zip(PLAN_FIELDS, list(out)[:n])) if n else None
 
 
 def launch_count() -> int:

@@ -126,6 +126,12 @@ unsigned long long hebb_debug_launch_count(void);
 /* 1 if (d, prec) runs on the tcgen05 kernels, 0 if on the CUDA-core kernels. */
 int hebb_uses_tensor_cores(const HebbDesc* d, int prec);
 
+/* Tile plan the tensor-core path would use (0 if it would not run there): fills out[0..n) with
+ * {MB, fwd SEGLEN, XST, WST, NACC, fwd TMEM cols, fwd tiles, fwd smem, dW by_kh, CM, CN, BLK, ST, dW SEGLEN,
+ *  tap groups, cin tiles, cout tiles, position splits, position blocks, dW TMEM cols, dW smem, dW HL, ws MiB};
+ * returns the number of fields. */
+int hebb_debug_plan(const HebbDesc* d, int prec, int* out, int n);
+
 /* One CTA: copy two raw operand images to shared memory, issue `ksteps` tcgen05.mma
  * (kind::f16, bf16 in, fp32 out) with descriptors {hi | (start + i*step) >> 4}, and dump
  * TMEM lanes 0..127 x n columns to d_out[128][n].  Pins the SWIZZLE_NONE descriptor
@@ -134,6 +140,13 @@ int hebb_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int
                           uint64_t a_desc_hi, uint32_t a_start, uint32_t a_step,
                           uint64_t b_desc_hi, uint32_t b_start, uint32_t b_step,
                           uint32_t idesc, int ksteps, int m, int n, float* d_out, void* stream);
+
+/* Issue `iters` rounds of `per_round` back-to-back tcgen05.mma per CTA from resident shared memory
+ * (two zeroed regions of region_bytes each; descriptor start advances by a_step/b_step per MMA)
+ * and report the elapsed SM cycles per CTA in cycles[ctas].  Used by scripts/umma_rate.py. */
+int hebb_debug_umma_rate(uint64_t a_desc_hi, uint32_t a_step, uint64_t b_desc_hi, uint32_t b_step,
+                         uint32_t region_bytes, uint32_t idesc, int per_round, int iters, int n, int ctas,
+                         long long* cycles, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,10 @@ def relerr(a, b):
 
 
 def check_winners(win_gpu, y_ref, tol_abs):
-    """Bit-exact wherever the reference's own top-2 margin exceeds the forward error bound."""
+    """Winner indices must equal the reference's argmax bit for bit wherever the reference's own
+    top-2 margin is resolvable (margin > tol_abs, a few times the forward rounding error; the
+    reference's CPU and GPU builds disagree below that too).  Returns the number of pixels
+    that differ inside the unresolvable band."""
     y_ref = torch.as_tensor(y_ref)
     want = y_ref.argmax(dim=1)
     top2 = y_ref.topk(2, dim=1).values
@@ -44,6 +47,9 @@ def check_winners(win_gpu, y_ref, tol_abs):
     got = win_gpu.cpu().long()
     bad = (got != want)
     assert not bool((bad & (margin > tol_abs)).any()), 'winner differs where the margin is resolvable'
+    if bool(bad.any()):            # a mismatch must pick the runner-up, never an arbitrary channel
+        second = y_ref.topk(2, dim=1).indices[:, 1]
+        assert bool((got[bad] == second[bad]).all())
     return int(bad.sum())
 
 
@@ -178,8 +184,10 @@ def test_tensor_core_shapes_vs_oracle(case, prec):
     layer = layer.to(DEV).train()
     y = layer(x.to(DEV))
     assert relerr(y, y_ref) < TOL_Y[prec]
-    nbad = check_winners(layer.winners, y_ref, 1e-4 * float(y_ref.abs().max()))
-    assert nbad <= (0 if prec != 'bf16' else 2)
+    # fp32 / bf16x3 forward error is ~4e-6 relative: exact above a 2e-5 margin, and at most a
+    # handful of near-ties (out of up to 131072 pixels) may resolve the other way
+    nbad = check_winners(layer.winners, y_ref, 2e-5 * float(y_ref.abs().max()))
+    assert nbad <= 4
     assert relerr(layer.delta_w, dw_ref) < TOL_DW[prec], (name, prec)
 
 
