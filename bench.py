@@ -209,7 +209,7 @@ def profile_layers(model, x, flush):
         xin = inp[0].detach().contiguous()
         desc = mod._desc(xin.shape, True)
         prec = _native.parse_prec(mod.prec)
-        tc = (not mod._transposed) and _native.uses_tensor_cores(desc, prec)
+        tc = _native.uses_tensor_cores(desc, prec)
         g = dict(kind=type(mod).__name__, Cin=mod.in_channels, Cout=mod.out_channels, k=list(mod.kernel_size),
                  x=list(xin.shape), y=list(out.shape), tensor_cores=bool(tc))
         P = out.numel() // mod.out_channels

@@ -106,7 +106,7 @@ int hebb_out_shape(const HebbDesc* d, int32_t out[3]) {
 }
 
 static bool use_tc(const Geo& g, int prec) {
-  return prec != HEBB_PREC_FP32 && !g.transposed && tc_supported(g, prec);
+  return prec != HEBB_PREC_FP32 && tc_supported(g, prec);
 }
 
 int hebb_workspace_bytes(const HebbDesc* d, int prec, size_t* bytes) {
@@ -166,6 +166,8 @@ int hebb_convT_swta_step(const HebbDesc* d, const float* x, const float* W, cons
   if ((flags & HEBB_F_UPDATE) && !delta_w) return HEBB_EARG;
   if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
   if (!aligned16(ws)) return HEBB_EALIGN;
+  if (use_tc(g, prec))
+    return tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, (cudaStream_t)stream);
   return simt_convT_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, (cudaStream_t)stream);
 }
 

@@ -77,7 +77,8 @@ pack_x_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __res
 
 // Wp[slab][tap][hl][c2][co] (uint4 = 8 input channels) : the forward B operand, K-major.
 __global__ void __launch_bounds__(256)
-pack_w_kernel(const float* __restrict__ W, uint4* __restrict__ wp, int Cin, int Cout, int taps, int NSLAB, int HL) {
+pack_w_kernel(const float* __restrict__ W, uint4* __restrict__ wp, int Cin, int Cout, int taps, int NSLAB, int HL,
+              int tr_taps, const float* __restrict__ inv_ci) {
   const long long total = (long long)NSLAB * taps * HL * 2 * Cout;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -94,7 +95,15 @@ pack_w_kernel(const float* __restrict__ W, uint4* __restrict__ wp, int Cin, int 
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int ci = (slab * 2 + c2) * 8 + 2 * i + j;
-        const float v = ci < Cin ? __ldg(W + ((long long)co * Cin + ci) * taps + tap) : 0.f;
+        float v = 0.f;
+        if (ci < Cin) {
+          if (tr_taps) {   // transposed conv as a 1x1 conv onto (co, offset) channels; W is [Cout][Cin][taps]
+            const int cr = co / tr_taps, off = co - cr * tr_taps;
+            v = __ldg(W + ((long long)cr * Cin + ci) * tr_taps + off) * (inv_ci ? inv_ci[ci] : 1.f);
+          } else {
+            v = __ldg(W + ((long long)co * Cin + ci) * taps + tap);
+          }
+        }
         __nv_bfloat16 hi, lo;
         split_bf16(v, hi, lo);
         e[j] = hl ? lo : hi;
@@ -114,6 +123,9 @@ struct FwdParams {
   uint4* rp[2];
   float* y; int32_t* winner; const float* inv; const float* bias; float* rsum; int* err;
   int Cout, CC, NSLAB, taps, nseg, HL;
+  int stackF;                  // bf16x3 forward: B = [w_hi | w_lo] stacked along N -> 2 MMAs instead of 3
+  int CT, n_ct, fuse;          // output-channel tile handled by one CTA (<= 512 TMEM columns); fuse: softmax in the epilogue
+  int tr, tD, tH, tW, CoutR;   // transposed conv (k == stride == 2): y scatter to the (tD,tH,tW) grid, CoutR real channels
   int RHL;                     // 1: r is consumed as single bf16 (hi only), 2: hi + lo
   long long PA, PR, PTOT;      // positions per chunk plane in Xp / Rp; real positions B*Qimg
   int MB, TILE_M, ntiles, SEGLEN;
@@ -149,6 +161,21 @@ template <int CH> struct TmemLd;
 template <> struct TmemLd<32> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[32]) { tmem_ld32(a, v); } };
 template <> struct TmemLd<16> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) { tmem_ld16(a, v); } };
 
+// Loads CH accumulator columns; with the stacked forward the x*w_lo partial lives `second` columns further on.
+template <int CH>
+__device__ __forceinline__ void ld_acc(uint32_t a, int second, uint32_t (&v)[CH]) {
+  TmemLd<CH>::ld(a, v);
+  if (second) {
+    uint32_t w[CH];
+    TmemLd<CH>::ld(a + second, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+  } else {
+    tmem_ld_wait();
+  }
+}
+
 template <int CH>
 __global__ void __launch_bounds__(192, 1)
 fwd_swta_kernel(const __grid_constant__ FwdParams p) {
@@ -158,20 +185,17 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
   const uint32_t sbase = smem_u32(smem);
   // misc region: [inv Cout][bias Cout][rs 4*Cout] floats, then barriers, then tmem ptr
   float* s_inv = reinterpret_cast<float*>(smem + p.off_misc);
-  float* s_bias = s_inv + p.Cout;
-  float* s_rs = s_bias + p.Cout;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rs + 4 * p.Cout);
+  float* s_bias = s_inv + p.CT;
+  float* s_rs = s_bias + p.CT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rs + 4 * p.CT);
+  const int total_work = p.ntiles * p.n_ct;      // work item = (position tile, output-channel tile)
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t x_full = bar0, x_empty = x_full + 8 * p.XST;
   const uint32_t w_full = x_empty + 8 * p.XST, w_empty = w_full + 8 * p.WST;
   const uint32_t t_full = w_empty + 8 * p.WST, t_empty = t_full + 8 * p.NACC;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * p.XST + 2 * p.WST + 2 * p.NACC);
 
-  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
-    s_inv[i] = p.inv ? p.inv[i] : 1.f;
-    s_bias[i] = p.bias ? p.bias[i] : 0.f;
-  }
-  for (int i = threadIdx.x; i < 4 * p.Cout; i += blockDim.x) s_rs[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * p.CT; i += blockDim.x) s_rs[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.XST; ++i) { mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 1); }
     for (int i = 0; i < p.WST; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
@@ -188,7 +212,8 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
     // ===================== producer: bulk copies =====================
     if (elect_one()) {
       int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work / p.n_ct, ct = work - tile * p.n_ct;
         const long long p0 = (long long)tile * p.TILE_M;
         for (int slab = 0; slab < p.NSLAB; ++slab) {
           for (int seg = 0; seg < p.nseg; ++seg) {
@@ -204,9 +229,11 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
             for (int tap = p.seg_tap_begin[seg]; tap < p.seg_tap_begin[seg + 1]; ++tap) {
               mbar_wait(w_empty + 8 * ws, wph ^ 1, p.err, 2);
               mbar_expect_tx(w_full + 8 * ws, p.w_stage_bytes);
-              bulk_g2s(sbase + p.off_w + ws * p.w_stage_bytes,
-                       p.wp + (long long)(slab * p.taps + tap) * p.HL * 2 * p.Cout, p.w_stage_bytes,
-                       w_full + 8 * ws);
+              for (int hl = 0; hl < p.HL; ++hl)          // staged as [k-chunk][hl][CT rows]: hi and lo rows adjacent
+                for (int c2 = 0; c2 < 2; ++c2)
+                  bulk_g2s(sbase + p.off_w + ws * p.w_stage_bytes + (c2 * p.HL + hl) * p.CT * 16,
+                           p.wp + ((long long)(slab * p.taps + tap) * p.HL * 2 + hl * 2 + c2) * p.Cout + ct * p.CT,
+                           p.CT * 16, w_full + 8 * ws);
               if (++ws == p.WST) { ws = 0; wph ^= 1; }
             }
           }
@@ -218,14 +245,18 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
     // The whole warp walks the (warp-uniform) loop nest; only the elected lane issues tcgen05.mma /
     // commit.  Keeping control flow uniform lets ptxas keep descriptors in uniform registers.
     {
-      const uint32_t idesc = idesc_bf16(128, p.Cout, 0, 0);
+      const int NH = (p.CT > 256) ? 2 : 1;          // one tcgen05.mma covers at most 256 output channels
+      const int NP = p.CT / NH;
+      const uint32_t idesc = idesc_bf16(128, NP, 0, 0);
+      const uint32_t idesc2 = idesc_bf16(128, 2 * NP, 0, 0);      // stacked [w_hi | w_lo]
+      const int cw = (p.stackF ? 2 : 1) * p.CT;                   // TMEM columns per M-block
       const uint64_t a_hi64 = smem_desc_hi(p.SEGLEN * 16, 128);   // LBO: chunk stride, SBO: 8 positions
-      const uint64_t b_hi64 = smem_desc_hi(p.Cout * 16, 128);
+      const uint64_t b_hi64 = smem_desc_hi(p.HL * p.CT * 16, 128);
       int xs = 0, ws = 0, acc = 0; uint32_t xph = 0, wph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * p.MB * p.Cout;
+        const uint32_t d0 = tmem_base + acc * p.MB * cw;
         uint32_t accum = 0u;
         for (int slab = 0; slab < p.NSLAB; ++slab) {
           for (int seg = 0; seg < p.nseg; ++seg) {
@@ -235,21 +266,27 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               mbar_wait(w_full + 8 * ws, wph, p.err, 5);
               tc_fence_after();
               const uint32_t wa = sbase + p.off_w + ws * p.w_stage_bytes;
-              const uint64_t bh = smem_desc(b_hi64, wa);
-              const uint64_t bl = smem_desc(b_hi64, wa + 2 * p.Cout * 16);
               const uint32_t a_tap = xa + p.tap_off[tap] * 16;
               if (elect_one()) {
-                for (int j = 0; j < p.MB; ++j) {
-                  const uint32_t a0 = a_tap + j * 2048;
-                  const uint64_t ah = smem_desc(a_hi64, a0);
-                  const uint32_t d = d0 + j * p.Cout;
-                  if (p.HL == 2) {
-                    const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
-                    umma_bf16(d, ah, bl, idesc, accum);
-                    umma_bf16(d, al, bh, idesc, 1u);
-                    umma_bf16(d, ah, bh, idesc, 1u);
-                  } else {
-                    umma_bf16(d, ah, bh, idesc, accum);
+                for (int h = 0; h < NH; ++h) {
+                  const uint64_t bh = smem_desc(b_hi64, wa + h * NP * 16);
+                  const uint64_t bl = smem_desc(b_hi64, wa + p.CT * 16 + h * NP * 16);
+                  for (int j = 0; j < p.MB; ++j) {
+                    const uint32_t a0 = a_tap + j * 2048;
+                    const uint64_t ah = smem_desc(a_hi64, a0);
+                    const uint32_t d = d0 + j * cw + h * NP;
+                    if (p.stackF) {          // x_hi*[w_hi|w_lo] -> columns [0,2CT) ; x_lo*w_hi -> columns [0,CT)
+                      const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
+                      umma_bf16(d, ah, bh, idesc2, accum);
+                      umma_bf16(d, al, bh, idesc, 1u);
+                    } else if (p.HL == 2) {
+                      const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
+                      umma_bf16(d, ah, bl, idesc, accum);
+                      umma_bf16(d, al, bh, idesc, 1u);
+                      umma_bf16(d, ah, bh, idesc, 1u);
+                    } else {
+                      umma_bf16(d, ah, bh, idesc, accum);
+                    }
                   }
                 }
                 umma_commit(w_empty + 8 * ws);
@@ -275,10 +312,21 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
     const int row = quad * 32 + lane;
     const long long outS = (long long)p.oD * p.oH * p.oW;
     const int oHW = p.oH * p.oW;
-    const int C8 = p.Cout / 8;
-    float* my_rs = s_rs + ew * p.Cout;
+    float* my_rs = s_rs + ew * p.CT;
     int acc = 0; uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    int cur_ct = -1;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      const int tile = work / p.n_ct, ct = work - tile * p.n_ct;
+      const int cbase = ct * p.CT;
+      if (ct != cur_ct) {      // (re)load this channel tile's 1/|W| and bias; only the 4 epilogue warps use them
+        asm volatile("bar.sync 1, 128;");
+        for (int i = threadIdx.x - 64; i < p.CT; i += 128) {
+          s_inv[i] = p.inv ? p.inv[cbase + i] : 1.f;
+          s_bias[i] = p.bias ? p.bias[p.tr ? ((cbase + i) >> 3) : (cbase + i)] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;");
+        cur_ct = ct;
+      }
       mbar_wait(t_full + 8 * acc, aph, p.err, 6);
       tc_fence_after();
       for (int j = 0; j < p.MB; ++j) {
@@ -290,28 +338,43 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
         const int ow = q - oh * p.WP;
         const bool valid = (od < p.oD) && (oh < p.oH) && (ow < p.oW) && (pp < p.PTOT);
         const long long s = (long long)od * oHW + (long long)oh * p.oW + ow;
-        float* yb = p.y + (long long)b * p.Cout * outS + s;
-        const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.MB * p.Cout + j * p.Cout;
+        float* yb = p.y + ((long long)b * p.Cout + cbase) * outS + s;
+        const long long tS = (long long)p.tD * p.tH * p.tW;
+        float* ytb = p.y + (long long)b * p.CoutR * tS + ((long long)(2 * od) * p.tH + 2 * oh) * p.tW + 2 * ow;
+        const int cw = (p.stackF ? 2 : 1) * p.CT;
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.MB * cw + j * cw;
         float mx = -INFINITY, best = -INFINITY;
         int bi = 0;
         uint32_t v[CH];
-        for (int c0 = 0; c0 < p.Cout; c0 += CH) {
-          TmemLd<CH>::ld(ta + c0, v);
-          tmem_ld_wait();
+        for (int c0 = 0; c0 < p.CT; c0 += CH) {
+          ld_acc<CH>(ta + c0, p.stackF ? p.CT : 0, v);
+          if (p.tr) {
+            // (co, offset) columns: offsets 2j, 2j+1 are x-neighbours in the up-sampled grid -> 8-byte stores
+            if (valid) {
 #pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            const float f = fmaf(__uint_as_float(v[i]), s_inv[c0 + i], s_bias[c0 + i]);
-            if (valid) yb[(long long)(c0 + i) * outS] = f;
-            mx = fmaxf(mx, f * p.kinv);
-            if (f > best) { best = f; bi = c0 + i; }
+              for (int i = 0; i < CH; i += 2) {
+                const int cc = cbase + c0 + i, off = cc & 7;
+                float2 o;
+                o.x = __uint_as_float(v[i]) + s_bias[c0 + i];
+                o.y = __uint_as_float(v[i + 1]) + s_bias[c0 + i + 1];
+                *reinterpret_cast<float2*>(ytb + (long long)(cc >> 3) * tS + ((long long)(off >> 2) * p.tH + ((off >> 1) & 1)) * p.tW) = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const float f = fmaf(__uint_as_float(v[i]), s_inv[c0 + i], s_bias[c0 + i]);
+              if (valid) yb[(long long)(c0 + i) * outS] = f;
+              mx = fmaxf(mx, f * p.kinv);
+              if (f > best) { best = f; bi = c0 + i; }
+            }
           }
         }
-        if (p.winner && valid) p.winner[(long long)b * outS + s] = bi;
-        if (p.write_r) {
+        if (p.fuse && p.winner && valid) p.winner[(long long)b * outS + s] = bi;
+        if (p.fuse && p.write_r) {
           float sum = 0.f;
-          for (int c0 = 0; c0 < p.Cout; c0 += CH) {
-            TmemLd<CH>::ld(ta + c0, v);
-            tmem_ld_wait();
+          for (int c0 = 0; c0 < p.CT; c0 += CH) {
+            ld_acc<CH>(ta + c0, p.stackF ? p.CT : 0, v);
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
               const float f = fmaf(__uint_as_float(v[i]), s_inv[c0 + i], s_bias[c0 + i]);
@@ -319,9 +382,8 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
             }
           }
           const float rinv = valid ? (1.f / sum) : 0.f;
-          for (int c0 = 0; c0 < p.Cout; c0 += CH) {
-            TmemLd<CH>::ld(ta + c0, v);
-            tmem_ld_wait();
+          for (int c0 = 0; c0 < p.CT; c0 += CH) {
+            ld_acc<CH>(ta + c0, p.stackF ? p.CT : 0, v);
             float rr[CH];
 #pragma unroll
             for (int g8 = 0; g8 < CH / 8; ++g8) {
@@ -357,13 +419,178 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       if (++acc == p.NACC) { acc = 0; aph ^= 1; }
     }
     __syncwarp();
-    if (p.write_r)
-      for (int c = lane; c < p.Cout; c += 32) atomicAdd(p.rsum + c, my_rs[c]);
-    (void)C8;
+    if (p.fuse && p.write_r)
+      for (int c = lane; c < p.CT; c += 32) atomicAdd(p.rsum + c, my_rs[c]);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// Unfused soft-WTA for layers whose channel count exceeds one CTA's TMEM (Cout > 512): one thread per
+// packed position reads its y row from global memory and writes the packed responses.  Only the
+// bottleneck layers of the 3-D network take this path (a few thousand positions).
+struct SmxParams {
+  const float* y; uint4* rp[2]; int32_t* winner; float* rsum;
+  int Cout, RHL, WP, plane, Qimg, oD, oH, oW;
+  long long PR, PTOT;
+  float kinv;
+};
+
+__global__ void __launch_bounds__(128)
+swta_softmax_pack_kernel(const __grid_constant__ SmxParams p) {
+  const long long pp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long outS = (long long)p.oD * p.oH * p.oW;
+  const int oHW = p.oH * p.oW;
+  const int b = (int)(pp / p.Qimg);
+  int q = (int)(pp - (long long)b * p.Qimg);
+  const int od = q / p.plane; q -= od * p.plane;
+  const int oh = q / p.WP;
+  const int ow = q - oh * p.WP;
+  const bool valid = (pp < p.PTOT) && (od < p.oD) && (oh < p.oH) && (ow < p.oW);
+  const long long s = (long long)od * oHW + (long long)oh * p.oW + ow;
+  const float* yb = p.y + (long long)b * p.Cout * outS + s;
+  float mx = -INFINITY, best = -INFINITY, sum = 0.f;
+  int bi = 0;
+  if (valid) {
+    for (int c = 0; c < p.Cout; ++c) {
+      const float f = __ldg(yb + (long long)c * outS);
+      mx = fmaxf(mx, f * p.kinv);
+      if (f > best) { best = f; bi = c; }
+    }
+    for (int c = 0; c < p.Cout; ++c) sum += __expf(fmaf(__ldg(yb + (long long)c * outS), p.kinv, -mx));
+    if (p.winner) p.winner[(long long)b * outS + s] = bi;
+  }
+  const float rinv = valid ? 1.f / sum : 0.f;
+  for (int c8 = 0; c8 < p.Cout / 8; ++c8) {
+    uint32_t oh4[4], ol4[4];
+    float rr[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat16 h2[2], l2[2];
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int c = c8 * 8 + i * 2 + k2;
+        const float r = valid ? __expf(fmaf(__ldg(yb + (long long)c * outS), p.kinv, -mx)) * rinv : 0.f;
+        split_bf16(r, h2[k2], l2[k2]);
+        rr[i * 2 + k2] = __bfloat162float(h2[k2]) + (p.RHL == 2 ? __bfloat162float(l2[k2]) : 0.f);
+      }
+      oh4[i] = pack_bf16x2(h2[0], h2[1]);
+      ol4[i] = pack_bf16x2(l2[0], l2[1]);
+    }
+    if (pp < p.PR) {
+      p.rp[0][(long long)c8 * p.PR + pp] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+      if (p.RHL == 2) p.rp[1][(long long)c8 * p.PR + pp] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = rr[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v != 0.f) atomicAdd(p.rsum + c8 * 8 + i, v);
+    }
+  }
+}
+
+// Transposed conv (k == stride == 2, 3-D): thread per INPUT voxel; its 8 output voxels (one per kernel
+// offset) each get a softmax over the real output channels (hebb3d.py:276-289).  Packed channel
+// index = co*8 + off, so one 16-byte vector holds the 8 offsets of one output channel.
+__global__ void __launch_bounds__(128)
+swta_softmax_pack_T_kernel(const __grid_constant__ SmxParams p, int tD, int tH, int tW, int CoutR) {
+  const long long pp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long tS = (long long)tD * tH * tW;
+  const int b = (int)(pp / p.Qimg);
+  int q = (int)(pp - (long long)b * p.Qimg);
+  const int id = q / p.plane; q -= id * p.plane;
+  const int ih = q / p.WP;
+  const int iw = q - ih * p.WP;
+  const bool valid = pp < p.PTOT;
+  const float* yb = p.y + (long long)b * CoutR * tS + ((long long)(2 * id) * tH + 2 * ih) * tW + 2 * iw;
+  long long o8[8];
+#pragma unroll
+  for (int off = 0; off < 8; ++off) o8[off] = ((long long)(off >> 2) * tH + ((off >> 1) & 1)) * tW + (off & 1);
+  float mx[8], sum[8], best[8];
+  int bi[8];
+#pragma unroll
+  for (int off = 0; off < 8; ++off) { mx[off] = -INFINITY; sum[off] = 0.f; best[off] = -INFINITY; bi[off] = 0; }
+  if (valid) {
+    for (int c = 0; c < CoutR; ++c)
+#pragma unroll
+      for (int off = 0; off < 8; off += 2) {
+        const float2 f2 = __ldg(reinterpret_cast<const float2*>(yb + (long long)c * tS + o8[off]));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float f = h ? f2.y : f2.x;
+          const float kv = f * p.kinv;
+          if (kv > mx[off + h]) { sum[off + h] *= __expf(mx[off + h] - kv); mx[off + h] = kv; }   // online rescale
+          sum[off + h] += __expf(kv - mx[off + h]);
+          if (f > best[off + h]) { best[off + h] = f; bi[off + h] = c; }
+        }
+      }
+    if (p.winner) {
+      int32_t* wb = p.winner + (long long)b * tS + ((long long)(2 * id) * tH + 2 * ih) * tW + 2 * iw;
+#pragma unroll
+      for (int off = 0; off < 8; ++off) wb[o8[off]] = bi[off];
+    }
+  }
+  for (int c = 0; c < CoutR; ++c) {
+    uint32_t oh4[4], ol4[4];
+    float rr[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat16 h2[2], l2[2];
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int off = i * 2 + k2;
+        const float r = valid ? __expf(fmaf(__ldg(yb + (long long)c * tS + o8[off]), p.kinv, -mx[off])) / sum[off] : 0.f;
+        split_bf16(r, h2[k2], l2[k2]);
+        rr[off] = __bfloat162float(h2[k2]) + (p.RHL == 2 ? __bfloat162float(l2[k2]) : 0.f);
+      }
+      oh4[i] = pack_bf16x2(h2[0], h2[1]);
+      ol4[i] = pack_bf16x2(l2[0], l2[1]);
+    }
+    if (pp < p.PR) {
+      p.rp[0][(long long)c * p.PR + pp] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+      if (p.RHL == 2) p.rp[1][(long long)c * p.PR + pp] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = rr[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v != 0.f) atomicAdd(p.rsum + c * 8 + i, v);
+    }
+  }
+}
+
+// delta_w[co][ci][off] += sum_s Hpart[s][0][ci][co*8+off] - sum_off' rsum[co*8+off'] * W[co][ci][off']
+__global__ void __launch_bounds__(256)
+tc_finalize_T_kernel(const float* __restrict__ hpart, const float* __restrict__ rsum, const float* __restrict__ W,
+                     float* __restrict__ dw, int PS, int Cin, int CinP, int CoutR) {
+  const long long n = (long long)Cin * CoutR;
+  const long long Cp = (long long)CoutR * 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % CoutR);
+    const int ci = (int)(idx / CoutR);
+    const float* w = W + ((long long)co * Cin + ci) * 8;
+    float* d = dw + ((long long)co * Cin + ci) * 8;
+    float dec = 0.f;
+#pragma unroll
+    for (int off = 0; off < 8; ++off) dec += rsum[co * 8 + off] * w[off];
+    float h[8];
+#pragma unroll
+    for (int off = 0; off < 8; ++off) h[off] = 0.f;
+    for (int s = 0; s < PS; ++s) {
+      const float* hp = hpart + ((long long)s * CinP + ci) * Cp + (long long)co * 8;
+#pragma unroll
+      for (int off = 0; off < 8; ++off) h[off] += hp[off];
+    }
+#pragma unroll
+    for (int off = 0; off < 8; ++off) d[off] += h[off] - dec;
+  }
 }
 
 // -------------------------------------------------------------------------------------
@@ -378,6 +605,8 @@ struct DwParams {
   int BLK, SEGLEN, total_blocks, blocks_per_split, PS;
   int ngrp; int grp_base[9]; int grp_tap_begin[10]; int tap_off[kMaxTaps];
   int CM, n_cin_tiles, CN, n_cout_tiles, ST, CinP;
+  int stackM, stackN, cpt;      // bf16x3 "precision stacking": [x_hi; x_lo] along M and/or [r_hi | r_lo] along N, so one
+                                // tcgen05.mma yields several of the hi/lo partial products; cpt = 8-channel chunks per cin tile
   uint32_t stage_bytes, x_bytes, off_bar, tmem_cols;
 };
 
@@ -398,9 +627,11 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   const int cout_tile = task % p.n_cout_tiles; task /= p.n_cout_tiles;
   const int cin_tile = task % p.n_cin_tiles; task /= p.n_cin_tiles;
   const int grp = task;
-  const int cm_chunks = min(p.CM / 8, p.CC - cin_tile * (p.CM / 8));
+  const int cm_chunks = min(p.cpt, p.CC - cin_tile * p.cpt);
   const int N = min(p.CN, p.Cout - cout_tile * p.CN);
   const int rn_chunks = N / 8;
+  const int Neff = p.stackN ? 2 * N : N;
+  const int colw = (p.stackN ? 2 : 1) * p.CN;        // TMEM columns per tap
   const int tap_b = p.grp_tap_begin[grp], tap_e = p.grp_tap_begin[grp + 1];
   const int blk_b = min(split * p.blocks_per_split, p.total_blocks);
   const int blk_e = min(blk_b + p.blocks_per_split, p.total_blocks);
@@ -416,8 +647,8 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const uint32_t r_off = p.x_bytes;                 // R region follows X region inside a stage
-  const uint32_t x_hl_stride = cm_chunks * p.SEGLEN * 16;
-  const uint32_t r_hl_stride = (p.CN / 8) * p.BLK * 16;
+  const uint32_t x_hl_stride = cm_chunks * p.SEGLEN * 16;   // lo chunks directly follow the hi chunks
+  const uint32_t r_hl_stride = rn_chunks * p.BLK * 16;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -431,7 +662,7 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
         for (int hl = 0; hl < p.HL; ++hl) {
           for (int c = 0; c < cm_chunks; ++c)
             bulk_g2s(dst + hl * x_hl_stride + c * p.SEGLEN * 16,
-                     p.xp[hl] + (long long)(cin_tile * (p.CM / 8) + c) * p.PA + p0 + p.grp_base[grp],
+                     p.xp[hl] + (long long)(cin_tile * p.cpt + c) * p.PA + p0 + p.grp_base[grp],
                      p.SEGLEN * 16, full + 8 * st);
           for (int c = 0; c < rn_chunks; ++c)
             bulk_g2s(dst + r_off + hl * r_hl_stride + c * p.BLK * 16,
@@ -442,11 +673,12 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
     }
   } else if (warp == 1) {
     {
-      const uint32_t idesc = idesc_bf16(p.CM, N, 1, 1);
+      const uint32_t idesc = idesc_bf16(p.CM, Neff, 1, 1);
       const uint64_t a_hi64 = smem_desc_hi(128, p.SEGLEN * 16);   // MN-major: LBO = next 8 positions, SBO = next chunk
       const uint64_t b_hi64 = smem_desc_hi(128, p.BLK * 16);
       int st = 0; uint32_t ph = 0;
       const int ksteps = p.BLK / 16;
+      const int mode = (p.HL == 2) ? (p.stackM ? (p.stackN ? 1 : 2) : (p.stackN ? 3 : 4)) : 0;
       for (int blk = blk_b; blk < blk_e; ++blk) {
         mbar_wait(full + 8 * st, ph, p.err, 12);
         tc_fence_after();
@@ -455,20 +687,26 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
         const uint32_t accum0 = (blk == blk_b) ? 0u : 1u;
         if (elect_one()) {
           for (int tap = tap_b; tap < tap_e; ++tap) {
-            const uint32_t d = tmem_base + (tap - tap_b) * p.CN;
+            const uint32_t d = tmem_base + (tap - tap_b) * colw;
             const uint32_t a_tap = xa + p.tap_off[tap] * 16;
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t a0 = a_tap + ks * 256;
               const uint32_t b0 = ra + ks * 256;
               const uint64_t ah = smem_desc(a_hi64, a0), bh = smem_desc(b_hi64, b0);
               const uint32_t acc = (ks == 0) ? accum0 : 1u;
-              if (p.HL == 2) {
+              if (mode <= 1) {                 // single bf16 pass, or [hi;lo] x [hi|lo] in one instruction
+                umma_bf16(d, ah, bh, idesc, acc);
+              } else if (mode == 2) {          // rows stacked: ([x_hi;x_lo], r_hi) + ([x_hi;x_lo], r_lo)
+                umma_bf16(d, ah, smem_desc(b_hi64, b0 + r_hl_stride), idesc, acc);
+                umma_bf16(d, ah, bh, idesc, 1u);
+              } else if (mode == 3) {          // columns stacked: (x_lo, [r_hi|r_lo]) + (x_hi, [r_hi|r_lo])
+                umma_bf16(d, smem_desc(a_hi64, a0 + x_hl_stride), bh, idesc, acc);
+                umma_bf16(d, ah, bh, idesc, 1u);
+              } else {                         // classic 3-pass split
                 const uint64_t al = smem_desc(a_hi64, a0 + x_hl_stride), bl = smem_desc(b_hi64, b0 + r_hl_stride);
                 umma_bf16(d, ah, bl, idesc, acc);
                 umma_bf16(d, al, bh, idesc, 1u);
                 umma_bf16(d, ah, bh, idesc, 1u);
-              } else {
-                umma_bf16(d, ah, bh, idesc, acc);
               }
             }
           }
@@ -487,23 +725,31 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
     int row; bool row_ok;
     if (p.CM == 128) { row = quad * 32 + lane; row_ok = true; }
     else { row = quad * 16 + (lane & 15); row_ok = lane < 16; }    // M=64: D row r lives in lane (r%16)+32*(r/16)
-    const int ci = cin_tile * p.CM + row;
-    const bool st_ok = row_ok && ci < p.Cin;
+    // stacked rows: [0, R) pair with x_hi, [R, 2R) with x_lo (R = real channels of this cin tile)
+    const int R = cm_chunks * 8;
+    const int row_lo = (p.stackM && row >= R) ? 1 : 0;
+    const int rloc = row - row_lo * R;
+    const int ci = cin_tile * p.cpt * 8 + rloc;
+    const bool st_ok = row_ok && rloc < R && ci < p.Cin && (p.stackM ? row < 2 * R : true);
     const bool have = blk_e > blk_b;
+    const int Q = (p.stackM ? 2 : 1) * (p.stackN ? 2 : 1);
     for (int tap = tap_b; tap < tap_e; ++tap) {
-      const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (tap - tap_b) * p.CN;
-      float* dst = p.hpart + (((long long)split * p.taps + tap) * p.CinP + ci) * p.Cout + cout_tile * p.CN;
-      for (int c0 = 0; c0 < N; c0 += 16) {
+      const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (tap - tap_b) * colw;
+      for (int c0 = 0; c0 < Neff; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(ta + c0, v);
         tmem_ld_wait();
+        const int col_lo = (p.stackN && c0 >= N) ? 1 : 0;
+        const int quadrant = row_lo * (p.stackN ? 2 : 1) + col_lo;
+        float* dst = p.hpart + ((((long long)split * Q + quadrant) * p.taps + tap) * p.CinP + ci) * p.Cout +
+                     cout_tile * p.CN + (c0 - col_lo * N);
         if (st_ok) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float4 o;
             o.x = have ? __uint_as_float(v[4 * i + 0]) : 0.f; o.y = have ? __uint_as_float(v[4 * i + 1]) : 0.f;
             o.z = have ? __uint_as_float(v[4 * i + 2]) : 0.f; o.w = have ? __uint_as_float(v[4 * i + 3]) : 0.f;
-            *reinterpret_cast<float4*>(dst + c0 + 4 * i) = o;
+            *reinterpret_cast<float4*>(dst + 4 * i) = o;
           }
         }
       }
@@ -544,21 +790,42 @@ struct Plan {
   long long PTOT, PR, PA;
   int maxshift;
   // forward
-  int f_HL, MB, TILE_M, f_SEGLEN, XST, WST, NACC, f_nseg, f_ntiles;
+  int f_HL, MB, TILE_M, f_SEGLEN, XST, WST, NACC, f_nseg, f_ntiles, CT, n_ct, stackF;
   uint32_t f_x_stage, f_w_stage, f_off_w, f_off_misc, f_smem, f_tmem;
   // dW
   int d_HL, BLK, d_SEGLEN, d_by_kh, ngrp, CM, n_cin_tiles, CN, n_cout_tiles, PS, total_blocks, blocks_per_split, ST, CinP;
+  int stackM, stackN, cpt, Q;
   uint32_t d_stage, d_x_bytes, d_off_bar, d_smem, d_tmem;
   // workspace carve (byte offsets)
   size_t o_inv, o_rsum, o_err, o_xp[2], o_rp[2], o_wp, o_hpart, total;
   bool ok;
 };
 
+// A transposed conv with kernel == stride == 2 (3-D) and no padding is a 1x1 conv onto Cout*8
+// "(co, offset)" channels followed by a pixel shuffle; its plasticity update is the matching 1x1 update.
+static bool equivalent_1x1(const Geo& g, Geo* e) {
+  if (!g.transposed) { *e = g; return true; }
+  if (g.nd != 3 || g.kD != 2 || g.kH != 2 || g.kW != 2 || g.sD != 2 || g.sH != 2 || g.sW != 2) return false;
+  if (g.pD || g.pH || g.pW || g.qD || g.qH || g.qW) return false;
+  if ((long long)g.Cout * 8 > 8192) return false;
+  *e = g;
+  e->transposed = 0;
+  e->Cout = g.Cout * 8;
+  e->kD = e->kH = e->kW = 1; e->sD = e->sH = e->sW = 1;
+  e->oD = g.iD; e->oH = g.iH; e->oW = g.iW;
+  e->taps = 1; e->K = g.Cin;
+  e->outS = g.inS;
+  return true;
+}
+
 static bool plan_layer(const Geo& g, int prec, Plan* P) {
   Plan& q = *P;
   q.ok = false;
   if (g.transposed || g.sD != 1 || g.sH != 1 || g.sW != 1) return false;
-  if (g.Cout % 16 || g.Cout > 256 || g.taps > kMaxTaps) return false;
+  if (g.Cout % 16 || g.taps > kMaxTaps) return false;
+  q.CT = g.Cout <= 512 ? g.Cout : 512;           // channel tile of the forward kernel (TMEM: 512 columns)
+  if (g.Cout % q.CT) return false;
+  q.n_ct = g.Cout / q.CT;
   if (g.kD > 3 || g.kH > 9 || g.kW > 9) return false;
   q.HP = g.iH + g.pH + g.qH; q.WP = g.iW + g.pW + g.qW;
   const int xD = g.iD + g.pD + g.qD;
@@ -575,11 +842,13 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   q.f_HL = 2;                                   // forward is always split (exact winners)
   const int halo = (g.kH - 1) * q.WP + (g.kW - 1);
   q.f_nseg = g.kD;
-  q.f_w_stage = (uint32_t)q.f_HL * 2 * g.Cout * 16;
-  const uint32_t misc = (uint32_t)(6 * g.Cout * 4 + 8 * 64 + 64);
+  q.stackF = (q.f_HL == 2 && q.CT <= 64 && !g.transposed) ? 1 : 0;
+  const int fcw = (q.stackF ? 2 : 1) * q.CT;
+  q.f_w_stage = (uint32_t)q.f_HL * 2 * q.CT * 16;
+  const uint32_t misc = (uint32_t)(6 * q.CT * 4 + 8 * 64 + 64);
   bool found = false;
   for (int mb = 4; mb >= 1 && !found; mb >>= 1) {
-    if (mb * g.Cout > 256 && !(mb == 1)) continue;
+    if (mb > 1 && mb * fcw > 256) continue;
     // do not make tiles so large that the grid cannot fill the machine
     if (mb > 1 && cdiv(q.PTOT, 128LL * mb) < 2LL * sms) continue;
     const int seglen = round_up_i(128 * mb + halo, 8);
@@ -595,8 +864,8 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
     }
   }
   if (!found) return false;
-  q.NACC = (2 * q.MB * g.Cout <= 512) ? 2 : 1;
-  q.f_tmem = pow2_cols(q.NACC * q.MB * g.Cout);
+  q.NACC = (2 * q.MB * fcw <= 512) ? 2 : 1;
+  q.f_tmem = pow2_cols(q.NACC * q.MB * fcw);
   q.f_off_w = q.XST * q.f_x_stage;
   q.f_off_misc = q.f_off_w + q.WST * q.f_w_stage;
   q.f_smem = q.f_off_misc + misc;
@@ -616,20 +885,24 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
     const int ngrp = by_kh ? g.kD * g.kH : g.kD;
     if (by_kh && g.kH == 1) continue;
     for (int cm = 128; cm >= 64; cm -= 64) {
-      if (cm == 128 && q.CC * 8 <= 64) continue;
-      const int cm_chunks = (q.CC < cm / 8) ? q.CC : cm / 8;
-      const int n_cin = (int)cdiv(q.CC * 8, cm);
+     for (int sm = 0; sm <= (q.d_HL == 2 ? 1 : 0); ++sm) {
+      for (int sn = 0; sn <= (q.d_HL == 2 ? 1 : 0); ++sn) {
+      const int cpt = sm ? cm / 16 : cm / 8;             // 8-channel chunks of x per cin tile
+      if (cm == 128 && q.CC <= cpt / 2) continue;        // a 64-row instruction already holds everything
+      const int cm_chunks = (q.CC < cpt) ? q.CC : cpt;
+      const int n_cin = (int)cdiv(q.CC, cpt);
       const int cn_opts[7] = {256, 128, 64, 48, 32, 16, g.Cout};
       for (int ci = 0; ci < 7; ++ci) {
         const int cn = cn_opts[ci];
-        if (cn > g.Cout || cn > 256 || gtaps * cn > 512 || cn % 16) continue;
+        const int neff = sn ? 2 * cn : cn;
+        if (cn > g.Cout || neff > 256 || gtaps * neff > 512 || cn % 16) continue;
         const int n_cout = (int)cdiv(g.Cout, cn);
         for (int blk = 1024; blk >= 64; blk >>= 1) {
           const int seglen = round_up_i(blk + ghalo, 8);
           const uint32_t xb = (uint32_t)q.d_HL * cm_chunks * seglen * 16;
           const uint32_t rb = (uint32_t)q.d_HL * (cn / 8) * blk * 16;
           for (int st = 3; st >= 2; --st) {
-            // the A descriptor always spans cm/8 chunks: rows past cm_chunks read whatever follows in
+            // the A descriptor always spans cm/8 chunks: rows past the real ones read whatever follows in
             // shared memory (discarded rows) but must stay inside the allocation
             const uint64_t ring = (uint64_t)st * (xb + rb);
             const uint64_t last_read = (uint64_t)(st - 1) * (xb + rb) + (uint64_t)(q.d_HL - 1) * cm_chunks * seglen * 16 +
@@ -637,18 +910,25 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
             uint64_t tot = ring > last_read ? ring : last_read;
             tot = (tot + 127) / 128 * 128 + 8 * 16 + 64;
             if (tot > (uint64_t)kSmemLimit - 1024) continue;
-            const double mma = (cn / 2.0 > 135.0) ? cn / 2.0 : 135.0;
-            const double t_mma = (double)gtaps * (blk / 16) * hl3 * mma;
+            // measured cycles per SWIZZLE_NONE MN-major tcgen05.mma (profiles/umma_rate_r1.txt)
+            (void)hl3;
+            const double floor_c = (cm == 64) ? 45.0 : 60.0;
+            const double mma = (neff * 0.5625 > floor_c) ? neff * 0.5625 : floor_c;
+            const int n_mma = (q.d_HL == 2) ? (sm && sn ? 1 : ((sm || sn) ? 2 : 3)) : 1;
+            const double t_mma = (double)gtaps * (blk / 16) * n_mma * mma;
             const double t_ld = (double)q.d_HL * 16.0 * ((double)cm_chunks * seglen + (cn / 8.0) * blk) / 40.0;
             const double per_blk = (t_mma > t_ld ? t_mma : t_ld) + 800.0 + (st == 2 ? 0.15 * t_ld : 0.0);
             const double out_tiles = (double)ngrp * n_cin * n_cout;
             const double blocks = (double)cdiv(q.PTOT, blk);
             double waves = out_tiles / sms;               // how unevenly the tasks fill the SMs
             waves = waves < 1.0 ? 1.0 : waves;
-            const double cost = blocks * per_blk * out_tiles / sms + 30000.0 * waves + 4.0 * gtaps * cn * waves;
+            double ctas = out_tiles < sms ? out_tiles * (double)((int)(sms / out_tiles)) : out_tiles;   // CTAs of the single wave
+            if (ctas > sms) ctas = sms;
+            const double cost = blocks * per_blk * out_tiles / ctas + 30000.0 * waves + 4.0 * gtaps * neff * waves;
             if (cost < best_cost) {
               best_cost = cost; found = true;
               q.d_by_kh = by_kh; q.BLK = blk; q.d_SEGLEN = seglen; q.ST = st; q.CN = cn; q.CM = cm;
+              q.stackM = sm; q.stackN = sn; q.cpt = cpt;
               q.d_x_bytes = xb; q.d_stage = xb + rb;
               q.d_off_bar = (uint32_t)(tot - (8 * 16 + 64));
               q.d_smem = (uint32_t)tot;
@@ -656,14 +936,17 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
           }
         }
       }
+      }
+     }
     }
   }
   if (!found) return false;
-  q.n_cin_tiles = (int)cdiv(q.CC * 8, q.CM);
-  q.CinP = q.n_cin_tiles * q.CM;
+  q.n_cin_tiles = (int)cdiv(q.CC, q.cpt);
+  q.CinP = q.n_cin_tiles * q.cpt * 8;
+  q.Q = (q.stackM ? 2 : 1) * (q.stackN ? 2 : 1);
   q.ngrp = q.d_by_kh ? g.kD * g.kH : g.kD;
   q.n_cout_tiles = (int)cdiv(g.Cout, q.CN);
-  q.d_tmem = pow2_cols((q.d_by_kh ? g.kW : g.kH * g.kW) * q.CN);
+  q.d_tmem = pow2_cols((q.d_by_kh ? g.kW : g.kH * g.kW) * q.CN * (q.stackN ? 2 : 1));
 
   // packed position space: multiples of both tile sizes
   const int big = q.TILE_M > q.BLK ? q.TILE_M : q.BLK;
@@ -672,7 +955,8 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   q.f_ntiles = (int)(q.PR / q.TILE_M);
   q.total_blocks = (int)(q.PR / q.BLK);
   const int out_tiles = q.ngrp * q.n_cin_tiles * q.n_cout_tiles;
-  int ps = (sms + out_tiles - 1) / out_tiles;
+  // one wave: never more CTAs than SMs (a 149th CTA would double the kernel's duration)
+  int ps = sms / out_tiles;
   if (ps > q.total_blocks) ps = q.total_blocks;
   if (ps < 1) ps = 1;
   q.blocks_per_split = (int)cdiv(q.total_blocks, ps);
@@ -681,7 +965,7 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   // ---------------- workspace ----------------
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-  q.o_inv = take(sizeof(float) * g.Cout);
+  q.o_inv = take(sizeof(float) * (g.Cout > g.Cin ? g.Cout : g.Cin));
   q.o_rsum = take(sizeof(float) * g.Cout);
   q.o_err = take(256);
   q.o_xp[0] = take((size_t)q.CC * q.PA * 16);
@@ -689,7 +973,7 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   q.o_rp[0] = take((size_t)q.C8 * q.PR * 16);
   q.o_rp[1] = take((size_t)q.C8 * q.PR * 16);
   q.o_wp = take((size_t)q.NSLAB * g.taps * q.f_HL * 2 * g.Cout * 16);
-  q.o_hpart = take((size_t)q.PS * g.taps * q.CinP * g.Cout * sizeof(float));
+  q.o_hpart = take((size_t)q.PS * q.Q * g.taps * q.CinP * g.Cout * sizeof(float));
   q.total = off;
   q.ok = true;
   return true;
@@ -697,21 +981,24 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
 
 bool tc_supported(const Geo& g, int prec) {
   Plan P;
-  return plan_layer(g, prec, &P);
+  Geo e;
+  return equivalent_1x1(g, &e) && plan_layer(e, prec, &P);
 }
 
 size_t tc_workspace_bytes(const Geo& g, int prec) {
   Plan P;
-  if (!plan_layer(g, prec, &P)) return 0;
+  Geo e;
+  if (!equivalent_1x1(g, &e) || !plan_layer(e, prec, &P)) return 0;
   return P.total;
 }
 
-int tc_describe_plan(const Geo& g, int prec, int* o, int n) {
+int tc_describe_plan(const Geo& g0, int prec, int* o, int n) {
   Plan P;
-  if (!plan_layer(g, prec, &P)) return 0;
+  Geo g;
+  if (!equivalent_1x1(g0, &g) || !plan_layer(g, prec, &P)) return 0;
   const int v[] = {P.MB, P.f_SEGLEN, P.XST, P.WST, P.NACC, (int)P.f_tmem, P.f_ntiles, (int)P.f_smem,
                    P.d_by_kh, P.CM, P.CN, P.BLK, P.ST, P.d_SEGLEN, P.ngrp, P.n_cin_tiles, P.n_cout_tiles, P.PS,
-                   P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20)};
+                   P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < m; ++i) o[i] = v[i];
   return m;
@@ -723,11 +1010,13 @@ static unsigned ew_grid(long long n) {
   return (unsigned)(gx > cap ? cap : (gx < 1 ? 1 : gx));
 }
 
-int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y,
+int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bias, float kinv, float* y,
                  int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
                  cudaStream_t st) {
   Plan P;
-  if (!plan_layer(g, prec, &P)) return HEBB_ESHAPE;
+  Geo g;
+  if (!equivalent_1x1(g0, &g) || !plan_layer(g, prec, &P)) return HEBB_ESHAPE;
+  const bool tr = g0.transposed != 0;
   if (!ws || ws_bytes < P.total) return HEBB_EWS;
   char* base = static_cast<char*>(ws);
   float* inv = reinterpret_cast<float*>(base + P.o_inv);
@@ -747,7 +1036,12 @@ int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias
   const bool do_fwd = !only || (only & HEBB_F_ONLY_FWD);
   const bool do_dw = upd && (!only || (only & HEBB_F_ONLY_DW));
   if (do_fwd) HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, (P.o_xp[0] - P.o_rsum), st));   // rsum + err word
-  if ((flags & HEBB_F_WNRM) && do_pack) HEBB_TRY(launch_wnorm(W, nullptr, inv, g.Cout, g.K, 1, 0, g.K, st));
+  if ((flags & HEBB_F_WNRM) && do_pack) {
+    if (tr)   // per INPUT channel over (Cout, taps) of the [Cout][Cin][taps] buffer (hebb3d.py:78 on the view)
+      HEBB_TRY(launch_wnorm(W, nullptr, inv, g0.Cin, g0.taps, g0.Cout, (long long)g0.Cin * g0.taps, g0.taps, st));
+    else
+      HEBB_TRY(launch_wnorm(W, nullptr, inv, g.Cout, g.K, 1, 0, g.K, st));
+  }
 
   PackGeo pg;
   pg.B = g.B; pg.Cin = g.Cin; pg.iD = g.iD; pg.iH = g.iH; pg.iW = g.iW; pg.pD = g.pD; pg.pH = g.pH; pg.pW = g.pW;
@@ -758,15 +1052,18 @@ int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias
   }
   if (do_pack) {
     const long long n = (long long)P.NSLAB * g.taps * P.f_HL * 2 * g.Cout;
-    pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL);
+    pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL, tr ? g0.taps : 0,
+                                              (tr && (flags & HEBB_F_WNRM)) ? inv : nullptr);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
 
   // ---- forward ----
   FwdParams f;
   f.xp[0] = xp0; f.xp[1] = xp1; f.wp = wp; f.rp[0] = rp0; f.rp[1] = rp1;
-  f.y = y; f.winner = winner; f.inv = (flags & HEBB_F_WNRM) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = err;
+  f.y = y; f.winner = winner; f.inv = ((flags & HEBB_F_WNRM) && !tr) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = err;
+  f.tr = tr ? 1 : 0; f.tD = g0.oD; f.tH = g0.oH; f.tW = g0.oW; f.CoutR = g0.Cout;
   f.Cout = g.Cout; f.CC = P.CC; f.NSLAB = P.NSLAB; f.taps = g.taps; f.nseg = P.f_nseg; f.HL = P.f_HL; f.RHL = P.d_HL;
+  f.stackF = P.stackF; f.CT = P.CT; f.n_ct = P.n_ct; f.fuse = (P.n_ct == 1 && !tr) ? 1 : 0;
   f.PA = P.PA; f.PR = P.PR; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
   f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC;
   f.WP = P.WP; f.plane = P.plane; f.Qimg = P.Qimg; f.oD = g.oD; f.oH = g.oH; f.oW = g.oW;
@@ -779,7 +1076,8 @@ int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias
       for (int kw = 0; kw < g.kW; ++kw, ++t) f.tap_off[t] = kh * P.WP + kw;
   f.x_stage_bytes = P.f_x_stage; f.w_stage_bytes = P.f_w_stage; f.off_w = P.f_off_w; f.off_misc = P.f_off_misc;
   f.tmem_cols = P.f_tmem;
-  const int fgrid = P.f_ntiles < num_sms() ? P.f_ntiles : num_sms();
+  const long long fwork = (long long)P.f_ntiles * P.n_ct;
+  const int fgrid = fwork < num_sms() ? (int)fwork : num_sms();
   if (!do_fwd) {
   } else if (g.Cout % 32 == 0) {
     HEBB_CUDA_TRY(cudaFuncSetAttribute(fwd_swta_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -789,6 +1087,19 @@ int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias
     fwd_swta_kernel<16><<<fgrid, 192, kSmemLimit, st>>>(f);
   }
   if (do_fwd) { HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED(); }
+  if (do_fwd && (P.n_ct > 1 || tr) && (upd || winner)) {
+    SmxParams sp;
+    sp.y = y; sp.rp[0] = rp0; sp.rp[1] = rp1; sp.winner = winner; sp.rsum = rsum;
+    sp.Cout = g.Cout; sp.RHL = P.d_HL; sp.WP = P.WP; sp.plane = P.plane; sp.Qimg = P.Qimg;
+    sp.oD = g.oD; sp.oH = g.oH; sp.oW = g.oW; sp.PR = P.PR; sp.PTOT = P.PTOT; sp.kinv = kinv;
+    if (tr) {
+      sp.Cout = g.Cout;
+      swta_softmax_pack_T_kernel<<<(unsigned)(P.PR / 128), 128, 0, st>>>(sp, g0.oD, g0.oH, g0.oW, g0.Cout);
+    } else {
+      swta_softmax_pack_kernel<<<(unsigned)(P.PR / 128), 128, 0, st>>>(sp);
+    }
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  }
   if (!do_dw) return HEBB_OK;
 
   // ---- dW ----
@@ -816,6 +1127,7 @@ int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias
     }
   }
   d.grp_tap_begin[P.ngrp] = g.taps;
+  d.stackM = P.stackM; d.stackN = P.stackN; d.cpt = P.cpt;
   d.CM = P.CM; d.n_cin_tiles = P.n_cin_tiles; d.CN = P.CN; d.n_cout_tiles = P.n_cout_tiles; d.ST = P.ST; d.CinP = P.CinP;
   d.stage_bytes = P.d_stage; d.x_bytes = P.d_x_bytes; d.off_bar = P.d_off_bar; d.tmem_cols = P.d_tmem;
   const int dgrid = P.ngrp * P.n_cin_tiles * P.n_cout_tiles * P.PS;
@@ -824,7 +1136,10 @@ int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   {
     const long long n = (long long)g.taps * g.Cin * g.Cout;
-    tc_finalize_kernel<<<ew_grid(n), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS, g.taps, g.Cin, P.CinP, g.Cout);
+    if (tr)
+      tc_finalize_T_kernel<<<ew_grid((long long)g0.Cin * g0.Cout), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g0.Cin, P.CinP, g0.Cout);
+    else
+      tc_finalize_kernel<<<ew_grid(n), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
   return HEBB_OK;

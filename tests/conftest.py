@@ -42,3 +42,22 @@ def golden():
 def golden_meta():
     with open(os.path.join(ROOT, 'tests', 'golden', 'makehebbian_golden.json')) as f:
         return json.load(f)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Dump the measured parity errors of the GPU tests (tests/helpers.py::record) for profiles/."""
+    try:
+        import helpers
+        if helpers.REPORT:
+            out = os.environ.get('HEBB_PARITY_REPORT', os.path.join(ROOT, 'gpurun_out', 'parity_report.json'))
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            old = {}
+            if os.path.exists(out):
+                with open(out) as f:
+                    old = json.load(f)
+            for k, v in helpers.REPORT.items():
+                old.setdefault(k, {}).update(v)
+            with open(out, 'w') as f:
+                json.dump(old, f, indent=1, sort_keys=True)
+    except Exception:
+        pass
