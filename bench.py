@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-layer-profile', action='store_true')
     ap.add_argument('--layers-out', default='', help='write the per-layer stage timings to this JSON file')
+    ap.add_argument('--no-fuse', action='store_true', help='keep stock BatchNorm/activation/Upsample modules (hebb.fused off)')
+    ap.add_argument('--head-nchw', action='store_true', help='keep the stock back-prop head in NCHW (default: channels_last)')
+    ap.add_argument('--cudnn-benchmark', action='store_true')
     return ap.parse_args()
 
 
@@ -69,7 +72,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------
-def build_model(workload, impl_ours, device):
+def build_model(workload, impl_ours, device, fuse=False):
     """Returns (model, make_batch(batch, seed, device), criterion)."""
     if workload == 'c1':
         if impl_ours:
@@ -104,6 +107,9 @@ def build_model(workload, impl_ours, device):
             from oracle import hebb_oracle as O
             O.oracle_makehebbian(net, exclude=excl, k=HEBB_PARAMS['k'], alpha=HEBB_PARAMS['alpha'])
     workloads.init_weights_like_reference(net)            # init_weights_unet(model,'kaiming') after surgery
+    if impl_ours and fuse:
+        from hebb.fused import fuse_norm_act
+        fuse_norm_act(net)                                # BatchNorm(train)+act and 2x bilinear up-sampling on our kernels
     return net.to(device).train(), batch, workloads.dice_loss
 
 
@@ -274,7 +280,11 @@ def run_ours(args):
         cpu = time_cpu_port(args.workload, cpu_b, 2 if args.workload != 'c4' else 1, 1 if args.workload != 'c4' else 0)
 
     torch.manual_seed(1234)
-    model, make_batch, crit = build_model(args.workload, True, dev)
+    model, make_batch, crit = build_model(args.workload, True, dev, fuse=not args.no_fuse)
+    if args.cudnn_benchmark:
+        torch.backends.cudnn.benchmark = True
+    if (not args.head_nchw) and hasattr(model, 'out_conv'):
+        model.out_conv.to(memory_format=torch.channels_last)
     lr = 1e-6 if args.workload != 'c4' else 1e-5
     opt = torch.optim.Adam(model.parameters(), lr=lr)
     stepper = HebbianStepper(model, opt, crit)
@@ -382,7 +392,9 @@ def run_ours(args):
             'data': 'synthetic',
             'config': {'workload': f'{args.workload}: {desc}', 'per_gpu_batch': B, 'global_batch': B * world,
                        'hebb_params': HEBB_PARAMS if args.workload != 'c1' else {'mode': 'swta', 'k': 3.0, 'alpha': 1.0},
-                       'optimizer': f'adam lr={lr}', 'precision_mode': args.prec, 'l2': 'flushed between timed steps (256 MB fill)',
+                       'optimizer': f'adam lr={lr}', 'precision_mode': args.prec,
+                       'fused_norm_act_upsample': (not args.no_fuse) and args.workload != 'c1',
+                       'backprop_head_memory_format': 'nchw' if (args.head_nchw or args.workload != 'c2') else 'channels_last', 'l2': 'flushed between timed steps (256 MB fill)',
                        'parallelism': f'dp{world} (batch shards, one all-reduce of delta_w per step)'},
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': e2e_ms / args.steps, 'last_loss': last},

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = ['api.cu', 'elementwise.cu', 'simt_path.cu', 'tc_path.cu']
+SRC = ['api.cu', 'elementwise.cu', 'simt_path.cu', 'tc_path.cu', 'norm_act.cu']
 OUT = os.path.join(HERE, 'hebb', 'libhebb_sm100.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -1,0 +1,186 @@
+// SURVEY.md §8(f) row 2 — the bandwidth-bound ops that sit between two Hebbian convolutions in the
+// reference's UNet blocks (models/networks_2d/unet.py:53-61,170-183; models/networks_3d/unet3d.py:97-125):
+//   BatchNorm(train) -> (Leaky)ReLU            : hebb_bn_stats + hebb_bn_act_apply   (2 reads + 1 write of y)
+//   Upsample(scale 2, bilinear, align_corners) : hebb_upsample2x_bilinear
+// They are opt-in (hebb/fused.py); the reference API surface is untouched.
+#include "common.cuh"
+
+namespace hebb {
+
+// Per-channel sum and sum of squares of y[B][C][S].  grid = (splits, C); each block reduces a
+// contiguous range of the B*S elements of its channel in fp32 and adds its partial in fp64.
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ y, double* __restrict__ sums, int C, long long S, long long BS,
+                long long per_block) {
+  const int c = blockIdx.y;
+  long long beg = (long long)blockIdx.x * per_block;
+  long long end = beg + per_block;
+  if (end > BS) end = BS;
+  float s1 = 0.f, s2 = 0.f;
+  const bool vec = ((S & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((per_block & 3) == 0);
+  if (vec) {
+    for (long long i = beg + 4LL * threadIdx.x; i < end; i += 4LL * blockDim.x) {
+      const long long b = i / S, s = i - b * S;
+      const float4 v = *reinterpret_cast<const float4*>(y + (b * C + c) * S + s);
+      s1 += (v.x + v.y) + (v.z + v.w);
+      s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  } else {
+    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      const long long b = i / S, s = i - b * S;
+      const float v = y[(b * C + c) * S + s];
+      s1 += v; s2 += v * v;
+    }
+  }
+  __shared__ float p1[8], p2[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((threadIdx.x & 31) == 0) { p1[threadIdx.x >> 5] = s1; p2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) { a += p1[i]; b += p2[i]; }
+    atomicAdd(sums + 2 * c, a);
+    atomicAdd(sums + 2 * c + 1, b);
+  }
+}
+
+// scale/shift per channel from the sums; also the running-stat update of nn.BatchNorm (momentum form)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale_shift,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   int C, double count, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[2 * c] / count;
+  double var = sums[2 * c + 1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale_shift[2 * c] = g * invstd;
+  scale_shift[2 * c + 1] = b - (float)mean * g * invstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// out = act(y * scale[c] + shift[c]), act(v) = v >= 0 ? v : slope * v   (slope 0 -> ReLU, 1 -> identity)
+__global__ void __launch_bounds__(256)
+bn_act_apply_kernel(const float* __restrict__ y, float* __restrict__ out, const float* __restrict__ scale_shift,
+                    int C, long long S, long long total, float slope) {
+  const bool vec = ((S & 3) == 0) && (((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    for (long long i = tid * 4; i < total; i += nth * 4) {
+      const int c = (int)((i / S) % C);
+      const float sc = __ldg(scale_shift + 2 * c), sh = __ldg(scale_shift + 2 * c + 1);
+      float4 v = *reinterpret_cast<const float4*>(y + i);
+      v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh); v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+      v.x = v.x >= 0.f ? v.x : v.x * slope; v.y = v.y >= 0.f ? v.y : v.y * slope;
+      v.z = v.z >= 0.f ? v.z : v.z * slope; v.w = v.w >= 0.f ? v.w : v.w * slope;
+      *reinterpret_cast<float4*>(out + i) = v;
+    }
+  } else {
+    for (long long i = tid; i < total; i += nth) {
+      const int c = (int)((i / S) % C);
+      float v = fmaf(y[i], scale_shift[2 * c], scale_shift[2 * c + 1]);
+      out[i] = v >= 0.f ? v : v * slope;
+    }
+  }
+}
+
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) on [N][H][W] planes (N = B*C).
+// One thread per output pixel pair; source coordinate = o * (in-1)/(out-1), like ATen's
+// area_pixel_compute_source_index(align_corners=true).
+__global__ void __launch_bounds__(256)
+upsample2x_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, long long N, int H, int W) {
+  const int OH = 2 * H, OW = 2 * W;
+  const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+  const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  const long long total = N * OH * (long long)W;      // each thread: output columns 2*w, 2*w+1
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long t = i / W;
+    const int oy = (int)(t % OH);
+    const long long n = t / OH;
+    const float fy = ry * oy;
+    const int y0 = (int)fy;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
+    const float ly = fy - y0, hy = 1.f - ly;
+    const float* r0 = in + (n * H + y0) * (long long)W;
+    const float* r1 = in + (n * H + y1) * (long long)W;
+    float o2[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int ox = 2 * w + k;
+      const float fx = rx * ox;
+      const int x0 = (int)fx;
+      const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
+      const float lx = fx - x0, hx = 1.f - lx;
+      o2[k] = hy * (hx * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) + ly * (hx * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
+    }
+    *reinterpret_cast<float2*>(out + (n * OH + oy) * (long long)OW + 2 * w) = make_float2(o2[0], o2[1]);
+  }
+}
+
+}  // namespace hebb
+
+using namespace hebb;
+
+extern "C" {
+
+int hebb_bn_act_train(const float* y, float* out, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, int64_t B, int64_t C, int64_t S, float eps, float momentum, float slope,
+                      void* ws, size_t ws_bytes, void* stream) {
+  HEBB_TRY(device_ok());
+  if (!y || !out || !ws) return HEBB_EARG;
+  if (B <= 0 || C <= 0 || S <= 0 || C > 65535) return HEBB_ESHAPE;
+  const size_t need = (size_t)C * (2 * sizeof(double) + 2 * sizeof(float));
+  if (ws_bytes < need) return HEBB_EWS;
+  if (reinterpret_cast<uintptr_t>(ws) & 15) return HEBB_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* sums = static_cast<double*>(ws);
+  float* ss = reinterpret_cast<float*>(sums + 2 * C);
+  HEBB_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(double), st));
+  const long long BS = B * S;
+  long long splits = ((long long)num_sms() * 8 + C - 1) / C;
+  const long long max_splits = cdiv(BS, 4096);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  long long per_block = cdiv(cdiv(BS, splits), 4) * 4;
+  splits = cdiv(BS, per_block);
+  dim3 grid((unsigned)splits, (unsigned)C);
+  bn_stats_kernel<<<grid, 256, 0, st>>>(y, sums, (int)C, S, BS, per_block);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  bn_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(sums, gamma, beta, ss, running_mean, running_var, (int)C,
+                                                             (double)BS, eps, momentum);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  const long long total = B * C * S;
+  long long gx = cdiv(total, 256 * 4 * 4);
+  const long long cap = (long long)num_sms() * 16;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  bn_act_apply_kernel<<<(unsigned)gx, 256, 0, st>>>(y, out, ss, (int)C, S, total, slope);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
+int hebb_upsample2x_bilinear(const float* in, float* out, int64_t N, int64_t H, int64_t W, void* stream) {
+  HEBB_TRY(device_ok());
+  if (!in || !out) return HEBB_EARG;
+  if (N <= 0 || H <= 0 || W <= 0 || H > (1 << 20) || W > (1 << 20)) return HEBB_ESHAPE;
+  const long long total = N * 2 * H * W;
+  long long gx = cdiv(total, 256 * 2);
+  const long long cap = (long long)num_sms() * 16;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  upsample2x_bilinear_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(in, out, N, (int)H, (int)W);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
+}  // extern "C"

@@ -24,6 +24,7 @@
 // out of TMEM (bias, y store, winner, softmax, bf16 split of r, column sums of r).
 #include "common.cuh"
 #include "umma.cuh"
+#include <cstdlib>
 
 namespace hebb {
 
@@ -761,20 +762,37 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
 }
 
 // delta_w[co][ci][t] += sum_s Hpart[s][t][ci][co] - rsum[co] * W[co][ci][t]
+// 256 threads = 8 split lanes x 32 consecutive outputs (co fastest -> coalesced partial reads); the
+// partials of one output are summed in a fixed order, so the result is deterministic.
 __global__ void __launch_bounds__(256)
 tc_finalize_kernel(const float* __restrict__ hpart, const float* __restrict__ rsum, const float* __restrict__ W,
                    float* __restrict__ dw, int PS, int taps, int Cin, int CinP, int Cout) {
+  __shared__ float red[8][33];
   const long long n = (long long)taps * Cin * Cout;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(idx % Cout);
-    long long t2 = idx / Cout;
-    const int ci = (int)(t2 % Cin);
-    const int t = (int)(t2 / Cin);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long plane = (long long)taps * CinP * Cout;
+  for (long long base = (long long)blockIdx.x * 32; base < n; base += (long long)gridDim.x * 32) {
+    const long long idx = base + tx;
     float acc = 0.f;
-    for (int s = 0; s < PS; ++s) acc += hpart[(((long long)s * taps + t) * CinP + ci) * Cout + co];
-    const long long wi = ((long long)co * Cin + ci) * taps + t;
-    dw[wi] += acc - rsum[co] * W[wi];
+    int co = 0, ci = 0, t = 0;
+    if (idx < n) {
+      co = (int)(idx % Cout);
+      const long long t2 = idx / Cout;
+      ci = (int)(t2 % Cin);
+      t = (int)(t2 / Cin);
+      const float* hp = hpart + ((long long)t * CinP + ci) * Cout + co;
+      for (int s = ty; s < PS; s += 8) acc += hp[(long long)s * plane];
+    }
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && idx < n) {
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += red[k][tx];
+      const long long wi = ((long long)co * Cin + ci) * taps + t;
+      dw[wi] += tot - rsum[co] * W[wi];
+    }
+    __syncthreads();
   }
 }
 
@@ -842,7 +860,11 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   q.f_HL = 2;                                   // forward is always split (exact winners)
   const int halo = (g.kH - 1) * q.WP + (g.kW - 1);
   q.f_nseg = g.kD;
-  q.stackF = (q.f_HL == 2 && q.CT <= 64 && !g.transposed) ? 1 : 0;
+  // Stacking [w_hi | w_lo] along N (2 MMAs instead of 3) measured SLOWER on B200 for every channel count
+  // (the doubled TMEM footprint halves the M-blocks per tile and doubles the epilogue's TMEM reads:
+  // profiles/README.md, "forward stacking"), so the planner keeps the 3-MMA form.  HEBB_STACKF=1 re-enables it.
+  static const bool want_stackf = [] { const char* e = getenv("HEBB_STACKF"); return e && e[0] == '1'; }();
+  q.stackF = (want_stackf && q.f_HL == 2 && q.CT <= 64 && !g.transposed) ? 1 : 0;
   const int fcw = (q.stackF ? 2 : 1) * q.CT;
   q.f_w_stage = (uint32_t)q.f_HL * 2 * q.CT * 16;
   const uint32_t misc = (uint32_t)(6 * q.CT * 4 + 8 * 64 + 64);
@@ -1139,7 +1161,12 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     if (tr)
       tc_finalize_T_kernel<<<ew_grid((long long)g0.Cin * g0.Cout), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g0.Cin, P.CinP, g0.Cout);
     else
-      tc_finalize_kernel<<<ew_grid(n), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
+    {
+      long long gx = cdiv(n, 32);
+      const long long cap = (long long)num_sms() * 32;
+      if (gx > cap) gx = cap;
+      tc_finalize_kernel<<<(unsigned)gx, 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
+    }
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
   return HEBB_OK;

@@ -25,7 +25,7 @@ EXPORTS = [
     'hebb_query', 'hebb_status_str', 'hebb_last_cuda_error', 'hebb_version', 'hebb_out_shape',
     'hebb_workspace_bytes', 'hebb_wnorm', 'hebb_conv_swta_step', 'hebb_convT_swta_step',
     'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
-    'hebb_debug_umma_rate', 'hebb_debug_plan',
+    'hebb_debug_umma_rate', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_upsample2x_bilinear',
 ]
 
 
@@ -75,6 +75,8 @@ def load():
                                               i32, i32, i32, vp, vp]
         lib.hebb_debug_umma_rate.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
                                              ctypes.c_uint32, ctypes.c_uint32, i32, i32, i32, i32, vp, vp]
+        lib.hebb_bn_act_train.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, vp, ctypes.c_size_t, vp]
+        lib.hebb_upsample2x_bilinear.argtypes = [vp, vp, i64, i64, i64, vp]
         lib.hebb_debug_launch_count.restype = ctypes.c_ulonglong
         lib.hebb_uses_tensor_cores.argtypes = [ctypes.POINTER(HebbDesc), i32]
         for name in EXPORTS:
@@ -226,6 +228,29 @@ def plan(desc: HebbDesc, prec: int):
     out = (ctypes.c_int * 32)()
     n = load().hebb_debug_plan(ctypes.byref(desc), int(prec), out, 32)
     return dict(zip(PLAN_FIELDS, list(out)[:n])) if n else None
+
+
+def bn_act_train(y, gamma, beta, running_mean, running_var, eps, momentum, slope, out=None):
+    """BatchNorm(train) + (Leaky)ReLU on a contiguous [B, C, *spatial] fp32 CUDA tensor (hebb_bn_act_train)."""
+    _require_cuda(y, 'input')
+    B, C = y.shape[0], y.shape[1]
+    S = y.numel() // (B * C)
+    if out is None:
+        out = torch.empty_like(y)
+    ws = workspace(y.device, C * 24 + 64)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    check(load().hebb_bn_act_train(y.data_ptr(), out.data_ptr(), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                   B, C, S, float(eps), float(momentum), float(slope), ws.data_ptr(), ws.numel(),
+                                   _stream_ptr(y.device)), 'bn_act_train')
+    return out
+
+
+def upsample2x_bilinear(x):
+    _require_cuda(x, 'input')
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, 2 * H, 2 * W), dtype=x.dtype, device=x.device)
+    check(load().hebb_upsample2x_bilinear(x.data_ptr(), out.data_ptr(), B * C, H, W, _stream_ptr(x.device)), 'upsample2x')
+    return out
 
 
 def launch_count() -> int:

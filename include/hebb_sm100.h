@@ -118,6 +118,21 @@ int hebb_convT_swta_step(const HebbDesc* d, const float* x, const float* W, cons
 int hebb_local_update_multi(int n, float* const* grad, float* const* dw, const int64_t* numel,
                             const float* alpha, const int32_t* has_grad, void* stream);
 
+/* ---- the bandwidth-bound ops between two Hebbian convs (opt-in, hebb/fused.py) ---- */
+
+/* nn.BatchNorm{2,3}d in TRAINING mode fused with (Leaky)ReLU — models/networks_2d/unet.py:53-61, unet3d.py:97-125:
+ *   out = act((y - mean_c) / sqrt(var_c + eps) * gamma_c + beta_c),  act(v) = v >= 0 ? v : slope*v
+ * (slope 0 = ReLU, 0.01 = LeakyReLU default, 1 = no activation); batch statistics over (B, S) per channel,
+ * biased variance for the normalisation, running_mean/var (nullable) updated with `momentum` and the unbiased
+ * variance exactly like torch.  y,out: [B][C][S] fp32 (out may alias y).  ws: >= C*24 bytes, 16-byte aligned. */
+int hebb_bn_act_train(const float* y, float* out, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, int64_t B, int64_t C, int64_t S, float eps, float momentum, float slope,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) — models/networks_2d/unet.py:171-172.
+ * in: [N][H][W], out: [N][2H][2W] fp32, N = batch*channels. */
+int hebb_upsample2x_bilinear(const float* in, float* out, int64_t N, int64_t H, int64_t W, void* stream);
+
 /* ---- exported for tests and profiling ---- */
 
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */

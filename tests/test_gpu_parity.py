@@ -343,3 +343,58 @@ def test_backprop_through_layer_when_alpha_below_one():
     gbp = layer.weight.grad.clone()
     layer.local_update()
     assert relerr(layer.weight.grad, 0.5 * gbp - 0.5 * dw) < 1e-6
+
+
+# ---- fused BatchNorm(train)+activation and 2x bilinear up-sampling ----
+@pytest.mark.parametrize('shape,slope', [((4, 16, 33, 20), 0.01), ((3, 7, 9, 5, 6), 0.0), ((64, 16, 64, 64), 0.01), ((2, 32, 8, 8), 1.0)])
+def test_fused_bn_act_matches_torch(shape, slope):
+    import torch.nn as nn
+    from hebb import _native as N
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(shape, generator=g) * 2.0 + 0.7).to(DEV)
+    C = shape[1]
+    bn = (nn.BatchNorm2d if len(shape) == 4 else nn.BatchNorm3d)(C).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(C, generator=g).to(DEV)); bn.bias.copy_(torch.randn(C, generator=g).to(DEV))
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    want = bn(x)
+    want = want if slope == 1.0 else torch.nn.functional.leaky_relu(want, slope)
+    got = N.bn_act_train(x, bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, bn.momentum, slope)
+    assert relerr(got, want) < 2e-6
+    assert relerr(rm, bn.running_mean) < 1e-6 and relerr(rv, bn.running_var) < 1e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 5, 7), (4, 16, 32, 32), (1, 1, 1, 1), (2, 8, 1, 9)])
+def test_upsample2x_matches_torch(shape):
+    from hebb import _native as N
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(4)).to(DEV)
+    want = torch.nn.functional.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)
+    got = N.upsample2x_bilinear(x)
+    assert got.shape == want.shape and float((got - want).abs().max()) < 2e-6
+
+
+def test_fuse_pass_keeps_network_output_and_state():
+    from hebb.fused import fuse_norm_act
+    torch.manual_seed(0)
+    net = workloads.unet2d(3, 2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        makehebbian(net, exclude=workloads.EXCLUDE_2D, hebb_params={'mode': 'swta_t', 'k': 50., 'w_nrm': True, 'alpha': 1.})
+    workloads.deterministic_state_(net)
+    workloads.disable_dropout_(net)
+    import copy
+    ref = copy.deepcopy(net).to(DEV).train()
+    keys = list(net.state_dict().keys())
+    fuse_norm_act(net)
+    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4}
+    net = net.to(DEV).train()
+    x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(5)).to(DEV)
+    a, b = ref(x), net(x)
+    assert relerr(b, a) < 1e-3          # 18 BatchNorms with 1e-6 rounding differences, 22 layers deep
+    for (n1, m1), (n2, m2) in zip(ref.named_modules(), net.named_modules()):
+        if hasattr(m1, 'local_update'):
+            assert relerr(m2.delta_w, m1.delta_w) < 2e-3, n1      # BN rounding differences feed the next layer
+        if isinstance(m1, torch.nn.BatchNorm2d):
+            assert relerr(m2.running_var, m1.running_var) < 1e-4 and int(m2.num_batches_tracked) == 1
+    net.eval()
+    ref.eval()
+    assert relerr(net(x), ref(x)) < 1e-3       # eval mode takes the stock path (running stats differ by rounding)
