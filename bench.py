@@ -329,15 +329,37 @@ def run_ours(args):
     value = B * world * args.steps / (dev_ms / 1e3)
 
     # ---- e2e: host (pinned) inputs in, loss out, every step ----
+    # The public-API loop a user writes: every step's batch is copied from pinned host memory (on a side
+    # stream, double-buffered so step i+1's copy overlaps step i's compute) and the loss is read back.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(x, m), (torch.empty_like(x), torch.empty_like(m) if m is not None else None)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        xb, mb = bufs[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[i % 2])          # the step that last read this buffer is done
+            xb.copy_(x_pin, non_blocking=True)
+            if mb is not None:
+                mb.copy_(m_pin, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
     sync_all()
+    cur = torch.cuda.current_stream(dev)
+    for ev in freed:
+        ev.record(cur)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     last = 0.0
-    for _ in range(args.steps):
-        x.copy_(x_pin, non_blocking=True)
-        if m is not None:
-            m.copy_(m_pin, non_blocking=True)
-        out, loss = stepper.step(x, m)
+    prefetch(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            prefetch(i + 1)
+        cur.wait_event(ready[i % 2])
+        xb, mb = bufs[i % 2]
+        out, loss = stepper.step(xb, mb)
+        freed[i % 2].record(cur)
         last = float(loss.item()) if loss is not None else float(out.flatten()[0].item())
     s1.record()
     sync_all()

@@ -178,17 +178,17 @@ __device__ __forceinline__ void ld_acc(uint32_t a, int second, uint32_t (&v)[CH]
 }
 
 template <int CH>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 fwd_swta_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
-  // misc region: [inv Cout][bias Cout][rs 4*Cout] floats, then barriers, then tmem ptr
+  // misc region: [inv CT][bias CT][rs 8*CT] floats, then barriers, then tmem ptr
   float* s_inv = reinterpret_cast<float*>(smem + p.off_misc);
   float* s_bias = s_inv + p.CT;
   float* s_rs = s_bias + p.CT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rs + 4 * p.CT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rs + 8 * p.CT);
   const int total_work = p.ntiles * p.n_ct;      // work item = (position tile, output-channel tile)
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t x_full = bar0, x_empty = x_full + 8 * p.XST;
@@ -196,7 +196,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
   const uint32_t t_full = w_empty + 8 * p.WST, t_empty = t_full + 8 * p.NACC;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * p.XST + 2 * p.WST + 2 * p.NACC);
 
-  for (int i = threadIdx.x; i < 4 * p.CT; i += blockDim.x) s_rs[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * p.CT; i += blockDim.x) s_rs[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.XST; ++i) { mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 1); }
     for (int i = 0; i < p.WST; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
@@ -307,25 +307,32 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9): two sets of four =====================
+    // A warp may only read its own TMEM lane quadrant (warp % 4), so the second set of four warps does not
+    // split rows: with two accumulator buffers set h drains buffer h, i.e. the sets alternate work items and
+    // each SM sub-partition has two epilogue warps to hide the tcgen05.ld / MUFU / store latencies.
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
     const int ew = warp - 2;
+    const int eset = ew >> 2;
     const int row = quad * 32 + lane;
     const long long outS = (long long)p.oD * p.oH * p.oW;
     const int oHW = p.oH * p.oW;
     float* my_rs = s_rs + ew * p.CT;
-    int acc = 0; uint32_t aph = 0;
+    uint32_t aph = 0;
     int cur_ct = -1;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+    int it = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+      const int acc = (p.NACC == 2) ? (it & 1) : 0;
+      if (acc != eset) continue;            // the other set's buffer (NACC == 1: set 1 has nothing to do)
       const int tile = work / p.n_ct, ct = work - tile * p.n_ct;
       const int cbase = ct * p.CT;
-      if (ct != cur_ct) {      // (re)load this channel tile's 1/|W| and bias; only the 4 epilogue warps use them
-        asm volatile("bar.sync 1, 128;");
-        for (int i = threadIdx.x - 64; i < p.CT; i += 128) {
+      if (ct != cur_ct) {      // (re)load this channel tile's 1/|W| and bias
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eset));
+        for (int i = (int)threadIdx.x - 64 - eset * 128; i < p.CT; i += 128) {
           s_inv[i] = p.inv ? p.inv[cbase + i] : 1.f;
           s_bias[i] = p.bias ? p.bias[p.tr ? ((cbase + i) >> 3) : (cbase + i)] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eset));
         cur_ct = ct;
       }
       mbar_wait(t_full + 8 * acc, aph, p.err, 6);
@@ -417,7 +424,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty + 8 * acc);
-      if (++acc == p.NACC) { acc = 0; aph ^= 1; }
+      aph ^= 1;                             // this set's buffer is reused every NACC-th item
     }
     __syncwarp();
     if (p.fuse && p.write_r)
@@ -867,7 +874,7 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   q.stackF = (want_stackf && q.f_HL == 2 && q.CT <= 64 && !g.transposed) ? 1 : 0;
   const int fcw = (q.stackF ? 2 : 1) * q.CT;
   q.f_w_stage = (uint32_t)q.f_HL * 2 * q.CT * 16;
-  const uint32_t misc = (uint32_t)(6 * q.CT * 4 + 8 * 64 + 64);
+  const uint32_t misc = (uint32_t)(10 * q.CT * 4 + 8 * 64 + 64);
   bool found = false;
   for (int mb = 4; mb >= 1 && !found; mb >>= 1) {
     if (mb > 1 && mb * fcw > 256) continue;
@@ -1103,10 +1110,10 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   if (!do_fwd) {
   } else if (g.Cout % 32 == 0) {
     HEBB_CUDA_TRY(cudaFuncSetAttribute(fwd_swta_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    fwd_swta_kernel<32><<<fgrid, 192, kSmemLimit, st>>>(f);
+    fwd_swta_kernel<32><<<fgrid, 320, kSmemLimit, st>>>(f);
   } else {
     HEBB_CUDA_TRY(cudaFuncSetAttribute(fwd_swta_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    fwd_swta_kernel<16><<<fgrid, 192, kSmemLimit, st>>>(f);
+    fwd_swta_kernel<16><<<fgrid, 320, kSmemLimit, st>>>(f);
   }
   if (do_fwd) { HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED(); }
   if (do_fwd && (P.n_ct > 1 || tr) && (upd || winner)) {
