@@ -114,7 +114,9 @@ int hebb_workspace_bytes(const HebbDesc* d, int prec, size_t* bytes) {
   HEBB_TRY(resolve_geo(d, &g));
   if (!bytes) return HEBB_EARG;
   if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
-  *bytes = use_tc(g, prec) ? tc_workspace_bytes(g, prec) : simt_workspace_bytes(g);
+  // the CUDA-core scratch is also what the HPCA rule uses, whatever the precision mode
+  const size_t a = use_tc(g, prec) ? tc_workspace_bytes(g, prec) : 0, b = simt_workspace_bytes(g);
+  *bytes = a > b ? a : b;
   return HEBB_OK;
 }
 
@@ -151,7 +153,8 @@ int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const
   if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
   if (!aligned16(ws)) return HEBB_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(g, prec)) return tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, st);
+  if (use_tc(g, prec) && !(flags & HEBB_F_RULE_HPCA))
+    return tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, st);
   return simt_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, st);
 }
 
@@ -166,7 +169,7 @@ int hebb_convT_swta_step(const HebbDesc* d, const float* x, const float* W, cons
   if ((flags & HEBB_F_UPDATE) && !delta_w) return HEBB_EARG;
   if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
   if (!aligned16(ws)) return HEBB_EALIGN;
-  if (use_tc(g, prec))
+  if (use_tc(g, prec) && !(flags & HEBB_F_RULE_HPCA))
     return tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, (cudaStream_t)stream);
   return simt_convT_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, (cudaStream_t)stream);
 }

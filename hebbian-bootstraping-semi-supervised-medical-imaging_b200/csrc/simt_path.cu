@@ -169,6 +169,86 @@ struct ConvTDw {
   }
 };
 
+// ---- HPCA (Sanger / generalised Hebbian rule), hebb/hebb.py:122-135, hebb/hebb3d.py:139-153 ----
+//   delta_w += y X - (tril(y y^T)) W        (patchwise; y = the layer output incl. bias)
+// G = y y^T  [Cout x Cout], contraction over pixels
+struct YYt {
+  DevGeo g; const float* y; float* G;
+  static constexpr bool kAMajorM = false;
+  static constexpr bool kBMajorK = true;
+  static constexpr bool kAtomic = true;
+  __device__ long long M() const { return g.Cout; }
+  __device__ int N() const { return g.Cout; }
+  __device__ long long Kd() const { return (long long)g.B * g.outS; }
+  __device__ float a(long long m, long long p) const {
+    const long long bb = p / g.outS;
+    return __ldg(y + (bb * g.Cout + m) * g.outS + (p - bb * g.outS));
+  }
+  __device__ float b(long long p, int n) const {
+    const long long bb = p / g.outS;
+    return __ldg(y + (bb * g.Cout + n) * g.outS + (p - bb * g.outS));
+  }
+  __device__ void store(long long m, int n, float v) const { atomicAdd(G + m * g.Cout + n, v); }
+};
+
+// delta_w[c][j] += H[c][j] - sum_{c' <= c} G[c][c'] W[c'][j]      (H is [Cout][K+1])
+struct HpcaDecay {
+  DevGeo g; const float* G; const float* W; const float* H; float* dw;
+  static constexpr bool kAMajorM = false;
+  static constexpr bool kBMajorK = false;
+  static constexpr bool kAtomic = false;
+  __device__ long long M() const { return g.Cout; }
+  __device__ int N() const { return g.K; }
+  __device__ long long Kd() const { return g.Cout; }
+  __device__ float a(long long m, long long c) const { return c <= m ? __ldg(G + m * g.Cout + c) : 0.f; }
+  __device__ float b(long long c, int n) const { return __ldg(W + c * g.K + n); }
+  __device__ void store(long long m, int n, float v) const {
+    dw[m * g.K + n] += __ldg(H + m * (g.K + 1) + n) - v;
+  }
+};
+
+// Transposed layers in mode 'hpca' use the conv rule with x and y exchanged (hebb.py:243-246): the layer
+// INPUT is the response, the unfolded OUTPUT is the presynaptic patch.
+// G = x x^T  [Cin x Cin], contraction over input pixels
+struct XXt {
+  DevGeo g; const float* x; float* G;
+  static constexpr bool kAMajorM = false;
+  static constexpr bool kBMajorK = true;
+  static constexpr bool kAtomic = true;
+  __device__ long long M() const { return g.Cin; }
+  __device__ int N() const { return g.Cin; }
+  __device__ long long Kd() const { return (long long)g.B * g.inS; }
+  __device__ float a(long long m, long long p) const {
+    const long long bb = p / g.inS;
+    return __ldg(x + (bb * g.Cin + m) * g.inS + (p - bb * g.inS));
+  }
+  __device__ float b(long long p, int n) const {
+    const long long bb = p / g.inS;
+    return __ldg(x + (bb * g.Cin + n) * g.inS + (p - bb * g.inS));
+  }
+  __device__ void store(long long m, int n, float v) const { atomicAdd(G + m * g.Cin + n, v); }
+};
+
+// delta_w[co][ci][off] += H[ci][(co,off)] - sum_{ci' <= ci} G[ci][ci'] W[co][ci'][off]   (H is [Cin+1][Cout*taps])
+struct HpcaDecayT {
+  DevGeo g; const float* G; const float* W; const float* H; float* dw;
+  static constexpr bool kAMajorM = false;
+  static constexpr bool kBMajorK = true;
+  static constexpr bool kAtomic = false;
+  __device__ long long M() const { return g.Cin; }
+  __device__ int N() const { return g.Cout * g.taps; }
+  __device__ long long Kd() const { return g.Cin; }
+  __device__ float a(long long m, long long c) const { return c <= m ? __ldg(G + m * g.Cin + c) : 0.f; }
+  __device__ float b(long long c, int n) const {
+    const int co = n / g.taps, off = n - co * g.taps;
+    return __ldg(W + ((long long)co * g.Cin + c) * g.taps + off);
+  }
+  __device__ void store(long long m, int n, float v) const {
+    const int co = n / g.taps, off = n - co * g.taps;
+    dw[((long long)co * g.Cin + m) * g.taps + off] += __ldg(H + m * ((long long)g.Cout * g.taps) + n) - v;
+  }
+};
+
 constexpr int BM = 64, BN = 64, BK = 16;
 
 template <class Prob>
@@ -338,7 +418,7 @@ static long long pick_splits(long long tiles, long long Kd, int sms) {
 }
 
 // workspace: [inv_norm (max(Cout,Cin))] [r: B*Cout*outS] [H: (Cout*(K+1)) or ((Cin+1)*Cout*taps)]
-struct SimtWs { float* inv; float* r; float* H; size_t h_bytes; };
+struct SimtWs { float* inv; float* r; float* H; size_t h_bytes; float* G; };
 
 static size_t h_elems(const Geo& g) {
   return g.transposed ? (size_t)(g.Cin + 1) * g.Cout * g.taps : (size_t)g.Cout * (g.K + 1);
@@ -348,7 +428,9 @@ size_t simt_workspace_bytes(const Geo& g) {
   size_t inv = align_up(sizeof(float) * (size_t)(g.Cout > g.Cin ? g.Cout : g.Cin), 256);
   size_t r = align_up(sizeof(float) * (size_t)g.B * g.Cout * g.outS, 256);
   size_t H = align_up(sizeof(float) * h_elems(g), 256);
-  return inv + r + H;
+  const size_t gd = g.transposed ? g.Cin : g.Cout;
+  size_t G = align_up(sizeof(float) * gd * gd, 256);                      // HPCA only
+  return inv + r + H + G;
 }
 
 static int carve(const Geo& g, void* ws, size_t ws_bytes, SimtWs* o) {
@@ -360,6 +442,8 @@ static int carve(const Geo& g, void* ws, size_t ws_bytes, SimtWs* o) {
   p += align_up(sizeof(float) * (size_t)g.B * g.Cout * g.outS, 256);
   o->H = reinterpret_cast<float*>(p);
   o->h_bytes = sizeof(float) * h_elems(g);
+  p += align_up(o->h_bytes, 256);
+  o->G = reinterpret_cast<float*>(p);
   return HEBB_OK;
 }
 
@@ -383,20 +467,36 @@ int simt_conv_step(const Geo& g, const float* x, const float* W, const float* bi
   dim3 grid((unsigned)cdiv(P, BM), (unsigned)cdiv(g.Cout, BN));
   simt_gemm_pixfast_kernel<ConvFwd><<<grid, 256, 0, st>>>(f);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-  if (upd || winner) {
-    swta_softmax_kernel<<<softmax_grid(P), 256, 0, st>>>(y, upd ? w.r : nullptr, winner, P, g.Cout, g.outS, kinv);
+  const bool hpca = (flags & HEBB_F_RULE_HPCA) != 0;
+  if ((upd && !hpca) || winner) {
+    swta_softmax_kernel<<<softmax_grid(P), 256, 0, st>>>(y, (upd && !hpca) ? w.r : nullptr, winner, P, g.Cout, g.outS, kinv);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
   if (upd) {
     HEBB_CUDA_TRY(cudaMemsetAsync(w.H, 0, w.h_bytes, st));
-    ConvDw d{dg, x, w.r, w.H};
+    ConvDw d{dg, x, hpca ? y : w.r, w.H};       // HPCA: the response is y itself (hebb.py:127)
     const long long tiles = cdiv(g.Cout, BM) * cdiv(g.K + 1, BN);
     const long long splits = pick_splits(tiles, P, num_sms());
     long long kps = cdiv(cdiv(P, splits), BK) * BK;
     dim3 g2((unsigned)cdiv(g.Cout, BM), (unsigned)cdiv(g.K + 1, BN), (unsigned)cdiv(P, kps));
     simt_gemm_kernel<ConvDw><<<g2, 256, 0, st>>>(d, kps);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-    HEBB_TRY(launch_finalize_conv(w.H, W, delta_w, g.Cout, g.K, st));
+    if (!hpca) {
+      HEBB_TRY(launch_finalize_conv(w.H, W, delta_w, g.Cout, g.K, st));
+    } else {
+      HEBB_CUDA_TRY(cudaMemsetAsync(w.G, 0, sizeof(float) * (size_t)g.Cout * g.Cout, st));
+      YYt yy{dg, y, w.G};
+      const long long t2 = cdiv(g.Cout, BM) * cdiv(g.Cout, BN);
+      const long long sp2 = pick_splits(t2, P, num_sms());
+      long long kps2 = cdiv(cdiv(P, sp2), BK) * BK;
+      dim3 g3((unsigned)cdiv(g.Cout, BM), (unsigned)cdiv(g.Cout, BN), (unsigned)cdiv(P, kps2));
+      simt_gemm_kernel<YYt><<<g3, 256, 0, st>>>(yy, kps2);
+      HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+      HpcaDecay hd{dg, w.G, W, w.H, delta_w};
+      dim3 g4((unsigned)cdiv(g.Cout, BM), (unsigned)cdiv(g.K, BN), 1);
+      simt_gemm_kernel<HpcaDecay><<<g4, 256, 0, st>>>(hd, (long long)cdiv(g.Cout, BK) * BK);
+      HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+    }
   }
   return HEBB_OK;
 }
@@ -417,13 +517,14 @@ int simt_convT_step(const Geo& g, const float* x, const float* W, const float* b
   dim3 grid((unsigned)cdiv(Pout, BM), (unsigned)cdiv(g.Cout, BN));
   simt_gemm_pixfast_kernel<ConvTFwd><<<grid, 256, 0, st>>>(f);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-  if (upd || winner) {
-    swta_softmax_kernel<<<softmax_grid(Pout), 256, 0, st>>>(y, upd ? w.r : nullptr, winner, Pout, g.Cout, g.outS, kinv);
+  const bool hpca = (flags & HEBB_F_RULE_HPCA) != 0;
+  if ((upd && !hpca) || winner) {
+    swta_softmax_kernel<<<softmax_grid(Pout), 256, 0, st>>>(y, (upd && !hpca) ? w.r : nullptr, winner, Pout, g.Cout, g.outS, kinv);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
   if (upd) {
     HEBB_CUDA_TRY(cudaMemsetAsync(w.H, 0, w.h_bytes, st));
-    ConvTDw d{dg, x, w.r, w.H};
+    ConvTDw d{dg, x, hpca ? y : w.r, w.H};
     const int N = g.Cout * g.taps;
     const long long tiles = cdiv(g.Cin + 1, BM) * cdiv(N, BN);
     const long long splits = pick_splits(tiles, Pin, num_sms());
@@ -431,7 +532,23 @@ int simt_convT_step(const Geo& g, const float* x, const float* W, const float* b
     dim3 g2((unsigned)cdiv(g.Cin + 1, BM), (unsigned)cdiv(N, BN), (unsigned)cdiv(Pin, kps));
     simt_gemm_kernel<ConvTDw><<<g2, 256, 0, st>>>(d, kps);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-    HEBB_TRY(launch_finalize_convT(w.H, W, delta_w, g.Cin, g.Cout, g.taps, st));
+    if (!hpca) {
+      HEBB_TRY(launch_finalize_convT(w.H, W, delta_w, g.Cin, g.Cout, g.taps, st));
+    } else {
+      const long long Px = (long long)g.B * g.inS;
+      HEBB_CUDA_TRY(cudaMemsetAsync(w.G, 0, sizeof(float) * (size_t)g.Cin * g.Cin, st));
+      XXt xx{dg, x, w.G};
+      const long long t2 = cdiv(g.Cin, BM) * cdiv(g.Cin, BN);
+      const long long sp2 = pick_splits(t2, Px, num_sms());
+      long long kps2 = cdiv(cdiv(Px, sp2), BK) * BK;
+      dim3 g3((unsigned)cdiv(g.Cin, BM), (unsigned)cdiv(g.Cin, BN), (unsigned)cdiv(Px, kps2));
+      simt_gemm_kernel<XXt><<<g3, 256, 0, st>>>(xx, kps2);
+      HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+      HpcaDecayT hd{dg, w.G, W, w.H, delta_w};
+      dim3 g4((unsigned)cdiv(g.Cin, BM), (unsigned)cdiv(N, BN), 1);
+      simt_gemm_kernel<HpcaDecayT><<<g4, 256, 0, st>>>(hd, (long long)cdiv(g.Cin, BK) * BK);
+      HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+    }
   }
   return HEBB_OK;
 }

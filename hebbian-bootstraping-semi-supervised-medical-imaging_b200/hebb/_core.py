@@ -194,6 +194,8 @@ class _HebbianConvNd(nn.Module):
         tmp_dw = None
         if update:
             flags |= _native.F_UPDATE
+            if self.mode == self.MODE_HPCA:
+                flags |= _native.F_RULE_HPCA
             dw = self._raw(self.delta_w)
             if dw is None:
                 tmp_dw = torch.zeros_like(w)
@@ -236,6 +238,9 @@ class _HebbianConvNd(nn.Module):
         if self.mode not in valid:
             raise NotImplementedError("Learning mode {} unavailable for {} layer".format(self.mode, self.__class__.__name__))
         native = self.MODE_SWTA_T if self._transposed else self.MODE_SWTA
+        if self.mode == self.MODE_HPCA and self.patchwise:
+            return                      # HPCA (transposed layers: the conv rule with x and y exchanged,
+                                        # hebb.py:243-246): fp32 CUDA-core kernels (HEBB_F_RULE_HPCA)
         if self.mode != native or not self.patchwise:
             raise NotImplementedError(
                 "Learning mode {} (patchwise={}) of {} is not built into libhebb_sm100 yet; the sm_100 library "

@@ -18,7 +18,7 @@ _LIB_PATH = os.path.join(_HERE, 'libhebb_sm100.so')
 
 PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 _PREC_NAMES = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'fp32x3': PREC_BF16X3, 'bf16': PREC_BF16}
-F_UPDATE, F_WNRM = 1, 2
+F_UPDATE, F_WNRM, F_RULE_HPCA = 1, 2, 4
 F_ONLY_PACK, F_ONLY_FWD, F_ONLY_DW = 0x100, 0x200, 0x400
 
 EXPORTS = [

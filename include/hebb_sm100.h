@@ -63,6 +63,8 @@ typedef struct HebbDesc {
 /* flags for hebb_conv_swta_step / hebb_convT_swta_step */
 #define HEBB_F_UPDATE 1u   /* also accumulate the plasticity update into delta_w */
 #define HEBB_F_WNRM   2u   /* divide each filter by its L2 norm (w_nrm=True) */
+#define HEBB_F_RULE_HPCA 4u /* plasticity rule = HPCA / Sanger (hebb/hebb.py:122-135): delta_w += y X - tril(y y^T) W,
+                              * patchwise; runs on the fp32 CUDA-core kernels whatever `prec` says */
 /* Profiling aids (tensor-core path only): re-run ONE stage of the step on the scratch a
  * preceding full call with the same arguments left in `ws`; outputs are rewritten. */
 #define HEBB_F_ONLY_PACK 0x100u   /* filter norms + bf16 packing of x and W */

@@ -133,6 +133,33 @@ def swta_delta(xp, y, weight, k, stride):
 
 
 # --------------------------------------------------------------------------
+# 8f-1  HPCA / Sanger delta (patchwise)  hebb/hebb.py:122-135, hebb/hebb3d.py:139-153
+# --------------------------------------------------------------------------
+def hpca_delta(xp, y, weight, stride):
+    """dW = y X - tril(y y^T) W : the response is the layer output itself, the decay couples
+    filter c to every filter c' <= c (generalised Hebbian algorithm)."""
+    kernel = tuple(weight.shape[2:])
+    X = patch_matrix(xp, kernel, stride)
+    r = y.transpose(0, 1).reshape(y.shape[1], -1)
+    C = weight.shape[0]
+    low = torch.tril(torch.ones(C, C, dtype=weight.dtype))
+    w2 = weight.reshape(C, -1)
+    return (r @ X - ((r @ r.t()) * low) @ w2).reshape(weight.shape)
+
+
+def hpca_exchanged_delta(x, y, weight, stride):
+    """Transposed layer in mode 'hpca' (hebb.py:243-246): the plain-conv rule with the roles of x and y
+    swapped — response = the layer INPUT x, patches = unfold(OUTPUT y); weight is the (Cin, Cout, k...) view."""
+    kernel = tuple(weight.shape[2:])
+    Y = patch_matrix(y, kernel, stride)                  # (P, Cout*taps)
+    r = x.transpose(0, 1).reshape(x.shape[1], -1)        # (Cin, P)
+    C = weight.shape[0]
+    low = torch.tril(torch.ones(C, C, dtype=weight.dtype))
+    w2 = weight.reshape(C, -1)
+    return (r @ Y - ((r @ r.t()) * low) @ w2).reshape(weight.shape)
+
+
+# --------------------------------------------------------------------------
 # a9  transposed SWTA delta              hebb/hebb.py:252-264, hebb/hebb3d.py:276-289
 # --------------------------------------------------------------------------
 def swta_t_delta(x, y, weight, k, stride):

@@ -97,6 +97,37 @@ def main():
         meta[name] = dict(kind='conv', nd=nd, B=B, Cin=Cin, Cout=Cout, kernel=kernel, stride=stride,
                           padding=padding, spatial=list(spatial), k=k, bias=bias)
 
+    # HPCA rule (the mode the reference's own test_makehebbian3d exercises)
+    for (name, nd, B, Cin, Cout, kernel, padding, spatial, bias) in [
+            ('hpca2d_3_8', 2, 2, 3, 8, 3, 1, (10, 12), False), ('hpca2d_16_16', 2, 2, 16, 16, 3, 1, (12, 10), True),
+            ('hpca3d_8_16', 3, 1, 8, 16, 3, 1, (5, 6, 7), False), ('hpca3d_40_8', 3, 1, 40, 8, 1, 0, (4, 4, 5), False)]:
+        cls = ref.HebbianConv2d if nd == 2 else ref.HebbianConv3d
+        layer = cls(Cin, Cout, kernel, stride=1, padding=padding, bias=bias, w_nrm=True, mode='hpca', k=1.,
+                    patchwise=True, alpha=1.)
+        with torch.no_grad():
+            layer.weight.copy_(rnd(*layer.weight.shape, scale=0.3))
+            if bias:
+                layer.bias.copy_(rnd(Cout, scale=0.1))
+        layer.train()
+        x = rnd(B, Cin, *spatial)
+        y = layer(x)
+        out[name + '/x'], out[name + '/w'], out[name + '/b'] = x.numpy(), layer.weight.detach().numpy(), layer.bias.detach().numpy()
+        out[name + '/y'], out[name + '/dw1'] = y.detach().numpy(), layer.delta_w.clone().numpy()
+        meta[name] = dict(kind='hpca', nd=nd, B=B, Cin=Cin, Cout=Cout, kernel=kernel, stride=1, padding=padding,
+                          spatial=list(spatial), bias=bias)
+
+    for (name, nd, B, Cin, Cout, spatial) in [('hpcaT2d_6_4', 2, 2, 6, 4, (5, 7)), ('hpcaT3d_8_4', 3, 1, 8, 4, (3, 4, 5))]:
+        cls = ref.HebbianConvTranspose2d if nd == 2 else ref.HebbianConvTranspose3d
+        layer = cls(Cin, Cout, 2, stride=2, padding=0, bias=False, w_nrm=True, mode='hpca', k=1., patchwise=True, alpha=1.)
+        with torch.no_grad():
+            layer.weight.copy_(rnd(*layer.weight.shape, scale=0.3))
+        layer.train()
+        x = rnd(B, Cin, *spatial)
+        y = layer(x)
+        out[name + '/x'], out[name + '/w'] = x.numpy(), layer.weight.detach().contiguous().numpy()
+        out[name + '/y'], out[name + '/dw1'] = y.detach().numpy(), layer.delta_w.clone().contiguous().numpy()
+        meta[name] = dict(kind='hpcaT', nd=nd, B=B, Cin=Cin, Cout=Cout, kernel=2, stride=2, spatial=list(spatial))
+
     # zero-norm filter + eval()/alpha==0 produce no update
     layer = ref.HebbianConv2d(3, 4, 3, padding=1, bias=False, k=5., alpha=1.)
     with torch.no_grad():

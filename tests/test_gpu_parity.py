@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 META = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'makehebbian_golden.json')))['meta']
 CONV = [n for n, m in META.items() if m['kind'] == 'conv' and n != 'zero_row']
 CONVT = [n for n, m in META.items() if m['kind'] == 'convT']
+HPCA = [n for n, m in META.items() if m['kind'] == 'hpca']
 PRECS = ['fp32', 'bf16x3', 'bf16']
 TOL_Y = {'fp32': 1e-5, 'bf16x3': 1e-4, 'bf16': 1e-4}
 TOL_DW = {'fp32': 1e-4, 'bf16x3': 1e-4, 'bf16': 1e-2}
@@ -398,3 +399,45 @@ def test_fuse_pass_keeps_network_output_and_state():
     net.eval()
     ref.eval()
     assert relerr(net(x), ref(x)) < 1e-3       # eval mode takes the stock path (running stats differ by rounding)
+
+
+# ---- HPCA rule ----
+@pytest.mark.parametrize('name', HPCA)
+def test_hpca_vs_reference_golden(golden, name):
+    m = META[name]
+    cls = hebb.HebbianConv2d if m['nd'] == 2 else hebb.HebbianConv3d
+    layer = cls(m['Cin'], m['Cout'], m['kernel'], stride=1, padding=m['padding'], bias=m['bias'], w_nrm=True,
+                mode='hpca', k=1., patchwise=True, alpha=1.)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(golden[name + '/w']))
+        layer.bias.copy_(torch.from_numpy(golden[name + '/b']))
+    layer = layer.to(DEV).train()
+    y = layer(torch.from_numpy(golden[name + '/x']).to(DEV))
+    assert relerr(y, golden[name + '/y']) < 1e-4
+    record('hpca_vs_reference_golden', name, y=relerr(y, golden[name + '/y']), dw=relerr(layer.delta_w, golden[name + '/dw1']))
+    assert relerr(layer.delta_w, golden[name + '/dw1']) < 1e-4
+
+
+def test_reference_hpca_smoke_test_shape():
+    """tests/test_makehebbian.py::test_makehebbian3d of the reference, on CUDA at a reduced width."""
+    net = workloads.UNet3D(1, 2, init_features=8)
+    with contextlib.redirect_stdout(io.StringIO()):
+        makehebbian(net, exclude=['conv'], hebb_params={'mode': 'hpca', 'k': 1.0, 'w_nrm': True, 'alpha': 1.0})
+    net = net.to(DEV).train()
+    out = net(torch.randn(2, 1, 32, 32, 16, device=DEV))
+    assert out.shape == (2, 2, 32, 32, 16)
+    conv = [m for m in net.modules() if type(m).__name__ == 'HebbianConv3d']
+    assert all(float(m.delta_w.abs().max()) > 0 for m in conv)
+
+
+@pytest.mark.parametrize('name', [n for n, m in META.items() if m['kind'] == 'hpcaT'])
+def test_hpca_transposed_vs_reference_golden(golden, name):
+    m = META[name]
+    cls = hebb.HebbianConvTranspose2d if m['nd'] == 2 else hebb.HebbianConvTranspose3d
+    layer = cls(m['Cin'], m['Cout'], 2, stride=2, padding=0, bias=False, w_nrm=True, mode='hpca', k=1., alpha=1.)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(golden[name + '/w']))
+    layer = layer.to(DEV).train()
+    y = layer(torch.from_numpy(golden[name + '/x']).to(DEV))
+    assert relerr(y, golden[name + '/y']) < 1e-5
+    assert relerr(layer.delta_w, golden[name + '/dw1']) < 1e-4

@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 META = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'makehebbian_golden.json')))['meta']
 CONV = [n for n, m in META.items() if m['kind'] == 'conv' and n != 'zero_row']
 CONVT = [n for n, m in META.items() if m['kind'] == 'convT']
+HPCA = [n for n, m in META.items() if m['kind'] == 'hpca']
 
 
 def relerr(a, b):
@@ -63,6 +64,27 @@ def test_convT_forward_and_delta(golden, name):
     assert relerr(dw, golden[name + '/dw1']) < 5e-6
     grad, _ = O.fold_delta_into_grad(None, dw, 1.0)
     assert relerr(grad, golden[name + '/grad']) < 5e-6
+
+
+@pytest.mark.parametrize('name', HPCA)
+def test_hpca_delta(golden, name):
+    m = META[name]
+    nd = m['nd']
+    x, w, b = (torch.from_numpy(golden[name + s]) for s in ('/x', '/w', '/b'))
+    xp = O.zero_halo(x, m['padding'], nd)
+    y = O.conv_activation(xp, w, b, (1,) * nd)
+    assert relerr(y, golden[name + '/y']) < 2e-6
+    assert relerr(O.hpca_delta(xp, y, w, (1,) * nd), golden[name + '/dw1']) < 5e-6
+
+
+@pytest.mark.parametrize('name', [n for n, m in META.items() if m['kind'] == 'hpcaT'])
+def test_hpca_on_transposed_layer(golden, name):
+    m = META[name]
+    x, w = torch.from_numpy(golden[name + '/x']), torch.from_numpy(golden[name + '/w'])
+    st = (2,) * m['nd']
+    y = O.convT_activation(x, w, None, st)
+    assert relerr(y, golden[name + '/y']) < 2e-6
+    assert relerr(O.hpca_exchanged_delta(x, y, w, st), golden[name + '/dw1']) < 5e-6
 
 
 def test_fp64_oracle_agrees_with_fp32_golden(golden):
