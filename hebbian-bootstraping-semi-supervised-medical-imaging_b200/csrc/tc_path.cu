@@ -339,10 +339,11 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       tc_fence_after();
       for (int j = 0; j < p.MB; ++j) {
         const long long pp = (long long)tile * p.TILE_M + j * 128 + row;
-        const int b = (int)(pp / p.Qimg);
-        int q = (int)(pp - (long long)b * p.Qimg);
-        const int od = q / p.plane; q -= od * p.plane;
-        const int oh = q / p.WP;
+        const unsigned pp32 = (unsigned)pp;                 // the planner guarantees PR < 2^31: 32-bit divisions
+        const int b = (int)(pp32 / (unsigned)p.Qimg);
+        int q = (int)(pp32 - (unsigned)b * (unsigned)p.Qimg);
+        const int od = (int)((unsigned)q / (unsigned)p.plane); q -= od * p.plane;
+        const int oh = (int)((unsigned)q / (unsigned)p.WP);
         const int ow = q - oh * p.WP;
         const bool valid = (od < p.oD) && (oh < p.oH) && (ow < p.oW) && (pp < p.PTOT);
         const long long s = (long long)od * oHW + (long long)oh * p.oW + ow;
@@ -354,6 +355,47 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
         float mx = -INFINITY, best = -INFINITY;
         int bi = 0;
         uint32_t v[CH];
+        if (p.CT == CH && p.fuse) {
+          // ---- whole channel row fits one TMEM load (Cout = 16 or 32): single pass, one exp per value ----
+          ld_acc<CH>(ta, p.stackF ? p.CT : 0, v);
+          float f[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            f[i] = fmaf(__uint_as_float(v[i]), s_inv[i], s_bias[i]);
+            if (valid) yb[(long long)i * outS] = f[i];
+            mx = fmaxf(mx, f[i] * p.kinv);
+            if (f[i] > best) { best = f[i]; bi = i; }
+          }
+          if (p.winner && valid) p.winner[(long long)b * outS + s] = bi;
+          if (p.write_r) {
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) { f[i] = __expf(fmaf(f[i], p.kinv, -mx)); sum += f[i]; }
+            const float rinv = valid ? (1.f / sum) : 0.f;
+#pragma unroll
+            for (int g8 = 0; g8 < CH / 8; ++g8) {
+              uint32_t oh4[4], ol4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat16 h2[2], l2[2];
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                  const int c = g8 * 8 + i * 2 + k2;
+                  split_bf16(f[c] * rinv, h2[k2], l2[k2]);
+                  f[c] = __bfloat162float(h2[k2]) + (p.RHL == 2 ? __bfloat162float(l2[k2]) : 0.f);
+                }
+                oh4[i] = pack_bf16x2(h2[0], h2[1]);
+                ol4[i] = pack_bf16x2(l2[0], l2[1]);
+              }
+              const long long ridx = (long long)g8 * p.PR + pp;
+              p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+              if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+            }
+            const float cs = lane_col_sum<CH>(f, lane);
+            if (lane < CH) my_rs[lane] += cs;
+          }
+          continue;
+        }
         for (int c0 = 0; c0 < p.CT; c0 += CH) {
           ld_acc<CH>(ta + c0, p.stackF ? p.CT : 0, v);
           if (p.tr) {
