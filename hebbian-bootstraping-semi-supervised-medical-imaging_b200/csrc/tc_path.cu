@@ -354,8 +354,12 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
         const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.MB * cw + j * cw;
         float mx = -INFINITY, best = -INFINITY;
         int bi = 0;
+        float mx8[8], best8[8];
+        int bi8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mx8[i] = -INFINITY; best8[i] = -INFINITY; bi8[i] = 0; }
         uint32_t v[CH];
-        if (p.CT == CH && p.fuse) {
+        if (p.CT == CH && p.fuse && !p.tr) {
           // ---- whole channel row fits one TMEM load (Cout = 16 or 32): single pass, one exp per value ----
           ld_acc<CH>(ta, p.stackF ? p.CT : 0, v);
           float f[CH];
@@ -400,15 +404,19 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
           ld_acc<CH>(ta + c0, p.stackF ? p.CT : 0, v);
           if (p.tr) {
             // (co, offset) columns: offsets 2j, 2j+1 are x-neighbours in the up-sampled grid -> 8-byte stores
-            if (valid) {
 #pragma unroll
-              for (int i = 0; i < CH; i += 2) {
-                const int cc = cbase + c0 + i, off = cc & 7;
-                float2 o;
-                o.x = __uint_as_float(v[i]) + s_bias[c0 + i];
-                o.y = __uint_as_float(v[i + 1]) + s_bias[c0 + i + 1];
+            for (int i = 0; i < CH; i += 2) {
+              const int cc = cbase + c0 + i, off = cc & 7;
+              float2 o;
+              o.x = __uint_as_float(v[i]) + s_bias[c0 + i];
+              o.y = __uint_as_float(v[i + 1]) + s_bias[c0 + i + 1];
+              if (valid)
                 *reinterpret_cast<float2*>(ytb + (long long)(cc >> 3) * tS + ((long long)(off >> 2) * p.tH + ((off >> 1) & 1)) * p.tW) = o;
-              }
+              // per-offset statistics: one softmax over the real channels for each of the 8 output voxels
+              mx8[i & 7] = fmaxf(mx8[i & 7], o.x * p.kinv);
+              mx8[(i + 1) & 7] = fmaxf(mx8[(i + 1) & 7], o.y * p.kinv);
+              if (o.x > best8[i & 7]) { best8[i & 7] = o.x; bi8[i & 7] = cc >> 3; }
+              if (o.y > best8[(i + 1) & 7]) { best8[(i + 1) & 7] = o.y; bi8[(i + 1) & 7] = cc >> 3; }
             }
           } else {
 #pragma unroll
@@ -419,6 +427,55 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               if (f > best) { best = f; bi = c0 + i; }
             }
           }
+        }
+        if (p.fuse && p.tr) {
+          // ---- transposed layer whose Cout*8 columns fit TMEM: grouped soft-WTA, group = column % 8 ----
+          if (p.winner && valid) {
+            int32_t* wb = p.winner + (long long)b * tS + ((long long)(2 * od) * p.tH + 2 * oh) * p.tW + 2 * ow;
+#pragma unroll
+            for (int off = 0; off < 8; ++off)
+              wb[((long long)(off >> 2) * p.tH + ((off >> 1) & 1)) * p.tW + (off & 1)] = bi8[off];
+          }
+          if (p.write_r) {
+            float sum8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum8[i] = 0.f;
+            for (int c0 = 0; c0 < p.CT; c0 += CH) {
+              ld_acc<CH>(ta + c0, 0, v);
+#pragma unroll
+              for (int i = 0; i < CH; ++i)
+                sum8[i & 7] += __expf(fmaf(__uint_as_float(v[i]) + s_bias[c0 + i], p.kinv, -mx8[i & 7]));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum8[i] = valid ? (1.f / sum8[i]) : 0.f;
+            for (int c0 = 0; c0 < p.CT; c0 += CH) {
+              ld_acc<CH>(ta + c0, 0, v);
+              float rr[CH];
+#pragma unroll
+              for (int g8 = 0; g8 < CH / 8; ++g8) {
+                uint32_t oh4[4], ol4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat16 h2[2], l2[2];
+#pragma unroll
+                  for (int k2 = 0; k2 < 2; ++k2) {
+                    const int c = g8 * 8 + i * 2 + k2, off = i * 2 + k2;
+                    const float r = __expf(fmaf(__uint_as_float(v[c]) + s_bias[c0 + c], p.kinv, -mx8[off])) * sum8[off];
+                    split_bf16(r, h2[k2], l2[k2]);
+                    rr[c] = __bfloat162float(h2[k2]) + (p.RHL == 2 ? __bfloat162float(l2[k2]) : 0.f);
+                  }
+                  oh4[i] = pack_bf16x2(h2[0], h2[1]);
+                  ol4[i] = pack_bf16x2(l2[0], l2[1]);
+                }
+                const long long ridx = (long long)(c0 / 8 + g8) * p.PR + pp;
+                p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+                if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+              }
+              const float cs = lane_col_sum<CH>(rr, lane);
+              if (lane < CH) my_rs[c0 + lane] += cs;
+            }
+          }
+          continue;
         }
         if (p.fuse && p.winner && valid) p.winner[(long long)b * outS + s] = bi;
         if (p.fuse && p.write_r) {
@@ -543,13 +600,15 @@ swta_softmax_pack_kernel(const __grid_constant__ SmxParams p) {
   }
 }
 
-// Transposed conv (k == stride == 2, 3-D): thread per INPUT voxel; its 8 output voxels (one per kernel
-// offset) each get a softmax over the real output channels (hebb3d.py:276-289).  Packed channel
-// index = co*8 + off, so one 16-byte vector holds the 8 offsets of one output channel.
-__global__ void __launch_bounds__(128)
+// Transposed conv (k == stride == 2, 3-D) with more than 512 packed channels: one WARP per INPUT voxel,
+// lanes stride over the real output channels; each of its 8 output voxels (one per kernel offset) gets
+// a softmax over the channels (hebb3d.py:276-289).  Packed channel index = co*8 + off, so one 16-byte
+// vector holds the 8 offsets of one output channel.  These layers have few voxels and many channels.
+__global__ void __launch_bounds__(256)
 swta_softmax_pack_T_kernel(const __grid_constant__ SmxParams p, int tD, int tH, int tW, int CoutR) {
-  const long long pp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  const long long pp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pp >= p.PR) return;
   const long long tS = (long long)tD * tH * tW;
   const int b = (int)(pp / p.Qimg);
   int q = (int)(pp - (long long)b * p.Qimg);
@@ -564,54 +623,103 @@ swta_softmax_pack_T_kernel(const __grid_constant__ SmxParams p, int tD, int tH, 
   float mx[8], sum[8], best[8];
   int bi[8];
 #pragma unroll
-  for (int off = 0; off < 8; ++off) { mx[off] = -INFINITY; sum[off] = 0.f; best[off] = -INFINITY; bi[off] = 0; }
+  for (int off = 0; off < 8; ++off) { mx[off] = -INFINITY; sum[off] = 0.f; best[off] = -INFINITY; bi[off] = 0x7fffffff; }
   if (valid) {
-    for (int c = 0; c < CoutR; ++c)
+    for (int c = lane; c < CoutR; c += 32)
 #pragma unroll
       for (int off = 0; off < 8; off += 2) {
         const float2 f2 = __ldg(reinterpret_cast<const float2*>(yb + (long long)c * tS + o8[off]));
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float f = h ? f2.y : f2.x;
-          const float kv = f * p.kinv;
-          if (kv > mx[off + h]) { sum[off + h] *= __expf(mx[off + h] - kv); mx[off + h] = kv; }   // online rescale
-          sum[off + h] += __expf(kv - mx[off + h]);
-          if (f > best[off + h]) { best[off + h] = f; bi[off + h] = c; }
-        }
+        mx[off] = fmaxf(mx[off], f2.x * p.kinv); mx[off + 1] = fmaxf(mx[off + 1], f2.y * p.kinv);
+        if (f2.x > best[off]) { best[off] = f2.x; bi[off] = c; }
+        if (f2.y > best[off + 1]) { best[off + 1] = f2.y; bi[off + 1] = c; }
       }
-    if (p.winner) {
-      int32_t* wb = p.winner + (long long)b * tS + ((long long)(2 * id) * tH + 2 * ih) * tW + 2 * iw;
 #pragma unroll
-      for (int off = 0; off < 8; ++off) wb[o8[off]] = bi[off];
+    for (int off = 0; off < 8; ++off) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx[off] = fmaxf(mx[off], __shfl_xor_sync(0xffffffffu, mx[off], o));
+        const float ob = __shfl_xor_sync(0xffffffffu, best[off], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi[off], o);
+        if (ob > best[off] || (ob == best[off] && oi < bi[off])) { best[off] = ob; bi[off] = oi; }   // lowest index wins ties
+      }
+    }
+    for (int c = lane; c < CoutR; c += 32)
+#pragma unroll
+      for (int off = 0; off < 8; off += 2) {
+        const float2 f2 = __ldg(reinterpret_cast<const float2*>(yb + (long long)c * tS + o8[off]));
+        sum[off] += __expf(fmaf(f2.x, p.kinv, -mx[off]));
+        sum[off + 1] += __expf(fmaf(f2.y, p.kinv, -mx[off + 1]));
+      }
+#pragma unroll
+    for (int off = 0; off < 8; ++off) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum[off] += __shfl_xor_sync(0xffffffffu, sum[off], o);
+      sum[off] = 1.f / sum[off];
+    }
+    if (p.winner && lane < 8) {
+      int32_t* wb = p.winner + (long long)b * tS + ((long long)(2 * id) * tH + 2 * ih) * tW + 2 * iw;
+      int sel = bi[0];
+#pragma unroll
+      for (int off = 1; off < 8; ++off) sel = (lane == off) ? bi[off] : sel;
+      wb[o8[0] + (((long long)(lane >> 2) * tH + ((lane >> 1) & 1)) * tW + (lane & 1))] = sel;
     }
   }
-  for (int c = 0; c < CoutR; ++c) {
+  for (int c = lane; c < CoutR; c += 32) {
     uint32_t oh4[4], ol4[4];
-    float rr[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+      float2 f2 = make_float2(0.f, 0.f);
+      if (valid) f2 = __ldg(reinterpret_cast<const float2*>(yb + (long long)c * tS + o8[2 * i]));
       __nv_bfloat16 h2[2], l2[2];
-#pragma unroll
-      for (int k2 = 0; k2 < 2; ++k2) {
-        const int off = i * 2 + k2;
-        const float r = valid ? __expf(fmaf(__ldg(yb + (long long)c * tS + o8[off]), p.kinv, -mx[off])) / sum[off] : 0.f;
-        split_bf16(r, h2[k2], l2[k2]);
-        rr[off] = __bfloat162float(h2[k2]) + (p.RHL == 2 ? __bfloat162float(l2[k2]) : 0.f);
-      }
+      const float r0 = valid ? __expf(fmaf(f2.x, p.kinv, -mx[2 * i])) * sum[2 * i] : 0.f;
+      const float r1 = valid ? __expf(fmaf(f2.y, p.kinv, -mx[2 * i + 1])) * sum[2 * i + 1] : 0.f;
+      split_bf16(r0, h2[0], l2[0]);
+      split_bf16(r1, h2[1], l2[1]);
       oh4[i] = pack_bf16x2(h2[0], h2[1]);
       ol4[i] = pack_bf16x2(l2[0], l2[1]);
     }
-    if (pp < p.PR) {
-      p.rp[0][(long long)c * p.PR + pp] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
-      if (p.RHL == 2) p.rp[1][(long long)c * p.PR + pp] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
-    }
+    p.rp[0][(long long)c * p.PR + pp] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+    if (p.RHL == 2) p.rp[1][(long long)c * p.PR + pp] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+  }
+}
+
+// rsum[c8*8 + i] = sum_p (hi + lo)(Rp[c8][p][i]) : one block per 8-channel chunk, fixed summation order.
+__global__ void __launch_bounds__(256)
+rsum_from_packed_kernel(const uint4* __restrict__ rhi, const uint4* __restrict__ rlo, float* __restrict__ rsum, long long PR) {
+  const int c8 = blockIdx.x;
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float v = rr[i];
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (long long pp = threadIdx.x; pp < PR; pp += blockDim.x) {
+    const uint4 h = __ldg(rhi + (long long)c8 * PR + pp);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && v != 0.f) atomicAdd(p.rsum + c * 8 + i, v);
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] += __uint_as_float(hw[i] << 16);
+      acc[2 * i + 1] += __uint_as_float(hw[i] & 0xffff0000u);
     }
+    if (rlo) {
+      const uint4 l = __ldg(rlo + (long long)c8 * PR + pp);
+      const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(lw[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(lw[i] & 0xffff0000u);
+      }
+    }
+  }
+  __shared__ float part[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+    rsum[c8 * 8 + threadIdx.x] = t;
   }
 }
 
@@ -842,6 +950,39 @@ tc_finalize_kernel(const float* __restrict__ hpart, const float* __restrict__ rs
       dw[wi] += tot - rsum[co] * W[wi];
     }
     __syncthreads();
+  }
+}
+
+// Same result for LARGE weight tensors (few position splits, millions of outputs): a 32(co) x 32(j) tile
+// goes through shared memory so that the partials are read coalesced along co and delta_w / W are
+// touched coalesced along j = ci*taps + t (a row of the [Cout][Cin*taps] weight).
+__global__ void __launch_bounds__(256)
+tc_finalize_tiled_kernel(const float* __restrict__ hpart, const float* __restrict__ rsum, const float* __restrict__ W,
+                         float* __restrict__ dw, int PS, int taps, int Cin, int CinP, int Cout) {
+  __shared__ float tile[32][33];
+  const int K = Cin * taps;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long plane = (long long)taps * CinP * Cout;
+  const int j0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = j0 + ty + 8 * r, co = co0 + tx;
+    float acc = 0.f;
+    if (j < K && co < Cout) {
+      const int ci = j / taps, t = j - ci * taps;
+      const float* hp = hpart + ((long long)t * CinP + ci) * Cout + co;
+      for (int sp = 0; sp < PS; ++sp) acc += hp[(long long)sp * plane];
+    }
+    tile[ty + 8 * r][tx] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int co = co0 + ty + 8 * r, j = j0 + tx;
+    if (j < K && co < Cout) {
+      const long long wi = (long long)co * K + j;
+      dw[wi] += tile[tx][ty + 8 * r] - rsum[co] * W[wi];
+    }
   }
 }
 
@@ -1134,7 +1275,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   f.y = y; f.winner = winner; f.inv = ((flags & HEBB_F_WNRM) && !tr) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = err;
   f.tr = tr ? 1 : 0; f.tD = g0.oD; f.tH = g0.oH; f.tW = g0.oW; f.CoutR = g0.Cout;
   f.Cout = g.Cout; f.CC = P.CC; f.NSLAB = P.NSLAB; f.taps = g.taps; f.nseg = P.f_nseg; f.HL = P.f_HL; f.RHL = P.d_HL;
-  f.stackF = P.stackF; f.CT = P.CT; f.n_ct = P.n_ct; f.fuse = (P.n_ct == 1 && !tr) ? 1 : 0;
+  f.stackF = P.stackF; f.CT = P.CT; f.n_ct = P.n_ct; f.fuse = (P.n_ct == 1) ? 1 : 0;   // transposed: grouped softmax when Cout*8 <= 512
   f.PA = P.PA; f.PR = P.PR; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
   f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC;
   f.WP = P.WP; f.plane = P.plane; f.Qimg = P.Qimg; f.oD = g.oD; f.oH = g.oH; f.oW = g.oW;
@@ -1158,14 +1299,18 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     fwd_swta_kernel<16><<<fgrid, 320, kSmemLimit, st>>>(f);
   }
   if (do_fwd) { HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED(); }
-  if (do_fwd && (P.n_ct > 1 || tr) && (upd || winner)) {
+  if (do_fwd && P.n_ct > 1 && (upd || winner)) {
     SmxParams sp;
     sp.y = y; sp.rp[0] = rp0; sp.rp[1] = rp1; sp.winner = winner; sp.rsum = rsum;
     sp.Cout = g.Cout; sp.RHL = P.d_HL; sp.WP = P.WP; sp.plane = P.plane; sp.Qimg = P.Qimg;
     sp.oD = g.oD; sp.oH = g.oH; sp.oW = g.oW; sp.PR = P.PR; sp.PTOT = P.PTOT; sp.kinv = kinv;
     if (tr) {
       sp.Cout = g.Cout;
-      swta_softmax_pack_T_kernel<<<(unsigned)(P.PR / 128), 128, 0, st>>>(sp, g0.oD, g0.oH, g0.oW, g0.Cout);
+      swta_softmax_pack_T_kernel<<<(unsigned)cdiv(P.PR, 8), 256, 0, st>>>(sp, g0.oD, g0.oH, g0.oW, g0.Cout);
+      if (upd) {
+        HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+        rsum_from_packed_kernel<<<(unsigned)P.C8, 256, 0, st>>>(rp0, P.d_HL == 2 ? rp1 : nullptr, rsum, P.PR);
+      }
     } else {
       swta_softmax_pack_kernel<<<(unsigned)(P.PR / 128), 128, 0, st>>>(sp);
     }
@@ -1210,7 +1355,10 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     if (tr)
       tc_finalize_T_kernel<<<ew_grid((long long)g0.Cin * g0.Cout), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g0.Cin, P.CinP, g0.Cout);
     else
-    {
+    if (n >= (1LL << 18) && P.PS * P.Q <= 32) {
+      dim3 fg((unsigned)cdiv((long long)g.Cin * g.taps, 32), (unsigned)cdiv(g.Cout, 32));
+      tc_finalize_tiled_kernel<<<fg, 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
+    } else {
       long long gx = cdiv(n, 32);
       const long long cap = (long long)num_sms() * 32;
       if (gx > cap) gx = cap;
