@@ -9,5 +9,6 @@ python bench.py --layers-out gpurun_out/layers_c2_bf16x3.json > gpurun_out/bench
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-layer-profile"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c2.csv $CMD > gpurun_out/ncu_ll.log 2>&1; echo "launchlist rc=$?"
+# DRAM traffic of our kernels over one timed step (3 warm-up steps x 110 matching launches skipped)
 $CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'hebb' -s 1200 -c 200 --csv --log-file gpurun_out/traffic_c2.csv $CMD > gpurun_out/ncu_tr.log 2>&1; echo "traffic rc=$?"
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'swta|pack_x|pack_w|finalize|wnorm_kernel' -s 330 -c 110 --csv --log-file gpurun_out/traffic_c2.csv $CMD > gpurun_out/ncu_tr.log 2>&1; echo "traffic rc=$?"

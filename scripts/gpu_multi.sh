@@ -5,6 +5,7 @@ N=${1:-2}
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus.txt 2>&1
 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --no-layer-profile > gpurun_out/scale_1.json 2> gpurun_out/scale_1.err; echo "n1 rc=$?"
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline --no-layer-profile > gpurun_out/scale_$N.json 2> gpurun_out/scale_$N.err; echo "n$N rc=$?"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 1 --warmup 0 > gpurun_out/scale_ref_$N.json 2> gpurun_out/scale_ref_$N.err; echo "ref n$N rc=$?"; cut -c1-200 gpurun_out/scale_ref_$N.json
 tail -3 gpurun_out/scale_$N.err
 python - <<PY
 import json

@@ -219,6 +219,16 @@ def main():
         structures['toy_swta_t'] = describe(net)
         net = mk.makehebbian(Net(), exclude=None, hebb_params=None)
         structures['toy_none'] = describe(net)
+    # a checkpoint in the reference's save_snapshot() layout (utils.py:29-55), produced by the reference modules
+    torch.manual_seed(7)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = mk.makehebbian(Net(), exclude=['clf.5'], hebb_params={'mode': 'swta_t', 'k': 50., 'w_nrm': True, 'alpha': 1.})
+    for n_, m_ in net.named_modules():
+        if hasattr(m_, 'delta_w'):
+            m_.delta_w.normal_()
+    torch.save({'model': net.state_dict(), 'threshold': 0.5,
+                'hebb_params': {'mode': 'swta_t', 'k': 50., 'w_nrm': True, 'alpha': 1.}, 'excluded_layers': ['clf.5']},
+               os.path.join(HERE, 'ref_checkpoint.pth'))
     structures['adjust'] = {
         'swta_t': mk.adjust_hebbian_params({'mode': 'swta_t', 'k': 3}),
         'hpca_t': mk.adjust_hebbian_params({'mode': 'hpca_t'}),

@@ -177,3 +177,25 @@ def test_flatten_delta_w_keeps_shapes_and_aliases():
     assert all(float(m.delta_w.min()) == 2.0 for m in hebbian_layers(net))
     net.up[0].delta_w.zero_()
     assert float(flat.sum()) < 2.0 * flat.numel()
+
+
+def test_reference_checkpoint_interchange():
+    """A checkpoint written by the REFERENCE modules in its save_snapshot() layout (utils.py:29-55) loads into the
+    drop-in network built the way the reference's consumers do (test_2d.py:105-109: makehebbian, then
+    load_state_dict), and the drop-in's own state_dict loads back bit-identically."""
+    ck = torch.load(os.path.join(ROOT, 'tests', 'golden', 'ref_checkpoint.pth'), map_location='cpu', weights_only=True)
+    assert set(ck) == {'model', 'threshold', 'hebb_params', 'excluded_layers'}
+    hp = dict(ck['hebb_params'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = makehebbian(Net(), exclude=ck['excluded_layers'], hebb_params=hp)
+    missing, unexpected = net.load_state_dict(ck['model'], strict=True)
+    assert not missing and not unexpected
+    for k, v in ck['model'].items():
+        assert torch.equal(net.state_dict()[k], v), k
+    up = net.up[0]
+    assert up.weight.shape == (16, 20, 3, 3) and up.weight.stride() == (9, 144, 3, 1)       # view kept
+    assert torch.equal(up.delta_w, ck['model']['up.0.delta_w'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        twin = makehebbian(Net(), exclude=ck['excluded_layers'], hebb_params=hp)
+    twin.load_state_dict(net.state_dict())
+    assert all(torch.equal(a, b) for a, b in zip(twin.state_dict().values(), net.state_dict().values()))
