@@ -761,7 +761,10 @@ struct DwParams {
   int Cin, Cout, CC, C8, taps, HL;
   long long PA, PR;
   int BLK, SEGLEN, total_blocks, blocks_per_split, PS;
-  int ngrp; int grp_base[9]; int grp_tap_begin[10]; int tap_off[kMaxTaps];
+  int ngrp; int grp_base[9];
+  // "super-taps": with nrep > 1 the staged x tile is replicated nrep times, copy r shifted by r positions, so the
+  // M rows of ONE tcgen05.mma cover nrep horizontally adjacent taps (kw0 .. kw0+nrep-1) of a kernel row.
+  int nrep; int grp_st_begin[10]; int st_off[kMaxTaps]; int st_first[kMaxTaps]; int st_n[kMaxTaps];
   int CM, n_cin_tiles, CN, n_cout_tiles, ST, CinP;
   int stackM, stackN, cpt;      // bf16x3 "precision stacking": [x_hi; x_lo] along M and/or [r_hi | r_lo] along N, so one
                                 // tcgen05.mma yields several of the hi/lo partial products; cpt = 8-channel chunks per cin tile
@@ -790,7 +793,7 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   const int rn_chunks = N / 8;
   const int Neff = p.stackN ? 2 * N : N;
   const int colw = (p.stackN ? 2 : 1) * p.CN;        // TMEM columns per tap
-  const int tap_b = p.grp_tap_begin[grp], tap_e = p.grp_tap_begin[grp + 1];
+  const int st_b = p.grp_st_begin[grp], st_e = p.grp_st_begin[grp + 1];
   const int blk_b = min(split * p.blocks_per_split, p.total_blocks);
   const int blk_e = min(blk_b + p.blocks_per_split, p.total_blocks);
 
@@ -806,22 +809,24 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   const uint32_t tmem_base = *s_tmem;
   const uint32_t r_off = p.x_bytes;                 // R region follows X region inside a stage
   const uint32_t x_hl_stride = cm_chunks * p.SEGLEN * 16;   // lo chunks directly follow the hi chunks
+  const uint32_t x_rep_stride = p.HL * x_hl_stride;         // replica r+1 directly follows replica r
   const uint32_t r_hl_stride = rn_chunks * p.BLK * 16;
 
   if (warp == 0) {
     if (elect_one()) {
       int st = 0; uint32_t ph = 0;
-      const uint32_t bytes = p.HL * (cm_chunks * p.SEGLEN + rn_chunks * p.BLK) * 16;
+      const uint32_t bytes = p.HL * (p.nrep * cm_chunks * p.SEGLEN + rn_chunks * p.BLK) * 16;
       for (int blk = blk_b; blk < blk_e; ++blk) {
         const long long p0 = (long long)blk * p.BLK;
         mbar_wait(empty + 8 * st, ph ^ 1, p.err, 11);
         mbar_expect_tx(full + 8 * st, bytes);
         const uint32_t dst = sbase + st * p.stage_bytes;
         for (int hl = 0; hl < p.HL; ++hl) {
-          for (int c = 0; c < cm_chunks; ++c)
-            bulk_g2s(dst + hl * x_hl_stride + c * p.SEGLEN * 16,
-                     p.xp[hl] + (long long)(cin_tile * p.cpt + c) * p.PA + p0 + p.grp_base[grp],
-                     p.SEGLEN * 16, full + 8 * st);
+          for (int rep = 0; rep < p.nrep; ++rep)
+            for (int c = 0; c < cm_chunks; ++c)
+              bulk_g2s(dst + rep * x_rep_stride + hl * x_hl_stride + c * p.SEGLEN * 16,
+                       p.xp[hl] + (long long)(cin_tile * p.cpt + c) * p.PA + p0 + p.grp_base[grp] + rep,
+                       p.SEGLEN * 16, full + 8 * st);
           for (int c = 0; c < rn_chunks; ++c)
             bulk_g2s(dst + r_off + hl * r_hl_stride + c * p.BLK * 16,
                      p.rp[hl] + (long long)(cout_tile * (p.CN / 8) + c) * p.PR + p0, p.BLK * 16, full + 8 * st);
@@ -844,9 +849,9 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
         const uint32_t ra = xa + r_off;
         const uint32_t accum0 = (blk == blk_b) ? 0u : 1u;
         if (elect_one()) {
-          for (int tap = tap_b; tap < tap_e; ++tap) {
-            const uint32_t d = tmem_base + (tap - tap_b) * colw;
-            const uint32_t a_tap = xa + p.tap_off[tap] * 16;
+          for (int stp = st_b; stp < st_e; ++stp) {
+            const uint32_t d = tmem_base + (stp - st_b) * colw;
+            const uint32_t a_tap = xa + p.st_off[stp] * 16;
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t a0 = a_tap + ks * 256;
               const uint32_t b0 = ra + ks * 256;
@@ -883,16 +888,22 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
     int row; bool row_ok;
     if (p.CM == 128) { row = quad * 32 + lane; row_ok = true; }
     else { row = quad * 16 + (lane & 15); row_ok = lane < 16; }    // M=64: D row r lives in lane (r%16)+32*(r/16)
-    // stacked rows: [0, R) pair with x_hi, [R, 2R) with x_lo (R = real channels of this cin tile)
+    // rows of one replica: [0, R) pair with x_hi and, when stacked, [R, 2R) with x_lo (R = real channels of
+    // this cin tile); replica `rep` (rows rep*RR ...) belongs to tap st_first + rep of the super-tap
     const int R = cm_chunks * 8;
-    const int row_lo = (p.stackM && row >= R) ? 1 : 0;
-    const int rloc = row - row_lo * R;
+    const int RR = (p.stackM ? 2 : 1) * R;
+    const int rep = row / RR;
+    const int rrow = row - rep * RR;
+    const int row_lo = (p.stackM && rrow >= R) ? 1 : 0;
+    const int rloc = rrow - row_lo * R;
     const int ci = cin_tile * p.cpt * 8 + rloc;
-    const bool st_ok = row_ok && rloc < R && ci < p.Cin && (p.stackM ? row < 2 * R : true);
+    const bool st_ok = row_ok && rep < p.nrep && ci < p.Cin;
     const bool have = blk_e > blk_b;
     const int Q = (p.stackM ? 2 : 1) * (p.stackN ? 2 : 1);
-    for (int tap = tap_b; tap < tap_e; ++tap) {
-      const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (tap - tap_b) * colw;
+    for (int stp = st_b; stp < st_e; ++stp) {
+      const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (stp - st_b) * colw;
+      const int tap = p.st_first[stp] + rep;
+      const bool tap_ok = st_ok && rep < p.st_n[stp];
       for (int c0 = 0; c0 < Neff; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(ta + c0, v);
@@ -901,7 +912,7 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
         const int quadrant = row_lo * (p.stackN ? 2 : 1) + col_lo;
         float* dst = p.hpart + ((((long long)split * Q + quadrant) * p.taps + tap) * p.CinP + ci) * p.Cout +
                      cout_tile * p.CN + (c0 - col_lo * N);
-        if (st_ok) {
+        if (tap_ok) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float4 o;
@@ -1002,7 +1013,7 @@ struct Plan {
   uint32_t f_x_stage, f_w_stage, f_off_w, f_off_misc, f_smem, f_tmem;
   // dW
   int d_HL, BLK, d_SEGLEN, d_by_kh, ngrp, CM, n_cin_tiles, CN, n_cout_tiles, PS, total_blocks, blocks_per_split, ST, CinP;
-  int stackM, stackN, cpt, Q;
+  int stackM, stackN, cpt, Q, nrep;
   uint32_t d_stage, d_x_bytes, d_off_bar, d_smem, d_tmem;
   // workspace carve (byte offsets)
   size_t o_inv, o_rsum, o_err, o_xp[2], o_rp[2], o_wp, o_hpart, total;
@@ -1092,26 +1103,31 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   double best_cost = 1e300;
   found = false;
   for (int by_kh = 0; by_kh <= 1; ++by_kh) {
-    const int gtaps = by_kh ? g.kW : g.kH * g.kW;
-    const int ghalo = by_kh ? (g.kW - 1) : halo;
     const int ngrp = by_kh ? g.kD * g.kH : g.kD;
     if (by_kh && g.kH == 1) continue;
     for (int cm = 128; cm >= 64; cm -= 64) {
      for (int sm = 0; sm <= (q.d_HL == 2 ? 1 : 0); ++sm) {
       for (int sn = 0; sn <= (q.d_HL == 2 ? 1 : 0); ++sn) {
       const int cpt = sm ? cm / 16 : cm / 8;             // 8-channel chunks of x per cin tile
-      if (cm == 128 && q.CC <= cpt / 2) continue;        // a 64-row instruction already holds everything
       const int cm_chunks = (q.CC < cpt) ? q.CC : cpt;
       const int n_cin = (int)cdiv(q.CC, cpt);
+      for (int nrep = 1; nrep <= 4; ++nrep) {
+      if (nrep == 1 && cm == 128 && q.CC <= cpt / 2) continue;   // a 64-row instruction already holds everything
+      // tap replication: nrep shifted copies of the x tile share one instruction's M rows; needs every channel in
+      // one tile, room for nrep replicas in the M rows, and (split mode) hi/lo stacked inside each replica
+      if (nrep > 1 && (n_cin != 1 || nrep > g.kW || (q.d_HL == 2 && !sm) || nrep * (sm ? 2 : 1) * cm_chunks > cm / 8)) continue;
+      const int st_row = (int)cdiv(g.kW, nrep);          // super-taps per kernel row
+      const int gst = by_kh ? st_row : g.kH * st_row;    // super-taps (= accumulator column groups) per tap group
+      const int rhalo = (st_row - 1) * nrep + (by_kh ? 0 : (g.kH - 1) * q.WP);
       const int cn_opts[7] = {256, 128, 64, 48, 32, 16, g.Cout};
       for (int ci = 0; ci < 7; ++ci) {
         const int cn = cn_opts[ci];
         const int neff = sn ? 2 * cn : cn;
-        if (cn > g.Cout || neff > 256 || gtaps * neff > 512 || cn % 16) continue;
+        if (cn > g.Cout || neff > 256 || gst * neff > 512 || cn % 16) continue;
         const int n_cout = (int)cdiv(g.Cout, cn);
         for (int blk = 1024; blk >= 64; blk >>= 1) {
-          const int seglen = round_up_i(blk + ghalo, 8);
-          const uint32_t xb = (uint32_t)q.d_HL * cm_chunks * seglen * 16;
+          const int seglen = round_up_i(blk + rhalo, 8);
+          const uint32_t xb = (uint32_t)nrep * q.d_HL * cm_chunks * seglen * 16;
           const uint32_t rb = (uint32_t)q.d_HL * (cn / 8) * blk * 16;
           for (int st = 3; st >= 2; --st) {
             // the A descriptor always spans cm/8 chunks: rows past the real ones read whatever follows in
@@ -1127,8 +1143,8 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
             const double floor_c = (cm == 64) ? 45.0 : 60.0;
             const double mma = (neff * 0.5625 > floor_c) ? neff * 0.5625 : floor_c;
             const int n_mma = (q.d_HL == 2) ? (sm && sn ? 1 : ((sm || sn) ? 2 : 3)) : 1;
-            const double t_mma = (double)gtaps * (blk / 16) * n_mma * mma;
-            const double t_ld = (double)q.d_HL * 16.0 * ((double)cm_chunks * seglen + (cn / 8.0) * blk) / 40.0;
+            const double t_mma = (double)gst * (blk / 16) * n_mma * mma;
+            const double t_ld = (double)q.d_HL * 16.0 * ((double)nrep * cm_chunks * seglen + (cn / 8.0) * blk) / 40.0;
             const double per_blk = (t_mma > t_ld ? t_mma : t_ld) + 800.0 + (st == 2 ? 0.15 * t_ld : 0.0);
             const double out_tiles = (double)ngrp * n_cin * n_cout;
             const double blocks = (double)cdiv(q.PTOT, blk);
@@ -1136,17 +1152,18 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
             waves = waves < 1.0 ? 1.0 : waves;
             double ctas = out_tiles < sms ? out_tiles * (double)((int)(sms / out_tiles)) : out_tiles;   // CTAs of the single wave
             if (ctas > sms) ctas = sms;
-            const double cost = blocks * per_blk * out_tiles / ctas + 30000.0 * waves + 4.0 * gtaps * neff * waves;
+            const double cost = blocks * per_blk * out_tiles / ctas + 30000.0 * waves + 4.0 * gst * neff * waves;
             if (cost < best_cost) {
               best_cost = cost; found = true;
               q.d_by_kh = by_kh; q.BLK = blk; q.d_SEGLEN = seglen; q.ST = st; q.CN = cn; q.CM = cm;
-              q.stackM = sm; q.stackN = sn; q.cpt = cpt;
+              q.stackM = sm; q.stackN = sn; q.cpt = cpt; q.nrep = nrep;
               q.d_x_bytes = xb; q.d_stage = xb + rb;
               q.d_off_bar = (uint32_t)(tot - (8 * 16 + 64));
               q.d_smem = (uint32_t)tot;
             }
           }
         }
+      }
       }
       }
      }
@@ -1158,7 +1175,7 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   q.Q = (q.stackM ? 2 : 1) * (q.stackN ? 2 : 1);
   q.ngrp = q.d_by_kh ? g.kD * g.kH : g.kD;
   q.n_cout_tiles = (int)cdiv(g.Cout, q.CN);
-  q.d_tmem = pow2_cols((q.d_by_kh ? g.kW : g.kH * g.kW) * q.CN * (q.stackN ? 2 : 1));
+  q.d_tmem = pow2_cols((q.d_by_kh ? 1 : g.kH) * (int)cdiv(g.kW, q.nrep) * q.CN * (q.stackN ? 2 : 1));
 
   // packed position space: multiples of both tile sizes
   const int big = q.TILE_M > q.BLK ? q.TILE_M : q.BLK;
@@ -1210,7 +1227,7 @@ int tc_describe_plan(const Geo& g0, int prec, int* o, int n) {
   if (!equivalent_1x1(g0, &g) || !plan_layer(g, prec, &P)) return 0;
   const int v[] = {P.MB, P.f_SEGLEN, P.XST, P.WST, P.NACC, (int)P.f_tmem, P.f_ntiles, (int)P.f_smem,
                    P.d_by_kh, P.CM, P.CN, P.BLK, P.ST, P.d_SEGLEN, P.ngrp, P.n_cin_tiles, P.n_cout_tiles, P.PS,
-                   P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct};
+                   P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct, P.nrep};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < m; ++i) o[i] = v[i];
   return m;
@@ -1325,24 +1342,26 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   d.PA = P.PA; d.PR = P.PR; d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
   d.blocks_per_split = P.blocks_per_split; d.PS = P.PS; d.ngrp = P.ngrp;
   for (int i = 0; i < 9; ++i) d.grp_base[i] = 0;
-  for (int i = 0; i < 10; ++i) d.grp_tap_begin[i] = g.taps;
-  for (int t = 0; t < kMaxTaps; ++t) d.tap_off[t] = 0;
-  if (P.d_by_kh) {
-    for (int kd = 0, gi = 0; kd < g.kD; ++kd)
-      for (int kh = 0; kh < g.kH; ++kh, ++gi) {
-        d.grp_base[gi] = kd * P.plane + kh * P.WP;
-        d.grp_tap_begin[gi] = gi * g.kW;
-        for (int kw = 0; kw < g.kW; ++kw) d.tap_off[gi * g.kW + kw] = kw;
-      }
-  } else {
+  d.nrep = P.nrep;
+  for (int t = 0; t < kMaxTaps; ++t) { d.st_off[t] = 0; d.st_first[t] = 0; d.st_n[t] = 0; }
+  {
+    // tap groups (one CTA column set each) -> super-taps (one accumulator column group each) -> taps
+    int nst = 0, gi = 0;
     for (int kd = 0; kd < g.kD; ++kd) {
-      d.grp_base[kd] = kd * P.plane;
-      d.grp_tap_begin[kd] = kd * g.kH * g.kW;
-      for (int kh = 0; kh < g.kH; ++kh)
-        for (int kw = 0; kw < g.kW; ++kw) d.tap_off[(kd * g.kH + kh) * g.kW + kw] = kh * P.WP + kw;
+      if (!P.d_by_kh) { d.grp_base[gi] = kd * P.plane; d.grp_st_begin[gi] = nst; }
+      for (int kh = 0; kh < g.kH; ++kh) {
+        if (P.d_by_kh) { d.grp_base[gi] = kd * P.plane + kh * P.WP; d.grp_st_begin[gi] = nst; }
+        for (int kw0 = 0; kw0 < g.kW; kw0 += P.nrep, ++nst) {
+          d.st_off[nst] = (P.d_by_kh ? 0 : kh * P.WP) + kw0;
+          d.st_first[nst] = (kd * g.kH + kh) * g.kW + kw0;
+          d.st_n[nst] = (g.kW - kw0 < P.nrep) ? (g.kW - kw0) : P.nrep;
+        }
+        if (P.d_by_kh) ++gi;
+      }
+      if (!P.d_by_kh) ++gi;
     }
+    for (int i = gi; i < 10; ++i) d.grp_st_begin[i] = nst;
   }
-  d.grp_tap_begin[P.ngrp] = g.taps;
   d.stackM = P.stackM; d.stackN = P.stackN; d.cpt = P.cpt;
   d.CM = P.CM; d.n_cin_tiles = P.n_cin_tiles; d.CN = P.CN; d.n_cout_tiles = P.n_cout_tiles; d.ST = P.ST; d.CinP = P.CinP;
   d.stage_bytes = P.d_stage; d.x_bytes = P.d_x_bytes; d.off_bar = P.d_off_bar; d.tmem_cols = P.d_tmem;

@@ -67,41 +67,45 @@ _CONV_TWINS = {
 }
 
 
+def _hebbian_twin(child, hebb_params):
+    """The Hebbian replacement for one stock layer, or None if `child` is not convertible."""
+    kind = type(child)
+    if kind in _CONV_TWINS:
+        twin, plain_rule, unit = _CONV_TWINS[kind]
+        if child.dilation != 1 and child.dilation != unit:
+            raise RuntimeError("Dilation not supported with Hebbian layers")
+        if child.groups != 1:
+            raise RuntimeError("Grouped convolution not supported with Hebbian layers")
+        kwargs = adjust_hebbian_params(hebb_params) if plain_rule else hebb_params
+        layer = twin(child.in_channels, child.out_channels, child.kernel_size, child.stride, child.padding, False, **kwargs)
+        return init_weights(layer, init_type='kaiming')
+    if kind is nn.Linear:
+        # a fully connected layer becomes a 1x1 Hebbian conv between two reshape shims (bias stays trainable)
+        conv = HebbianConv2d(child.in_features, child.out_features, 1, 1, **adjust_hebbian_params(hebb_params))
+        return nn.Sequential(UnsqueezeLast(2), init_weights(conv, init_type='kaiming'), FlattenLast(2))
+    return None
+
+
 def makehebbian(model, exclude=None, hebb_params=None):
-    if hebb_params is None:
-        hebb_params = default_hebb_params
-    wanted = list(exclude) if exclude is not None else []
-    roots = [(n, m) for n, m in model.named_modules() if n in wanted]
+    """In-place conversion; returns `model`.  `exclude` holds exact `named_modules()` names whose whole
+    sub-trees stay as they are (and stay trainable by back-prop)."""
+    hebb_params = default_hebb_params if hebb_params is None else hebb_params
+    names = set(exclude or ())
+    roots = [(n, m) for n, m in model.named_modules() if n in names]
     print("Layers excluded from conversion to Hebbian: {}".format([n for n, _ in roots]))
-    kept = [s for _, r in roots for s in r.modules()]
+    protected = {id(sub) for _, root in roots for sub in root.modules()}
 
-    def convert(parent):
-        for name, child in parent.named_children():
-            if any(child is k for k in kept):
-                continue
-            kind = type(child)
-            if kind in _CONV_TWINS:
-                twin, adjust, unit = _CONV_TWINS[kind]
-                if child.dilation != 1 and child.dilation != unit:
-                    raise RuntimeError("Dilation not supported with Hebbian layers")
-                if child.groups != 1:
-                    raise RuntimeError("Grouped convolution not supported with Hebbian layers")
-                params = adjust_hebbian_params(hebb_params) if adjust else hebb_params
-                new = twin(child.in_channels, child.out_channels, child.kernel_size, child.stride, child.padding,
-                           False, **params)
-                parent.register_module(name, init_weights(new, init_type='kaiming'))
-                if kind in (nn.Conv2d, nn.ConvTranspose2d):
-                    # reference quirk (makehebbian.py:64 vs :72 are separate if-chains): the replaced
-                    # 2-D layer also reaches the final else and has its own parameters frozen
-                    for p in child.parameters(recurse=False):
-                        p.requires_grad = False
-            elif kind is nn.Linear:
-                conv = HebbianConv2d(child.in_features, child.out_features, 1, 1, **adjust_hebbian_params(hebb_params))
-                parent.register_module(name, nn.Sequential(UnsqueezeLast(2), init_weights(conv, init_type='kaiming'),
-                                                           FlattenLast(2)))
-            else:
-                for p in child.parameters(recurse=False):
-                    p.requires_grad = False
-
-    model.apply(convert)
+    # snapshot of the ORIGINAL tree: layers created below are never revisited (their parameters stay trainable)
+    edges = [(parent, name, child) for parent in list(model.modules()) for name, child in list(parent.named_children())]
+    for parent, name, child in edges:
+        if id(child) in protected:
+            continue
+        new = _hebbian_twin(child, hebb_params)
+        if new is not None:
+            parent.register_module(name, new)
+        if new is None or type(child) in (nn.Conv2d, nn.ConvTranspose2d):
+            # everything that is not converted is frozen; so are the orphaned parameters of a replaced
+            # 2-D conv (reference quirk: makehebbian.py:64 and :72 are separate if-chains)
+            for prm in child.parameters(recurse=False):
+                prm.requires_grad = False
     return model
