@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c4'])
+    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c4', 'c5'])
     ap.add_argument('--prec', default=os.environ.get('HEBB_PREC', 'bf16x3'), choices=['fp32', 'bf16x3', 'bf16'])
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (0 = the workload default)')
     ap.add_argument('--cpu-sample-batch', type=int, default=0)
@@ -58,6 +58,9 @@ WORKLOADS = {
     'c1': ('single HebbianConv2d 3->64 k3 soft-WTA, 8x3x128x128', 8, 8),
     'c2': ('2D UNet Hebbian pretraining, synthetic GlaS 256x256 RGB', 64, 4),
     'c4': ('3D UNet Hebbian pretraining, synthetic LA 96x96x80', 8, 1),
+    # BASELINE configs[4]: forward throughput of the fine-tune-stage network (hebb alpha = 0, nothing updates).  The XNet
+    # dual-branch model is not in the reference tree: the same 2-D UNet on a 3-channel image stands in.
+    'c5': ('2D UNet forward only, hebb alpha=0 (fine-tune stage), synthetic 256x256 RGB', 64, 4),
 }
 
 
@@ -89,7 +92,7 @@ def build_model(workload, impl_ours, device, fuse=False):
             g = torch.Generator().manual_seed(seed)
             return torch.randn(b, 3, 128, 128, generator=g).to(dev), None
         return layer.to(device).train(), batch, None
-    if workload == 'c2':
+    if workload in ('c2', 'c5'):
         net, excl = workloads.unet2d(3, 2), workloads.EXCLUDE_2D
 
         def batch(b, seed, dev):
@@ -99,22 +102,28 @@ def build_model(workload, impl_ours, device, fuse=False):
 
         def batch(b, seed, dev):
             return workloads.la_batch(b, (96, 96, 80), seed=seed, device=dev)
+    alpha = 0. if workload == 'c5' else HEBB_PARAMS['alpha']
     with contextlib.redirect_stdout(io.StringIO()):
         if impl_ours:
             from hebb.makehebbian import makehebbian
-            makehebbian(net, exclude=excl, hebb_params=dict(HEBB_PARAMS))
+            makehebbian(net, exclude=excl, hebb_params=dict(HEBB_PARAMS, alpha=alpha))
         else:
             from oracle import hebb_oracle as O
-            O.oracle_makehebbian(net, exclude=excl, k=HEBB_PARAMS['k'], alpha=HEBB_PARAMS['alpha'])
+            O.oracle_makehebbian(net, exclude=excl, k=HEBB_PARAMS['k'], alpha=alpha)
     workloads.init_weights_like_reference(net)            # init_weights_unet(model,'kaiming') after surgery
     if impl_ours and fuse:
         from hebb.fused import fuse_norm_act
         fuse_norm_act(net)                                # BatchNorm(train)+act and 2x bilinear up-sampling on our kernels
+    if workload == 'c5':
+        return net.to(device).eval(), batch, None
     return net.to(device).train(), batch, workloads.dice_loss
 
 
 def reference_step(model, opt, crit, x, m):
     """The reference loop body, verbatim in structure (pretrain_hebbian_unsup_2d.py:181-196)."""
+    if not model.training:                 # c5: inference-style forward of the alpha=0 network
+        with torch.no_grad():
+            return model(x).sum()
     opt.zero_grad()
     out = model(x)
     loss = None
@@ -402,6 +411,18 @@ def run_ours(args):
                 ach = by / (tot[dom] / 1e3) / 1e9
                 roof = dict(bound='hbm', kernel='pack_x_kernel', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'],
                             traffic=None, peak_source=pk['source'], stage_ms=tot)
+        if roof is not None:
+            # DRAM bytes of that kernel per step from the committed ncu capture of this command (profiles/)
+            tpath = os.path.join(ROOT, 'profiles', f'r1_traffic_{args.workload}.json')
+            if os.path.exists(tpath) and args.prec == 'bf16x3':
+                try:
+                    with open(tpath) as f:
+                        tr = json.load(f).get(roof['kernel'])
+                    if tr:
+                        roof['traffic'] = tr['dram_read_bytes_per_step'] + tr['dram_write_bytes_per_step']
+                        roof['traffic_note'] = 'dram__bytes_read+write of all launches of this kernel in one step (ncu, profiles/r1_traffic_%s.json)' % args.workload
+                except Exception:
+                    pass
         if args.layers_out:
             with open(args.layers_out, 'w') as f:
                 json.dump(dict(workload=args.workload, prec=args.prec, batch=B, layers=rows), f, indent=1)

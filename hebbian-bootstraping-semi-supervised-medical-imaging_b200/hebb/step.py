@@ -93,6 +93,9 @@ class HebbianStepper:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
 
     def step(self, x, target=None):
+        if not self.model.training:          # forward-only use (e.g. throughput of the alpha=0 network)
+            with torch.no_grad():
+                return self.model(x), None
         self.optimizer.zero_grad()
         out = self.model(x)
         loss = None
