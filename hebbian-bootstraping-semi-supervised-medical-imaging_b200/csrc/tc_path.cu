@@ -76,19 +76,74 @@ pack_x_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __res
   }
 }
 
-// Wp[slab][tap][hl][c2][co] (uint4 = 8 input channels) : the forward B operand, K-major.
+// Patch-gathering pack for layers with very few input channels (see equivalent_1x1): position p runs over
+// the OUTPUT grid, pseudo-channel k' = ci*taps + tap holds x[ci] at the tap's input position (0 in the halo).
+struct GatherGeo {
+  int B, Cin, iD, iH, iW, pD, pH, pW, kH, kW, taps, oD, oH, oW, Kp, CC;
+  long long PA, PTOT;
+};
+
+__global__ void __launch_bounds__(256)
+pack_x_gather_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __restrict__ xlo, const __grid_constant__ GatherGeo g) {
+  const long long total = (long long)g.CC * g.PA;
+  const long long iHW = (long long)g.iH * g.iW;
+  const long long inS = (long long)g.iD * iHW;
+  const int oHW = g.oH * g.oW, kHW = g.kH * g.kW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx / g.PA);
+    const long long p = idx - (long long)c8 * g.PA;
+    uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+    if (p < g.PTOT) {
+      const long long oS = (long long)g.oD * oHW;
+      const int b = (int)(p / oS);
+      int q = (int)(p - (long long)b * oS);
+      const int od = q / oHW; q -= od * oHW;
+      const int oh = q / g.oW;
+      const int ow = q - oh * g.oW;
+      __nv_bfloat16 vh[8], vl[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int kp = c8 * 8 + i;
+        float v = 0.f;
+        if (kp < g.Kp) {
+          const int ci = kp / g.taps;
+          int t = kp - ci * g.taps;
+          const int kd = t / kHW; t -= kd * kHW;
+          const int kh = t / g.kW;
+          const int kw = t - kh * g.kW;
+          const int id = od + kd - g.pD, ih = oh + kh - g.pH, iw = ow + kw - g.pW;
+          if ((unsigned)id < (unsigned)g.iD && (unsigned)ih < (unsigned)g.iH && (unsigned)iw < (unsigned)g.iW)
+            v = __ldg(x + ((long long)b * g.Cin + ci) * inS + (long long)id * iHW + (long long)ih * g.iW + iw);
+        }
+        split_bf16(v, vh[i], vl[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { h[i] = pack_bf16x2(vh[2 * i], vh[2 * i + 1]); l[i] = pack_bf16x2(vl[2 * i], vl[2 * i + 1]); }
+    }
+    xhi[idx] = make_uint4(h[0], h[1], h[2], h[3]);
+    if (xlo) xlo[idx] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// Wp[slab][ct][tap][c2][hl][CT] (uint4 = 8 input channels) : the forward B operand, K-major.  For one
+// (slab, channel tile) any run of consecutive taps is ONE contiguous block already in the shared-memory stage
+// layout ([tap][k-chunk][hi|lo][CT rows]), so the producer moves a whole tap group with a single bulk copy.
 __global__ void __launch_bounds__(256)
 pack_w_kernel(const float* __restrict__ W, uint4* __restrict__ wp, int Cin, int Cout, int taps, int NSLAB, int HL,
-              int tr_taps, const float* __restrict__ inv_ci) {
+              int CT, int tr_taps, const float* __restrict__ inv_ci) {
   const long long total = (long long)NSLAB * taps * HL * 2 * Cout;
+  const int n_ct = Cout / CT;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     long long t = idx;
-    const int co = (int)(t % Cout); t /= Cout;
-    const int c2 = (int)(t % 2); t /= 2;
+    const int cl = (int)(t % CT); t /= CT;
     const int hl = (int)(t % HL); t /= HL;
+    const int c2 = (int)(t % 2); t /= 2;
     const int tap = (int)(t % taps); t /= taps;
+    const int ct = (int)(t % n_ct); t /= n_ct;
     const int slab = (int)t;
+    const int co = ct * CT + cl;
     uint32_t o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -130,9 +185,10 @@ struct FwdParams {
   int RHL;                     // 1: r is consumed as single bf16 (hi only), 2: hi + lo
   long long PA, PR, PTOT;      // positions per chunk plane in Xp / Rp; real positions B*Qimg
   int MB, TILE_M, ntiles, SEGLEN;
-  int XST, WST, NACC;
+  int XST, WST, NACC, WG;      // WG: taps per weight stage (one bulk copy)
   int WP, plane, Qimg, oD, oH, oW;
   float kinv; int write_r;
+  int dbg;                     // HEBB_FWD_DBG bit mask (profiling only): 1 skip epilogue, 2 skip MMAs, 4 no y stores, 8 no r stores
   int seg_base[4]; int seg_tap_begin[5]; int tap_off[kMaxTaps];
   uint32_t x_stage_bytes, w_stage_bytes, off_w, off_misc;
   uint32_t tmem_cols;
@@ -213,28 +269,33 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
     // ===================== producer: bulk copies =====================
     if (elect_one()) {
       int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
+      const uint32_t w_tap_bytes = (uint32_t)p.HL * 2 * p.CT * 16;   // one tap: [k-chunk][hi|lo][CT rows]
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         const int tile = work / p.n_ct, ct = work - tile * p.n_ct;
         const long long p0 = (long long)tile * p.TILE_M;
-        for (int slab = 0; slab < p.NSLAB; ++slab) {
+        const int slab0 = (p.dbg & 64) ? (int)(blockIdx.x % (unsigned)p.NSLAB) : 0;
+        for (int s_i = 0; s_i < p.NSLAB; ++s_i) {
+          const int slab = (s_i + slab0) % p.NSLAB;
           for (int seg = 0; seg < p.nseg; ++seg) {
             mbar_wait(x_empty + 8 * xs, xph ^ 1, p.err, 1);
-            mbar_expect_tx(x_full + 8 * xs, p.x_stage_bytes);
+            mbar_expect_tx(x_full + 8 * xs, (p.dbg & 16) ? 0u : p.x_stage_bytes);
             const uint32_t dst = sbase + xs * p.x_stage_bytes;
-            for (int hl = 0; hl < p.HL; ++hl)
+            for (int hl = 0; hl < ((p.dbg & 16) ? 0 : p.HL); ++hl)
               for (int c = 0; c < 2; ++c)
                 bulk_g2s(dst + (hl * 2 + c) * p.SEGLEN * 16,
                          p.xp[hl] + (long long)(slab * 2 + c) * p.PA + p0 + p.seg_base[seg],
                          p.SEGLEN * 16, x_full + 8 * xs);
             if (++xs == p.XST) { xs = 0; xph ^= 1; }
-            for (int tap = p.seg_tap_begin[seg]; tap < p.seg_tap_begin[seg + 1]; ++tap) {
+            const int t_end = p.seg_tap_begin[seg + 1];
+            for (int t0 = p.seg_tap_begin[seg]; t0 < t_end; t0 += p.WG) {
+              const int nt = (t_end - t0 < p.WG) ? (t_end - t0) : p.WG;
+              const uint32_t bytes = (uint32_t)nt * w_tap_bytes;
               mbar_wait(w_empty + 8 * ws, wph ^ 1, p.err, 2);
-              mbar_expect_tx(w_full + 8 * ws, p.w_stage_bytes);
-              for (int hl = 0; hl < p.HL; ++hl)          // staged as [k-chunk][hl][CT rows]: hi and lo rows adjacent
-                for (int c2 = 0; c2 < 2; ++c2)
-                  bulk_g2s(sbase + p.off_w + ws * p.w_stage_bytes + (c2 * p.HL + hl) * p.CT * 16,
-                           p.wp + ((long long)(slab * p.taps + tap) * p.HL * 2 + hl * 2 + c2) * p.Cout + ct * p.CT,
-                           p.CT * 16, w_full + 8 * ws);
+              mbar_expect_tx(w_full + 8 * ws, (p.dbg & 32) ? 0u : bytes);
+              if (!(p.dbg & 32))
+                bulk_g2s(sbase + p.off_w + ws * p.w_stage_bytes,
+                         p.wp + ((long long)(slab * p.n_ct + ct) * p.taps + t0) * (w_tap_bytes >> 4), bytes,
+                         w_full + 8 * ws);
               if (++ws == p.WST) { ws = 0; wph ^= 1; }
             }
           }
@@ -253,6 +314,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       const int cw = (p.stackF ? 2 : 1) * p.CT;                   // TMEM columns per M-block
       const uint64_t a_hi64 = smem_desc_hi(p.SEGLEN * 16, 128);   // LBO: chunk stride, SBO: 8 positions
       const uint64_t b_hi64 = smem_desc_hi(p.HL * p.CT * 16, 128);
+      const uint32_t w_tap_bytes = (uint32_t)p.HL * 2 * p.CT * 16;
       int xs = 0, ws = 0, acc = 0; uint32_t xph = 0, wph = 0, aph = 0;
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
@@ -263,32 +325,37 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
           for (int seg = 0; seg < p.nseg; ++seg) {
             mbar_wait(x_full + 8 * xs, xph, p.err, 4);
             const uint32_t xa = sbase + xs * p.x_stage_bytes;
-            for (int tap = p.seg_tap_begin[seg]; tap < p.seg_tap_begin[seg + 1]; ++tap) {
+            const int t_end = p.seg_tap_begin[seg + 1];
+            for (int t0 = p.seg_tap_begin[seg]; t0 < t_end; t0 += p.WG) {
+              const int nt = (t_end - t0 < p.WG) ? (t_end - t0) : p.WG;
               mbar_wait(w_full + 8 * ws, wph, p.err, 5);
               tc_fence_after();
-              const uint32_t wa = sbase + p.off_w + ws * p.w_stage_bytes;
-              const uint32_t a_tap = xa + p.tap_off[tap] * 16;
               if (elect_one()) {
-                for (int h = 0; h < NH; ++h) {
-                  const uint64_t bh = smem_desc(b_hi64, wa + h * NP * 16);
-                  const uint64_t bl = smem_desc(b_hi64, wa + p.CT * 16 + h * NP * 16);
-                  for (int j = 0; j < p.MB; ++j) {
-                    const uint32_t a0 = a_tap + j * 2048;
-                    const uint64_t ah = smem_desc(a_hi64, a0);
-                    const uint32_t d = d0 + j * cw + h * NP;
-                    if (p.stackF) {          // x_hi*[w_hi|w_lo] -> columns [0,2CT) ; x_lo*w_hi -> columns [0,CT)
-                      const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
-                      umma_bf16(d, ah, bh, idesc2, accum);
-                      umma_bf16(d, al, bh, idesc, 1u);
-                    } else if (p.HL == 2) {
-                      const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
-                      umma_bf16(d, ah, bl, idesc, accum);
-                      umma_bf16(d, al, bh, idesc, 1u);
-                      umma_bf16(d, ah, bh, idesc, 1u);
-                    } else {
-                      umma_bf16(d, ah, bh, idesc, accum);
+                for (int ti = 0; ti < ((p.dbg & 2) ? 0 : nt); ++ti) {
+                  const uint32_t wa = sbase + p.off_w + ws * p.w_stage_bytes + ti * w_tap_bytes;
+                  const uint32_t a_tap = xa + p.tap_off[t0 + ti] * 16;
+                  for (int h = 0; h < NH; ++h) {
+                    const uint64_t bh = smem_desc(b_hi64, wa + h * NP * 16);
+                    const uint64_t bl = smem_desc(b_hi64, wa + p.CT * 16 + h * NP * 16);
+                    for (int j = 0; j < p.MB; ++j) {
+                      const uint32_t a0 = a_tap + j * 2048;
+                      const uint64_t ah = smem_desc(a_hi64, a0);
+                      const uint32_t d = d0 + j * cw + h * NP;
+                      if (p.stackF) {          // x_hi*[w_hi|w_lo] -> columns [0,2CT) ; x_lo*w_hi -> columns [0,CT)
+                        const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
+                        umma_bf16(d, ah, bh, idesc2, accum);
+                        umma_bf16(d, al, bh, idesc, 1u);
+                      } else if (p.HL == 2) {
+                        const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
+                        umma_bf16(d, ah, bl, idesc, accum);
+                        umma_bf16(d, al, bh, idesc, 1u);
+                        umma_bf16(d, ah, bh, idesc, 1u);
+                      } else {
+                        umma_bf16(d, ah, bh, idesc, accum);
+                      }
                     }
                   }
+                  accum = 1u;
                 }
                 umma_commit(w_empty + 8 * ws);
               }
@@ -337,7 +404,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       }
       mbar_wait(t_full + 8 * acc, aph, p.err, 6);
       tc_fence_after();
-      for (int j = 0; j < p.MB; ++j) {
+      for (int j = 0; j < ((p.dbg & 1) ? 0 : p.MB); ++j) {
         const long long pp = (long long)tile * p.TILE_M + j * 128 + row;
         const unsigned pp32 = (unsigned)pp;                 // the planner guarantees PR < 2^31: 32-bit divisions
         const int b = (int)(pp32 / (unsigned)p.Qimg);
@@ -345,7 +412,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
         const int od = (int)((unsigned)q / (unsigned)p.plane); q -= od * p.plane;
         const int oh = (int)((unsigned)q / (unsigned)p.WP);
         const int ow = q - oh * p.WP;
-        const bool valid = (od < p.oD) && (oh < p.oH) && (ow < p.oW) && (pp < p.PTOT);
+        const bool valid = (od < p.oD) && (oh < p.oH) && (ow < p.oW) && (pp < p.PTOT) && !(p.dbg & 4);
         const long long s = (long long)od * oHW + (long long)oh * p.oW + ow;
         float* yb = p.y + ((long long)b * p.Cout + cbase) * outS + s;
         const long long tS = (long long)p.tD * p.tH * p.tW;
@@ -392,6 +459,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                 ol4[i] = pack_bf16x2(l2[0], l2[1]);
               }
               const long long ridx = (long long)g8 * p.PR + pp;
+              if (p.dbg & 8) continue;
               p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
               if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
             }
@@ -468,6 +536,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                   ol4[i] = pack_bf16x2(l2[0], l2[1]);
                 }
                 const long long ridx = (long long)(c0 / 8 + g8) * p.PR + pp;
+                if (p.dbg & 8) continue;
                 p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
                 if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
               }
@@ -510,7 +579,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                 ol4[i] = pack_bf16x2(l2[0], l2[1]);
               }
               const long long ridx = (long long)(c0 / 8 + g8) * p.PR + pp;
-              if (pp < p.PR) {
+              if (pp < p.PR && !(p.dbg & 8)) {
                 p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
                 if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
               }
@@ -1009,7 +1078,7 @@ struct Plan {
   long long PTOT, PR, PA;
   int maxshift;
   // forward
-  int f_HL, MB, TILE_M, f_SEGLEN, XST, WST, NACC, f_nseg, f_ntiles, CT, n_ct, stackF;
+  int f_HL, MB, TILE_M, f_SEGLEN, XST, WST, NACC, WG, f_nseg, f_ntiles, CT, n_ct, stackF;
   uint32_t f_x_stage, f_w_stage, f_off_w, f_off_misc, f_smem, f_tmem;
   // dW
   int d_HL, BLK, d_SEGLEN, d_by_kh, ngrp, CM, n_cin_tiles, CN, n_cout_tiles, PS, total_blocks, blocks_per_split, ST, CinP;
@@ -1023,7 +1092,21 @@ struct Plan {
 // A transposed conv with kernel == stride == 2 (3-D) and no padding is a 1x1 conv onto Cout*8
 // "(co, offset)" channels followed by a pixel shuffle; its plasticity update is the matching 1x1 update.
 static bool equivalent_1x1(const Geo& g, Geo* e) {
-  if (!g.transposed) { *e = g; return true; }
+  if (!g.transposed) {
+    *e = g;
+    // Few input channels (first layers: 1 or 3): a 16-channel K slab would be mostly zero padding and every
+    // tap would cost a full MMA.  Gather the patch at pack time instead — (ci, tap) pairs become Cin*taps
+    // pseudo-channels of a 1x1 layer over the OUTPUT grid; [Cout][Cin][taps] is already that layer's weight.
+    if (g.Cin <= 4 && g.taps > 1 && g.sD == 1 && g.sH == 1 && g.sW == 1 && g.Cin * g.taps <= 128) {
+      e->Cin = g.Cin * g.taps;
+      e->kD = e->kH = e->kW = 1;
+      e->pD = e->pH = e->pW = e->qD = e->qH = e->qW = 0;
+      e->iD = g.oD; e->iH = g.oH; e->iW = g.oW;
+      e->taps = 1; e->K = e->Cin;
+      e->inS = g.outS;
+    }
+    return true;
+  }
   if (g.nd != 3 || g.kD != 2 || g.kH != 2 || g.kW != 2 || g.sD != 2 || g.sH != 2 || g.sW != 2) return false;
   if (g.pD || g.pH || g.pW || g.qD || g.qH || g.qW) return false;
   if ((long long)g.Cout * 8 > 8192) return false;
@@ -1067,8 +1150,13 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
   static const bool want_stackf = [] { const char* e = getenv("HEBB_STACKF"); return e && e[0] == '1'; }();
   q.stackF = (want_stackf && q.f_HL == 2 && q.CT <= 64 && !g.transposed) ? 1 : 0;
   const int fcw = (q.stackF ? 2 : 1) * q.CT;
-  q.f_w_stage = (uint32_t)q.f_HL * 2 * q.CT * 16;
+  const uint32_t w_tap = (uint32_t)q.f_HL * 2 * q.CT * 16;     // one tap of one slab: [k-chunk][hi|lo][CT rows]
   const uint32_t misc = (uint32_t)(10 * q.CT * 4 + 8 * 64 + 64);
+  // Weight stages hold a GROUP of taps moved by one bulk copy: every stage costs the producer and the MMA
+  // warp a full mbarrier round trip (~600 cycles measured with per-tap stages, which starved the tensor
+  // pipe), so prefer the largest group (a whole kd plane, else a kernel row, else one tap) that fits.
+  const int seg_taps = g.kH * g.kW;
+  const int wg_opts[3] = {seg_taps, g.kW, 1};
   bool found = false;
   for (int mb = 4; mb >= 1 && !found; mb >>= 1) {
     if (mb > 1 && mb * fcw > 256) continue;
@@ -1077,11 +1165,16 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
     const int seglen = round_up_i(128 * mb + halo, 8);
     const uint32_t xst = (uint32_t)q.f_HL * 2 * seglen * 16;
     for (int nx = 3; nx >= 2 && !found; --nx) {
-      for (int nw = 8; nw >= 2 && !found; nw >>= 1) {
-        const uint32_t tot = nx * xst + nw * q.f_w_stage + misc + 256;
-        if (tot <= (uint32_t)kSmemLimit - 1024) {
-          q.MB = mb; q.TILE_M = 128 * mb; q.f_SEGLEN = seglen; q.XST = nx; q.WST = nw;
-          q.f_x_stage = xst; found = true;
+      for (int wi = 0; wi < 3 && !found; ++wi) {
+        const int wg = wg_opts[wi];
+        if (wi > 0 && wg == wg_opts[wi - 1]) continue;
+        for (int nw = (wg == 1 ? 8 : 4); nw >= 2 && !found; --nw) {
+          const uint32_t tot = nx * xst + nw * wg * w_tap + misc + 256;
+          if (tot <= (uint32_t)kSmemLimit - 1024) {
+            q.MB = mb; q.TILE_M = 128 * mb; q.f_SEGLEN = seglen; q.XST = nx; q.WST = nw; q.WG = wg;
+            q.f_w_stage = (uint32_t)wg * w_tap;
+            q.f_x_stage = xst; found = true;
+          }
         }
       }
     }
@@ -1227,7 +1320,7 @@ int tc_describe_plan(const Geo& g0, int prec, int* o, int n) {
   if (!equivalent_1x1(g0, &g) || !plan_layer(g, prec, &P)) return 0;
   const int v[] = {P.MB, P.f_SEGLEN, P.XST, P.WST, P.NACC, (int)P.f_tmem, P.f_ntiles, (int)P.f_smem,
                    P.d_by_kh, P.CM, P.CN, P.BLK, P.ST, P.d_SEGLEN, P.ngrp, P.n_cin_tiles, P.n_cout_tiles, P.PS,
-                   P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct, P.nrep};
+                   P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct, P.nrep, P.WG};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < m; ++i) o[i] = v[i];
   return m;
@@ -1275,13 +1368,21 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   PackGeo pg;
   pg.B = g.B; pg.Cin = g.Cin; pg.iD = g.iD; pg.iH = g.iH; pg.iW = g.iW; pg.pD = g.pD; pg.pH = g.pH; pg.pW = g.pW;
   pg.HP = P.HP; pg.WP = P.WP; pg.plane = P.plane; pg.Qimg = P.Qimg; pg.CC = P.CC; pg.PA = P.PA; pg.PTOT = P.PTOT;
-  if (do_pack) {
+  const bool gathered = !tr && g.taps != g0.taps;      // few-input-channel layer re-stated as a 1x1 layer
+  if (do_pack && gathered) {
+    GatherGeo gg;
+    gg.B = g0.B; gg.Cin = g0.Cin; gg.iD = g0.iD; gg.iH = g0.iH; gg.iW = g0.iW; gg.pD = g0.pD; gg.pH = g0.pH; gg.pW = g0.pW;
+    gg.kH = g0.kH; gg.kW = g0.kW; gg.taps = g0.taps; gg.oD = g0.oD; gg.oH = g0.oH; gg.oW = g0.oW; gg.Kp = g.Cin;
+    gg.CC = P.CC; gg.PA = P.PA; gg.PTOT = P.PTOT;
+    pack_x_gather_kernel<<<ew_grid((long long)P.CC * P.PA), 256, 0, st>>>(x, xp0, xp1, gg);
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  } else if (do_pack) {
     pack_x_kernel<<<ew_grid((long long)P.CC * P.PA), 256, 0, st>>>(x, xp0, xp1, pg);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
   if (do_pack) {
     const long long n = (long long)P.NSLAB * g.taps * P.f_HL * 2 * g.Cout;
-    pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL, tr ? g0.taps : 0,
+    pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL, P.CT, tr ? g0.taps : 0,
                                               (tr && (flags & HEBB_F_WNRM)) ? inv : nullptr);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
@@ -1292,9 +1393,11 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   f.y = y; f.winner = winner; f.inv = ((flags & HEBB_F_WNRM) && !tr) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = err;
   f.tr = tr ? 1 : 0; f.tD = g0.oD; f.tH = g0.oH; f.tW = g0.oW; f.CoutR = g0.Cout;
   f.Cout = g.Cout; f.CC = P.CC; f.NSLAB = P.NSLAB; f.taps = g.taps; f.nseg = P.f_nseg; f.HL = P.f_HL; f.RHL = P.d_HL;
+  static const int fwd_dbg = [] { const char* e = getenv("HEBB_FWD_DBG"); return e ? atoi(e) : 0; }();
+  f.dbg = fwd_dbg;
   f.stackF = P.stackF; f.CT = P.CT; f.n_ct = P.n_ct; f.fuse = (P.n_ct == 1) ? 1 : 0;   // transposed: grouped softmax when Cout*8 <= 512
   f.PA = P.PA; f.PR = P.PR; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
-  f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC;
+  f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC; f.WG = P.WG;
   f.WP = P.WP; f.plane = P.plane; f.Qimg = P.Qimg; f.oD = g.oD; f.oH = g.oH; f.oW = g.oW;
   f.kinv = kinv; f.write_r = upd ? 1 : 0;
   for (int s = 0; s < 4; ++s) f.seg_base[s] = s * P.plane;
