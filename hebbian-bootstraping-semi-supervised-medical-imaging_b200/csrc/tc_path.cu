@@ -233,6 +233,49 @@ __device__ __forceinline__ void ld_acc(uint32_t a, int second, uint32_t (&v)[CH]
   }
 }
 
+// One tap of one 16-channel slab for all M-blocks of the tile (called by the elected lane of the MMA warp).
+// a_tap / wa are shared-memory byte addresses of the tap's first position and of the tap's weight tile.
+// Operand-A collector hints: an instruction that shares its A tile (128 positions x 16 channels, 4 KB) with
+// the next one keeps it and the next re-uses it instead of fetching it from shared memory again -- small-N
+// instructions are bound by that fetch (profiles/README.md).
+template <int ACC>
+__device__ __forceinline__ void fwd_issue(const FwdParams& p, int mode, uint32_t a_tap, uint32_t wa, uint32_t d0, int cw,
+                                          int NP, uint32_t a_lbo, uint32_t a_hi32, uint32_t b_lbo, uint32_t b_hi32,
+                                          uint32_t idesc, uint32_t idesc2) {
+  uint32_t ah = a_lbo | (a_tap >> 4);                              // x_hi tile of M-block 0
+  uint32_t al = a_lbo | ((a_tap + 2u * p.SEGLEN * 16u) >> 4);      // x_lo tile
+  const uint32_t bh = b_lbo | (wa >> 4);                           // w_hi rows
+  const uint32_t bl = b_lbo | ((wa + (uint32_t)p.CT * 16u) >> 4);  // w_lo rows
+  uint32_t d = d0;
+  if (mode == 1) {                 // bf16x3, one N block: x_hi*w_lo + x_hi*w_hi + x_lo*w_hi
+    for (int j = 0; j < p.MB; ++j, ah += 128u, al += 128u, d += cw) {
+      umma_lo<1, ACC>(d, ah, a_hi32, bl, b_hi32, idesc);
+      umma_lo<3, 1>(d, ah, a_hi32, bh, b_hi32, idesc);
+      umma_lo<0, 1>(d, al, a_hi32, bh, b_hi32, idesc);
+    }
+  } else if (mode == 2) {          // two N halves (CT > 256): x_hi serves four instructions, x_lo two
+    const uint32_t bh1 = bh + (uint32_t)NP, bl1 = bl + (uint32_t)NP;
+    for (int j = 0; j < p.MB; ++j, ah += 128u, al += 128u, d += cw) {
+      umma_lo<1, ACC>(d, ah, a_hi32, bl, b_hi32, idesc);
+      umma_lo<2, 1>(d, ah, a_hi32, bh, b_hi32, idesc);
+      umma_lo<2, ACC>(d + NP, ah, a_hi32, bl1, b_hi32, idesc);
+      umma_lo<3, 1>(d + NP, ah, a_hi32, bh1, b_hi32, idesc);
+      umma_lo<1, 1>(d, al, a_hi32, bh, b_hi32, idesc);
+      umma_lo<3, 1>(d + NP, al, a_hi32, bh1, b_hi32, idesc);
+    }
+  } else if (mode == 3) {          // stacked [w_hi | w_lo]: x_hi*[w_hi|w_lo] -> columns [0,2CT) ; x_lo*w_hi -> [0,CT)
+    for (int j = 0; j < p.MB; ++j, ah += 128u, al += 128u, d += cw) {
+      umma_lo<0, ACC>(d, ah, a_hi32, bh, b_hi32, idesc2);
+      umma_lo<0, 1>(d, al, a_hi32, bh, b_hi32, idesc);
+    }
+  } else {                         // single bf16 pass
+    const int NH = p.CT / NP;
+    for (int j = 0; j < p.MB; ++j, ah += 128u, d += cw)
+      for (int h = 0; h < NH; ++h)
+        umma_lo<0, ACC>(d + h * NP, ah, a_hi32, bh + (uint32_t)(h * NP), b_hi32, idesc);
+  }
+}
+
 template <int CH>
 __global__ void __launch_bounds__(320, 1)
 fwd_swta_kernel(const __grid_constant__ FwdParams p) {
@@ -314,6 +357,9 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       const int cw = (p.stackF ? 2 : 1) * p.CT;                   // TMEM columns per M-block
       const uint64_t a_hi64 = smem_desc_hi(p.SEGLEN * 16, 128);   // LBO: chunk stride, SBO: 8 positions
       const uint64_t b_hi64 = smem_desc_hi(p.HL * p.CT * 16, 128);
+      const uint32_t a_lbo = (uint32_t)a_hi64, a_hi32 = (uint32_t)(a_hi64 >> 32);
+      const uint32_t b_lbo = (uint32_t)b_hi64, b_hi32 = (uint32_t)(b_hi64 >> 32);
+      const int mode = p.stackF ? 3 : (p.HL == 2 ? (NH == 1 ? 1 : 2) : 0);
       const uint32_t w_tap_bytes = (uint32_t)p.HL * 2 * p.CT * 16;
       int xs = 0, ws = 0, acc = 0; uint32_t xph = 0, wph = 0, aph = 0;
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
@@ -331,31 +377,17 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               mbar_wait(w_full + 8 * ws, wph, p.err, 5);
               tc_fence_after();
               if (elect_one()) {
-                for (int ti = 0; ti < ((p.dbg & 2) ? 0 : nt); ++ti) {
-                  const uint32_t wa = sbase + p.off_w + ws * p.w_stage_bytes + ti * w_tap_bytes;
-                  const uint32_t a_tap = xa + p.tap_off[t0 + ti] * 16;
-                  for (int h = 0; h < NH; ++h) {
-                    const uint64_t bh = smem_desc(b_hi64, wa + h * NP * 16);
-                    const uint64_t bl = smem_desc(b_hi64, wa + p.CT * 16 + h * NP * 16);
-                    for (int j = 0; j < p.MB; ++j) {
-                      const uint32_t a0 = a_tap + j * 2048;
-                      const uint64_t ah = smem_desc(a_hi64, a0);
-                      const uint32_t d = d0 + j * cw + h * NP;
-                      if (p.stackF) {          // x_hi*[w_hi|w_lo] -> columns [0,2CT) ; x_lo*w_hi -> columns [0,CT)
-                        const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
-                        umma_bf16(d, ah, bh, idesc2, accum);
-                        umma_bf16(d, al, bh, idesc, 1u);
-                      } else if (p.HL == 2) {
-                        const uint64_t al = smem_desc(a_hi64, a0 + 2 * p.SEGLEN * 16);
-                        umma_bf16(d, ah, bl, idesc, accum);
-                        umma_bf16(d, al, bh, idesc, 1u);
-                        umma_bf16(d, ah, bh, idesc, 1u);
-                      } else {
-                        umma_bf16(d, ah, bh, idesc, accum);
-                      }
-                    }
-                  }
-                  accum = 1u;
+                const uint32_t wst = sbase + p.off_w + ws * p.w_stage_bytes;
+                const int ntd = (p.dbg & 2) ? 0 : nt;
+                if (accum == 0u && ntd > 0) {          // first tap of a tile overwrites the accumulators
+                  fwd_issue<0>(p, mode, xa + p.tap_off[t0] * 16, wst, d0, cw, NP, a_lbo, a_hi32, b_lbo, b_hi32, idesc, idesc2);
+                  for (int ti = 1; ti < ntd; ++ti)
+                    fwd_issue<1>(p, mode, xa + p.tap_off[t0 + ti] * 16, wst + ti * w_tap_bytes, d0, cw, NP, a_lbo, a_hi32,
+                                 b_lbo, b_hi32, idesc, idesc2);
+                } else {
+                  for (int ti = 0; ti < ntd; ++ti)
+                    fwd_issue<1>(p, mode, xa + p.tap_off[t0 + ti] * 16, wst + ti * w_tap_bytes, d0, cw, NP, a_lbo, a_hi32,
+                                 b_lbo, b_hi32, idesc, idesc2);
                 }
                 umma_commit(w_empty + 8 * ws);
               }
@@ -928,17 +960,17 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
               const uint32_t acc = (ks == 0) ? accum0 : 1u;
               if (mode <= 1) {                 // single bf16 pass, or [hi;lo] x [hi|lo] in one instruction
                 umma_bf16(d, ah, bh, idesc, acc);
-              } else if (mode == 2) {          // rows stacked: ([x_hi;x_lo], r_hi) + ([x_hi;x_lo], r_lo)
-                umma_bf16(d, ah, smem_desc(b_hi64, b0 + r_hl_stride), idesc, acc);
-                umma_bf16(d, ah, bh, idesc, 1u);
+              } else if (mode == 2) {          // rows stacked: ([x_hi;x_lo], r_hi) + ([x_hi;x_lo], r_lo): same A twice
+                umma_bf16_keep_a(d, ah, smem_desc(b_hi64, b0 + r_hl_stride), idesc, acc);
+                umma_bf16_reuse_a(d, ah, bh, idesc, 1u);
               } else if (mode == 3) {          // columns stacked: (x_lo, [r_hi|r_lo]) + (x_hi, [r_hi|r_lo])
                 umma_bf16(d, smem_desc(a_hi64, a0 + x_hl_stride), bh, idesc, acc);
                 umma_bf16(d, ah, bh, idesc, 1u);
               } else {                         // classic 3-pass split
                 const uint64_t al = smem_desc(a_hi64, a0 + x_hl_stride), bl = smem_desc(b_hi64, b0 + r_hl_stride);
-                umma_bf16(d, ah, bl, idesc, acc);
+                umma_bf16_keep_a(d, ah, bl, idesc, acc);
+                umma_bf16_reuse_a(d, ah, bh, idesc, 1u);
                 umma_bf16(d, al, bh, idesc, 1u);
-                umma_bf16(d, ah, bh, idesc, 1u);
               }
             }
           }

@@ -91,6 +91,53 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same, with the A-operand collector hint: the first instruction of a pair that shares its A tile keeps the
+// fetched tile in the collector (SASS A_KEEP), the second re-uses it instead of fetching it again (A_REUSE).
+__device__ __forceinline__ void umma_bf16_keep_a(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_reuse_a(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_use_a(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {     // re-use and keep for a further use
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Lean issue form for the hot loops: descriptors as (lo, hi) 32-bit halves -- start address and LBO live in
+// the low word, SBO/version in the constant high word, so stepping an operand is one 32-bit add -- and the
+// accumulate flag / collector hint as template constants (no predicate set-up per instruction).
+// COLL: 0 discard (default), 1 fill (fetch A and keep it), 2 use (re-use, keep), 3 lastuse (re-use, drop).
+template <int COLL, int ACC>
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc) {
+#define HEBB_UMMA_LO(SUFFIX)                                                                  \
+  asm volatile(                                                                               \
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                          \
+      "setp.ne.b32 p, %6, 0;\n\t"                                                             \
+      "mov.b64 da, {%1, %2};\n\t"                                                             \
+      "mov.b64 db, {%3, %4};\n\t"                                                             \
+      "tcgen05.mma.cta_group::1.kind::f16" SUFFIX " [%0], da, db, %5, p;\n\t}\n"              \
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC) : "memory")
+  if (COLL == 1) HEBB_UMMA_LO(".collector::a::fill");
+  else if (COLL == 2) HEBB_UMMA_LO(".collector::a::use");
+  else if (COLL == 3) HEBB_UMMA_LO(".collector::a::lastuse");
+  else HEBB_UMMA_LO("");
+#undef HEBB_UMMA_LO
+}
 // Arrives once on `bar` when every MMA issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
