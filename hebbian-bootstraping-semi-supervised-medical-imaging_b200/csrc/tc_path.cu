@@ -872,6 +872,42 @@ struct DwParams {
   uint32_t stage_bytes, x_bytes, off_bar, tmem_cols;
 };
 
+// All MMAs of one staged position block (called by the elected lane of the MMA warp): for every super-tap of
+// this CTA's tap group, BLK/16 k-steps of 16 positions.  MODE: 1 one instruction per k-step (bf16, or both
+// operands precision-stacked), 2 rows stacked (same A twice: keep / re-use), 3 columns stacked, 4 classic
+// 3-product split.  ACC0 = 0 on the first block of the split (overwrite the accumulators).
+template <int MODE, int ACC0>
+__device__ __forceinline__ void dw_issue(const DwParams& p, uint32_t xa, uint32_t ra, int st_b, int st_e, uint32_t tmem_base,
+                                         int colw, int ksteps, uint32_t a_lbo, uint32_t a_hi32, uint32_t b_lbo,
+                                         uint32_t b_hi32, uint32_t idesc, uint32_t xhl16, uint32_t rhl16) {
+  const uint32_t bh0 = b_lbo | (ra >> 4);
+  uint32_t d = tmem_base;
+  for (int stp = st_b; stp < st_e; ++stp, d += colw) {
+    uint32_t ah = a_lbo | ((xa + p.st_off[stp] * 16) >> 4);
+    uint32_t bh = bh0;
+#define HEBB_DW_STEP(ACC)                                                        \
+    if (MODE == 2) {                                                             \
+      umma_lo<1, ACC>(d, ah, a_hi32, bh + rhl16, b_hi32, idesc);                 \
+      umma_lo<3, 1>(d, ah, a_hi32, bh, b_hi32, idesc);                           \
+    } else if (MODE == 3) {                                                      \
+      umma_lo<0, ACC>(d, ah + xhl16, a_hi32, bh, b_hi32, idesc);                 \
+      umma_lo<0, 1>(d, ah, a_hi32, bh, b_hi32, idesc);                           \
+    } else if (MODE == 4) {                                                      \
+      umma_lo<1, ACC>(d, ah, a_hi32, bh + rhl16, b_hi32, idesc);                 \
+      umma_lo<3, 1>(d, ah, a_hi32, bh, b_hi32, idesc);                           \
+      umma_lo<0, 1>(d, ah + xhl16, a_hi32, bh, b_hi32, idesc);                   \
+    } else {                                                                     \
+      umma_lo<0, ACC>(d, ah, a_hi32, bh, b_hi32, idesc);                         \
+    }
+    HEBB_DW_STEP(ACC0)
+    for (int ks = 1; ks < ksteps; ++ks) {
+      ah += 16u; bh += 16u;                    // next 16 positions: 256 bytes in both operands
+      HEBB_DW_STEP(1)
+    }
+#undef HEBB_DW_STEP
+  }
+}
+
 __global__ void __launch_bounds__(192, 1)
 dw_swta_kernel(const __grid_constant__ DwParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -940,6 +976,9 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
       const uint32_t idesc = idesc_bf16(p.CM, Neff, 1, 1);
       const uint64_t a_hi64 = smem_desc_hi(128, p.SEGLEN * 16);   // MN-major: LBO = next 8 positions, SBO = next chunk
       const uint64_t b_hi64 = smem_desc_hi(128, p.BLK * 16);
+      const uint32_t a_lbo = (uint32_t)a_hi64, a_hi32 = (uint32_t)(a_hi64 >> 32);
+      const uint32_t b_lbo = (uint32_t)b_hi64, b_hi32 = (uint32_t)(b_hi64 >> 32);
+      const uint32_t xhl16 = x_hl_stride >> 4, rhl16 = r_hl_stride >> 4;
       int st = 0; uint32_t ph = 0;
       const int ksteps = p.BLK / 16;
       const int mode = (p.HL == 2) ? (p.stackM ? (p.stackN ? 1 : 2) : (p.stackN ? 3 : 4)) : 0;
@@ -948,31 +987,17 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
         tc_fence_after();
         const uint32_t xa = sbase + st * p.stage_bytes;
         const uint32_t ra = xa + r_off;
-        const uint32_t accum0 = (blk == blk_b) ? 0u : 1u;
         if (elect_one()) {
-          for (int stp = st_b; stp < st_e; ++stp) {
-            const uint32_t d = tmem_base + (stp - st_b) * colw;
-            const uint32_t a_tap = xa + p.st_off[stp] * 16;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t a0 = a_tap + ks * 256;
-              const uint32_t b0 = ra + ks * 256;
-              const uint64_t ah = smem_desc(a_hi64, a0), bh = smem_desc(b_hi64, b0);
-              const uint32_t acc = (ks == 0) ? accum0 : 1u;
-              if (mode <= 1) {                 // single bf16 pass, or [hi;lo] x [hi|lo] in one instruction
-                umma_bf16(d, ah, bh, idesc, acc);
-              } else if (mode == 2) {          // rows stacked: ([x_hi;x_lo], r_hi) + ([x_hi;x_lo], r_lo): same A twice
-                umma_bf16_keep_a(d, ah, smem_desc(b_hi64, b0 + r_hl_stride), idesc, acc);
-                umma_bf16_reuse_a(d, ah, bh, idesc, 1u);
-              } else if (mode == 3) {          // columns stacked: (x_lo, [r_hi|r_lo]) + (x_hi, [r_hi|r_lo])
-                umma_bf16(d, smem_desc(a_hi64, a0 + x_hl_stride), bh, idesc, acc);
-                umma_bf16(d, ah, bh, idesc, 1u);
-              } else {                         // classic 3-pass split
-                const uint64_t al = smem_desc(a_hi64, a0 + x_hl_stride), bl = smem_desc(b_hi64, b0 + r_hl_stride);
-                umma_bf16_keep_a(d, ah, bl, idesc, acc);
-                umma_bf16_reuse_a(d, ah, bh, idesc, 1u);
-                umma_bf16(d, al, bh, idesc, 1u);
-              }
-            }
+          const bool first = (blk == blk_b);
+          switch (mode) {
+            case 2: first ? dw_issue<2, 0>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16)
+                          : dw_issue<2, 1>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16); break;
+            case 3: first ? dw_issue<3, 0>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16)
+                          : dw_issue<3, 1>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16); break;
+            case 4: first ? dw_issue<4, 0>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16)
+                          : dw_issue<4, 1>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16); break;
+            default: first ? dw_issue<1, 0>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16)
+                           : dw_issue<1, 1>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16); break;
           }
           umma_commit(empty + 8 * st);
         }
