@@ -26,6 +26,9 @@
 #include "umma.cuh"
 #include <cstdlib>
 
+// the single-pass instantiations of the forward epilogue leave the generic multi-pass code unreachable
+#pragma nv_diag_suppress 128
+
 namespace hebb {
 
 using namespace ptx;
@@ -85,44 +88,62 @@ struct GatherGeo {
 
 __global__ void __launch_bounds__(256)
 pack_x_gather_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __restrict__ xlo, const __grid_constant__ GatherGeo g) {
-  const long long total = (long long)g.CC * g.PA;
+  // one thread per output position: walks (ci, kd, kh, kw) with counters (no divisions per element) and
+  // shifts each bf16 into a 128-bit register window that is stored once per 8 pseudo-channels
   const long long iHW = (long long)g.iH * g.iW;
   const long long inS = (long long)g.iD * iHW;
-  const int oHW = g.oH * g.oW, kHW = g.kH * g.kW;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx / g.PA);
-    const long long p = idx - (long long)c8 * g.PA;
-    uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
-    if (p < g.PTOT) {
-      const long long oS = (long long)g.oD * oHW;
-      const int b = (int)(p / oS);
+  const int oHW = g.oH * g.oW;
+  const long long oS = (long long)g.oD * oHW;
+  const int kD = g.taps / (g.kH * g.kW);
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < g.PA;
+       p += (long long)gridDim.x * blockDim.x) {
+    const bool real = p < g.PTOT;
+    int b = 0, od = 0, oh = 0, ow = 0;
+    if (real) {
+      b = (int)(p / oS);
       int q = (int)(p - (long long)b * oS);
-      const int od = q / oHW; q -= od * oHW;
-      const int oh = q / g.oW;
-      const int ow = q - oh * g.oW;
-      __nv_bfloat16 vh[8], vl[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int kp = c8 * 8 + i;
-        float v = 0.f;
-        if (kp < g.Kp) {
-          const int ci = kp / g.taps;
-          int t = kp - ci * g.taps;
-          const int kd = t / kHW; t -= kd * kHW;
-          const int kh = t / g.kW;
-          const int kw = t - kh * g.kW;
-          const int id = od + kd - g.pD, ih = oh + kh - g.pH, iw = ow + kw - g.pW;
-          if ((unsigned)id < (unsigned)g.iD && (unsigned)ih < (unsigned)g.iH && (unsigned)iw < (unsigned)g.iW)
-            v = __ldg(x + ((long long)b * g.Cin + ci) * inS + (long long)id * iHW + (long long)ih * g.iW + iw);
-        }
-        split_bf16(v, vh[i], vl[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { h[i] = pack_bf16x2(vh[2 * i], vh[2 * i + 1]); l[i] = pack_bf16x2(vl[2 * i], vl[2 * i + 1]); }
+      od = q / oHW; q -= od * oHW;
+      oh = q / g.oW;
+      ow = q - oh * g.oW;
     }
-    xhi[idx] = make_uint4(h[0], h[1], h[2], h[3]);
-    if (xlo) xlo[idx] = make_uint4(l[0], l[1], l[2], l[3]);
+    unsigned long long h0 = 0, h1 = 0, l0 = 0, l1 = 0;     // 8 x bf16 windows (hi and lo parts), oldest in the low bits
+    int filled = 0, c8 = 0;
+    const float* xb = x + (long long)b * g.Cin * inS;
+    for (int ci = 0; ci < g.Cin; ++ci) {
+      for (int kd = 0; kd < kD; ++kd) {
+        const int id = od + kd - g.pD;
+        for (int kh = 0; kh < g.kH; ++kh) {
+          const int ih = oh + kh - g.pH;
+          const bool row_ok = real && (unsigned)id < (unsigned)g.iD && (unsigned)ih < (unsigned)g.iH;
+          const float* row = xb + (long long)ci * inS + (long long)id * iHW + (long long)ih * g.iW;
+          for (int kw = 0; kw < g.kW; ++kw) {
+            const int iw = ow + kw - g.pW;
+            float v = 0.f;
+            if (row_ok && (unsigned)iw < (unsigned)g.iW) v = __ldg(row + iw);
+            __nv_bfloat16 vh, vl;
+            split_bf16(v, vh, vl);
+            h0 = (h0 >> 16) | (h1 << 48); h1 = (h1 >> 16) | ((unsigned long long)__bfloat16_as_ushort(vh) << 48);
+            l0 = (l0 >> 16) | (l1 << 48); l1 = (l1 >> 16) | ((unsigned long long)__bfloat16_as_ushort(vl) << 48);
+            if (++filled == 8) {
+              const long long idx = (long long)c8 * g.PA + p;
+              xhi[idx] = make_uint4((uint32_t)h0, (uint32_t)(h0 >> 32), (uint32_t)h1, (uint32_t)(h1 >> 32));
+              if (xlo) xlo[idx] = make_uint4((uint32_t)l0, (uint32_t)(l0 >> 32), (uint32_t)l1, (uint32_t)(l1 >> 32));
+              filled = 0; ++c8;
+            }
+          }
+        }
+      }
+    }
+    for (; c8 < g.CC; ++c8) {          // zero-pad the last partly filled chunk and any wholly empty ones
+      for (; filled < 8; ++filled) {
+        h0 = (h0 >> 16) | (h1 << 48); h1 >>= 16;
+        l0 = (l0 >> 16) | (l1 << 48); l1 >>= 16;
+      }
+      const long long idx = (long long)c8 * g.PA + p;
+      xhi[idx] = make_uint4((uint32_t)h0, (uint32_t)(h0 >> 32), (uint32_t)h1, (uint32_t)(h1 >> 32));
+      if (xlo) xlo[idx] = make_uint4((uint32_t)l0, (uint32_t)(l0 >> 32), (uint32_t)l1, (uint32_t)(l1 >> 32));
+      filled = 0; h0 = h1 = l0 = l1 = 0;
+    }
   }
 }
 
@@ -276,7 +297,9 @@ __device__ __forceinline__ void fwd_issue(const FwdParams& p, int mode, uint32_t
   }
 }
 
-template <int CH>
+// SP > 0: the whole channel row (SP * CH <= 64 values) is held in registers -- a single pass out of TMEM with
+// one exp per value and per-thread running column sums; SP == 0: generic multi-pass epilogue.
+template <int CH, int SP>
 __global__ void __launch_bounds__(320, 1)
 fwd_swta_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -420,6 +443,10 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
     uint32_t aph = 0;
     int cur_ct = -1;
     int it = 0;
+    constexpr int NV = SP > 0 ? SP * CH : 1;
+    float racc[NV];                           // SP > 0: this thread's running sum of r per channel
+#pragma unroll
+    for (int i = 0; i < NV; ++i) racc[i] = 0.f;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
       const int acc = (p.NACC == 2) ? (it & 1) : 0;
       if (acc != eset) continue;            // the other set's buffer (NACC == 1: set 1 has nothing to do)
@@ -458,45 +485,65 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { mx8[i] = -INFINITY; best8[i] = -INFINITY; bi8[i] = 0; }
         uint32_t v[CH];
-        if (p.CT == CH && p.fuse && !p.tr) {
-          // ---- whole channel row fits one TMEM load (Cout = 16 or 32): single pass, one exp per value ----
-          ld_acc<CH>(ta, p.stackF ? p.CT : 0, v);
-          float f[CH];
+        if constexpr (SP > 0) {
+          // ---- single pass: y = acc * 1/|w| + b, winner, r = softmax(k y), bf16 split, running column sums ----
+          float f[NV];
 #pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            f[i] = fmaf(__uint_as_float(v[i]), s_inv[i], s_bias[i]);
+          for (int ck = 0; ck < SP; ++ck) {
+            ld_acc<CH>(ta + ck * CH, p.stackF ? p.CT : 0, v);
+#pragma unroll
+            for (int i4 = 0; i4 < CH; i4 += 4) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_inv + ck * CH + i4);
+              const float4 bs = *reinterpret_cast<const float4*>(s_bias + ck * CH + i4);
+              f[ck * CH + i4 + 0] = fmaf(__uint_as_float(v[i4 + 0]), sc.x, bs.x);
+              f[ck * CH + i4 + 1] = fmaf(__uint_as_float(v[i4 + 1]), sc.y, bs.y);
+              f[ck * CH + i4 + 2] = fmaf(__uint_as_float(v[i4 + 2]), sc.z, bs.z);
+              f[ck * CH + i4 + 3] = fmaf(__uint_as_float(v[i4 + 3]), sc.w, bs.w);
+            }
+          }
+          const float k2 = p.kinv * 1.4426950408889634f;      // exp(k y) = 2^(k2 y)
+          float mx2 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
             if (valid) yb[(long long)i * outS] = f[i];
-            mx = fmaxf(mx, f[i] * p.kinv);
-            if (f[i] > best) { best = f[i]; bi = i; }
+            if (f[i] > best) { best = f[i]; bi = i; }          // strict: the lowest index wins ties
+            f[i] *= k2;
+            mx2 = fmaxf(mx2, f[i]);
           }
           if (p.winner && valid) p.winner[(long long)b * outS + s] = bi;
           if (p.write_r) {
             float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < CH; ++i) { f[i] = __expf(fmaf(f[i], p.kinv, -mx)); sum += f[i]; }
+            for (int i = 0; i < NV; ++i) {
+              float e;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(f[i] - mx2));
+              f[i] = e; sum += e;
+            }
             const float rinv = valid ? (1.f / sum) : 0.f;
 #pragma unroll
-            for (int g8 = 0; g8 < CH / 8; ++g8) {
+            for (int g8 = 0; g8 < NV / 8; ++g8) {
               uint32_t oh4[4], ol4[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                __nv_bfloat16 h2[2], l2[2];
-#pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) {
-                  const int c = g8 * 8 + i * 2 + k2;
-                  split_bf16(f[c] * rinv, h2[k2], l2[k2]);
-                  f[c] = __bfloat162float(h2[k2]) + (p.RHL == 2 ? __bfloat162float(l2[k2]) : 0.f);
+                const int c = g8 * 8 + i * 2;
+                const float r0 = f[c] * rinv, r1 = f[c + 1] * rinv;
+                uint32_t hp, lp;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(r1), "f"(r0));
+                const float h0 = __uint_as_float(hp << 16), h1 = __uint_as_float(hp & 0xffff0000u);
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(r1 - h1), "f"(r0 - h0));
+                oh4[i] = hp; ol4[i] = lp;
+                if (p.RHL == 2) {
+                  racc[c] += h0 + __uint_as_float(lp << 16);
+                  racc[c + 1] += h1 + __uint_as_float(lp & 0xffff0000u);
+                } else {
+                  racc[c] += h0; racc[c + 1] += h1;
                 }
-                oh4[i] = pack_bf16x2(h2[0], h2[1]);
-                ol4[i] = pack_bf16x2(l2[0], l2[1]);
               }
-              const long long ridx = (long long)g8 * p.PR + pp;
               if (p.dbg & 8) continue;
+              const long long ridx = (long long)g8 * p.PR + pp;
               p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
               if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
             }
-            const float cs = lane_col_sum<CH>(f, lane);
-            if (lane < CH) my_rs[lane] += cs;
           }
           continue;
         }
@@ -627,6 +674,17 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       aph ^= 1;                             // this set's buffer is reused every NACC-th item
     }
     __syncwarp();
+    if constexpr (SP > 0) {                 // fold the per-thread column sums: one butterfly per CH columns
+#pragma unroll
+      for (int ck = 0; ck < SP; ++ck) {
+        float t[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) t[i] = racc[ck * CH + i];
+        const float cs = lane_col_sum<CH>(t, lane);
+        if (lane < CH) my_rs[ck * CH + lane] += cs;
+      }
+      __syncwarp();
+    }
     if (p.fuse && p.write_r)
       for (int c = lane; c < p.CT; c += 32) atomicAdd(p.rsum + c, my_rs[c]);
   }
@@ -1431,7 +1489,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     gg.B = g0.B; gg.Cin = g0.Cin; gg.iD = g0.iD; gg.iH = g0.iH; gg.iW = g0.iW; gg.pD = g0.pD; gg.pH = g0.pH; gg.pW = g0.pW;
     gg.kH = g0.kH; gg.kW = g0.kW; gg.taps = g0.taps; gg.oD = g0.oD; gg.oH = g0.oH; gg.oW = g0.oW; gg.Kp = g.Cin;
     gg.CC = P.CC; gg.PA = P.PA; gg.PTOT = P.PTOT;
-    pack_x_gather_kernel<<<ew_grid((long long)P.CC * P.PA), 256, 0, st>>>(x, xp0, xp1, gg);
+    pack_x_gather_kernel<<<ew_grid(P.PA), 256, 0, st>>>(x, xp0, xp1, gg);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   } else if (do_pack) {
     pack_x_kernel<<<ew_grid((long long)P.CC * P.PA), 256, 0, st>>>(x, xp0, xp1, pg);
@@ -1467,13 +1525,22 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   f.tmem_cols = P.f_tmem;
   const long long fwork = (long long)P.f_ntiles * P.n_ct;
   const int fgrid = fwork < num_sms() ? (int)fwork : num_sms();
-  if (!do_fwd) {
-  } else if (g.Cout % 32 == 0) {
-    HEBB_CUDA_TRY(cudaFuncSetAttribute(fwd_swta_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    fwd_swta_kernel<32><<<fgrid, 320, kSmemLimit, st>>>(f);
-  } else {
-    HEBB_CUDA_TRY(cudaFuncSetAttribute(fwd_swta_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    fwd_swta_kernel<16><<<fgrid, 320, kSmemLimit, st>>>(f);
+  if (do_fwd) {
+    const int ch = (g.Cout % 32 == 0) ? 32 : 16;
+    // single-pass epilogue: whole channel row in registers (fused soft-WTA, plain conv, <= 64 channels)
+    const int sp = (f.fuse && !tr && P.CT <= 64 && P.CT % ch == 0 && !P.stackF) ? P.CT / ch : 0;
+#define HEBB_FWD_LAUNCH(CHV, SPV)                                                                                   \
+    do {                                                                                                            \
+      HEBB_CUDA_TRY(cudaFuncSetAttribute(fwd_swta_kernel<CHV, SPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                         kSmemLimit));                                                               \
+      fwd_swta_kernel<CHV, SPV><<<fgrid, 320, kSmemLimit, st>>>(f);                                                  \
+    } while (0)
+    if (ch == 32) {
+      if (sp == 1) HEBB_FWD_LAUNCH(32, 1); else if (sp == 2) HEBB_FWD_LAUNCH(32, 2); else HEBB_FWD_LAUNCH(32, 0);
+    } else {
+      if (sp == 1) HEBB_FWD_LAUNCH(16, 1); else if (sp == 3) HEBB_FWD_LAUNCH(16, 3); else HEBB_FWD_LAUNCH(16, 0);
+    }
+#undef HEBB_FWD_LAUNCH
   }
   if (do_fwd) { HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED(); }
   if (do_fwd && P.n_ct > 1 && (upd || winner)) {
