@@ -152,7 +152,7 @@ pack_x_gather_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4
 // layout ([tap][k-chunk][hi|lo][CT rows]), so the producer moves a whole tap group with a single bulk copy.
 __global__ void __launch_bounds__(256)
 pack_w_kernel(const float* __restrict__ W, uint4* __restrict__ wp, int Cin, int Cout, int taps, int NSLAB, int HL,
-              int CT, int tr_taps, const float* __restrict__ inv_ci) {
+              int CT, int tr_taps, int tr_q, const float* __restrict__ inv_ci) {
   const long long total = (long long)NSLAB * taps * HL * 2 * Cout;
   const int n_ct = Cout / CT;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -175,7 +175,9 @@ pack_w_kernel(const float* __restrict__ W, uint4* __restrict__ wp, int Cin, int 
         float v = 0.f;
         if (ci < Cin) {
           if (tr_taps) {   // transposed conv as a 1x1 conv onto (co, offset) channels; W is [Cout][Cin][taps]
-            const int cr = co / tr_taps, off = co - cr * tr_taps;
+            int cr, off;
+            if (tr_q) { const int bk = co / tr_q, rem = co - bk * tr_q; cr = rem >> 1; off = 2 * bk + (rem & 1); }
+            else { cr = co / tr_taps; off = co - cr * tr_taps; }
             v = __ldg(W + ((long long)cr * Cin + ci) * tr_taps + off) * (inv_ci ? inv_ci[ci] : 1.f);
           } else {
             v = __ldg(W + ((long long)co * Cin + ci) * taps + tap);
@@ -203,6 +205,8 @@ struct FwdParams {
   int stackF;                  // bf16x3 forward: B = [w_hi | w_lo] stacked along N -> 2 MMAs instead of 3
   int CT, n_ct, fuse;          // output-channel tile handled by one CTA (<= 512 TMEM columns); fuse: softmax in the epilogue
   int tr, tD, tH, tW, CoutR;   // transposed conv (k == stride == 2): y scatter to the (tD,tH,tW) grid, CoutR real channels
+                               // tr == 1: columns co*8 + off; tr == 2: columns (off>>1)*trQ + 2*co + (off&1), trQ = 2*CoutR
+  int trQ;
   int RHL;                     // 1: r is consumed as single bf16 (hi only), 2: hi + lo
   long long PA, PR, PTOT;      // positions per chunk plane in Xp / Rp; real positions B*Qimg
   int MB, TILE_M, ntiles, SEGLEN;
@@ -337,7 +341,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
       const uint32_t w_tap_bytes = (uint32_t)p.HL * 2 * p.CT * 16;   // one tap: [k-chunk][hi|lo][CT rows]
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        const int tile = work / p.n_ct, ct = work - tile * p.n_ct;
+        const int ct = work / p.ntiles, tile = work - ct * p.ntiles;   // channel tile slowest: it changes at most n_ct times per CTA
         const long long p0 = (long long)tile * p.TILE_M;
         const int slab0 = (p.dbg & 64) ? (int)(blockIdx.x % (unsigned)p.NSLAB) : 0;
         for (int s_i = 0; s_i < p.NSLAB; ++s_i) {
@@ -450,13 +454,18 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
       const int acc = (p.NACC == 2) ? (it & 1) : 0;
       if (acc != eset) continue;            // the other set's buffer (NACC == 1: set 1 has nothing to do)
-      const int tile = work / p.n_ct, ct = work - tile * p.n_ct;
+      const int ct = work / p.ntiles, tile = work - ct * p.ntiles;   // channel tile slowest: it changes at most n_ct times per CTA
       const int cbase = ct * p.CT;
       if (ct != cur_ct) {      // (re)load this channel tile's 1/|W| and bias
+        if (cur_ct >= 0 && p.fuse && p.write_r) {      // flush the finished tile's column sums
+          __syncwarp();
+          for (int c = lane; c < p.CT; c += 32) { atomicAdd(p.rsum + cur_ct * p.CT + c, my_rs[c]); my_rs[c] = 0.f; }
+          __syncwarp();
+        }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eset));
         for (int i = (int)threadIdx.x - 64 - eset * 128; i < p.CT; i += 128) {
           s_inv[i] = p.inv ? p.inv[cbase + i] : 1.f;
-          s_bias[i] = p.bias ? p.bias[p.tr ? ((cbase + i) >> 3) : (cbase + i)] : 0.f;
+          s_bias[i] = p.bias ? p.bias[p.tr == 2 ? (((cbase + i) % p.trQ) >> 1) : (p.tr ? ((cbase + i) >> 3) : (cbase + i))] : 0.f;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eset));
         cur_ct = ct;
@@ -543,6 +552,77 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               const long long ridx = (long long)g8 * p.PR + pp;
               p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
               if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+            }
+          }
+          continue;
+        }
+        if (p.tr == 2) {
+          // ---- transposed layer, columns ordered (od2, oh2) block > channel > ow2: every block of trQ = 2*CoutR
+          // columns holds two complete soft-WTA groups (one per x-parity), so any whole number of blocks is a
+          // self-contained channel tile and wide layers still get the fused epilogue ----
+          const int nblk = p.CT / p.trQ;
+          for (int bk = 0; bk < nblk; ++bk) {
+            const int off_hi = cbase / p.trQ + bk;            // (od2, oh2)
+            const long long sub = ((long long)(off_hi >> 1) * p.tH + (off_hi & 1)) * p.tW;
+            float* yo = ytb + sub;
+            const int cb = bk * p.trQ;
+            float mxa = -INFINITY, mxb = -INFINITY, besta = -INFINITY, bestb = -INFINITY;
+            int bia = 0, bib = 0;
+            for (int c0 = cb; c0 < cb + p.trQ; c0 += CH) {
+              ld_acc<CH>(ta + c0, 0, v);
+#pragma unroll
+              for (int i = 0; i < CH; i += 2) {
+                const int co = (c0 - cb + i) >> 1;
+                float2 o;
+                o.x = __uint_as_float(v[i]) + s_bias[c0 + i];
+                o.y = __uint_as_float(v[i + 1]) + s_bias[c0 + i + 1];
+                if (valid) *reinterpret_cast<float2*>(yo + (long long)co * tS) = o;
+                mxa = fmaxf(mxa, o.x * p.kinv); mxb = fmaxf(mxb, o.y * p.kinv);
+                if (o.x > besta) { besta = o.x; bia = co; }
+                if (o.y > bestb) { bestb = o.y; bib = co; }
+              }
+            }
+            if (p.winner && valid) {
+              int32_t* wb = p.winner + (long long)b * tS + ((long long)(2 * od) * p.tH + 2 * oh) * p.tW + 2 * ow + sub;
+              *reinterpret_cast<int2*>(wb) = make_int2(bia, bib);
+            }
+            if (!p.write_r) continue;
+            float suma = 0.f, sumb = 0.f;
+            for (int c0 = cb; c0 < cb + p.trQ; c0 += CH) {
+              ld_acc<CH>(ta + c0, 0, v);
+#pragma unroll
+              for (int i = 0; i < CH; i += 2) {
+                suma += __expf(fmaf(__uint_as_float(v[i]) + s_bias[c0 + i], p.kinv, -mxa));
+                sumb += __expf(fmaf(__uint_as_float(v[i + 1]) + s_bias[c0 + i + 1], p.kinv, -mxb));
+              }
+            }
+            const float ria = valid ? (1.f / suma) : 0.f, rib = valid ? (1.f / sumb) : 0.f;
+            for (int c0 = cb; c0 < cb + p.trQ; c0 += CH) {
+              ld_acc<CH>(ta + c0, 0, v);
+              float rr[CH];
+#pragma unroll
+              for (int g8 = 0; g8 < CH / 8; ++g8) {
+                uint32_t oh4[4], ol4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int c = g8 * 8 + i * 2;
+                  const float r0 = __expf(fmaf(__uint_as_float(v[c]) + s_bias[c0 + c], p.kinv, -mxa)) * ria;
+                  const float r1 = __expf(fmaf(__uint_as_float(v[c + 1]) + s_bias[c0 + c + 1], p.kinv, -mxb)) * rib;
+                  __nv_bfloat16 h0, l0, h1, l1;
+                  split_bf16(r0, h0, l0);
+                  split_bf16(r1, h1, l1);
+                  rr[c] = __bfloat162float(h0) + (p.RHL == 2 ? __bfloat162float(l0) : 0.f);
+                  rr[c + 1] = __bfloat162float(h1) + (p.RHL == 2 ? __bfloat162float(l1) : 0.f);
+                  oh4[i] = pack_bf16x2(h0, h1);
+                  ol4[i] = pack_bf16x2(l0, l1);
+                }
+                if (p.dbg & 8) continue;
+                const long long ridx = (long long)((cbase + c0) / 8 + g8) * p.PR + pp;
+                p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+                if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+              }
+              const float cs = lane_col_sum<CH>(rr, lane);
+              if (lane < CH) my_rs[c0 + lane] += cs;
             }
           }
           continue;
@@ -685,8 +765,8 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
       }
       __syncwarp();
     }
-    if (p.fuse && p.write_r)
-      for (int c = lane; c < p.CT; c += 32) atomicAdd(p.rsum + c, my_rs[c]);
+    if (p.fuse && p.write_r && cur_ct >= 0)
+      for (int c = lane; c < p.CT; c += 32) atomicAdd(p.rsum + cur_ct * p.CT + c, my_rs[c]);
   }
   tc_fence_before();
   __syncthreads();
@@ -885,7 +965,7 @@ rsum_from_packed_kernel(const uint4* __restrict__ rhi, const uint4* __restrict__
 // delta_w[co][ci][off] += sum_s Hpart[s][0][ci][co*8+off] - sum_off' rsum[co*8+off'] * W[co][ci][off']
 __global__ void __launch_bounds__(256)
 tc_finalize_T_kernel(const float* __restrict__ hpart, const float* __restrict__ rsum, const float* __restrict__ W,
-                     float* __restrict__ dw, int PS, int Cin, int CinP, int CoutR) {
+                     float* __restrict__ dw, int PS, int Cin, int CinP, int CoutR, int tr_q) {
   const long long n = (long long)Cin * CoutR;
   const long long Cp = (long long)CoutR * 8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
@@ -894,16 +974,19 @@ tc_finalize_T_kernel(const float* __restrict__ hpart, const float* __restrict__ 
     const int ci = (int)(idx / CoutR);
     const float* w = W + ((long long)co * Cin + ci) * 8;
     float* d = dw + ((long long)co * Cin + ci) * 8;
+    int col[8];      // packed column of (co, off): co*8 + off, or (off>>1)*tr_q + 2*co + (off&1)
+#pragma unroll
+    for (int off = 0; off < 8; ++off) col[off] = tr_q ? ((off >> 1) * tr_q + 2 * co + (off & 1)) : (co * 8 + off);
     float dec = 0.f;
 #pragma unroll
-    for (int off = 0; off < 8; ++off) dec += rsum[co * 8 + off] * w[off];
+    for (int off = 0; off < 8; ++off) dec += rsum[col[off]] * w[off];
     float h[8];
 #pragma unroll
     for (int off = 0; off < 8; ++off) h[off] = 0.f;
     for (int s = 0; s < PS; ++s) {
-      const float* hp = hpart + ((long long)s * CinP + ci) * Cp + (long long)co * 8;
+      const float* hp = hpart + ((long long)s * CinP + ci) * Cp;
 #pragma unroll
-      for (int off = 0; off < 8; ++off) h[off] += hp[off];
+      for (int off = 0; off < 8; ++off) h[off] += hp[col[off]];
     }
 #pragma unroll
     for (int off = 0; off < 8; ++off) d[off] += h[off] - dec;
@@ -1235,12 +1318,24 @@ static bool equivalent_1x1(const Geo& g, Geo* e) {
   return true;
 }
 
-static bool plan_layer(const Geo& g, int prec, Plan* P) {
+// Transposed layers whose 2*Cout columns (one (od2, oh2) block: all channels x both x-parities) fit a channel
+// tile use the block-major column order, which keeps the soft-WTA fused however many tiles the layer needs.
+static int tr_quantum(const Geo& g0) {
+  if (!g0.transposed) return 0;
+  const int q = 2 * g0.Cout;
+  return (q <= 512 && q % 32 == 0) ? q : 0;
+}
+
+static bool plan_layer(const Geo& g, int prec, Plan* P, int trq = 0) {
   Plan& q = *P;
   q.ok = false;
   if (g.transposed || g.sD != 1 || g.sH != 1 || g.sW != 1) return false;
   if (g.Cout % 16 || g.taps > kMaxTaps) return false;
   q.CT = g.Cout <= 512 ? g.Cout : 512;           // channel tile of the forward kernel (TMEM: 512 columns)
+  if (trq) {     // whole blocks, and at most 256 columns when possible so that two accumulator buffers fit TMEM
+    q.CT = trq <= 256 ? trq * (256 / trq) : trq;
+    if (q.CT > g.Cout) q.CT = g.Cout;
+  }
   if (g.Cout % q.CT) return false;
   q.n_ct = g.Cout / q.CT;
   if (g.kD > 3 || g.kH > 9 || g.kW > 9) return false;
@@ -1419,20 +1514,20 @@ static bool plan_layer(const Geo& g, int prec, Plan* P) {
 bool tc_supported(const Geo& g, int prec) {
   Plan P;
   Geo e;
-  return equivalent_1x1(g, &e) && plan_layer(e, prec, &P);
+  return equivalent_1x1(g, &e) && plan_layer(e, prec, &P, tr_quantum(g));
 }
 
 size_t tc_workspace_bytes(const Geo& g, int prec) {
   Plan P;
   Geo e;
-  if (!equivalent_1x1(g, &e) || !plan_layer(e, prec, &P)) return 0;
+  if (!equivalent_1x1(g, &e) || !plan_layer(e, prec, &P, tr_quantum(g))) return 0;
   return P.total;
 }
 
 int tc_describe_plan(const Geo& g0, int prec, int* o, int n) {
   Plan P;
   Geo g;
-  if (!equivalent_1x1(g0, &g) || !plan_layer(g, prec, &P)) return 0;
+  if (!equivalent_1x1(g0, &g) || !plan_layer(g, prec, &P, tr_quantum(g0))) return 0;
   const int v[] = {P.MB, P.f_SEGLEN, P.XST, P.WST, P.NACC, (int)P.f_tmem, P.f_ntiles, (int)P.f_smem,
                    P.d_by_kh, P.CM, P.CN, P.BLK, P.ST, P.d_SEGLEN, P.ngrp, P.n_cin_tiles, P.n_cout_tiles, P.PS,
                    P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct, P.nrep, P.WG};
@@ -1452,7 +1547,8 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
                  cudaStream_t st) {
   Plan P;
   Geo g;
-  if (!equivalent_1x1(g0, &g) || !plan_layer(g, prec, &P)) return HEBB_ESHAPE;
+  const int trq = tr_quantum(g0);
+  if (!equivalent_1x1(g0, &g) || !plan_layer(g, prec, &P, trq)) return HEBB_ESHAPE;
   const bool tr = g0.transposed != 0;
   if (!ws || ws_bytes < P.total) return HEBB_EWS;
   char* base = static_cast<char*>(ws);
@@ -1497,7 +1593,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   }
   if (do_pack) {
     const long long n = (long long)P.NSLAB * g.taps * P.f_HL * 2 * g.Cout;
-    pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL, P.CT, tr ? g0.taps : 0,
+    pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL, P.CT, tr ? g0.taps : 0, trq,
                                               (tr && (flags & HEBB_F_WNRM)) ? inv : nullptr);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
@@ -1506,11 +1602,11 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   FwdParams f;
   f.xp[0] = xp0; f.xp[1] = xp1; f.wp = wp; f.rp[0] = rp0; f.rp[1] = rp1;
   f.y = y; f.winner = winner; f.inv = ((flags & HEBB_F_WNRM) && !tr) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = err;
-  f.tr = tr ? 1 : 0; f.tD = g0.oD; f.tH = g0.oH; f.tW = g0.oW; f.CoutR = g0.Cout;
+  f.tr = tr ? (trq ? 2 : 1) : 0; f.trQ = trq; f.tD = g0.oD; f.tH = g0.oH; f.tW = g0.oW; f.CoutR = g0.Cout;
   f.Cout = g.Cout; f.CC = P.CC; f.NSLAB = P.NSLAB; f.taps = g.taps; f.nseg = P.f_nseg; f.HL = P.f_HL; f.RHL = P.d_HL;
   static const int fwd_dbg = [] { const char* e = getenv("HEBB_FWD_DBG"); return e ? atoi(e) : 0; }();
   f.dbg = fwd_dbg;
-  f.stackF = P.stackF; f.CT = P.CT; f.n_ct = P.n_ct; f.fuse = (P.n_ct == 1) ? 1 : 0;   // transposed: grouped softmax when Cout*8 <= 512
+  f.stackF = P.stackF; f.CT = P.CT; f.n_ct = P.n_ct; f.fuse = (P.n_ct == 1 || trq) ? 1 : 0;   // transposed: grouped softmax when Cout*8 <= 512
   f.PA = P.PA; f.PR = P.PR; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
   f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC; f.WG = P.WG;
   f.WP = P.WP; f.plane = P.plane; f.Qimg = P.Qimg; f.oD = g.oD; f.oH = g.oH; f.oW = g.oW;
@@ -1543,7 +1639,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
 #undef HEBB_FWD_LAUNCH
   }
   if (do_fwd) { HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED(); }
-  if (do_fwd && P.n_ct > 1 && (upd || winner)) {
+  if (do_fwd && P.n_ct > 1 && !trq && (upd || winner)) {
     SmxParams sp;
     sp.y = y; sp.rp[0] = rp0; sp.rp[1] = rp1; sp.winner = winner; sp.rsum = rsum;
     sp.Cout = g.Cout; sp.RHL = P.d_HL; sp.WP = P.WP; sp.plane = P.plane; sp.Qimg = P.Qimg;
@@ -1599,7 +1695,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   {
     const long long n = (long long)g.taps * g.Cin * g.Cout;
     if (tr)
-      tc_finalize_T_kernel<<<ew_grid((long long)g0.Cin * g0.Cout), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g0.Cin, P.CinP, g0.Cout);
+      tc_finalize_T_kernel<<<ew_grid((long long)g0.Cin * g0.Cout), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g0.Cin, P.CinP, g0.Cout, trq);
     else
     if (n >= (1LL << 18) && P.PS * P.Q <= 32) {
       dim3 fg((unsigned)cdiv((long long)g.Cin * g.taps, 32), (unsigned)cdiv(g.Cout, 32));

@@ -209,7 +209,8 @@ def test_tensor_core_shapes_vs_oracle(case, prec):
 
 
 @pytest.mark.parametrize('prec', PRECS)
-@pytest.mark.parametrize('shape', [(2, 128, 64, (6, 6, 5)), (1, 1024, 512, (3, 3, 2)), (2, 32, 16, (8, 10, 12))])
+@pytest.mark.parametrize('shape', [(2, 128, 64, (6, 6, 5)), (1, 1024, 512, (3, 3, 2)), (2, 32, 16, (8, 10, 12)),
+                                   (2, 256, 128, (4, 6, 5)), (1, 512, 256, (3, 4, 4)), (1, 64, 8, (4, 4, 6))])
 def test_transposed_3d_tensor_core_vs_oracle(shape, prec):
     """HebbianConvTranspose3d(k=2, s=2) = 1x1 conv onto (co, offset) channels + pixel shuffle."""
     B, Cin, Cout, sp = shape
