@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c4', 'c5'])
+    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c4', 'c5', 'c6'])
+    ap.add_argument('--aten-backward', action='store_true', help='c6: differentiate with stock ATen ops instead of the native dgrad/wgrad kernels')
     ap.add_argument('--prec', default=os.environ.get('HEBB_PREC', 'bf16x3'), choices=['fp32', 'bf16x3', 'bf16'])
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (0 = the workload default)')
     ap.add_argument('--cpu-sample-batch', type=int, default=0)
@@ -61,6 +62,7 @@ WORKLOADS = {
     # BASELINE configs[4]: forward throughput of the fine-tune-stage network (hebb alpha = 0, nothing updates).  The XNet
     # dual-branch model is not in the reference tree: the same 2-D UNet on a 3-channel image stands in.
     'c5': ('2D UNet forward only, hebb alpha=0 (fine-tune stage), synthetic 256x256 RGB', 64, 4),
+    'c6': ('2D UNet fine-tuning step, hebb alpha=0: forward + back-prop through every layer, synthetic 256x256 RGB', 64, 4),
 }
 
 
@@ -92,7 +94,7 @@ def build_model(workload, impl_ours, device, fuse=False):
             g = torch.Generator().manual_seed(seed)
             return torch.randn(b, 3, 128, 128, generator=g).to(dev), None
         return layer.to(device).train(), batch, None
-    if workload in ('c2', 'c5'):
+    if workload in ('c2', 'c5', 'c6'):
         net, excl = workloads.unet2d(3, 2), workloads.EXCLUDE_2D
 
         def batch(b, seed, dev):
@@ -102,7 +104,7 @@ def build_model(workload, impl_ours, device, fuse=False):
 
         def batch(b, seed, dev):
             return workloads.la_batch(b, (96, 96, 80), seed=seed, device=dev)
-    alpha = 0. if workload == 'c5' else HEBB_PARAMS['alpha']
+    alpha = 0. if workload in ('c5', 'c6') else HEBB_PARAMS['alpha']
     with contextlib.redirect_stdout(io.StringIO()):
         if impl_ours:
             from hebb.makehebbian import makehebbian
@@ -280,6 +282,8 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     hebb.set_precision(args.prec)
+    if args.aten_backward:
+        os.environ['HEBB_ATEN_BACKWARD'] = '1'
     desc, dflt_b, cpu_b = WORKLOADS[args.workload]
     B = args.batch or dflt_b
     cpu_b = args.cpu_sample_batch or cpu_b
@@ -437,6 +441,7 @@ def run_ours(args):
                        'hebb_params': HEBB_PARAMS if args.workload != 'c1' else {'mode': 'swta', 'k': 3.0, 'alpha': 1.0},
                        'optimizer': f'adam lr={lr}', 'precision_mode': args.prec,
                        'fused_norm_act_upsample': (not args.no_fuse) and args.workload != 'c1',
+                       'backward': 'stock ATen' if args.aten_backward else 'native dgrad/wgrad on the tcgen05 kernels where the planner takes the layer',
                        'backprop_head_memory_format': 'nchw' if (args.head_nchw or args.workload != 'c2') else 'channels_last', 'l2': 'flushed between timed steps (256 MB fill)',
                        'parallelism': f'dp{world} (batch shards, one all-reduce of delta_w per step)'},
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,

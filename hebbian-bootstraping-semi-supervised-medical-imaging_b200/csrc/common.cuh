@@ -28,6 +28,9 @@ extern unsigned long long g_launches;
     if (_s != HEBB_OK) return _s;    \
   } while (0)
 
+// internal flag of tc_conv_step (never accepted through the C ABI): weight-gradient mode, see hebb_conv_wgrad
+#define HEBB_F_WGRAD_INTERNAL 0x10000u
+
 // Geometry of one layer, resolved from HebbDesc (device-friendly POD).
 struct Geo {
   int nd, B, Cin, Cout;

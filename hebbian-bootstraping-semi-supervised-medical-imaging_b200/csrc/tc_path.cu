@@ -147,6 +147,46 @@ pack_x_gather_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4
   }
 }
 
+// Packs an OUTPUT-shaped fp32 tensor (the back-propagated dL/dy of hebb_conv_wgrad) into the response layout
+// Rp[hl][c8][p][8] over the padded position index space: 0 at positions that are not output pixels and in
+// channels >= C (the packed channel count is a multiple of 16).
+struct PackRGeo {
+  int B, C, C8, oD, oH, oW, WP, plane, Qimg;
+  long long outS, PR, PTOT;
+};
+
+__global__ void __launch_bounds__(256)
+pack_r_kernel(const float* __restrict__ gy, uint4* __restrict__ rhi, uint4* __restrict__ rlo, const __grid_constant__ PackRGeo g) {
+  const long long total = (long long)g.C8 * g.PR;
+  const int oHW = g.oH * g.oW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx / g.PR);
+    const long long p = idx - (long long)c8 * g.PR;
+    uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+    if (p < g.PTOT) {
+      const int b = (int)(p / g.Qimg);
+      int q = (int)(p - (long long)b * g.Qimg);
+      const int od = q / g.plane; q -= od * g.plane;
+      const int oh = q / g.WP;
+      const int ow = q - oh * g.WP;
+      if (od < g.oD && oh < g.oH && ow < g.oW) {
+        const float* src = gy + ((long long)b * g.C + c8 * 8) * g.outS + (long long)od * oHW + (long long)oh * g.oW + ow;
+        __nv_bfloat16 vh[8], vl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = (c8 * 8 + i < g.C) ? __ldg(src + (long long)i * g.outS) : 0.f;
+          split_bf16(v, vh[i], vl[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h[i] = pack_bf16x2(vh[2 * i], vh[2 * i + 1]); l[i] = pack_bf16x2(vl[2 * i], vl[2 * i + 1]); }
+      }
+    }
+    rhi[idx] = make_uint4(h[0], h[1], h[2], h[3]);
+    if (rlo) rlo[idx] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // Wp[slab][ct][tap][c2][hl][CT] (uint4 = 8 input channels) : the forward B operand, K-major.  For one
 // (slab, channel tile) any run of consecutive taps is ONE contiguous block already in the shared-memory stage
 // layout ([tap][k-chunk][hi|lo][CT rows]), so the producer moves a whole tap group with a single bulk copy.
@@ -1225,7 +1265,7 @@ tc_finalize_kernel(const float* __restrict__ hpart, const float* __restrict__ rs
 #pragma unroll
       for (int k = 0; k < 8; ++k) tot += red[k][tx];
       const long long wi = ((long long)co * Cin + ci) * taps + t;
-      dw[wi] += tot - rsum[co] * W[wi];
+      dw[wi] += rsum ? (tot - rsum[co] * W[wi]) : tot;
     }
     __syncthreads();
   }
@@ -1259,7 +1299,7 @@ tc_finalize_tiled_kernel(const float* __restrict__ hpart, const float* __restric
     const int co = co0 + ty + 8 * r, j = j0 + tx;
     if (j < K && co < Cout) {
       const long long wi = (long long)co * K + j;
-      dw[wi] += tile[tx][ty + 8 * r] - rsum[co] * W[wi];
+      dw[wi] += rsum ? (tile[tx][ty + 8 * r] - rsum[co] * W[wi]) : tile[tx][ty + 8 * r];
     }
   }
 }
@@ -1561,15 +1601,19 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   uint4* rp1 = reinterpret_cast<uint4*>(base + P.o_rp[1]);
   uint4* wp = reinterpret_cast<uint4*>(base + P.o_wp);
   float* hpart = reinterpret_cast<float*>(base + P.o_hpart);
-  const bool upd = (flags & HEBB_F_UPDATE) != 0;
+  // weight-gradient mode (hebb_conv_wgrad): `y` holds dL/dy; only x is packed, dL/dy takes the place of the
+  // responses, and the finalize pass adds the plain contraction (no decay term) to delta_w
+  const bool wgrad = (flags & HEBB_F_WGRAD_INTERNAL) != 0;
+  if (wgrad && tr) return HEBB_ESHAPE;
+  const bool upd = (flags & HEBB_F_UPDATE) != 0 || wgrad;
 
   // profiling aid: HEBB_F_ONLY_* re-run one stage on the scratch left by a preceding full call
   const unsigned only = flags & (HEBB_F_ONLY_PACK | HEBB_F_ONLY_FWD | HEBB_F_ONLY_DW);
   const bool do_pack = !only || (only & HEBB_F_ONLY_PACK);
-  const bool do_fwd = !only || (only & HEBB_F_ONLY_FWD);
+  const bool do_fwd = !wgrad && (!only || (only & HEBB_F_ONLY_FWD));
   const bool do_dw = upd && (!only || (only & HEBB_F_ONLY_DW));
   if (do_fwd) HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, (P.o_xp[0] - P.o_rsum), st));   // rsum + err word
-  if ((flags & HEBB_F_WNRM) && do_pack) {
+  if ((flags & HEBB_F_WNRM) && do_pack && !wgrad) {
     if (tr)   // per INPUT channel over (Cout, taps) of the [Cout][Cin][taps] buffer (hebb3d.py:78 on the view)
       HEBB_TRY(launch_wnorm(W, nullptr, inv, g0.Cin, g0.taps, g0.Cout, (long long)g0.Cin * g0.taps, g0.taps, st));
     else
@@ -1591,7 +1635,14 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     pack_x_kernel<<<ew_grid((long long)P.CC * P.PA), 256, 0, st>>>(x, xp0, xp1, pg);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
-  if (do_pack) {
+  if (wgrad) {
+    PackRGeo rg;
+    rg.B = g.B; rg.C = g.Cout; rg.C8 = P.C8; rg.oD = g.oD; rg.oH = g.oH; rg.oW = g.oW; rg.WP = P.WP; rg.plane = P.plane;
+    rg.Qimg = P.Qimg; rg.outS = g.outS; rg.PR = P.PR; rg.PTOT = P.PTOT;
+    pack_r_kernel<<<ew_grid((long long)P.C8 * P.PR), 256, 0, st>>>(y, rp0, P.d_HL == 2 ? rp1 : nullptr, rg);
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  }
+  if (do_pack && !wgrad) {
     const long long n = (long long)P.NSLAB * g.taps * P.f_HL * 2 * g.Cout;
     pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL, P.CT, tr ? g0.taps : 0, trq,
                                               (tr && (flags & HEBB_F_WNRM)) ? inv : nullptr);
@@ -1699,12 +1750,12 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     else
     if (n >= (1LL << 18) && P.PS * P.Q <= 32) {
       dim3 fg((unsigned)cdiv((long long)g.Cin * g.taps, 32), (unsigned)cdiv(g.Cout, 32));
-      tc_finalize_tiled_kernel<<<fg, 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
+      tc_finalize_tiled_kernel<<<fg, 256, 0, st>>>(hpart, wgrad ? nullptr : rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
     } else {
       long long gx = cdiv(n, 32);
       const long long cap = (long long)num_sms() * 32;
       if (gx > cap) gx = cap;
-      tc_finalize_kernel<<<(unsigned)gx, 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
+      tc_finalize_kernel<<<(unsigned)gx, 256, 0, st>>>(hpart, wgrad ? nullptr : rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
     }
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }

@@ -52,9 +52,12 @@ def _ntuple(v, n):
 
 
 class _HebbFn(torch.autograd.Function):
-    """Forward = the sm_100 kernels.  Backward (only reached when back-prop gradients are wanted,
-    i.e. alpha < 1 or a trainable layer upstream) differentiates the same formula with stock ATen
-    convolution-backward — SURVEY.md §8(f) row 3 lists native dgrad/wgrad as a later step."""
+    """Forward = the sm_100 kernels.  Backward (only reached when back-prop gradients are wanted, i.e.
+    alpha < 1 or a trainable layer upstream; reference hebb/hebb.py:185-191 via loss.backward()):
+    stride-1 convolutions the tcgen05 planner takes run natively as well -- dL/dW on the plasticity
+    contraction kernel with dL/dy in place of the responses (hebb_conv_wgrad), dL/dx as a forward
+    convolution of dL/dy with the flipped, transposed filters -- everything else (transposed layers, strided
+    or odd shapes, fp32 mode) differentiates the same formula with stock ATen ops.  SURVEY.md section 8(f) row 3."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, layer, update):
@@ -67,6 +70,9 @@ class _HebbFn(torch.autograd.Function):
         x, weight, bias = ctx.saved_tensors
         layer = ctx.layer
         need = ctx.needs_input_grad
+        native = layer._native_backward(x, weight, bias, gy, need)
+        if native is not None:
+            return native[0], native[1], native[2], None, None
         with torch.enable_grad():
             xx = x.detach().requires_grad_(need[0])
             ww = weight.detach().requires_grad_(need[1])
@@ -206,6 +212,54 @@ class _HebbianConvNd(nn.Module):
             self.delta_w += tmp_dw.transpose(0, 1) if self._transposed else tmp_dw
         self.winners = win
         return y
+
+    def _native_backward(self, x, weight, bias, gy, need):
+        """(dL/dx, dL/dW, dL/db) on the sm_100 kernels, or None when this layer / shape is not covered."""
+        import os
+        if os.environ.get('HEBB_ATEN_BACKWARD') == '1' or self._transposed or not x.is_cuda:
+            return None
+        nd = self._nd
+        prec = _native.parse_prec(self.prec)
+        if prec == _native.PREC_FP32 or any(s != 1 for s in _ntuple(self.stride, nd)):
+            return None
+        w_raw = self._raw(weight.detach())
+        if w_raw is None or x.dtype != torch.float32:
+            return None
+        x = x.detach().contiguous()
+        gy = gy.detach().contiguous()
+        desc = self._desc(x.shape, True)
+        lo, hi = self._pad_lo_hi()
+        ks = _ntuple(self.kernel_size, nd)
+        gx = gw = gb = None
+        if need[0]:
+            lo2 = [k - 1 - p for k, p in zip(ks, lo)]
+            hi2 = [k - 1 - p for k, p in zip(ks, hi)]
+            if min(lo2 + hi2) < 0:
+                return None
+            d2 = _native.make_desc(nd, x.shape[0], self.out_channels, self.in_channels, gy.shape[2:], ks,
+                                   (1,) * nd, lo2, hi2, False)
+            if not _native.uses_tensor_cores(d2, prec):
+                return None
+        if need[1] and not _native.uses_tensor_cores(desc, prec):
+            return None
+        if need[0]:
+            wn = normalize(weight.detach(), dim=tuple(range(1, nd + 2))) if self.w_nrm else weight.detach()
+            wf = wn.flip(tuple(range(2, nd + 2))).transpose(0, 1).contiguous()
+            gx = torch.empty_like(x)
+            _native.conv_step(d2, gy, wf, None, 1.0, gx, None, None, 0, prec)
+        if need[1]:
+            gwn = _native.conv_wgrad(desc, x, gy, prec).reshape(weight.shape)
+            if self.w_nrm:          # chain rule through W / |W| on the (small) weight tensor
+                with torch.enable_grad():
+                    ww = weight.detach().requires_grad_(True)
+                    nrm = (ww ** 2).sum(dim=tuple(range(1, ww.dim())), keepdim=True) ** 0.5
+                    wn2 = ww / torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+                    gw, = torch.autograd.grad(wn2, ww, gwn)
+            else:
+                gw = gwn
+        if need[2] and bias is not None:
+            gb = gy.sum(dim=(0, *range(2, nd + 2)))
+        return gx, gw, gb
 
     def _aten_formula(self, x, w, b):
         """The reference formula with stock ops; used ONLY to differentiate (see _HebbFn.backward)."""

@@ -68,6 +68,7 @@ def load():
         step = [ctypes.POINTER(HebbDesc), vp, vp, vp, f32, vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_uint, i32, vp]
         lib.hebb_conv_swta_step.argtypes = step
         lib.hebb_convT_swta_step.argtypes = step
+        lib.hebb_conv_wgrad.argtypes = [ctypes.POINTER(HebbDesc), vp, vp, vp, vp, ctypes.c_size_t, i32, vp]
         lib.hebb_local_update_multi.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
                                                 ctypes.POINTER(f32), ctypes.POINTER(ctypes.c_int32), vp]
         lib.hebb_debug_umma_probe.argtypes = [vp, i32, vp, i32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
@@ -192,6 +193,20 @@ def conv_step(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w, flags
             delta_w.data_ptr() if delta_w is not None else None, ws.data_ptr(), ws.numel(),
             int(flags), int(prec), _stream_ptr(x.device))
     check(st, 'conv_swta_step')
+
+
+def conv_wgrad(desc: HebbDesc, x, grad_y, prec: int):
+    """grad_w[Cout][Cin][taps] of a stride-1 convolution on the tcgen05 contraction kernel (hebb_conv_wgrad).
+    Returns None when the layer is outside the tensor-core planner (the caller then uses ATen)."""
+    if desc.transposed or prec == PREC_FP32 or not uses_tensor_cores(desc, prec):
+        return None
+    _require_cuda(x, 'x'); _require_cuda(grad_y, 'grad_y')
+    taps = desc.k[0] * desc.k[1] * desc.k[2]
+    gw = torch.zeros((desc.Cout, desc.Cin, taps), dtype=torch.float32, device=x.device)
+    ws = workspace(x.device, workspace_bytes(desc, prec))
+    check(load().hebb_conv_wgrad(ctypes.byref(desc), x.data_ptr(), grad_y.data_ptr(), gw.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), int(prec), _stream_ptr(x.device)), 'conv_wgrad')
+    return gw
 
 
 def wnorm(W: torch.Tensor, rows: int, row_stride: int, mid: int, mid_stride: int, inner: int,

@@ -104,6 +104,17 @@ int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const
                         float kinv, float* y, int32_t* winner, float* delta_w,
                         void* ws, size_t ws_bytes, unsigned flags, int prec, void* stream);
 
+/* Weight gradient of a stride-1 convolution on the same tcgen05 contraction kernel as the plasticity update
+ * ("the wgrad kernel *is* a6 with dL/dy in place of r"):
+ *     grad_w[co][ci][tap] += sum_p grad_y[b][co][p] * xpad[b][ci][p + tap]
+ * Replaces the weight-gradient half of torch's convolution backward that the reference reaches through
+ * loss.backward() for layers with alpha < 1 (hebb/hebb.py:185-191, train_sup_2d.py:150-168).
+ * x: [B][Cin][in...], grad_y: [B][Cout][out...], grad_w: [Cout][Cin][taps], all fp32 contiguous.
+ * prec: HEBB_PREC_BF16X3 (fp32-equivalent) or HEBB_PREC_BF16.  HEBB_ESHAPE for layers the tcgen05 planner
+ * does not take (the caller then uses its own fallback; nothing is computed). */
+int hebb_conv_wgrad(const HebbDesc* d, const float* x, const float* grad_y, float* grad_w, void* ws,
+                    size_t ws_bytes, int prec, void* stream);
+
 /* a9: one HebbianConvTranspose{2,3}d.forward in swta_t/patchwise mode —
  * hebb/hebb.py:226-264, hebb/hebb3d.py:250-289.  W and delta_w are the CONTIGUOUS
  * [Cout,Cin,k..] buffers underneath the reference's transposed (Cin,Cout,k..) view; the

@@ -16,3 +16,11 @@ d=json.loads(open('gpurun_out/bench_$w.json').read().strip().splitlines()[-1])
 print('$w', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline'].get('stages_ms'), d['roofline']['frac'])
 PY
 done
+for extra in "" "--aten-backward"; do
+  python bench.py --workload c6 --steps 5 --warmup 3 --no-cpu-baseline --no-layer-profile $extra > gpurun_out/bench_c6$extra.json 2>gpurun_out/bench_c6.err || tail -5 gpurun_out/bench_c6.err
+  python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_c6$extra.json').read().strip().splitlines()[-1])
+print('c6 $extra', d['value'], d['ms_per_step'], d['e2e']['value'])
+PY
+done

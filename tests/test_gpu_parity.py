@@ -347,6 +347,44 @@ def test_backprop_through_layer_when_alpha_below_one():
     assert relerr(layer.weight.grad, 0.5 * gbp - 0.5 * dw) < 1e-6
 
 
+# ---- dL/dW on the plasticity contraction kernel, dL/dx on the forward kernel ----
+@pytest.mark.parametrize('prec', ['bf16x3', 'bf16'])
+@pytest.mark.parametrize('case', [(2, 2, 16, 32, (20, 24), 3, 1, True), (2, 4, 3, 16, (33, 17), 3, 1, False),
+                                  (3, 2, 32, 32, (6, 10, 8), 3, 1, True), (2, 2, 64, 16, (16, 16), 1, 0, True),
+                                  (2, 2, 128, 64, (12, 9), 3, 1, True)])
+def test_native_backward_matches_oracle_autograd(case, prec):
+    """alpha = 0 (fine-tuning stage, train_sup_2d.py:150-168): gradients of a loss through the layer, native
+    tcgen05 backward vs. autograd through the CPU oracle formula; also vs. the library's own ATen backward."""
+    nd, B, Cin, Cout, sp, k, pad, xgrad = case
+    g = torch.Generator().manual_seed(Cin + Cout)
+    cls = hebb.HebbianConv2d if nd == 2 else hebb.HebbianConv3d
+    layer = cls(Cin, Cout, k, padding=pad, bias=True, k=3., alpha=0.)
+    with torch.no_grad():
+        layer.bias.copy_(torch.randn(Cout, generator=g) * 0.1)
+    layer.prec = prec
+    layer = layer.to(DEV).train()
+    x0 = torch.randn(B, Cin, *sp, generator=g)
+    t = torch.randn(B, Cout, *sp, generator=g)          # same-size output for these paddings
+    x = x0.to(DEV).requires_grad_(xgrad)
+    from hebb import _native as N
+    n0 = N.launch_count()
+    y = layer(x)
+    (y * t.to(DEV)).sum().backward()
+    assert N.launch_count() - n0 >= 6                    # forward + native backward kernels really ran
+    xr = x0.clone().requires_grad_(xgrad)
+    wr = layer.weight.detach().cpu().clone().requires_grad_(True)
+    br = layer.bias.detach().cpu().clone().requires_grad_(True)
+    yr = O.conv_activation(O.zero_halo(xr, pad, nd), wr, br, (1,) * nd)
+    (yr * t).sum().backward()
+    tol = 1e-4 if prec == 'bf16x3' else 1e-2
+    record('native_backward_vs_oracle', f'{Cin}x{Cout}k{k}/{nd}d/{prec}', gw=relerr(layer.weight.grad, wr.grad),
+           gx=(relerr(x.grad, xr.grad) if xgrad else 0.0))
+    assert relerr(layer.weight.grad, wr.grad) < tol
+    assert relerr(layer.bias.grad, br.grad) < 1e-5
+    if xgrad:
+        assert relerr(x.grad, xr.grad) < tol
+
+
 # ---- SURVEY §8f row 2: fused BatchNorm(train)+activation and 2x bilinear up-sampling ----
 @pytest.mark.parametrize('shape,slope', [((4, 16, 33, 20), 0.01), ((3, 7, 9, 5, 6), 0.0), ((64, 16, 64, 64), 0.01), ((2, 32, 8, 8), 1.0)])
 def test_fused_bn_act_matches_torch(shape, slope):
