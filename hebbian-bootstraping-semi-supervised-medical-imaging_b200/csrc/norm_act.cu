@@ -127,6 +127,40 @@ upsample2x_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out
   }
 }
 
+// 2x max pooling (kernel = stride = 2, no padding, floor mode) of [N][D][H][W] planes; POOL_D = false keeps D
+// (2-D pooling).  NaNs propagate like torch's max_pool.  One thread per output element, 8-byte loads when W is even.
+__device__ __forceinline__ float nanmax(float a, float b) { return (a > b || a != a) ? a : b; }
+
+template <bool POOL_D, bool VEC>
+__global__ void __launch_bounds__(256)
+maxpool2x_kernel(const float* __restrict__ in, float* __restrict__ out, long long N, int D, int H, int W) {
+  const int OD = POOL_D ? D / 2 : D, OH = H / 2, OW = W / 2;
+  const long long total = N * OD * OH * OW;
+  const long long HW = (long long)H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(idx % OW);
+    long long t = idx / OW;
+    const int oh = (int)(t % OH); t /= OH;
+    const int od = (int)(t % OD);
+    const long long n = t / OD;
+    const float* p = in + (n * D + (POOL_D ? 2 * od : od)) * HW + (long long)(2 * oh) * W + 2 * ow;
+    float m;
+    if (VEC) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(p)), b = __ldg(reinterpret_cast<const float2*>(p + W));
+      m = nanmax(nanmax(a.x, a.y), nanmax(b.x, b.y));
+      if (POOL_D) {
+        const float2 c = __ldg(reinterpret_cast<const float2*>(p + HW)), d = __ldg(reinterpret_cast<const float2*>(p + HW + W));
+        m = nanmax(m, nanmax(nanmax(c.x, c.y), nanmax(d.x, d.y)));
+      }
+    } else {
+      m = nanmax(nanmax(__ldg(p), __ldg(p + 1)), nanmax(__ldg(p + W), __ldg(p + W + 1)));
+      if (POOL_D) m = nanmax(m, nanmax(nanmax(__ldg(p + HW), __ldg(p + HW + 1)), nanmax(__ldg(p + HW + W), __ldg(p + HW + W + 1))));
+    }
+    out[idx] = m;
+  }
+}
+
 }  // namespace hebb
 
 using namespace hebb;
@@ -179,6 +213,28 @@ int hebb_upsample2x_bilinear(const float* in, float* out, int64_t N, int64_t H, 
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   upsample2x_bilinear_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(in, out, N, (int)H, (int)W);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
+int hebb_maxpool2x(const float* in, float* out, int64_t N, int64_t D, int64_t H, int64_t W, int pool_depth, void* stream) {
+  HEBB_TRY(device_ok());
+  if (!in || !out) return HEBB_EARG;
+  if (N <= 0 || D <= 0 || H < 2 || W < 2 || (pool_depth && D < 2) || D > (1 << 20) || H > (1 << 20) || W > (1 << 20))
+    return HEBB_ESHAPE;
+  const long long total = N * (pool_depth ? D / 2 : D) * (H / 2) * (W / 2);
+  long long gx = cdiv(total, 256);
+  const long long cap = (long long)num_sms() * 32;
+  if (gx > cap) gx = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7) == 0);
+  if (pool_depth) {
+    if (vec) maxpool2x_kernel<true, true><<<(unsigned)gx, 256, 0, st>>>(in, out, N, (int)D, (int)H, (int)W);
+    else maxpool2x_kernel<true, false><<<(unsigned)gx, 256, 0, st>>>(in, out, N, (int)D, (int)H, (int)W);
+  } else {
+    if (vec) maxpool2x_kernel<false, true><<<(unsigned)gx, 256, 0, st>>>(in, out, N, (int)D, (int)H, (int)W);
+    else maxpool2x_kernel<false, false><<<(unsigned)gx, 256, 0, st>>>(in, out, N, (int)D, (int)H, (int)W);
+  }
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   return HEBB_OK;
 }

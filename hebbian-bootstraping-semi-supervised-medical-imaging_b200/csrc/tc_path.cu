@@ -233,6 +233,48 @@ pack_w_kernel(const float* __restrict__ W, uint4* __restrict__ wp, int Cin, int 
   }
 }
 
+// Same packed layout for plain convolutions with LARGE weights, read coalesced: a block stages the 16 input
+// channels x all taps of 16 filters (each a contiguous run of 16*taps floats of [Cout][Cin][taps]) in shared
+// memory and emits 16 consecutive filters per 256-byte store run.  (The element-wise kernel above reads with a
+// stride of Cin*taps floats between threads, which costs ~8x the bytes on the 57-113 MB bottleneck weights.)
+__global__ void __launch_bounds__(256)
+pack_w_tiled_kernel(const float* __restrict__ W, uint4* __restrict__ wp, int Cin, int Cout, int taps, int HL, int CT) {
+  extern __shared__ float tile[];               // [16 filters][16*taps + 1]
+  const int slab = blockIdx.x, co0 = blockIdx.y * 16;
+  const int row = 16 * taps, pitch = row + 1;
+  const int ci0 = slab * 16;
+  const int nci = (Cin - ci0 < 16) ? (Cin - ci0) : 16;
+  for (int i = threadIdx.x; i < 16 * row; i += blockDim.x) {
+    const int f = i / row, j = i - f * row;
+    tile[f * pitch + j] = (j < nci * taps) ? __ldg(W + ((long long)(co0 + f) * Cin + ci0) * taps + j) : 0.f;
+  }
+  __syncthreads();
+  const int n_ct = Cout / CT;
+  const int ct = co0 / CT, cl0 = co0 - ct * CT;
+  const int items = taps * 2 * HL * 16;         // (tap, c2, hl, filter) with the filter fastest
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int f = i & 15;
+    int t = i >> 4;
+    const int hl = t % HL; t /= HL;
+    const int c2 = t & 1;
+    const int tap = t >> 1;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat16 e[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float v = tile[f * pitch + (c2 * 8 + 2 * k + j) * taps + tap];
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        e[j] = hl ? lo : hi;
+      }
+      o[k] = pack_bf16x2(e[0], e[1]);
+    }
+    wp[((((long long)(slab * n_ct + ct) * taps + tap) * 2 + c2) * HL + hl) * CT + cl0 + f] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // -------------------------------------------------------------------------------------
 // Forward shift-GEMM + fused soft-WTA epilogue
 // -------------------------------------------------------------------------------------
@@ -1644,8 +1686,14 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   }
   if (do_pack && !wgrad) {
     const long long n = (long long)P.NSLAB * g.taps * P.f_HL * 2 * g.Cout;
-    pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL, P.CT, tr ? g0.taps : 0, trq,
-                                              (tr && (flags & HEBB_F_WNRM)) ? inv : nullptr);
+    const size_t tile_bytes = (size_t)16 * (16 * g.taps + 1) * sizeof(float);
+    if (!tr && n >= (1LL << 16) && tile_bytes <= 48 * 1024) {
+      dim3 wg((unsigned)P.NSLAB, (unsigned)(g.Cout / 16));
+      pack_w_tiled_kernel<<<wg, 256, tile_bytes, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.f_HL, P.CT);
+    } else {
+      pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, wp, g.Cin, g.Cout, g.taps, P.NSLAB, P.f_HL, P.CT, tr ? g0.taps : 0, trq,
+                                                (tr && (flags & HEBB_F_WNRM)) ? inv : nullptr);
+    }
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
 

@@ -78,6 +78,7 @@ def load():
                                              ctypes.c_uint32, ctypes.c_uint32, i32, i32, i32, i32, vp, vp]
         lib.hebb_bn_act_train.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, vp, ctypes.c_size_t, vp]
         lib.hebb_upsample2x_bilinear.argtypes = [vp, vp, i64, i64, i64, vp]
+        lib.hebb_maxpool2x.argtypes = [vp, vp, i64, i64, i64, i64, i32, vp]
         lib.hebb_debug_launch_count.restype = ctypes.c_ulonglong
         lib.hebb_uses_tensor_cores.argtypes = [ctypes.POINTER(HebbDesc), i32]
         for name in EXPORTS:
@@ -265,6 +266,20 @@ def upsample2x_bilinear(x):
     B, C, H, W = x.shape
     out = torch.empty((B, C, 2 * H, 2 * W), dtype=x.dtype, device=x.device)
     check(load().hebb_upsample2x_bilinear(x.data_ptr(), out.data_ptr(), B * C, H, W, _stream_ptr(x.device)), 'upsample2x')
+    return out
+
+
+def maxpool2x(x):
+    """max_pool{2,3}d(kernel_size=2, stride=2) of a contiguous fp32 CUDA tensor (hebb_maxpool2x)."""
+    _require_cuda(x, 'input')
+    if x.dim() == 4:
+        B, C, H, W = x.shape
+        D, pd, out_shape = 1, 0, (B, C, H // 2, W // 2)
+    else:
+        B, C, D, H, W = x.shape
+        pd, out_shape = 1, (B, C, D // 2, H // 2, W // 2)
+    out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
+    check(load().hebb_maxpool2x(x.data_ptr(), out.data_ptr(), B * C, D, H, W, pd, _stream_ptr(x.device)), 'maxpool2x')
     return out
 
 

@@ -4,7 +4,8 @@
 every `HebbianConv -> BatchNorm{2,3}d -> ReLU/LeakyReLU` run inside an `nn.Sequential` so that the
 BatchNorm(train) + activation pair runs as `hebb_bn_act_train` (one statistics pass, one
 normalise+activate pass), and every `nn.Upsample(scale_factor=2, bilinear, align_corners=True)` so it
-runs as `hebb_upsample2x_bilinear`.  Numerics follow torch (biased variance for normalisation, unbiased
+runs as `hebb_upsample2x_bilinear`, and every 2x `nn.MaxPool{2,3}d` (kernel = stride = 2, no padding) so it runs
+as `hebb_maxpool2x`.  Numerics follow torch (biased variance for normalisation, unbiased
 for the running estimate, momentum update, num_batches_tracked).  Anything the kernels do not cover —
 eval mode, inputs or affine parameters that require grad, CPU tensors, cumulative-average momentum —
 takes the stock torch path of the parent class, so the pass is always safe to apply.
@@ -54,6 +55,43 @@ class FastUpsample2x(nn.Upsample):
         return super().forward(x)
 
 
+def _is_two(v, n):
+    v = tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
+    return len(v) == n and all(int(i) == 2 for i in v)
+
+
+def _is_zero(v, n):
+    v = tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
+    return all(int(i) == 0 for i in v)
+
+
+def _is_one(v, n):
+    v = tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
+    return all(int(i) == 1 for i in v)
+
+
+class _FastMaxPoolMixin:
+    def forward(self, x):
+        nd = x.dim() - 2
+        if _fast_ok(x, self) and min(x.shape[2:]) >= 2:
+            return _native.maxpool2x(x)
+        return super().forward(x)
+
+
+class FastMaxPool2d(_FastMaxPoolMixin, nn.MaxPool2d):
+    pass
+
+
+class FastMaxPool3d(_FastMaxPoolMixin, nn.MaxPool3d):
+    pass
+
+
+def _pool_is_2x(m, n):
+    stride = m.stride if m.stride is not None else m.kernel_size
+    return (_is_two(m.kernel_size, n) and _is_two(stride, n) and _is_zero(m.padding, n) and _is_one(m.dilation, n)
+            and not m.ceil_mode and not m.return_indices)
+
+
 def _slope_of(m):
     if type(m) is nn.ReLU:
         return 0.0
@@ -63,7 +101,7 @@ def _slope_of(m):
 
 
 def fuse_norm_act(model: nn.Module) -> nn.Module:
-    n_bn = n_up = 0
+    n_bn = n_up = n_pool = 0
     for mod in model.modules():
         if isinstance(mod, nn.Sequential):
             items = list(mod._modules.items())
@@ -79,5 +117,11 @@ def fuse_norm_act(model: nn.Module) -> nn.Module:
             if type(m) is nn.Upsample and m.mode == 'bilinear' and m.align_corners and m.scale_factor in (2, 2.0, (2, 2), (2.0, 2.0)):
                 m.__class__ = FastUpsample2x
                 n_up += 1
-    model._hebb_fused = dict(bn_act=n_bn, upsample=n_up)
+            elif type(m) is nn.MaxPool2d and _pool_is_2x(m, 2):
+                m.__class__ = FastMaxPool2d
+                n_pool += 1
+            elif type(m) is nn.MaxPool3d and _pool_is_2x(m, 3):
+                m.__class__ = FastMaxPool3d
+                n_pool += 1
+    model._hebb_fused = dict(bn_act=n_bn, upsample=n_up, maxpool=n_pool)
     return model

@@ -146,6 +146,12 @@ int hebb_bn_act_train(const float* y, float* out, const float* gamma, const floa
  * in: [N][H][W], out: [N][2H][2W] fp32, N = batch*channels. */
 int hebb_upsample2x_bilinear(const float* in, float* out, int64_t N, int64_t H, int64_t W, void* stream);
 
+/* 2x max pooling (kernel = stride = 2, no padding, floor mode, NaNs propagate) of N planes [D][H][W]:
+ * nn.MaxPool2d(2) (pool_depth = 0, D = 1) and nn.MaxPool3d(kernel_size=2, stride=2) (pool_depth = 1) between
+ * the Hebbian blocks (reference models/networks_2d/unet.py:70-80, networks_3d/unet3d.py:31-43).  SURVEY §8f row 2. */
+int hebb_maxpool2x(const float* in, float* out, int64_t N, int64_t D, int64_t H, int64_t W, int pool_depth,
+                   void* stream);
+
 /* ---- exported for tests and profiling ---- */
 
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */

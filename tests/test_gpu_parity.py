@@ -413,6 +413,19 @@ def test_upsample2x_matches_torch(shape):
     assert got.shape == want.shape and float((got - want).abs().max()) < 2e-6
 
 
+@pytest.mark.parametrize('shape', [(2, 3, 8, 10), (4, 16, 33, 31), (1, 1, 2, 2), (2, 4, 6, 8, 10), (1, 3, 5, 7, 9), (2, 2, 2, 2, 3)])
+def test_maxpool2x_matches_torch(shape):
+    from hebb import _native as N
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(5)).to(DEV)
+    x.view(-1)[3] = float('nan')                    # torch's max_pool propagates NaNs
+    pool = torch.nn.functional.max_pool2d if len(shape) == 4 else torch.nn.functional.max_pool3d
+    want = pool(x, kernel_size=2, stride=2)
+    got = N.maxpool2x(x)
+    assert got.shape == want.shape
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want))
+
+
 def test_fuse_pass_keeps_network_output_and_state():
     from hebb.fused import fuse_norm_act
     torch.manual_seed(0)
