@@ -154,8 +154,10 @@ int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const
   if (!aligned16(ws)) return HEBB_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   flags &= 0xFFFFu;                       // bits above are library-internal
-  if (use_tc(g, prec) && !(flags & HEBB_F_RULE_HPCA))
-    return tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, st);
+  if (use_tc(g, prec)) {      // HPCA layers the planner cannot give a Gram plan fall through to the fp32 kernels
+    const int s = tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, st);
+    if (!(s == HEBB_ESHAPE && (flags & HEBB_F_RULE_HPCA))) return s;
+  }
   return simt_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, st);
 }
 

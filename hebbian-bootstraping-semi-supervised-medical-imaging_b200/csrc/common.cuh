@@ -73,6 +73,9 @@ int simt_convT_step(const Geo& g, const float* x, const float* W, const float* b
                     int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags,
                     cudaStream_t st);
 
+// delta_w[c][j] -= sum_{c' <= c} G[c][c'] W[c'][j]   (HPCA decay on the CUDA cores; G, W fp32)
+int launch_hpca_decay(const float* G, const float* W, float* delta_w, int Cout, int K, cudaStream_t st);
+
 // ---- tcgen05 path (tc_path.cu) ----
 bool tc_supported(const Geo& g, int prec);
 size_t tc_workspace_bytes(const Geo& g, int prec);

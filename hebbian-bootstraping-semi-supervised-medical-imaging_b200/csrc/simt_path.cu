@@ -207,6 +207,20 @@ struct HpcaDecay {
   }
 };
 
+// delta_w[c][j] -= sum_{c' <= c} G[c][c'] W[c'][j]   (decay alone: the tensor-core path adds y X itself)
+struct HpcaDecayOnly {
+  const float* G; const float* W; float* dw; int Cout, K;
+  static constexpr bool kAMajorM = false;
+  static constexpr bool kBMajorK = false;
+  static constexpr bool kAtomic = false;
+  __device__ long long M() const { return Cout; }
+  __device__ int N() const { return K; }
+  __device__ long long Kd() const { return Cout; }
+  __device__ float a(long long m, long long c) const { return c <= m ? __ldg(G + m * Cout + c) : 0.f; }
+  __device__ float b(long long c, int n) const { return __ldg(W + c * (long long)K + n); }
+  __device__ void store(long long m, int n, float v) const { dw[m * K + n] -= v; }
+};
+
 // Transposed layers in mode 'hpca' use the conv rule with x and y exchanged (hebb.py:243-246): the layer
 // INPUT is the response, the unfolded OUTPUT is the presynaptic patch.
 // G = x x^T  [Cin x Cin], contraction over input pixels
@@ -498,6 +512,14 @@ int simt_conv_step(const Geo& g, const float* x, const float* W, const float* bi
       HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
     }
   }
+  return HEBB_OK;
+}
+
+int launch_hpca_decay(const float* G, const float* W, float* delta_w, int Cout, int K, cudaStream_t st) {
+  HpcaDecayOnly hd{G, W, delta_w, Cout, K};
+  dim3 grid((unsigned)cdiv(Cout, BM), (unsigned)cdiv(K, BN), 1);
+  simt_gemm_kernel<HpcaDecayOnly><<<grid, 256, 0, st>>>(hd, (long long)cdiv(Cout, BK) * BK);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   return HEBB_OK;
 }
 

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include <cstdlib>
+#include <vector>
 
 // the single-pass instantiations of the forward epilogue leave the generic multi-pass code unreachable
 #pragma nv_diag_suppress 128
@@ -1365,8 +1366,8 @@ struct Plan {
   int stackM, stackN, cpt, Q, nrep;
   uint32_t d_stage, d_x_bytes, d_off_bar, d_smem, d_tmem;
   // workspace carve (byte offsets)
-  size_t o_inv, o_rsum, o_err, o_xp[2], o_rp[2], o_wp, o_hpart, total;
-  bool ok;
+  size_t o_inv, o_rsum, o_err, o_xp[2], o_rp[2], o_wp, o_hpart, o_gram, o_hpart2, total;
+  bool ok, gram_ok;
 };
 
 // A transposed conv with kernel == stride == 2 (3-D) and no padding is a 1x1 conv onto Cout*8
@@ -1408,7 +1409,21 @@ static int tr_quantum(const Geo& g0) {
   return (q <= 512 && q % 32 == 0) ? q : 0;
 }
 
-static bool plan_layer(const Geo& g, int prec, Plan* P, int trq = 0) {
+// The Gram matrix G = y y^T of the HPCA rule as a layer: 1x1, Cout -> Cout, over a 1-D image of PR positions.
+static Geo gram_geo(const Geo& g, long long PR) {
+  Geo e = g;
+  e.nd = 3; e.B = 1; e.Cin = g.Cout; e.Cout = g.Cout;
+  e.iD = 1; e.iH = 1; e.iW = (int)PR;
+  e.kD = e.kH = e.kW = 1; e.sD = e.sH = e.sW = 1;
+  e.pD = e.pH = e.pW = e.qD = e.qH = e.qW = 0;
+  e.oD = 1; e.oH = 1; e.oW = (int)PR;
+  e.taps = 1; e.K = g.Cout; e.inS = PR; e.outS = PR; e.transposed = 0;
+  return e;
+}
+
+static bool plan_layer(const Geo& g, int prec, Plan* P, int trq = 0, bool gram = false);
+
+static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gram) {
   Plan& q = *P;
   q.ok = false;
   if (g.transposed || g.sD != 1 || g.sH != 1 || g.sW != 1) return false;
@@ -1563,7 +1578,8 @@ static bool plan_layer(const Geo& g, int prec, Plan* P, int trq = 0) {
   q.d_tmem = pow2_cols((q.d_by_kh ? 1 : g.kH) * (int)cdiv(g.kW, q.nrep) * q.CN * (q.stackN ? 2 : 1));
 
   // packed position space: multiples of both tile sizes
-  const int big = q.TILE_M > q.BLK ? q.TILE_M : q.BLK;
+  // multiple of every stage size (<= 1024 positions), also of a second plan's over the same positions (HPCA Gram)
+  const int big = 1024;
   q.PR = (q.PTOT + big - 1) / big * big;
   q.PA = (q.PR + q.maxshift + 16 + 7) / 8 * 8;
   q.f_ntiles = (int)(q.PR / q.TILE_M);
@@ -1588,9 +1604,49 @@ static bool plan_layer(const Geo& g, int prec, Plan* P, int trq = 0) {
   q.o_rp[1] = take((size_t)q.C8 * q.PR * 16);
   q.o_wp = take((size_t)q.NSLAB * g.taps * q.f_HL * 2 * g.Cout * 16);
   q.o_hpart = take((size_t)q.PS * q.Q * g.taps * q.CinP * g.Cout * sizeof(float));
+  q.gram_ok = false; q.o_gram = q.o_hpart2 = 0;
+  if (!gram && !trq) {
+    // HPCA (hebb.py:122-135) also needs G = y y^T: the same contraction kernel over the packed responses,
+    // planned as a 1x1 layer Cout -> Cout over the PR packed positions (a 1-D "image")
+    Geo g2 = gram_geo(g, q.PR);
+    Plan P2;
+    if (plan_layer(g2, prec, &P2, 0, true) && P2.PR == q.PR) {
+      q.gram_ok = true;
+      q.o_gram = take(sizeof(float) * (size_t)g.Cout * g.Cout);
+      q.o_hpart2 = take((size_t)P2.PS * P2.Q * P2.CinP * g.Cout * sizeof(float));
+    }
+  }
   q.total = off;
   q.ok = true;
   return true;
+}
+
+// The search above costs tens of microseconds and runs for every launch and workspace query: keep the last
+// few plans per host thread (a network has a few dozen distinct layer shapes).
+static bool geo_eq(const Geo& a, const Geo& b) {
+  return a.nd == b.nd && a.B == b.B && a.Cin == b.Cin && a.Cout == b.Cout && a.iD == b.iD && a.iH == b.iH &&
+         a.iW == b.iW && a.kD == b.kD && a.kH == b.kH && a.kW == b.kW && a.sD == b.sD && a.sH == b.sH && a.sW == b.sW &&
+         a.pD == b.pD && a.pH == b.pH && a.pW == b.pW && a.qD == b.qD && a.qH == b.qH && a.qW == b.qW &&
+         a.oD == b.oD && a.oH == b.oH && a.oW == b.oW && a.taps == b.taps && a.K == b.K && a.inS == b.inS &&
+         a.outS == b.outS && a.transposed == b.transposed;
+}
+
+static bool plan_layer(const Geo& g, int prec, Plan* P, int trq, bool gram) {
+  struct Entry { Geo g; int prec, trq, gram, sms; Plan plan; bool ok; };
+  thread_local std::vector<Entry> cache;
+  const int sms = num_sms();
+  for (const Entry& e : cache)
+    if (e.prec == prec && e.trq == trq && e.gram == (int)gram && e.sms == sms && geo_eq(e.g, g)) {
+      *P = e.plan;
+      return e.ok;
+    }
+  Entry e;
+  e.g = g; e.prec = prec; e.trq = trq; e.gram = gram; e.sms = sms;
+  e.ok = plan_layer_search(g, prec, &e.plan, trq, gram);
+  if (cache.size() >= 128) cache.erase(cache.begin());
+  cache.push_back(e);
+  *P = e.plan;
+  return e.ok;
 }
 
 bool tc_supported(const Geo& g, int prec) {
@@ -1624,6 +1680,46 @@ static unsigned ew_grid(long long n) {
   return (unsigned)(gx > cap ? cap : (gx < 1 ? 1 : gx));
 }
 
+// Fills the parameter block of the contraction kernel for plan P / geometry g and launches it.  `PA` is the
+// position stride between 8-channel planes of the x operand (P.PA for packed activations).
+static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4* xp1, const uint4* rp0, const uint4* rp1,
+                     float* hpart, int* err, long long PA, cudaStream_t st) {
+  DwParams d;
+  d.xp[0] = xp0; d.xp[1] = xp1; d.rp[0] = rp0; d.rp[1] = rp1; d.hpart = hpart; d.err = err;
+  d.Cin = g.Cin; d.Cout = g.Cout; d.CC = P.CC; d.C8 = P.C8; d.taps = g.taps; d.HL = P.d_HL;
+  d.PA = PA; d.PR = P.PR; d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
+  d.blocks_per_split = P.blocks_per_split; d.PS = P.PS; d.ngrp = P.ngrp;
+  for (int i = 0; i < 9; ++i) d.grp_base[i] = 0;
+  d.nrep = P.nrep;
+  for (int t = 0; t < kMaxTaps; ++t) { d.st_off[t] = 0; d.st_first[t] = 0; d.st_n[t] = 0; }
+  {
+    // tap groups (one CTA column set each) -> super-taps (one accumulator column group each) -> taps
+    int nst = 0, gi = 0;
+    for (int kd = 0; kd < g.kD; ++kd) {
+      if (!P.d_by_kh) { d.grp_base[gi] = kd * P.plane; d.grp_st_begin[gi] = nst; }
+      for (int kh = 0; kh < g.kH; ++kh) {
+        if (P.d_by_kh) { d.grp_base[gi] = kd * P.plane + kh * P.WP; d.grp_st_begin[gi] = nst; }
+        for (int kw0 = 0; kw0 < g.kW; kw0 += P.nrep, ++nst) {
+          d.st_off[nst] = (P.d_by_kh ? 0 : kh * P.WP) + kw0;
+          d.st_first[nst] = (kd * g.kH + kh) * g.kW + kw0;
+          d.st_n[nst] = (g.kW - kw0 < P.nrep) ? (g.kW - kw0) : P.nrep;
+        }
+        if (P.d_by_kh) ++gi;
+      }
+      if (!P.d_by_kh) ++gi;
+    }
+    for (int i = gi; i < 10; ++i) d.grp_st_begin[i] = nst;
+  }
+  d.stackM = P.stackM; d.stackN = P.stackN; d.cpt = P.cpt;
+  d.CM = P.CM; d.n_cin_tiles = P.n_cin_tiles; d.CN = P.CN; d.n_cout_tiles = P.n_cout_tiles; d.ST = P.ST; d.CinP = P.CinP;
+  d.stage_bytes = P.d_stage; d.x_bytes = P.d_x_bytes; d.off_bar = P.d_off_bar; d.tmem_cols = P.d_tmem;
+  const int dgrid = P.ngrp * P.n_cin_tiles * P.n_cout_tiles * P.PS;
+  HEBB_CUDA_TRY(cudaFuncSetAttribute(dw_swta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  dw_swta_kernel<<<dgrid, 192, kSmemLimit, st>>>(d);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
 int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bias, float kinv, float* y,
                  int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
                  cudaStream_t st) {
@@ -1647,6 +1743,9 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   // responses, and the finalize pass adds the plain contraction (no decay term) to delta_w
   const bool wgrad = (flags & HEBB_F_WGRAD_INTERNAL) != 0;
   if (wgrad && tr) return HEBB_ESHAPE;
+  // HPCA (hebb.py:122-135): the response is y itself, the decay is tril(y y^T) W
+  const bool hpca = (flags & HEBB_F_RULE_HPCA) != 0 && (flags & HEBB_F_UPDATE) != 0;
+  if (hpca && (tr || !P.gram_ok)) return HEBB_ESHAPE;
   const bool upd = (flags & HEBB_F_UPDATE) != 0 || wgrad;
 
   // profiling aid: HEBB_F_ONLY_* re-run one stage on the scratch left by a preceding full call
@@ -1709,7 +1808,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   f.PA = P.PA; f.PR = P.PR; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
   f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC; f.WG = P.WG;
   f.WP = P.WP; f.plane = P.plane; f.Qimg = P.Qimg; f.oD = g.oD; f.oH = g.oH; f.oW = g.oW;
-  f.kinv = kinv; f.write_r = upd ? 1 : 0;
+  f.kinv = kinv; f.write_r = (upd && !hpca) ? 1 : 0;
   for (int s = 0; s < 4; ++s) f.seg_base[s] = s * P.plane;
   for (int s = 0; s <= 4; ++s) f.seg_tap_begin[s] = (s <= g.kD ? s : g.kD) * g.kH * g.kW;
   for (int t = 0; t < kMaxTaps; ++t) f.tap_off[t] = 0;
@@ -1738,7 +1837,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
 #undef HEBB_FWD_LAUNCH
   }
   if (do_fwd) { HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED(); }
-  if (do_fwd && P.n_ct > 1 && !trq && (upd || winner)) {
+  if (do_fwd && P.n_ct > 1 && !trq && ((upd && !hpca) || winner)) {
     SmxParams sp;
     sp.y = y; sp.rp[0] = rp0; sp.rp[1] = rp1; sp.winner = winner; sp.rsum = rsum;
     sp.Cout = g.Cout; sp.RHL = P.d_HL; sp.WP = P.WP; sp.plane = P.plane; sp.Qimg = P.Qimg;
@@ -1757,40 +1856,15 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   }
   if (!do_dw) return HEBB_OK;
 
-  // ---- dW ----
-  DwParams d;
-  d.xp[0] = xp0; d.xp[1] = xp1; d.rp[0] = rp0; d.rp[1] = rp1; d.hpart = hpart; d.err = err;
-  d.Cin = g.Cin; d.Cout = g.Cout; d.CC = P.CC; d.C8 = P.C8; d.taps = g.taps; d.HL = P.d_HL;
-  d.PA = P.PA; d.PR = P.PR; d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
-  d.blocks_per_split = P.blocks_per_split; d.PS = P.PS; d.ngrp = P.ngrp;
-  for (int i = 0; i < 9; ++i) d.grp_base[i] = 0;
-  d.nrep = P.nrep;
-  for (int t = 0; t < kMaxTaps; ++t) { d.st_off[t] = 0; d.st_first[t] = 0; d.st_n[t] = 0; }
-  {
-    // tap groups (one CTA column set each) -> super-taps (one accumulator column group each) -> taps
-    int nst = 0, gi = 0;
-    for (int kd = 0; kd < g.kD; ++kd) {
-      if (!P.d_by_kh) { d.grp_base[gi] = kd * P.plane; d.grp_st_begin[gi] = nst; }
-      for (int kh = 0; kh < g.kH; ++kh) {
-        if (P.d_by_kh) { d.grp_base[gi] = kd * P.plane + kh * P.WP; d.grp_st_begin[gi] = nst; }
-        for (int kw0 = 0; kw0 < g.kW; kw0 += P.nrep, ++nst) {
-          d.st_off[nst] = (P.d_by_kh ? 0 : kh * P.WP) + kw0;
-          d.st_first[nst] = (kd * g.kH + kh) * g.kW + kw0;
-          d.st_n[nst] = (g.kW - kw0 < P.nrep) ? (g.kW - kw0) : P.nrep;
-        }
-        if (P.d_by_kh) ++gi;
-      }
-      if (!P.d_by_kh) ++gi;
-    }
-    for (int i = gi; i < 10; ++i) d.grp_st_begin[i] = nst;
+  if (hpca) {
+    PackRGeo rg;
+    rg.B = g.B; rg.C = g.Cout; rg.C8 = P.C8; rg.oD = g.oD; rg.oH = g.oH; rg.oW = g.oW; rg.WP = P.WP; rg.plane = P.plane;
+    rg.Qimg = P.Qimg; rg.outS = g.outS; rg.PR = P.PR; rg.PTOT = P.PTOT;
+    pack_r_kernel<<<ew_grid((long long)P.C8 * P.PR), 256, 0, st>>>(y, rp0, P.d_HL == 2 ? rp1 : nullptr, rg);
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
-  d.stackM = P.stackM; d.stackN = P.stackN; d.cpt = P.cpt;
-  d.CM = P.CM; d.n_cin_tiles = P.n_cin_tiles; d.CN = P.CN; d.n_cout_tiles = P.n_cout_tiles; d.ST = P.ST; d.CinP = P.CinP;
-  d.stage_bytes = P.d_stage; d.x_bytes = P.d_x_bytes; d.off_bar = P.d_off_bar; d.tmem_cols = P.d_tmem;
-  const int dgrid = P.ngrp * P.n_cin_tiles * P.n_cout_tiles * P.PS;
-  HEBB_CUDA_TRY(cudaFuncSetAttribute(dw_swta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  dw_swta_kernel<<<dgrid, 192, kSmemLimit, st>>>(d);
-  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  // ---- dW ----
+  HEBB_TRY(launch_dw(P, g, xp0, xp1, rp0, rp1, hpart, err, P.PA, st));
   {
     const long long n = (long long)g.taps * g.Cin * g.Cout;
     if (tr)
@@ -1798,14 +1872,31 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     else
     if (n >= (1LL << 18) && P.PS * P.Q <= 32) {
       dim3 fg((unsigned)cdiv((long long)g.Cin * g.taps, 32), (unsigned)cdiv(g.Cout, 32));
-      tc_finalize_tiled_kernel<<<fg, 256, 0, st>>>(hpart, wgrad ? nullptr : rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
+      tc_finalize_tiled_kernel<<<fg, 256, 0, st>>>(hpart, (wgrad || hpca) ? nullptr : rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
     } else {
       long long gx = cdiv(n, 32);
       const long long cap = (long long)num_sms() * 32;
       if (gx > cap) gx = cap;
-      tc_finalize_kernel<<<(unsigned)gx, 256, 0, st>>>(hpart, wgrad ? nullptr : rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
+      tc_finalize_kernel<<<(unsigned)gx, 256, 0, st>>>(hpart, (wgrad || hpca) ? nullptr : rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
     }
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  }
+  if (hpca) {
+    // G = y y^T on the same contraction kernel (both operands are the packed responses), then the
+    // triangular decay  delta_w -= tril(G) W  as a small fp32 GEMM
+    Geo g2 = gram_geo(g, P.PR);
+    Plan P2;
+    if (!plan_layer(g2, prec, &P2, 0, true) || P2.PR != P.PR) return HEBB_ESHAPE;
+    float* G = reinterpret_cast<float*>(base + P.o_gram);
+    float* hpart2 = reinterpret_cast<float*>(base + P.o_hpart2);
+    HEBB_CUDA_TRY(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)g.Cout * g.Cout, st));
+    HEBB_TRY(launch_dw(P2, g2, rp0, rp1, rp0, rp1, hpart2, err, P.PR, st));
+    long long gx = cdiv((long long)g.Cout * g.Cout, 32);
+    const long long cap = (long long)num_sms() * 32;
+    if (gx > cap) gx = cap;
+    tc_finalize_kernel<<<(unsigned)gx, 256, 0, st>>>(hpart2, nullptr, hpart2, G, P2.PS * P2.Q, 1, g.Cout, P2.CinP, g.Cout);
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+    HEBB_TRY(launch_hpca_decay(G, W, delta_w, g.Cout, g.K, st));
   }
   return HEBB_OK;
 }

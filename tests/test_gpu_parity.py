@@ -470,6 +470,30 @@ def test_hpca_vs_reference_golden(golden, name):
     assert relerr(layer.delta_w, golden[name + '/dw1']) < 1e-4
 
 
+@pytest.mark.parametrize('prec', ['bf16x3', 'bf16'])
+@pytest.mark.parametrize('case', [(2, 4, 32, 64, (32, 32), 3, 1), (2, 2, 64, 128, (24, 20), 3, 1), (3, 2, 16, 32, (6, 10, 8), 3, 1),
+                                  (2, 3, 64, 32, (16, 16), 1, 0)])
+def test_hpca_tensor_core_vs_oracle(case, prec):
+    """HPCA on the tcgen05 kernels: y X and the Gram matrix y y^T are both runs of the contraction kernel."""
+    nd, B, Cin, Cout, sp, k, pad = case
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    cls = hebb.HebbianConv2d if nd == 2 else hebb.HebbianConv3d
+    layer = cls(Cin, Cout, k, padding=pad, bias=False, w_nrm=True, mode='hpca', k=1., alpha=1.)
+    x = torch.randn(B, Cin, *sp, generator=g)
+    w = layer.weight.detach().clone()
+    xpad = O.zero_halo(x, pad, nd)
+    y_ref = O.conv_activation(xpad, w, None, (1,) * nd)
+    dw_ref = O.hpca_delta(xpad, y_ref, w, (1,) * nd)
+    layer.prec = prec
+    layer = layer.to(DEV).train()
+    from hebb import _native as N
+    assert N.uses_tensor_cores(layer._desc(x.shape, True), N.parse_prec(prec))
+    y = layer(x.to(DEV))
+    record('hpca_tensor_core_vs_oracle', f'{Cin}x{Cout}k{k}/{nd}d/{prec}', y=relerr(y, y_ref), dw=relerr(layer.delta_w, dw_ref))
+    assert relerr(y, y_ref) < TOL_Y[prec]
+    assert relerr(layer.delta_w, dw_ref) < TOL_DW[prec]
+
+
 def test_reference_hpca_smoke_test_shape():
     """tests/test_makehebbian.py::test_makehebbian3d of the reference, on CUDA at a reduced width."""
     net = workloads.UNet3D(1, 2, init_features=8)
