@@ -87,6 +87,9 @@ struct GatherGeo {
   long long PA, PTOT;
 };
 
+// KD/KH/KW > 0: compile-time kernel extent (3x3 and 3x3x3 get fully unrolled loops, so all loads of a
+// position are in flight together); 0: run-time extent from g.
+template <int KD, int KH, int KW>
 __global__ void __launch_bounds__(256)
 pack_x_gather_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __restrict__ xlo, const __grid_constant__ GatherGeo g) {
   // one thread per output position: walks (ci, kd, kh, kw) with counters (no divisions per element) and
@@ -95,7 +98,8 @@ pack_x_gather_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4
   const long long inS = (long long)g.iD * iHW;
   const int oHW = g.oH * g.oW;
   const long long oS = (long long)g.oD * oHW;
-  const int kD = g.taps / (g.kH * g.kW);
+  const int kD = KD > 0 ? KD : g.taps / (g.kH * g.kW);
+  const int kH = KH > 0 ? KH : g.kH, kW = KW > 0 ? KW : g.kW;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < g.PA;
        p += (long long)gridDim.x * blockDim.x) {
     const bool real = p < g.PTOT;
@@ -111,13 +115,16 @@ pack_x_gather_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4
     int filled = 0, c8 = 0;
     const float* xb = x + (long long)b * g.Cin * inS;
     for (int ci = 0; ci < g.Cin; ++ci) {
+#pragma unroll
       for (int kd = 0; kd < kD; ++kd) {
         const int id = od + kd - g.pD;
-        for (int kh = 0; kh < g.kH; ++kh) {
+#pragma unroll
+        for (int kh = 0; kh < kH; ++kh) {
           const int ih = oh + kh - g.pH;
           const bool row_ok = real && (unsigned)id < (unsigned)g.iD && (unsigned)ih < (unsigned)g.iH;
           const float* row = xb + (long long)ci * inS + (long long)id * iHW + (long long)ih * g.iW;
-          for (int kw = 0; kw < g.kW; ++kw) {
+#pragma unroll
+          for (int kw = 0; kw < kW; ++kw) {
             const int iw = ow + kw - g.pW;
             float v = 0.f;
             if (row_ok && (unsigned)iw < (unsigned)g.iW) v = __ldg(row + iw);
@@ -1770,7 +1777,9 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     gg.B = g0.B; gg.Cin = g0.Cin; gg.iD = g0.iD; gg.iH = g0.iH; gg.iW = g0.iW; gg.pD = g0.pD; gg.pH = g0.pH; gg.pW = g0.pW;
     gg.kH = g0.kH; gg.kW = g0.kW; gg.taps = g0.taps; gg.oD = g0.oD; gg.oH = g0.oH; gg.oW = g0.oW; gg.Kp = g.Cin;
     gg.CC = P.CC; gg.PA = P.PA; gg.PTOT = P.PTOT;
-    pack_x_gather_kernel<<<ew_grid(P.PA), 256, 0, st>>>(x, xp0, xp1, gg);
+    if (g0.kD == 3 && g0.kH == 3 && g0.kW == 3) pack_x_gather_kernel<3, 3, 3><<<ew_grid(P.PA), 256, 0, st>>>(x, xp0, xp1, gg);
+    else if (g0.kD == 1 && g0.kH == 3 && g0.kW == 3) pack_x_gather_kernel<1, 3, 3><<<ew_grid(P.PA), 256, 0, st>>>(x, xp0, xp1, gg);
+    else pack_x_gather_kernel<0, 0, 0><<<ew_grid(P.PA), 256, 0, st>>>(x, xp0, xp1, gg);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   } else if (do_pack) {
     pack_x_kernel<<<ew_grid((long long)P.CC * P.PA), 256, 0, st>>>(x, xp0, xp1, pg);
