@@ -1533,6 +1533,7 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
         if (cn > g.Cout || neff > 256 || gst * neff > 512 || cn % 16) continue;
         const int n_cout = (int)cdiv(g.Cout, cn);
         for (int blk = 1024; blk >= 64; blk >>= 1) {
+          if (gram && q.PTOT % blk) continue;          // must tile the host plan's packed positions exactly
           const int seglen = round_up_i(blk + rhalo, 8);
           const uint32_t xb = (uint32_t)nrep * q.d_HL * cm_chunks * seglen * 16;
           const uint32_t rb = (uint32_t)q.d_HL * (cn / 8) * blk * 16;
@@ -1585,8 +1586,8 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   q.d_tmem = pow2_cols((q.d_by_kh ? 1 : g.kH) * (int)cdiv(g.kW, q.nrep) * q.CN * (q.stackN ? 2 : 1));
 
   // packed position space: multiples of both tile sizes
-  // multiple of every stage size (<= 1024 positions), also of a second plan's over the same positions (HPCA Gram)
-  const int big = 1024;
+  // (a Gram plan runs over another plan's PR positions: its stage size divides them, see the search above)
+  const int big = gram ? q.BLK : (q.TILE_M > q.BLK ? q.TILE_M : q.BLK);
   q.PR = (q.PTOT + big - 1) / big * big;
   q.PA = (q.PR + q.maxshift + 16 + 7) / 8 * 8;
   q.f_ntiles = (int)(q.PR / q.TILE_M);

@@ -293,8 +293,17 @@ class _HebbianConvNd(nn.Module):
             raise NotImplementedError("Learning mode {} unavailable for {} layer".format(self.mode, self.__class__.__name__))
         native = self.MODE_SWTA_T if self._transposed else self.MODE_SWTA
         if self.mode == self.MODE_HPCA and self.patchwise:
-            return                      # HPCA (transposed layers: the conv rule with x and y exchanged,
-                                        # hebb.py:243-246): fp32 CUDA-core kernels (HEBB_F_RULE_HPCA)
+            return                      # HPCA: tcgen05 kernels for plain convs; transposed layers (the conv rule
+                                        # with x and y exchanged, hebb.py:243-246) on the fp32 CUDA-core kernels
+        if self.mode == self.MODE_CONTRASTIVE:
+            # Built for what the reference itself can execute: 2-D plain conv layers without uniformity weighting
+            # (its 3-D twin calls unfold3d() with a zero stride, hebb3d.py:170, and the uniformity branch adds the
+            # [Cout] bias to a 1-channel map, hebb.py:75,160 -- both raise RuntimeError in the reference).
+            if self._nd != 2 or self._transposed or self.uniformity:
+                raise NotImplementedError(
+                    "Learning mode contrastive is available for HebbianConv2d with uniformity=False (the only "
+                    "configuration the reference implementation executes without raising)")
+            return
         if self.mode != native or not self.patchwise:
             raise NotImplementedError(
                 "Learning mode {} (patchwise={}) of {} is not built into libhebb_sm100 yet; the sm_100 library "
@@ -309,11 +318,38 @@ class _HebbianConvNd(nn.Module):
         if self.alpha == 1:
             w = w.detach()       # (1 - alpha) * grad == 0 in local_update(): no need to back-prop into W
         b = self.bias
+        contrastive = update and self.mode == self.MODE_CONTRASTIVE
+        if contrastive:
+            update = False               # the rule is a loss on the output, not a fused plasticity kernel
         if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
             y = _HebbFn.apply(x, w, b, self, update)
         else:
             y = self._launch(x, w, b, update)
+        if contrastive:
+            self._contrastive_update(x)
         return self.act(y)
+
+    def _contrastive_update(self, x):
+        """hebb.py:143-172: delta_w += dL/dW of  L = sum [ -(S*y) + contrast * (S[perm]*y) ],  y = the layer
+        output normalised over channels, S = its 3x3 box sum, perm = torch.randperm(batch).  The forward and the
+        weight gradient run on the sm_100 kernels (through _HebbFn); the pixel-wise loss is a handful of
+        element-wise torch ops.  As in the reference, L.backward() also deposits dL/dbias in bias.grad."""
+        with torch.enable_grad():
+            w, b = self.weight, self.bias
+            leaves = [t for t in (w, b) if t.requires_grad]
+            if w not in leaves:
+                raise RuntimeError('contrastive learning needs weight.requires_grad=True (it is a gradient of a loss)')
+            y = self.act(_HebbFn.apply(x.detach(), w, b, self, False))
+            nrm = (y ** 2).sum(dim=1, keepdim=True) ** 0.5
+            y = y / torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+            S = F.avg_pool2d(y, 3, stride=1, padding=1, count_include_pad=True) * 9.0
+            idx = torch.randperm(y.size(0), device=y.device)
+            L = (-(S * y) + self.contrast * S[idx] * y).sum()
+            grads = torch.autograd.grad(L, leaves)
+        with torch.no_grad():
+            self.delta_w += grads[0]
+            if len(leaves) > 1:
+                b.grad = grads[1] if b.grad is None else b.grad + grads[1]
 
     def compute_update(self, x, y):
         """Accumulate the plasticity update for an already padded x into delta_w (y is recomputed

@@ -191,6 +191,39 @@ def swta_t_delta(x, y, weight, k, stride):
 
 
 # --------------------------------------------------------------------------
+# §8f-4  contrastive rule                hebb/hebb.py:143-172, hebb/hebb3d.py:167-197
+# --------------------------------------------------------------------------
+def _box_sum(t):
+    """Sum over the 3^nd neighbourhood (zero beyond the border): unfold(.., 3, padding=1).sum(-1) of the reference."""
+    nd = t.dim() - 2
+    pool = F.avg_pool2d if nd == 2 else F.avg_pool3d
+    return pool(t, 3, stride=1, padding=1, count_include_pad=True) * float(3 ** nd)
+
+
+def _unit_channels(t):
+    nrm = t.pow(2).sum(dim=1, keepdim=True).sqrt()
+    return t / torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+
+
+def contrastive_delta(xp, weight, bias, stride, contrast=1., perm=None, w_nrm=True):
+    """delta_w (and dL/dbias) of the reference's contrastive rule for a plain conv layer on the padded input xp:
+    L = sum_pixels [ -(S*y) + contrast * (S[perm]*y) ],  y = channel-normalised layer output, S = 3^nd box sum of
+    y, perm = a permutation of the batch (the reference draws torch.randperm(B) at this point).
+    delta_w += dL/dW; dL/dbias lands in bias.grad as a side effect of the reference's L.backward().
+    (uniformity=True is not restated: that branch of the reference raises for Cout > 1 -- apply_weights() adds
+    the [Cout] bias to a 1-channel map, hebb.py:75,160.)"""
+    w = weight.detach().clone().requires_grad_(True)
+    b = bias.detach().clone().requires_grad_(True) if bias is not None else None
+    y = _unit_channels(conv_activation(xp.detach(), w, b, stride, w_nrm))
+    S = _box_sum(y)
+    if perm is None:
+        perm = torch.randperm(y.shape[0])
+    L = (-(S * y) + contrast * S[perm] * y).sum()
+    grads = torch.autograd.grad(L, [w] + ([b] if b is not None else []), allow_unused=True)
+    return grads[0], (grads[1] if b is not None else None)
+
+
+# --------------------------------------------------------------------------
 # a8  local_update()                     hebb/hebb.py:174-192, hebb/hebb3d.py:198-216
 # --------------------------------------------------------------------------
 def fold_delta_into_grad(grad: Optional[torch.Tensor], delta_w: torch.Tensor, alpha: float):

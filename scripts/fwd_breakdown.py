@@ -9,7 +9,8 @@ from hebb import _native
 LAYERS = [  # (cls, Cin, Cout, k, B, spatial)
     ('c3', 1, 64, 3, 4, (96, 96, 80)), ('c3', 64, 64, 3, 4, (96, 96, 80)), ('c3', 128, 64, 3, 4, (96, 96, 80)),
     ('c3', 128, 128, 3, 8, (48, 48, 40)), ('c3', 256, 256, 3, 8, (24, 24, 20)), ('t3', 128, 64, 2, 8, (48, 48, 40)),
-    ('t3', 256, 128, 2, 8, (24, 24, 20)), ('c3', 1024, 1024, 3, 8, (6, 6, 5)),
+    ('t3', 256, 128, 2, 8, (24, 24, 20)), ('c3', 1024, 1024, 3, 8, (6, 6, 5)), ('c3', 512, 512, 3, 8, (12, 12, 10)),
+    ('c3', 256, 512, 3, 8, (12, 12, 10)), ('c3', 1024, 512, 3, 8, (12, 12, 10)),
     ('c2', 16, 16, 3, 64, (256, 256)), ('c2', 32, 16, 3, 64, (256, 256)), ('c2', 64, 64, 3, 64, (64, 64)),
 ]
 flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')

@@ -185,6 +185,36 @@ def main():
         out[f'drift_{opt_name}/w100'] = layer.weight.detach().numpy()
         meta[f'drift_{opt_name}'] = dict(kind='drift', opt=opt_name, lr=1e-3, k=10., steps=100)
 
+    # contrastive rule (hebb.py:143-172, hebb3d.py:167-197): a loss on the layer output whose
+    # weight gradient becomes delta_w.  The rule draws torch.randperm(B) from the global generator: seed it and
+    # store the permutation.
+    for (name, nd, B, Cin, Cout, spatial, bias, uniformity, contrast) in [
+            # (uniformity=True cannot be pinned: the reference's own uniformity branch raises for Cout > 1 --
+            #  apply_weights() adds the [Cout] bias to a 1-channel map, hebb.py:75,160)
+            #  the 3-D layer cannot either: hebb3d.py:170 calls unfold3d() with a stride of 0 and raises)
+            ('ctr2d_3_8', 2, 4, 3, 8, (10, 12), False, False, 1.0), ('ctr2d_16_16', 2, 3, 16, 16, (12, 10), True, False, 0.5),
+            ('ctr2d_8_32', 2, 2, 8, 32, (9, 7), True, False, 2.0)]:
+        cls = ref.HebbianConv2d if nd == 2 else ref.HebbianConv3d
+        layer = cls(Cin, Cout, 3, stride=1, padding=1, bias=bias, w_nrm=True, mode='contrastive', k=1.,
+                    contrast=contrast, uniformity=uniformity, alpha=1.)
+        with torch.no_grad():
+            layer.weight.copy_(rnd(*layer.weight.shape, scale=0.3))
+            if bias:
+                layer.bias.copy_(rnd(Cout, scale=0.1))
+        layer.train()
+        x = rnd(B, Cin, *spatial)
+        torch.manual_seed(4242)
+        perm = torch.randperm(B)
+        torch.manual_seed(4242)
+        y = layer(x)
+        out[name + '/x'], out[name + '/w'], out[name + '/b'] = x.numpy(), layer.weight.detach().numpy(), layer.bias.detach().numpy()
+        out[name + '/y'], out[name + '/dw1'] = y.detach().numpy(), layer.delta_w.clone().numpy()
+        out[name + '/perm'] = perm.numpy()
+        if bias:
+            out[name + '/gb'] = layer.bias.grad.detach().numpy()
+        meta[name] = dict(kind='contrastive', nd=nd, B=B, Cin=Cin, Cout=Cout, kernel=3, stride=1, padding=1,
+                          spatial=list(spatial), bias=bias, uniformity=uniformity, contrast=contrast)
+
     np.savez_compressed(os.path.join(HERE, 'hebb_golden.npz'), **out)
 
     # ---- makehebbian structure on the reference test's toy net (tests/test_makehebbian.py:5-39)

@@ -494,6 +494,37 @@ def test_hpca_tensor_core_vs_oracle(case, prec):
     assert relerr(layer.delta_w, dw_ref) < TOL_DW[prec]
 
 
+# ---- contrastive rule (2-D, the configuration the reference can execute) ----
+@pytest.mark.parametrize('prec', ['bf16x3', 'fp32'])
+@pytest.mark.parametrize('name', [n for n, m in META.items() if m['kind'] == 'contrastive'])
+def test_contrastive_vs_reference_golden(golden, name, prec, monkeypatch):
+    m = META[name]
+    layer = hebb.HebbianConv2d(m['Cin'], m['Cout'], 3, stride=1, padding=1, bias=m['bias'], w_nrm=True, mode='contrastive',
+                               k=1., contrast=m['contrast'], uniformity=False, alpha=1.)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(golden[name + '/w']))
+        layer.bias.copy_(torch.from_numpy(golden[name + '/b']))
+    layer.prec = prec
+    layer = layer.to(DEV).train()
+    perm = torch.from_numpy(golden[name + '/perm'])
+    monkeypatch.setattr(torch, 'randperm', lambda n, **kw: perm.to(kw.get('device', 'cpu')))   # the reference's draw
+    y = layer(torch.from_numpy(golden[name + '/x']).to(DEV))
+    record('contrastive_vs_reference_golden', f'{name}/{prec}', y=relerr(y, golden[name + '/y']),
+           dw=relerr(layer.delta_w, golden[name + '/dw1']))
+    assert relerr(y, golden[name + '/y']) < TOL_Y[prec]
+    assert relerr(layer.delta_w, golden[name + '/dw1']) < 1e-4
+    if m['bias']:
+        assert relerr(layer.bias.grad, golden[name + '/gb']) < 1e-4
+
+
+def test_contrastive_raises_where_the_reference_raises():
+    x = torch.randn(2, 4, 6, 6, 6, device=DEV)
+    with pytest.raises(NotImplementedError):
+        hebb.HebbianConv3d(4, 16, 3, padding=1, mode='contrastive', alpha=1.).to(DEV).train()(x)
+    with pytest.raises(NotImplementedError):
+        hebb.HebbianConv2d(4, 16, 3, padding=1, mode='contrastive', uniformity=True, alpha=1.).to(DEV).train()(x[:, :, 0])
+
+
 def test_reference_hpca_smoke_test_shape():
     """tests/test_makehebbian.py::test_makehebbian3d of the reference, on CUDA at a reduced width."""
     net = workloads.UNet3D(1, 2, init_features=8)

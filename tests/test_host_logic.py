@@ -46,6 +46,33 @@ def test_geometry_queries_need_no_gpu():
         _native.out_shape(bad)
 
 
+def _desc3(B, Cin, Cout, sp, k=3, transposed=False):
+    nd = len(sp)
+    return _native.make_desc(nd, B, Cin, Cout, sp, (k,) * nd, ((k if transposed else 1),) * nd,
+                             ((0 if transposed else k // 2),) * nd, ((0 if transposed else k // 2),) * nd, transposed)
+
+
+def test_planner_keeps_single_wave_and_tiles_every_c4_layer():
+    """Host-side planner (no GPU needed).  147 position tiles of the 12x12x10 layers must stay ONE wave on
+    148 SMs (a padded position count once pushed them to 152 = two waves = 2x the time), and every layer
+    of the two benchmark networks must get a tensor-core plan."""
+    for cin, cout in ((256, 512), (512, 512), (1024, 512)):
+        p = _native.plan(_desc3(8, cin, cout, (12, 12, 10)), _native.PREC_BF16X3)
+        assert p is not None and p['f_tiles'] == 147 and p['f_tiles'] * p['n_ct'] <= 148
+    for cin, cout, sp in ((1, 64, (96, 96, 80)), (64, 64, (96, 96, 80)), (128, 64, (96, 96, 80)), (128, 128, (48, 48, 40)),
+                          (256, 256, (24, 24, 20)), (512, 1024, (6, 6, 5)), (1024, 1024, (6, 6, 5))):
+        for prec in (_native.PREC_BF16X3, _native.PREC_BF16):
+            p = _native.plan(_desc3(8, cin, cout, sp), prec)
+            assert p is not None, (cin, cout, sp)
+            assert p['f_smem'] <= 227 * 1024 and p['d_smem'] <= 227 * 1024 and p['f_tmem'] <= 512 and p['d_tmem'] <= 512
+            # the update kernel is launched as one wave
+            assert p['ngrp'] * p['n_cin'] * p['n_cout'] * p['PS'] <= 148 or p['PS'] == 1
+    for cin, cout, sp in ((3, 16, (256, 256)), (16, 16, (256, 256)), (32, 16, (256, 256)), (256, 128, (16, 16))):
+        assert _native.plan(_desc3(64, cin, cout, sp), _native.PREC_BF16X3) is not None
+    for cin, cout, sp in ((1024, 512, (6, 6, 5)), (256, 128, (24, 24, 20)), (128, 64, (48, 48, 40))):
+        assert _native.plan(_desc3(8, cin, cout, sp, k=2, transposed=True), _native.PREC_BF16X3) is not None
+
+
 def test_no_cpu_fallback():
     layer = hebb.HebbianConv2d(3, 8, 3, padding=1, alpha=1.)
     with pytest.raises(RuntimeError, match='no CPU fallback'):

@@ -157,3 +157,17 @@ def test_identities():
     hebb = torch.nn.grad.conv2d_weight(xp, w.shape, rr)
     dec = r.sum(1).reshape(-1, 1, 1, 1) * w
     assert relerr(hebb - dec, full) < 1e-12
+
+
+@pytest.mark.parametrize('name', [n for n, m in META.items() if m['kind'] == 'contrastive'])
+def test_contrastive_delta(golden, name):
+    """hebb.py:143-172 — the permutation the reference drew is part of the fixture."""
+    m = META[name]
+    x, w, b = (torch.from_numpy(golden[name + k]) for k in ('/x', '/w', '/b'))
+    xp = O.zero_halo(x, m['padding'], m['nd'])
+    y = O.conv_activation(xp, w, b, (1,) * m['nd'])
+    assert relerr(y, golden[name + '/y']) < 2e-6
+    gw, gb = O.contrastive_delta(xp, w, b, (1,) * m['nd'], m['contrast'], perm=torch.from_numpy(golden[name + '/perm']))
+    assert relerr(gw, golden[name + '/dw1']) < 5e-6
+    if m['bias']:
+        assert relerr(gb, golden[name + '/gb']) < 5e-6
