@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c4', 'c5', 'c6'])
+    ap.add_argument('--head-wgrad', action='store_true', help='weight gradients of the back-prop head through hebb_conv_wgrad (default: cuDNN)')
     ap.add_argument('--aten-backward', action='store_true', help='c6: differentiate with stock ATen ops instead of the native dgrad/wgrad kernels')
     ap.add_argument('--prec', default=os.environ.get('HEBB_PREC', 'bf16x3'), choices=['fp32', 'bf16x3', 'bf16'])
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (0 = the workload default)')
@@ -77,7 +78,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------
-def build_model(workload, impl_ours, device, fuse=False):
+def build_model(workload, impl_ours, device, fuse=False, head_wgrad=False):
     """Returns (model, make_batch(batch, seed, device), criterion)."""
     if workload == 'c1':
         if impl_ours:
@@ -115,7 +116,7 @@ def build_model(workload, impl_ours, device, fuse=False):
     workloads.init_weights_like_reference(net)            # init_weights_unet(model,'kaiming') after surgery
     if impl_ours and fuse:
         from hebb.fused import fuse_norm_act
-        fuse_norm_act(net)                                # BatchNorm(train)+act and 2x bilinear up-sampling on our kernels
+        fuse_norm_act(net, head_wgrad=head_wgrad)         # BatchNorm(train)+act, 2x up-sampling / max pooling, head weight gradients on our kernels
     if workload == 'c5':
         return net.to(device).eval(), batch, None
     return net.to(device).train(), batch, workloads.dice_loss
@@ -293,7 +294,7 @@ def run_ours(args):
         cpu = time_cpu_port(args.workload, cpu_b, 2 if args.workload != 'c4' else 1, 1 if args.workload != 'c4' else 0)
 
     torch.manual_seed(1234)
-    model, make_batch, crit = build_model(args.workload, True, dev, fuse=not args.no_fuse)
+    model, make_batch, crit = build_model(args.workload, True, dev, fuse=not args.no_fuse, head_wgrad=args.head_wgrad)
     if args.cudnn_benchmark:
         torch.backends.cudnn.benchmark = True
     if (not args.head_nchw) and hasattr(model, 'out_conv'):
@@ -441,6 +442,7 @@ def run_ours(args):
                        'hebb_params': HEBB_PARAMS if args.workload != 'c1' else {'mode': 'swta', 'k': 3.0, 'alpha': 1.0},
                        'optimizer': f'adam lr={lr}', 'precision_mode': args.prec,
                        'fused_norm_act_upsample': (not args.no_fuse) and args.workload != 'c1',
+                       'head_weight_gradient': 'hebb_conv_wgrad (bf16x3)' if ((not args.no_fuse) and args.head_wgrad and args.workload != 'c1') else 'cuDNN',
                        'backward': 'stock ATen' if args.aten_backward else 'native dgrad/wgrad on the tcgen05 kernels where the planner takes the layer',
                        'backprop_head_memory_format': 'nchw' if (args.head_nchw or args.workload != 'c2') else 'channels_last', 'l2': 'flushed between timed steps (256 MB fill)',
                        'parallelism': f'dp{world} (batch shards, one all-reduce of delta_w per step)'},

@@ -161,18 +161,21 @@ int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const
   return simt_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, st);
 }
 
-int hebb_conv_wgrad(const HebbDesc* d, const float* x, const float* grad_y, float* grad_w, void* ws, size_t ws_bytes,
-                    int prec, void* stream) {
+int hebb_conv_wgrad(const HebbDesc* d, const float* x, const float* grad_y, float* grad_w, int gy_channels,
+                    int channels_last, void* ws, size_t ws_bytes, int prec, void* stream) {
   HEBB_TRY(device_ok());
   Geo g;
   HEBB_TRY(resolve_geo(d, &g));
   if (g.transposed) return HEBB_ESHAPE;
   if (!x || !grad_y || !grad_w) return HEBB_EARG;
   if (prec != HEBB_PREC_BF16X3 && prec != HEBB_PREC_BF16) return HEBB_EARG;
+  if (gy_channels < 0 || gy_channels > g.Cout) return HEBB_EARG;
   if (!aligned16(ws)) return HEBB_EALIGN;
   if (!use_tc(g, prec)) return HEBB_ESHAPE;          // shapes outside the tcgen05 planner: caller's choice what to do
+  if (channels_last && g.Cin <= 4 && g.taps > 1) return HEBB_ESHAPE;   // the patch-gathering pack reads NCHW only
+  const int aux = (gy_channels & 0xFFFF) | ((channels_last ? 1 : 0) << 16);
   return tc_conv_step(g, x, grad_w, nullptr, 1.f, const_cast<float*>(grad_y), nullptr, grad_w, ws, ws_bytes,
-                      HEBB_F_WGRAD_INTERNAL, prec, (cudaStream_t)stream);
+                      HEBB_F_WGRAD_INTERNAL, prec, (cudaStream_t)stream, aux);
 }
 
 int hebb_convT_swta_step(const HebbDesc* d, const float* x, const float* W, const float* bias, float kinv,

@@ -44,13 +44,12 @@ struct PackGeo {
   int B, Cin, iD, iH, iW, pD, pH, pW, HP, WP, plane, Qimg, CC;
   long long PA;   // positions per chunk plane (incl. zero slack)
   long long PTOT; // B*Qimg
+  long long sB, sC, sD, sH, sW;   // element strides of x (NCHW: sC = inS, sW = 1; channels_last: sC = 1, sW = C)
 };
 
 __global__ void __launch_bounds__(256)
 pack_x_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __restrict__ xlo, const __grid_constant__ PackGeo g) {
   const long long total = (long long)g.CC * g.PA;
-  const long long iHW = (long long)g.iH * g.iW;
-  const long long inS = (long long)g.iD * iHW;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(idx / g.PA);
@@ -64,12 +63,20 @@ pack_x_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __res
       const int w = q - hh * g.WP;
       const int id = d - g.pD, ih = hh - g.pH, iw = w - g.pW;
       if ((unsigned)id < (unsigned)g.iD && (unsigned)ih < (unsigned)g.iH && (unsigned)iw < (unsigned)g.iW) {
-        const float* src = x + ((long long)b * g.Cin + c8 * 8) * inS + (long long)id * iHW + (long long)ih * g.iW + iw;
+        const float* src = x + (long long)b * g.sB + (long long)(c8 * 8) * g.sC + (long long)id * g.sD + (long long)ih * g.sH +
+                           (long long)iw * g.sW;
         __nv_bfloat16 vh[8], vl[8];
+        if (g.sC == 1 && c8 * 8 + 8 <= g.Cin && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {   // channels_last: 2 x 16 B
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          const float v8[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float v = (c8 * 8 + i < g.Cin) ? __ldg(src + (long long)i * inS) : 0.f;
-          split_bf16(v, vh[i], vl[i]);
+          for (int i = 0; i < 8; ++i) split_bf16(v8[i], vh[i], vl[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float v = (c8 * 8 + i < g.Cin) ? __ldg(src + (long long)i * g.sC) : 0.f;
+            split_bf16(v, vh[i], vl[i]);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) { h[i] = pack_bf16x2(vh[2 * i], vh[2 * i + 1]); l[i] = pack_bf16x2(vl[2 * i], vl[2 * i + 1]); }
@@ -159,14 +166,14 @@ pack_x_gather_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4
 // Rp[hl][c8][p][8] over the padded position index space: 0 at positions that are not output pixels and in
 // channels >= C (the packed channel count is a multiple of 16).
 struct PackRGeo {
-  int B, C, C8, oD, oH, oW, WP, plane, Qimg;
+  int B, C, C8, oD, oH, oW, WP, plane, Qimg;     // C: channels actually present in gy (the rest of C8*8 is zero)
   long long outS, PR, PTOT;
+  long long sB, sC, sD, sH, sW;                  // element strides of gy
 };
 
 __global__ void __launch_bounds__(256)
 pack_r_kernel(const float* __restrict__ gy, uint4* __restrict__ rhi, uint4* __restrict__ rlo, const __grid_constant__ PackRGeo g) {
   const long long total = (long long)g.C8 * g.PR;
-  const int oHW = g.oH * g.oW;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(idx / g.PR);
@@ -179,12 +186,20 @@ pack_r_kernel(const float* __restrict__ gy, uint4* __restrict__ rhi, uint4* __re
       const int oh = q / g.WP;
       const int ow = q - oh * g.WP;
       if (od < g.oD && oh < g.oH && ow < g.oW) {
-        const float* src = gy + ((long long)b * g.C + c8 * 8) * g.outS + (long long)od * oHW + (long long)oh * g.oW + ow;
+        const float* src = gy + (long long)b * g.sB + (long long)(c8 * 8) * g.sC + (long long)od * g.sD + (long long)oh * g.sH +
+                           (long long)ow * g.sW;
         __nv_bfloat16 vh[8], vl[8];
+        if (g.sC == 1 && c8 * 8 + 8 <= g.C && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          const float v8[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float v = (c8 * 8 + i < g.C) ? __ldg(src + (long long)i * g.outS) : 0.f;
-          split_bf16(v, vh[i], vl[i]);
+          for (int i = 0; i < 8; ++i) split_bf16(v8[i], vh[i], vl[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float v = (c8 * 8 + i < g.C) ? __ldg(src + (long long)i * g.sC) : 0.f;
+            split_bf16(v, vh[i], vl[i]);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) { h[i] = pack_bf16x2(vh[2 * i], vh[2 * i + 1]); l[i] = pack_bf16x2(vl[2 * i], vl[2 * i + 1]); }
@@ -1730,7 +1745,7 @@ static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4*
 
 int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bias, float kinv, float* y,
                  int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
-                 cudaStream_t st) {
+                 cudaStream_t st, int aux) {
   Plan P;
   Geo g;
   const int trq = tr_quantum(g0);
@@ -1772,6 +1787,9 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   PackGeo pg;
   pg.B = g.B; pg.Cin = g.Cin; pg.iD = g.iD; pg.iH = g.iH; pg.iW = g.iW; pg.pD = g.pD; pg.pH = g.pH; pg.pW = g.pW;
   pg.HP = P.HP; pg.WP = P.WP; pg.plane = P.plane; pg.Qimg = P.Qimg; pg.CC = P.CC; pg.PA = P.PA; pg.PTOT = P.PTOT;
+  const bool nhwc = wgrad && ((aux >> 16) & 1);         // hebb_conv_wgrad on channels_last tensors
+  if (nhwc) { pg.sC = 1; pg.sW = g.Cin; pg.sH = (long long)g.iW * g.Cin; pg.sD = (long long)g.iH * g.iW * g.Cin; pg.sB = g.inS * g.Cin; }
+  else { pg.sW = 1; pg.sH = g.iW; pg.sD = (long long)g.iH * g.iW; pg.sC = g.inS; pg.sB = g.inS * g.Cin; }
   const bool gathered = !tr && g.taps != g0.taps;      // few-input-channel layer re-stated as a 1x1 layer
   if (do_pack && gathered) {
     GatherGeo gg;
@@ -1788,7 +1806,10 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   }
   if (wgrad) {
     PackRGeo rg;
-    rg.B = g.B; rg.C = g.Cout; rg.C8 = P.C8; rg.oD = g.oD; rg.oH = g.oH; rg.oW = g.oW; rg.WP = P.WP; rg.plane = P.plane;
+    const int gyC = (aux & 0xFFFF) ? (aux & 0xFFFF) : g.Cout;      // channels really present in dL/dy
+    rg.B = g.B; rg.C = gyC; rg.C8 = P.C8;
+    if (nhwc) { rg.sC = 1; rg.sW = gyC; rg.sH = (long long)g.oW * gyC; rg.sD = (long long)g.oH * g.oW * gyC; rg.sB = g.outS * gyC; }
+    else { rg.sW = 1; rg.sH = g.oW; rg.sD = (long long)g.oH * g.oW; rg.sC = g.outS; rg.sB = g.outS * gyC; } rg.oD = g.oD; rg.oH = g.oH; rg.oW = g.oW; rg.WP = P.WP; rg.plane = P.plane;
     rg.Qimg = P.Qimg; rg.outS = g.outS; rg.PR = P.PR; rg.PTOT = P.PTOT;
     pack_r_kernel<<<ew_grid((long long)P.C8 * P.PR), 256, 0, st>>>(y, rp0, P.d_HL == 2 ? rp1 : nullptr, rg);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
@@ -1868,6 +1889,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
 
   if (hpca) {
     PackRGeo rg;
+    rg.sW = 1; rg.sH = g.oW; rg.sD = (long long)g.oH * g.oW; rg.sC = g.outS; rg.sB = g.outS * g.Cout;
     rg.B = g.B; rg.C = g.Cout; rg.C8 = P.C8; rg.oD = g.oD; rg.oH = g.oH; rg.oW = g.oW; rg.WP = P.WP; rg.plane = P.plane;
     rg.Qimg = P.Qimg; rg.outS = g.outS; rg.PR = P.PR; rg.PTOT = P.PTOT;
     pack_r_kernel<<<ew_grid((long long)P.C8 * P.PR), 256, 0, st>>>(y, rp0, P.d_HL == 2 ? rp1 : nullptr, rg);

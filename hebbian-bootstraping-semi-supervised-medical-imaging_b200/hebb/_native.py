@@ -68,7 +68,7 @@ def load():
         step = [ctypes.POINTER(HebbDesc), vp, vp, vp, f32, vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_uint, i32, vp]
         lib.hebb_conv_swta_step.argtypes = step
         lib.hebb_convT_swta_step.argtypes = step
-        lib.hebb_conv_wgrad.argtypes = [ctypes.POINTER(HebbDesc), vp, vp, vp, vp, ctypes.c_size_t, i32, vp]
+        lib.hebb_conv_wgrad.argtypes = [ctypes.POINTER(HebbDesc), vp, vp, vp, i32, i32, vp, ctypes.c_size_t, i32, vp]
         lib.hebb_local_update_multi.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
                                                 ctypes.POINTER(f32), ctypes.POINTER(ctypes.c_int32), vp]
         lib.hebb_debug_umma_probe.argtypes = [vp, i32, vp, i32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
@@ -196,17 +196,21 @@ def conv_step(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w, flags
     check(st, 'conv_swta_step')
 
 
-def conv_wgrad(desc: HebbDesc, x, grad_y, prec: int):
+def conv_wgrad(desc: HebbDesc, x, grad_y, prec: int, gy_channels: int = 0, channels_last: bool = False):
     """grad_w[Cout][Cin][taps] of a stride-1 convolution on the tcgen05 contraction kernel (hebb_conv_wgrad).
-    Returns None when the layer is outside the tensor-core planner (the caller then uses ATen)."""
+    x / grad_y: dense NCHW (default) or dense channels_last storage.  Returns None when the layer is outside
+    the tensor-core planner (the caller then uses ATen)."""
     if desc.transposed or prec == PREC_FP32 or not uses_tensor_cores(desc, prec):
         return None
-    _require_cuda(x, 'x'); _require_cuda(grad_y, 'grad_y')
     taps = desc.k[0] * desc.k[1] * desc.k[2]
+    if channels_last and desc.Cin <= 4 and taps > 1:
+        return None
+    _require_cuda(x, 'x'); _require_cuda(grad_y, 'grad_y')
     gw = torch.zeros((desc.Cout, desc.Cin, taps), dtype=torch.float32, device=x.device)
     ws = workspace(x.device, workspace_bytes(desc, prec))
-    check(load().hebb_conv_wgrad(ctypes.byref(desc), x.data_ptr(), grad_y.data_ptr(), gw.data_ptr(), ws.data_ptr(),
-                                 ws.numel(), int(prec), _stream_ptr(x.device)), 'conv_wgrad')
+    check(load().hebb_conv_wgrad(ctypes.byref(desc), x.data_ptr(), grad_y.data_ptr(), gw.data_ptr(), int(gy_channels),
+                                 1 if channels_last else 0, ws.data_ptr(), ws.numel(), int(prec),
+                                 _stream_ptr(x.device)), 'conv_wgrad')
     return gw
 
 

@@ -5,7 +5,9 @@ every `HebbianConv -> BatchNorm{2,3}d -> ReLU/LeakyReLU` run inside an `nn.Seque
 BatchNorm(train) + activation pair runs as `hebb_bn_act_train` (one statistics pass, one
 normalise+activate pass), and every `nn.Upsample(scale_factor=2, bilinear, align_corners=True)` so it
 runs as `hebb_upsample2x_bilinear`, and every 2x `nn.MaxPool{2,3}d` (kernel = stride = 2, no padding) so it runs
-as `hebb_maxpool2x`.  Numerics follow torch (biased variance for normalisation, unbiased
+as `hebb_maxpool2x`; the stock convolutions a Hebbian network keeps for back-prop (makehebbian's `exclude` list)
+can get their weight gradient from `hebb_conv_wgrad` (`head_wgrad=True`; off by default: on the C2 head it is
+fp32-equivalent instead of TF32 but no faster than cuDNN once the packing passes are counted).  Numerics follow torch (biased variance for normalisation, unbiased
 for the running estimate, momentum update, num_batches_tracked).  Anything the kernels do not cover —
 eval mode, inputs or affine parameters that require grad, CPU tensors, cumulative-average momentum —
 takes the stock torch path of the parent class, so the pass is always safe to apply.
@@ -92,6 +94,87 @@ def _pool_is_2x(m, n):
             and not m.ceil_mode and not m.return_indices)
 
 
+class _ConvWgradFn(torch.autograd.Function):
+    """A stock convolution whose WEIGHT gradient runs on the Hebbian contraction kernel (hebb_conv_wgrad): the
+    back-prop layers a Hebbian network keeps (the `exclude` list of makehebbian: the segmentation head) have the
+    tall-skinny weight-gradient shape -- a few dozen filters reduced over millions of pixels -- that the update
+    kernel is built for and cuDNN serves poorly.  Forward and dL/dx stay with cuDNN."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod):
+        ctx.mod = mod
+        ctx.save_for_backward(x, weight)
+        return mod._conv_forward(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        mod = ctx.mod
+        need = ctx.needs_input_grad
+        nd = x.dim() - 2
+        gx = gw = gb = None
+        if need[1]:
+            gw = mod._native_wgrad(x, gy)
+        mask = (need[0], need[1] and gw is None, False)
+        if mask[0] or mask[1]:
+            r = torch.ops.aten.convolution_backward(gy, x, weight, None, list(mod.stride), list(mod.padding), list(mod.dilation),
+                                                    False, [0] * nd, mod.groups, list(mask))
+            gx = r[0] if mask[0] else None
+            gw = r[1] if mask[1] else gw
+        if need[2]:
+            gb = gy.sum(dim=(0, *range(2, nd + 2)))
+        return gx, gw, gb, None
+
+
+class _FastWgradMixin:
+    def _native_wgrad(self, x, gy):
+        """dL/dW through hebb_conv_wgrad, or None (shape / layout / precision not covered -> ATen)."""
+        nd = x.dim() - 2
+        if not (x.is_cuda and x.dtype == torch.float32 and gy.dtype == torch.float32):
+            return None
+        if _native.get_default_precision() == _native.PREC_FP32:
+            return None
+        prec = _native.PREC_BF16X3             # fp32-equivalent split (cuDNN's own path here is TF32)
+        cl_fmt = torch.channels_last if nd == 2 else torch.channels_last_3d
+        # follow the layout dL/dy arrives in (cuDNN hands back channels_last for a channels_last layer); x is
+        # copied into that layout only if it differs (the first head layer gets a plain NCHW activation)
+        if gy.is_contiguous():
+            cl = False
+            x = x.contiguous()
+        elif gy.is_contiguous(memory_format=cl_fmt):
+            cl = True
+            x = x.contiguous(memory_format=cl_fmt)
+        else:
+            return None
+        cout = self.out_channels
+        cpad = (cout + 15) // 16 * 16          # the kernel works on multiples of 16 filters; the extra rows are zero
+        desc = _native.make_desc(nd, x.shape[0], self.in_channels, cpad, x.shape[2:], self.kernel_size, (1,) * nd,
+                                 self.padding, self.padding, False)
+        gw = _native.conv_wgrad(desc, x, gy, prec, gy_channels=cout, channels_last=cl)
+        if gw is None:
+            return None
+        gw = gw[:cout].reshape(self.weight.shape)
+        if self.weight.is_contiguous(memory_format=cl_fmt) and not self.weight.is_contiguous():
+            gw = gw.contiguous(memory_format=cl_fmt)
+        return gw
+
+    def forward(self, x):
+        ok = (self.padding_mode == 'zeros' and isinstance(self.padding, tuple) and self.groups == 1
+              and all(s == 1 for s in self.stride) and all(d == 1 for d in self.dilation)
+              and x.is_cuda and torch.is_grad_enabled() and self.weight.requires_grad)
+        if not ok:
+            return super().forward(x)
+        return _ConvWgradFn.apply(x, self.weight, self.bias, self)
+
+
+class FastWgradConv2d(_FastWgradMixin, nn.Conv2d):
+    pass
+
+
+class FastWgradConv3d(_FastWgradMixin, nn.Conv3d):
+    pass
+
+
 def _slope_of(m):
     if type(m) is nn.ReLU:
         return 0.0
@@ -100,8 +183,8 @@ def _slope_of(m):
     return None
 
 
-def fuse_norm_act(model: nn.Module) -> nn.Module:
-    n_bn = n_up = n_pool = 0
+def fuse_norm_act(model: nn.Module, head_wgrad: bool = False) -> nn.Module:
+    n_bn = n_up = n_pool = n_head = 0
     for mod in model.modules():
         if isinstance(mod, nn.Sequential):
             items = list(mod._modules.items())
@@ -123,5 +206,8 @@ def fuse_norm_act(model: nn.Module) -> nn.Module:
             elif type(m) is nn.MaxPool3d and _pool_is_2x(m, 3):
                 m.__class__ = FastMaxPool3d
                 n_pool += 1
-    model._hebb_fused = dict(bn_act=n_bn, upsample=n_up, maxpool=n_pool)
+            elif head_wgrad and type(m) in (nn.Conv2d, nn.Conv3d) and m.weight.requires_grad:
+                m.__class__ = FastWgradConv2d if type(m) is nn.Conv2d else FastWgradConv3d
+                n_head += 1
+    model._hebb_fused = dict(bn_act=n_bn, upsample=n_up, maxpool=n_pool, head_wgrad=n_head)
     return model

@@ -109,11 +109,14 @@ int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const
  *     grad_w[co][ci][tap] += sum_p grad_y[b][co][p] * xpad[b][ci][p + tap]
  * Replaces the weight-gradient half of torch's convolution backward that the reference reaches through
  * loss.backward() for layers with alpha < 1 (hebb/hebb.py:185-191, train_sup_2d.py:150-168).
- * x: [B][Cin][in...], grad_y: [B][Cout][out...], grad_w: [Cout][Cin][taps], all fp32 contiguous.
+ * x: [B][Cin][in...], grad_y: [B][gy_channels][out...], grad_w: [Cout][Cin][taps], all fp32.
+ * gy_channels: channels actually present in grad_y (0 = d->Cout); rows gy_channels..Cout-1 of grad_w receive 0 —
+ *   lets a layer with few output channels (a 2-class head) use a descriptor padded to a multiple of 16.
+ * channels_last: 0 = x and grad_y are contiguous NCHW / NCDHW, 1 = contiguous NHWC / NDHWC (torch channels_last).
  * prec: HEBB_PREC_BF16X3 (fp32-equivalent) or HEBB_PREC_BF16.  HEBB_ESHAPE for layers the tcgen05 planner
  * does not take (the caller then uses its own fallback; nothing is computed). */
-int hebb_conv_wgrad(const HebbDesc* d, const float* x, const float* grad_y, float* grad_w, void* ws,
-                    size_t ws_bytes, int prec, void* stream);
+int hebb_conv_wgrad(const HebbDesc* d, const float* x, const float* grad_y, float* grad_w, int gy_channels,
+                    int channels_last, void* ws, size_t ws_bytes, int prec, void* stream);
 
 /* a9: one HebbianConvTranspose{2,3}d.forward in swta_t/patchwise mode —
  * hebb/hebb.py:226-264, hebb/hebb3d.py:250-289.  W and delta_w are the CONTIGUOUS

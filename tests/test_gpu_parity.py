@@ -426,6 +426,41 @@ def test_maxpool2x_matches_torch(shape):
     assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want))
 
 
+@pytest.mark.parametrize('fmt', ['nchw', 'channels_last'])
+@pytest.mark.parametrize('case', [(2, 16, 64, (40, 36), 3, 1), (2, 64, 32, (24, 28), 3, 1), (3, 32, 2, (20, 20), 3, 1), (2, 32, 16, (12, 12), 1, 0)])
+def test_fast_wgrad_conv_matches_stock_conv(case, fmt):
+    """hebb.fused.FastWgradConv2d: forward and dL/dx are cuDNN's, dL/dW comes from hebb_conv_wgrad."""
+    import torch.nn as nn
+    from hebb.fused import FastWgradConv2d
+    B, Cin, Cout, sp, k, pad = case
+    torch.manual_seed(Cin + Cout)
+    ref = nn.Conv2d(Cin, Cout, k, padding=pad).to(DEV)
+    fast = nn.Conv2d(Cin, Cout, k, padding=pad).to(DEV)
+    fast.load_state_dict(ref.state_dict())
+    fast.__class__ = FastWgradConv2d
+    x = torch.randn(B, Cin, *sp, device=DEV)
+    t = torch.randn(B, Cout, *sp, device=DEV)
+    if fmt == 'channels_last':
+        ref, fast = ref.to(memory_format=torch.channels_last), fast.to(memory_format=torch.channels_last)
+        x, t = x.contiguous(memory_format=torch.channels_last), t.contiguous(memory_format=torch.channels_last)
+    was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # an fp32 yardstick for the gradient
+    try:
+        xr = x.clone().requires_grad_(True)
+        (ref(xr) * t).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = was
+    from hebb import _native as N
+    n0 = N.launch_count()
+    xf = x.clone().requires_grad_(True)
+    (fast(xf) * t).sum().backward()
+    assert N.launch_count() - n0 >= 3                # pack x, pack dL/dy, contraction, finalize
+    record('fast_wgrad_conv', f'{Cin}x{Cout}k{k}/{fmt}', gw=relerr(fast.weight.grad, ref.weight.grad))
+    assert relerr(fast.weight.grad, ref.weight.grad) < 1e-4
+    assert relerr(fast.bias.grad, ref.bias.grad) < 1e-5
+    assert relerr(xf.grad, xr.grad) < 2e-3           # cuDNN dgrad (TF32 by default) on both sides
+
+
 def test_fuse_pass_keeps_network_output_and_state():
     from hebb.fused import fuse_norm_act
     torch.manual_seed(0)
@@ -438,7 +473,7 @@ def test_fuse_pass_keeps_network_output_and_state():
     ref = copy.deepcopy(net).to(DEV).train()
     keys = list(net.state_dict().keys())
     fuse_norm_act(net)
-    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4}
+    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4, 'head_wgrad': 0}
     net = net.to(DEV).train()
     x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(5)).to(DEV)
     a, b = ref(x), net(x)
