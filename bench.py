@@ -367,14 +367,21 @@ def run_ours(args):
     s0.record()
     last = 0.0
     prefetch(0)
+    dbg = os.environ.get('HEBB_BENCH_E2E_DEBUG') == '1'
     for i in range(args.steps):
+        t0 = time.perf_counter()
         if i + 1 < args.steps:
             prefetch(i + 1)
         cur.wait_event(ready[i % 2])
         xb, mb = bufs[i % 2]
+        t1 = time.perf_counter()
         out, loss = stepper.step(xb, mb)
         freed[i % 2].record(cur)
+        t2 = time.perf_counter()
         last = float(loss.item()) if loss is not None else float(out.flatten()[0].item())
+        if dbg:
+            print(f'[e2e rank {rank}] step {i}: prefetch {1e3 * (t1 - t0):.2f} ms, launch {1e3 * (t2 - t1):.2f} ms, '
+                  f'sync {1e3 * (time.perf_counter() - t2):.2f} ms', file=sys.stderr, flush=True)
     s1.record()
     sync_all()
     t = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
