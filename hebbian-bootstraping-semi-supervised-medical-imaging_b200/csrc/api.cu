@@ -161,6 +161,24 @@ int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const
   return simt_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, st);
 }
 
+int hebb_conv_swta_step_stats(const HebbDesc* d, const float* x, const float* W, const float* bias, float kinv,
+                              float* y, int32_t* winner, float* delta_w, void* ws, size_t ws_bytes,
+                              unsigned flags, int prec, double* y_stats, int* y_stats_written, void* stream) {
+  if (y_stats_written) *y_stats_written = 0;
+  HEBB_TRY(device_ok());
+  Geo g;
+  HEBB_TRY(resolve_geo(d, &g));
+  flags &= 0xFFFFu;
+  if (!y_stats || g.transposed || !use_tc(g, prec) || (flags & HEBB_F_RULE_HPCA))      // nothing to fuse: plain step
+    return hebb_conv_swta_step(d, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, stream);
+  if (!x || !W || !y) return HEBB_EARG;
+  if ((flags & HEBB_F_UPDATE) && !delta_w) return HEBB_EARG;
+  if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
+  if (!aligned16(ws)) return HEBB_EALIGN;
+  return tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, (cudaStream_t)stream, 0,
+                      y_stats, y_stats_written);
+}
+
 int hebb_conv_wgrad(const HebbDesc* d, const float* x, const float* grad_y, float* grad_w, int gy_channels,
                     int channels_last, void* ws, size_t ws_bytes, int prec, void* stream) {
   HEBB_TRY(device_ok());

@@ -82,6 +82,6 @@ size_t tc_workspace_bytes(const Geo& g, int prec);
 int tc_describe_plan(const Geo& g, int prec, int* out, int n);
 int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y,
                  int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
-                 cudaStream_t st, int aux = 0);
+                 cudaStream_t st, int aux = 0, double* ystats = nullptr, int* ystats_written = nullptr);
 
 }  // namespace hebb

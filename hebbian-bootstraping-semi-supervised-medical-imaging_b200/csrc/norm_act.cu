@@ -203,6 +203,29 @@ int hebb_bn_act_train(const float* y, float* out, const float* gamma, const floa
   return HEBB_OK;
 }
 
+int hebb_bn_act_from_stats(const float* y, float* out, const double* y_stats, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, int64_t B, int64_t C, int64_t S, float eps,
+                           float momentum, float slope, void* ws, size_t ws_bytes, void* stream) {
+  HEBB_TRY(device_ok());
+  if (!y || !out || !ws || !y_stats) return HEBB_EARG;
+  if (B <= 0 || C <= 0 || S <= 0 || C > 65535) return HEBB_ESHAPE;
+  if (ws_bytes < (size_t)C * 2 * sizeof(float)) return HEBB_EWS;
+  if (reinterpret_cast<uintptr_t>(ws) & 15) return HEBB_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ss = static_cast<float*>(ws);
+  bn_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(y_stats, gamma, beta, ss, running_mean, running_var, (int)C,
+                                                             (double)(B * S), eps, momentum);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  const long long total = B * C * S;
+  long long gx = cdiv(total, 256 * 4 * 4);
+  const long long cap = (long long)num_sms() * 16;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  bn_act_apply_kernel<<<(unsigned)gx, 256, 0, st>>>(y, out, ss, (int)C, S, total, slope);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
 int hebb_upsample2x_bilinear(const float* in, float* out, int64_t N, int64_t H, int64_t W, void* stream) {
   HEBB_TRY(device_ok());
   if (!in || !out) return HEBB_EARG;

@@ -306,6 +306,7 @@ struct FwdParams {
   const uint4* wp;
   uint4* rp[2];
   float* y; int32_t* winner; const float* inv; const float* bias; float* rsum; int* err;
+  double* ystats;              // optional [Cout][2]: per-channel sum and sum of squares of y (BatchNorm statistics)
   int Cout, CC, NSLAB, taps, nseg, HL;
   int stackF;                  // bf16x3 forward: B = [w_hi | w_lo] stacked along N -> 2 MMAs instead of 3
   int CT, n_ct, fuse;          // output-channel tile handled by one CTA (<= 512 TMEM columns); fuse: softmax in the epilogue
@@ -415,11 +416,13 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
-  // misc region: [inv CT][bias CT][rs 8*CT] floats, then barriers, then tmem ptr
+  // misc region: [inv CT][bias CT][rs 8*CT][ysum CT][ysq CT] floats, then barriers, then tmem ptr
   float* s_inv = reinterpret_cast<float*>(smem + p.off_misc);
   float* s_bias = s_inv + p.CT;
   float* s_rs = s_bias + p.CT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rs + 8 * p.CT);
+  float* s_ys = s_rs + 8 * p.CT;             // per-CTA sum of y per channel (shared by the 8 epilogue warps)
+  float* s_yq = s_ys + p.CT;                 //         sum of y^2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_yq + p.CT);
   const int total_work = p.ntiles * p.n_ct;      // work item = (position tile, output-channel tile)
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t x_full = bar0, x_empty = x_full + 8 * p.XST;
@@ -427,7 +430,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
   const uint32_t t_full = w_empty + 8 * p.WST, t_empty = t_full + 8 * p.NACC;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * p.XST + 2 * p.WST + 2 * p.NACC);
 
-  for (int i = threadIdx.x; i < 8 * p.CT; i += blockDim.x) s_rs[i] = 0.f;
+  for (int i = threadIdx.x; i < 10 * p.CT; i += blockDim.x) s_rs[i] = 0.f;      // rs, ysum, ysq
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.XST; ++i) { mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 1); }
     for (int i = 0; i < p.WST; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
@@ -556,6 +559,14 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
     float racc[NV];                           // SP > 0: this thread's running sum of r per channel
 #pragma unroll
     for (int i = 0; i < NV; ++i) racc[i] = 0.f;
+    // BatchNorm statistics of y (p.ystats): rows of up to 32 channels keep per-thread running sums like racc;
+    // wider rows are folded per M-block by the butterfly (those layers are tensor-bound, the epilogue has slack)
+    constexpr bool YACC = SP > 0 && NV <= 32;
+    constexpr int NY = YACC ? NV : 1;
+    float ysacc[NY], yqacc[NY];
+#pragma unroll
+    for (int i = 0; i < NY; ++i) { ysacc[i] = 0.f; yqacc[i] = 0.f; }
+    const bool want_ys = p.ystats != nullptr;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
       const int acc = (p.NACC == 2) ? (it & 1) : 0;
       if (acc != eset) continue;            // the other set's buffer (NACC == 1: set 1 has nothing to do)
@@ -613,6 +624,21 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               f[ck * CH + i4 + 1] = fmaf(__uint_as_float(v[i4 + 1]), sc.y, bs.y);
               f[ck * CH + i4 + 2] = fmaf(__uint_as_float(v[i4 + 2]), sc.z, bs.z);
               f[ck * CH + i4 + 3] = fmaf(__uint_as_float(v[i4 + 3]), sc.w, bs.w);
+            }
+          }
+          if (want_ys) {
+            if constexpr (YACC) {
+#pragma unroll
+              for (int i = 0; i < NV; ++i) { const float t = valid ? f[i] : 0.f; ysacc[i] += t; yqacc[i] = fmaf(t, t, yqacc[i]); }
+            } else {
+#pragma unroll
+              for (int ck = 0; ck < SP; ++ck) {
+                float t1[CH], t2[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) { t1[i] = valid ? f[ck * CH + i] : 0.f; t2[i] = t1[i] * t1[i]; }
+                const float a1 = lane_col_sum<CH>(t1, lane), a2 = lane_col_sum<CH>(t2, lane);
+                if (lane < CH) { atomicAdd(s_ys + ck * CH + lane, a1); atomicAdd(s_yq + ck * CH + lane, a2); }
+              }
             }
           }
           const float k2 = p.kinv * 1.4426950408889634f;      // exp(k y) = 2^(k2 y)
@@ -751,12 +777,18 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               if (o.y > best8[(i + 1) & 7]) { best8[(i + 1) & 7] = o.y; bi8[(i + 1) & 7] = cc >> 3; }
             }
           } else {
+            float t1[CH], t2[CH];
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
               const float f = fmaf(__uint_as_float(v[i]), s_inv[c0 + i], s_bias[c0 + i]);
               if (valid) yb[(long long)(c0 + i) * outS] = f;
               mx = fmaxf(mx, f * p.kinv);
               if (f > best) { best = f; bi = c0 + i; }
+              t1[i] = valid ? f : 0.f; t2[i] = t1[i] * t1[i];
+            }
+            if (want_ys) {
+              const float a1 = lane_col_sum<CH>(t1, lane), a2 = lane_col_sum<CH>(t2, lane);
+              if (lane < CH) { atomicAdd(s_ys + c0 + lane, a1); atomicAdd(s_yq + c0 + lane, a2); }
             }
           }
         }
@@ -872,6 +904,23 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
     }
     if (p.fuse && p.write_r && cur_ct >= 0)
       for (int c = lane; c < p.CT; c += 32) atomicAdd(p.rsum + cur_ct * p.CT + c, my_rs[c]);
+    if (want_ys) {                          // host side guarantees n_ct == 1: columns are channels
+      if constexpr (YACC) {
+#pragma unroll
+        for (int ck = 0; ck < SP; ++ck) {
+          float t1[CH], t2[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) { t1[i] = ysacc[ck * CH + i]; t2[i] = yqacc[ck * CH + i]; }
+          const float a1 = lane_col_sum<CH>(t1, lane), a2 = lane_col_sum<CH>(t2, lane);
+          if (lane < CH) { atomicAdd(s_ys + ck * CH + lane, a1); atomicAdd(s_yq + ck * CH + lane, a2); }
+        }
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");        // the 8 epilogue warps
+      for (int c = (int)threadIdx.x - 64; c < p.CT; c += 256) {
+        atomicAdd(p.ystats + 2 * c, (double)s_ys[c]);
+        atomicAdd(p.ystats + 2 * c + 1, (double)s_yq[c]);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1480,7 +1529,7 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   q.stackF = (want_stackf && q.f_HL == 2 && q.CT <= 64 && !g.transposed) ? 1 : 0;
   const int fcw = (q.stackF ? 2 : 1) * q.CT;
   const uint32_t w_tap = (uint32_t)q.f_HL * 2 * q.CT * 16;     // one tap of one slab: [k-chunk][hi|lo][CT rows]
-  const uint32_t misc = (uint32_t)(10 * q.CT * 4 + 8 * 64 + 64);
+  const uint32_t misc = (uint32_t)(12 * q.CT * 4 + 8 * 64 + 64);
   // Weight stages hold a GROUP of taps moved by one bulk copy: every stage costs the producer and the MMA
   // warp a full mbarrier round trip (~600 cycles measured with per-tap stages, which starved the tensor
   // pipe), so prefer the largest group (a whole kd plane, else a kernel row, else one tap) that fits.
@@ -1745,7 +1794,8 @@ static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4*
 
 int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bias, float kinv, float* y,
                  int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
-                 cudaStream_t st, int aux) {
+                 cudaStream_t st, int aux, double* ystats, int* ystats_written) {
+  if (ystats_written) *ystats_written = 0;
   Plan P;
   Geo g;
   const int trq = tr_quantum(g0);
@@ -1831,6 +1881,12 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   FwdParams f;
   f.xp[0] = xp0; f.xp[1] = xp1; f.wp = wp; f.rp[0] = rp0; f.rp[1] = rp1;
   f.y = y; f.winner = winner; f.inv = ((flags & HEBB_F_WNRM) && !tr) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = err;
+  // BatchNorm statistics of y ride along when the layer is one channel tile of a plain convolution
+  f.ystats = (ystats && do_fwd && !tr && P.n_ct == 1) ? ystats : nullptr;
+  if (f.ystats) {
+    HEBB_CUDA_TRY(cudaMemsetAsync(ystats, 0, sizeof(double) * 2 * (size_t)g.Cout, st));
+    if (ystats_written) *ystats_written = 1;
+  }
   f.tr = tr ? (trq ? 2 : 1) : 0; f.trQ = trq; f.tD = g0.oD; f.tH = g0.oH; f.tW = g0.oW; f.CoutR = g0.Cout;
   f.Cout = g.Cout; f.CC = P.CC; f.NSLAB = P.NSLAB; f.taps = g.taps; f.nseg = P.f_nseg; f.HL = P.f_HL; f.RHL = P.d_HL;
   static const int fwd_dbg = [] { const char* e = getenv("HEBB_FWD_DBG"); return e ? atoi(e) : 0; }();

@@ -125,6 +125,8 @@ class _HebbianConvNd(nn.Module):
         self.record_winners = False   # when True the last forward's argmax map is kept in .winners
         self.winners = None
         self._desc_cache = {}
+        self._emit_y_stats = False     # set by hebb.fused.fuse_norm_act when a fused BatchNorm consumes the output
+        self._y_stats = None           # (y, [Cout, 2] float64 sums) of the last forward, if produced
 
     # ------------------------------------------------------------------ geometry
     def _pad_list(self):
@@ -207,7 +209,14 @@ class _HebbianConvNd(nn.Module):
                 tmp_dw = torch.zeros_like(w)
                 dw = tmp_dw
         b = bias.detach() if bias is not None else None
-        _native.conv_step(desc, x, w, b, float(self.k), y, win, dw, flags, _native.parse_prec(self.prec))
+        self._y_stats = None
+        if self._emit_y_stats and not self._transposed and pad:
+            # a fused BatchNorm follows (hebb.fused.fuse_norm_act): its statistics ride along in the forward epilogue
+            stats = _native.conv_step_stats(desc, x, w, b, float(self.k), y, win, dw, flags, _native.parse_prec(self.prec))
+            if stats is not None:
+                self._y_stats = (y, stats)
+        else:
+            _native.conv_step(desc, x, w, b, float(self.k), y, win, dw, flags, _native.parse_prec(self.prec))
         if tmp_dw is not None:
             self.delta_w += tmp_dw.transpose(0, 1) if self._transposed else tmp_dw
         self.winners = win

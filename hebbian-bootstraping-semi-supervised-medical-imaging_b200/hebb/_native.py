@@ -68,6 +68,8 @@ def load():
         step = [ctypes.POINTER(HebbDesc), vp, vp, vp, f32, vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_uint, i32, vp]
         lib.hebb_conv_swta_step.argtypes = step
         lib.hebb_convT_swta_step.argtypes = step
+        lib.hebb_conv_swta_step_stats.argtypes = step[:-1] + [vp, ctypes.POINTER(i32), vp]
+        lib.hebb_bn_act_from_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, vp, ctypes.c_size_t, vp]
         lib.hebb_conv_wgrad.argtypes = [ctypes.POINTER(HebbDesc), vp, vp, vp, i32, i32, vp, ctypes.c_size_t, i32, vp]
         lib.hebb_local_update_multi.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
                                                 ctypes.POINTER(f32), ctypes.POINTER(ctypes.c_int32), vp]
@@ -194,6 +196,36 @@ def conv_step(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w, flags
             delta_w.data_ptr() if delta_w is not None else None, ws.data_ptr(), ws.numel(),
             int(flags), int(prec), _stream_ptr(x.device))
     check(st, 'conv_swta_step')
+
+
+def conv_step_stats(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w, flags: int, prec: int):
+    """hebb_conv_swta_step_stats: the step plus the BatchNorm statistics of y.  Returns the [Cout, 2] float64
+    tensor (sum, sum of squares per channel) or None when the library did not produce them."""
+    lib = load()
+    _require_cuda(x, 'x'); _require_cuda(W, 'weight')
+    ws = workspace(x.device, workspace_bytes(desc, prec))
+    stats = torch.empty((desc.Cout, 2), dtype=torch.float64, device=x.device)
+    written = ctypes.c_int32(0)
+    st = lib.hebb_conv_swta_step_stats(ctypes.byref(desc), x.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                       float(kinv), y.data_ptr(), winner.data_ptr() if winner is not None else None,
+                                       delta_w.data_ptr() if delta_w is not None else None, ws.data_ptr(), ws.numel(),
+                                       int(flags), int(prec), stats.data_ptr(), ctypes.byref(written), _stream_ptr(x.device))
+    check(st, 'conv_swta_step_stats')
+    return stats if written.value else None
+
+
+def bn_act_from_stats(y, stats, gamma, beta, running_mean, running_var, eps, momentum, slope):
+    """BatchNorm(train) + activation of y from precomputed per-channel (sum, sum of squares) (hebb_bn_act_from_stats)."""
+    _require_cuda(y, 'input')
+    B, C = y.shape[0], y.shape[1]
+    S = y.numel() // (B * C)
+    out = torch.empty_like(y)
+    ws = workspace(y.device, C * 8 + 64)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    check(load().hebb_bn_act_from_stats(y.data_ptr(), out.data_ptr(), stats.data_ptr(), ptr(gamma), ptr(beta), ptr(running_mean),
+                                        ptr(running_var), B, C, S, float(eps), float(momentum), float(slope), ws.data_ptr(),
+                                        ws.numel(), _stream_ptr(y.device)), 'bn_act_from_stats')
+    return out
 
 
 def conv_wgrad(desc: HebbDesc, x, grad_y, prec: int, gy_channels: int = 0, channels_last: bool = False):

@@ -3,12 +3,13 @@
 `fuse_norm_act(model)` rewrites, in place and without touching parameter names or state_dict keys,
 every `HebbianConv -> BatchNorm{2,3}d -> ReLU/LeakyReLU` run inside an `nn.Sequential` so that the
 BatchNorm(train) + activation pair runs as `hebb_bn_act_train` (one statistics pass, one
-normalise+activate pass), and every `nn.Upsample(scale_factor=2, bilinear, align_corners=True)` so it
-runs as `hebb_upsample2x_bilinear`, and every 2x `nn.MaxPool{2,3}d` (kernel = stride = 2, no padding) so it runs
+normalise+activate pass) — or, with `fuse_stats=True`, as `hebb_bn_act_from_stats` on the per-channel sums
+the producing layer's forward epilogue hands back (`hebb_conv_swta_step_stats`: no statistics pass at all) —
+and every `nn.Upsample(scale_factor=2, bilinear, align_corners=True)` so it runs as `hebb_upsample2x_bilinear`, and every 2x `nn.MaxPool{2,3}d` (kernel = stride = 2, no padding) so it runs
 as `hebb_maxpool2x`; the stock convolutions a Hebbian network keeps for back-prop (makehebbian's `exclude` list)
 can get their weight gradient from `hebb_conv_wgrad` (`head_wgrad=True`; off by default: on the C2 head it is
-fp32-equivalent instead of TF32 but no faster than cuDNN once the packing passes are counted).  Numerics follow torch (biased variance for normalisation, unbiased
-for the running estimate, momentum update, num_batches_tracked).  Anything the kernels do not cover —
+fp32-equivalent instead of TF32 but no faster than cuDNN once the packing passes are counted).
+Numerics follow torch (biased variance for normalisation, unbiased for the running estimate, momentum update, num_batches_tracked).  Anything the kernels do not cover —
 eval mode, inputs or affine parameters that require grad, CPU tensors, cumulative-average momentum —
 takes the stock torch path of the parent class, so the pass is always safe to apply.
 """
@@ -38,6 +39,14 @@ class _FusedBNActMixin:
         self._check_input_dim(x)
         if self.num_batches_tracked is not None:
             self.num_batches_tracked.add_(1)
+        src = self.__dict__.get('_src_conv')
+        src = src[0] if src else None
+        held = getattr(src, '_y_stats', None) if src is not None else None
+        if held is not None and held[0] is x:
+            # the producing Hebbian layer already summed y and y^2 in its epilogue: skip the statistics pass
+            src._y_stats = None
+            return _native.bn_act_from_stats(x, held[1], self.weight, self.bias, self.running_mean, self.running_var,
+                                             self.eps, self.momentum, self._act_slope)
         return _native.bn_act_train(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
                                     self.momentum, self._act_slope)
 
@@ -183,7 +192,7 @@ def _slope_of(m):
     return None
 
 
-def fuse_norm_act(model: nn.Module, head_wgrad: bool = False) -> nn.Module:
+def fuse_norm_act(model: nn.Module, head_wgrad: bool = False, fuse_stats: bool = True) -> nn.Module:
     n_bn = n_up = n_pool = n_head = 0
     for mod in model.modules():
         if isinstance(mod, nn.Sequential):
@@ -193,6 +202,10 @@ def fuse_norm_act(model: nn.Module, head_wgrad: bool = False) -> nn.Module:
                     slope = _slope_of(items[i + 1][1]) if i + 1 < len(items) else None
                     m.__class__ = FusedBatchNormAct2d if type(m) is nn.BatchNorm2d else FusedBatchNormAct3d
                     m._act_slope = 1.0 if slope is None else slope
+                    conv = items[i - 1][1]
+                    if fuse_stats and type(getattr(conv, 'act', None)) is nn.Identity:
+                        conv._emit_y_stats = True                    # statistics come out of the conv's epilogue
+                        m.__dict__['_src_conv'] = (conv,)            # plain attribute, not a sub-module: no state_dict entry
                     if slope is not None:
                         mod._modules[items[i + 1][0]] = nn.Identity()     # activation now lives in the fused module
                     n_bn += 1

@@ -104,6 +104,16 @@ int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const
                         float kinv, float* y, int32_t* winner, float* delta_w,
                         void* ws, size_t ws_bytes, unsigned flags, int prec, void* stream);
 
+/* hebb_conv_swta_step that also hands back the BatchNorm statistics of its output: y_stats[c][0] = sum over
+ * batch and pixels of y[:,c], y_stats[c][1] = sum of squares (doubles, overwritten), accumulated in the forward
+ * kernel's epilogue so that the BatchNorm that follows the layer in the networks (models/networks_2d/unet.py:53-61,
+ * networks_3d/unet3d.py:97-125) needs no statistics pass of its own (hebb_bn_act_from_stats).  *y_stats_written
+ * is 1 if the statistics were produced (tensor-core path, at most 512 output channels), else 0 — the step
+ * itself is carried out either way and the caller falls back to hebb_bn_act_train.  SURVEY §8f row 2. */
+int hebb_conv_swta_step_stats(const HebbDesc* d, const float* x, const float* W, const float* bias, float kinv,
+                              float* y, int32_t* winner, float* delta_w, void* ws, size_t ws_bytes,
+                              unsigned flags, int prec, double* y_stats, int* y_stats_written, void* stream);
+
 /* Weight gradient of a stride-1 convolution on the same tcgen05 contraction kernel as the plasticity update
  * ("the wgrad kernel *is* a6 with dL/dy in place of r"):
  *     grad_w[co][ci][tap] += sum_p grad_y[b][co][p] * xpad[b][ci][p + tap]
@@ -144,6 +154,13 @@ int hebb_local_update_multi(int n, float* const* grad, float* const* dw, const i
 int hebb_bn_act_train(const float* y, float* out, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, int64_t B, int64_t C, int64_t S, float eps, float momentum, float slope,
                       void* ws, size_t ws_bytes, void* stream);
+
+/* BatchNorm(train) + activation from statistics that hebb_conv_swta_step_stats already produced: only the
+ * scale/shift + running-statistics update and the normalise+activate pass run (one read, one write of y).
+ * ws: >= 2*C floats. */
+int hebb_bn_act_from_stats(const float* y, float* out, const double* y_stats, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, int64_t B, int64_t C, int64_t S, float eps,
+                           float momentum, float slope, void* ws, size_t ws_bytes, void* stream);
 
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) — models/networks_2d/unet.py:171-172.
  * in: [N][H][W], out: [N][2H][2W] fp32, N = batch*channels. */

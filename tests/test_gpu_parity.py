@@ -461,6 +461,28 @@ def test_fast_wgrad_conv_matches_stock_conv(case, fmt):
     assert relerr(xf.grad, xr.grad) < 2e-3           # cuDNN dgrad (TF32 by default) on both sides
 
 
+@pytest.mark.parametrize('case', [(2, 8, 3, 16, (40, 36)), (2, 4, 16, 32, (24, 28)), (2, 3, 32, 64, (20, 20)), (2, 2, 64, 128, (12, 16)),
+                                  (3, 2, 16, 64, (6, 10, 8)), (2, 2, 128, 256, (8, 8))])
+def test_forward_epilogue_hands_back_batchnorm_statistics(case):
+    """hebb_conv_swta_step_stats: per-channel sum / sum of squares of y out of the forward epilogue (every epilogue
+    form: <= 32 channels per-thread sums, 64 channels per-block butterfly, wider rows the multi-pass form)."""
+    nd, B, Cin, Cout, sp = case
+    g = torch.Generator().manual_seed(Cin + Cout)
+    cls = hebb.HebbianConv2d if nd == 2 else hebb.HebbianConv3d
+    layer = cls(Cin, Cout, 3, padding=1, bias=True, k=5., alpha=1.)
+    with torch.no_grad():
+        layer.bias.copy_(torch.randn(Cout, generator=g) * 0.2)
+    layer = layer.to(DEV).train()
+    layer._emit_y_stats = True
+    y = layer(torch.randn(B, Cin, *sp, generator=g).to(DEV))
+    assert layer._y_stats is not None and layer._y_stats[0] is y
+    st = layer._y_stats[1]
+    dims = (0, *range(2, nd + 2))
+    yd = y.double()
+    assert relerr(st[:, 0], yd.sum(dim=dims)) < 1e-5
+    assert relerr(st[:, 1], (yd * yd).sum(dim=dims)) < 1e-5
+
+
 def test_fuse_pass_keeps_network_output_and_state():
     from hebb.fused import fuse_norm_act
     torch.manual_seed(0)
