@@ -4,6 +4,7 @@
 //   Upsample(scale 2, bilinear, align_corners) : hebb_upsample2x_bilinear
 // They are opt-in (hebb/fused.py); the reference API surface is untouched.
 #include "common.cuh"
+#include <curand_kernel.h>
 
 namespace hebb {
 
@@ -161,6 +162,71 @@ maxpool2x_kernel(const float* __restrict__ in, float* __restrict__ out, long lon
   }
 }
 
+// out = dropout(relu(z + bias[c])) in ONE pass (the Conv -> ReLU -> Dropout runs of the back-prop head:
+// models/networks_2d/unet.py:449-457), with the 1-byte mask (kept AND positive) the backward needs.
+// Element i belongs to channel (i / inner) % C: inner = 1 for channels_last storage, = spatial size for NCHW.
+// Philox4x32-10 counter-based stream: (seed, thread index) -> independent of the launch geometry's order.
+__global__ void __launch_bounds__(256)
+bias_relu_dropout_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ out,
+                             uint8_t* __restrict__ mask, long long n, int C, long long inner, float p, float scale,
+                             unsigned long long seed) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  curandStatePhilox4_32_10_t rng;
+  curand_init(seed, (unsigned long long)tid, 0, &rng);
+  const bool vec = ((n & 3) == 0) && ((inner & 3) == 0 || (inner == 1 && (C & 3) == 0)) &&
+                   (((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(mask) & 3) == 0);
+  if (vec) {
+    for (long long i = tid * 4; i < n; i += nth * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(z + i);
+      const float4 r = curand_uniform4(&rng);
+      const int c0 = (int)((i / inner) % C);
+      float b[4];
+      if (inner == 1) { b[0] = __ldg(bias + c0); b[1] = __ldg(bias + c0 + 1); b[2] = __ldg(bias + c0 + 2); b[3] = __ldg(bias + c0 + 3); }
+      else { b[0] = b[1] = b[2] = b[3] = __ldg(bias + c0); }
+      const float x[4] = {v.x + b[0], v.y + b[1], v.z + b[2], v.w + b[3]};
+      const float u[4] = {r.x, r.y, r.z, r.w};
+      float o[4]; uint32_t m = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool keep = (u[k] > p) && (x[k] > 0.f);          // curand_uniform is in (0, 1]: P(keep) = 1 - p
+        o[k] = keep ? x[k] * scale : 0.f;
+        m |= (keep ? 1u : 0u) << (8 * k);
+      }
+      *reinterpret_cast<float4*>(out + i) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint32_t*>(mask + i) = m;
+    }
+  } else {
+    for (long long i = tid; i < n; i += nth) {
+      const float x = z[i] + __ldg(bias + (int)((i / inner) % C));
+      const bool keep = (curand_uniform(&rng) > p) && (x > 0.f);
+      out[i] = keep ? x * scale : 0.f;
+      mask[i] = keep ? 1 : 0;
+    }
+  }
+}
+
+// gz = gout * mask * scale
+__global__ void __launch_bounds__(256)
+mask_scale_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ mask, float* __restrict__ gz, long long n,
+                      float scale) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  const bool vec = ((n & 3) == 0) && (((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(gz)) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(mask) & 3) == 0);
+  if (vec) {
+    for (long long i = tid * 4; i < n; i += nth * 4) {
+      const float4 g = *reinterpret_cast<const float4*>(gout + i);
+      const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + i);
+      *reinterpret_cast<float4*>(gz + i) = make_float4((m & 0xffu) ? g.x * scale : 0.f, (m & 0xff00u) ? g.y * scale : 0.f,
+                                                       (m & 0xff0000u) ? g.z * scale : 0.f, (m & 0xff000000u) ? g.w * scale : 0.f);
+    }
+  } else {
+    for (long long i = tid; i < n; i += nth) gz[i] = mask[i] ? gout[i] * scale : 0.f;
+  }
+}
+
 }  // namespace hebb
 
 using namespace hebb;
@@ -222,6 +288,34 @@ int hebb_bn_act_from_stats(const float* y, float* out, const double* y_stats, co
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   bn_act_apply_kernel<<<(unsigned)gx, 256, 0, st>>>(y, out, ss, (int)C, S, total, slope);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
+int hebb_bias_relu_dropout(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
+                           int64_t inner, float p, uint64_t seed, void* stream) {
+  HEBB_TRY(device_ok());
+  if (!z || !bias || !out || !mask) return HEBB_EARG;
+  if (n <= 0 || C <= 0 || inner <= 0 || !(p >= 0.f && p < 1.f)) return HEBB_ESHAPE;
+  long long gx = cdiv(n, 256 * 4 * 2);
+  const long long cap = (long long)num_sms() * 16;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  bias_relu_dropout_fwd_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(z, bias, out, mask, n, (int)C, inner, p,
+                                                                              1.f / (1.f - p), seed);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
+int hebb_mask_scale(const float* gout, const uint8_t* mask, float* gz, int64_t n, float scale, void* stream) {
+  HEBB_TRY(device_ok());
+  if (!gout || !mask || !gz) return HEBB_EARG;
+  if (n <= 0) return HEBB_ESHAPE;
+  long long gx = cdiv(n, 256 * 4 * 2);
+  const long long cap = (long long)num_sms() * 16;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  mask_scale_bwd_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(gout, mask, gz, n, scale);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   return HEBB_OK;
 }

@@ -81,6 +81,8 @@ def load():
         lib.hebb_bn_act_train.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, vp, ctypes.c_size_t, vp]
         lib.hebb_upsample2x_bilinear.argtypes = [vp, vp, i64, i64, i64, vp]
         lib.hebb_maxpool2x.argtypes = [vp, vp, i64, i64, i64, i64, i32, vp]
+        lib.hebb_bias_relu_dropout.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, ctypes.c_uint64, vp]
+        lib.hebb_mask_scale.argtypes = [vp, vp, vp, i64, f32, vp]
         lib.hebb_debug_launch_count.restype = ctypes.c_ulonglong
         lib.hebb_uses_tensor_cores.argtypes = [ctypes.POINTER(HebbDesc), i32]
         for name in EXPORTS:
@@ -317,6 +319,37 @@ def maxpool2x(x):
     out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
     check(load().hebb_maxpool2x(x.data_ptr(), out.data_ptr(), B * C, D, H, W, pd, _stream_ptr(x.device)), 'maxpool2x')
     return out
+
+
+def _dense_channel_inner(t):
+    """(inner) such that element i of t's dense storage belongs to channel (i / inner) % C, or None."""
+    nd = t.dim() - 2
+    if t.is_contiguous():
+        return t[0, 0].numel()
+    cl = torch.channels_last if nd == 2 else (torch.channels_last_3d if nd == 3 else None)
+    if cl is not None and t.is_contiguous(memory_format=cl):
+        return 1
+    return None
+
+
+def bias_relu_dropout(z, bias, p: float, seed: int):
+    """(out, mask) = hebb_bias_relu_dropout on z's dense storage (NCHW or channels_last; out keeps z's layout)."""
+    _require_cuda(z, 'input')
+    inner = _dense_channel_inner(z)
+    if inner is None:
+        raise RuntimeError('bias_relu_dropout needs a dense NCHW or channels_last tensor')
+    out = torch.empty_like(z)                      # preserves the memory format
+    mask = torch.empty_like(z, dtype=torch.uint8)
+    check(load().hebb_bias_relu_dropout(z.data_ptr(), bias.data_ptr(), out.data_ptr(), mask.data_ptr(), z.numel(), z.shape[1],
+                                        inner, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream_ptr(z.device)), 'bias_relu_dropout')
+    return out, mask
+
+
+def mask_scale(gout, mask, scale: float):
+    gz = torch.empty_like(mask, dtype=torch.float32)
+    check(load().hebb_mask_scale(gout.data_ptr(), mask.data_ptr(), gz.data_ptr(), gout.numel(), float(scale),
+                                 _stream_ptr(gout.device)), 'mask_scale')
+    return gz
 
 
 def launch_count() -> int:

@@ -7,7 +7,9 @@ normalise+activate pass) — or, with `fuse_stats=True`, as `hebb_bn_act_from_st
 the producing layer's forward epilogue hands back (`hebb_conv_swta_step_stats`: no statistics pass at all) —
 and every `nn.Upsample(scale_factor=2, bilinear, align_corners=True)` so it runs as `hebb_upsample2x_bilinear`, and every 2x `nn.MaxPool{2,3}d` (kernel = stride = 2, no padding) so it runs
 as `hebb_maxpool2x`; the stock convolutions a Hebbian network keeps for back-prop (makehebbian's `exclude` list)
-can get their weight gradient from `hebb_conv_wgrad` (`head_wgrad=True`; off by default: on the C2 head it is
+have their `Conv -> ReLU -> Dropout` runs turned into convolution-without-bias + one `hebb_bias_relu_dropout`
+pass (`fuse_head_act=True`; statistically the same dropout, its own Philox stream), and can get their weight
+gradient from `hebb_conv_wgrad` (`head_wgrad=True`; off by default: on the C2 head it is
 fp32-equivalent instead of TF32 but no faster than cuDNN once the packing passes are counted).
 Numerics follow torch (biased variance for normalisation, unbiased for the running estimate, momentum update, num_batches_tracked).  Anything the kernels do not cover —
 eval mode, inputs or affine parameters that require grad, CPU tensors, cumulative-average momentum —
@@ -184,6 +186,58 @@ class FastWgradConv3d(_FastWgradMixin, nn.Conv3d):
     pass
 
 
+class _BiasReluDropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, bias, p):
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())      # torch.manual_seed() governs it
+        out, mask = _native.bias_relu_dropout(z.detach(), bias.detach(), p, seed)
+        ctx.save_for_backward(mask)
+        ctx.scale = 1.0 / (1.0 - p)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        mask, = ctx.saved_tensors
+        if gout.stride() != mask.stride():          # bring dL/dout into the layout the mask was written in
+            cl = mask.dim() == 4 and _native._dense_channel_inner(mask) == 1
+            gout = gout.contiguous(memory_format=torch.channels_last) if cl else gout.contiguous()
+        gz = _native.mask_scale(gout, mask, ctx.scale)
+        gb = gz.sum(dim=(0, *range(2, gz.dim()))) if ctx.needs_input_grad[1] else None
+        return gz, gb, None
+
+
+class _NoBiasConvMixin:
+    """The bias add moves into the fused activation kernel that follows (see FusedBiasReluDropout)."""
+
+    def forward(self, x):
+        follower = self.__dict__.get('_bias_follower')
+        if follower is not None and follower[0]._takes_bias(x):
+            return self._conv_forward(x, self.weight, None)
+        return super().forward(x)
+
+
+class NoBiasConv2d(_NoBiasConvMixin, nn.Conv2d):
+    pass
+
+
+class FusedBiasReluDropout(nn.ReLU):
+    """Stands where the ReLU of a `Conv -> ReLU -> Dropout` run stood (the Dropout becomes an Identity): adds the
+    convolution's bias, applies ReLU and dropout in one pass (hebb_bias_relu_dropout).  Parameter-free, so the
+    state_dict is unchanged; eval mode, CPU tensors and odd layouts take the stock ops."""
+
+    def _takes_bias(self, x):
+        return self.training and x.is_cuda and x.dtype == torch.float32 and 0.0 <= self._p < 1.0
+
+    def forward(self, z):
+        conv = self.__dict__['_conv'][0]
+        if self._takes_bias(z) and _native._dense_channel_inner(z) is not None:
+            return _BiasReluDropoutFn.apply(z, conv.bias, self._p)
+        # stock path: the convolution added its bias itself unless it saw a training-mode CUDA input
+        if self._takes_bias(z):
+            z = z + conv.bias.view(1, -1, *([1] * (z.dim() - 2)))
+        return F.dropout(F.relu(z), self._p, self.training)
+
+
 def _slope_of(m):
     if type(m) is nn.ReLU:
         return 0.0
@@ -192,8 +246,8 @@ def _slope_of(m):
     return None
 
 
-def fuse_norm_act(model: nn.Module, head_wgrad: bool = False, fuse_stats: bool = True) -> nn.Module:
-    n_bn = n_up = n_pool = n_head = 0
+def fuse_norm_act(model: nn.Module, head_wgrad: bool = False, fuse_stats: bool = True, fuse_head_act: bool = True) -> nn.Module:
+    n_bn = n_up = n_pool = n_head = n_act = 0
     for mod in model.modules():
         if isinstance(mod, nn.Sequential):
             items = list(mod._modules.items())
@@ -209,6 +263,20 @@ def fuse_norm_act(model: nn.Module, head_wgrad: bool = False, fuse_stats: bool =
                     if slope is not None:
                         mod._modules[items[i + 1][0]] = nn.Identity()     # activation now lives in the fused module
                     n_bn += 1
+        if fuse_head_act and isinstance(mod, nn.Sequential):
+            items = list(mod._modules.items())
+            for i in range(len(items) - 2):
+                c, r, d = items[i][1], items[i + 1][1], items[i + 2][1]
+                if (type(c) is nn.Conv2d and c.bias is not None and type(r) is nn.ReLU and type(d) is nn.Dropout
+                        and 0.0 <= d.p < 1.0):
+                    c.__class__ = NoBiasConv2d
+                    act = FusedBiasReluDropout()
+                    act._p = float(d.p)
+                    act.__dict__['_conv'] = (c,)
+                    c.__dict__['_bias_follower'] = (act,)
+                    mod._modules[items[i + 1][0]] = act
+                    mod._modules[items[i + 2][0]] = nn.Identity()
+                    n_act += 1
         for name, m in list(mod._modules.items()):
             if type(m) is nn.Upsample and m.mode == 'bilinear' and m.align_corners and m.scale_factor in (2, 2.0, (2, 2), (2.0, 2.0)):
                 m.__class__ = FastUpsample2x
@@ -222,5 +290,5 @@ def fuse_norm_act(model: nn.Module, head_wgrad: bool = False, fuse_stats: bool =
             elif head_wgrad and type(m) in (nn.Conv2d, nn.Conv3d) and m.weight.requires_grad:
                 m.__class__ = FastWgradConv2d if type(m) is nn.Conv2d else FastWgradConv3d
                 n_head += 1
-    model._hebb_fused = dict(bn_act=n_bn, upsample=n_up, maxpool=n_pool, head_wgrad=n_head)
+    model._hebb_fused = dict(bn_act=n_bn, upsample=n_up, maxpool=n_pool, head_wgrad=n_head, bias_relu_dropout=n_act)
     return model

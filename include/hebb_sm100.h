@@ -172,6 +172,16 @@ int hebb_upsample2x_bilinear(const float* in, float* out, int64_t N, int64_t H, 
 int hebb_maxpool2x(const float* in, float* out, int64_t N, int64_t D, int64_t H, int64_t W, int pool_depth,
                    void* stream);
 
+/* out = dropout_p(relu(z + bias[c])) in one pass, plus the 1-byte mask (kept AND positive) for the backward:
+ * the Conv -> ReLU -> Dropout runs of the back-prop head (reference models/networks_2d/unet.py:449-457) with the
+ * bias add taken out of the convolution.  z, out: n floats; element i belongs to channel (i / inner) % C
+ * (inner = 1 for channels_last storage, = spatial size for NCHW).  Kept values are scaled by 1/(1-p); the random
+ * stream is Philox4x32-10 keyed by (seed, thread) -- statistically the nn.Dropout mask, not torch's bit stream.
+ * hebb_mask_scale is its backward: gz = gout * mask * scale.  Opt-in (hebb.fused.fuse_norm_act). */
+int hebb_bias_relu_dropout(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
+                           int64_t inner, float p, uint64_t seed, void* stream);
+int hebb_mask_scale(const float* gout, const uint8_t* mask, float* gz, int64_t n, float scale, void* stream);
+
 /* ---- exported for tests and profiling ---- */
 
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 PY="python -m pytest -q -p no:cacheprovider --timeout 600 -m gpu"
 timeout 900 $PY tests/test_umma_probe.py > gpurun_out/t_probe.log 2>&1; echo "probe rc=$?"
-timeout 1500 $PY tests/test_gpu_parity.py -k "fp32 or zero_norm or wnorm or backprop or fused or upsample or maxpool or fuse_pass or fast_wgrad or batchnorm_statistics" > gpurun_out/t_simt.log 2>&1; echo "simt rc=$?"
-timeout 1500 $PY tests/test_gpu_parity.py -k "not (fp32 or zero_norm or wnorm or backprop or fused or upsample or maxpool or fuse_pass or fast_wgrad or batchnorm_statistics)" > gpurun_out/t_tc.log 2>&1; echo "tc rc=$?"
+timeout 1500 $PY tests/test_gpu_parity.py -k "fp32 or zero_norm or wnorm or backprop or fused or upsample or maxpool or fuse_pass or fast_wgrad or batchnorm_statistics or bias_relu" > gpurun_out/t_simt.log 2>&1; echo "simt rc=$?"
+timeout 1500 $PY tests/test_gpu_parity.py -k "not (fp32 or zero_norm or wnorm or backprop or fused or upsample or maxpool or fuse_pass or fast_wgrad or batchnorm_statistics or bias_relu)" > gpurun_out/t_tc.log 2>&1; echo "tc rc=$?"
 timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
 tail -n 25 gpurun_out/t_probe.log gpurun_out/t_simt.log gpurun_out/t_tc.log gpurun_out/smoke.log

@@ -483,6 +483,36 @@ def test_forward_epilogue_hands_back_batchnorm_statistics(case):
     assert relerr(st[:, 1], (yd * yd).sum(dim=dims)) < 1e-5
 
 
+@pytest.mark.parametrize('fmt', ['nchw', 'channels_last'])
+@pytest.mark.parametrize('p', [0.0, 0.5])
+def test_fused_bias_relu_dropout(fmt, p):
+    """hebb_bias_relu_dropout / hebb_mask_scale: exact for p = 0, and for p > 0 exactly relu(z+b)/(1-p) where kept,
+    0 where dropped, with the kept fraction of the positive entries at 1-p and a backward that re-uses the mask."""
+    from hebb.fused import _BiasReluDropoutFn
+    torch.manual_seed(7)
+    z = torch.randn(4, 32, 40, 36, device=DEV)
+    b = torch.randn(32, device=DEV)
+    if fmt == 'channels_last':
+        z = z.contiguous(memory_format=torch.channels_last)
+    zr = z.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    out = _BiasReluDropoutFn.apply(zr, br, p)
+    assert out.stride() == z.stride()
+    want = torch.relu(z + b.view(1, -1, 1, 1))
+    kept = out != 0
+    assert torch.equal(out[kept], (want / (1.0 - p))[kept]) or relerr(out[kept], (want / (1.0 - p))[kept]) < 1e-6
+    pos = want > 0
+    assert not bool((kept & ~pos).any())
+    frac = float(kept.sum()) / float(pos.sum())
+    assert abs(frac - (1.0 - p)) < 0.01
+    g = torch.randn_like(out)
+    out.backward(g)
+    assert relerr(zr.grad, g * kept / (1.0 - p)) < 1e-6
+    assert relerr(br.grad, (g * kept / (1.0 - p)).sum(dim=(0, 2, 3))) < 1e-5
+    if p == 0.0:
+        assert relerr(out, want) < 1e-7
+
+
 def test_fuse_pass_keeps_network_output_and_state():
     from hebb.fused import fuse_norm_act
     torch.manual_seed(0)
@@ -495,7 +525,7 @@ def test_fuse_pass_keeps_network_output_and_state():
     ref = copy.deepcopy(net).to(DEV).train()
     keys = list(net.state_dict().keys())
     fuse_norm_act(net)
-    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4, 'head_wgrad': 0}
+    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4, 'head_wgrad': 0, 'bias_relu_dropout': 2}
     net = net.to(DEV).train()
     x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(5)).to(DEV)
     a, b = ref(x), net(x)
