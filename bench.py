@@ -449,6 +449,7 @@ def run_ours(args):
                        'hebb_params': HEBB_PARAMS if args.workload != 'c1' else {'mode': 'swta', 'k': 3.0, 'alpha': 1.0},
                        'optimizer': f'adam lr={lr}', 'precision_mode': args.prec,
                        'fused_norm_act_upsample': (not args.no_fuse) and args.workload != 'c1',
+                       'fused_ops': 'BatchNorm(train)+act with statistics from the conv epilogue, 2x up-sampling, 2x max pooling, bias+ReLU+dropout of the back-prop head (own Philox dropout stream)' if ((not args.no_fuse) and args.workload != 'c1') else 'none',
                        'head_weight_gradient': 'hebb_conv_wgrad (bf16x3)' if ((not args.no_fuse) and args.head_wgrad and args.workload != 'c1') else 'cuDNN',
                        'backward': 'stock ATen' if args.aten_backward else 'native dgrad/wgrad on the tcgen05 kernels where the planner takes the layer',
                        'backprop_head_memory_format': 'nchw' if (args.head_nchw or args.workload != 'c2') else 'channels_last', 'l2': 'flushed between timed steps (256 MB fill)',
