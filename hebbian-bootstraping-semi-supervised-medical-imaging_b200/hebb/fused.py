@@ -9,8 +9,9 @@ and every `nn.Upsample(scale_factor=2, bilinear, align_corners=True)` so it runs
 as `hebb_maxpool2x`; the stock convolutions a Hebbian network keeps for back-prop (makehebbian's `exclude` list)
 have their `Conv -> ReLU -> Dropout` runs turned into convolution-without-bias + one `hebb_bias_relu_dropout`
 pass (`fuse_head_act=True`; statistically the same dropout, its own Philox stream), and can get their weight
-gradient from `hebb_conv_wgrad` (`head_wgrad=True`; off by default: on the C2 head it is
-fp32-equivalent instead of TF32 but no faster than cuDNN once the packing passes are counted).
+gradient from `hebb_conv_wgrad` (`head_wgrad=N`: convolutions with at most N filters, default 16 — the 2-class
+output layer, whose cuDNN weight gradient costs 1.7 ms against 0.9 ms here, fp32-equivalent instead of TF32; for
+the wider head layers the packing passes eat the gain).
 Numerics follow torch (biased variance for normalisation, unbiased for the running estimate, momentum update, num_batches_tracked).  Anything the kernels do not cover —
 eval mode, inputs or affine parameters that require grad, CPU tensors, cumulative-average momentum —
 takes the stock torch path of the parent class, so the pass is always safe to apply.
@@ -246,7 +247,7 @@ def _slope_of(m):
     return None
 
 
-def fuse_norm_act(model: nn.Module, head_wgrad: bool = False, fuse_stats: bool = True, fuse_head_act: bool = True) -> nn.Module:
+def fuse_norm_act(model: nn.Module, head_wgrad: int = 16, fuse_stats: bool = True, fuse_head_act: bool = True) -> nn.Module:
     n_bn = n_up = n_pool = n_head = n_act = 0
     for mod in model.modules():
         if isinstance(mod, nn.Sequential):
@@ -287,7 +288,7 @@ def fuse_norm_act(model: nn.Module, head_wgrad: bool = False, fuse_stats: bool =
             elif type(m) is nn.MaxPool3d and _pool_is_2x(m, 3):
                 m.__class__ = FastMaxPool3d
                 n_pool += 1
-            elif head_wgrad and type(m) in (nn.Conv2d, nn.Conv3d) and m.weight.requires_grad:
+            elif head_wgrad and type(m) in (nn.Conv2d, nn.Conv3d) and m.weight.requires_grad and m.out_channels <= int(head_wgrad):
                 m.__class__ = FastWgradConv2d if type(m) is nn.Conv2d else FastWgradConv3d
                 n_head += 1
     model._hebb_fused = dict(bn_act=n_bn, upsample=n_up, maxpool=n_pool, head_wgrad=n_head, bias_relu_dropout=n_act)

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-for extra in "" "--cudnn-benchmark" "--head-nchw --cudnn-benchmark"; do
+for extra in "" "--head-wgrad 16" "--head-wgrad 32" "--head-wgrad 64"; do
   python bench.py --workload c2 --steps 5 --warmup 4 --no-cpu-baseline --no-layer-profile $extra > gpurun_out/bench_head.json 2>gpurun_out/bench_head.err || tail -5 gpurun_out/bench_head.err
   python - <<PY
 import json

@@ -525,7 +525,7 @@ def test_fuse_pass_keeps_network_output_and_state():
     ref = copy.deepcopy(net).to(DEV).train()
     keys = list(net.state_dict().keys())
     fuse_norm_act(net)
-    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4, 'head_wgrad': 0, 'bias_relu_dropout': 2}
+    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4, 'head_wgrad': 1, 'bias_relu_dropout': 2}
     net = net.to(DEV).train()
     x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(5)).to(DEV)
     a, b = ref(x), net(x)
