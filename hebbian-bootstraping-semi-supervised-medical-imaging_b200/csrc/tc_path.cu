@@ -1120,30 +1120,47 @@ rsum_from_packed_kernel(const uint4* __restrict__ rhi, const uint4* __restrict__
 __global__ void __launch_bounds__(256)
 tc_finalize_T_kernel(const float* __restrict__ hpart, const float* __restrict__ rsum, const float* __restrict__ W,
                      float* __restrict__ dw, int PS, int Cin, int CinP, int CoutR, int tr_q) {
+  // 256 threads = 8 split lanes x 32 consecutive (ci, co) outputs: the position splits of one output are summed
+  // by 8 threads in a fixed order (deterministic), so layers with few weights and many splits stay parallel
+  __shared__ float red[8][32][9];
   const long long n = (long long)Cin * CoutR;
   const long long Cp = (long long)CoutR * 8;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(idx % CoutR);
-    const int ci = (int)(idx / CoutR);
-    const float* w = W + ((long long)co * Cin + ci) * 8;
-    float* d = dw + ((long long)co * Cin + ci) * 8;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long base = (long long)blockIdx.x * 32; base < n; base += (long long)gridDim.x * 32) {
+    const long long idx = base + tx;
+    const bool ok = idx < n;
+    const int co = ok ? (int)(idx % CoutR) : 0;
+    const int ci = ok ? (int)(idx / CoutR) : 0;
     int col[8];      // packed column of (co, off): co*8 + off, or (off>>1)*tr_q + 2*co + (off&1)
 #pragma unroll
     for (int off = 0; off < 8; ++off) col[off] = tr_q ? ((off >> 1) * tr_q + 2 * co + (off & 1)) : (co * 8 + off);
-    float dec = 0.f;
-#pragma unroll
-    for (int off = 0; off < 8; ++off) dec += rsum[col[off]] * w[off];
     float h[8];
 #pragma unroll
     for (int off = 0; off < 8; ++off) h[off] = 0.f;
-    for (int s = 0; s < PS; ++s) {
-      const float* hp = hpart + ((long long)s * CinP + ci) * Cp;
+    if (ok)
+      for (int s = ty; s < PS; s += 8) {
+        const float* hp = hpart + ((long long)s * CinP + ci) * Cp;
 #pragma unroll
-      for (int off = 0; off < 8; ++off) h[off] += hp[col[off]];
+        for (int off = 0; off < 8; ++off) h[off] += hp[col[off]];
+      }
+#pragma unroll
+    for (int off = 0; off < 8; ++off) red[ty][tx][off] = h[off];
+    __syncthreads();
+    if (ty == 0 && ok) {
+      const float* w = W + ((long long)co * Cin + ci) * 8;
+      float* d = dw + ((long long)co * Cin + ci) * 8;
+      float dec = 0.f;
+#pragma unroll
+      for (int off = 0; off < 8; ++off) dec += rsum[col[off]] * w[off];
+#pragma unroll
+      for (int off = 0; off < 8; ++off) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += red[k][tx][off];
+        d[off] += tot - dec;
+      }
     }
-#pragma unroll
-    for (int off = 0; off < 8; ++off) d[off] += h[off] - dec;
+    __syncthreads();
   }
 }
 
@@ -1385,35 +1402,72 @@ tc_finalize_kernel(const float* __restrict__ hpart, const float* __restrict__ rs
   }
 }
 
-// Same result for LARGE weight tensors (few position splits, millions of outputs): a 32(co) x 32(j) tile
-// goes through shared memory so that the partials are read coalesced along co and delta_w / W are
-// touched coalesced along j = ci*taps + t (a row of the [Cout][Cin*taps] weight).
+// Same result for LARGE weight tensors (few position splits, millions of outputs).  It is a transposition:
+// the partials are contiguous along co, delta_w / W along j = ci*taps + t (a row of the [Cout][Cin*taps] weight).
+// A T(j) x T(co) tile goes through shared memory; for the largest tensors T = 128, so that BOTH sides move in
+// 512-byte runs -- with 32 x 32 tiles every 128-byte piece fell into a different DRAM page and the pass ran at a
+// quarter of the HBM rate (1024 -> 1024 3x3x3: 283 us for 452 MB).
+template <int kFinT>
 __global__ void __launch_bounds__(256)
 tc_finalize_tiled_kernel(const float* __restrict__ hpart, const float* __restrict__ rsum, const float* __restrict__ W,
                          float* __restrict__ dw, int PS, int taps, int Cin, int CinP, int Cout) {
-  __shared__ float tile[32][33];
+  extern __shared__ float fin_tile[];                 // [kFinT j][kFinT + 1 co]
+  constexpr int V = kFinT / 32;                       // consecutive co per lane: one 4/8/16-byte load
+  constexpr int RU = 4;                               // rows in flight per warp (memory-level parallelism)
   const int K = Cin * taps;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long plane = (long long)taps * CinP * Cout;
-  const int j0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int j0 = blockIdx.x * kFinT, co0 = blockIdx.y * kFinT;
+  const bool co_ok = co0 + V * lane < Cout;           // Cout is a multiple of 16 >= V: a lane is all in or all out
+  for (int r0 = warp * RU; r0 < kFinT; r0 += 8 * RU) {
+    float acc[RU][V];
+    const float* hp[RU];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int j = j0 + ty + 8 * r, co = co0 + tx;
-    float acc = 0.f;
-    if (j < K && co < Cout) {
-      const int ci = j / taps, t = j - ci * taps;
-      const float* hp = hpart + ((long long)t * CinP + ci) * Cout + co;
-      for (int sp = 0; sp < PS; ++sp) acc += hp[(long long)sp * plane];
+    for (int u = 0; u < RU; ++u) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[u][k] = 0.f;
+      const int j = j0 + r0 + u;
+      hp[u] = nullptr;
+      if (j < K && co_ok) {
+        const int ci = j / taps, t = j - ci * taps;
+        hp[u] = hpart + ((long long)t * CinP + ci) * Cout + co0 + V * lane;
+      }
     }
-    tile[ty + 8 * r][tx] = acc;
+    for (int sp = 0; sp < PS; ++sp) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        if (hp[u]) {
+          if (V == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(hp[u])); acc[u][0] += v.x; acc[u][1 % V] += v.y; acc[u][2 % V] += v.z; acc[u][3 % V] += v.w; }
+          else if (V == 2) { const float2 v = __ldg(reinterpret_cast<const float2*>(hp[u])); acc[u][0] += v.x; acc[u][1 % V] += v.y; }
+          else acc[u][0] += __ldg(hp[u]);
+          hp[u] += plane;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u)
+#pragma unroll
+      for (int k = 0; k < V; ++k) fin_tile[(r0 + u) * (kFinT + 1) + V * lane + k] = acc[u][k];
   }
   __syncthreads();
+#pragma unroll 2
+  for (int c = warp; c < kFinT; c += 8) {
+    const int co = co0 + c;
+    if (co >= Cout) break;
+    const float rs = rsum ? rsum[co] : 0.f;
+    const long long row = (long long)co * K + j0;
+    float wv[V], dv[V];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int co = co0 + ty + 8 * r, j = j0 + tx;
-    if (j < K && co < Cout) {
-      const long long wi = (long long)co * K + j;
-      dw[wi] += rsum ? (tile[tx][ty + 8 * r] - rsum[co] * W[wi]) : tile[tx][ty + 8 * r];
+    for (int i = 0; i < V; ++i) {
+      const int jj = lane + 32 * i;
+      const bool ok = j0 + jj < K;
+      dv[i] = ok ? dw[row + jj] : 0.f;
+      wv[i] = (ok && rsum) ? __ldg(W + row + jj) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int jj = lane + 32 * i;
+      if (j0 + jj < K) dw[row + jj] = dv[i] + (fin_tile[jj * (kFinT + 1) + c] - rs * wv[i]);
     }
   }
 }
@@ -1956,11 +2010,25 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   {
     const long long n = (long long)g.taps * g.Cin * g.Cout;
     if (tr)
-      tc_finalize_T_kernel<<<ew_grid((long long)g0.Cin * g0.Cout), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g0.Cin, P.CinP, g0.Cout, trq);
+    {
+      long long gx = cdiv((long long)g0.Cin * g0.Cout, 32);
+      const long long cap = (long long)num_sms() * 32;
+      tc_finalize_T_kernel<<<(unsigned)(gx > cap ? cap : gx), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g0.Cin, P.CinP, g0.Cout, trq);
+    }
     else
     if (n >= (1LL << 18) && P.PS * P.Q <= 32) {
-      dim3 fg((unsigned)cdiv((long long)g.Cin * g.taps, 32), (unsigned)cdiv(g.Cout, 32));
-      tc_finalize_tiled_kernel<<<fg, 256, 0, st>>>(hpart, (wgrad || hpca) ? nullptr : rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
+      const float* rs = (wgrad || hpca) ? nullptr : rsum;
+#define HEBB_FIN_LAUNCH(T)                                                                                              \
+      do {                                                                                                              \
+        dim3 fg((unsigned)cdiv((long long)g.Cin * g.taps, T), (unsigned)cdiv(g.Cout, T));                               \
+        const int fin_smem = T * (T + 1) * (int)sizeof(float);                                                          \
+        HEBB_CUDA_TRY(cudaFuncSetAttribute(tc_finalize_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           fin_smem));                                                                  \
+        tc_finalize_tiled_kernel<T><<<fg, 256, fin_smem, st>>>(hpart, rs, W, delta_w, P.PS * P.Q, g.taps, g.Cin,        \
+                                                               P.CinP, g.Cout);                                         \
+      } while (0)
+      if (n >= (1LL << 22)) HEBB_FIN_LAUNCH(128); else if (n >= (1LL << 20)) HEBB_FIN_LAUNCH(64); else HEBB_FIN_LAUNCH(32);
+#undef HEBB_FIN_LAUNCH
     } else {
       long long gx = cdiv(n, 32);
       const long long cap = (long long)num_sms() * 32;
@@ -2079,6 +2147,60 @@ umma_rate_kernel(uint64_t a_hi, uint32_t a_step, uint64_t b_hi, uint32_t b_step,
   if (warp == 0) tmem_dealloc(tb, cols);
 }
 
+// Same measurement with groups of `group` consecutive MMAs that share their A tile (the A descriptor advances
+// once per group, the B descriptor per MMA) under the A-operand collector hints fill / use / lastuse
+// (hint = 0 issues the same sequence without hints).
+__global__ void __launch_bounds__(128, 1)
+umma_rate_shared_a_kernel(uint64_t a_hi, uint32_t a_step, uint64_t b_hi, uint32_t b_step, uint32_t b_off, uint32_t idesc,
+                          int per_round, int group, int hint, int d_step, int iters, int n,
+                          long long* __restrict__ cycles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t sa = smem_u32(smem);
+  for (int i = threadIdx.x; i < (int)(b_off * 2 / 16); i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  const uint32_t cols = pow2_cols(d_step ? d_step * group : n);
+  if (warp == 0) { tmem_alloc(smem_u32(&s_tmem), cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = s_tmem;
+  if (__shfl_sync(0xffffffffu, warp, 0) == 0) {
+    const uint32_t a_lbo = (uint32_t)a_hi, a_hi32 = (uint32_t)(a_hi >> 32);
+    const uint32_t b_lbo = (uint32_t)b_hi, b_hi32 = (uint32_t)(b_hi >> 32);
+    const long long t0 = clock64();
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+        uint32_t al = a_lbo | (sa >> 4), bl = b_lbo | ((sa + b_off) >> 4);
+        for (int k = 0; k < per_round; k += group, al += a_step >> 4) {
+          uint32_t d = tb;
+          if (!hint) {
+            for (int j = 0; j < group; ++j, bl += b_step >> 4, d += d_step) umma_lo<0, 1>(d, al, a_hi32, bl, b_hi32, idesc);
+          } else {
+            umma_lo<1, 1>(d, al, a_hi32, bl, b_hi32, idesc); bl += b_step >> 4; d += d_step;
+            for (int j = 1; j < group - 1; ++j, bl += b_step >> 4, d += d_step) umma_lo<2, 1>(d, al, a_hi32, bl, b_hi32, idesc);
+            if (hint == 1) umma_lo<3, 1>(d, al, a_hi32, bl, b_hi32, idesc);
+            else umma_lo<2, 1>(d, al, a_hi32, bl, b_hi32, idesc);
+            bl += b_step >> 4;
+          }
+        }
+        umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bar), ph, nullptr, 0);
+      ph ^= 1;
+    }
+    if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, cols);
+}
+
 }  // namespace hebb
 
 extern "C" int hebb_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
@@ -2109,6 +2231,22 @@ extern "C" int hebb_debug_umma_rate(uint64_t a_desc_hi, uint32_t a_step, uint64_
   HEBB_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(a_desc_hi, a_step, b_desc_hi, b_step, region_bytes, idesc,
                                                              per_round, iters, n, cycles);
+  HEBB_CUDA_TRY(cudaGetLastError());
+  return HEBB_OK;
+}
+
+extern "C" int hebb_debug_umma_rate_shared_a(uint64_t a_desc_hi, uint32_t a_step, uint64_t b_desc_hi, uint32_t b_step,
+                                             uint32_t region_bytes, uint32_t idesc, int per_round, int group, int hint,
+                                             int d_step, int iters, int n, int ctas, long long* cycles, void* stream) {
+  using namespace hebb;
+  HEBB_TRY(device_ok());
+  if (!cycles || region_bytes % 1024 || region_bytes * 2 + 1024 > (uint32_t)kSmemLimit || group < 2 || per_round % group ||
+      d_step < 0 || d_step * group > 512)
+    return HEBB_EARG;
+  const size_t smem = (size_t)region_bytes * 2 + 1024;
+  HEBB_CUDA_TRY(cudaFuncSetAttribute(umma_rate_shared_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_rate_shared_a_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(a_desc_hi, a_step, b_desc_hi, b_step, region_bytes,
+                                                                      idesc, per_round, group, hint, d_step, iters, n, cycles);
   HEBB_CUDA_TRY(cudaGetLastError());
   return HEBB_OK;
 }

@@ -25,7 +25,7 @@ EXPORTS = [
     'hebb_query', 'hebb_status_str', 'hebb_last_cuda_error', 'hebb_version', 'hebb_out_shape',
     'hebb_workspace_bytes', 'hebb_wnorm', 'hebb_conv_swta_step', 'hebb_convT_swta_step',
     'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
-    'hebb_debug_umma_rate', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_upsample2x_bilinear',
+    'hebb_debug_umma_rate', 'hebb_debug_umma_rate_shared_a', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_upsample2x_bilinear',
 ]
 
 
@@ -78,6 +78,8 @@ def load():
                                               i32, i32, i32, vp, vp]
         lib.hebb_debug_umma_rate.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
                                              ctypes.c_uint32, ctypes.c_uint32, i32, i32, i32, i32, vp, vp]
+        lib.hebb_debug_umma_rate_shared_a.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
+                                                      ctypes.c_uint32, ctypes.c_uint32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
         lib.hebb_bn_act_train.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, vp, ctypes.c_size_t, vp]
         lib.hebb_upsample2x_bilinear.argtypes = [vp, vp, i64, i64, i64, vp]
         lib.hebb_maxpool2x.argtypes = [vp, vp, i64, i64, i64, i64, i32, vp]

@@ -212,6 +212,13 @@ int hebb_debug_umma_rate(uint64_t a_desc_hi, uint32_t a_step, uint64_t b_desc_hi
                          uint32_t region_bytes, uint32_t idesc, int per_round, int iters, int n, int ctas,
                          long long* cycles, void* stream);
 
+/* Same, with groups of `group` consecutive MMAs sharing one A tile (A advances per group, B per MMA) under the
+ * A-operand collector hints (hint = 0: none, 1: fill/use/lastuse, 2: fill/use/use); MMA j of a group accumulates
+ * into TMEM column j*d_step.  Used by scripts/umma_rate3.py. */
+int hebb_debug_umma_rate_shared_a(uint64_t a_desc_hi, uint32_t a_step, uint64_t b_desc_hi, uint32_t b_step,
+                                  uint32_t region_bytes, uint32_t idesc, int per_round, int group, int hint,
+                                  int d_step, int iters, int n, int ctas, long long* cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
