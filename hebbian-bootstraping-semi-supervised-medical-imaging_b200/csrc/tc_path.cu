@@ -168,6 +168,7 @@ pack_x_gather_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4
 struct PackRGeo {
   int B, C, C8, oD, oH, oW, WP, plane, Qimg;     // C: channels actually present in gy (the rest of C8*8 is zero)
   long long outS, PR, PTOT;
+  long long PRS;                                 // positions between the 8-channel planes of Rp (PR + zero pads)
   long long sB, sC, sD, sH, sW;                  // element strides of gy
 };
 
@@ -205,8 +206,9 @@ pack_r_kernel(const float* __restrict__ gy, uint4* __restrict__ rhi, uint4* __re
         for (int i = 0; i < 4; ++i) { h[i] = pack_bf16x2(vh[2 * i], vh[2 * i + 1]); l[i] = pack_bf16x2(vl[2 * i], vl[2 * i + 1]); }
       }
     }
-    rhi[idx] = make_uint4(h[0], h[1], h[2], h[3]);
-    if (rlo) rlo[idx] = make_uint4(l[0], l[1], l[2], l[3]);
+    const long long ridx = (long long)c8 * g.PRS + p;
+    rhi[ridx] = make_uint4(h[0], h[1], h[2], h[3]);
+    if (rlo) rlo[ridx] = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -314,7 +316,8 @@ struct FwdParams {
                                // tr == 1: columns co*8 + off; tr == 2: columns (off>>1)*trQ + 2*co + (off&1), trQ = 2*CoutR
   int trQ;
   int RHL;                     // 1: r is consumed as single bf16 (hi only), 2: hi + lo
-  long long PA, PR, PTOT;      // positions per chunk plane in Xp / Rp; real positions B*Qimg
+  long long PA, PR, PTOT;      // positions per chunk plane in Xp; packed output positions; real positions B*Qimg
+  long long PRS;               // positions between the 8-channel planes of Rp (PR + the zero pads the dW kernel reads)
   int MB, TILE_M, ntiles, SEGLEN;
   int XST, WST, NACC, WG;      // WG: taps per weight stage (one bulk copy)
   int WP, plane, Qimg, oD, oH, oW;
@@ -680,7 +683,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                 }
               }
               if (p.dbg & 8) continue;
-              const long long ridx = (long long)g8 * p.PR + pp;
+              const long long ridx = (long long)g8 * p.PRS + pp;
               p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
               if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
             }
@@ -748,7 +751,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                   ol4[i] = pack_bf16x2(l0, l1);
                 }
                 if (p.dbg & 8) continue;
-                const long long ridx = (long long)((cbase + c0) / 8 + g8) * p.PR + pp;
+                const long long ridx = (long long)((cbase + c0) / 8 + g8) * p.PRS + pp;
                 p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
                 if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
               }
@@ -831,7 +834,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                   oh4[i] = pack_bf16x2(h2[0], h2[1]);
                   ol4[i] = pack_bf16x2(l2[0], l2[1]);
                 }
-                const long long ridx = (long long)(c0 / 8 + g8) * p.PR + pp;
+                const long long ridx = (long long)(c0 / 8 + g8) * p.PRS + pp;
                 if (p.dbg & 8) continue;
                 p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
                 if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
@@ -874,7 +877,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                 oh4[i] = pack_bf16x2(h2[0], h2[1]);
                 ol4[i] = pack_bf16x2(l2[0], l2[1]);
               }
-              const long long ridx = (long long)(c0 / 8 + g8) * p.PR + pp;
+              const long long ridx = (long long)(c0 / 8 + g8) * p.PRS + pp;
               if (pp < p.PR && !(p.dbg & 8)) {
                 p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
                 if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
@@ -933,7 +936,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
 struct SmxParams {
   const float* y; uint4* rp[2]; int32_t* winner; float* rsum;
   int Cout, RHL, WP, plane, Qimg, oD, oH, oW;
-  long long PR, PTOT;
+  long long PR, PTOT, PRS;
   float kinv;
 };
 
@@ -980,8 +983,8 @@ swta_softmax_pack_kernel(const __grid_constant__ SmxParams p) {
       ol4[i] = pack_bf16x2(l2[0], l2[1]);
     }
     if (pp < p.PR) {
-      p.rp[0][(long long)c8 * p.PR + pp] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
-      if (p.RHL == 2) p.rp[1][(long long)c8 * p.PR + pp] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+      p.rp[0][(long long)c8 * p.PRS + pp] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+      if (p.RHL == 2) p.rp[1][(long long)c8 * p.PRS + pp] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -1071,20 +1074,21 @@ swta_softmax_pack_T_kernel(const __grid_constant__ SmxParams p, int tD, int tH, 
       oh4[i] = pack_bf16x2(h2[0], h2[1]);
       ol4[i] = pack_bf16x2(l2[0], l2[1]);
     }
-    p.rp[0][(long long)c * p.PR + pp] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
-    if (p.RHL == 2) p.rp[1][(long long)c * p.PR + pp] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
+    p.rp[0][(long long)c * p.PRS + pp] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
+    if (p.RHL == 2) p.rp[1][(long long)c * p.PRS + pp] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
   }
 }
 
 // rsum[c8*8 + i] = sum_p (hi + lo)(Rp[c8][p][i]) : one block per 8-channel chunk, fixed summation order.
 __global__ void __launch_bounds__(256)
-rsum_from_packed_kernel(const uint4* __restrict__ rhi, const uint4* __restrict__ rlo, float* __restrict__ rsum, long long PR) {
+rsum_from_packed_kernel(const uint4* __restrict__ rhi, const uint4* __restrict__ rlo, float* __restrict__ rsum, long long PR,
+                        long long PRS) {
   const int c8 = blockIdx.x;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   for (long long pp = threadIdx.x; pp < PR; pp += blockDim.x) {
-    const uint4 h = __ldg(rhi + (long long)c8 * PR + pp);
+    const uint4 h = __ldg(rhi + (long long)c8 * PRS + pp);
     const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1092,7 +1096,7 @@ rsum_from_packed_kernel(const uint4* __restrict__ rhi, const uint4* __restrict__
       acc[2 * i + 1] += __uint_as_float(hw[i] & 0xffff0000u);
     }
     if (rlo) {
-      const uint4 l = __ldg(rlo + (long long)c8 * PR + pp);
+      const uint4 l = __ldg(rlo + (long long)c8 * PRS + pp);
       const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -1164,59 +1168,133 @@ tc_finalize_T_kernel(const float* __restrict__ hpart, const float* __restrict__ 
   }
 }
 
+// Zero pads of the packed responses: `lead` positions before and `tail` positions after the PR written ones, in
+// every 8-channel plane (the contraction kernel reads r[q - shift] for every q of its position blocks).
+__global__ void __launch_bounds__(256)
+zero_r_pads_kernel(uint4* __restrict__ rhi, uint4* __restrict__ rlo, int C8, long long PRS, int lead, long long PR, int tail) {
+  const int per = lead + tail;
+  const long long total = (long long)C8 * per;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx / per);
+    const int i = (int)(idx - (long long)c8 * per);
+    const long long off = (long long)c8 * PRS + (i < lead ? (long long)i - lead : PR + (i - lead));
+    rhi[off] = make_uint4(0, 0, 0, 0);
+    if (rlo) rlo[off] = make_uint4(0, 0, 0, 0);
+  }
+}
+
 // -------------------------------------------------------------------------------------
-// dW shift-GEMM:  Hpart[split][tap][ci][co] = sum_{p in split} Xp[ci][p+shift(tap)] * Rp[co][p]
+// dW shift-GEMM:  Hpart[split][tap][ci][co] = sum_q Xp[ci][q] * Rp[co][q - shift(tap)]
+//
+// The A operand (x, the M rows) is the SAME tile for every tap of a position block; the tap is an address offset
+// of the B operand (the responses), whose packed planes carry zero pads of `maxshift` positions on both sides.
+// Shared-memory bandwidth bounds this kernel for Cout <= 64 (an M=128 A tile is 4 KB per 16 positions against
+// 32 cycles of math at N=64: profiles/README.md), so keeping A fixed lets a run of instructions fetch it once
+// through the A-operand collector (fill / use / lastuse) -- measured 37-42 cycles per MMA in runs of >= 6
+// against 59 with one A fetch per instruction (profiles/umma_rate3_r1.txt).
 // -------------------------------------------------------------------------------------
 struct DwParams {
   const uint4* xp[2];
   const uint4* rp[2];
   float* hpart; int* err;
   int Cin, Cout, CC, C8, taps, HL;
-  long long PA, PR;
-  int BLK, SEGLEN, total_blocks, blocks_per_split, PS;
+  long long PA, PRS;            // positions between the 8-channel planes of the x / r operands
+  int BLK, SEGLEN, total_blocks, blocks_per_split, PS;     // SEGLEN: staged r positions = BLK + tap halo
   int ngrp; int grp_base[9];
   // "super-taps": with nrep > 1 the staged x tile is replicated nrep times, copy r shifted by r positions, so the
   // M rows of ONE tcgen05.mma cover nrep horizontally adjacent taps (kw0 .. kw0+nrep-1) of a kernel row.
-  int nrep; int grp_st_begin[10]; int st_off[kMaxTaps]; int st_first[kMaxTaps]; int st_n[kMaxTaps];
+  // st_boff: where the B operand of a super-tap starts inside the staged r tile (positions).
+  int nrep; int grp_st_begin[10]; int st_boff[kMaxTaps]; int st_first[kMaxTaps]; int st_n[kMaxTaps];
+  int rhalo;                    // the staged r tile starts rhalo + grp_base positions before the x tile
+  int reuse;                    // 1: k-step outer / tap inner with A collector re-use; 0: tap outer, one A fetch per MMA
   int CM, n_cin_tiles, CN, n_cout_tiles, ST, CinP;
   int stackM, stackN, cpt;      // bf16x3 "precision stacking": [x_hi; x_lo] along M and/or [r_hi | r_lo] along N, so one
                                 // tcgen05.mma yields several of the hi/lo partial products; cpt = 8-channel chunks per cin tile
   uint32_t stage_bytes, x_bytes, off_bar, tmem_cols;
 };
 
-// All MMAs of one staged position block (called by the elected lane of the MMA warp): for every super-tap of
-// this CTA's tap group, BLK/16 k-steps of 16 positions.  MODE: 1 one instruction per k-step (bf16, or both
-// operands precision-stacked), 2 rows stacked (same A twice: keep / re-use), 3 columns stacked, 4 classic
-// 3-product split.  ACC0 = 0 on the first block of the split (overwrite the accumulators).
-template <int MODE, int ACC0>
+constexpr int kMaxRun = 9;       // super-taps per tap group the collector loop order handles (3 x 3 taps of a plane)
+
+// One pass of a k-step: the n super-taps of the CTA's tap group against ONE A tile, NB B tiles per super-tap
+// (bks + bo[j] + bx0, then + bx1).  With n > 1 the run shares A through the collector (fill, then use).  The B
+// offsets live in registers and the loop is fully unrolled: a load from the parameter block between two
+// `asm volatile` issues would sit on the issuing thread's critical path.  ACC = 0: the first instruction into each
+// accumulator overwrites it.
+template <int NB, int ACC>
+__device__ __forceinline__ void dw_pass(int n, uint32_t d0, int colw, uint32_t ah, uint32_t a_hi32, uint32_t bks,
+                                        uint32_t b_hi32, uint32_t idesc, uint32_t bx0, uint32_t bx1,
+                                        const uint32_t (&bo)[kMaxRun]) {
+  if (n == 1) {
+    const uint32_t bh = bks + bo[0];
+    if (NB == 1) umma_lo<0, ACC>(d0, ah, a_hi32, bh + bx0, b_hi32, idesc);
+    else { umma_lo<1, ACC>(d0, ah, a_hi32, bh + bx0, b_hi32, idesc); umma_lo<3, 1>(d0, ah, a_hi32, bh + bx1, b_hi32, idesc); }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxRun; ++j) {
+    if (j < n) {
+      const uint32_t bh = bks + bo[j];
+      const uint32_t d = d0 + j * colw;
+      if (j == 0) umma_lo<1, ACC>(d, ah, a_hi32, bh + bx0, b_hi32, idesc);
+      else umma_lo<2, ACC>(d, ah, a_hi32, bh + bx0, b_hi32, idesc);
+      if (NB == 2) umma_lo<2, 1>(d, ah, a_hi32, bh + bx1, b_hi32, idesc);
+    }
+  }
+}
+
+// All MMAs of one k-step (16 positions).  MODE: 1 one instruction per super-tap (bf16, or both operands
+// precision-stacked), 2 rows stacked ([x_hi; x_lo] against r_lo, r_hi), 3 columns stacked (x_lo, x_hi against
+// [r_hi | r_lo]), 4 classic 3-product split.
+template <int MODE, int ACC>
+__device__ __forceinline__ void dw_kstep(int n, uint32_t d, int colw, uint32_t ah, uint32_t a_hi32, uint32_t bks,
+                                         uint32_t b_hi32, uint32_t idesc, uint32_t xhl16, uint32_t rhl16,
+                                         const uint32_t (&bo)[kMaxRun]) {
+  if (MODE == 2) {
+    dw_pass<2, ACC>(n, d, colw, ah, a_hi32, bks, b_hi32, idesc, rhl16, 0u, bo);
+  } else if (MODE == 3) {
+    dw_pass<1, ACC>(n, d, colw, ah + xhl16, a_hi32, bks, b_hi32, idesc, 0u, 0u, bo);
+    dw_pass<1, 1>(n, d, colw, ah, a_hi32, bks, b_hi32, idesc, 0u, 0u, bo);
+  } else if (MODE == 4) {
+    dw_pass<2, ACC>(n, d, colw, ah, a_hi32, bks, b_hi32, idesc, rhl16, 0u, bo);
+    dw_pass<1, 1>(n, d, colw, ah + xhl16, a_hi32, bks, b_hi32, idesc, 0u, 0u, bo);
+  } else {
+    dw_pass<1, ACC>(n, d, colw, ah, a_hi32, bks, b_hi32, idesc, 0u, 0u, bo);
+  }
+}
+
+// All MMAs of one staged position block (called by the elected lane of the MMA warp).  ACC0 = 0 on the first
+// block of the split (overwrite the accumulators).  REUSE = 1: k-step outer, the taps of the group share the A
+// tile of a k-step through the collector; REUSE = 0 (small tap groups, where the collector hand-over costs more
+// than it saves): tap outer, BLK/16 k-steps inner, one A fetch per instruction.
+template <int MODE, int ACC0, int REUSE>
 __device__ __forceinline__ void dw_issue(const DwParams& p, uint32_t xa, uint32_t ra, int st_b, int st_e, uint32_t tmem_base,
                                          int colw, int ksteps, uint32_t a_lbo, uint32_t a_hi32, uint32_t b_lbo,
                                          uint32_t b_hi32, uint32_t idesc, uint32_t xhl16, uint32_t rhl16) {
-  const uint32_t bh0 = b_lbo | (ra >> 4);
-  uint32_t d = tmem_base;
-  for (int stp = st_b; stp < st_e; ++stp, d += colw) {
-    uint32_t ah = a_lbo | ((xa + p.st_off[stp] * 16) >> 4);
-    uint32_t bh = bh0;
-#define HEBB_DW_STEP(ACC)                                                        \
-    if (MODE == 2) {                                                             \
-      umma_lo<1, ACC>(d, ah, a_hi32, bh + rhl16, b_hi32, idesc);                 \
-      umma_lo<3, 1>(d, ah, a_hi32, bh, b_hi32, idesc);                           \
-    } else if (MODE == 3) {                                                      \
-      umma_lo<0, ACC>(d, ah + xhl16, a_hi32, bh, b_hi32, idesc);                 \
-      umma_lo<0, 1>(d, ah, a_hi32, bh, b_hi32, idesc);                           \
-    } else if (MODE == 4) {                                                      \
-      umma_lo<1, ACC>(d, ah, a_hi32, bh + rhl16, b_hi32, idesc);                 \
-      umma_lo<3, 1>(d, ah, a_hi32, bh, b_hi32, idesc);                           \
-      umma_lo<0, 1>(d, ah + xhl16, a_hi32, bh, b_hi32, idesc);                   \
-    } else {                                                                     \
-      umma_lo<0, ACC>(d, ah, a_hi32, bh, b_hi32, idesc);                         \
-    }
-    HEBB_DW_STEP(ACC0)
+  uint32_t ah = a_lbo | (xa >> 4);
+  uint32_t bks = b_lbo | (ra >> 4);
+  uint32_t bo[kMaxRun];
+  if (REUSE) {
+    const int n = st_e - st_b;
+#pragma unroll
+    for (int j = 0; j < kMaxRun; ++j) bo[j] = (j < n) ? (uint32_t)p.st_boff[st_b + j] : 0u;
+    dw_kstep<MODE, ACC0>(n, tmem_base, colw, ah, a_hi32, bks, b_hi32, idesc, xhl16, rhl16, bo);
     for (int ks = 1; ks < ksteps; ++ks) {
-      ah += 16u; bh += 16u;                    // next 16 positions: 256 bytes in both operands
-      HEBB_DW_STEP(1)
+      ah += 16u; bks += 16u;                     // next 16 positions: 256 bytes in both operands
+      dw_kstep<MODE, 1>(n, tmem_base, colw, ah, a_hi32, bks, b_hi32, idesc, xhl16, rhl16, bo);
     }
-#undef HEBB_DW_STEP
+  } else {
+#pragma unroll
+    for (int j = 0; j < kMaxRun; ++j) bo[j] = 0u;
+    uint32_t d = tmem_base;
+    for (int stp = st_b; stp < st_e; ++stp, d += colw) {
+      uint32_t a = ah, b = bks + (uint32_t)p.st_boff[stp];
+      dw_kstep<MODE, ACC0>(1, d, colw, a, a_hi32, b, b_hi32, idesc, xhl16, rhl16, bo);
+      for (int ks = 1; ks < ksteps; ++ks) {
+        a += 16u; b += 16u;
+        dw_kstep<MODE, 1>(1, d, colw, a, a_hi32, b, b_hi32, idesc, xhl16, rhl16, bo);
+      }
+    }
   }
 }
 
@@ -1257,28 +1335,29 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const uint32_t r_off = p.x_bytes;                 // R region follows X region inside a stage
-  const uint32_t x_hl_stride = cm_chunks * p.SEGLEN * 16;   // lo chunks directly follow the hi chunks
+  const uint32_t x_hl_stride = cm_chunks * p.BLK * 16;      // lo chunks directly follow the hi chunks
   const uint32_t x_rep_stride = p.HL * x_hl_stride;         // replica r+1 directly follows replica r
-  const uint32_t r_hl_stride = rn_chunks * p.BLK * 16;
+  const uint32_t r_hl_stride = rn_chunks * p.SEGLEN * 16;
 
   if (warp == 0) {
     if (elect_one()) {
       int st = 0; uint32_t ph = 0;
-      const uint32_t bytes = p.HL * (p.nrep * cm_chunks * p.SEGLEN + rn_chunks * p.BLK) * 16;
+      const uint32_t bytes = p.HL * (p.nrep * cm_chunks * p.BLK + rn_chunks * p.SEGLEN) * 16;
+      const long long r_back = (long long)p.grp_base[grp] + p.rhalo;      // the r tile starts this far before the x tile
       for (int blk = blk_b; blk < blk_e; ++blk) {
-        const long long p0 = (long long)blk * p.BLK;
+        const long long q0 = (long long)blk * p.BLK;
         mbar_wait(empty + 8 * st, ph ^ 1, p.err, 11);
         mbar_expect_tx(full + 8 * st, bytes);
         const uint32_t dst = sbase + st * p.stage_bytes;
         for (int hl = 0; hl < p.HL; ++hl) {
           for (int rep = 0; rep < p.nrep; ++rep)
             for (int c = 0; c < cm_chunks; ++c)
-              bulk_g2s(dst + rep * x_rep_stride + hl * x_hl_stride + c * p.SEGLEN * 16,
-                       p.xp[hl] + (long long)(cin_tile * p.cpt + c) * p.PA + p0 + p.grp_base[grp] + rep,
-                       p.SEGLEN * 16, full + 8 * st);
+              bulk_g2s(dst + rep * x_rep_stride + hl * x_hl_stride + c * p.BLK * 16,
+                       p.xp[hl] + (long long)(cin_tile * p.cpt + c) * p.PA + q0 + rep, p.BLK * 16, full + 8 * st);
           for (int c = 0; c < rn_chunks; ++c)
-            bulk_g2s(dst + r_off + hl * r_hl_stride + c * p.BLK * 16,
-                     p.rp[hl] + (long long)(cout_tile * (p.CN / 8) + c) * p.PR + p0, p.BLK * 16, full + 8 * st);
+            bulk_g2s(dst + r_off + hl * r_hl_stride + c * p.SEGLEN * 16,
+                     p.rp[hl] + (long long)(cout_tile * (p.CN / 8) + c) * p.PRS + q0 - r_back, p.SEGLEN * 16,
+                     full + 8 * st);
         }
         if (++st == p.ST) { st = 0; ph ^= 1; }
       }
@@ -1286,14 +1365,15 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   } else if (warp == 1) {
     {
       const uint32_t idesc = idesc_bf16(p.CM, Neff, 1, 1);
-      const uint64_t a_hi64 = smem_desc_hi(128, p.SEGLEN * 16);   // MN-major: LBO = next 8 positions, SBO = next chunk
-      const uint64_t b_hi64 = smem_desc_hi(128, p.BLK * 16);
+      const uint64_t a_hi64 = smem_desc_hi(128, p.BLK * 16);      // MN-major: LBO = next 8 positions, SBO = next chunk
+      const uint64_t b_hi64 = smem_desc_hi(128, p.SEGLEN * 16);
       const uint32_t a_lbo = (uint32_t)a_hi64, a_hi32 = (uint32_t)(a_hi64 >> 32);
       const uint32_t b_lbo = (uint32_t)b_hi64, b_hi32 = (uint32_t)(b_hi64 >> 32);
       const uint32_t xhl16 = x_hl_stride >> 4, rhl16 = r_hl_stride >> 4;
       int st = 0; uint32_t ph = 0;
       const int ksteps = p.BLK / 16;
-      const int mode = (p.HL == 2) ? (p.stackM ? (p.stackN ? 1 : 2) : (p.stackN ? 3 : 4)) : 0;
+      const int mode = (p.HL == 2) ? (p.stackM ? (p.stackN ? 1 : 2) : (p.stackN ? 3 : 4)) : 1;
+      const int sel = (mode - 1) * 2 + (p.reuse ? 1 : 0);
       for (int blk = blk_b; blk < blk_e; ++blk) {
         mbar_wait(full + 8 * st, ph, p.err, 12);
         tc_fence_after();
@@ -1301,16 +1381,22 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
         const uint32_t ra = xa + r_off;
         if (elect_one()) {
           const bool first = (blk == blk_b);
-          switch (mode) {
-            case 2: first ? dw_issue<2, 0>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16)
-                          : dw_issue<2, 1>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16); break;
-            case 3: first ? dw_issue<3, 0>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16)
-                          : dw_issue<3, 1>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16); break;
-            case 4: first ? dw_issue<4, 0>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16)
-                          : dw_issue<4, 1>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16); break;
-            default: first ? dw_issue<1, 0>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16)
-                           : dw_issue<1, 1>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc, xhl16, rhl16); break;
+#define HEBB_DW_ISSUE(M, R)                                                                                               \
+          (first ? dw_issue<M, 0, R>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc,  \
+                                     xhl16, rhl16)                                                                        \
+                 : dw_issue<M, 1, R>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc,  \
+                                     xhl16, rhl16))
+          switch (sel) {
+            case 0: HEBB_DW_ISSUE(1, 0); break;
+            case 1: HEBB_DW_ISSUE(1, 1); break;
+            case 2: HEBB_DW_ISSUE(2, 0); break;
+            case 3: HEBB_DW_ISSUE(2, 1); break;
+            case 4: HEBB_DW_ISSUE(3, 0); break;
+            case 5: HEBB_DW_ISSUE(3, 1); break;
+            case 6: HEBB_DW_ISSUE(4, 0); break;
+            default: HEBB_DW_ISSUE(4, 1); break;
           }
+#undef HEBB_DW_ISSUE
           umma_commit(empty + 8 * st);
         }
         __syncwarp();
@@ -1488,7 +1574,8 @@ struct Plan {
   uint32_t f_x_stage, f_w_stage, f_off_w, f_off_misc, f_smem, f_tmem;
   // dW
   int d_HL, BLK, d_SEGLEN, d_by_kh, ngrp, CM, n_cin_tiles, CN, n_cout_tiles, PS, total_blocks, blocks_per_split, ST, CinP;
-  int stackM, stackN, cpt, Q, nrep;
+  int stackM, stackN, cpt, Q, nrep, rhalo, reuse;
+  long long PRS; int r_lead;      // Rp plane: r_lead zero positions, PR packed responses, zero tail (PRS in all)
   uint32_t d_stage, d_x_bytes, d_off_bar, d_smem, d_tmem;
   // workspace carve (byte offsets)
   size_t o_inv, o_rsum, o_err, o_xp[2], o_rp[2], o_wp, o_hpart, o_gram, o_hpart2, total;
@@ -1627,6 +1714,8 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   const int hl3 = (q.d_HL == 2) ? 3 : 1;
   double best_cost = 1e300;
   found = false;
+  // HEBB_DW_REUSE=0/1 forces the loop order of the contraction kernel (profiling aid)
+  static const int want_reuse = [] { const char* e = getenv("HEBB_DW_REUSE"); return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1; }();
   for (int by_kh = 0; by_kh <= 1; ++by_kh) {
     const int ngrp = by_kh ? g.kD * g.kH : g.kD;
     if (by_kh && g.kH == 1) continue;
@@ -1652,28 +1741,31 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
         const int n_cout = (int)cdiv(g.Cout, cn);
         for (int blk = 1024; blk >= 64; blk >>= 1) {
           if (gram && q.PTOT % blk) continue;          // must tile the host plan's packed positions exactly
-          const int seglen = round_up_i(blk + rhalo, 8);
-          const uint32_t xb = (uint32_t)nrep * q.d_HL * cm_chunks * seglen * 16;
-          const uint32_t rb = (uint32_t)q.d_HL * (cn / 8) * blk * 16;
+          const int seglen = round_up_i(blk + rhalo, 8);     // staged r positions: the block plus the tap halo
+          const uint32_t xb = (uint32_t)nrep * q.d_HL * cm_chunks * blk * 16;
+          const uint32_t rb = (uint32_t)q.d_HL * (cn / 8) * seglen * 16;
           for (int st = 3; st >= 2; --st) {
             // the A descriptor always spans cm/8 chunks: rows past the real ones read whatever follows in
             // shared memory (discarded rows) but must stay inside the allocation
             const uint64_t ring = (uint64_t)st * (xb + rb);
-            const uint64_t last_read = (uint64_t)(st - 1) * (xb + rb) + (uint64_t)(q.d_HL - 1) * cm_chunks * seglen * 16 +
-                                       (uint64_t)(cm / 8) * seglen * 16 + 256;
+            const uint64_t last_read = (uint64_t)(st - 1) * (xb + rb) + (uint64_t)(q.d_HL - 1) * cm_chunks * blk * 16 +
+                                       (uint64_t)(cm / 8) * blk * 16 + 256;
             uint64_t tot = ring > last_read ? ring : last_read;
             tot = (tot + 127) / 128 * 128 + 8 * 16 + 64;
             if (tot > (uint64_t)kSmemLimit - 1024) continue;
-            // measured cycles per SWIZZLE_NONE MN-major tcgen05.mma (profiles/umma_rate_r1.txt)
+            // measured cycles per SWIZZLE_NONE MN-major tcgen05.mma (profiles/umma_rate_r1.txt); a run of >= 5
+            // instructions that share the A tile through the collector costs ~38 (profiles/umma_rate3_r1.txt)
             (void)hl3;
-            const double floor_c = (cm == 64) ? 45.0 : 60.0;
-            const double mma = (neff * 0.5625 > floor_c) ? neff * 0.5625 : floor_c;
             const int n_mma = (q.d_HL == 2) ? (sm && sn ? 1 : ((sm || sn) ? 2 : 3)) : 1;
+            const int run = gst * ((q.d_HL == 2 && !sn) ? 2 : 1);      // longest run of instructions with one A tile
+            const int reuse = (want_reuse >= 0) ? (want_reuse && gst <= 9) : ((run >= 5 && gst <= 9 && neff <= 96 && cm == 128) ? 1 : 0);
+            const double floor_c = reuse ? 38.0 : ((cm == 64) ? 45.0 : 60.0);
+            const double mma = (neff * 0.5625 > floor_c) ? neff * 0.5625 : floor_c;
             const double t_mma = (double)gst * (blk / 16) * n_mma * mma;
-            const double t_ld = (double)q.d_HL * 16.0 * ((double)nrep * cm_chunks * seglen + (cn / 8.0) * blk) / 40.0;
+            const double t_ld = (double)q.d_HL * 16.0 * ((double)nrep * cm_chunks * blk + (cn / 8.0) * seglen) / 40.0;
             const double per_blk = (t_mma > t_ld ? t_mma : t_ld) + 800.0 + (st == 2 ? 0.15 * t_ld : 0.0);
             const double out_tiles = (double)ngrp * n_cin * n_cout;
-            const double blocks = (double)cdiv(q.PTOT, blk);
+            const double blocks = (double)cdiv(q.PTOT + q.maxshift, blk);
             double waves = out_tiles / sms;               // how unevenly the tasks fill the SMs
             waves = waves < 1.0 ? 1.0 : waves;
             double ctas = out_tiles < sms ? out_tiles * (double)((int)(sms / out_tiles)) : out_tiles;   // CTAs of the single wave
@@ -1682,7 +1774,7 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
             if (cost < best_cost) {
               best_cost = cost; found = true;
               q.d_by_kh = by_kh; q.BLK = blk; q.d_SEGLEN = seglen; q.ST = st; q.CN = cn; q.CM = cm;
-              q.stackM = sm; q.stackN = sn; q.cpt = cpt; q.nrep = nrep;
+              q.stackM = sm; q.stackN = sn; q.cpt = cpt; q.nrep = nrep; q.rhalo = rhalo; q.reuse = reuse;
               q.d_x_bytes = xb; q.d_stage = xb + rb;
               q.d_off_bar = (uint32_t)(tot - (8 * 16 + 64));
               q.d_smem = (uint32_t)tot;
@@ -1707,9 +1799,13 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   // (a Gram plan runs over another plan's PR positions: its stage size divides them, see the search above)
   const int big = gram ? q.BLK : (q.TILE_M > q.BLK ? q.TILE_M : q.BLK);
   q.PR = (q.PTOT + big - 1) / big * big;
-  q.PA = (q.PR + q.maxshift + 16 + 7) / 8 * 8;
+  // the contraction pairs x[q] with r[q - shift]: its position blocks run over q in [0, PTOT + maxshift), so the
+  // x planes extend that far (zeros) and the r planes carry zero pads of maxshift positions on both sides
+  q.total_blocks = (int)cdiv(q.PTOT + q.maxshift, q.BLK);
+  q.PA = (q.PR + q.maxshift + q.BLK + 16 + 7) / 8 * 8;
+  q.r_lead = (q.maxshift + 7) / 8 * 8;
+  q.PRS = q.r_lead + ((q.PR + q.maxshift + q.BLK + 16 + 7) / 8 * 8);
   q.f_ntiles = (int)(q.PR / q.TILE_M);
-  q.total_blocks = (int)(q.PR / q.BLK);
   const int out_tiles = q.ngrp * q.n_cin_tiles * q.n_cout_tiles;
   // one wave: never more CTAs than SMs (a 149th CTA would double the kernel's duration)
   int ps = sms / out_tiles;
@@ -1726,8 +1822,8 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   q.o_err = take(256);
   q.o_xp[0] = take((size_t)q.CC * q.PA * 16);
   q.o_xp[1] = take((size_t)q.CC * q.PA * 16);
-  q.o_rp[0] = take((size_t)q.C8 * q.PR * 16);
-  q.o_rp[1] = take((size_t)q.C8 * q.PR * 16);
+  q.o_rp[0] = take((size_t)q.C8 * q.PRS * 16);
+  q.o_rp[1] = take((size_t)q.C8 * q.PRS * 16);
   q.o_wp = take((size_t)q.NSLAB * g.taps * q.f_HL * 2 * g.Cout * 16);
   q.o_hpart = take((size_t)q.PS * q.Q * g.taps * q.CinP * g.Cout * sizeof(float));
   q.gram_ok = false; q.o_gram = q.o_hpart2 = 0;
@@ -1809,15 +1905,16 @@ static unsigned ew_grid(long long n) {
 // Fills the parameter block of the contraction kernel for plan P / geometry g and launches it.  `PA` is the
 // position stride between 8-channel planes of the x operand (P.PA for packed activations).
 static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4* xp1, const uint4* rp0, const uint4* rp1,
-                     float* hpart, int* err, long long PA, cudaStream_t st) {
+                     float* hpart, int* err, long long PA, long long PRS, cudaStream_t st) {
   DwParams d;
   d.xp[0] = xp0; d.xp[1] = xp1; d.rp[0] = rp0; d.rp[1] = rp1; d.hpart = hpart; d.err = err;
   d.Cin = g.Cin; d.Cout = g.Cout; d.CC = P.CC; d.C8 = P.C8; d.taps = g.taps; d.HL = P.d_HL;
-  d.PA = PA; d.PR = P.PR; d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
+  d.PA = PA; d.PRS = PRS; d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
+  d.rhalo = P.rhalo; d.reuse = P.reuse;
   d.blocks_per_split = P.blocks_per_split; d.PS = P.PS; d.ngrp = P.ngrp;
   for (int i = 0; i < 9; ++i) d.grp_base[i] = 0;
   d.nrep = P.nrep;
-  for (int t = 0; t < kMaxTaps; ++t) { d.st_off[t] = 0; d.st_first[t] = 0; d.st_n[t] = 0; }
+  for (int t = 0; t < kMaxTaps; ++t) { d.st_boff[t] = 0; d.st_first[t] = 0; d.st_n[t] = 0; }
   {
     // tap groups (one CTA column set each) -> super-taps (one accumulator column group each) -> taps
     int nst = 0, gi = 0;
@@ -1826,7 +1923,7 @@ static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4*
       for (int kh = 0; kh < g.kH; ++kh) {
         if (P.d_by_kh) { d.grp_base[gi] = kd * P.plane + kh * P.WP; d.grp_st_begin[gi] = nst; }
         for (int kw0 = 0; kw0 < g.kW; kw0 += P.nrep, ++nst) {
-          d.st_off[nst] = (P.d_by_kh ? 0 : kh * P.WP) + kw0;
+          d.st_boff[nst] = P.rhalo - ((P.d_by_kh ? 0 : kh * P.WP) + kw0);    // tap offset = grp_base + rhalo - st_boff (+ replica)
           d.st_first[nst] = (kd * g.kH + kh) * g.kW + kw0;
           d.st_n[nst] = (g.kW - kw0 < P.nrep) ? (g.kW - kw0) : P.nrep;
         }
@@ -1862,8 +1959,8 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   int* err = reinterpret_cast<int*>(base + P.o_err);
   uint4* xp0 = reinterpret_cast<uint4*>(base + P.o_xp[0]);
   uint4* xp1 = reinterpret_cast<uint4*>(base + P.o_xp[1]);
-  uint4* rp0 = reinterpret_cast<uint4*>(base + P.o_rp[0]);
-  uint4* rp1 = reinterpret_cast<uint4*>(base + P.o_rp[1]);
+  uint4* rp0 = reinterpret_cast<uint4*>(base + P.o_rp[0]) + P.r_lead;      // position 0 of the first plane
+  uint4* rp1 = reinterpret_cast<uint4*>(base + P.o_rp[1]) + P.r_lead;
   uint4* wp = reinterpret_cast<uint4*>(base + P.o_wp);
   float* hpart = reinterpret_cast<float*>(base + P.o_hpart);
   // weight-gradient mode (hebb_conv_wgrad): `y` holds dL/dy; only x is packed, dL/dy takes the place of the
@@ -1914,7 +2011,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     rg.B = g.B; rg.C = gyC; rg.C8 = P.C8;
     if (nhwc) { rg.sC = 1; rg.sW = gyC; rg.sH = (long long)g.oW * gyC; rg.sD = (long long)g.oH * g.oW * gyC; rg.sB = g.outS * gyC; }
     else { rg.sW = 1; rg.sH = g.oW; rg.sD = (long long)g.oH * g.oW; rg.sC = g.outS; rg.sB = g.outS * gyC; } rg.oD = g.oD; rg.oH = g.oH; rg.oW = g.oW; rg.WP = P.WP; rg.plane = P.plane;
-    rg.Qimg = P.Qimg; rg.outS = g.outS; rg.PR = P.PR; rg.PTOT = P.PTOT;
+    rg.Qimg = P.Qimg; rg.outS = g.outS; rg.PR = P.PR; rg.PTOT = P.PTOT; rg.PRS = P.PRS;
     pack_r_kernel<<<ew_grid((long long)P.C8 * P.PR), 256, 0, st>>>(y, rp0, P.d_HL == 2 ? rp1 : nullptr, rg);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
@@ -1946,7 +2043,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   static const int fwd_dbg = [] { const char* e = getenv("HEBB_FWD_DBG"); return e ? atoi(e) : 0; }();
   f.dbg = fwd_dbg;
   f.stackF = P.stackF; f.CT = P.CT; f.n_ct = P.n_ct; f.fuse = (P.n_ct == 1 || trq) ? 1 : 0;   // transposed: grouped softmax when Cout*8 <= 512
-  f.PA = P.PA; f.PR = P.PR; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
+  f.PA = P.PA; f.PR = P.PR; f.PRS = P.PRS; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
   f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC; f.WG = P.WG;
   f.WP = P.WP; f.plane = P.plane; f.Qimg = P.Qimg; f.oD = g.oD; f.oH = g.oH; f.oW = g.oW;
   f.kinv = kinv; f.write_r = (upd && !hpca) ? 1 : 0;
@@ -1982,13 +2079,13 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     SmxParams sp;
     sp.y = y; sp.rp[0] = rp0; sp.rp[1] = rp1; sp.winner = winner; sp.rsum = rsum;
     sp.Cout = g.Cout; sp.RHL = P.d_HL; sp.WP = P.WP; sp.plane = P.plane; sp.Qimg = P.Qimg;
-    sp.oD = g.oD; sp.oH = g.oH; sp.oW = g.oW; sp.PR = P.PR; sp.PTOT = P.PTOT; sp.kinv = kinv;
+    sp.oD = g.oD; sp.oH = g.oH; sp.oW = g.oW; sp.PR = P.PR; sp.PRS = P.PRS; sp.PTOT = P.PTOT; sp.kinv = kinv;
     if (tr) {
       sp.Cout = g.Cout;
       swta_softmax_pack_T_kernel<<<(unsigned)cdiv(P.PR, 8), 256, 0, st>>>(sp, g0.oD, g0.oH, g0.oW, g0.Cout);
       if (upd) {
         HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-        rsum_from_packed_kernel<<<(unsigned)P.C8, 256, 0, st>>>(rp0, P.d_HL == 2 ? rp1 : nullptr, rsum, P.PR);
+        rsum_from_packed_kernel<<<(unsigned)P.C8, 256, 0, st>>>(rp0, P.d_HL == 2 ? rp1 : nullptr, rsum, P.PR, P.PRS);
       }
     } else {
       swta_softmax_pack_kernel<<<(unsigned)(P.PR / 128), 128, 0, st>>>(sp);
@@ -2001,12 +2098,18 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     PackRGeo rg;
     rg.sW = 1; rg.sH = g.oW; rg.sD = (long long)g.oH * g.oW; rg.sC = g.outS; rg.sB = g.outS * g.Cout;
     rg.B = g.B; rg.C = g.Cout; rg.C8 = P.C8; rg.oD = g.oD; rg.oH = g.oH; rg.oW = g.oW; rg.WP = P.WP; rg.plane = P.plane;
-    rg.Qimg = P.Qimg; rg.outS = g.outS; rg.PR = P.PR; rg.PTOT = P.PTOT;
+    rg.Qimg = P.Qimg; rg.outS = g.outS; rg.PR = P.PR; rg.PTOT = P.PTOT; rg.PRS = P.PRS;
     pack_r_kernel<<<ew_grid((long long)P.C8 * P.PR), 256, 0, st>>>(y, rp0, P.d_HL == 2 ? rp1 : nullptr, rg);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
   // ---- dW ----
-  HEBB_TRY(launch_dw(P, g, xp0, xp1, rp0, rp1, hpart, err, P.PA, st));
+  if (P.maxshift > 0) {
+    const int tail = (int)(P.PRS - P.r_lead - P.PR);
+    zero_r_pads_kernel<<<ew_grid((long long)P.C8 * (P.r_lead + tail)), 256, 0, st>>>(rp0, P.d_HL == 2 ? rp1 : nullptr, P.C8, P.PRS,
+                                                                                   P.r_lead, P.PR, tail);
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  }
+  HEBB_TRY(launch_dw(P, g, xp0, xp1, rp0, rp1, hpart, err, P.PA, P.PRS, st));
   {
     const long long n = (long long)g.taps * g.Cin * g.Cout;
     if (tr)
@@ -2046,7 +2149,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     float* G = reinterpret_cast<float*>(base + P.o_gram);
     float* hpart2 = reinterpret_cast<float*>(base + P.o_hpart2);
     HEBB_CUDA_TRY(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)g.Cout * g.Cout, st));
-    HEBB_TRY(launch_dw(P2, g2, rp0, rp1, rp0, rp1, hpart2, err, P.PR, st));
+    HEBB_TRY(launch_dw(P2, g2, rp0, rp1, rp0, rp1, hpart2, err, P.PRS, P.PRS, st));
     long long gx = cdiv((long long)g.Cout * g.Cout, 32);
     const long long cap = (long long)num_sms() * 32;
     if (gx > cap) gx = cap;
