@@ -45,9 +45,12 @@ struct PackGeo {
   long long PA;   // positions per chunk plane (incl. zero slack)
   long long PTOT; // B*Qimg
   long long sB, sC, sD, sH, sW;   // element strides of x (NCHW: sC = inS, sW = 1; channels_last: sC = 1, sW = C)
+  // zero pads of the packed responses (written here so the step needs no extra launch): in each of the C8 planes
+  // of Rp, r_lead positions before and r_tail positions after the PR the forward pass writes; r_lead + r_tail = 0: none
+  uint4* rhi; uint4* rlo; int C8, r_lead, r_tail; long long PR, PRS;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 pack_x_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __restrict__ xlo, const __grid_constant__ PackGeo g) {
   const long long total = (long long)g.CC * g.PA;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -84,6 +87,17 @@ pack_x_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __res
     }
     xhi[idx] = make_uint4(h[0], h[1], h[2], h[3]);
     if (xlo) xlo[idx] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+  // zero pads of Rp: one block per 8-channel plane, no divisions (keeps the kernel at 32 registers per thread)
+  const int per = g.r_lead + g.r_tail;
+  for (int c8 = blockIdx.x; c8 < g.C8 && per > 0; c8 += gridDim.x) {
+    uint4* ph = g.rhi + (long long)c8 * g.PRS;
+    uint4* pl = g.rlo ? g.rlo + (long long)c8 * g.PRS : nullptr;
+    for (int i = threadIdx.x; i < per; i += blockDim.x) {
+      const long long off = i < g.r_lead ? (long long)(i - g.r_lead) : g.PR + (i - g.r_lead);
+      ph[off] = make_uint4(0, 0, 0, 0);
+      if (pl) pl[off] = make_uint4(0, 0, 0, 0);
+    }
   }
 }
 
@@ -1168,22 +1182,6 @@ tc_finalize_T_kernel(const float* __restrict__ hpart, const float* __restrict__ 
   }
 }
 
-// Zero pads of the packed responses: `lead` positions before and `tail` positions after the PR written ones, in
-// every 8-channel plane (the contraction kernel reads r[q - shift] for every q of its position blocks).
-__global__ void __launch_bounds__(256)
-zero_r_pads_kernel(uint4* __restrict__ rhi, uint4* __restrict__ rlo, int C8, long long PRS, int lead, long long PR, int tail) {
-  const int per = lead + tail;
-  const long long total = (long long)C8 * per;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx / per);
-    const int i = (int)(idx - (long long)c8 * per);
-    const long long off = (long long)c8 * PRS + (i < lead ? (long long)i - lead : PR + (i - lead));
-    rhi[off] = make_uint4(0, 0, 0, 0);
-    if (rlo) rlo[off] = make_uint4(0, 0, 0, 0);
-  }
-}
-
 // -------------------------------------------------------------------------------------
 // dW shift-GEMM:  Hpart[split][tap][ci][co] = sum_q Xp[ci][q] * Rp[co][q - shift(tap)]
 //
@@ -1890,7 +1888,8 @@ int tc_describe_plan(const Geo& g0, int prec, int* o, int n) {
   if (!equivalent_1x1(g0, &g) || !plan_layer(g, prec, &P, tr_quantum(g0))) return 0;
   const int v[] = {P.MB, P.f_SEGLEN, P.XST, P.WST, P.NACC, (int)P.f_tmem, P.f_ntiles, (int)P.f_smem,
                    P.d_by_kh, P.CM, P.CN, P.BLK, P.ST, P.d_SEGLEN, P.ngrp, P.n_cin_tiles, P.n_cout_tiles, P.PS,
-                   P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct, P.nrep, P.WG};
+                   P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct, P.nrep, P.WG,
+                   P.reuse, P.rhalo};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < m; ++i) o[i] = v[i];
   return m;
@@ -1988,6 +1987,10 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   PackGeo pg;
   pg.B = g.B; pg.Cin = g.Cin; pg.iD = g.iD; pg.iH = g.iH; pg.iW = g.iW; pg.pD = g.pD; pg.pH = g.pH; pg.pW = g.pW;
   pg.HP = P.HP; pg.WP = P.WP; pg.plane = P.plane; pg.Qimg = P.Qimg; pg.CC = P.CC; pg.PA = P.PA; pg.PTOT = P.PTOT;
+  // the contraction kernel reads r[q - shift]: zero pads around the packed responses, written by the pack pass
+  const bool zpads = upd && P.maxshift > 0;
+  pg.rhi = rp0; pg.rlo = P.d_HL == 2 ? rp1 : nullptr; pg.C8 = P.C8; pg.PR = P.PR; pg.PRS = P.PRS;
+  pg.r_lead = zpads ? P.r_lead : 0; pg.r_tail = zpads ? (int)(P.PRS - P.r_lead - P.PR) : 0;
   const bool nhwc = wgrad && ((aux >> 16) & 1);         // hebb_conv_wgrad on channels_last tensors
   if (nhwc) { pg.sC = 1; pg.sW = g.Cin; pg.sH = (long long)g.iW * g.Cin; pg.sD = (long long)g.iH * g.iW * g.Cin; pg.sB = g.inS * g.Cin; }
   else { pg.sW = 1; pg.sH = g.iW; pg.sD = (long long)g.iH * g.iW; pg.sC = g.inS; pg.sB = g.inS * g.Cin; }
@@ -2103,12 +2106,6 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
   // ---- dW ----
-  if (P.maxshift > 0) {
-    const int tail = (int)(P.PRS - P.r_lead - P.PR);
-    zero_r_pads_kernel<<<ew_grid((long long)P.C8 * (P.r_lead + tail)), 256, 0, st>>>(rp0, P.d_HL == 2 ? rp1 : nullptr, P.C8, P.PRS,
-                                                                                   P.r_lead, P.PR, tail);
-    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-  }
   HEBB_TRY(launch_dw(P, g, xp0, xp1, rp0, rp1, hpart, err, P.PA, P.PRS, st));
   {
     const long long n = (long long)g.taps * g.Cin * g.Cout;

@@ -73,6 +73,20 @@ def test_planner_keeps_single_wave_and_tiles_every_c4_layer():
         assert _native.plan(_desc3(8, cin, cout, sp, k=2, transposed=True), _native.PREC_BF16X3) is not None
 
 
+def test_planner_collector_reuse_cases_are_the_ones_the_gpu_tests_run():
+    """The contraction kernel has two loop orders (tap outer / k-step outer with A-operand collector re-use).  The
+    GPU parity cases named *_run6 / *_run9 exist to exercise the second one in both precision modes: pin that the
+    planner really picks it for them, and that the full-size 64 -> 64 layer of the 3-D network uses it."""
+    for cin, cout, sp in ((64, 64, (16, 16, 16)), (128, 32, (10, 10, 10))):
+        for prec in (_native.PREC_BF16X3, _native.PREC_BF16):
+            p = _native.plan(_desc3(1, cin, cout, sp), prec)
+            assert p is not None and p['reuse'] == 1, (cin, cout, prec, p)
+    p = _native.plan(_desc3(8, 64, 64, (96, 96, 80)), _native.PREC_BF16)
+    assert p['reuse'] == 1 and p['nrep'] == 2 and p['by_kh'] == 0
+    # wide response tiles are math-bound: no re-use
+    assert _native.plan(_desc3(8, 128, 128, (48, 48, 40)), _native.PREC_BF16)['reuse'] == 0
+
+
 def test_no_cpu_fallback():
     layer = hebb.HebbianConv2d(3, 8, 3, padding=1, alpha=1.)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
