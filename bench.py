@@ -418,6 +418,14 @@ def run_ours(args):
                             note=f'algorithmic 2*P*Cout*K flops of the {len(tc_rows)} tensor-core layers / summed CUDA-event time of that '
                                  f'stage ({args.prec}: {"3 MMAs per product" if (args.prec == "bf16x3" or dom == "fwd") else "1 MMA per product"})',
                             stage_ms=tot)
+                # both contractions against the tensor peak, and the whole Hebbian stage against HBM (the small-channel
+                # layers are bandwidth-bound: SURVEY.md 8d) -- algorithmic bytes = x once + y once + 3 x weights
+                roof['per_stage'] = {k: dict(achieved=fl / (tot[k] / 1e3) / 1e12, frac=fl / (tot[k] / 1e3) / 1e12 / pk['tf'])
+                                     for k in ('fwd', 'dw') if tot.get(k)}
+                by = sum(r['bytes_min'] for r in tc_rows)
+                t_all = sum(tot.values())
+                roof['hbm_view'] = dict(algorithmic_bytes=by, achieved=by / (t_all / 1e3) / 1e9, peak=pk['hbm'], unit='GB/s',
+                                        frac=by / (t_all / 1e3) / 1e9 / pk['hbm'], stage_ms_total=t_all)
             else:
                 by = sum(4.0 * torch.tensor(r['x']).prod().item() * 1.5 for r in tc_rows)
                 ach = by / (tot[dom] / 1e3) / 1e9

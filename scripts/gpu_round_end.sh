@@ -26,6 +26,10 @@ for P in bf16x3 bf16; do
 python scripts/profile_layer.py 128 128 3 48 40 8 $P 48 > gpurun_out/pl_$P.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'dw_swta|fwd_swta' -s 6 -c 2 -o gpurun_out/prof_c4_128x128_$P python scripts/profile_layer.py 128 128 3 48 40 8 $P 48 > gpurun_out/ncu_$P.log 2>&1; echo "ncu $P rc=$?"; cat gpurun_out/pl_$P.log
 done
+# shared-memory-bound layer of the 3-D network: 64->64 3x3x3 @96x96x80, batch 8, bf16 (k-step-outer loop, A collector re-use)
+python scripts/profile_layer.py 64 64 3 96 80 8 bf16 96 > gpurun_out/pl_c4_64.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'dw_swta' -s 3 -c 1 -o gpurun_out/prof_c4_64x64_bf16 python scripts/profile_layer.py 64 64 3 96 80 8 bf16 96 > gpurun_out/ncu_c4_64.log 2>&1; echo "ncu c4 64 rc=$?"
+python scripts/umma_rate3.py > gpurun_out/umma_rate3.txt 2>&1; echo "rate3 rc=$?"
 # small-channel layer of the 2-D network: 16->16 3x3 @256x256, batch 64
 python scripts/profile_layer.py 16 16 3 256 256 64 bf16x3 > gpurun_out/pl_c2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'dw_swta|fwd_swta|pack_x' -s 9 -c 3 -o gpurun_out/prof_c2_16x16 python scripts/profile_layer.py 16 16 3 256 256 64 bf16x3 > gpurun_out/ncu_c2.log 2>&1; echo "ncu c2 rc=$?"
