@@ -2168,12 +2168,14 @@ umma_probe_kernel(const uint8_t* __restrict__ a_img, int a_bytes, const uint8_t*
   __shared__ uint64_t bar;
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t sa = smem_u32(smem);
+  // both images start on 1024-byte boundaries of the shared-memory window (the swizzled layouts repeat every 1024 B)
+  uint8_t* const base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  const uint32_t sa = smem_u32(base);
   const uint32_t b_off = (uint32_t)((a_bytes + 1023) / 1024 * 1024);
   for (int i = threadIdx.x; i < a_bytes / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+    reinterpret_cast<uint4*>(base)[i] = reinterpret_cast<const uint4*>(a_img)[i];
   for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem + b_off)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+    reinterpret_cast<uint4*>(base + b_off)[i] = reinterpret_cast<const uint4*>(b_img)[i];
   fence_proxy_async();
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
   const uint32_t cols = pow2_cols(n);
@@ -2311,7 +2313,7 @@ extern "C" int hebb_debug_umma_probe(const void* a_img, int a_bytes, const void*
   HEBB_TRY(device_ok());
   if (!a_img || !b_img || !d_out) return HEBB_EARG;
   if (a_bytes % 16 || b_bytes % 16 || n % 8 || n < 8 || n > 256 || (m != 64 && m != 128)) return HEBB_ESHAPE;
-  const size_t smem = (size_t)((a_bytes + 1023) / 1024 * 1024) + b_bytes + 1024;
+  const size_t smem = (size_t)((a_bytes + 1023) / 1024 * 1024) + b_bytes + 2048;
   if (smem > (size_t)kSmemLimit) return HEBB_ESHAPE;
   HEBB_CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
