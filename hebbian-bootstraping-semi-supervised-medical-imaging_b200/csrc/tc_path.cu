@@ -37,6 +37,15 @@ using namespace ptx;
 constexpr int kMaxTaps = 27;
 constexpr int kSmemLimit = 227 * 1024;
 
+// Index (in 16-byte vectors) of the 8-channel group g8 of packed position pp in the response planes.
+// rsw = 0: planes of 8 channels, one vector per position.  rsw = 1: planes of 64 channels, 128 bytes per position,
+// the 16-byte chunks XOR-ed with (position % 8) -- the MN-major SWIZZLE_128B image that the dW kernel's B operand
+// reads with a ONE-position atom stride, so that an N = 192 instruction covers the three taps of a kernel row
+// without staging shifted copies (tests/test_umma_probe.py pins that descriptor behaviour).
+__device__ __forceinline__ long long r_index(int rsw, long long PRS, int g8, long long pp) {
+  return rsw ? (((long long)(g8 >> 3) * PRS + pp) * 8 + ((g8 & 7) ^ (int)(pp & 7))) : ((long long)g8 * PRS + pp);
+}
+
 // -------------------------------------------------------------------------------------
 // Packing kernels
 // -------------------------------------------------------------------------------------
@@ -47,7 +56,8 @@ struct PackGeo {
   long long sB, sC, sD, sH, sW;   // element strides of x (NCHW: sC = inS, sW = 1; channels_last: sC = 1, sW = C)
   // zero pads of the packed responses (written here so the step needs no extra launch): in each of the C8 planes
   // of Rp, r_lead positions before and r_tail positions after the PR the forward pass writes; r_lead + r_tail = 0: none
-  uint4* rhi; uint4* rlo; int C8, r_lead, r_tail; long long PR, PRS;
+  // r_ushift = 0: C8 planes of one vector per position; 3: C8/8 planes of 8 vectors per position (see r_index)
+  uint4* rhi; uint4* rlo; int C8, r_lead, r_tail, r_ushift; long long PR, PRS;
 };
 
 __global__ void __launch_bounds__(256, 8)
@@ -88,15 +98,17 @@ pack_x_kernel(const float* __restrict__ x, uint4* __restrict__ xhi, uint4* __res
     xhi[idx] = make_uint4(h[0], h[1], h[2], h[3]);
     if (xlo) xlo[idx] = make_uint4(l[0], l[1], l[2], l[3]);
   }
-  // zero pads of Rp: one block per 8-channel plane, no divisions (keeps the kernel at 32 registers per thread)
-  const int per = g.r_lead + g.r_tail;
-  for (int c8 = blockIdx.x; c8 < g.C8 && per > 0; c8 += gridDim.x) {
-    uint4* ph = g.rhi + (long long)c8 * g.PRS;
-    uint4* pl = g.rlo ? g.rlo + (long long)c8 * g.PRS : nullptr;
+  // zero pads of Rp: one block per plane, no divisions (keeps the kernel at 32 registers per thread)
+  const int per = (g.r_lead + g.r_tail) << g.r_ushift;
+  const int planes = g.C8 >> g.r_ushift;
+  for (int pl = blockIdx.x; pl < planes && per > 0; pl += gridDim.x) {
+    uint4* ph = g.rhi + (((long long)pl * g.PRS) << g.r_ushift);
+    uint4* plo = g.rlo ? g.rlo + (((long long)pl * g.PRS) << g.r_ushift) : nullptr;
+    const int nlead = g.r_lead << g.r_ushift;
     for (int i = threadIdx.x; i < per; i += blockDim.x) {
-      const long long off = i < g.r_lead ? (long long)(i - g.r_lead) : g.PR + (i - g.r_lead);
+      const long long off = i < nlead ? (long long)(i - nlead) : (g.PR << g.r_ushift) + (i - nlead);
       ph[off] = make_uint4(0, 0, 0, 0);
-      if (pl) pl[off] = make_uint4(0, 0, 0, 0);
+      if (plo) plo[off] = make_uint4(0, 0, 0, 0);
     }
   }
 }
@@ -332,6 +344,7 @@ struct FwdParams {
   int RHL;                     // 1: r is consumed as single bf16 (hi only), 2: hi + lo
   long long PA, PR, PTOT;      // positions per chunk plane in Xp; packed output positions; real positions B*Qimg
   long long PRS;               // positions between the 8-channel planes of Rp (PR + the zero pads the dW kernel reads)
+  int rsw;                     // responses in the 64-channel swizzled layout (see r_index)
   int MB, TILE_M, ntiles, SEGLEN;
   int XST, WST, NACC, WG;      // WG: taps per weight stage (one bulk copy)
   int WP, plane, Qimg, oD, oH, oW;
@@ -697,7 +710,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                 }
               }
               if (p.dbg & 8) continue;
-              const long long ridx = (long long)g8 * p.PRS + pp;
+              const long long ridx = r_index(p.rsw, p.PRS, g8, pp);
               p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
               if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
             }
@@ -765,7 +778,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                   ol4[i] = pack_bf16x2(l0, l1);
                 }
                 if (p.dbg & 8) continue;
-                const long long ridx = (long long)((cbase + c0) / 8 + g8) * p.PRS + pp;
+                const long long ridx = r_index(p.rsw, p.PRS, (cbase + c0) / 8 + g8, pp);
                 p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
                 if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
               }
@@ -848,7 +861,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                   oh4[i] = pack_bf16x2(h2[0], h2[1]);
                   ol4[i] = pack_bf16x2(l2[0], l2[1]);
                 }
-                const long long ridx = (long long)(c0 / 8 + g8) * p.PRS + pp;
+                const long long ridx = r_index(p.rsw, p.PRS, c0 / 8 + g8, pp);
                 if (p.dbg & 8) continue;
                 p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
                 if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
@@ -891,7 +904,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                 oh4[i] = pack_bf16x2(h2[0], h2[1]);
                 ol4[i] = pack_bf16x2(l2[0], l2[1]);
               }
-              const long long ridx = (long long)(c0 / 8 + g8) * p.PRS + pp;
+              const long long ridx = r_index(p.rsw, p.PRS, c0 / 8 + g8, pp);
               if (pp < p.PR && !(p.dbg & 8)) {
                 p.rp[0][ridx] = make_uint4(oh4[0], oh4[1], oh4[2], oh4[3]);
                 if (p.RHL == 2) p.rp[1][ridx] = make_uint4(ol4[0], ol4[1], ol4[2], ol4[3]);
@@ -1205,6 +1218,11 @@ struct DwParams {
   // st_boff: where the B operand of a super-tap starts inside the staged r tile (positions).
   int nrep; int grp_st_begin[10]; int st_boff[kMaxTaps]; int st_first[kMaxTaps]; int st_n[kMaxTaps];
   int rhalo;                    // the staged r tile starts rhalo + grp_base positions before the x tile
+  // replicas of the x tile are rep_stride positions apart and tap_rep taps apart (1 / 1: kw neighbours; rsw: WP / kW)
+  int rep_stride, tap_rep; int st_aoff[kMaxTaps];           // st_aoff: A start of a super-tap inside the x region (16 B units)
+  // rsw: responses staged as the 64-channel swizzled image; ONE instruction reads ncopy position-shifted copies of
+  // the tile (N = 64 * ncopy: the kW taps of a kernel row); b_rows staged rows, fetched from an 8-aligned start
+  int rsw, ncopy, b_rows, r_lead;
   int reuse;                    // 1: k-step outer / tap inner with A collector re-use; 0: tap outer, one A fetch per MMA
   int CM, n_cin_tiles, CN, n_cout_tiles, ST, CinP;
   int stackM, stackN, cpt;      // bf16x3 "precision stacking": [x_hi; x_lo] along M and/or [r_hi | r_lo] along N, so one
@@ -1268,7 +1286,7 @@ __device__ __forceinline__ void dw_kstep(int n, uint32_t d, int colw, uint32_t a
 template <int MODE, int ACC0, int REUSE>
 __device__ __forceinline__ void dw_issue(const DwParams& p, uint32_t xa, uint32_t ra, int st_b, int st_e, uint32_t tmem_base,
                                          int colw, int ksteps, uint32_t a_lbo, uint32_t a_hi32, uint32_t b_lbo,
-                                         uint32_t b_hi32, uint32_t idesc, uint32_t xhl16, uint32_t rhl16) {
+                                         uint32_t b_hi32, uint32_t idesc, uint32_t xhl16, uint32_t rhl16, uint32_t bstep) {
   uint32_t ah = a_lbo | (xa >> 4);
   uint32_t bks = b_lbo | (ra >> 4);
   uint32_t bo[kMaxRun];
@@ -1278,7 +1296,7 @@ __device__ __forceinline__ void dw_issue(const DwParams& p, uint32_t xa, uint32_
     for (int j = 0; j < kMaxRun; ++j) bo[j] = (j < n) ? (uint32_t)p.st_boff[st_b + j] : 0u;
     dw_kstep<MODE, ACC0>(n, tmem_base, colw, ah, a_hi32, bks, b_hi32, idesc, xhl16, rhl16, bo);
     for (int ks = 1; ks < ksteps; ++ks) {
-      ah += 16u; bks += 16u;                     // next 16 positions: 256 bytes in both operands
+      ah += 16u; bks += bstep;                   // next 16 positions: 256 bytes (2048 in the swizzled response image)
       dw_kstep<MODE, 1>(n, tmem_base, colw, ah, a_hi32, bks, b_hi32, idesc, xhl16, rhl16, bo);
     }
   } else {
@@ -1286,10 +1304,10 @@ __device__ __forceinline__ void dw_issue(const DwParams& p, uint32_t xa, uint32_
     for (int j = 0; j < kMaxRun; ++j) bo[j] = 0u;
     uint32_t d = tmem_base;
     for (int stp = st_b; stp < st_e; ++stp, d += colw) {
-      uint32_t a = ah, b = bks + (uint32_t)p.st_boff[stp];
+      uint32_t a = ah + (uint32_t)p.st_aoff[stp], b = bks + (uint32_t)p.st_boff[stp];
       dw_kstep<MODE, ACC0>(1, d, colw, a, a_hi32, b, b_hi32, idesc, xhl16, rhl16, bo);
       for (int ks = 1; ks < ksteps; ++ks) {
-        a += 16u; b += 16u;
+        a += 16u; b += bstep;
         dw_kstep<MODE, 1>(1, d, colw, a, a_hi32, b, b_hi32, idesc, xhl16, rhl16, bo);
       }
     }
@@ -1298,7 +1316,9 @@ __device__ __forceinline__ void dw_issue(const DwParams& p, uint32_t xa, uint32_
 
 __global__ void __launch_bounds__(192, 1)
 dw_swta_kernel(const __grid_constant__ DwParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // stages start on 1024-byte boundaries of the shared-memory window: the swizzled response image repeats every 1024 B
+  uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -1316,8 +1336,8 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   const int cm_chunks = min(p.cpt, p.CC - cin_tile * p.cpt);
   const int N = min(p.CN, p.Cout - cout_tile * p.CN);
   const int rn_chunks = N / 8;
-  const int Neff = p.stackN ? 2 * N : N;
-  const int colw = (p.stackN ? 2 : 1) * p.CN;        // TMEM columns per tap
+  const int Neff = p.rsw ? p.ncopy * N : (p.stackN ? 2 * N : N);
+  const int colw = p.rsw ? p.ncopy * p.CN : (p.stackN ? 2 : 1) * p.CN;        // TMEM columns per super-tap
   const int st_b = p.grp_st_begin[grp], st_e = p.grp_st_begin[grp + 1];
   const int blk_b = min(split * p.blocks_per_split, p.total_blocks);
   const int blk_e = min(blk_b + p.blocks_per_split, p.total_blocks);
@@ -1340,7 +1360,8 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   if (warp == 0) {
     if (elect_one()) {
       int st = 0; uint32_t ph = 0;
-      const uint32_t bytes = p.HL * (p.nrep * cm_chunks * p.BLK + rn_chunks * p.SEGLEN) * 16;
+      const uint32_t bytes = p.rsw ? (uint32_t)(p.nrep * cm_chunks * p.BLK * 16 + p.b_rows * 128)
+                                   : p.HL * (p.nrep * cm_chunks * p.BLK + rn_chunks * p.SEGLEN) * 16;
       const long long r_back = (long long)p.grp_base[grp] + p.rhalo;      // the r tile starts this far before the x tile
       for (int blk = blk_b; blk < blk_e; ++blk) {
         const long long q0 = (long long)blk * p.BLK;
@@ -1351,11 +1372,19 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
           for (int rep = 0; rep < p.nrep; ++rep)
             for (int c = 0; c < cm_chunks; ++c)
               bulk_g2s(dst + rep * x_rep_stride + hl * x_hl_stride + c * p.BLK * 16,
-                       p.xp[hl] + (long long)(cin_tile * p.cpt + c) * p.PA + q0 + rep, p.BLK * 16, full + 8 * st);
-          for (int c = 0; c < rn_chunks; ++c)
-            bulk_g2s(dst + r_off + hl * r_hl_stride + c * p.SEGLEN * 16,
-                     p.rp[hl] + (long long)(cout_tile * (p.CN / 8) + c) * p.PRS + q0 - r_back, p.SEGLEN * 16,
-                     full + 8 * st);
+                       p.xp[hl] + (long long)(cin_tile * p.cpt + c) * p.PA + q0 + (long long)rep * p.rep_stride,
+                       p.BLK * 16, full + 8 * st);
+          if (p.rsw) {
+            // one copy: b_rows whole positions (128 B each) of this 64-channel plane, from an 8-aligned row so the
+            // staged image keeps the swizzle phase of the global one (r_lead and q0 are multiples of 8)
+            const long long r0a = ((q0 - r_back + p.r_lead) & ~7LL) - p.r_lead;
+            bulk_g2s(dst + r_off, p.rp[0] + ((long long)cout_tile * p.PRS + r0a) * 8, p.b_rows * 128, full + 8 * st);
+          } else {
+            for (int c = 0; c < rn_chunks; ++c)
+              bulk_g2s(dst + r_off + hl * r_hl_stride + c * p.SEGLEN * 16,
+                       p.rp[hl] + (long long)(cout_tile * (p.CN / 8) + c) * p.PRS + q0 - r_back, p.SEGLEN * 16,
+                       full + 8 * st);
+          }
         }
         if (++st == p.ST) { st = 0; ph ^= 1; }
       }
@@ -1364,7 +1393,11 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
     {
       const uint32_t idesc = idesc_bf16(p.CM, Neff, 1, 1);
       const uint64_t a_hi64 = smem_desc_hi(128, p.BLK * 16);      // MN-major: LBO = next 8 positions, SBO = next chunk
-      const uint64_t b_hi64 = smem_desc_hi(128, p.SEGLEN * 16);
+      // rsw: MN-major SWIZZLE_128B (layout type 2), 8-position groups 1024 B apart, 64-channel atoms ONE position apart
+      const uint64_t b_hi64 = p.rsw ? (smem_desc_hi(128, 1024) | (2ull << 61)) : smem_desc_hi(128, p.SEGLEN * 16);
+      const uint32_t bstep = p.rsw ? 128u : 16u;
+      // first staged row = (q0 - r_back) rounded down to a multiple of 8: the B operand starts r_rem rows further
+      const uint32_t r_rem = p.rsw ? (uint32_t)(((long long)blk_b * p.BLK - p.grp_base[grp] - p.rhalo + p.r_lead) & 7LL) : 0u;
       const uint32_t a_lbo = (uint32_t)a_hi64, a_hi32 = (uint32_t)(a_hi64 >> 32);
       const uint32_t b_lbo = (uint32_t)b_hi64, b_hi32 = (uint32_t)(b_hi64 >> 32);
       const uint32_t xhl16 = x_hl_stride >> 4, rhl16 = r_hl_stride >> 4;
@@ -1376,14 +1409,14 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
         mbar_wait(full + 8 * st, ph, p.err, 12);
         tc_fence_after();
         const uint32_t xa = sbase + st * p.stage_bytes;
-        const uint32_t ra = xa + r_off;
+        const uint32_t ra = xa + r_off + r_rem * 128u;
         if (elect_one()) {
           const bool first = (blk == blk_b);
 #define HEBB_DW_ISSUE(M, R)                                                                                               \
           (first ? dw_issue<M, 0, R>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc,  \
-                                     xhl16, rhl16)                                                                        \
+                                     xhl16, rhl16, bstep)                                                                 \
                  : dw_issue<M, 1, R>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc,  \
-                                     xhl16, rhl16))
+                                     xhl16, rhl16, bstep))
           switch (sel) {
             case 0: HEBB_DW_ISSUE(1, 0); break;
             case 1: HEBB_DW_ISSUE(1, 1); break;
@@ -1424,16 +1457,19 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
     const int Q = (p.stackM ? 2 : 1) * (p.stackN ? 2 : 1);
     for (int stp = st_b; stp < st_e; ++stp) {
       const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (stp - st_b) * colw;
-      const int tap = p.st_first[stp] + rep;
+      const int tap0 = p.st_first[stp] + rep * p.tap_rep;
       const bool tap_ok = st_ok && rep < p.st_n[stp];
       for (int c0 = 0; c0 < Neff; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(ta + c0, v);
         tmem_ld_wait();
-        const int col_lo = (p.stackN && c0 >= N) ? 1 : 0;
+        // rsw: column block j holds the tile shifted by +j positions = tap kw = ncopy-1-j of the kernel row
+        const int jcopy = p.rsw ? c0 / N : 0;
+        const int tap = tap0 + (p.rsw ? p.ncopy - 1 - jcopy : 0);
+        const int col_lo = (!p.rsw && p.stackN && c0 >= N) ? 1 : 0;
         const int quadrant = row_lo * (p.stackN ? 2 : 1) + col_lo;
         float* dst = p.hpart + ((((long long)split * Q + quadrant) * p.taps + tap) * p.CinP + ci) * p.Cout +
-                     cout_tile * p.CN + (c0 - col_lo * N);
+                     cout_tile * p.CN + (c0 - (p.rsw ? jcopy : col_lo) * N);
         if (tap_ok) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -1574,6 +1610,10 @@ struct Plan {
   int d_HL, BLK, d_SEGLEN, d_by_kh, ngrp, CM, n_cin_tiles, CN, n_cout_tiles, PS, total_blocks, blocks_per_split, ST, CinP;
   int stackM, stackN, cpt, Q, nrep, rhalo, reuse;
   long long PRS; int r_lead;      // Rp plane: r_lead zero positions, PR packed responses, zero tail (PRS in all)
+  // swizzled-response variant of the dW kernel (bf16 operands, 64 response channels, 3-wide kernel rows): its own
+  // tiling, chosen per call (the weight-gradient and HPCA calls keep the plain layout); 0 = not available
+  int rsw, rs_BLK, rs_ST, rs_nrep, rs_by_kh, rs_cpt, rs_n_cin, rs_CinP, rs_PS, rs_total_blocks, rs_blocks_per_split, rs_b_rows;
+  uint32_t rs_stage, rs_x_bytes, rs_off_bar, rs_smem, rs_tmem;
   uint32_t d_stage, d_x_bytes, d_off_bar, d_smem, d_tmem;
   // workspace carve (byte offsets)
   size_t o_inv, o_rsum, o_err, o_xp[2], o_rp[2], o_wp, o_hpart, o_gram, o_hpart2, total;
@@ -1793,16 +1833,47 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   q.n_cout_tiles = (int)cdiv(g.Cout, q.CN);
   q.d_tmem = pow2_cols((q.d_by_kh ? 1 : g.kH) * (int)cdiv(g.kW, q.nrep) * q.CN * (q.stackN ? 2 : 1));
 
+  // ---------------- dW, swizzled-response variant ----------------
+  // Layers with 64 response channels are bound by shared-memory bandwidth (one 4 KB A fetch per 32 cycles of math).
+  // With the responses stored as [position][64 channels] (SWIZZLE_128B image) the B descriptor's atom stride can be
+  // ONE position, so a single N = 192 instruction computes the three taps of a kernel row from one staged tile.
+  // Cin = 64: three kh-shifted replicas of the x tile (rows of M), tap groups = kd planes; Cin = k*128: tap groups =
+  // kernel rows, 128-channel tiles.
+  static const int want_rsw = [] { const char* e = getenv("HEBB_DW_RSW"); return (e && e[0] == '0') ? 0 : 1; }();
+  q.rsw = 0; q.rs_BLK = 0;
+  if (want_rsw && prec == HEBB_PREC_BF16 && !gram && !trq && g.Cout == 64 && q.n_ct == 1 && g.kW == 3 && g.kH == 3 &&
+      (g.Cin == 64 || g.Cin % 128 == 0)) {
+    const bool rep3 = g.Cin == 64;
+    q.rs_nrep = rep3 ? 3 : 1; q.rs_by_kh = rep3 ? 0 : 1; q.rs_cpt = rep3 ? 8 : 16;
+    q.rs_n_cin = rep3 ? 1 : g.Cin / 128; q.rs_CinP = g.Cin;
+    q.rs_BLK = rep3 ? 128 : 256; q.rs_ST = rep3 ? 3 : 2;
+    q.rs_b_rows = round_up_i(q.rs_BLK + (g.kW - 1) + 7, 8);
+    q.rs_x_bytes = (uint32_t)q.rs_nrep * q.rs_cpt * q.rs_BLK * 16;
+    q.rs_stage = q.rs_x_bytes + (uint32_t)q.rs_b_rows * 128;
+    // the last A descriptor (rep3: start at replica 2, spanning 16 chunks) must stay inside the allocation
+    const uint64_t ring = (uint64_t)q.rs_ST * q.rs_stage;
+    const uint64_t last_read = (uint64_t)(q.rs_ST - 1) * q.rs_stage + (rep3 ? 2ull * 8 * q.rs_BLK * 16 : 0ull) +
+                               16ull * q.rs_BLK * 16 + 256;
+    uint64_t tot = ring > last_read ? ring : last_read;
+    tot = (tot + 1023) / 1024 * 1024 + 8 * 16 + 64;
+    q.rs_off_bar = (uint32_t)(tot - (8 * 16 + 64)); q.rs_smem = (uint32_t)tot;
+    q.rs_tmem = pow2_cols((rep3 ? 2 : 1) * 64 * g.kW);
+    if (q.rs_stage % 1024 == 0 && q.rs_x_bytes % 1024 == 0 && tot <= (uint64_t)kSmemLimit - 1024 && q.rs_tmem <= 512) q.rsw = 1;
+  }
+
   // packed position space: multiples of both tile sizes
   // (a Gram plan runs over another plan's PR positions: its stage size divides them, see the search above)
-  const int big = gram ? q.BLK : (q.TILE_M > q.BLK ? q.TILE_M : q.BLK);
+  int big = gram ? q.BLK : (q.TILE_M > q.BLK ? q.TILE_M : q.BLK);
+  if (q.rsw && q.rs_BLK > big) big = q.rs_BLK;
   q.PR = (q.PTOT + big - 1) / big * big;
   // the contraction pairs x[q] with r[q - shift]: its position blocks run over q in [0, PTOT + maxshift), so the
   // x planes extend that far (zeros) and the r planes carry zero pads of maxshift positions on both sides
   q.total_blocks = (int)cdiv(q.PTOT + q.maxshift, q.BLK);
-  q.PA = (q.PR + q.maxshift + q.BLK + 16 + 7) / 8 * 8;
+  const int blk_max = (q.rsw && q.rs_BLK > q.BLK) ? q.rs_BLK : q.BLK;
+  // rsw: the x replicas reach (nrep-1)*WP positions past a block
+  q.PA = (q.PR + q.maxshift + blk_max + (q.rsw ? (q.rs_nrep - 1) * q.WP : 0) + 16 + 7) / 8 * 8;
   q.r_lead = (q.maxshift + 7) / 8 * 8;
-  q.PRS = q.r_lead + ((q.PR + q.maxshift + q.BLK + 16 + 7) / 8 * 8);
+  q.PRS = q.r_lead + ((q.PR + q.maxshift + blk_max + 16 + 7) / 8 * 8);
   q.f_ntiles = (int)(q.PR / q.TILE_M);
   const int out_tiles = q.ngrp * q.n_cin_tiles * q.n_cout_tiles;
   // one wave: never more CTAs than SMs (a 149th CTA would double the kernel's duration)
@@ -1811,6 +1882,15 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   if (ps < 1) ps = 1;
   q.blocks_per_split = (int)cdiv(q.total_blocks, ps);
   q.PS = (int)cdiv(q.total_blocks, q.blocks_per_split);
+  if (q.rsw) {
+    q.rs_total_blocks = (int)cdiv(q.PTOT + q.maxshift, q.rs_BLK);
+    const int rs_tiles = (q.rs_by_kh ? g.kD * g.kH : g.kD) * q.rs_n_cin;
+    int rps = sms / rs_tiles;
+    if (rps > q.rs_total_blocks) rps = q.rs_total_blocks;
+    if (rps < 1) rps = 1;
+    q.rs_blocks_per_split = (int)cdiv(q.rs_total_blocks, rps);
+    q.rs_PS = (int)cdiv(q.rs_total_blocks, q.rs_blocks_per_split);
+  }
 
   // ---------------- workspace ----------------
   size_t off = 0;
@@ -1823,7 +1903,11 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   q.o_rp[0] = take((size_t)q.C8 * q.PRS * 16);
   q.o_rp[1] = take((size_t)q.C8 * q.PRS * 16);
   q.o_wp = take((size_t)q.NSLAB * g.taps * q.f_HL * 2 * g.Cout * 16);
-  q.o_hpart = take((size_t)q.PS * q.Q * g.taps * q.CinP * g.Cout * sizeof(float));
+  {
+    size_t hp = (size_t)q.PS * q.Q * g.taps * q.CinP * g.Cout * sizeof(float);
+    const size_t hp2 = q.rsw ? (size_t)q.rs_PS * g.taps * q.rs_CinP * g.Cout * sizeof(float) : 0;
+    q.o_hpart = take(hp > hp2 ? hp : hp2);
+  }
   q.gram_ok = false; q.o_gram = q.o_hpart2 = 0;
   if (!gram && !trq) {
     // HPCA (hebb.py:122-135) also needs G = y y^T: the same contraction kernel over the packed responses,
@@ -1889,7 +1973,7 @@ int tc_describe_plan(const Geo& g0, int prec, int* o, int n) {
   const int v[] = {P.MB, P.f_SEGLEN, P.XST, P.WST, P.NACC, (int)P.f_tmem, P.f_ntiles, (int)P.f_smem,
                    P.d_by_kh, P.CM, P.CN, P.BLK, P.ST, P.d_SEGLEN, P.ngrp, P.n_cin_tiles, P.n_cout_tiles, P.PS,
                    P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct, P.nrep, P.WG,
-                   P.reuse, P.rhalo};
+                   P.reuse, P.rhalo, P.rsw};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < m; ++i) o[i] = v[i];
   return m;
@@ -1904,17 +1988,52 @@ static unsigned ew_grid(long long n) {
 // Fills the parameter block of the contraction kernel for plan P / geometry g and launches it.  `PA` is the
 // position stride between 8-channel planes of the x operand (P.PA for packed activations).
 static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4* xp1, const uint4* rp0, const uint4* rp1,
-                     float* hpart, int* err, long long PA, long long PRS, cudaStream_t st) {
+                     float* hpart, int* err, long long PA, long long PRS, cudaStream_t st, bool rsw = false) {
   DwParams d;
   d.xp[0] = xp0; d.xp[1] = xp1; d.rp[0] = rp0; d.rp[1] = rp1; d.hpart = hpart; d.err = err;
   d.Cin = g.Cin; d.Cout = g.Cout; d.CC = P.CC; d.C8 = P.C8; d.taps = g.taps; d.HL = P.d_HL;
-  d.PA = PA; d.PRS = PRS; d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
-  d.rhalo = P.rhalo; d.reuse = P.reuse;
-  d.blocks_per_split = P.blocks_per_split; d.PS = P.PS; d.ngrp = P.ngrp;
+  d.PA = PA; d.PRS = PRS;
   for (int i = 0; i < 9; ++i) d.grp_base[i] = 0;
-  d.nrep = P.nrep;
-  for (int t = 0; t < kMaxTaps; ++t) { d.st_boff[t] = 0; d.st_first[t] = 0; d.st_n[t] = 0; }
-  {
+  for (int t = 0; t < kMaxTaps; ++t) { d.st_boff[t] = 0; d.st_aoff[t] = 0; d.st_first[t] = 0; d.st_n[t] = 0; }
+  d.r_lead = P.r_lead;
+  int dgrid;
+  if (rsw) {
+    // swizzled responses: one N = 64*kW instruction per kernel row (see plan_layer_search)
+    d.rsw = 1; d.ncopy = g.kW; d.b_rows = P.rs_b_rows; d.reuse = 0;
+    d.BLK = P.rs_BLK; d.SEGLEN = P.rs_b_rows; d.total_blocks = P.rs_total_blocks;
+    d.blocks_per_split = P.rs_blocks_per_split; d.PS = P.rs_PS;
+    d.rhalo = g.kW - 1;
+    d.nrep = P.rs_nrep; d.rep_stride = P.WP; d.tap_rep = g.kW;
+    d.ngrp = P.rs_by_kh ? g.kD * g.kH : g.kD;
+    int nst = 0, gi = 0;
+    for (int kd = 0; kd < g.kD; ++kd) {
+      if (!P.rs_by_kh) {
+        // tap group = kd plane; super-tap 0: x replicas 0,1 = kernel rows kh 0,1 (M = 128), super-tap 1: replica 2 = kh 2
+        d.grp_base[gi] = kd * P.plane; d.grp_st_begin[gi] = nst;
+        for (int kh0 = 0; kh0 < g.kH; kh0 += 2, ++nst) {
+          d.st_aoff[nst] = kh0 * (P.rs_cpt * P.rs_BLK);              // replica kh0 starts kh0 * cpt * BLK vectors into the x region
+          d.st_first[nst] = (kd * g.kH + kh0) * g.kW;
+          d.st_n[nst] = (g.kH - kh0 < 2) ? (g.kH - kh0) : 2;
+        }
+        ++gi;
+      } else {
+        for (int kh = 0; kh < g.kH; ++kh, ++gi, ++nst) {
+          d.grp_base[gi] = kd * P.plane + kh * P.WP; d.grp_st_begin[gi] = nst;
+          d.st_first[nst] = (kd * g.kH + kh) * g.kW; d.st_n[nst] = 1;
+        }
+      }
+    }
+    for (int i = gi; i < 10; ++i) d.grp_st_begin[i] = nst;
+    d.stackM = 0; d.stackN = 0; d.cpt = P.rs_cpt;
+    d.CM = 128; d.n_cin_tiles = P.rs_n_cin; d.CN = 64; d.n_cout_tiles = 1; d.ST = P.rs_ST; d.CinP = P.rs_CinP;
+    d.stage_bytes = P.rs_stage; d.x_bytes = P.rs_x_bytes; d.off_bar = P.rs_off_bar; d.tmem_cols = P.rs_tmem;
+    dgrid = d.ngrp * d.n_cin_tiles * P.rs_PS;
+  } else {
+    d.rsw = 0; d.ncopy = 1; d.b_rows = 0; d.rep_stride = 1; d.tap_rep = 1;
+    d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
+    d.rhalo = P.rhalo; d.reuse = P.reuse;
+    d.blocks_per_split = P.blocks_per_split; d.PS = P.PS; d.ngrp = P.ngrp;
+    d.nrep = P.nrep;
     // tap groups (one CTA column set each) -> super-taps (one accumulator column group each) -> taps
     int nst = 0, gi = 0;
     for (int kd = 0; kd < g.kD; ++kd) {
@@ -1931,11 +2050,11 @@ static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4*
       if (!P.d_by_kh) ++gi;
     }
     for (int i = gi; i < 10; ++i) d.grp_st_begin[i] = nst;
+    d.stackM = P.stackM; d.stackN = P.stackN; d.cpt = P.cpt;
+    d.CM = P.CM; d.n_cin_tiles = P.n_cin_tiles; d.CN = P.CN; d.n_cout_tiles = P.n_cout_tiles; d.ST = P.ST; d.CinP = P.CinP;
+    d.stage_bytes = P.d_stage; d.x_bytes = P.d_x_bytes; d.off_bar = P.d_off_bar; d.tmem_cols = P.d_tmem;
+    dgrid = P.ngrp * P.n_cin_tiles * P.n_cout_tiles * P.PS;
   }
-  d.stackM = P.stackM; d.stackN = P.stackN; d.cpt = P.cpt;
-  d.CM = P.CM; d.n_cin_tiles = P.n_cin_tiles; d.CN = P.CN; d.n_cout_tiles = P.n_cout_tiles; d.ST = P.ST; d.CinP = P.CinP;
-  d.stage_bytes = P.d_stage; d.x_bytes = P.d_x_bytes; d.off_bar = P.d_off_bar; d.tmem_cols = P.d_tmem;
-  const int dgrid = P.ngrp * P.n_cin_tiles * P.n_cout_tiles * P.PS;
   HEBB_CUDA_TRY(cudaFuncSetAttribute(dw_swta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   dw_swta_kernel<<<dgrid, 192, kSmemLimit, st>>>(d);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
@@ -1958,8 +2077,8 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   int* err = reinterpret_cast<int*>(base + P.o_err);
   uint4* xp0 = reinterpret_cast<uint4*>(base + P.o_xp[0]);
   uint4* xp1 = reinterpret_cast<uint4*>(base + P.o_xp[1]);
-  uint4* rp0 = reinterpret_cast<uint4*>(base + P.o_rp[0]) + P.r_lead;      // position 0 of the first plane
-  uint4* rp1 = reinterpret_cast<uint4*>(base + P.o_rp[1]) + P.r_lead;
+  uint4* rp0 = reinterpret_cast<uint4*>(base + P.o_rp[0]);
+  uint4* rp1 = reinterpret_cast<uint4*>(base + P.o_rp[1]);
   uint4* wp = reinterpret_cast<uint4*>(base + P.o_wp);
   float* hpart = reinterpret_cast<float*>(base + P.o_hpart);
   // weight-gradient mode (hebb_conv_wgrad): `y` holds dL/dy; only x is packed, dL/dy takes the place of the
@@ -1970,6 +2089,10 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   const bool hpca = (flags & HEBB_F_RULE_HPCA) != 0 && (flags & HEBB_F_UPDATE) != 0;
   if (hpca && (tr || !P.gram_ok)) return HEBB_ESHAPE;
   const bool upd = (flags & HEBB_F_UPDATE) != 0 || wgrad;
+  // swizzled-response variant of the update (forward epilogue writes the layout, the dW kernel reads it)
+  const bool rsw = P.rsw && (flags & HEBB_F_UPDATE) != 0 && !wgrad && !hpca && !tr && g.taps == g0.taps;
+  rp0 += (long long)P.r_lead * (rsw ? 8 : 1);      // position 0 of the first plane (rsw: 8 vectors per position)
+  rp1 += (long long)P.r_lead * (rsw ? 8 : 1);
 
   // profiling aid: HEBB_F_ONLY_* re-run one stage on the scratch left by a preceding full call
   const unsigned only = flags & (HEBB_F_ONLY_PACK | HEBB_F_ONLY_FWD | HEBB_F_ONLY_DW);
@@ -1990,7 +2113,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   // the contraction kernel reads r[q - shift]: zero pads around the packed responses, written by the pack pass
   const bool zpads = upd && P.maxshift > 0;
   pg.rhi = rp0; pg.rlo = P.d_HL == 2 ? rp1 : nullptr; pg.C8 = P.C8; pg.PR = P.PR; pg.PRS = P.PRS;
-  pg.r_lead = zpads ? P.r_lead : 0; pg.r_tail = zpads ? (int)(P.PRS - P.r_lead - P.PR) : 0;
+  pg.r_lead = zpads ? P.r_lead : 0; pg.r_tail = zpads ? (int)(P.PRS - P.r_lead - P.PR) : 0; pg.r_ushift = rsw ? 3 : 0;
   const bool nhwc = wgrad && ((aux >> 16) & 1);         // hebb_conv_wgrad on channels_last tensors
   if (nhwc) { pg.sC = 1; pg.sW = g.Cin; pg.sH = (long long)g.iW * g.Cin; pg.sD = (long long)g.iH * g.iW * g.Cin; pg.sB = g.inS * g.Cin; }
   else { pg.sW = 1; pg.sH = g.iW; pg.sD = (long long)g.iH * g.iW; pg.sC = g.inS; pg.sB = g.inS * g.Cin; }
@@ -2046,7 +2169,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   static const int fwd_dbg = [] { const char* e = getenv("HEBB_FWD_DBG"); return e ? atoi(e) : 0; }();
   f.dbg = fwd_dbg;
   f.stackF = P.stackF; f.CT = P.CT; f.n_ct = P.n_ct; f.fuse = (P.n_ct == 1 || trq) ? 1 : 0;   // transposed: grouped softmax when Cout*8 <= 512
-  f.PA = P.PA; f.PR = P.PR; f.PRS = P.PRS; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
+  f.PA = P.PA; f.PR = P.PR; f.PRS = P.PRS; f.rsw = rsw ? 1 : 0; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
   f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC; f.WG = P.WG;
   f.WP = P.WP; f.plane = P.plane; f.Qimg = P.Qimg; f.oD = g.oD; f.oH = g.oH; f.oW = g.oW;
   f.kinv = kinv; f.write_r = (upd && !hpca) ? 1 : 0;
@@ -2106,7 +2229,9 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
   // ---- dW ----
-  HEBB_TRY(launch_dw(P, g, xp0, xp1, rp0, rp1, hpart, err, P.PA, P.PRS, st));
+  HEBB_TRY(launch_dw(P, g, xp0, xp1, rp0, rp1, hpart, err, P.PA, P.PRS, st, rsw));
+  const int n_part = rsw ? P.rs_PS : P.PS * P.Q;           // partial planes the finalize pass sums
+  const int cin_p = rsw ? P.rs_CinP : P.CinP;
   {
     const long long n = (long long)g.taps * g.Cin * g.Cout;
     if (tr)
@@ -2116,7 +2241,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
       tc_finalize_T_kernel<<<(unsigned)(gx > cap ? cap : gx), 256, 0, st>>>(hpart, rsum, W, delta_w, P.PS * P.Q, g0.Cin, P.CinP, g0.Cout, trq);
     }
     else
-    if (n >= (1LL << 18) && P.PS * P.Q <= 32) {
+    if (n >= (1LL << 18) && n_part <= 32) {
       const float* rs = (wgrad || hpca) ? nullptr : rsum;
 #define HEBB_FIN_LAUNCH(T)                                                                                              \
       do {                                                                                                              \
@@ -2124,8 +2249,8 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
         const int fin_smem = T * (T + 1) * (int)sizeof(float);                                                          \
         HEBB_CUDA_TRY(cudaFuncSetAttribute(tc_finalize_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                            fin_smem));                                                                  \
-        tc_finalize_tiled_kernel<T><<<fg, 256, fin_smem, st>>>(hpart, rs, W, delta_w, P.PS * P.Q, g.taps, g.Cin,        \
-                                                               P.CinP, g.Cout);                                         \
+        tc_finalize_tiled_kernel<T><<<fg, 256, fin_smem, st>>>(hpart, rs, W, delta_w, n_part, g.taps, g.Cin,             \
+                                                               cin_p, g.Cout);                                          \
       } while (0)
       if (n >= (1LL << 22)) HEBB_FIN_LAUNCH(128); else if (n >= (1LL << 20)) HEBB_FIN_LAUNCH(64); else HEBB_FIN_LAUNCH(32);
 #undef HEBB_FIN_LAUNCH
@@ -2133,7 +2258,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
       long long gx = cdiv(n, 32);
       const long long cap = (long long)num_sms() * 32;
       if (gx > cap) gx = cap;
-      tc_finalize_kernel<<<(unsigned)gx, 256, 0, st>>>(hpart, (wgrad || hpca) ? nullptr : rsum, W, delta_w, P.PS * P.Q, g.taps, g.Cin, P.CinP, g.Cout);
+      tc_finalize_kernel<<<(unsigned)gx, 256, 0, st>>>(hpart, (wgrad || hpca) ? nullptr : rsum, W, delta_w, n_part, g.taps, g.Cin, cin_p, g.Cout);
     }
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }

@@ -277,7 +277,7 @@ def local_update_multi(grads, dws, alphas, has_grad):
 
 
 PLAN_FIELDS = ['MB', 'f_SEGLEN', 'XST', 'WST', 'NACC', 'f_tmem', 'f_tiles', 'f_smem', 'by_kh', 'CM', 'CN', 'BLK', 'ST',
-               'd_SEGLEN', 'ngrp', 'n_cin', 'n_cout', 'PS', 'blocks', 'd_tmem', 'd_smem', 'd_HL', 'ws_MiB', 'stackM', 'stackN', 'CT', 'n_ct', 'nrep', 'WG', 'reuse', 'rhalo']
+               'd_SEGLEN', 'ngrp', 'n_cin', 'n_cout', 'PS', 'blocks', 'd_tmem', 'd_smem', 'd_HL', 'ws_MiB', 'stackM', 'stackN', 'CT', 'n_ct', 'nrep', 'WG', 'reuse', 'rhalo', 'rsw']
 
 
 def plan(desc: HebbDesc, prec: int):
