@@ -1223,6 +1223,9 @@ struct DwParams {
   // rsw: responses staged as the 64-channel swizzled image; ONE instruction reads ncopy position-shifted copies of
   // the tile (N = 64 * ncopy: the kW taps of a kernel row); b_rows staged rows, fetched from an 8-aligned start
   int rsw, ncopy, b_rows, r_lead;
+  // tap groups may carry different numbers of taps: group g is split grp_w[g] * (grid / virtual tiles) ways over the
+  // positions, so that every CTA issues the same number of instructions.  Virtual tile v = (vt_grp[v], vt_w[v]).
+  int n_vt, vt_grp[2 * 9], vt_w[2 * 9], grp_w[9], blocks_per_split2;       // blocks_per_split2: for groups of weight 2
   int reuse;                    // 1: k-step outer / tap inner with A collector re-use; 0: tap outer, one A fetch per MMA
   int CM, n_cin_tiles, CN, n_cout_tiles, ST, CinP;
   int stackM, stackN, cpt;      // bf16x3 "precision stacking": [x_hi; x_lo] along M and/or [r_hi | r_lo] along N, so one
@@ -1328,19 +1331,27 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
 
   // output tile fastest: CTAs that stream the same positions run side by side (L2 reuse)
   int task = blockIdx.x;
-  const int out_tiles = p.ngrp * p.n_cin_tiles * p.n_cout_tiles;
-  const int split = task / out_tiles; task -= split * out_tiles;
+  const int out_tiles = p.n_vt * p.n_cin_tiles * p.n_cout_tiles;
+  const int usplit = task / out_tiles; task -= usplit * out_tiles;
   const int cout_tile = task % p.n_cout_tiles; task /= p.n_cout_tiles;
   const int cin_tile = task % p.n_cin_tiles; task /= p.n_cin_tiles;
-  const int grp = task;
+  const int grp = p.vt_grp[task];
+  const int split = usplit * p.grp_w[grp] + p.vt_w[task];
+  const int bps = p.grp_w[grp] == 2 ? p.blocks_per_split2 : p.blocks_per_split;
   const int cm_chunks = min(p.cpt, p.CC - cin_tile * p.cpt);
   const int N = min(p.CN, p.Cout - cout_tile * p.CN);
   const int rn_chunks = N / 8;
   const int Neff = p.rsw ? p.ncopy * N : (p.stackN ? 2 * N : N);
   const int colw = p.rsw ? p.ncopy * p.CN : (p.stackN ? 2 : 1) * p.CN;        // TMEM columns per super-tap
   const int st_b = p.grp_st_begin[grp], st_e = p.grp_st_begin[grp + 1];
-  const int blk_b = min(split * p.blocks_per_split, p.total_blocks);
-  const int blk_e = min(blk_b + p.blocks_per_split, p.total_blocks);
+  const int blk_b = min(split * bps, p.total_blocks);
+  const int blk_e = min(blk_b + bps, p.total_blocks);
+  // A weight-1 group next to weight-2 groups covers the position range of TWO of their splits: it walks the two
+  // halves interleaved, so that at any time all CTAs of a unit split stream the same two windows (L2 re-use).
+  const int nblk = blk_e - blk_b;
+  const int ihalf = (p.blocks_per_split2 > 0 && p.grp_w[grp] == 1) ? p.blocks_per_split2 : nblk;
+  const int ih2 = nblk > ihalf ? nblk - ihalf : 0;       // blocks in the second half
+#define HEBB_DW_BLK(i) (blk_b + ((i) < 2 * ih2 ? ((i) >> 1) + ((i) & 1) * ihalf : (i) - ih2))
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ST; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
@@ -1363,8 +1374,8 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
       const uint32_t bytes = p.rsw ? (uint32_t)(p.nrep * cm_chunks * p.BLK * 16 + p.b_rows * 128)
                                    : p.HL * (p.nrep * cm_chunks * p.BLK + rn_chunks * p.SEGLEN) * 16;
       const long long r_back = (long long)p.grp_base[grp] + p.rhalo;      // the r tile starts this far before the x tile
-      for (int blk = blk_b; blk < blk_e; ++blk) {
-        const long long q0 = (long long)blk * p.BLK;
+      for (int i = 0; i < nblk; ++i) {
+        const long long q0 = (long long)HEBB_DW_BLK(i) * p.BLK;
         mbar_wait(empty + 8 * st, ph ^ 1, p.err, 11);
         mbar_expect_tx(full + 8 * st, bytes);
         const uint32_t dst = sbase + st * p.stage_bytes;
@@ -1405,13 +1416,13 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
       const int ksteps = p.BLK / 16;
       const int mode = (p.HL == 2) ? (p.stackM ? (p.stackN ? 1 : 2) : (p.stackN ? 3 : 4)) : 1;
       const int sel = (mode - 1) * 2 + (p.reuse ? 1 : 0);
-      for (int blk = blk_b; blk < blk_e; ++blk) {
+      for (int i = 0; i < nblk; ++i) {
         mbar_wait(full + 8 * st, ph, p.err, 12);
         tc_fence_after();
         const uint32_t xa = sbase + st * p.stage_bytes;
         const uint32_t ra = xa + r_off + r_rem * 128u;
         if (elect_one()) {
-          const bool first = (blk == blk_b);
+          const bool first = (i == 0);
 #define HEBB_DW_ISSUE(M, R)                                                                                               \
           (first ? dw_issue<M, 0, R>(p, xa, ra, st_b, st_e, tmem_base, colw, ksteps, a_lbo, a_hi32, b_lbo, b_hi32, idesc,  \
                                      xhl16, rhl16, bstep)                                                                 \
@@ -1482,6 +1493,7 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
       }
     }
   }
+#undef HEBB_DW_BLK
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
@@ -1613,6 +1625,7 @@ struct Plan {
   // swizzled-response variant of the dW kernel (bf16 operands, 64 response channels, 3-wide kernel rows): its own
   // tiling, chosen per call (the weight-gradient and HPCA calls keep the plain layout); 0 = not available
   int rsw, rs_BLK, rs_ST, rs_nrep, rs_by_kh, rs_cpt, rs_n_cin, rs_CinP, rs_PS, rs_total_blocks, rs_blocks_per_split, rs_b_rows;
+  int rs_pair, rs_rhalo, rs_PSu, rs_bps2;     // rs_pair: kernel rows grouped (kh0, kh1) + (kh2), weights 2 : 1
   uint32_t rs_stage, rs_x_bytes, rs_off_bar, rs_smem, rs_tmem;
   uint32_t d_stage, d_x_bytes, d_off_bar, d_smem, d_tmem;
   // workspace carve (byte offsets)
@@ -1846,19 +1859,29 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
     const bool rep3 = g.Cin == 64;
     q.rs_nrep = rep3 ? 3 : 1; q.rs_by_kh = rep3 ? 0 : 1; q.rs_cpt = rep3 ? 8 : 16;
     q.rs_n_cin = rep3 ? 1 : g.Cin / 128; q.rs_CinP = g.Cin;
-    q.rs_BLK = rep3 ? 128 : 256; q.rs_ST = rep3 ? 3 : 2;
-    q.rs_b_rows = round_up_i(q.rs_BLK + (g.kW - 1) + 7, 8);
-    q.rs_x_bytes = (uint32_t)q.rs_nrep * q.rs_cpt * q.rs_BLK * 16;
-    q.rs_stage = q.rs_x_bytes + (uint32_t)q.rs_b_rows * 128;
-    // the last A descriptor (rep3: start at replica 2, spanning 16 chunks) must stay inside the allocation
-    const uint64_t ring = (uint64_t)q.rs_ST * q.rs_stage;
-    const uint64_t last_read = (uint64_t)(q.rs_ST - 1) * q.rs_stage + (rep3 ? 2ull * 8 * q.rs_BLK * 16 : 0ull) +
-                               16ull * q.rs_BLK * 16 + 256;
-    uint64_t tot = ring > last_read ? ring : last_read;
-    tot = (tot + 1023) / 1024 * 1024 + 8 * 16 + 64;
-    q.rs_off_bar = (uint32_t)(tot - (8 * 16 + 64)); q.rs_smem = (uint32_t)tot;
-    q.rs_tmem = pow2_cols((rep3 ? 2 : 1) * 64 * g.kW);
-    if (q.rs_stage % 1024 == 0 && q.rs_x_bytes % 1024 == 0 && tot <= (uint64_t)kSmemLimit - 1024 && q.rs_tmem <= 512) q.rsw = 1;
+    // Cin = k*128, opt-in (HEBB_DW_RSW_PAIR=1): one CTA handles the kernel rows (kh 0, kh 1) of a plane -- two
+    // instructions per k-step share the staged x tile, the response tile carries a halo of one image row -- and
+    // another one the row kh 2 with half as many position splits.  Measured no faster (128 -> 64 @96x96x80: 2.19 vs
+    // 2.09 ms): with one N = 192 instruction per k-step the layer already runs at 77 % of the measured tensor peak.
+    static const int want_pair = [] { const char* e = getenv("HEBB_DW_RSW_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
+    q.rs_pair = (!rep3 && want_pair && q.rs_n_cin * g.kD * 3 <= sms) ? 1 : 0;
+    q.rs_rhalo = (g.kW - 1) + (q.rs_pair ? q.WP : 0);
+    const int blk_opts[2] = {rep3 ? 128 : 256, 128}, st_opts[2] = {rep3 ? 3 : 2, 2};
+    for (int o = 0; o < 2 && !q.rsw; ++o) {
+      q.rs_BLK = blk_opts[o]; q.rs_ST = st_opts[o];
+      q.rs_b_rows = round_up_i(q.rs_BLK + q.rs_rhalo + 7, 8);
+      q.rs_x_bytes = (uint32_t)q.rs_nrep * q.rs_cpt * q.rs_BLK * 16;
+      q.rs_stage = q.rs_x_bytes + (uint32_t)q.rs_b_rows * 128;
+      // the last A descriptor (rep3: start at replica 2, spanning 16 chunks) must stay inside the allocation
+      const uint64_t ring = (uint64_t)q.rs_ST * q.rs_stage;
+      const uint64_t last_read = (uint64_t)(q.rs_ST - 1) * q.rs_stage + (rep3 ? 2ull * 8 * q.rs_BLK * 16 : 0ull) +
+                                 16ull * q.rs_BLK * 16 + 256;
+      uint64_t tot = ring > last_read ? ring : last_read;
+      tot = (tot + 1023) / 1024 * 1024 + 8 * 16 + 64;
+      q.rs_off_bar = (uint32_t)(tot - (8 * 16 + 64)); q.rs_smem = (uint32_t)tot;
+      q.rs_tmem = pow2_cols(((rep3 || q.rs_pair) ? 2 : 1) * 64 * g.kW);
+      if (q.rs_stage % 1024 == 0 && q.rs_x_bytes % 1024 == 0 && tot <= (uint64_t)kSmemLimit - 1024 && q.rs_tmem <= 512) q.rsw = 1;
+    }
   }
 
   // packed position space: multiples of both tile sizes
@@ -1872,7 +1895,7 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   const int blk_max = (q.rsw && q.rs_BLK > q.BLK) ? q.rs_BLK : q.BLK;
   // rsw: the x replicas reach (nrep-1)*WP positions past a block
   q.PA = (q.PR + q.maxshift + blk_max + (q.rsw ? (q.rs_nrep - 1) * q.WP : 0) + 16 + 7) / 8 * 8;
-  q.r_lead = (q.maxshift + 7) / 8 * 8;
+  q.r_lead = (q.maxshift + ((q.rsw && q.rs_pair) ? q.WP : 0) + 7) / 8 * 8;      // pair mode stages one more image row ahead
   q.PRS = q.r_lead + ((q.PR + q.maxshift + blk_max + 16 + 7) / 8 * 8);
   q.f_ntiles = (int)(q.PR / q.TILE_M);
   const int out_tiles = q.ngrp * q.n_cin_tiles * q.n_cout_tiles;
@@ -1884,12 +1907,15 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   q.PS = (int)cdiv(q.total_blocks, q.blocks_per_split);
   if (q.rsw) {
     q.rs_total_blocks = (int)cdiv(q.PTOT + q.maxshift, q.rs_BLK);
-    const int rs_tiles = (q.rs_by_kh ? g.kD * g.kH : g.kD) * q.rs_n_cin;
+    // virtual tiles: pair mode counts a (kh0, kh1) group twice (it gets twice the position splits)
+    const int rs_tiles = (q.rs_pair ? g.kD * 3 : (q.rs_by_kh ? g.kD * g.kH : g.kD)) * q.rs_n_cin;
     int rps = sms / rs_tiles;
     if (rps > q.rs_total_blocks) rps = q.rs_total_blocks;
     if (rps < 1) rps = 1;
+    q.rs_PSu = rps;
     q.rs_blocks_per_split = (int)cdiv(q.rs_total_blocks, rps);
-    q.rs_PS = (int)cdiv(q.rs_total_blocks, q.rs_blocks_per_split);
+    q.rs_bps2 = (int)cdiv(q.rs_total_blocks, 2 * rps);
+    q.rs_PS = q.rs_pair ? 2 * rps : (int)cdiv(q.rs_total_blocks, q.rs_blocks_per_split);     // partial planes summed by finalize
   }
 
   // ---------------- workspace ----------------
@@ -1997,15 +2023,17 @@ static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4*
   for (int t = 0; t < kMaxTaps; ++t) { d.st_boff[t] = 0; d.st_aoff[t] = 0; d.st_first[t] = 0; d.st_n[t] = 0; }
   d.r_lead = P.r_lead;
   int dgrid;
+  for (int i = 0; i < 9; ++i) d.grp_w[i] = 1;
+  for (int i = 0; i < 18; ++i) { d.vt_grp[i] = i < 9 ? i : 0; d.vt_w[i] = 0; }
+  d.blocks_per_split2 = 0;
   if (rsw) {
     // swizzled responses: one N = 64*kW instruction per kernel row (see plan_layer_search)
     d.rsw = 1; d.ncopy = g.kW; d.b_rows = P.rs_b_rows; d.reuse = 0;
     d.BLK = P.rs_BLK; d.SEGLEN = P.rs_b_rows; d.total_blocks = P.rs_total_blocks;
-    d.blocks_per_split = P.rs_blocks_per_split; d.PS = P.rs_PS;
-    d.rhalo = g.kW - 1;
+    d.blocks_per_split = P.rs_blocks_per_split; d.blocks_per_split2 = P.rs_bps2; d.PS = P.rs_PS;
+    d.rhalo = P.rs_rhalo;
     d.nrep = P.rs_nrep; d.rep_stride = P.WP; d.tap_rep = g.kW;
-    d.ngrp = P.rs_by_kh ? g.kD * g.kH : g.kD;
-    int nst = 0, gi = 0;
+    int nst = 0, gi = 0, nvt = 0;
     for (int kd = 0; kd < g.kD; ++kd) {
       if (!P.rs_by_kh) {
         // tap group = kd plane; super-tap 0: x replicas 0,1 = kernel rows kh 0,1 (M = 128), super-tap 1: replica 2 = kh 2
@@ -2015,21 +2043,38 @@ static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4*
           d.st_first[nst] = (kd * g.kH + kh0) * g.kW;
           d.st_n[nst] = (g.kH - kh0 < 2) ? (g.kH - kh0) : 2;
         }
+        d.vt_grp[nvt] = gi; d.vt_w[nvt++] = 0;
+        ++gi;
+      } else if (P.rs_pair) {
+        // group (kh 0, kh 1): two super-taps whose B operands start one image row apart in the staged response tile
+        // (tap offset = grp_base + rhalo - row offset - column copy); weight 2.  Group (kh 2): weight 1.
+        d.grp_base[gi] = kd * P.plane; d.grp_st_begin[gi] = nst; d.grp_w[gi] = 2;
+        d.st_boff[nst] = P.WP * 8; d.st_first[nst] = (kd * g.kH + 0) * g.kW; d.st_n[nst] = 1; ++nst;
+        d.st_boff[nst] = 0;        d.st_first[nst] = (kd * g.kH + 1) * g.kW; d.st_n[nst] = 1; ++nst;
+        d.vt_grp[nvt] = gi; d.vt_w[nvt++] = 0; d.vt_grp[nvt] = gi; d.vt_w[nvt++] = 1;
+        ++gi;
+        d.grp_base[gi] = kd * P.plane + 2 * P.WP; d.grp_st_begin[gi] = nst; d.grp_w[gi] = 1;
+        d.st_boff[nst] = P.WP * 8; d.st_first[nst] = (kd * g.kH + 2) * g.kW; d.st_n[nst] = 1; ++nst;
+        d.vt_grp[nvt] = gi; d.vt_w[nvt++] = 0;
         ++gi;
       } else {
         for (int kh = 0; kh < g.kH; ++kh, ++gi, ++nst) {
           d.grp_base[gi] = kd * P.plane + kh * P.WP; d.grp_st_begin[gi] = nst;
           d.st_first[nst] = (kd * g.kH + kh) * g.kW; d.st_n[nst] = 1;
+          d.vt_grp[nvt] = gi; d.vt_w[nvt++] = 0;
         }
       }
     }
+    d.ngrp = gi; d.n_vt = nvt;
     for (int i = gi; i < 10; ++i) d.grp_st_begin[i] = nst;
     d.stackM = 0; d.stackN = 0; d.cpt = P.rs_cpt;
     d.CM = 128; d.n_cin_tiles = P.rs_n_cin; d.CN = 64; d.n_cout_tiles = 1; d.ST = P.rs_ST; d.CinP = P.rs_CinP;
     d.stage_bytes = P.rs_stage; d.x_bytes = P.rs_x_bytes; d.off_bar = P.rs_off_bar; d.tmem_cols = P.rs_tmem;
-    dgrid = d.ngrp * d.n_cin_tiles * P.rs_PS;
+    dgrid = nvt * d.n_cin_tiles * P.rs_PSu;
+    if (P.rs_pair)     // the (kh 2) groups fill only half of the partial planes the finalize pass sums
+      HEBB_CUDA_TRY(cudaMemsetAsync(hpart, 0, (size_t)P.rs_PS * g.taps * P.rs_CinP * g.Cout * sizeof(float), st));
   } else {
-    d.rsw = 0; d.ncopy = 1; d.b_rows = 0; d.rep_stride = 1; d.tap_rep = 1;
+    d.rsw = 0; d.ncopy = 1; d.b_rows = 0; d.rep_stride = 1; d.tap_rep = 1; d.n_vt = P.ngrp;
     d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
     d.rhalo = P.rhalo; d.reuse = P.reuse;
     d.blocks_per_split = P.blocks_per_split; d.PS = P.PS; d.ngrp = P.ngrp;

@@ -87,6 +87,19 @@ def test_planner_collector_reuse_cases_are_the_ones_the_gpu_tests_run():
     assert _native.plan(_desc3(8, 128, 128, (48, 48, 40)), _native.PREC_BF16)['reuse'] == 0
 
 
+def test_planner_swizzled_response_variant_only_where_it_applies():
+    """bf16 operands, exactly 64 response channels, 3-wide kernel rows, 64 or k*128 input channels: the update reads
+    the responses as a SWIZZLE_128B [position][64] image (one N = 192 instruction per kernel row).  Everything else,
+    and every bf16x3 plan, keeps the plain planes."""
+    for cin, sp in ((64, (96, 96, 80)), (128, (96, 96, 80)), (64, (8, 8, 8)), (256, (12, 12, 10))):
+        assert _native.plan(_desc3(8, cin, 64, sp), _native.PREC_BF16)['rsw'] == 1, (cin, sp)
+        assert _native.plan(_desc3(8, cin, 64, sp), _native.PREC_BF16X3)['rsw'] == 0
+    assert _native.plan(_desc3(64, 128, 64, (64, 64)), _native.PREC_BF16)['rsw'] == 1          # 2-D
+    for cin, cout in ((32, 64), (64, 128), (128, 128), (64, 32), (96, 64)):
+        assert _native.plan(_desc3(8, cin, cout, (24, 24, 20)), _native.PREC_BF16)['rsw'] == 0, (cin, cout)
+    assert _native.plan(_desc3(8, 64, 64, (24, 24, 20), k=1), _native.PREC_BF16)['rsw'] == 0
+
+
 def test_no_cpu_fallback():
     layer = hebb.HebbianConv2d(3, 8, 3, padding=1, alpha=1.)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
