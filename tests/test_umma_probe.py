@@ -1,5 +1,6 @@
 """Pins the shared-memory descriptor semantics the tensor-core kernels rely on: SWIZZLE_NONE
-K-major and MN-major operands whose start address is shifted by whole 16-byte position slots."""
+K-major and MN-major operands whose start address is shifted by whole 16-byte position slots, and MN-major
+SWIZZLE_128B operands ([position][64 channels] images) with position-shifted starts and a one-position atom stride."""
 import ctypes
 
 import numpy as np
@@ -85,3 +86,69 @@ def test_mn_major_shifted_positions(m, shift):
         lanes = [(r % 16) + 32 * (r // 16) for r in range(64)]
         got = d[lanes]
     assert np.abs(got - want).max() < 1e-3 * np.abs(want).max()
+
+
+# ---- MN-major SWIZZLE_128B: the image is [position][64 channels], 16-byte chunks XOR-ed with (position % 8) ----
+SW128 = 2
+
+
+def desc_hi_sw(lbo, sbo):
+    return desc_hi(lbo, sbo) | (SW128 << 61)
+
+
+def sw128_image(T):
+    """T: [positions][64] bf16 -> the swizzled shared-memory image as uint16."""
+    P = T.shape[0]
+    src = to_u16(T).reshape(P, 8, 8)
+    img = np.zeros_like(src)
+    for r in range(P):
+        for c in range(8):
+            img[r, c ^ (r & 7)] = src[r, c]
+    return img.reshape(-1)
+
+
+def _sw128_operands(seed, px=64, pr=64):
+    rng = np.random.default_rng(seed)
+    X0, X1 = bf16_round(rng.standard_normal((px, 64))), bf16_round(rng.standard_normal((px, 64)))
+    R = bf16_round(rng.standard_normal((pr, 64)))
+    a_img = np.concatenate([sw128_image(X0), sw128_image(X1)])
+    f64 = lambda t: t.float().numpy().astype(np.float64)
+    return a_img, sw128_image(R), f64(X0), f64(X1), f64(R), px * 128
+
+
+@pytest.mark.parametrize('shift', [0, 1, 3, 8, 13])
+def test_mn_major_sw128_shifted_start(shift):
+    """The hardware swizzles on absolute shared-memory address bits: a start address moved by whole positions
+    (128 B) reads the shifted tile with base_offset = 0 (the swizzled-response dW variant relies on it)."""
+    a_img, b_img, X0, X1, R, atom_a = _sw128_operands(shift)
+    K = 32
+    d = run_probe(a_img, b_img, desc_hi_sw(atom_a, 1024), 0, 2048, desc_hi_sw(1024, 1024), shift * 128, 2048,
+                  idesc(128, 64, 1, 1), K // 16, 128, 64)
+    want = np.concatenate([X0[:K], X1[:K]], axis=1).T @ R[shift:shift + K]
+    assert np.abs(d - want).max() < 1e-3 * np.abs(want).max()
+
+
+@pytest.mark.parametrize('shift', [0, 2, 5])
+def test_mn_major_sw128_one_position_atom_stride(shift):
+    """LBO = 128 B: the 64-channel atoms of the B operand are ONE position apart, so an N = 192 instruction reads
+    three position-shifted copies of the same response tile (the three taps of a kernel row) without replicas."""
+    a_img, b_img, X0, X1, R, atom_a = _sw128_operands(100 + shift)
+    K = 32
+    d = run_probe(a_img, b_img, desc_hi_sw(atom_a, 1024), 0, 2048, desc_hi_sw(128, 1024), shift * 128, 2048,
+                  idesc(128, 192, 1, 1), K // 16, 128, 192)
+    B = np.concatenate([R[shift + j:shift + j + K] for j in range(3)], axis=1)
+    want = np.concatenate([X0[:K], X1[:K]], axis=1).T @ B
+    assert np.abs(d - want).max() < 1e-3 * np.abs(want).max()
+
+
+@pytest.mark.parametrize('rows_apart', [1, 5, 10])
+def test_mn_major_sw128_shifted_replica_rows(rows_apart):
+    """The same on the A side: M = 128 = a 64-channel x tile and the tile `rows_apart` positions further (round-2
+    layout: kh replicas without staging copies)."""
+    a_img, b_img, X0, X1, R, atom_a = _sw128_operands(200 + rows_apart)
+    K = 32
+    d = run_probe(a_img, b_img, desc_hi_sw(rows_apart * 128, 1024), 0, 2048, desc_hi_sw(128, 1024), 0, 2048,
+                  idesc(128, 192, 1, 1), K // 16, 128, 192)
+    B = np.concatenate([R[j:j + K] for j in range(3)], axis=1)
+    want = np.concatenate([X0[:K], X0[rows_apart:rows_apart + K]], axis=1).T @ B
+    assert np.abs(d - want).max() < 1e-3 * np.abs(want).max()
