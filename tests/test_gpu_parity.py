@@ -253,6 +253,33 @@ def test_batch_shard_additivity_at_size(prec):
     assert relerr(layer.delta_w, full) < 1e-4        # fp32 accumulation-order noise only
 
 
+@pytest.mark.parametrize('cin', [64, 128])
+def test_swizzled_response_update_at_size(cin):
+    """The bf16 update of 64-response-channel layers reads the responses as a swizzled [position][64] image (one
+    N = 192 instruction per kernel row, many position blocks and splits per CTA).  At a size the CPU oracle cannot
+    reach: (1) dW(batch) == sum of dW(shards); (2) it agrees with the split-precision path -- a different kernel
+    variant on a different response layout -- within the bf16 operand tolerance."""
+    from hebb import _native
+    g = torch.Generator().manual_seed(20 + cin)
+    x = (torch.randn(2, cin, 40, 36, 28, generator=g) * 0.5).to(DEV)
+    assert _native.plan(_native.make_desc(3, 2, cin, 64, (40, 36, 28), (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), False),
+                        _native.PREC_BF16)['rsw'] == 1
+    got = {}
+    for prec in ('bf16', 'bf16x3'):
+        torch.manual_seed(3)
+        layer = hebb.HebbianConv3d(cin, 64, 3, padding=1, bias=False, k=20., alpha=1.)
+        layer.prec = prec
+        layer = layer.to(DEV).train()
+        layer(x)
+        got[prec] = layer.delta_w.clone()
+        if prec == 'bf16':
+            layer.delta_w.zero_()
+            layer(x[:1]); layer(x[1:])
+            assert relerr(layer.delta_w, got[prec]) < 1e-4          # fp32 accumulation-order noise only
+    record('swizzled_response_update_at_size', f'cin{cin}', dw_vs_split_path=relerr(got['bf16'], got['bf16x3']))
+    assert relerr(got['bf16'], got['bf16x3']) < TOL_DW['bf16']
+
+
 def test_softmax_rows_sum_to_one_property():
     """sum_c r = 1 per pixel  =>  sum_c (dW_c + rsum_c W_c) == sum_p X_p ; checked through dW."""
     g = torch.Generator().manual_seed(12)
