@@ -1886,8 +1886,9 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   // kernel rows, 128-channel tiles.
   static const int want_rsw = [] { const char* e = getenv("HEBB_DW_RSW"); return (e && e[0] == '0') ? 0 : 1; }();
   q.rsw = 0; q.rs_BLK = 0;
-  if (want_rsw && prec == HEBB_PREC_BF16 && !gram && !trq && g.Cout == 64 && q.n_ct == 1 && g.kW == 3 && g.kH == 3 &&
-      (g.Cin == 64 || g.Cin % 128 == 0)) {
+  // (Cout = 128 only with Cin = 64: two 64-channel response planes; wider layers are math-bound as they are)
+  if (want_rsw && prec == HEBB_PREC_BF16 && !gram && !trq && (g.Cout == 64 || (g.Cout == 128 && g.Cin == 64)) && q.n_ct == 1 &&
+      g.kW == 3 && g.kH == 3 && (g.Cin == 64 || g.Cin % 128 == 0)) {
     const bool rep3 = g.Cin == 64;
     q.rs_nrep = rep3 ? 3 : 1; q.rs_by_kh = rep3 ? 0 : 1; q.rs_cpt = rep3 ? 8 : 16;
     q.rs_n_cin = rep3 ? 1 : g.Cin / 128; q.rs_CinP = g.Cin;
@@ -1896,7 +1897,7 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
     // another one the row kh 2 with half as many position splits.  Measured no faster (128 -> 64 @96x96x80: 2.19 vs
     // 2.09 ms): with one N = 192 instruction per k-step the layer already runs at 77 % of the measured tensor peak.
     static const int want_pair = [] { const char* e = getenv("HEBB_DW_RSW_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
-    q.rs_pair = (!rep3 && want_pair && q.rs_n_cin * g.kD * 3 <= sms) ? 1 : 0;
+    q.rs_pair = (!rep3 && want_pair && g.Cout == 64 && q.rs_n_cin * g.kD * 3 <= sms) ? 1 : 0;
     q.rs_rhalo = (g.kW - 1) + (q.rs_pair ? q.WP : 0);
     const int blk_opts[2] = {rep3 ? 128 : 256, 128}, st_opts[2] = {rep3 ? 3 : 2, 2};
     for (int o = 0; o < 2 && !q.rsw; ++o) {
@@ -1940,7 +1941,7 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   if (q.rsw) {
     q.rs_total_blocks = (int)cdiv(q.PTOT + q.maxshift, q.rs_BLK);
     // virtual tiles: pair mode counts a (kh0, kh1) group twice (it gets twice the position splits)
-    const int rs_tiles = (q.rs_pair ? g.kD * 3 : (q.rs_by_kh ? g.kD * g.kH : g.kD)) * q.rs_n_cin;
+    const int rs_tiles = (q.rs_pair ? g.kD * 3 : (q.rs_by_kh ? g.kD * g.kH : g.kD)) * q.rs_n_cin * (g.Cout / 64);
     int rps = sms / rs_tiles;
     if (rps > q.rs_total_blocks) rps = q.rs_total_blocks;
     if (rps < 1) rps = 1;
@@ -2100,9 +2101,9 @@ static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4*
     d.ngrp = gi; d.n_vt = nvt;
     for (int i = gi; i < 10; ++i) d.grp_st_begin[i] = nst;
     d.stackM = 0; d.stackN = 0; d.cpt = P.rs_cpt;
-    d.CM = 128; d.n_cin_tiles = P.rs_n_cin; d.CN = 64; d.n_cout_tiles = 1; d.ST = P.rs_ST; d.CinP = P.rs_CinP;
+    d.CM = 128; d.n_cin_tiles = P.rs_n_cin; d.CN = 64; d.n_cout_tiles = g.Cout / 64; d.ST = P.rs_ST; d.CinP = P.rs_CinP;
     d.stage_bytes = P.rs_stage; d.x_bytes = P.rs_x_bytes; d.off_bar = P.rs_off_bar; d.tmem_cols = P.rs_tmem;
-    dgrid = nvt * d.n_cin_tiles * P.rs_PSu;
+    dgrid = nvt * d.n_cin_tiles * d.n_cout_tiles * P.rs_PSu;
     if (P.rs_pair)     // the (kh 2) groups fill only half of the partial planes the finalize pass sums
       HEBB_CUDA_TRY(cudaMemsetAsync(hpart, 0, (size_t)P.rs_PS * g.taps * P.rs_CinP * g.Cout * sizeof(float), st));
   } else {

@@ -19,6 +19,10 @@ python bench.py --workload c6 --steps 5 --warmup 3 --no-cpu-baseline --no-layer-
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-layer-profile"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c2.csv $CMD > gpurun_out/ncu_ll.log 2>&1; echo "launchlist rc=$?"
+# the same launch list for the 3-D network (bf16 operands)
+CMD4="python bench.py --workload c4 --prec bf16 --steps 1 --warmup 3 --no-cpu-baseline --no-layer-profile"
+$CMD4 > gpurun_out/plain_c4.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c4.csv $CMD4 > gpurun_out/ncu_ll_c4.log 2>&1; echo "launchlist c4 rc=$?"
 # DRAM traffic of our kernels over one timed step (3 warm-up steps x 132 matching launches skipped)
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'swta|pack_x|pack_w|tc_finalize|wnorm_kernel' -s 396 -c 132 --csv --log-file gpurun_out/traffic_c2.csv $CMD > gpurun_out/ncu_tr.log 2>&1; echo "traffic rc=$?"
 # tensor-bound layer of the 3-D network: 128->128 3x3x3 @48x48x40, batch 8

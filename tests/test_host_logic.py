@@ -95,7 +95,8 @@ def test_planner_swizzled_response_variant_only_where_it_applies():
         assert _native.plan(_desc3(8, cin, 64, sp), _native.PREC_BF16)['rsw'] == 1, (cin, sp)
         assert _native.plan(_desc3(8, cin, 64, sp), _native.PREC_BF16X3)['rsw'] == 0
     assert _native.plan(_desc3(64, 128, 64, (64, 64)), _native.PREC_BF16)['rsw'] == 1          # 2-D
-    for cin, cout in ((32, 64), (64, 128), (128, 128), (64, 32), (96, 64)):
+    assert _native.plan(_desc3(8, 64, 128, (48, 48, 40)), _native.PREC_BF16)['rsw'] == 1       # two 64-channel response planes
+    for cin, cout in ((32, 64), (128, 128), (256, 128), (64, 32), (96, 64)):
         assert _native.plan(_desc3(8, cin, cout, (24, 24, 20)), _native.PREC_BF16)['rsw'] == 0, (cin, cout)
     assert _native.plan(_desc3(8, 64, 64, (24, 24, 20), k=1), _native.PREC_BF16)['rsw'] == 0
 
