@@ -148,16 +148,27 @@ class _FastWgradMixin:
             return None
         prec = _native.PREC_BF16X3             # fp32-equivalent split (cuDNN's own path here is TF32)
         cl_fmt = torch.channels_last if nd == 2 else torch.channels_last_3d
-        # follow the layout dL/dy arrives in (cuDNN hands back channels_last for a channels_last layer); x is
-        # copied into that layout only if it differs (the first head layer gets a plain NCHW activation)
-        if gy.is_contiguous():
-            cl = False
-            x = x.contiguous()
-        elif gy.is_contiguous(memory_format=cl_fmt):
-            cl = True
-            x = x.contiguous(memory_format=cl_fmt)
-        else:
+        # x and dL/dy must share one dense layout (NCHW or channels_last).  When they differ, the SMALLER tensor is
+        # copied: the 2-class output layer gets its dL/dy in NCHW from the softmax backward while its saved
+        # 32-channel input is channels_last -- converting x there cost 0.58 ms per step, converting dL/dy 0.03 ms
+        def layout(t):
+            if t.is_contiguous():
+                return 'nchw'
+            return 'cl' if t.is_contiguous(memory_format=cl_fmt) else None
+        lx, lg = layout(x), layout(gy)
+        if lg is None and lx is None:
             return None
+        if lx == lg:
+            want = lx
+        elif lx is None or lg is None:
+            want = lx or lg
+        else:
+            want = lx if x.numel() >= gy.numel() else lg
+        cl = want == 'cl'
+        if cl:
+            x, gy = x.contiguous(memory_format=cl_fmt), gy.contiguous(memory_format=cl_fmt)
+        else:
+            x, gy = x.contiguous(), gy.contiguous()
         cout = self.out_channels
         cpad = (cout + 15) // 16 * 16          # the kernel works on multiples of 16 filters; the extra rows are zero
         desc = _native.make_desc(nd, x.shape[0], self.in_channels, cpad, x.shape[2:], self.kernel_size, (1,) * nd,

@@ -492,6 +492,24 @@ def test_fast_wgrad_conv_matches_stock_conv(case, fmt):
     assert relerr(xf.grad, xr.grad) < 2e-3           # cuDNN dgrad (TF32 by default) on both sides
 
 
+@pytest.mark.parametrize('x_fmt,gy_fmt', [('channels_last', 'nchw'), ('nchw', 'channels_last')])
+def test_fast_wgrad_mixed_layouts_copy_the_smaller_tensor(x_fmt, gy_fmt):
+    """The 2-class output layer of the benchmark head: saved input channels_last, dL/dy NCHW (from the softmax
+    backward).  The native weight gradient brings both into one layout by copying the smaller tensor."""
+    import torch.nn as nn
+    from hebb.fused import FastWgradConv2d
+    torch.manual_seed(5)
+    conv = nn.Conv2d(32, 2, 3, padding=1).to(DEV)
+    conv.__class__ = FastWgradConv2d
+    x = torch.randn(3, 32, 20, 24, device=DEV)
+    gy = torch.randn(3, 2, 20, 24, device=DEV)
+    fmt = lambda t, f: t.contiguous(memory_format=torch.channels_last) if f == 'channels_last' else t.contiguous()
+    gw = conv._native_wgrad(fmt(x, x_fmt), fmt(gy, gy_fmt))
+    assert gw is not None
+    ref = torch.nn.grad.conv2d_weight(x.double(), conv.weight.shape, gy.double(), padding=1).float()
+    assert relerr(gw, ref) < 1e-4
+
+
 @pytest.mark.parametrize('case', [(2, 8, 3, 16, (40, 36)), (2, 4, 16, 32, (24, 28)), (2, 3, 32, 64, (20, 20)), (2, 2, 64, 128, (12, 16)),
                                   (3, 2, 16, 64, (6, 10, 8)), (2, 2, 128, 256, (8, 8))])
 def test_forward_epilogue_hands_back_batchnorm_statistics(case):
