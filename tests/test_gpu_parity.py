@@ -174,6 +174,9 @@ TC_CASES = [
     ('c3d_128_32_run9', 3, 1, 128, 32, 3, 1, (10, 10, 10), 50.0),  # ... 9 taps of a plane
     ('c3d_256_64_rsw', 3, 1, 256, 64, 3, 1, (6, 6, 5), 50.0),      # bf16: swizzled responses, two 128-channel x tiles
     ('c2d_64_64_rsw', 2, 2, 64, 64, 3, 1, (24, 20), 50.0),         # bf16: swizzled responses, kh-replicated x tile, 2-D
+    ('c2d_64_64_rsw_nopad', 2, 3, 64, 64, 3, 0, (21, 19), 50.0),   # ... without padding, odd sizes
+    ('c3d_128_64_rsw_nopad', 3, 2, 128, 64, 3, 0, (7, 8, 9), 50.0),
+    ('c3d_64_128_rsw', 3, 1, 64, 128, 3, 1, (8, 8, 8), 50.0),      # bf16: two 64-channel response planes
     ('c3d_256_512', 3, 1, 256, 512, 3, 1, (4, 4, 4), 50.0),        # two 256-wide MMAs per step, fused softmax
     ('c2d_64_1024', 2, 2, 64, 1024, 3, 1, (8, 8), 20.0),           # two channel tiles, unfused softmax
     ('c3d_512_1024_k1', 3, 1, 512, 1024, 1, 0, (3, 3, 2), 5.0),
