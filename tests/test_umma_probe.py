@@ -152,3 +152,36 @@ def test_mn_major_sw128_shifted_replica_rows(rows_apart):
     B = np.concatenate([R[j:j + K] for j in range(3)], axis=1)
     want = np.concatenate([X0[:K], X0[rows_apart:rows_apart + K]], axis=1).T @ B
     assert np.abs(d - want).max() < 1e-3 * np.abs(want).max()
+
+
+# ---- SWIZZLE_64B / SWIZZLE_32B: [position][32 channels] and [position][16 channels] images ----
+def swz_image(T, W):
+    """T: [positions][W/2] bf16 -> image whose 16-byte chunks are XOR-ed with the address bits from bit 7 up."""
+    P = T.shape[0]
+    nch = W // 16
+    src = to_u16(T).reshape(P, nch, 8)
+    img = np.zeros_like(src)
+    for r in range(P):
+        phase = ((r * W) >> 7) & (nch - 1)
+        for c in range(nch):
+            img[r, c ^ phase] = src[r, c]
+    return img.reshape(-1)
+
+
+@pytest.mark.parametrize('W,layout', [(64, 4), (32, 6)])
+@pytest.mark.parametrize('shift', [0, 5])
+def test_mn_major_narrow_swizzles_one_position_atom_stride(W, layout, shift):
+    """Small-channel analogue of the SWIZZLE_128B case (round-2 layout for the 16/32-channel layers): M = 128 rows =
+    position-shifted copies of a 32- or 16-channel x tile, N = three position-shifted copies of the response tile."""
+    C = W // 2
+    rng = np.random.default_rng(W + shift)
+    X, R = bf16_round(rng.standard_normal((64, C))), bf16_round(rng.standard_normal((64, C)))
+    Xf, Rf = X.float().numpy().astype(np.float64), R.float().numpy().astype(np.float64)
+    hi = lambda lbo: desc_hi(lbo, 8 * W) | (layout << 61)
+    K, nA = 32, 128 // C
+    d = run_probe(swz_image(X, W), swz_image(R, W), hi(W), 0, 16 * W, hi(W), shift * W, 16 * W,
+                  idesc(128, 3 * C, 1, 1), K // 16, 128, 3 * C)
+    A = np.concatenate([Xf[j:j + K] for j in range(nA)], axis=1)
+    B = np.concatenate([Rf[shift + j:shift + j + K] for j in range(3)], axis=1)
+    want = A.T @ B
+    assert np.abs(d - want).max() < 1e-3 * np.abs(want).max()
