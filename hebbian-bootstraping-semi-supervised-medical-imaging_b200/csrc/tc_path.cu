@@ -1398,12 +1398,12 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
   const uint32_t r_off = p.x_bytes;                 // R region follows X region inside a stage
   const uint32_t x_hl_stride = cm_chunks * p.BLK * 16;      // lo chunks directly follow the hi chunks
   const uint32_t x_rep_stride = p.HL * x_hl_stride;         // replica r+1 directly follows replica r
-  const uint32_t r_hl_stride = rn_chunks * p.SEGLEN * 16;
+  const uint32_t r_hl_stride = p.rsw ? (uint32_t)(p.b_rows * 128) : rn_chunks * p.SEGLEN * 16;
 
   if (warp == 0) {
     if (elect_one()) {
       int st = 0; uint32_t ph = 0;
-      const uint32_t bytes = p.rsw ? (uint32_t)(p.nrep * cm_chunks * p.BLK * 16 + p.b_rows * 128)
+      const uint32_t bytes = p.rsw ? (uint32_t)(p.HL * (p.nrep * cm_chunks * p.BLK * 16 + p.b_rows * 128))
                                    : p.HL * (p.nrep * cm_chunks * p.BLK + rn_chunks * p.SEGLEN) * 16;
       const long long r_back = (long long)p.grp_base[grp] + p.rhalo;      // the r tile starts this far before the x tile
       for (int i = 0; i < nblk; ++i) {
@@ -1421,7 +1421,8 @@ dw_swta_kernel(const __grid_constant__ DwParams p) {
             // one copy: b_rows whole positions (128 B each) of this 64-channel plane, from an 8-aligned row so the
             // staged image keeps the swizzle phase of the global one (r_lead and q0 are multiples of 8)
             const long long r0a = ((q0 - r_back + p.r_lead) & ~7LL) - p.r_lead;
-            bulk_g2s(dst + r_off, p.rp[0] + ((long long)cout_tile * p.PRS + r0a) * 8, p.b_rows * 128, full + 8 * st);
+            bulk_g2s(dst + r_off + hl * (uint32_t)(p.b_rows * 128), p.rp[hl] + ((long long)cout_tile * p.PRS + r0a) * 8,
+                     p.b_rows * 128, full + 8 * st);
           } else {
             for (int c = 0; c < rn_chunks; ++c)
               bulk_g2s(dst + r_off + hl * r_hl_stride + c * p.SEGLEN * 16,
@@ -1658,6 +1659,7 @@ struct Plan {
   // tiling, chosen per call (the weight-gradient and HPCA calls keep the plain layout); 0 = not available
   int rsw, rs_BLK, rs_ST, rs_nrep, rs_by_kh, rs_cpt, rs_n_cin, rs_CinP, rs_PS, rs_total_blocks, rs_blocks_per_split, rs_b_rows;
   int rs_pair, rs_rhalo, rs_PSu, rs_bps2;     // rs_pair: kernel rows grouped (kh0, kh1) + (kh2), weights 2 : 1
+  int rs_stackM;                               // split precision, Cin = 64: M = [x_hi; x_lo] (two partial planes per split)
   uint32_t rs_stage, rs_x_bytes, rs_off_bar, rs_smem, rs_tmem;
   uint32_t d_stage, d_x_bytes, d_off_bar, d_smem, d_tmem;
   // workspace carve (byte offsets)
@@ -1887,24 +1889,30 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   static const int want_rsw = [] { const char* e = getenv("HEBB_DW_RSW"); return (e && e[0] == '0') ? 0 : 1; }();
   q.rsw = 0; q.rs_BLK = 0;
   // (Cout = 128 only with Cin = 64: two 64-channel response planes; wider layers are math-bound as they are)
-  if (want_rsw && prec == HEBB_PREC_BF16 && !gram && !trq && (g.Cout == 64 || (g.Cout == 128 && g.Cin == 64)) && q.n_ct == 1 &&
+  // Split precision (bf16x3): the hi and lo response images are staged side by side; Cin = k*128 issues the classic
+  // three products per kernel row (x_hi r_lo, x_hi r_hi, x_lo r_hi: 3 x N = 192 instead of 9 x N = 64), Cin = 64 stacks
+  // [x_hi; x_lo] along M (two instructions per kernel row, tap groups = kernel rows).
+  if (want_rsw && (prec == HEBB_PREC_BF16 || prec == HEBB_PREC_BF16X3) && !gram && !trq &&
+      (g.Cout == 64 || (g.Cout == 128 && g.Cin == 64)) && q.n_ct == 1 &&
       g.kW == 3 && g.kH == 3 && (g.Cin == 64 || g.Cin % 128 == 0)) {
-    const bool rep3 = g.Cin == 64;
-    q.rs_nrep = rep3 ? 3 : 1; q.rs_by_kh = rep3 ? 0 : 1; q.rs_cpt = rep3 ? 8 : 16;
-    q.rs_n_cin = rep3 ? 1 : g.Cin / 128; q.rs_CinP = g.Cin;
+    const int HL = q.d_HL;
+    const bool rep3 = g.Cin == 64 && HL == 1;
+    q.rs_stackM = (g.Cin == 64 && HL == 2) ? 1 : 0;
+    q.rs_nrep = rep3 ? 3 : 1; q.rs_by_kh = rep3 ? 0 : 1; q.rs_cpt = g.Cin == 64 ? 8 : 16;
+    q.rs_n_cin = g.Cin == 64 ? 1 : g.Cin / 128; q.rs_CinP = g.Cin;
     // Cin = k*128, opt-in (HEBB_DW_RSW_PAIR=1): one CTA handles the kernel rows (kh 0, kh 1) of a plane -- two
     // instructions per k-step share the staged x tile, the response tile carries a halo of one image row -- and
     // another one the row kh 2 with half as many position splits.  Measured no faster (128 -> 64 @96x96x80: 2.19 vs
     // 2.09 ms): with one N = 192 instruction per k-step the layer already runs at 77 % of the measured tensor peak.
     static const int want_pair = [] { const char* e = getenv("HEBB_DW_RSW_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
-    q.rs_pair = (!rep3 && want_pair && g.Cout == 64 && q.rs_n_cin * g.kD * 3 <= sms) ? 1 : 0;
+    q.rs_pair = (!rep3 && HL == 1 && want_pair && g.Cout == 64 && q.rs_n_cin * g.kD * 3 <= sms) ? 1 : 0;
     q.rs_rhalo = (g.kW - 1) + (q.rs_pair ? q.WP : 0);
-    const int blk_opts[2] = {rep3 ? 128 : 256, 128}, st_opts[2] = {rep3 ? 3 : 2, 2};
+    const int blk_opts[2] = {(rep3 || HL == 2) ? 128 : 256, 128}, st_opts[2] = {(rep3 || q.rs_stackM) ? 3 : 2, 2};
     for (int o = 0; o < 2 && !q.rsw; ++o) {
       q.rs_BLK = blk_opts[o]; q.rs_ST = st_opts[o];
       q.rs_b_rows = round_up_i(q.rs_BLK + q.rs_rhalo + 7, 8);
-      q.rs_x_bytes = (uint32_t)q.rs_nrep * q.rs_cpt * q.rs_BLK * 16;
-      q.rs_stage = q.rs_x_bytes + (uint32_t)q.rs_b_rows * 128;
+      q.rs_x_bytes = (uint32_t)q.rs_nrep * HL * q.rs_cpt * q.rs_BLK * 16;
+      q.rs_stage = q.rs_x_bytes + (uint32_t)HL * q.rs_b_rows * 128;
       // the last A descriptor (rep3: start at replica 2, spanning 16 chunks) must stay inside the allocation
       const uint64_t ring = (uint64_t)q.rs_ST * q.rs_stage;
       const uint64_t last_read = (uint64_t)(q.rs_ST - 1) * q.rs_stage + (rep3 ? 2ull * 8 * q.rs_BLK * 16 : 0ull) +
@@ -1964,7 +1972,7 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   q.o_wp = take((size_t)q.NSLAB * g.taps * q.f_HL * 2 * g.Cout * 16);
   {
     size_t hp = (size_t)q.PS * q.Q * g.taps * q.CinP * g.Cout * sizeof(float);
-    const size_t hp2 = q.rsw ? (size_t)q.rs_PS * g.taps * q.rs_CinP * g.Cout * sizeof(float) : 0;
+    const size_t hp2 = q.rsw ? (size_t)q.rs_PS * (q.rs_stackM ? 2 : 1) * g.taps * q.rs_CinP * g.Cout * sizeof(float) : 0;
     q.o_hpart = take(hp > hp2 ? hp : hp2);
   }
   q.gram_ok = false; q.o_gram = q.o_hpart2 = 0;
@@ -2100,12 +2108,12 @@ static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4*
     }
     d.ngrp = gi; d.n_vt = nvt;
     for (int i = gi; i < 10; ++i) d.grp_st_begin[i] = nst;
-    d.stackM = 0; d.stackN = 0; d.cpt = P.rs_cpt;
+    d.stackM = P.rs_stackM; d.stackN = 0; d.cpt = P.rs_cpt;
     d.CM = 128; d.n_cin_tiles = P.rs_n_cin; d.CN = 64; d.n_cout_tiles = g.Cout / 64; d.ST = P.rs_ST; d.CinP = P.rs_CinP;
     d.stage_bytes = P.rs_stage; d.x_bytes = P.rs_x_bytes; d.off_bar = P.rs_off_bar; d.tmem_cols = P.rs_tmem;
     dgrid = nvt * d.n_cin_tiles * d.n_cout_tiles * P.rs_PSu;
     if (P.rs_pair)     // the (kh 2) groups fill only half of the partial planes the finalize pass sums
-      HEBB_CUDA_TRY(cudaMemsetAsync(hpart, 0, (size_t)P.rs_PS * g.taps * P.rs_CinP * g.Cout * sizeof(float), st));
+      HEBB_CUDA_TRY(cudaMemsetAsync(hpart, 0, (size_t)P.rs_PS * (P.rs_stackM ? 2 : 1) * g.taps * P.rs_CinP * g.Cout * sizeof(float), st));
   } else {
     d.rsw = 0; d.ncopy = 1; d.b_rows = 0; d.rep_stride = 1; d.tap_rep = 1; d.n_vt = P.ngrp;
     d.BLK = P.BLK; d.SEGLEN = P.d_SEGLEN; d.total_blocks = P.total_blocks;
@@ -2308,7 +2316,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   }
   // ---- dW ----
   HEBB_TRY(launch_dw(P, g, xp0, xp1, rp0, rp1, hpart, err, P.PA, P.PRS, st, rsw));
-  const int n_part = rsw ? P.rs_PS : P.PS * P.Q;           // partial planes the finalize pass sums
+  const int n_part = rsw ? P.rs_PS * (P.rs_stackM ? 2 : 1) : P.PS * P.Q;           // partial planes the finalize pass sums
   const int cin_p = rsw ? P.rs_CinP : P.CinP;
   {
     const long long n = (long long)g.taps * g.Cin * g.Cout;

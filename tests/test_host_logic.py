@@ -88,12 +88,13 @@ def test_planner_collector_reuse_cases_are_the_ones_the_gpu_tests_run():
 
 
 def test_planner_swizzled_response_variant_only_where_it_applies():
-    """bf16 operands, exactly 64 response channels, 3-wide kernel rows, 64 or k*128 input channels: the update reads
-    the responses as a SWIZZLE_128B [position][64] image (one N = 192 instruction per kernel row).  Everything else,
-    and every bf16x3 plan, keeps the plain planes."""
+    """64 response channels (128 with 64 input channels), 3-wide kernel rows, 64 or k*128 input channels: the update
+    reads the responses as SWIZZLE_128B [position][64] images (N = 192 instructions, one kernel row each), in both
+    tensor-core precision modes.  Everything else keeps the plain planes."""
     for cin, sp in ((64, (96, 96, 80)), (128, (96, 96, 80)), (64, (8, 8, 8)), (256, (12, 12, 10))):
-        assert _native.plan(_desc3(8, cin, 64, sp), _native.PREC_BF16)['rsw'] == 1, (cin, sp)
-        assert _native.plan(_desc3(8, cin, 64, sp), _native.PREC_BF16X3)['rsw'] == 0
+        for prec in (_native.PREC_BF16, _native.PREC_BF16X3):
+            p = _native.plan(_desc3(8, cin, 64, sp), prec)
+            assert p['rsw'] == 1 and p['ws_MiB'] >= 0, (cin, sp, prec)
     assert _native.plan(_desc3(64, 128, 64, (64, 64)), _native.PREC_BF16)['rsw'] == 1          # 2-D
     assert _native.plan(_desc3(8, 64, 128, (48, 48, 40)), _native.PREC_BF16)['rsw'] == 1       # two 64-channel response planes
     for cin, cout in ((32, 64), (128, 128), (256, 128), (64, 32), (96, 64)):
