@@ -258,29 +258,31 @@ def test_batch_shard_additivity_at_size(prec):
 
 @pytest.mark.parametrize('cin', [64, 128])
 def test_swizzled_response_update_at_size(cin):
-    """The bf16 update of 64-response-channel layers reads the responses as a swizzled [position][64] image (one
-    N = 192 instruction per kernel row, many position blocks and splits per CTA).  At a size the CPU oracle cannot
-    reach: (1) dW(batch) == sum of dW(shards); (2) it agrees with the split-precision path -- a different kernel
-    variant on a different response layout -- within the bf16 operand tolerance."""
+    """The update of 64-response-channel layers reads the responses as swizzled [position][64] images (N = 192
+    instructions, many position blocks and splits per CTA), in bf16 and in split precision.  At a size the CPU oracle
+    cannot reach: (1) dW(batch) == sum of dW(shards); (2) both modes agree with the fp32 CUDA-core path -- an
+    independent kernel on the plain response layout -- within their tolerances."""
     from hebb import _native
     g = torch.Generator().manual_seed(20 + cin)
     x = (torch.randn(2, cin, 40, 36, 28, generator=g) * 0.5).to(DEV)
-    assert _native.plan(_native.make_desc(3, 2, cin, 64, (40, 36, 28), (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), False),
-                        _native.PREC_BF16)['rsw'] == 1
+    desc = _native.make_desc(3, 2, cin, 64, (40, 36, 28), (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), False)
+    assert _native.plan(desc, _native.PREC_BF16)['rsw'] == 1 and _native.plan(desc, _native.PREC_BF16X3)['rsw'] == 1
     got = {}
-    for prec in ('bf16', 'bf16x3'):
+    for prec in ('fp32', 'bf16x3', 'bf16'):
         torch.manual_seed(3)
         layer = hebb.HebbianConv3d(cin, 64, 3, padding=1, bias=False, k=20., alpha=1.)
         layer.prec = prec
         layer = layer.to(DEV).train()
         layer(x)
         got[prec] = layer.delta_w.clone()
-        if prec == 'bf16':
+        if prec != 'fp32':
             layer.delta_w.zero_()
             layer(x[:1]); layer(x[1:])
             assert relerr(layer.delta_w, got[prec]) < 1e-4          # fp32 accumulation-order noise only
-    record('swizzled_response_update_at_size', f'cin{cin}', dw_vs_split_path=relerr(got['bf16'], got['bf16x3']))
-    assert relerr(got['bf16'], got['bf16x3']) < TOL_DW['bf16']
+    record('swizzled_response_update_at_size', f'cin{cin}', dw_bf16x3_vs_fp32=relerr(got['bf16x3'], got['fp32']),
+           dw_bf16_vs_fp32=relerr(got['bf16'], got['fp32']))
+    assert relerr(got['bf16x3'], got['fp32']) < TOL_DW['bf16x3']
+    assert relerr(got['bf16'], got['fp32']) < TOL_DW['bf16']
 
 
 def test_softmax_rows_sum_to_one_property():
