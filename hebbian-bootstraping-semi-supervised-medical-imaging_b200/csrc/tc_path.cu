@@ -37,8 +37,9 @@ using namespace ptx;
 constexpr int kMaxTaps = 27;
 constexpr int kSmemLimit = 227 * 1024;
 
-// Index (in 16-byte vectors) of the 8-channel group g8 of packed position pp in the response planes.
-// rsw = 0: planes of 8 channels, one vector per position.  rsw = 1: planes of 64 channels, 128 bytes per position,
+// Index (in 16-byte vectors) of the 8-channel group g8 of packed position pp in the response planes (the hi and
+// the lo plane set use the same index).  rsw = 0: planes of 8 channels, one vector per position.  rsw = 1: planes of
+// 64 channels, 128 bytes per position,
 // the 16-byte chunks XOR-ed with (position % 8) -- the MN-major SWIZZLE_128B image that the dW kernel's B operand
 // reads with a ONE-position atom stride, so that an N = 192 instruction covers the three taps of a kernel row
 // without staging shifted copies (tests/test_umma_probe.py pins that descriptor behaviour).
@@ -2040,7 +2041,8 @@ int tc_describe_plan(const Geo& g0, int prec, int* o, int n) {
   const int v[] = {P.MB, P.f_SEGLEN, P.XST, P.WST, P.NACC, (int)P.f_tmem, P.f_ntiles, (int)P.f_smem,
                    P.d_by_kh, P.CM, P.CN, P.BLK, P.ST, P.d_SEGLEN, P.ngrp, P.n_cin_tiles, P.n_cout_tiles, P.PS,
                    P.total_blocks, (int)P.d_tmem, (int)P.d_smem, P.d_HL, (int)(P.total >> 20), P.stackM, P.stackN, P.CT, P.n_ct, P.nrep, P.WG,
-                   P.reuse, P.rhalo, P.rsw};
+                   P.reuse, P.rhalo, P.rsw, P.rsw ? P.rs_BLK : 0, P.rsw ? P.rs_ST : 0, P.rsw ? (int)P.rs_smem : 0,
+                   P.rsw ? (int)P.rs_tmem : 0, P.rsw ? P.rs_PS : 0, P.rsw ? P.rs_stackM : 0};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < m; ++i) o[i] = v[i];
   return m;

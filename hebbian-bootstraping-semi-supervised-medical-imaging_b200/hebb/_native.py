@@ -277,12 +277,12 @@ def local_update_multi(grads, dws, alphas, has_grad):
 
 
 PLAN_FIELDS = ['MB', 'f_SEGLEN', 'XST', 'WST', 'NACC', 'f_tmem', 'f_tiles', 'f_smem', 'by_kh', 'CM', 'CN', 'BLK', 'ST',
-               'd_SEGLEN', 'ngrp', 'n_cin', 'n_cout', 'PS', 'blocks', 'd_tmem', 'd_smem', 'd_HL', 'ws_MiB', 'stackM', 'stackN', 'CT', 'n_ct', 'nrep', 'WG', 'reuse', 'rhalo', 'rsw']
+               'd_SEGLEN', 'ngrp', 'n_cin', 'n_cout', 'PS', 'blocks', 'd_tmem', 'd_smem', 'd_HL', 'ws_MiB', 'stackM', 'stackN', 'CT', 'n_ct', 'nrep', 'WG', 'reuse', 'rhalo', 'rsw', 'rs_BLK', 'rs_ST', 'rs_smem', 'rs_tmem', 'rs_PS', 'rs_stackM']
 
 
 def plan(desc: HebbDesc, prec: int):
-    out = (ctypes.c_int * 32)()
-    n = load().hebb_debug_plan(ctypes.byref(desc), int(prec), out, 32)
+    out = (ctypes.c_int * 48)()
+    n = load().hebb_debug_plan(ctypes.byref(desc), int(prec), out, 48)
     return dict(zip(PLAN_FIELDS, list(out)[:n])) if n else None
 
 

@@ -193,7 +193,8 @@ int hebb_uses_tensor_cores(const HebbDesc* d, int prec);
 /* Tile plan the tensor-core path would use (0 if it would not run there): fills out[0..n) with
  * {MB, fwd SEGLEN, XST, WST, NACC, fwd TMEM cols, fwd tiles, fwd smem, dW by_kh, CM, CN, BLK, ST, dW SEGLEN,
  *  tap groups, cin tiles, cout tiles, position splits, position blocks, dW TMEM cols, dW smem, dW HL, ws MiB,
- *  stackM, stackN, CT, channel tiles, nrep, WG, dW collector re-use, dW tap halo};
+ *  stackM, stackN, CT, channel tiles, nrep, WG, dW collector re-use, dW tap halo, swizzled-response variant available,
+ *  and its BLK, ST, smem, TMEM cols, position splits, stackM};
  * returns the number of fields. */
 int hebb_debug_plan(const HebbDesc* d, int prec, int* out, int n);
 

@@ -102,6 +102,32 @@ def test_planner_swizzled_response_variant_only_where_it_applies():
     assert _native.plan(_desc3(8, 64, 64, (24, 24, 20), k=1), _native.PREC_BF16)['rsw'] == 0
 
 
+def test_planner_invariants_over_a_shape_grid():
+    """Every plan the tensor-core planner returns must fit the machine: shared memory <= 227 KB, TMEM <= 512 columns,
+    the update kernel one wave (or unsplit), the swizzled-response variant 1024-byte-aligned stages within the same
+    limits.  Swept over channel counts, image sizes, 2-D/3-D and both tensor-core precision modes."""
+    n = 0
+    for nd, sps in ((2, ((16, 16), (64, 64), (256, 256), (33, 17))), (3, ((6, 6, 5), (12, 12, 10), (48, 48, 40), (96, 96, 80)))):
+        for sp in sps:
+            for cin in (1, 3, 16, 32, 64, 128, 256, 512):
+                for cout in (16, 32, 64, 128, 256, 1024):
+                    if nd == 3 and max(sp) >= 48 and cin * cout > 128 * 128:
+                        continue                                  # beyond the networks' shapes (and the workspace)
+                    for prec in (_native.PREC_BF16X3, _native.PREC_BF16):
+                        p = _native.plan(_desc3(4, cin, cout, sp), prec)
+                        if p is None:
+                            continue
+                        n += 1
+                        assert p['f_smem'] <= 227 * 1024 and p['d_smem'] <= 227 * 1024, (nd, sp, cin, cout, prec, p)
+                        assert p['f_tmem'] <= 512 and p['d_tmem'] <= 512
+                        assert p['ngrp'] * p['n_cin'] * p['n_cout'] * p['PS'] <= 148 or p['PS'] == 1
+                        if p['rsw']:
+                            assert cout in (64, 128) and (cin == 64 or cin % 128 == 0)
+                            assert p['rs_smem'] <= 226 * 1024 and p['rs_tmem'] <= 512 and p['rs_BLK'] % 16 == 0
+                            assert p['rs_PS'] >= 1 and p['rs_stackM'] == (1 if (cin == 64 and prec == _native.PREC_BF16X3) else 0)
+    assert n > 500
+
+
 def test_no_cpu_fallback():
     layer = hebb.HebbianConv2d(3, 8, 3, padding=1, alpha=1.)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
