@@ -1,33 +1,35 @@
 // C-ABI entry points of libhebb_sm100.so (see include/hebb_sm100.h).
 #include "common.cuh"
+#include <atomic>
 #include <mutex>
 
 namespace hebb {
 
 thread_local int g_last_cuda_error = 0;
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
-static int g_dev_checked = 0;   // 0 unknown, 1 ok, -1 bad
-static int g_num_sms = 148;
-static int g_sm_major = 0, g_sm_minor = 0;
+// Per-device cache of the properties the launches need (a process may drive several B200s, one current at a time).
+constexpr int kMaxDev = 64;
+static int g_dev_state[kMaxDev];   // 0 unknown, 1 sm_100, -1 anything else
+static int g_dev_sms[kMaxDev], g_dev_major[kMaxDev], g_dev_minor[kMaxDev];
 static std::mutex g_mu;
 
-static void probe_device() {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_dev_checked) return;
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { (void)cudaGetLastError(); g_dev_checked = -1; return; }
+// Returns the current device's slot (after probing it once), or -1 without a usable CUDA device.
+static int current_slot() {
   int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { (void)cudaGetLastError(); return -1; }
+  if (g_dev_state[dev]) return dev;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_dev_state[dev]) return dev;
   cudaDeviceProp p;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
-    (void)cudaGetLastError(); g_dev_checked = -1; return;
-  }
-  g_sm_major = p.major; g_sm_minor = p.minor; g_num_sms = p.multiProcessorCount;
-  g_dev_checked = (p.major == 10) ? 1 : -1;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+  g_dev_major[dev] = p.major; g_dev_minor[dev] = p.minor; g_dev_sms[dev] = p.multiProcessorCount;
+  g_dev_state[dev] = (p.major == 10) ? 1 : -1;
+  return dev;
 }
 
-int device_ok() { if (!g_dev_checked) probe_device(); return g_dev_checked == 1 ? HEBB_OK : HEBB_EARCH; }
-int num_sms() { if (!g_dev_checked) probe_device(); return g_num_sms; }
+int device_ok() { const int s = current_slot(); return (s >= 0 && g_dev_state[s] == 1) ? HEBB_OK : HEBB_EARCH; }
+int num_sms() { const int s = current_slot(); return s >= 0 ? g_dev_sms[s] : 148; }
 
 int resolve_geo(const HebbDesc* d, Geo* g) {
   if (!d || !g) return HEBB_EARG;
@@ -71,9 +73,10 @@ extern "C" {
 
 int hebb_query(int* sm_major, int* sm_minor, int* n_sms) {
   const int ok = device_ok();
-  if (sm_major) *sm_major = g_sm_major;
-  if (sm_minor) *sm_minor = g_sm_minor;
-  if (n_sms) *n_sms = g_num_sms;
+  const int sl = current_slot();
+  if (sm_major) *sm_major = sl >= 0 ? g_dev_major[sl] : 0;
+  if (sm_minor) *sm_minor = sl >= 0 ? g_dev_minor[sl] : 0;
+  if (n_sms) *n_sms = sl >= 0 ? g_dev_sms[sl] : 0;
   return ok;
 }
 
@@ -93,7 +96,7 @@ const char* hebb_status_str(int s) {
 
 int hebb_last_cuda_error(void) { return g_last_cuda_error; }
 
-unsigned long long hebb_debug_launch_count(void) { return g_launches; }
+unsigned long long hebb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* hebb_version(void) { return "hebb_sm100 0.1 (sm_100a; fp32 CUDA-core + tcgen05 bf16/bf16x3)"; }
 

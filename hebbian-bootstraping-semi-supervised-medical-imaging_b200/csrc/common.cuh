@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include "hebb_sm100.h"
 
 namespace hebb {
@@ -10,8 +11,8 @@ namespace hebb {
 // Thread-local record of the last failing CUDA runtime call (hebb_last_cuda_error()).
 extern thread_local int g_last_cuda_error;
 // Number of kernels this library has launched in this process (hebb_debug_launch_count()).
-extern unsigned long long g_launches;
-#define HEBB_LAUNCHED() (++::hebb::g_launches)
+extern std::atomic<unsigned long long> g_launches;
+#define HEBB_LAUNCHED() (::hebb::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 #define HEBB_CUDA_TRY(expr)                                   \
   do {                                                        \
@@ -75,6 +76,13 @@ int simt_convT_step(const Geo& g, const float* x, const float* W, const float* b
 
 // delta_w[c][j] -= sum_{c' <= c} G[c][c'] W[c'][j]   (HPCA decay on the CUDA cores; G, W fp32)
 int launch_hpca_decay(const float* G, const float* W, float* delta_w, int Cout, int K, cudaStream_t st);
+
+// ---- exact winners for near-tie pixels (fixup.cu) ----
+// Re-evaluates the pixels listed in list[0 .. min(*count, cap)) (indices into `winner`) from the fp32 inputs with
+// fp64 accumulation and rewrites winner[]: argmax_c of  (sum_k x_k W[c][k]) * inv[c] + bias[c]  (plain conv,
+// inv per output channel) or of the transposed convolution with inv per INPUT channel.  W: [Cout][Cin][taps].
+int launch_winner_fixup(const Geo& g, const float* x, const float* W, const float* inv, const float* bias,
+                        int32_t* winner, const int* list, const int* count, int cap, cudaStream_t st);
 
 // ---- tcgen05 path (tc_path.cu) ----
 bool tc_supported(const Geo& g, int prec);

@@ -47,6 +47,12 @@ __device__ __forceinline__ long long r_index(int rsw, long long PRS, int g8, lon
   return rsw ? (((long long)(g8 >> 3) * PRS + pp) * 8 + ((g8 & 7) ^ (int)(pp & 7))) : ((long long)g8 * PRS + pp);
 }
 
+// Appends winner-array index `pid` to the near-tie worklist (see fixup.cu).
+__device__ __forceinline__ void flag_tie(int* list, int* count, int cap, long long pid) {
+  const int i = atomicAdd(count, 1);
+  if (i < cap) list[i] = (int)pid;
+}
+
 // -------------------------------------------------------------------------------------
 // Packing kernels
 // -------------------------------------------------------------------------------------
@@ -351,6 +357,8 @@ struct FwdParams {
   int WP, plane, Qimg, oD, oH, oW;
   float kinv; int write_r;
   int dbg;                     // HEBB_FWD_DBG bit mask (profiling only): 1 skip epilogue, 2 skip MMAs, 4 no y stores, 8 no r stores
+  // near-tie worklist (fixup.cu): pixels whose top-2 margin is below tie_rel * max_c |y_c| are re-evaluated exactly
+  int* fix_list; int* fix_count; int fix_cap; float tie_rel;
   int seg_base[4]; int seg_tap_begin[5]; int tap_off[kMaxTaps];
   uint32_t x_stage_bytes, w_stage_bytes, off_w, off_misc;
   uint32_t tmem_cols;
@@ -635,11 +643,12 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
         const int cw = (p.stackF ? 2 : 1) * p.CT;
         const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.MB * cw + j * cw;
         float mx = -INFINITY, best = -INFINITY;
+        float second = -INFINITY, amax = 0.f;       // runner-up and largest |y| of the pixel: near-tie test (fixup.cu)
         int bi = 0;
-        float mx8[8], best8[8];
+        float mx8[8], best8[8], second8[8], amax8[8];
         int bi8[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { mx8[i] = -INFINITY; best8[i] = -INFINITY; bi8[i] = 0; }
+        for (int i = 0; i < 8; ++i) { mx8[i] = -INFINITY; best8[i] = -INFINITY; bi8[i] = 0; second8[i] = -INFINITY; amax8[i] = 0.f; }
         uint32_t v[CH];
         if constexpr (SP > 0) {
           // ---- single pass: y = acc * 1/|w| + b, winner, r = softmax(k y), bf16 split, running column sums ----
@@ -678,10 +687,16 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
           for (int i = 0; i < NV; ++i) {
             if (valid) yb[(long long)i * outS] = f[i];
             if (f[i] > best) { best = f[i]; bi = i; }          // strict: the lowest index wins ties
-            f[i] *= k2;
-            mx2 = fmaxf(mx2, f[i]);
           }
-          if (p.winner && valid) p.winner[(long long)b * outS + s] = bi;
+          if (p.winner && valid) {
+            p.winner[(long long)b * outS + s] = bi;
+            float second = -INFINITY, amax = 0.f;              // runner-up and scale of this pixel
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { second = fmaxf(second, i == bi ? -INFINITY : f[i]); amax = fmaxf(amax, fabsf(f[i])); }
+            if (best - second <= p.tie_rel * amax) flag_tie(p.fix_list, p.fix_count, p.fix_cap, (long long)b * outS + s);
+          }
+#pragma unroll
+          for (int i = 0; i < NV; ++i) { f[i] *= k2; mx2 = fmaxf(mx2, f[i]); }
           if (p.write_r) {
             float sum = 0.f;
 #pragma unroll
@@ -729,6 +744,7 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
             float* yo = ytb + sub;
             const int cb = bk * p.trQ;
             float mxa = -INFINITY, mxb = -INFINITY, besta = -INFINITY, bestb = -INFINITY;
+            float seca = -INFINITY, secb = -INFINITY, amaxa = 0.f, amaxb = 0.f;
             int bia = 0, bib = 0;
             for (int c0 = cb; c0 < cb + p.trQ; c0 += CH) {
               ld_acc<CH>(ta + c0, 0, v);
@@ -740,13 +756,16 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
                 o.y = __uint_as_float(v[i + 1]) + s_bias[c0 + i + 1];
                 if (valid) *reinterpret_cast<float2*>(yo + (long long)co * tS) = o;
                 mxa = fmaxf(mxa, o.x * p.kinv); mxb = fmaxf(mxb, o.y * p.kinv);
-                if (o.x > besta) { besta = o.x; bia = co; }
-                if (o.y > bestb) { bestb = o.y; bib = co; }
+                if (o.x > besta) { seca = besta; besta = o.x; bia = co; } else seca = fmaxf(seca, o.x);
+                if (o.y > bestb) { secb = bestb; bestb = o.y; bib = co; } else secb = fmaxf(secb, o.y);
+                amaxa = fmaxf(amaxa, fabsf(o.x)); amaxb = fmaxf(amaxb, fabsf(o.y));
               }
             }
             if (p.winner && valid) {
               int32_t* wb = p.winner + (long long)b * tS + ((long long)(2 * od) * p.tH + 2 * oh) * p.tW + 2 * ow + sub;
               *reinterpret_cast<int2*>(wb) = make_int2(bia, bib);
+              if (besta - seca <= p.tie_rel * amaxa) flag_tie(p.fix_list, p.fix_count, p.fix_cap, wb - p.winner);
+              if (bestb - secb <= p.tie_rel * amaxb) flag_tie(p.fix_list, p.fix_count, p.fix_cap, wb - p.winner + 1);
             }
             if (!p.write_r) continue;
             float suma = 0.f, sumb = 0.f;
@@ -804,8 +823,11 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               // per-offset statistics: one softmax over the real channels for each of the 8 output voxels
               mx8[i & 7] = fmaxf(mx8[i & 7], o.x * p.kinv);
               mx8[(i + 1) & 7] = fmaxf(mx8[(i + 1) & 7], o.y * p.kinv);
-              if (o.x > best8[i & 7]) { best8[i & 7] = o.x; bi8[i & 7] = cc >> 3; }
-              if (o.y > best8[(i + 1) & 7]) { best8[(i + 1) & 7] = o.y; bi8[(i + 1) & 7] = cc >> 3; }
+              if (o.x > best8[i & 7]) { second8[i & 7] = best8[i & 7]; best8[i & 7] = o.x; bi8[i & 7] = cc >> 3; }
+              else second8[i & 7] = fmaxf(second8[i & 7], o.x);
+              if (o.y > best8[(i + 1) & 7]) { second8[(i + 1) & 7] = best8[(i + 1) & 7]; best8[(i + 1) & 7] = o.y; bi8[(i + 1) & 7] = cc >> 3; }
+              else second8[(i + 1) & 7] = fmaxf(second8[(i + 1) & 7], o.y);
+              amax8[i & 7] = fmaxf(amax8[i & 7], fabsf(o.x)); amax8[(i + 1) & 7] = fmaxf(amax8[(i + 1) & 7], fabsf(o.y));
             }
           } else {
             float t1[CH], t2[CH];
@@ -814,7 +836,8 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
               const float f = fmaf(__uint_as_float(v[i]), s_inv[c0 + i], s_bias[c0 + i]);
               if (valid) yb[(long long)(c0 + i) * outS] = f;
               mx = fmaxf(mx, f * p.kinv);
-              if (f > best) { best = f; bi = c0 + i; }
+              if (f > best) { second = best; best = f; bi = c0 + i; } else second = fmaxf(second, f);
+              amax = fmaxf(amax, fabsf(f));
               t1[i] = valid ? f : 0.f; t2[i] = t1[i] * t1[i];
             }
             if (want_ys) {
@@ -828,8 +851,11 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
           if (p.winner && valid) {
             int32_t* wb = p.winner + (long long)b * tS + ((long long)(2 * od) * p.tH + 2 * oh) * p.tW + 2 * ow;
 #pragma unroll
-            for (int off = 0; off < 8; ++off)
-              wb[((long long)(off >> 2) * p.tH + ((off >> 1) & 1)) * p.tW + (off & 1)] = bi8[off];
+            for (int off = 0; off < 8; ++off) {
+              const long long wo = ((long long)(off >> 2) * p.tH + ((off >> 1) & 1)) * p.tW + (off & 1);
+              wb[wo] = bi8[off];
+              if (best8[off] - second8[off] <= p.tie_rel * amax8[off]) flag_tie(p.fix_list, p.fix_count, p.fix_cap, wb + wo - p.winner);
+            }
           }
           if (p.write_r) {
             float sum8[8];
@@ -873,7 +899,10 @@ fwd_swta_kernel(const __grid_constant__ FwdParams p) {
           }
           continue;
         }
-        if (p.fuse && p.winner && valid) p.winner[(long long)b * outS + s] = bi;
+        if (p.fuse && p.winner && valid) {
+          p.winner[(long long)b * outS + s] = bi;
+          if (best - second <= p.tie_rel * amax) flag_tie(p.fix_list, p.fix_count, p.fix_cap, (long long)b * outS + s);
+        }
         if (p.fuse && p.write_r) {
           float sum = 0.f;
           for (int c0 = 0; c0 < p.CT; c0 += CH) {
@@ -966,6 +995,7 @@ struct SmxParams {
   int Cout, RHL, WP, plane, Qimg, oD, oH, oW;
   long long PR, PTOT, PRS;
   float kinv;
+  int* fix_list; int* fix_count; int fix_cap; float tie_rel;      // near-tie worklist (fixup.cu)
 };
 
 // A block takes 32 consecutive packed positions (the lanes: for one channel their y values are contiguous, so
@@ -974,7 +1004,7 @@ struct SmxParams {
 // per position over all channels: 28 blocks of 128 threads and 380 us for the 1024-channel layers of the 3-D net.)
 __global__ void __launch_bounds__(256)
 swta_softmax_pack_kernel(const __grid_constant__ SmxParams p) {
-  __shared__ float s_mx[8][32], s_best[8][32], s_sum[8][32];
+  __shared__ float s_mx[8][32], s_best[8][32], s_sum[8][32], s_sec[8][32], s_amax[8][32];
   __shared__ int s_bi[8][32];
   const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
   const long long pp = (long long)blockIdx.x * 32 + lane;
@@ -990,7 +1020,7 @@ swta_softmax_pack_kernel(const __grid_constant__ SmxParams p) {
   const float* yb = p.y + (long long)b * p.Cout * outS + s;
   const int C8 = p.Cout / 8;
   // pass 1: maximum of k*y and the winner (largest y, lowest index on ties) over this warp's chunks
-  float mx = -INFINITY, best = -INFINITY;
+  float mx = -INFINITY, best = -INFINITY, second = -INFINITY, amax = 0.f;
   int bi = 0x7fffffff;
   if (valid)
     for (int c8 = wg; c8 < C8; c8 += 8) {
@@ -999,19 +1029,27 @@ swta_softmax_pack_kernel(const __grid_constant__ SmxParams p) {
         const int c = c8 * 8 + i;
         const float f = __ldg(yb + (long long)c * outS);
         mx = fmaxf(mx, f * p.kinv);
-        if (f > best) { best = f; bi = c; }
+        if (f > best) { second = best; best = f; bi = c; } else second = fmaxf(second, f);
+        amax = fmaxf(amax, fabsf(f));
       }
     }
-  s_mx[wg][lane] = mx; s_best[wg][lane] = best; s_bi[wg][lane] = bi;
+  s_mx[wg][lane] = mx; s_best[wg][lane] = best; s_bi[wg][lane] = bi; s_sec[wg][lane] = second; s_amax[wg][lane] = amax;
   __syncthreads();
+  best = -INFINITY; second = -INFINITY; bi = 0x7fffffff;
 #pragma unroll
   for (int w = 0; w < 8; ++w) {
     mx = fmaxf(mx, s_mx[w][lane]);
+    amax = fmaxf(amax, s_amax[w][lane]);
     const float ob = s_best[w][lane];
     const int oi = s_bi[w][lane];
-    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    second = fmaxf(second, s_sec[w][lane]);
+    if (ob > best || (ob == best && oi < bi)) { second = fmaxf(second, best); best = ob; bi = oi; }
+    else second = fmaxf(second, ob);
   }
-  if (wg == 0 && valid && p.winner) p.winner[(long long)b * outS + s] = bi;
+  if (wg == 0 && valid && p.winner) {
+    p.winner[(long long)b * outS + s] = bi;
+    if (best - second <= p.tie_rel * amax) flag_tie(p.fix_list, p.fix_count, p.fix_cap, (long long)b * outS + s);
+  }
   // pass 2: sum of exponentials
   float sum = 0.f;
   if (valid)
@@ -1076,26 +1114,30 @@ swta_softmax_pack_T_kernel(const __grid_constant__ SmxParams p, int tD, int tH, 
   long long o8[8];
 #pragma unroll
   for (int off = 0; off < 8; ++off) o8[off] = ((long long)(off >> 2) * tH + ((off >> 1) & 1)) * tW + (off & 1);
-  float mx[8], sum[8], best[8];
+  float mx[8], sum[8], best[8], sec[8], amx[8];
   int bi[8];
 #pragma unroll
-  for (int off = 0; off < 8; ++off) { mx[off] = -INFINITY; sum[off] = 0.f; best[off] = -INFINITY; bi[off] = 0x7fffffff; }
+  for (int off = 0; off < 8; ++off) { mx[off] = -INFINITY; sum[off] = 0.f; best[off] = -INFINITY; bi[off] = 0x7fffffff; sec[off] = -INFINITY; amx[off] = 0.f; }
   if (valid) {
     for (int c = lane; c < CoutR; c += 32)
 #pragma unroll
       for (int off = 0; off < 8; off += 2) {
         const float2 f2 = __ldg(reinterpret_cast<const float2*>(yb + (long long)c * tS + o8[off]));
         mx[off] = fmaxf(mx[off], f2.x * p.kinv); mx[off + 1] = fmaxf(mx[off + 1], f2.y * p.kinv);
-        if (f2.x > best[off]) { best[off] = f2.x; bi[off] = c; }
-        if (f2.y > best[off + 1]) { best[off + 1] = f2.y; bi[off + 1] = c; }
+        if (f2.x > best[off]) { sec[off] = best[off]; best[off] = f2.x; bi[off] = c; } else sec[off] = fmaxf(sec[off], f2.x);
+        if (f2.y > best[off + 1]) { sec[off + 1] = best[off + 1]; best[off + 1] = f2.y; bi[off + 1] = c; } else sec[off + 1] = fmaxf(sec[off + 1], f2.y);
+        amx[off] = fmaxf(amx[off], fabsf(f2.x)); amx[off + 1] = fmaxf(amx[off + 1], fabsf(f2.y));
       }
 #pragma unroll
     for (int off = 0; off < 8; ++off) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         mx[off] = fmaxf(mx[off], __shfl_xor_sync(0xffffffffu, mx[off], o));
+        amx[off] = fmaxf(amx[off], __shfl_xor_sync(0xffffffffu, amx[off], o));
         const float ob = __shfl_xor_sync(0xffffffffu, best[off], o);
+        const float os = __shfl_xor_sync(0xffffffffu, sec[off], o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi[off], o);
+        sec[off] = fmaxf(fmaxf(sec[off], os), fminf(best[off], ob));      // runner-up of the merged sets
         if (ob > best[off] || (ob == best[off] && oi < bi[off])) { best[off] = ob; bi[off] = oi; }   // lowest index wins ties
       }
     }
@@ -1117,7 +1159,12 @@ swta_softmax_pack_T_kernel(const __grid_constant__ SmxParams p, int tD, int tH, 
       int sel = bi[0];
 #pragma unroll
       for (int off = 1; off < 8; ++off) sel = (lane == off) ? bi[off] : sel;
-      wb[o8[0] + (((long long)(lane >> 2) * tH + ((lane >> 1) & 1)) * tW + (lane & 1))] = sel;
+      const long long wo = o8[0] + (((long long)(lane >> 2) * tH + ((lane >> 1) & 1)) * tW + (lane & 1));
+      wb[wo] = sel;
+      float bsel = best[0], ssel = sec[0], asel = amx[0];
+#pragma unroll
+      for (int off = 1; off < 8; ++off) { bsel = (lane == off) ? best[off] : bsel; ssel = (lane == off) ? sec[off] : ssel; asel = (lane == off) ? amx[off] : asel; }
+      if (bsel - ssel <= p.tie_rel * asel) flag_tie(p.fix_list, p.fix_count, p.fix_cap, wb + wo - p.winner);
     }
   }
   for (int c = lane; c < CoutR; c += 32) {
@@ -1664,7 +1711,8 @@ struct Plan {
   uint32_t rs_stage, rs_x_bytes, rs_off_bar, rs_smem, rs_tmem;
   uint32_t d_stage, d_x_bytes, d_off_bar, d_smem, d_tmem;
   // workspace carve (byte offsets)
-  size_t o_inv, o_rsum, o_err, o_xp[2], o_rp[2], o_wp, o_hpart, o_gram, o_hpart2, total;
+  size_t o_inv, o_rsum, o_err, o_xp[2], o_rp[2], o_wp, o_hpart, o_gram, o_hpart2, o_fix, total;
+  int fix_cap;                    // entries of the near-tie worklist (fixup.cu); its counter sits 16 bytes after the error word
   bool ok, gram_ok;
 };
 
@@ -1971,6 +2019,8 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   q.o_rp[0] = take((size_t)q.C8 * q.PRS * 16);
   q.o_rp[1] = take((size_t)q.C8 * q.PRS * 16);
   q.o_wp = take((size_t)q.NSLAB * g.taps * q.f_HL * 2 * g.Cout * 16);
+  q.fix_cap = (int)((q.PTOT * 8) < (1LL << 18) ? (q.PTOT * 8) : (1LL << 18));     // (a transposed layer has 8 outputs per position)
+  q.o_fix = take(sizeof(int) * (size_t)q.fix_cap);
   {
     size_t hp = (size_t)q.PS * q.Q * g.taps * q.CinP * g.Cout * sizeof(float);
     const size_t hp2 = q.rsw ? (size_t)q.rs_PS * (q.rs_stackM ? 2 : 1) * g.taps * q.rs_CinP * g.Cout * sizeof(float) : 0;
@@ -2256,6 +2306,12 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   f.Cout = g.Cout; f.CC = P.CC; f.NSLAB = P.NSLAB; f.taps = g.taps; f.nseg = P.f_nseg; f.HL = P.f_HL; f.RHL = P.d_HL;
   static const int fwd_dbg = [] { const char* e = getenv("HEBB_FWD_DBG"); return e ? atoi(e) : 0; }();
   f.dbg = fwd_dbg;
+  // near-tie worklist: the forward error is a few 1e-6 of the pixel's response scale; 2.5e-4 leaves a wide margin and
+  // still lists only ~1e-3 of the pixels (HEBB_TIE_REL overrides; 0 disables the exact pass)
+  static const float tie_rel = [] { const char* e = getenv("HEBB_TIE_REL"); return e ? (float)atof(e) : 2.5e-4f; }();
+  int* fix_count = err + 4;
+  int* fix_list = reinterpret_cast<int*>(base + P.o_fix);
+  f.fix_list = fix_list; f.fix_count = fix_count; f.fix_cap = P.fix_cap; f.tie_rel = tie_rel;
   f.stackF = P.stackF; f.CT = P.CT; f.n_ct = P.n_ct; f.fuse = (P.n_ct == 1 || trq) ? 1 : 0;   // transposed: grouped softmax when Cout*8 <= 512
   f.PA = P.PA; f.PR = P.PR; f.PRS = P.PRS; f.rsw = rsw ? 1 : 0; f.PTOT = P.PTOT; f.MB = P.MB; f.TILE_M = P.TILE_M; f.ntiles = P.f_ntiles; f.SEGLEN = P.f_SEGLEN;
   f.XST = P.XST; f.WST = P.WST; f.NACC = P.NACC; f.WG = P.WG;
@@ -2294,6 +2350,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     sp.y = y; sp.rp[0] = rp0; sp.rp[1] = rp1; sp.winner = winner; sp.rsum = rsum;
     sp.Cout = g.Cout; sp.RHL = P.d_HL; sp.WP = P.WP; sp.plane = P.plane; sp.Qimg = P.Qimg;
     sp.oD = g.oD; sp.oH = g.oH; sp.oW = g.oW; sp.PR = P.PR; sp.PRS = P.PRS; sp.PTOT = P.PTOT; sp.kinv = kinv;
+    sp.fix_list = fix_list; sp.fix_count = fix_count; sp.fix_cap = P.fix_cap; sp.tie_rel = tie_rel;
     if (tr) {
       sp.Cout = g.Cout;
       swta_softmax_pack_T_kernel<<<(unsigned)cdiv(P.PR, 8), 256, 0, st>>>(sp, g0.oD, g0.oH, g0.oW, g0.Cout);
@@ -2306,6 +2363,9 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     }
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
+  // exact re-evaluation of the listed near-tie pixels (winner indices bit-exact with the reference's argmax)
+  if (do_fwd && winner && tie_rel > 0.f)
+    HEBB_TRY(launch_winner_fixup(g0, x, W, (flags & HEBB_F_WNRM) ? inv : nullptr, bias, winner, fix_list, fix_count, P.fix_cap, st));
   if (!do_dw) return HEBB_OK;
 
   if (hpca) {

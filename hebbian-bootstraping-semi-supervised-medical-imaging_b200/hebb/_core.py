@@ -319,10 +319,40 @@ class _HebbianConvNd(nn.Module):
                 "implements the pretraining path ('{}', patchwise=True) and has no PyTorch fallback".format(
                     self.mode, self.patchwise, self.__class__.__name__, native))
 
+    def _act_is_identity(self):
+        return self.act is None or isinstance(self.act, nn.Identity)
+
+    def _update_through_act(self, x, ya, pad=True):
+        """Soft-WTA update for a layer with a non-Identity `act`: the reference feeds act(conv(x)) to the rule
+        (hebb.py:80,87-90,107), so the responses are r = softmax_c(k * act(y)) and the fused epilogue (which sees the
+        pre-activation y) cannot be used.  r is formed with element-wise torch ops; both contractions stay on the
+        sm_100 kernels: delta_w += r X - (sum_p r) W  with r X = hebb_conv_wgrad(x, r)."""
+        if self._transposed or self.mode != self.MODE_SWTA or not self.patchwise:
+            raise NotImplementedError(
+                'a non-Identity act is supported for plain convolutions in swta/patchwise mode only '
+                '(the reference applies the plasticity rule to act(y): hebb.py:80,107)')
+        prec = _native.parse_prec(self.prec)
+        if prec == _native.PREC_FP32:
+            prec = _native.PREC_BF16X3
+        desc = self._desc(x.shape, pad)
+        with torch.no_grad():
+            r = (ya.detach() * float(self.k)).softmax(dim=1).contiguous()
+            h = _native.conv_wgrad(desc, x.detach().contiguous(), r, prec)
+            if h is None:
+                raise NotImplementedError('this layer shape is outside the tensor-core planner; a non-Identity act is '
+                                          'only supported on layers the tcgen05 kernels take')
+            rs = r.sum(dim=tuple(i for i in range(r.dim()) if i != 1))
+            w = self.weight.detach()
+            self.delta_w += h.reshape(w.shape) - rs.view(-1, *([1] * (w.dim() - 1))) * w
+
     def forward(self, x):
         update = bool(self.training and self.alpha != 0)
         if update:
             self._check_mode()
+        if update and not self._act_is_identity() and self.mode != self.MODE_CONTRASTIVE:
+            y = self.act(self._forward_no_update(x))
+            self._update_through_act(x, y)
+            return y
         w = self.weight
         if self.alpha == 1:
             w = w.detach()       # (1 - alpha) * grad == 0 in local_update(): no need to back-prop into W
@@ -337,6 +367,13 @@ class _HebbianConvNd(nn.Module):
         if contrastive:
             self._contrastive_update(x)
         return self.act(y)
+
+    def _forward_no_update(self, x):
+        w = self.weight.detach() if self.alpha == 1 else self.weight
+        b = self.bias
+        if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
+            return _HebbFn.apply(x, w, b, self, False)
+        return self._launch(x, w, b, False)
 
     def _contrastive_update(self, x):
         """hebb.py:143-172: delta_w += dL/dW of  L = sum [ -(S*y) + contrast * (S[perm]*y) ],  y = the layer
@@ -364,6 +401,8 @@ class _HebbianConvNd(nn.Module):
         """Accumulate the plasticity update for an already padded x into delta_w (y is recomputed
         on chip; the argument is accepted for signature compatibility)."""
         self._check_mode()
+        if not self._act_is_identity() and self.mode != self.MODE_CONTRASTIVE:
+            return self._update_through_act(x, y, pad=False)
         self._launch(x, self.weight, self.bias, update=True, pad=False)
 
     @torch.no_grad()

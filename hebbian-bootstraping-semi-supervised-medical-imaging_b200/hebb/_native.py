@@ -188,6 +188,26 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _device_guard(argidx):
+    """Run the wrapped launch with the CUDA device of its tensor argument current (like torch's own ops): the C
+    library launches on the current device with the stream handle of the tensor's device."""
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapped(*a, **k):
+            t = a[argidx]
+            if isinstance(t, (list, tuple)):
+                t = t[0] if len(t) else None
+            if t is None or not getattr(t, 'is_cuda', False) or t.device.index == torch.cuda.current_device():
+                return fn(*a, **k)
+            with torch.cuda.device(t.device):
+                return fn(*a, **k)
+        return wrapped
+    return deco
+
+
+@_device_guard(1)
 def conv_step(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w, flags: int, prec: int):
     """Launch hebb_conv_swta_step / hebb_convT_swta_step (by desc.transposed) on the current stream."""
     lib = load()
@@ -202,6 +222,7 @@ def conv_step(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w, flags
     check(st, 'conv_swta_step')
 
 
+@_device_guard(1)
 def conv_step_stats(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w, flags: int, prec: int):
     """hebb_conv_swta_step_stats: the step plus the BatchNorm statistics of y.  Returns the [Cout, 2] float64
     tensor (sum, sum of squares per channel) or None when the library did not produce them."""
@@ -218,6 +239,7 @@ def conv_step_stats(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w,
     return stats if written.value else None
 
 
+@_device_guard(0)
 def bn_act_from_stats(y, stats, gamma, beta, running_mean, running_var, eps, momentum, slope):
     """BatchNorm(train) + activation of y from precomputed per-channel (sum, sum of squares) (hebb_bn_act_from_stats)."""
     _require_cuda(y, 'input')
@@ -232,6 +254,7 @@ def bn_act_from_stats(y, stats, gamma, beta, running_mean, running_var, eps, mom
     return out
 
 
+@_device_guard(1)
 def conv_wgrad(desc: HebbDesc, x, grad_y, prec: int, gy_channels: int = 0, channels_last: bool = False):
     """grad_w[Cout][Cin][taps] of a stride-1 convolution on the tcgen05 contraction kernel (hebb_conv_wgrad).
     x / grad_y: dense NCHW (default) or dense channels_last storage.  Returns None when the layer is outside
@@ -250,6 +273,7 @@ def conv_wgrad(desc: HebbDesc, x, grad_y, prec: int, gy_channels: int = 0, chann
     return gw
 
 
+@_device_guard(0)
 def wnorm(W: torch.Tensor, rows: int, row_stride: int, mid: int, mid_stride: int, inner: int,
           want_inv: bool = False):
     """normalize() over the raw storage addressing described in hebb_sm100.h."""
@@ -261,6 +285,7 @@ def wnorm(W: torch.Tensor, rows: int, row_stride: int, mid: int, mid_stride: int
     return (out, inv) if want_inv else out
 
 
+@_device_guard(1)
 def local_update_multi(grads, dws, alphas, has_grad):
     """grad_i = (1-a_i) grad_i - a_i dw_i  (or -a_i dw_i), dw_i = 0, for all i in ONE launch."""
     n = len(dws)
@@ -286,6 +311,7 @@ def plan(desc: HebbDesc, prec: int):
     return dict(zip(PLAN_FIELDS, list(out)[:n])) if n else None
 
 
+@_device_guard(0)
 def bn_act_train(y, gamma, beta, running_mean, running_var, eps, momentum, slope, out=None):
     """BatchNorm(train) + (Leaky)ReLU on a contiguous [B, C, *spatial] fp32 CUDA tensor (hebb_bn_act_train)."""
     _require_cuda(y, 'input')
@@ -301,6 +327,7 @@ def bn_act_train(y, gamma, beta, running_mean, running_var, eps, momentum, slope
     return out
 
 
+@_device_guard(0)
 def upsample2x_bilinear(x):
     _require_cuda(x, 'input')
     B, C, H, W = x.shape
@@ -309,6 +336,7 @@ def upsample2x_bilinear(x):
     return out
 
 
+@_device_guard(0)
 def maxpool2x(x):
     """max_pool{2,3}d(kernel_size=2, stride=2) of a contiguous fp32 CUDA tensor (hebb_maxpool2x)."""
     _require_cuda(x, 'input')
@@ -334,6 +362,7 @@ def _dense_channel_inner(t):
     return None
 
 
+@_device_guard(0)
 def bias_relu_dropout(z, bias, p: float, seed: int):
     """(out, mask) = hebb_bias_relu_dropout on z's dense storage (NCHW or channels_last; out keeps z's layout)."""
     _require_cuda(z, 'input')
@@ -347,6 +376,7 @@ def bias_relu_dropout(z, bias, p: float, seed: int):
     return out, mask
 
 
+@_device_guard(0)
 def mask_scale(gout, mask, scale: float):
     gz = torch.empty_like(mask, dtype=torch.float32)
     check(load().hebb_mask_scale(gout.data_ptr(), mask.data_ptr(), gz.data_ptr(), gout.numel(), float(scale),

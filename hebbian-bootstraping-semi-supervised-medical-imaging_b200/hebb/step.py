@@ -4,11 +4,16 @@ The reference's training loop (pretrain_hebbian_unsup_2d.py:181-196) does, per b
     optimizer.zero_grad(); out = model(x); loss.backward()
     for m in model.modules():  m.local_update()      # if it has one
     optimizer.step()
-`HebbianStepper` restates that step with two B200-side changes that keep results identical:
-  * all delta_w buffers alias ONE flat fp32 buffer, so the data-parallel exchange is a single
-    all-reduce(sum) per step (the update is a sum over patches, hence additive over batch
-    shards — SURVEY.md §3.5-vi), and
-  * local_update() of every layer runs as one multi-tensor kernel launch.
+`HebbianStepper` restates that step with B200-side changes that keep results identical:
+  * all delta_w buffers alias ONE flat fp32 buffer, so the data-parallel exchange of the plasticity
+    updates is a single all-reduce(sum) per step (the update is a sum over patches, hence additive over
+    batch shards — SURVEY.md §3.5-vi); it is issued asynchronously right after the forward pass, so it
+    overlaps the backward pass of the back-prop head,
+  * the gradients of every back-prop parameter (the `exclude`d head of makehebbian, layers with
+    alpha < 1, trainable biases) alias a second flat buffer that is averaged over the ranks after the
+    backward pass (what DistributedDataParallel would do), so all replicas take the same optimiser step,
+  * local_update() of every layer runs as one multi-tensor kernel launch,
+  * optionally the whole step is replayed from a CUDA graph (`capture=True`).
 """
 from __future__ import annotations
 
@@ -44,7 +49,7 @@ def flatten_delta_w(model: nn.Module, align: int = 64) -> Optional[torch.Tensor]
     for m, o in zip(layers, offs):
         old = m.delta_w
         n = old.numel()
-        if getattr(m, '_transposed', False):
+        if getattr(m, '_transposed', False) or (not old.is_contiguous() and old.transpose(0, 1).is_contiguous()):
             base = flat[o:o + n].view(old.shape[1], old.shape[0], *old.shape[2:])
             base.copy_(old.transpose(0, 1))
             new = base.transpose(0, 1)
@@ -55,12 +60,52 @@ def flatten_delta_w(model: nn.Module, align: int = 64) -> Optional[torch.Tensor]
     return flat
 
 
+def backprop_parameters(model: nn.Module, layers: Optional[List[nn.Module]] = None) -> List[nn.Parameter]:
+    """Parameters whose .grad comes out of loss.backward(): everything trainable except the weights of fully
+    Hebbian layers (alpha == 1: their forward detaches the weight, hebb/_core.py, so autograd never reaches it and
+    weight.grad is produced by local_update() alone)."""
+    layers = hebbian_layers(model) if layers is None else layers
+    hebb_only = {id(m.weight) for m in layers if getattr(m, 'alpha', 0) == 1}
+    out, seen = [], set()
+    for p in model.parameters():
+        if p.requires_grad and id(p) not in hebb_only and id(p) not in seen:
+            seen.add(id(p))
+            out.append(p)
+    return out
+
+
+def flatten_grads(params: List[nn.Parameter], align: int = 64) -> Optional[torch.Tensor]:
+    """Point the .grad of every parameter into one flat zero-initialised buffer (dense parameters keep their
+    strides; anything else gets a contiguous gradient).  autograd accumulates in place into an existing .grad,
+    so the buffer IS the gradient after backward()."""
+    if not params:
+        return None
+    offs, total = [], 0
+    for p in params:
+        offs.append(total)
+        total += (p.numel() + align - 1) // align * align
+    flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
+    for p, o in zip(params, offs):
+        n = p.numel()
+        if p.is_contiguous():
+            g = flat[o:o + n].view(p.shape)
+        elif p.dim() >= 2 and p.transpose(0, 1).is_contiguous():        # the transposed-view weights of HebbianConvTranspose
+            g = flat[o:o + n].view(p.shape[1], p.shape[0], *p.shape[2:]).transpose(0, 1)
+        else:
+            g = flat[o:o + n].view(p.shape)
+        p.grad = g
+    return flat
+
+
 @torch.no_grad()
 def local_update_all(layers: List[nn.Module]):
     """Every layer's local_update() (hebb.py:174-192) in one kernel launch."""
     grads, dws, alphas, had = [], [], [], []
     for m in layers:
         dw = m.delta_w
+        if not dw.is_cuda:            # a layer that is not ours (the CPU oracle in the tests): its own method
+            m.local_update()
+            continue
         h = m.weight.grad is not None
         if not h:
             m.weight.grad = torch.empty_like(dw)
@@ -69,14 +114,21 @@ def local_update_all(layers: List[nn.Module]):
             m.local_update()          # odd layout: per-layer path handles it
             continue
         grads.append(g); dws.append(dw); alphas.append(m.alpha); had.append(h)
-    _native.local_update_multi(grads, dws, alphas, had)
+    if dws:
+        _native.local_update_multi(grads, dws, alphas, had)
 
 
 class HebbianStepper:
-    """One Hebbian pretraining step (the unit samples/s counts), optionally data-parallel."""
+    """One Hebbian pretraining step (the unit samples/s counts), optionally data-parallel.
+
+    process_group / allreduce: the data-parallel exchange (default: on iff torch.distributed is initialised with
+    more than one rank).  overlap: issue the delta_w all-reduce asynchronously after the forward pass.
+    capture: record the step (zero gradients, forward, loss, backward, local_update, optimiser step) into a CUDA
+    graph on first use and replay it afterwards; needs static input buffers (step() copies into them), a
+    capturable optimiser and no collective inside (single-process use)."""
 
     def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, criterion=None,
-                 process_group=None, allreduce: Optional[bool] = None):
+                 process_group=None, allreduce: Optional[bool] = None, overlap: bool = True, capture: bool = False):
         self.model = model
         self.optimizer = optimizer
         self.criterion = criterion
@@ -86,24 +138,112 @@ class HebbianStepper:
         if allreduce is None:
             allreduce = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
         self.allreduce = allreduce
+        self.overlap = overlap
+        self.world = dist.get_world_size(process_group) if (allreduce and dist.is_initialized()) else 1
+        self.bp_params = backprop_parameters(model, self.layers)
+        self.hebb_only = [m for m in self.layers if getattr(m, 'alpha', 0) == 1]
+        # the back-prop gradients live in one flat buffer: one collective, and zeroing them is one fill
+        self.flat_grad = flatten_grads(self.bp_params)
+        self._grad_views = [p.grad for p in self.bp_params] if self.flat_grad is not None else []
+        self._pending = None
+        self.capture = capture and not allreduce
+        self._graph = None
+        self._static = None
+
+    # ------------------------------------------------------------------ data-parallel exchange
+    def exchange_begin(self):
+        """Start summing the per-rank partial delta_w of ALL layers (one collective over the flat buffer)."""
+        if self.allreduce and self.flat is not None:
+            self._pending = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=self.overlap)
+
+    def exchange_end(self):
+        """Average the back-prop gradients over the ranks (one collective) and wait for the delta_w sum."""
+        if self.allreduce and self.flat_grad is not None:
+            self.flat_grad.mul_(1.0 / self.world)
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        if self._pending is not None:
+            self._pending.wait()
+        self._pending = None
 
     def exchange(self):
-        """Sum the per-rank partial delta_w of ALL layers with one collective."""
-        if self.allreduce and self.flat is not None:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        """Both collectives back to back (kept for callers that drive the step themselves)."""
+        self.exchange_begin()
+        self.exchange_end()
+
+    # ------------------------------------------------------------------ the step
+    def _zero_grad(self):
+        # == optimizer.zero_grad(): the back-prop gradients are zeroed in place (their storage is the flat buffer),
+        # the fully Hebbian weights get their gradient from local_update() alone
+        if self.flat_grad is not None:
+            self.flat_grad.zero_()
+            for p, g in zip(self.bp_params, self._grad_views):     # (a caller's own zero_grad() may have dropped the views)
+                p.grad = g
+        for m in self.hebb_only:
+            m.weight.grad = None
+
+    def _step_body(self, x, target):
+        self._zero_grad()
+        out = self.model(x)
+        self.exchange_begin()                 # delta_w of every layer is final once the forward pass is enqueued
+        loss = None
+        if self.criterion is not None and target is not None:
+            loss = self.criterion(out, target)
+            if loss.requires_grad:
+                loss.backward()
+        self.exchange_end()
+        local_update_all(self.layers)
+        self.optimizer.step()
+        return out, loss
 
     def step(self, x, target=None):
         if not self.model.training:          # forward-only use (e.g. throughput of the alpha=0 network)
             with torch.no_grad():
                 return self.model(x), None
-        self.optimizer.zero_grad()
+        if not self.capture:
+            return self._step_body(x, target)
+        return self._graph_step(x, target)
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def _graph_step(self, x, target):
+        if self._graph is None:
+            self._static = (x.clone(), target.clone() if target is not None else None)
+            sx, st = self._static
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):     # warm-up outside the capture (allocator, lazy initialisation)
+                for _ in range(2):
+                    self._step_body(sx, st)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            for m in self.hebb_only:          # a captured local_update must see the same gradient tensor every replay
+                if m.weight.grad is None:
+                    m.weight.grad = torch.zeros_like(m.delta_w)
+            self._keep_hebb_grads = True
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._out = self._captured_body(sx, st)
+            self._graph = g
+        sx, st = self._static
+        sx.copy_(x, non_blocking=True)
+        if st is not None:
+            st.copy_(target, non_blocking=True)
+        self._graph.replay()
+        return self._out
+
+    def _captured_body(self, x, target):
+        # like _step_body, but the fully Hebbian weights keep one persistent gradient tensor that local_update
+        # overwrites (grad = -alpha * delta_w): `had` must be False for them without dropping the tensor
+        if self.flat_grad is not None:
+            self.flat_grad.zero_()
         out = self.model(x)
         loss = None
         if self.criterion is not None and target is not None:
             loss = self.criterion(out, target)
             if loss.requires_grad:
                 loss.backward()
-        self.exchange()
-        local_update_all(self.layers)
+        grads, dws, alphas, had = [], [], [], []
+        hebb_only = {id(m) for m in self.hebb_only}
+        for m in self.layers:
+            grads.append(m.weight.grad); dws.append(m.delta_w); alphas.append(m.alpha); had.append(id(m) not in hebb_only)
+        _native.local_update_multi(grads, dws, alphas, had)
         self.optimizer.step()
         return out, loss

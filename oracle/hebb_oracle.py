@@ -247,7 +247,7 @@ class OracleHebbConv(nn.Module):
     """HebbianConv{2,3}d in SWTA/patchwise mode (hebb.py:16-192, hebb3d.py:15-216)."""
 
     def __init__(self, nd, cin, cout, kernel, stride=1, padding=0, bias=True,
-                 w_nrm=True, k=1., alpha=0.):
+                 w_nrm=True, k=1., alpha=0., act=None):
         super().__init__()
         self.nd = nd
         self.kernel_size = _tuple(kernel, nd)
@@ -258,10 +258,12 @@ class OracleHebbConv(nn.Module):
         self.bias = nn.Parameter(torch.zeros(cout), requires_grad=bias)
         self.register_buffer('delta_w', torch.zeros_like(self.weight))
         self.w_nrm, self.k, self.alpha = w_nrm, k, alpha
+        self.act = act if act is not None else nn.Identity()
 
     def forward(self, x):
         xp = zero_halo(x, self.padding, self.nd)
-        y = conv_activation(xp, self.weight, self.bias, self.stride, self.w_nrm)
+        # the rule sees the ACTIVATED output: y = act(conv(...)) feeds compute_update (hebb.py:80,87-90,107)
+        y = self.act(conv_activation(xp, self.weight, self.bias, self.stride, self.w_nrm))
         if self.training and self.alpha != 0:
             with torch.no_grad():
                 self.delta_w += swta_delta(xp, y, self.weight, self.k, self.stride)

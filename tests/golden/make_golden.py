@@ -327,5 +327,109 @@ def network_goldens(mk):
         json.dump(res, f)
 
 
+def round2_goldens():
+    """Round-2 fixtures (written to separate files so the round-1 arrays stay byte-identical):
+      hebb_golden_r2.npz   100-step weight drift of TENSOR-CORE-shaped layers (Cin = Cout = 64, 3x3 2-D and 3x3x3 3-D)
+                           under SGD and Adam, k = 50, plus an act=ReLU layer (the rule sees act(y), hebb.py:80,107)
+      network_steps_golden.json   the reference `unet` (2-D) / UNet3D(f=4) driven by the reference training loop
+                           (pretrain_hebbian_unsup_2d.py:181-196: zero_grad, forward, loss.backward, local_update of
+                           every layer, optimizer.step) for 1 and N steps, Adam with the reference learning rates,
+                           dropout off: per-layer digests of W and of the weight movement W_n - W_0."""
+    ref, mk = load_reference()
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import workloads
+    out, meta = {}, {}
+    g = torch.Generator().manual_seed(20261019)
+
+    def rnd(*shape, scale=1.0):
+        return torch.randn(*shape, generator=g) * scale
+
+    for nd, sp, B in ((2, (12, 12), 2), (3, (6, 6, 6), 1)):
+        cls = ref.HebbianConv2d if nd == 2 else ref.HebbianConv3d
+        w0 = rnd(64, 64, *([3] * nd), scale=(2.0 / (64 * 3 ** nd)) ** 0.5)
+        xs = rnd(4, B, 64, *sp)
+        out[f'drift64_{nd}d/xs'], out[f'drift64_{nd}d/w0'] = xs.numpy(), w0.numpy()
+        idx = torch.linspace(0, w0.numel() - 1, 8192).long()          # W after 1 / 100 steps: 8192 evenly spaced samples
+        out[f'drift64_{nd}d/idx'] = idx.numpy()
+        for opt_name in ('sgd', 'adam'):
+            layer = cls(64, 64, 3, padding=1, bias=False, k=50., alpha=1.)
+            with torch.no_grad():
+                layer.weight.copy_(w0)
+            opt = (torch.optim.SGD([layer.weight], lr=1e-3) if opt_name == 'sgd' else torch.optim.Adam([layer.weight], lr=1e-3))
+            layer.train()
+            w1 = None
+            for step in range(100):
+                opt.zero_grad()
+                layer(xs[step % 4])
+                layer.local_update()
+                opt.step()
+                if step == 0:
+                    w1 = layer.weight.detach().clone()
+            name = f'drift64_{nd}d_{opt_name}'
+            out[name + '/w1'] = w1.reshape(-1)[idx].numpy()
+            out[name + '/w100'] = layer.weight.detach().reshape(-1)[idx].numpy()
+            out[name + '/norms'] = np.array([float(w1.norm()), float(layer.weight.detach().norm())])
+            meta[name] = dict(kind='drift64', nd=nd, opt=opt_name, lr=1e-3, k=50., steps=100, spatial=list(sp), B=B)
+
+    # a layer with a non-Identity activation: the plasticity rule is applied to act(y)
+    for (name, Cin, Cout, sp) in [('act_relu_16_16', 16, 16, (12, 10)), ('act_relu_32_64', 32, 64, (9, 11))]:
+        layer = ref.HebbianConv2d(Cin, Cout, 3, padding=1, bias=True, w_nrm=True, act=nn.ReLU(), mode='swta', k=5., alpha=1.)
+        with torch.no_grad():
+            layer.weight.copy_(rnd(*layer.weight.shape, scale=0.3))
+            layer.bias.copy_(rnd(Cout, scale=0.1))
+        layer.train()
+        x = rnd(2, Cin, *sp)
+        y = layer(x)
+        out[name + '/x'], out[name + '/w'], out[name + '/b'] = x.numpy(), layer.weight.detach().numpy(), layer.bias.detach().numpy()
+        out[name + '/y'], out[name + '/dw1'] = y.detach().numpy(), layer.delta_w.clone().numpy()
+        meta[name] = dict(kind='act', Cin=Cin, Cout=Cout, spatial=list(sp), k=5., act='relu')
+    np.savez_compressed(os.path.join(HERE, 'hebb_golden_r2.npz'), **out)
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        r2 = _load_file(os.path.join(REF, 'models/networks_2d/unet.py'), 'ref_unet2d')
+        r3 = _load_file(os.path.join(REF, 'models/networks_3d/unet3d.py'), 'ref_unet3d')
+    hp = {'mode': 'swta_t', 'k': 50., 'w_nrm': True, 'alpha': 1.}
+    res = {}
+    # (Adam normalises every element's step to ~lr: its weight movement is sign-like.  The SGD run keeps the
+    #  movement linear in the accumulated updates, which makes a strict check of the summed delta_w possible.)
+    cases = [('unet2d', lambda: r2.unet(3, 2), workloads.EXCLUDE_2D, (2, 3, 32, 32), 1e-6, 20, 'adam'),
+             ('unet3d_f4', lambda: r3.UNet3D(1, 2, init_features=4), workloads.EXCLUDE_3D, (2, 1, 16, 16, 16), 1e-5, 10, 'adam'),
+             ('unet2d_sgd', lambda: r2.unet(3, 2), workloads.EXCLUDE_2D, (2, 3, 32, 32), 1e-7, 5, 'sgd')]
+    for name, ctor, excl, shape, lr, nsteps, opt_name in cases:
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = ctor()
+            mk.makehebbian(net, exclude=excl, hebb_params=hp)
+        workloads.deterministic_state_(net)
+        workloads.disable_dropout_(net)
+        net.train()
+        gg = torch.Generator().manual_seed(78)
+        xs = [torch.randn(*shape, generator=gg) for _ in range(2)]
+        ms = [torch.randint(0, 2, (shape[0], *shape[2:]), generator=gg) for _ in range(2)]
+        opt = torch.optim.Adam(net.parameters(), lr=lr) if opt_name == 'adam' else torch.optim.SGD(net.parameters(), lr=lr)
+        w0 = {n: p.detach().clone() for n, p in net.named_parameters() if p.requires_grad}
+        snaps = {}
+        for step in range(nsteps):
+            opt.zero_grad()
+            o = net(xs[step % 2])
+            loss = workloads.dice_loss(o, ms[step % 2])
+            loss.backward()
+            for m in net.modules():
+                if hasattr(m, 'local_update'):
+                    m.local_update()
+            opt.step()
+            if step in (0, nsteps - 1):
+                snaps[str(step + 1)] = dict(
+                    loss=float(loss),
+                    W={n: layer_digest(p) for n, p in net.named_parameters() if p.requires_grad},
+                    move={n: layer_digest((p.detach() - w0[n]) / lr) for n, p in net.named_parameters() if p.requires_grad})
+        res[name] = dict(shape=list(shape), lr=lr, steps=nsteps, opt=opt_name, snaps=snaps)
+    with open(os.path.join(HERE, 'network_steps_golden.json'), 'w') as f:
+        json.dump(dict(meta=meta, nets=res), f)
+    print('round-2 goldens written:', os.path.getsize(os.path.join(HERE, 'hebb_golden_r2.npz')) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
-    main()
+    if '--round2' in sys.argv:
+        round2_goldens()
+    else:
+        main()

@@ -37,22 +37,15 @@ def relerr(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def check_winners(win_gpu, y_ref, tol_abs):
-    """Winner indices must equal the reference's argmax bit for bit wherever the reference's own
-    top-2 margin is resolvable (margin > tol_abs, a few times the forward rounding error; the
-    reference's CPU and GPU builds disagree below that too).  Returns the number of pixels
-    that differ inside the unresolvable band."""
+def check_winners(win_gpu, y_ref, tol_abs=None):
+    """Winner indices must equal the reference's argmax (first maximum) bit for bit on EVERY pixel: the forward
+    epilogue lists the pixels whose top-2 margin is within its rounding error and the library re-evaluates those
+    exactly (csrc/fixup.cu).  Returns the number of differing pixels (asserted to be 0 by the callers); tol_abs is
+    kept in the signature for the report only."""
     y_ref = torch.as_tensor(y_ref)
     want = y_ref.argmax(dim=1)
-    top2 = y_ref.topk(2, dim=1).values
-    margin = top2[:, 0] - top2[:, 1]
     got = win_gpu.cpu().long()
-    bad = (got != want)
-    assert not bool((bad & (margin > tol_abs)).any()), 'winner differs where the margin is resolvable'
-    if bool(bad.any()):            # a mismatch must pick the runner-up, never an arbitrary channel
-        second = y_ref.topk(2, dim=1).indices[:, 1]
-        assert bool((got[bad] == second[bad]).all())
-    return int(bad.sum())
+    return int((got != want).sum())
 
 
 def make_layer(m, golden, name, prec):
@@ -81,7 +74,7 @@ def test_conv_vs_reference_golden(golden, name, prec):
     record('conv_vs_reference_golden', f'{name}/{prec}', y=relerr(y, golden[name + '/y']),
            dw=relerr(layer.delta_w, golden[name + '/dw1']), winner_mismatch=nbad, k=m['k'])
     assert relerr(y, golden[name + '/y']) < TOL_Y[prec]
-    assert nbad <= 2
+    assert nbad == 0
     assert relerr(layer.delta_w, golden[name + '/dw1']) < TOL_DW[prec]
     layer(x * 0.5)                                    # accumulates
     assert relerr(layer.delta_w, golden[name + '/dw2']) < TOL_DW[prec]
@@ -106,7 +99,7 @@ def test_convT_vs_reference_golden(golden, name, prec):
     x = torch.from_numpy(golden[name + '/x']).to(DEV)
     y = layer(x)
     assert relerr(y, golden[name + '/y']) < TOL_Y[prec]
-    assert check_winners(layer.winners, golden[name + '/y'], 2e-5 * float(np.abs(golden[name + '/y']).max())) <= 2
+    assert check_winners(layer.winners, golden[name + '/y']) == 0
     assert relerr(layer.delta_w, golden[name + '/dw1']) < TOL_DW[prec]
     layer.local_update()
     assert relerr(layer.weight.grad, golden[name + '/grad']) < TOL_DW[prec]
@@ -202,16 +195,17 @@ def test_tensor_core_shapes_vs_oracle(case, prec):
     layer.record_winners = True
     layer = layer.to(DEV).train()
     y = layer(x.to(DEV))
-    # fp32 / bf16x3 forward error is ~4e-6 relative: exact above a 2e-5 margin, and at most a
-    # handful of near-ties (out of up to 131072 pixels) may resolve the other way
+    # the forward error is ~4e-6 relative; near-ties below that are listed by the epilogue and resolved exactly
     nbad = check_winners(layer.winners, y_ref, 2e-5 * float(y_ref.abs().max()))
     record('tensor_core_shapes_vs_oracle', f'{name}/{prec}', y=relerr(y, y_ref), dw=relerr(layer.delta_w, dw_ref),
            winner_mismatch=nbad, pixels=int(y_ref.numel() // Cout), k=kinv)
     assert relerr(y, y_ref) < TOL_Y[prec]
-    assert nbad <= 4
-    # r = softmax(k*y) amplifies the forward rounding by k: allow 2e-4 on the one adversarial case
-    # (64 pixels x 512 channels, K = 6912, k = 50); everything else sits below 1e-4
-    tol = TOL_DW[prec] * (2.0 if name == 'c3d_256_512' else 1.0)
+    assert nbad == 0
+    # One stated exception to the 1e-4 bound: c3d_256_512 (64 pixels x 512 channels, K = 6912, k = 50).  The split
+    # operands carry 16 mantissa bits, so y is exact to ~1e-5 relative; r = softmax(k*y) amplifies that by k = 50 and
+    # with only 64 pixels nothing averages out: measured 1.2e-4 (the reference's own fp32-vs-fp64 noise on this case is
+    # 1.7e-6, i.e. this IS our rounding, bounded here at 2e-4; every layer of the BASELINE workloads has >= 1440 pixels)
+    tol = TOL_DW[prec] * (2.0 if (name == 'c3d_256_512' and prec != 'bf16') else 1.0)
     assert relerr(layer.delta_w, dw_ref) < tol, (name, prec)
 
 
@@ -237,7 +231,7 @@ def test_transposed_3d_tensor_core_vs_oracle(shape, prec):
     record('transposed_3d_vs_oracle', f'{Cin}x{Cout}/{prec}', y=relerr(y, y_ref), dw=relerr(layer.delta_w, dw_ref),
            winner_mismatch=nbad, k=50.)
     assert relerr(y, y_ref) < TOL_Y[prec]
-    assert nbad <= 4
+    assert nbad == 0
     assert relerr(layer.delta_w, dw_ref) < TOL_DW[prec]
 
 
@@ -689,3 +683,214 @@ def test_hpca_transposed_vs_reference_golden(golden, name):
     y = layer(torch.from_numpy(golden[name + '/x']).to(DEV))
     assert relerr(y, golden[name + '/y']) < 1e-5
     assert relerr(layer.delta_w, golden[name + '/dw1']) < 1e-4
+
+
+# ---- round 2: tensor-core-shaped 100-step drift, non-Identity act, network training loop, NCCL exchange ----
+G2 = np.load(os.path.join(ROOT, 'tests', 'golden', 'hebb_golden_r2.npz'))
+STEPS = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'network_steps_golden.json')))
+
+
+def sampled_relerr(w, idx, ref_samples):
+    got = w.detach().reshape(-1).double().cpu()[torch.from_numpy(idx)]
+    ref = torch.from_numpy(ref_samples).double()
+    return float((got - ref).norm() / ref.norm())
+
+
+@pytest.mark.parametrize('prec', PRECS)
+@pytest.mark.parametrize('opt_name', ['sgd', 'adam'])
+@pytest.mark.parametrize('nd', [2, 3])
+def test_hundred_step_drift_tensor_core_layer(nd, opt_name, prec):
+    """W after 1 and after 100 optimiser steps of a Cin = Cout = 64 layer (3x3 / 3x3x3, k = 50, lr 1e-3) against the
+    reference run: 1e-4 in fp32 / bf16x3, 1e-2 in bf16 (north-star tolerances)."""
+    xs = torch.from_numpy(G2[f'drift64_{nd}d/xs']).to(DEV)
+    cls = hebb.HebbianConv2d if nd == 2 else hebb.HebbianConv3d
+    layer = cls(64, 64, 3, padding=1, bias=False, k=50., alpha=1.)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(G2[f'drift64_{nd}d/w0']))
+    layer.prec = prec
+    layer = layer.to(DEV).train()
+    if prec != 'fp32':
+        assert _native.uses_tensor_cores(layer._desc(xs[0].shape, True), _native.parse_prec(prec))
+    opt = torch.optim.SGD([layer.weight], lr=1e-3) if opt_name == 'sgd' else torch.optim.Adam([layer.weight], lr=1e-3)
+    idx = G2[f'drift64_{nd}d/idx']
+    w0 = layer.weight.detach().clone()
+    for step in range(100):
+        opt.zero_grad()
+        layer(xs[step % 4])
+        layer.local_update()
+        opt.step()
+        if step == 0:
+            e1 = sampled_relerr(layer.weight, idx, G2[f'drift64_{nd}d_{opt_name}/w1'])
+    e100 = sampled_relerr(layer.weight, idx, G2[f'drift64_{nd}d_{opt_name}/w100'])
+    ref_move = torch.from_numpy(G2[f'drift64_{nd}d_{opt_name}/w100']).double() - w0.reshape(-1).double().cpu()[torch.from_numpy(idx)]
+    got_move = (layer.weight.detach() - w0).reshape(-1).double().cpu()[torch.from_numpy(idx)]
+    record('hundred_step_drift_tc', f'{nd}d/{opt_name}/{prec}', w_after_1=e1, w_after_100=e100,
+           movement_after_100=float((got_move - ref_move).norm() / ref_move.norm()))
+    assert e1 < TOL_DW[prec] and e100 < TOL_DW[prec]
+
+
+@pytest.mark.parametrize('prec', ['bf16x3', 'bf16'])
+@pytest.mark.parametrize('name', ['act_relu_16_16', 'act_relu_32_64'])
+def test_nonidentity_act_vs_reference_golden(name, prec):
+    """A layer constructed with act=ReLU: the plasticity rule is applied to act(y) (hebb.py:80,87-90,107)."""
+    m = STEPS['meta'][name]
+    layer = hebb.HebbianConv2d(m['Cin'], m['Cout'], 3, padding=1, bias=True, w_nrm=True, act=torch.nn.ReLU(), mode='swta',
+                               k=m['k'], alpha=1.)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(G2[name + '/w']))
+        layer.bias.copy_(torch.from_numpy(G2[name + '/b']))
+    layer.prec = prec
+    layer = layer.to(DEV).train()
+    y = layer(torch.from_numpy(G2[name + '/x']).to(DEV))
+    record('nonidentity_act', f'{name}/{prec}', y=relerr(y, G2[name + '/y']), dw=relerr(layer.delta_w, G2[name + '/dw1']))
+    assert relerr(y, G2[name + '/y']) < TOL_Y[prec]
+    assert relerr(layer.delta_w, G2[name + '/dw1']) < TOL_DW[prec]
+    with pytest.raises(NotImplementedError):
+        t = hebb.HebbianConvTranspose2d(4, 4, 2, stride=2, act=torch.nn.ReLU(), alpha=1.).to(DEV).train()
+        t(torch.randn(1, 4, 4, 4, device=DEV))
+
+
+def _build_net(name, fuse=False):
+    if name.startswith('unet2d'):
+        net, excl = workloads.unet2d(3, 2), workloads.EXCLUDE_2D
+    else:
+        net, excl = workloads.UNet3D(1, 2, init_features=4), workloads.EXCLUDE_3D
+    with contextlib.redirect_stdout(io.StringIO()):
+        makehebbian(net, exclude=excl, hebb_params={'mode': 'swta_t', 'k': 50., 'w_nrm': True, 'alpha': 1.})
+    workloads.deterministic_state_(net)
+    workloads.disable_dropout_(net)
+    return net.to(DEV).train()
+
+
+@pytest.mark.parametrize('name', ['unet2d', 'unet3d_f4', 'unet2d_sgd'])
+def test_training_loop_vs_reference_after_1_and_n_steps(name):
+    """The reference training loop (pretrain_hebbian_unsup_2d.py:181-196) through HebbianStepper on the CUDA path:
+    every trainable tensor after 1 and after N optimiser steps against the reference run (Adam with the reference's
+    learning rates, or SGD whose weight movement is linear in the summed updates)."""
+    from helpers import digest_err
+    gold = STEPS['nets'][name]
+    net = _build_net(name)
+    gg = torch.Generator().manual_seed(78)
+    shape = gold['shape']
+    xs = [torch.randn(*shape, generator=gg) for _ in range(2)]
+    ms = [torch.randint(0, 2, (shape[0], *shape[2:]), generator=gg) for _ in range(2)]
+    opt = (torch.optim.Adam if gold['opt'] == 'adam' else torch.optim.SGD)(net.parameters(), lr=gold['lr'])
+    w0 = {n: p.detach().clone() for n, p in net.named_parameters() if p.requires_grad}
+    st = HebbianStepper(net, opt, workloads.dice_loss)
+    for step in range(gold['steps']):
+        out, loss = st.step(xs[step % 2].to(DEV), ms[step % 2].to(DEV))
+        if str(step + 1) not in gold['snaps']:
+            continue
+        snap = gold['snaps'][str(step + 1)]
+        assert abs(float(loss) - snap['loss']) < 2e-3 * max(1.0, abs(snap['loss']))
+        worst_w = worst_m = 0.0
+        for n, p in net.named_parameters():
+            if not p.requires_grad:
+                continue
+            worst_w = max(worst_w, digest_err(p, snap['W'][n]))
+            worst_m = max(worst_m, digest_err((p.detach() - w0[n]) / gold['lr'], snap['move'][n]))
+        record('training_loop_vs_reference', f'{name}/step{step + 1}', w=worst_w, movement=worst_m)
+        assert worst_w < 1e-4, (name, step, worst_w)               # W within 1e-4 (north-star)
+        if gold['opt'] == 'sgd':
+            # movement / lr = -(sum of the updates): deep layers inherit the upstream rounding through BatchNorm on a
+            # 2-sample batch (same bound as test_network_vs_reference_golden)
+            assert worst_m < 2e-2, (name, step, worst_m)
+
+
+def _nccl_rank(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(hebb.HebbianConv2d(16, 32, 3, padding=1, bias=False, k=20., alpha=1.),
+                                  torch.nn.ReLU(),
+                                  hebb.HebbianConv2d(32, 32, 3, padding=1, bias=True, k=20., alpha=0.5),
+                                  torch.nn.Conv2d(32, 2, 1)).to(dev).train()
+        crit = lambda o, t: ((o - t) ** 2).mean()
+        g = torch.Generator().manual_seed(5)
+        x, t = torch.randn(8, 16, 24, 24, generator=g).to(dev), torch.randn(8, 2, 24, 24, generator=g).to(dev)
+        ref_dw = ref_w = None
+        if rank == 0:
+            import copy
+            single = copy.deepcopy(net)
+            single[0](x)
+            ref_dw = single[0].delta_w.clone()
+            single[0].delta_w.zero_()
+            s1 = HebbianStepper(single, torch.optim.SGD(single.parameters(), lr=1e-2), crit, allreduce=False)
+            for _ in range(3):
+                s1.step(x, t)
+            ref_w = [p.detach().clone() for p in single.parameters()]
+        st = HebbianStepper(net, torch.optim.SGD(net.parameters(), lr=1e-2), crit)
+        h = x.shape[0] // world
+        net[0](x[rank * h:(rank + 1) * h])
+        st.exchange()
+        dw_sum = net[0].delta_w.clone()
+        st.flat.zero_()
+        for _ in range(3):
+            st.step(x[rank * h:(rank + 1) * h], t[rank * h:(rank + 1) * h])
+        mine = [p.detach().clone() for p in net.parameters()]
+        gathered = [[torch.zeros_like(p) for _ in range(world)] for p in mine]
+        for p, lst in zip(mine, gathered):
+            dist.all_gather(lst, p)
+        if rank == 0:
+            same = all(torch.equal(lst[0], l2) for lst in gathered for l2 in lst[1:])
+            e_dw = float((dw_sum - ref_dw).norm() / ref_dw.norm())
+            e_w = max(float((a - b).norm() / b.norm().clamp_min(1e-30)) for a, b in zip(mine, ref_w))
+            q.put((same, e_dw, e_w))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_data_parallel_step_nccl_two_gpus():
+    """CUDA / NCCL twin of the gloo test: delta_w(full batch) == all-reduced shards on the CUDA path, and after 3 steps
+    every parameter (incl. the back-prop head and a mixed alpha = 0.5 layer) is bit-identical on both ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_nccl_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    same, e_dw, e_w = q.get(timeout=5)
+    record('data_parallel_nccl', 'world2', dw_sum_vs_full=e_dw, w_vs_single=e_w, replicas_identical=int(same))
+    assert same
+    assert e_dw < 1e-4 and e_w < 1e-4
+
+
+def test_modules_follow_their_tensors_device_not_the_current_device():
+    """A layer on cuda:1 while cuda:0 is current must work like a torch module; single-GPU boxes check the
+    guard with the one device."""
+    idx = 1 if torch.cuda.device_count() > 1 else 0
+    dev = torch.device('cuda', idx)
+    layer = hebb.HebbianConv2d(16, 16, 3, padding=1, bias=False, k=5., alpha=1.).to(dev).train()
+    torch.cuda.set_device(0)
+    x = torch.randn(2, 16, 20, 20, device=dev)
+    y = layer(x)
+    layer.local_update()
+    assert y.device == dev and torch.isfinite(y).all() and float(layer.weight.grad.abs().max()) > 0
+
+
+def test_stepper_cuda_graph_replay_matches_eager():
+    """HebbianStepper(capture=True): the step replayed from a CUDA graph leaves the same weights as the eager step."""
+    import copy
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(hebb.HebbianConv2d(3, 64, 3, padding=1, bias=False, k=3., alpha=1.)).to(DEV).train()
+    net2 = copy.deepcopy(net)
+    xs = [torch.randn(8, 3, 32, 32, device=DEV) for _ in range(4)]
+    a = HebbianStepper(net, torch.optim.SGD(net.parameters(), lr=1e-3))
+    b = HebbianStepper(net2, torch.optim.SGD(net2.parameters(), lr=1e-3), capture=True)
+    # the capture warms up with two steps on its first input: give the eager twin the same history
+    a.step(xs[0]); a.step(xs[0])
+    for x in xs:
+        a.step(x)
+        b.step(x)
+    torch.cuda.synchronize()
+    assert relerr(net2[0].weight, net[0].weight) < 1e-6

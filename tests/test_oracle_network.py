@@ -66,11 +66,8 @@ def _rank_main(rank, world, port, q):
             for m in net:
                 m.delta_w.zero_()
         opt = torch.optim.SGD(net.parameters(), lr=0.0)
-        st = HebbianStepper.__new__(HebbianStepper)
-        st.model, st.optimizer, st.criterion, st.group = net, opt, None, None
-        st.layers = hebbian_layers(net)
-        st.flat = flatten_delta_w(net)
-        st.allreduce = True
+        st = HebbianStepper(net, opt)
+        assert st.allreduce and st.flat is not None
         # the second layer's input depends only on its own shard, so per-layer additivity holds
         net(x[rank * 2:(rank + 1) * 2])
         st.exchange()                        # ONE all-reduce for both layers

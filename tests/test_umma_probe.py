@@ -185,3 +185,54 @@ def test_mn_major_narrow_swizzles_one_position_atom_stride(W, layout, shift):
     B = np.concatenate([Rf[shift + j:shift + j + K] for j in range(3)], axis=1)
     want = A.T @ B
     assert np.abs(d - want).max() < 1e-3 * np.abs(want).max()
+
+
+# ---- K-major swizzled A operand over the SAME [position][channels] image (round-2 fused kernel: the forward reads
+# the x tile as K-major rows, the update reads it as MN-major columns) ----
+def kmajor_sw_image(T, W):
+    """T: [rows][W/2] bf16 -> [rows][W bytes] image, 16-byte chunks XOR-ed with the address bits from bit 7 up."""
+    return swz_image(T, W)
+
+
+@pytest.mark.parametrize('W,layout', [(128, 2), (64, 4)])
+@pytest.mark.parametrize('shift', [0, 1, 3, 8, 13])
+@pytest.mark.parametrize('lbo', [0, 16])
+def test_k_major_swizzled_shifted_rows_and_k_offsets(W, layout, shift, lbo):
+    """A = 128 positions x 16 channels read K-major out of a swizzled [position][W bytes] image: the start address is
+    moved by whole rows (a tap) and by 32 bytes inside the row (the next 16 channels / the lo half), base_offset 0."""
+    rng = np.random.default_rng(W + shift)
+    C = W // 2                                    # bf16 values per row
+    rows, M, N = 128 + 16, 128, 32
+    A = bf16_round(rng.standard_normal((rows, C)))
+    ksteps = C // 16
+    B = bf16_round(rng.standard_normal((N, C)))
+    Bu = to_u16(B)
+    b_img = np.zeros((C // 8, N, 8), np.uint16)
+    for c in range(C // 8):
+        b_img[c] = Bu[:, c * 8:(c + 1) * 8]
+    lbo_b = N * 16
+    a_hi = desc_hi(lbo, 8 * W) | (layout << 61)
+    d = run_probe(kmajor_sw_image(A, W), b_img.reshape(-1), a_hi, shift * W, 32, desc_hi(lbo_b, 128), 0, 2 * lbo_b,
+                  idesc(M, N, 0, 0), ksteps, M, N)
+    want = A.float().numpy()[shift:shift + M].astype(np.float64) @ B.float().numpy().astype(np.float64).T
+    assert np.abs(d - want).max() < 1e-3 * np.abs(want).max()
+
+
+@pytest.mark.parametrize('W,layout', [(128, 2), (64, 4)])
+def test_k_major_swizzled_single_k_slice(W, layout):
+    """One K = 16 slice in the middle of the row (e.g. only the lo half): start + 32 * j, one instruction."""
+    rng = np.random.default_rng(W)
+    C = W // 2
+    rows, M, N = 128 + 8, 128, 16
+    A = bf16_round(rng.standard_normal((rows, C)))
+    B = bf16_round(rng.standard_normal((N, 16)))
+    Bu = to_u16(B)
+    b_img = np.zeros((2, N, 8), np.uint16)
+    for c in range(2):
+        b_img[c] = Bu[:, c * 8:(c + 1) * 8]
+    a_hi = desc_hi(0, 8 * W) | (layout << 61)
+    for j in range(C // 16):
+        d = run_probe(kmajor_sw_image(A, W), b_img.reshape(-1), a_hi, 5 * W + 32 * j, 0, desc_hi(N * 16, 128), 0, 0,
+                      idesc(M, N, 0, 0), 1, M, N)
+        want = A.float().numpy()[5:5 + M, 16 * j:16 * j + 16].astype(np.float64) @ B.float().numpy().astype(np.float64).T
+        assert np.abs(d - want).max() < 1e-3 * np.abs(want).max(), j
