@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument('--no-fuse', action='store_true', help='keep stock BatchNorm/activation/Upsample modules (hebb.fused off)')
     ap.add_argument('--head-nchw', action='store_true', help='keep the stock back-prop head in NCHW (default: channels_last)')
     ap.add_argument('--cudnn-benchmark', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the companions of the default line (3-D workload, plain drop-in, GPU-eager reference, element-wise kernels)')
+    ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph (HebbianStepper(capture=True); single GPU)')
     return ap.parse_args()
 
 
@@ -218,8 +220,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------
 def profile_layers(model, x, flush):
-    """Per-layer, per-stage CUDA-event timings of the tensor-core path (pack / forward / dW), taken in
-    one extra forward pass by re-running each stage alone (HEBB_F_ONLY_*) on the layer's real input."""
+    """Per-layer CUDA-event timings in one extra forward pass on each layer's real input: layers on the fused
+    small-channel kernel are timed as a whole step (`fused_ms`), layers on the pack / forward / update kernels
+    stage by stage (HEBB_F_ONLY_* re-runs one stage alone)."""
     from hebb import _native
     rows = []
 
@@ -227,9 +230,10 @@ def profile_layers(model, x, flush):
         xin = inp[0].detach().contiguous()
         desc = mod._desc(xin.shape, True)
         prec = _native.parse_prec(mod.prec)
-        tc = _native.uses_tensor_cores(desc, prec)
+        base = _native.F_WNRM | _native.F_UPDATE
+        path = _native.layer_path(desc, prec, base)
         g = dict(kind=type(mod).__name__, Cin=mod.in_channels, Cout=mod.out_channels, k=list(mod.kernel_size),
-                 x=list(xin.shape), y=list(out.shape), tensor_cores=bool(tc))
+                 x=list(xin.shape), y=list(out.shape), tensor_cores=bool(path >= 1), path={0: 'simt', 1: 'tc', 2: 'fused'}[path])
         P = out.numel() // mod.out_channels
         K = mod.in_channels * int(torch.tensor(mod.kernel_size).prod())
         if mod._transposed:
@@ -242,8 +246,7 @@ def profile_layers(model, x, flush):
         w = mod._raw(mod.weight.detach())
         scratch_dw = torch.zeros_like(w)
         yb = torch.empty_like(out)
-        base = _native.F_WNRM | _native.F_UPDATE
-        stages = [('full', 0)] + ([('pack', _native.F_ONLY_PACK), ('fwd', _native.F_ONLY_FWD), ('dw', _native.F_ONLY_DW)] if tc else [])
+        stages = [('full', 0)] + ([('pack', _native.F_ONLY_PACK), ('fwd', _native.F_ONLY_FWD), ('dw', _native.F_ONLY_DW)] if path == 1 else [])
         for name, fl in stages:
             best = None
             for rep in range(3):
@@ -256,6 +259,8 @@ def profile_layers(model, x, flush):
                 t = e0.elapsed_time(e1)
                 best = t if best is None else min(best, t)
             g[name + '_ms'] = best
+        if path == 2:
+            g['fused_ms'] = g['full_ms']
         rows.append(g)
 
     hs = [m.register_forward_hook(hook) for m in model.modules() if hasattr(m, 'local_update')]
@@ -269,42 +274,77 @@ def profile_layers(model, x, flush):
     return rows
 
 
-def run_ours(args):
+def roofline_from_rows(rows, prec, pk):
+    """Roofline of the dominant kernel class + every class, from the per-layer stage timings."""
+    tc = [r for r in rows if r['path'] == 'tc']
+    fu = [r for r in rows if r['path'] == 'fused']
+    if not tc and not fu:
+        return None
+    tot = {s: sum(r[s + '_ms'] for r in tc) for s in ('pack', 'fwd', 'dw')} if tc else {}
+    if fu:
+        tot['fused'] = sum(r['fused_ms'] for r in fu)
+    fl_tc = sum(r['flops_one_contraction'] for r in tc)
+    fl_fu = sum(r['flops_one_contraction'] for r in fu)
+    by_tc = sum(r['bytes_min'] for r in tc)
+    by_fu = sum(r['bytes_min'] for r in fu)
+    per = {}
+    for k in ('fwd', 'dw'):
+        if tot.get(k):
+            a = fl_tc / (tot[k] / 1e3) / 1e12
+            per[{'fwd': 'fwd_swta_kernel', 'dw': 'dw_swta_kernel'}[k]] = dict(bound='tensor', achieved=a, peak=pk['tf'], unit='TFLOP/s', frac=a / pk['tf'],
+                                                                           ms=tot[k], launches_per_step=len(tc))
+    if tot.get('pack'):
+        by = sum(4.0 * torch.tensor(r['x']).prod().item() * 2.0 for r in tc)        # read fp32, write bf16 hi + lo
+        a = by / (tot['pack'] / 1e3) / 1e9
+        per['pack_x_kernel'] = dict(bound='hbm', achieved=a, peak=pk['hbm'], unit='GB/s', frac=a / pk['hbm'], ms=tot['pack'], launches_per_step=len(tc))
+    if tot.get('fused'):
+        a = by_fu / (tot['fused'] / 1e3) / 1e9
+        t = 2.0 * fl_fu / (tot['fused'] / 1e3) / 1e12
+        per['fused_small_kernel'] = dict(bound='hbm', achieved=a, peak=pk['hbm'], unit='GB/s', frac=a / pk['hbm'], ms=tot['fused'],
+                                         launches_per_step=len(fu), tensor_view=dict(achieved=t, unit='TFLOP/s', frac=t / pk['tf'],
+                                                                                       note='forward + update flops of these layers'),
+                                         note='algorithmic bytes (x once + y once + 3 x weights, SURVEY 8d) of the layers on the fused kernel / their '
+                                              'summed CUDA-event time (includes the weight-prep and finalize launches of the step)')
+    dom_stage = max(tot, key=tot.get)
+    dom = {'fwd': 'fwd_swta_kernel', 'dw': 'dw_swta_kernel', 'pack': 'pack_x_kernel', 'fused': 'fused_small_kernel'}[dom_stage]
+    roof = dict(per[dom])
+    roof['kernel'] = dom
+    roof['traffic'] = None
+    roof['traffic_note'] = 'DRAM bytes per launch are not measurable inside the run; the ncu capture of this command is profiles/r2_traffic_c2.json'
+    roof['peak_source'] = pk['source'] + (' bf16 burst' if roof['bound'] == 'tensor' else ' copy bandwidth')
+    roof['precision'] = prec
+    roof['stage_ms'] = tot
+    roof['per_kernel'] = per
+    if 'fwd_swta_kernel' in per or 'dw_swta_kernel' in per:
+        roof['per_stage'] = {k: dict(achieved=per[n]['achieved'], frac=per[n]['frac']) for k, n in (('fwd', 'fwd_swta_kernel'), ('dw', 'dw_swta_kernel')) if n in per}
+    t_all = sum(tot.values())
+    roof['hbm_view'] = dict(algorithmic_bytes=by_tc + by_fu, achieved=(by_tc + by_fu) / (t_all / 1e3) / 1e9, peak=pk['hbm'], unit='GB/s',
+                            frac=(by_tc + by_fu) / (t_all / 1e3) / 1e9 / pk['hbm'], stage_ms_total=t_all,
+                            note='all Hebbian layers of the step: algorithmic x + y + 3 x weight bytes / summed stage time')
+    return roof
+
+
+def measure(args, workload, prec, B, steps, warmup, dev, world, rank, fuse=True, head_nchw=False, e2e=True, profile=True,
+            capture=False, layers_out=''):
+    """Build the workload on `dev`, time `steps` steps (HBM-resident inputs, CUDA events per step, L2 flushed between
+    steps, max over ranks) and, optionally, the end-to-end loop (pinned host batch in, loss out) and the per-layer profile."""
     import torch.distributed as dist
     from hebb import _native
     from hebb.step import HebbianStepper
     import hebb
-    rank = int(os.environ.get('RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    local = int(os.environ.get('LOCAL_RANK', 0))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
-    hebb.set_precision(args.prec)
-    if args.aten_backward:
-        os.environ['HEBB_ATEN_BACKWARD'] = '1'
-    desc, dflt_b, cpu_b = WORKLOADS[args.workload]
-    B = args.batch or dflt_b
-    cpu_b = args.cpu_sample_batch or cpu_b
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = time_cpu_port(args.workload, cpu_b, 2 if args.workload != 'c4' else 1, 1 if args.workload != 'c4' else 0)
-
+    hebb.set_precision(prec)
+    desc = WORKLOADS[workload][0]
     torch.manual_seed(1234)
-    model, make_batch, crit = build_model(args.workload, True, dev, fuse=not args.no_fuse, head_wgrad=args.head_wgrad)
-    if args.cudnn_benchmark:
-        torch.backends.cudnn.benchmark = True
-    if (not args.head_nchw) and hasattr(model, 'out_conv'):
+    model, make_batch, crit = build_model(workload, True, dev, fuse=fuse, head_wgrad=args.head_wgrad)
+    if (not head_nchw) and hasattr(model, 'out_conv') and workload == 'c2':
         model.out_conv.to(memory_format=torch.channels_last)
         # hand the head its input already in channels_last: cuDNN would otherwise convert the NCHW activation once
         # in the forward and once more (from the saved NCHW tensor) for the weight gradient
         model.out_conv.register_forward_pre_hook(lambda mod, a: (a[0].contiguous(memory_format=torch.channels_last),))
-    lr = 1e-6 if args.workload != 'c4' else 1e-5
-    opt = torch.optim.Adam(model.parameters(), lr=lr)
-    stepper = HebbianStepper(model, opt, crit)
+    lr = 1e-6 if workload != 'c4' else 1e-5
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=lr, capturable=bool(capture)) if params else None
+    stepper = HebbianStepper(model, opt, crit, capture=capture)
     x_host, m_host = make_batch(B, 100 + rank, 'cpu')
     x_pin = x_host.pin_memory()
     m_pin = m_host.pin_memory() if m_host is not None else None
@@ -320,14 +360,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         stepper.step(x, m)
     sync_all()
 
-    # ---- value: inputs resident in HBM ----
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     n0 = _native.launch_count()
-    with ClockSampler(local) as clk:
+    with ClockSampler(dev.index or 0) as clk:
         sync_all()
         t_wall0 = time.perf_counter()
         for e0, e1 in evs:
@@ -343,62 +382,55 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
-    value = B * world * args.steps / (dev_ms / 1e3)
+    res = dict(workload=f'{workload}: {desc}', prec=prec, B=B, lr=lr, value=B * world * steps / (dev_ms / 1e3), ms_per_step=dev_ms / steps,
+               launches=int(launches), clocks=clk.summary(), wall_s=t_wall, steps=steps)
 
-    # ---- e2e: host (pinned) inputs in, loss out, every step ----
-    # The public-API loop a user writes: every step's batch is copied from pinned host memory (on a side
-    # stream, double-buffered so step i+1's copy overlaps step i's compute) and the loss is read back.
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(x, m), (torch.empty_like(x), torch.empty_like(m) if m is not None else None)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    if e2e:
+        # The public-API loop a user writes: every step's batch is copied from pinned host memory (on a side
+        # stream, double-buffered so step i+1's copy overlaps step i's compute) and the loss is read back.
+        copy_stream = torch.cuda.Stream(device=dev)
+        bufs = [(x, m), (torch.empty_like(x), torch.empty_like(m) if m is not None else None)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def prefetch(i):
-        xb, mb = bufs[i % 2]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[i % 2])          # the step that last read this buffer is done
-            xb.copy_(x_pin, non_blocking=True)
-            if mb is not None:
-                mb.copy_(m_pin, non_blocking=True)
-            ready[i % 2].record(copy_stream)
+        def prefetch(i):
+            xb, mb = bufs[i % 2]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[i % 2])          # the step that last read this buffer is done
+                xb.copy_(x_pin, non_blocking=True)
+                if mb is not None:
+                    mb.copy_(m_pin, non_blocking=True)
+                ready[i % 2].record(copy_stream)
 
-    sync_all()
-    cur = torch.cuda.current_stream(dev)
-    for ev in freed:
-        ev.record(cur)
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    last = 0.0
-    prefetch(0)
-    dbg = os.environ.get('HEBB_BENCH_E2E_DEBUG') == '1'
-    for i in range(args.steps):
-        t0 = time.perf_counter()
-        if i + 1 < args.steps:
-            prefetch(i + 1)
-        cur.wait_event(ready[i % 2])
-        xb, mb = bufs[i % 2]
-        t1 = time.perf_counter()
-        out, loss = stepper.step(xb, mb)
-        freed[i % 2].record(cur)
-        t2 = time.perf_counter()
-        last = float(loss.item()) if loss is not None else float(out.flatten()[0].item())
-        if dbg:
-            print(f'[e2e rank {rank}] step {i}: prefetch {1e3 * (t1 - t0):.2f} ms, launch {1e3 * (t2 - t1):.2f} ms, '
-                  f'sync {1e3 * (time.perf_counter() - t2):.2f} ms', file=sys.stderr, flush=True)
-    s1.record()
-    sync_all()
-    t = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = B * world * args.steps / (e2e_ms / 1e3)
-    h2d = x_pin.numel() * x_pin.element_size() + (m_pin.numel() * m_pin.element_size() if m_pin is not None else 0)
+        sync_all()
+        cur = torch.cuda.current_stream(dev)
+        for ev in freed:
+            ev.record(cur)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        last = 0.0
+        prefetch(0)
+        for i in range(steps):
+            if i + 1 < steps:
+                prefetch(i + 1)
+            cur.wait_event(ready[i % 2])
+            xb, mb = bufs[i % 2]
+            out, loss = stepper.step(xb, mb)
+            freed[i % 2].record(cur)
+            last = float(loss.item()) if loss is not None else float(out.flatten()[0].item())
+        s1.record()
+        sync_all()
+        t = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        h2d = x_pin.numel() * x_pin.element_size() + (m_pin.numel() * m_pin.element_size() if m_pin is not None else 0)
+        res['e2e'] = {'value': B * world * steps / (e2e_ms / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                      'ms_per_step': e2e_ms / steps, 'last_loss': last}
 
-    # ---- roofline of the dominant kernel class (per-layer stage timings) ----
-    roof, rows = None, []
-    pk = peaks()
-    if rank == 0 and not args.no_layer_profile:
-        if args.workload == 'c1':
+    res['roofline'] = None
+    if profile and rank == 0:
+        if workload == 'c1':
             class _W(torch.nn.Module):
                 def __init__(s, l):
                     super().__init__(); s.l = l
@@ -408,52 +440,165 @@ def run_ours(args):
             rows = profile_layers(_W(model), x, flush)
         else:
             rows = profile_layers(model, x, flush)
-        tc_rows = [r for r in rows if r['tensor_cores']]
-        tot = {s: sum(r[s + '_ms'] for r in tc_rows) for s in ('pack', 'fwd', 'dw')} if tc_rows else {}
-        if tot:
-            dom = max(tot, key=tot.get)
-            fl = sum(r['flops_one_contraction'] for r in tc_rows)
-            if dom in ('fwd', 'dw'):
-                ach = fl / (tot[dom] / 1e3) / 1e12
-                roof = dict(bound='tensor', kernel={'fwd': 'fwd_swta_kernel', 'dw': 'dw_swta_kernel'}[dom], achieved=ach,
-                            peak=pk['tf'], unit='TFLOP/s', frac=ach / pk['tf'], traffic=None,
-                            peak_source=pk['source'] + ' bf16 burst', launches_per_step=len(tc_rows),
-                            note=f'algorithmic 2*P*Cout*K flops of the {len(tc_rows)} tensor-core layers / summed CUDA-event time of that '
-                                 f'stage ({args.prec}: {"3 MMAs per product" if (args.prec == "bf16x3" or dom == "fwd") else "1 MMA per product"})',
-                            stage_ms=tot)
-                # both contractions against the tensor peak, and the whole Hebbian stage against HBM (the small-channel
-                # layers are bandwidth-bound: SURVEY.md 8d) -- algorithmic bytes = x once + y once + 3 x weights
-                roof['per_stage'] = {k: dict(achieved=fl / (tot[k] / 1e3) / 1e12, frac=fl / (tot[k] / 1e3) / 1e12 / pk['tf'])
-                                     for k in ('fwd', 'dw') if tot.get(k)}
-                by = sum(r['bytes_min'] for r in tc_rows)
-                t_all = sum(tot.values())
-                roof['hbm_view'] = dict(algorithmic_bytes=by, achieved=by / (t_all / 1e3) / 1e9, peak=pk['hbm'], unit='GB/s',
-                                        frac=by / (t_all / 1e3) / 1e9 / pk['hbm'], stage_ms_total=t_all)
-            else:
-                by = sum(4.0 * torch.tensor(r['x']).prod().item() * 1.5 for r in tc_rows)
-                ach = by / (tot[dom] / 1e3) / 1e9
-                roof = dict(bound='hbm', kernel='pack_x_kernel', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'],
-                            traffic=None, peak_source=pk['source'], stage_ms=tot)
-        if roof is not None:
-            # DRAM bytes of that kernel per step from the committed ncu capture of this command (profiles/)
-            tpath = os.path.join(ROOT, 'profiles', f'r1_traffic_{args.workload}.json')
-            if os.path.exists(tpath) and args.prec == 'bf16x3':
-                try:
-                    with open(tpath) as f:
-                        tr = json.load(f).get(roof['kernel'])
-                    if tr:
-                        roof['traffic'] = tr['dram_read_bytes_per_step'] + tr['dram_write_bytes_per_step']
-                        roof['traffic_note'] = 'dram__bytes_read+write of all launches of this kernel in one step (ncu, profiles/r1_traffic_%s.json)' % args.workload
-                except Exception:
-                    pass
-        if args.layers_out:
-            with open(args.layers_out, 'w') as f:
-                json.dump(dict(workload=args.workload, prec=args.prec, batch=B, layers=rows), f, indent=1)
+        res['roofline'] = roofline_from_rows(rows, prec, peaks())
+        if layers_out:
+            with open(layers_out, 'w') as f:
+                json.dump(dict(workload=workload, prec=prec, batch=B, layers=rows), f, indent=1)
+    del stepper, model, opt, x, m, flush_buf
+    _native.release_workspaces()
+    torch.cuda.empty_cache()
+    return res
+
+
+def time_gpu_eager(workload, B, dev, steps=2, warmup=1):
+    """The reference's own formulation on the GPU: the oracle port's modules (materialised unfold + matmul + softmax in
+    stock PyTorch ops, i.e. cuDNN / cuBLAS) run eagerly on the B200 -- SURVEY 8d's "bar on the box" -- with TF32 off and
+    on, at a reduced batch (the unfold of the widest layer needs ~0.6 GB per sample); reported per sample."""
+    out = {}
+    model, make_batch, crit = build_model(workload, False, dev)
+    lr = 1e-6 if workload != 'c4' else 1e-5
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    x, m = make_batch(B, 0, dev)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for name, tf32 in (('fp32', False), ('tf32', True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(warmup):
+                reference_step(model, opt, crit, x, m)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                reference_step(model, opt, crit, x, m)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = dict(value=B / (ms / 1e3), ms_per_step=ms)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out['unit'] = 'samples/s'
+    out['batch'] = B
+    out['kind'] = 'port (oracle modules on cuda: unfold + cuBLAS/cuDNN eager ops)'
+    del model, opt, x, m
+    torch.cuda.empty_cache()
+    return out
+
+
+def elementwise_gbs(dev, pk):
+    """Achieved HBM GB/s of the element-wise kernels of the path (north-star: "achieved HBM GB/s for the elementwise and
+    normalisation stages"): normalize() (hebb_wnorm), local_update() (hebb_local_update_multi) on a weight set shaped like
+    the 3-D network's (90 M weights, 361 MB) and on the 2-D network's (1.8 M)."""
+    from hebb import _native
+    res = {}
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for tag, shapes in (('c4_weights', [(1024, 1024, 27), (1024, 512, 27), (512, 512, 27), (512, 512, 27), (512, 256, 27), (256, 256, 27), (256, 256, 27)]),
+                        ('c2_weights', [(256, 256, 9), (256, 128, 9), (128, 256, 9), (128, 128, 9), (128, 128, 9), (64, 128, 9), (64, 64, 9)])):
+        ws = [torch.randn(s, device=dev) for s in shapes]
+        n = sum(w.numel() for w in ws)
+        # normalize(): read W, write W/|W| (8 B per weight)
+        best = None
+        for rep in range(3):
+            flush_buf.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for w in ws:
+                _native.wnorm(w, w.shape[0], w[0].numel(), 1, 0, w[0].numel())
+            e1.record(); e1.synchronize()
+            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        a = 8.0 * n / (best / 1e3) / 1e9
+        res[f'wnorm_kernel/{tag}'] = dict(achieved=a, unit='GB/s', frac=a / pk['hbm'], ms=best, bytes=8.0 * n)
+        # local_update(): read grad and delta_w, write grad and zero delta_w (16 B per weight; 12 B when grad is not read)
+        grads = [torch.randn_like(w) for w in ws]
+        dws = [torch.randn_like(w) for w in ws]
+        best = None
+        for rep in range(3):
+            flush_buf.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _native.local_update_multi(grads, dws, [1.0] * len(ws), [False] * len(ws))
+            e1.record(); e1.synchronize()
+            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        a = 12.0 * n / (best / 1e3) / 1e9
+        res[f'local_update_kernel/{tag}'] = dict(achieved=a, unit='GB/s', frac=a / pk['hbm'], ms=best, bytes=12.0 * n)
+    res['peak'] = pk['hbm']
+    res['peak_source'] = pk['source'] + ' copy bandwidth'
+    return res
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    if args.aten_backward:
+        os.environ['HEBB_ATEN_BACKWARD'] = '1'
+    if args.cudnn_benchmark:
+        torch.backends.cudnn.benchmark = True
+    desc, dflt_b, cpu_b = WORKLOADS[args.workload]
+    B = args.batch or dflt_b
+    cpu_b = args.cpu_sample_batch or cpu_b
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = time_cpu_port(args.workload, cpu_b, 2 if args.workload != 'c4' else 1, 1 if args.workload != 'c4' else 0)
+
+    main = measure(args, args.workload, args.prec, B, args.steps, args.warmup, dev, world, rank, fuse=not args.no_fuse,
+                   head_nchw=args.head_nchw, e2e=True, profile=not args.no_layer_profile, capture=args.graph, layers_out=args.layers_out)
+
+    # ---- companions of the headline (single GPU, default workload only): the 3-D half of BASELINE's metric, the plain
+    # drop-in number, the reference formulation on this GPU, the element-wise kernels ----
+    extras = {}
+    if world == 1 and rank == 0 and args.workload == 'c2' and not args.no_extras:
+        pk = peaks()
+        try:
+            plain = measure(args, 'c2', args.prec, B, 3, 3, dev, world, rank, fuse=False, head_nchw=True, e2e=False, profile=False)
+            extras['value_plain_dropin'] = dict(value=plain['value'], ms_per_step=plain['ms_per_step'], unit='samples/s',
+                                                note='same step with the stock module tree: no hebb.fused pass, back-prop head in NCHW (bench.py --no-fuse --head-nchw)')
+        except Exception as e:          # an extra must never take the headline down
+            extras['value_plain_dropin'] = dict(error=str(e)[:200])
+        c4 = {}
+        for prec in ('bf16x3', 'bf16'):
+            try:
+                r = measure(args, 'c4', prec, WORKLOADS['c4'][1], 3, 3, dev, world, rank, e2e=True, profile=True,
+                            layers_out=(args.layers_out.replace('.json', f'_c4_{prec}.json') if args.layers_out else ''))
+                roof = r['roofline'] or {}
+                c4[prec] = dict(value=r['value'], unit='samples/s', ms_per_step=r['ms_per_step'], e2e=r.get('e2e'), clocks=r['clocks'],
+                                gpu_launches=r['launches'], steps=r['steps'],
+                                roofline=dict(per_stage=roof.get('per_stage'), per_kernel={k: dict(achieved=v['achieved'], unit=v['unit'], frac=v['frac'], ms=v['ms'])
+                                                                                             for k, v in (roof.get('per_kernel') or {}).items()},
+                                              peak=pk['tf'], peak_source=pk['source'] + ' bf16 burst',
+                                              note='dw = the update contraction of all 22 layers: algorithmic 2*P*Cout*K flops / summed CUDA-event time '
+                                                   f'({"3-4 MMAs per product (split operands)" if prec == "bf16x3" else "1 MMA per product"})'))
+            except Exception as e:
+                c4[prec] = dict(error=str(e)[:200])
+        c4['config'] = {'workload': 'c4: ' + WORKLOADS['c4'][0], 'per_gpu_batch': WORKLOADS['c4'][1], 'optimizer': 'adam lr=1e-05'}
+        extras['c4'] = c4
+        try:
+            eager = {'c2': time_gpu_eager('c2', 8, dev), 'c4': time_gpu_eager('c4', 1, dev, steps=1, warmup=1)}
+            eager['c2']['ours_over_eager_fp32'] = main['value'] / eager['c2']['fp32']['value']
+            eager['c2']['ours_over_eager_tf32'] = main['value'] / eager['c2']['tf32']['value']
+            if 'value' in c4.get('bf16x3', {}):
+                eager['c4']['ours_over_eager_fp32'] = c4['bf16x3']['value'] / eager['c4']['fp32']['value']
+                eager['c4']['ours_over_eager_tf32'] = c4['bf16x3']['value'] / eager['c4']['tf32']['value']
+            extras['gpu_eager_baseline'] = eager
+        except Exception as e:
+            extras['gpu_eager_baseline'] = dict(error=str(e)[:200])
+        try:
+            extras['elementwise'] = elementwise_gbs(dev, pk)
+        except Exception as e:
+            extras['elementwise'] = dict(error=str(e)[:200])
 
     if rank == 0:
+        lr = main['lr']
         line = {
-            'metric': 'hebbian_pretrain_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+            'metric': 'hebbian_pretrain_samples_per_sec', 'value': main['value'], 'unit': 'samples/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': main['ms_per_step'], 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16x3': 'bf16x3 (fp32-equivalent split)', 'bf16': 'bf16'}[args.prec],
             'data': 'synthetic',
             'config': {'workload': f'{args.workload}: {desc}', 'per_gpu_batch': B, 'global_batch': B * world,
@@ -464,16 +609,17 @@ def run_ours(args):
                        'head_weight_gradient': ('hebb_conv_wgrad (bf16x3) for <= %d filters' % args.head_wgrad) if ((not args.no_fuse) and args.head_wgrad and args.workload != 'c1') else 'cuDNN',
                        'backward': 'stock ATen' if args.aten_backward else 'native dgrad/wgrad on the tcgen05 kernels where the planner takes the layer',
                        'backprop_head_memory_format': 'nchw' if (args.head_nchw or args.workload != 'c2') else 'channels_last (input converted once, by a forward pre-hook)', 'l2': 'flushed between timed steps (256 MB fill)',
-                       'parallelism': f'dp{world} (batch shards, one all-reduce of delta_w per step)'},
-            'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                    'ms_per_step': e2e_ms / args.steps, 'last_loss': last},
-            'gpu_launches': int(launches),
-            'clocks': clk.summary(),
-            'wall_s_timed_region': t_wall,
-            'roofline': roof,
+                       'cuda_graph': bool(args.graph),
+                       'parallelism': f'dp{world} (batch shards; delta_w summed by one all-reduce issued after the forward, back-prop gradients of the head averaged by a second one)'},
+            'e2e': main.get('e2e'),
+            'gpu_launches': main['launches'],
+            'clocks': main['clocks'],
+            'wall_s_timed_region': main['wall_s'],
+            'roofline': main['roofline'],
             'cpu_baseline': (dict(value=cpu['value'], unit='samples/s', cores=cpu['cores'], kind='port', sample=cpu['sample'],
                                   ms_per_step=cpu['ms_per_step']) if cpu else None),
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

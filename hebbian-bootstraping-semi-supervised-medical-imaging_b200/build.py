@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = ['api.cu', 'elementwise.cu', 'simt_path.cu', 'tc_path.cu', 'fixup.cu', 'norm_act.cu']
+SRC = ['api.cu', 'elementwise.cu', 'simt_path.cu', 'tc_path.cu', 'fused_path.cu', 'fixup.cu', 'norm_act.cu']
 OUT = os.path.join(HERE, 'hebb', 'libhebb_sm100.so')
 OBJ = os.path.join(HERE, 'build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')

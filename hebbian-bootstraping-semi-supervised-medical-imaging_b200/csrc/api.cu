@@ -28,6 +28,27 @@ static int current_slot() {
   return dev;
 }
 
+// Watchdog word: every tcgen05 kernel writes the code of a timed-out mbarrier wait here before it traps (umma.cuh:
+// mbar_wait).  The word lives in pinned, mapped host memory so that the host can still read it after the trap has
+// taken the CUDA context down; hebb_watchdog_code() returns it and the Python binding reports HEBB_EKERNEL.
+static int* g_wd_host = nullptr;
+static int* g_wd_dev = nullptr;
+int* watchdog_word() {
+  if (g_wd_dev) return g_wd_dev;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_wd_dev) return g_wd_dev;
+  int* h = nullptr;
+  if (cudaHostAlloc(reinterpret_cast<void**>(&h), 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  h[0] = 0;
+  int* d = nullptr;
+  if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  g_wd_host = h; g_wd_dev = d;
+  return d;
+}
+
 int device_ok() { const int s = current_slot(); return (s >= 0 && g_dev_state[s] == 1) ? HEBB_OK : HEBB_EARCH; }
 int num_sms() { const int s = current_slot(); return s >= 0 ? g_dev_sms[s] : 148; }
 
@@ -96,6 +117,8 @@ const char* hebb_status_str(int s) {
 
 int hebb_last_cuda_error(void) { return g_last_cuda_error; }
 
+int hebb_watchdog_code(void) { return g_wd_host ? *reinterpret_cast<volatile int*>(g_wd_host) : 0; }
+
 unsigned long long hebb_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* hebb_version(void) { return "hebb_sm100 0.1 (sm_100a; fp32 CUDA-core + tcgen05 bf16/bf16x3)"; }
@@ -119,14 +142,29 @@ int hebb_workspace_bytes(const HebbDesc* d, int prec, size_t* bytes) {
   if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
   // the CUDA-core scratch is also what the HPCA rule uses, whatever the precision mode
   const size_t a = use_tc(g, prec) ? tc_workspace_bytes(g, prec) : 0, b = simt_workspace_bytes(g);
-  *bytes = a > b ? a : b;
+  const size_t c = (prec != HEBB_PREC_FP32 && fused_supported(g, prec, 0)) ? fused_workspace_bytes(g) : 0;
+  *bytes = a > b ? (a > c ? a : c) : (b > c ? b : c);
   return HEBB_OK;
 }
 
 int hebb_uses_tensor_cores(const HebbDesc* d, int prec) {
   Geo g;
   if (resolve_geo(d, &g) != HEBB_OK) return 0;
+  if (prec != HEBB_PREC_FP32 && !g.transposed && fused_supported(g, prec, 0)) return 1;
   return use_tc(g, prec) ? 1 : 0;
+}
+
+int hebb_layer_path(const HebbDesc* d, int prec, unsigned flags) {
+  Geo g;
+  if (resolve_geo(d, &g) != HEBB_OK) return -1;
+  if (prec != HEBB_PREC_FP32 && !g.transposed && fused_supported(g, prec, flags & 0xFFFFu)) return 2;
+  return use_tc(g, prec) ? 1 : 0;
+}
+
+int hebb_debug_fused_plan(const HebbDesc* d, int* out, int n) {
+  Geo g;
+  if (resolve_geo(d, &g) != HEBB_OK || !out) return 0;
+  return fused_describe_plan(g, out, n);
 }
 
 int hebb_debug_plan(const HebbDesc* d, int prec, int* out, int n) {
@@ -157,6 +195,8 @@ int hebb_conv_swta_step(const HebbDesc* d, const float* x, const float* W, const
   if (!aligned16(ws)) return HEBB_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   flags &= 0xFFFFu;                       // bits above are library-internal
+  if (prec != HEBB_PREC_FP32 && fused_supported(g, prec, flags))     // small-channel 2-D layers: one fused kernel
+    return fused_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, st);
   if (use_tc(g, prec)) {      // HPCA layers the planner cannot give a Gram plan fall through to the fp32 kernels
     const int s = tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, st);
     if (!(s == HEBB_ESHAPE && (flags & HEBB_F_RULE_HPCA))) return s;
@@ -178,6 +218,9 @@ int hebb_conv_swta_step_stats(const HebbDesc* d, const float* x, const float* W,
   if ((flags & HEBB_F_UPDATE) && !delta_w) return HEBB_EARG;
   if (prec < HEBB_PREC_FP32 || prec > HEBB_PREC_BF16) return HEBB_EARG;
   if (!aligned16(ws)) return HEBB_EALIGN;
+  if (fused_supported(g, prec, flags))
+    return fused_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, (cudaStream_t)stream, y_stats,
+                           y_stats_written);
   return tc_conv_step(g, x, W, bias, kinv, y, winner, delta_w, ws, ws_bytes, flags, prec, (cudaStream_t)stream, 0,
                       y_stats, y_stats_written);
 }

@@ -50,6 +50,7 @@ struct Geo {
 int resolve_geo(const HebbDesc* d, Geo* g);
 int device_ok();          // HEBB_OK iff current device is sm_100
 int num_sms();
+int* watchdog_word();   // device pointer of the pinned watchdog word (nullptr if it could not be allocated)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
@@ -88,8 +89,19 @@ int launch_winner_fixup(const Geo& g, const float* x, const float* W, const floa
 bool tc_supported(const Geo& g, int prec);
 size_t tc_workspace_bytes(const Geo& g, int prec);
 int tc_describe_plan(const Geo& g, int prec, int* out, int n);
+int tc_launch_pack_w(const float* W, void* wp, int Cin, int Cout, int taps, int NSLAB, int CT, cudaStream_t st);
+int tc_launch_finalize(const float* hpart, const float* rsum, const float* W, float* dw, int n_part, int taps, int Cin,
+                       int CinP, int Cout, cudaStream_t st);
 int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y,
                  int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
                  cudaStream_t st, int aux = 0, double* ystats = nullptr, int* ystats_written = nullptr);
+
+// ---- fused forward + update kernel of the small-channel 2-D layers (fused_path.cu) ----
+bool fused_supported(const Geo& g, int prec, unsigned flags);
+size_t fused_workspace_bytes(const Geo& g);
+int fused_describe_plan(const Geo& g, int* out, int n);
+int fused_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y, int32_t* winner,
+                    float* delta_w, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st, double* ystats = nullptr,
+                    int* ystats_written = nullptr);
 
 }  // namespace hebb

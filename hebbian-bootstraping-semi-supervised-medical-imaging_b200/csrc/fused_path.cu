@@ -1,0 +1,659 @@
+// Fused forward + plasticity-update kernel for the small-channel 2-D layers (Cin, Cout in {16, 32}; 1x1 or 3x3,
+// stride 1) -- hebb/hebb.py:87-115 as ONE kernel (SURVEY.md 8b `hebb_fwd_dw_fused`).
+//
+// These layers are HBM-bound (48 % of the 2-D network's flops, 82 % of its bytes).  The
+// two-kernel path moves every activation five times (pack: read fp32 + write bf16 hi/lo; forward: read packed x,
+// write y and the packed responses; update: read packed x and r).  Here x is read ONCE as fp32 NCHW by TMA tensor-map
+// loads (out-of-bounds zero fill materialises the zero halo of hebb.py:83-85), converted to bf16 hi/lo in shared
+// memory, y is written once, and the responses r = softmax_c(k y) never leave the SM.
+//
+//   persistent CTA (one per SM), work item = (image b, TH x TW output tile); per CTA:
+//   warp 0      TMA producer: per padded tile row and 16-channel group one 3-D box  [16 ch][1 row][pitch] fp32
+//   warps 2-5   converter: fp32 [ch][pos] staging -> x image [pos][hi Cin | lo Cin] bf16, 16-byte chunks XOR-swizzled
+//               on absolute address bits (SWIZZLE_64B for Cin = 16, SWIZZLE_128B for Cin = 32)
+//   warp 1      tcgen05.mma issuer, per 128-position block:
+//                 forward  D[pos, co] += x[pos + tap][ci] W[tap][ci][co]: A = the x image read K-major (a tap is a
+//                          start-address offset of whole rows, hi/lo halves are 32-byte offsets), B = packed weights;
+//                          3 products (hi*lo, hi*hi, lo*hi) per tap and 16-channel slab into one fp32 accumulator
+//                 update   H[(kh, hl, ci), (kw, hl', co)] += x[q + kh*pitch] r[q - kw]: the SAME x image read MN-major
+//                          with an atom stride of one tile row (M = 128 rows = kh copies x [hi; lo] x Cin), the response
+//                          image read with an atom stride of ONE position (N = kW copies x [hi | lo] x Cout): ONE
+//                          instruction per 16 positions covers all taps and all four hi/lo products
+//                          (tests/test_umma_probe.py pins these descriptor forms on hardware)
+//   warps 6-13  epilogue (two sets alternate blocks): TMEM -> y = acc/|w| + b -> global; winner (+ near-tie list);
+//               BatchNorm sums; r = softmax -> bf16 hi/lo -> response image in shared memory; running sums of r
+//   The update accumulators stay in TMEM for the whole kernel; each CTA writes ONE partial [taps][Cin][Cout] (x2 for the
+//   hi/lo rows of x), summed in a fixed order by tc_finalize_kernel together with the decay term -(sum_p r) W.
+#include "common.cuh"
+#include "umma.cuh"
+#include <cuda.h>
+#include <cstdlib>
+
+namespace hebb {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kSmemLimitF = 227 * 1024;
+constexpr int kRLead = 8;                 // zero / carried-over positions in front of every response slot
+constexpr int kRSlotPos = kRLead + 128;
+constexpr int kMaxRows = 18;              // x tile rows (TH + kH - 1) a CTA keeps barriers for
+constexpr int kThreadsF = 448;
+
+struct FusedParams {
+  float* y; int32_t* winner; const float* inv; const float* bias; float* rsum; double* ystats; float* hpart; int* err;
+  int* fix_list; int* fix_count; int fix_cap; float tie_rel;
+  const uint4* wp;
+  int B, oH, oW, kH, kW, pH, pW, taps;
+  int TH, TW, pitch, nTH, nTW, ntiles, XROWS, NBLK, XPOS, NST;
+  int BW, padl;                // TMA box width (floats) and left pad of the box start: staging column = tile column + padl - pW
+  float kinv; int update;
+  uint32_t off_r, off_stage, off_w, off_misc, w_bytes, stage_bytes, tmem_cols;
+};
+
+__device__ __forceinline__ void flag_tie_f(int* list, int* count, int cap, long long pid) {
+  const int i = atomicAdd(count, 1);       // near-tie worklist, see fixup.cu
+  if (i < cap) list[i] = (int)pid;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// tcgen05.mma with a run-time accumulate flag (the update accumulators are overwritten exactly once per kernel)
+__device__ __forceinline__ void umma_rt(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
+}
+
+// byte address of 16-byte chunk `c` of the position whose (unswizzled) row starts at `row_addr`; NCH chunks per row.
+// The hardware XORs address bits [4, 4+log2 NCH) with the bits from 7 up (Swizzle<b,4,3> on absolute addresses).
+template <int NCH>
+__device__ __forceinline__ uint32_t swz(uint32_t row_addr, int c) {
+  return row_addr + ((((uint32_t)c) ^ ((row_addr >> 7) & (NCH - 1))) << 4);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kThreadsF, 1)
+fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
+  constexpr int XB = CIN * 4;              // bytes per position of the x image: [hi Cin | lo Cin] bf16
+  constexpr int RB = COUT * 4;             // ... of the response image
+  constexpr int XCH = XB / 16, RCH = RB / 16;
+  constexpr uint32_t XLAY = (XB == 128) ? 2u : 4u, RLAY = (RB == 128) ? 2u : 4u;     // SWIZZLE_128B : SWIZZLE_64B
+  constexpr int NSL = CIN / 16;            // 16-channel slabs (K steps of the forward)
+  constexpr int COPIES = 128 / (2 * CIN);  // kh copies of the x tile in the M = 128 rows of an update instruction
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  float* s_inv = reinterpret_cast<float*>(smem + p.off_misc);
+  float* s_bias = s_inv + COUT;
+  float* s_rs = s_bias + COUT;               // [8 warps][COUT]
+  float* s_ys = s_rs + 8 * COUT;
+  float* s_yq = s_ys + COUT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_yq + COUT);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t st_full = bar0, st_empty = st_full + 8 * 8;
+  const uint32_t xr_full = st_empty + 8 * 8, xr_empty = xr_full + 8 * kMaxRows;
+  const uint32_t tf_full = xr_empty + 8 * kMaxRows, tf_empty = tf_full + 16;
+  const uint32_t r_full = tf_empty + 16, w_full = r_full + 24, done = w_full + 8;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16 + 2 * kMaxRows + 2 + 2 + 3 + 2);
+
+  const int NACC = (p.kH + COPIES - 1) / COPIES;          // update accumulators actually used (at most 2)
+  // accumulator 1 re-reads the last COPIES kernel rows (kh = kH-COPIES ..), so that no copy reaches past kh = kH-1
+  const int kh_base1 = p.kH - COPIES;
+  const int NW = p.kW * 2 * COUT;                          // columns of one update accumulator
+  const uint32_t xb = sbase;
+  const uint32_t rb = sbase + p.off_r;
+
+  // ---- one-time set-up: constants, zero fill of what the tensor pipe may read before anyone wrote it ----
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+    s_inv[i] = p.inv ? p.inv[i] : 1.f;
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 10 * COUT; i += blockDim.x) s_rs[i] = 0.f;     // rs, ys, yq
+  {
+    // x image beyond the converted rows (read by the wasted kh copies / the last block) and the response ring
+    const uint32_t x_tail = (uint32_t)p.XROWS * p.pitch * XB, x_end = (uint32_t)p.XPOS * XB;
+    for (uint32_t a = x_tail + threadIdx.x * 16; a < x_end; a += blockDim.x * 16) st_shared_v4(xb + a, 0, 0, 0, 0);
+    const uint32_t r_end = 3u * kRSlotPos * RB;
+    for (uint32_t a = threadIdx.x * 16; a < r_end; a += blockDim.x * 16) st_shared_v4(rb + a, 0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, 4); }
+    for (int i = 0; i < kMaxRows; ++i) { mbar_init(xr_full + 8 * i, 4 * NSL); mbar_init(xr_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tf_full + 8 * i, 1); mbar_init(tf_empty + 8 * i, 4); }
+    for (int i = 0; i < 3; ++i) mbar_init(r_full + 8 * i, 4);
+    mbar_init(w_full, 1); mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(s_tmem), p.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_f = tmem_base;                      // 2 forward accumulators of COUT columns
+  const uint32_t tmem_d = tmem_base + 2 * COUT;           // NACC update accumulators of NW columns
+  const int per_img = p.nTH * p.nTW;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(w_full, p.w_bytes);
+      bulk_g2s(sbase + p.off_w, p.wp, p.w_bytes, w_full);
+      int s = 0; uint32_t ph = 0;
+      const uint32_t row_bytes = (uint32_t)p.BW * 16 * 4;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int b = tile / per_img, rem = tile - b * per_img;
+        const int th = rem / p.nTW, tw = rem - th * p.nTW;
+        const int h0 = th * p.TH - p.pH, w0 = tw * p.TW - p.padl;      // box start: a multiple of 4 floats (16 bytes)
+        for (int r = 0; r < p.XROWS; ++r)
+          for (int cg = 0; cg < NSL; ++cg) {
+            mbar_wait(st_empty + 8 * s, ph ^ 1, p.err, 21);
+            mbar_expect_tx(st_full + 8 * s, row_bytes);
+            tma_load_3d(sbase + p.off_stage + s * p.stage_bytes, &tmap, w0, h0 + r, b * CIN + cg * 16, st_full + 8 * s);
+            if (++s == p.NST) { s = 0; ph ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_f = idesc_bf16(128, COUT, 0, 0);
+    const uint32_t idesc_d = idesc_bf16(128, NW, 1, 1);
+    // forward A: K-major swizzled rows of XB bytes, 8-row groups 8*XB apart (LBO unused: K = 32 bytes < row)
+    const uint32_t fa_hi = ((8u * XB) >> 4) | (1u << 14) | (XLAY << 29);
+    // forward B: SWIZZLE_NONE K-major packed weights [k-chunk][hi|lo][COUT rows][16 B]
+    const uint32_t fb_hi = (128u >> 4) | (1u << 14);
+    const uint32_t fb_lbo = ((2u * COUT * 16u) >> 4) << 16;
+    // update A: MN-major swizzled, atoms (kh copies) one tile row apart, 8-position groups 8*XB apart
+    const uint32_t da_hi = ((8u * XB) >> 4) | (1u << 14) | (XLAY << 29);
+    const uint32_t da_lbo = (((uint32_t)p.pitch * XB) >> 4) << 16;
+    // update B: MN-major swizzled response image, atoms (kw copies) ONE position apart
+    const uint32_t db_hi = ((8u * RB) >> 4) | (1u << 14) | (RLAY << 29);
+    const uint32_t db_lbo = ((uint32_t)RB >> 4) << 16;
+    const uint32_t wb = sbase + p.off_w;
+    mbar_wait(w_full, 0, p.err, 20);
+    uint32_t kk = 0;               // blocks issued by this CTA so far
+    uint32_t d_acc = 0;            // 0 until the update accumulators hold something
+    int it = 0;
+    // update MMAs of block j of the current tile (kkj = its running index), then release the x rows it was last to read
+    auto dw_block = [&](int j, uint32_t kkj, int& rows_freed, bool last) {
+      const uint32_t slot = kkj % 3u;
+      mbar_wait(r_full + 8 * slot, (kkj / 3u) & 1u, p.err, 24);
+      tc_fence_after();
+      int free_to = last ? p.XROWS : (int)(((j + 1) * 128) / p.pitch);
+      if (free_to > p.XROWS) free_to = p.XROWS;
+      if (elect_one()) {
+        uint32_t a = da_lbo | (((xb + (uint32_t)(j * 128) * XB) >> 4) & 0x3FFFu);
+        uint32_t b = db_lbo | (((rb + slot * (kRSlotPos * RB) + (uint32_t)(kRLead - (p.kW - 1)) * RB) >> 4) & 0x3FFFu);
+        const uint32_t a2 = (uint32_t)(kh_base1 * p.pitch * XB) >> 4;    // second accumulator: kh copies kH-COPIES ..
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks, a += XB, b += RB) {              // 16 positions per instruction
+          umma_rt(tmem_d, a, da_hi, b, db_hi, idesc_d, d_acc);
+          if (NACC > 1) umma_rt(tmem_d + NW, a + a2, da_hi, b, db_hi, idesc_d, d_acc);
+          d_acc = 1u;
+        }
+        for (int r = rows_freed; r < free_to; ++r) umma_commit(xr_empty + 8 * r);
+      }
+      __syncwarp();
+      d_acc = 1u;
+      rows_freed = free_to > rows_freed ? free_to : rows_freed;
+    };
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      int rows_ready = 0, rows_freed = 0;
+      for (int k = 0; k < p.NBLK; ++k, ++kk) {
+        int need = ((k + 1) * 128 - 1 + (p.kH - 1) * p.pitch + (p.kW - 1)) / p.pitch + 1;
+        if (need > p.XROWS) need = p.XROWS;
+        for (; rows_ready < need; ++rows_ready) mbar_wait(xr_full + 8 * rows_ready, it & 1, p.err, 22);
+        const uint32_t acc = kk & 1u;
+        mbar_wait(tf_empty + 8 * acc, ((kk >> 1) & 1u) ^ 1u, p.err, 23);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d = tmem_f + acc * COUT;
+          bool first = true;
+          for (int kh = 0; kh < p.kH; ++kh)
+            for (int kw = 0; kw < p.kW; ++kw) {
+              const int tap = kh * p.kW + kw;
+              const uint32_t qa = xb + (uint32_t)(k * 128 + kh * p.pitch + kw) * XB;
+#pragma unroll
+              for (int s = 0; s < NSL; ++s) {
+                const uint32_t ah = ((qa + 32u * s) >> 4) & 0x3FFFu, al = ((qa + 2u * CIN + 32u * s) >> 4) & 0x3FFFu;
+                const uint32_t wa = wb + (uint32_t)((s * p.taps + tap) * 4 * COUT) * 16u;
+                const uint32_t bh = fb_lbo | ((wa >> 4) & 0x3FFFu), bl = fb_lbo | (((wa + COUT * 16u) >> 4) & 0x3FFFu);
+                if (first) umma_lo<1, 0>(d, ah, fa_hi, bl, fb_hi, idesc_f);
+                else umma_lo<1, 1>(d, ah, fa_hi, bl, fb_hi, idesc_f);
+                umma_lo<3, 1>(d, ah, fa_hi, bh, fb_hi, idesc_f);
+                umma_lo<0, 1>(d, al, fa_hi, bh, fb_hi, idesc_f);
+                first = false;
+              }
+            }
+          umma_commit(tf_full + 8 * acc);
+        }
+        __syncwarp();
+        if (p.update) {
+          if (k > 0) dw_block(k - 1, kk - 1, rows_freed, false);
+        } else {
+          // forward only: rows are free once the blocks that read them have been issued
+          int free_to = (k == p.NBLK - 1) ? p.XROWS : (int)(((k + 1) * 128) / p.pitch);
+          if (free_to > p.XROWS) free_to = p.XROWS;
+          if (elect_one())
+            for (int r = rows_freed; r < free_to; ++r) umma_commit(xr_empty + 8 * r);
+          __syncwarp();
+          rows_freed = free_to > rows_freed ? free_to : rows_freed;
+        }
+      }
+      if (p.update) dw_block(p.NBLK - 1, kk - 1, rows_freed, true);
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  } else if (warp < 6) {
+    // ===================== converter (warps 2..5) =====================
+    const int t = threadIdx.x - 64;
+    int s = 0; uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      for (int r = 0; r < p.XROWS; ++r)
+        for (int cg = 0; cg < NSL; ++cg) {
+          mbar_wait(st_full + 8 * s, ph, p.err, 25);
+          if (cg == 0) mbar_wait(xr_empty + 8 * r, (it & 1) ^ 1, p.err, 26);      // the previous tile no longer reads this row
+          const float* st = reinterpret_cast<const float*>(smem + p.off_stage + s * p.stage_bytes) + (p.padl - p.pW);
+          for (int c = t; c < p.pitch; c += 128) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = st[i * p.BW + c];
+            uint32_t hp[8], lp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+              const float h0 = __uint_as_float(hp[i] << 16), h1 = __uint_as_float(hp[i] & 0xffff0000u);
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp[i]) : "f"(v[2 * i + 1] - h1), "f"(v[2 * i] - h0));
+            }
+            const uint32_t row = xb + (uint32_t)(r * p.pitch + c) * XB;
+            st_shared_v4(swz<XCH>(row, 2 * cg), hp[0], hp[1], hp[2], hp[3]);
+            st_shared_v4(swz<XCH>(row, 2 * cg + 1), hp[4], hp[5], hp[6], hp[7]);
+            st_shared_v4(swz<XCH>(row, XCH / 2 + 2 * cg), lp[0], lp[1], lp[2], lp[3]);
+            st_shared_v4(swz<XCH>(row, XCH / 2 + 2 * cg + 1), lp[4], lp[5], lp[6], lp[7]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(xr_full + 8 * r); mbar_arrive(st_empty + 8 * s); }
+          if (++s == p.NST) { s = 0; ph ^= 1; }
+        }
+    }
+  } else {
+    // ===================== epilogue warps 6..13: two sets of four alternate blocks =====================
+    const int quad = warp & 3;
+    const int ew = warp - 6;
+    const int eset = ew >> 2;
+    float* my_rs = s_rs + ew * COUT;
+    const long long outS = (long long)p.oH * p.oW;
+    float racc[COUT], ysacc[COUT], yqacc[COUT];
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) { racc[i] = 0.f; ysacc[i] = 0.f; yqacc[i] = 0.f; }
+    const bool want_ys = p.ystats != nullptr;
+    const float k2 = p.kinv * 1.4426950408889634f;      // exp(k y) = 2^(k2 y)
+    uint32_t kk = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int b = tile / per_img, rem = tile - b * per_img;
+      const int th = rem / p.nTW, tw = rem - th * p.nTW;
+      const int h0 = th * p.TH, w0 = tw * p.TW;
+      const int THv = min(p.TH, p.oH - h0), TWv = min(p.TW, p.oW - w0);
+      for (int k = 0; k < p.NBLK; ++k, ++kk) {
+        if ((int)(kk & 1u) != eset) continue;
+        const uint32_t acc = kk & 1u;
+        mbar_wait(tf_full + 8 * acc, (kk >> 1) & 1u, p.err, 27);
+        tc_fence_after();
+        uint32_t v[COUT];
+        TmemLd<COUT>::ld(tmem_f + (static_cast<uint32_t>(quad * 32) << 16) + acc * COUT, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tf_empty + 8 * acc);        // the accumulator is in registers: hand the buffer back
+        const int loc = quad * 32 + lane;
+        const int q = k * 128 + loc;
+        const int r_ = q / p.pitch, c_ = q - r_ * p.pitch;
+        const bool valid = r_ < THv && c_ < TWv;
+        float f[COUT];
+#pragma unroll
+        for (int i = 0; i < COUT; ++i) f[i] = fmaf(__uint_as_float(v[i]), s_inv[i], s_bias[i]);
+        const long long pix = (long long)(h0 + r_) * p.oW + (w0 + c_);
+        float* yb = p.y + (long long)b * COUT * outS + pix;
+        float best = -INFINITY;
+        int bi = 0;
+#pragma unroll
+        for (int i = 0; i < COUT; ++i) {
+          if (valid) yb[(long long)i * outS] = f[i];
+          if (f[i] > best) { best = f[i]; bi = i; }            // strict: the lowest index wins ties
+        }
+        if (want_ys) {
+#pragma unroll
+          for (int i = 0; i < COUT; ++i) { const float tt = valid ? f[i] : 0.f; ysacc[i] += tt; yqacc[i] = fmaf(tt, tt, yqacc[i]); }
+        }
+        if (p.winner && valid) {
+          p.winner[(long long)b * outS + pix] = bi;
+          float second = -INFINITY, amax = 0.f;
+#pragma unroll
+          for (int i = 0; i < COUT; ++i) { second = fmaxf(second, i == bi ? -INFINITY : f[i]); amax = fmaxf(amax, fabsf(f[i])); }
+          if (best - second <= p.tie_rel * amax) flag_tie_f(p.fix_list, p.fix_count, p.fix_cap, (long long)b * outS + pix);
+        }
+        if (!p.update) continue;
+        // ---- responses: r = softmax_c(k y), bf16 hi/lo, into this block's slot of the response ring ----
+        float mx2 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < COUT; ++i) { f[i] *= k2; mx2 = fmaxf(mx2, f[i]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < COUT; ++i) {
+          float e;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(f[i] - mx2));
+          f[i] = e; sum += e;
+        }
+        const float rinv = valid ? (1.f / sum) : 0.f;
+        const uint32_t slot = kk % 3u, nslot = (kk + 1u) % 3u;
+        const uint32_t row = rb + slot * (kRSlotPos * RB) + (uint32_t)(kRLead + loc) * RB;
+        // the last kW-1 positions of a block are also the lead of the next block's slot (zeros at a tile's end)
+        const bool carry = loc >= 128 - kRLead;
+        const uint32_t lrow = rb + nslot * (kRSlotPos * RB) + (uint32_t)(loc - (128 - kRLead)) * RB;
+        const bool tile_end = (k == p.NBLK - 1);
+#pragma unroll
+        for (int g8 = 0; g8 < COUT / 8; ++g8) {
+          uint32_t oh4[4], ol4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = g8 * 8 + i * 2;
+            const float r0 = f[c] * rinv, r1 = f[c + 1] * rinv;
+            uint32_t hp, lp;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(r1), "f"(r0));
+            const float hh0 = __uint_as_float(hp << 16), hh1 = __uint_as_float(hp & 0xffff0000u);
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(r1 - hh1), "f"(r0 - hh0));
+            oh4[i] = hp; ol4[i] = lp;
+            racc[c] += hh0 + __uint_as_float(lp << 16);
+            racc[c + 1] += hh1 + __uint_as_float(lp & 0xffff0000u);
+          }
+          st_shared_v4(swz<RCH>(row, g8), oh4[0], oh4[1], oh4[2], oh4[3]);
+          st_shared_v4(swz<RCH>(row, RCH / 2 + g8), ol4[0], ol4[1], ol4[2], ol4[3]);
+          if (carry) {
+            if (tile_end) { oh4[0] = oh4[1] = oh4[2] = oh4[3] = 0u; ol4[0] = ol4[1] = ol4[2] = ol4[3] = 0u; }
+            st_shared_v4(swz<RCH>(lrow, g8), oh4[0], oh4[1], oh4[2], oh4[3]);
+            st_shared_v4(swz<RCH>(lrow, RCH / 2 + g8), ol4[0], ol4[1], ol4[2], ol4[3]);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(r_full + 8 * slot);
+      }
+    }
+    // ---- fold the per-thread running sums ----
+    __syncwarp();
+    if (p.update) {
+      constexpr int CHF = COUT >= 32 ? 32 : 16;
+#pragma unroll
+      for (int ck = 0; ck < COUT / CHF; ++ck) {
+        float tt[CHF];
+#pragma unroll
+        for (int i = 0; i < CHF; ++i) tt[i] = racc[ck * CHF + i];
+        const float cs = lane_col_sum<CHF>(tt, lane);
+        if (lane < CHF) my_rs[ck * CHF + lane] = cs;
+      }
+      __syncwarp();
+      for (int c = lane; c < COUT; c += 32) atomicAdd(p.rsum + c, my_rs[c]);
+    }
+    if (want_ys) {
+      constexpr int CHF = COUT >= 32 ? 32 : 16;
+#pragma unroll
+      for (int ck = 0; ck < COUT / CHF; ++ck) {
+        float t1[CHF], t2[CHF];
+#pragma unroll
+        for (int i = 0; i < CHF; ++i) { t1[i] = ysacc[ck * CHF + i]; t2[i] = yqacc[ck * CHF + i]; }
+        const float a1 = lane_col_sum<CHF>(t1, lane), a2 = lane_col_sum<CHF>(t2, lane);
+        if (lane < CHF) { atomicAdd(s_ys + ck * CHF + lane, a1); atomicAdd(s_yq + ck * CHF + lane, a2); }
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");        // the 8 epilogue warps
+      for (int c = (int)threadIdx.x - 192; c < COUT; c += 256) {
+        atomicAdd(p.ystats + 2 * c, (double)s_ys[c]);
+        atomicAdd(p.ystats + 2 * c + 1, (double)s_yq[c]);
+      }
+    }
+    // ---- the update accumulators: one partial per CTA and hi/lo half of x; set s drains accumulator s ----
+    if (p.update) {
+      mbar_wait(done, 0, p.err, 28);
+      tc_fence_after();
+      const bool have = (int)blockIdx.x < p.ntiles;
+      if (eset < NACC) {
+        const int rowi = quad * 32 + lane;
+        const int jj = rowi / (2 * CIN), rr = rowi - jj * (2 * CIN);
+        const int hl = rr / CIN, ci = rr - hl * CIN;
+        const int kh = eset == 0 ? jj : kh_base1 + jj;
+        const bool mine = kh < p.kH && (eset == 0 || kh >= COPIES);      // accumulator 1 repeats rows accumulator 0 owns
+        const uint32_t ta = tmem_d + (static_cast<uint32_t>(quad * 32) << 16) + eset * NW;
+        for (int i = 0; i < p.kW; ++i) {
+          const int tap = kh * p.kW + (p.kW - 1 - i);          // column copy i holds r shifted by +i positions: kw = kW-1-i
+          float* dst = p.hpart + ((((long long)blockIdx.x * 2 + hl) * p.taps + tap) * CIN + ci) * COUT;
+#pragma unroll
+          for (int c0 = 0; c0 < COUT; c0 += 16) {
+            uint32_t vh[16], vl[16];
+            tmem_ld16(ta + i * 2 * COUT + c0, vh);
+            tmem_ld16(ta + i * 2 * COUT + COUT + c0, vl);
+            tmem_ld_wait();
+            if (mine) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float4 o;
+                o.x = have ? __uint_as_float(vh[4 * u + 0]) + __uint_as_float(vl[4 * u + 0]) : 0.f;
+                o.y = have ? __uint_as_float(vh[4 * u + 1]) + __uint_as_float(vl[4 * u + 1]) : 0.f;
+                o.z = have ? __uint_as_float(vh[4 * u + 2]) + __uint_as_float(vl[4 * u + 2]) : 0.f;
+                o.w = have ? __uint_as_float(vh[4 * u + 3]) + __uint_as_float(vl[4 * u + 3]) : 0.f;
+                *reinterpret_cast<float4*>(dst + c0 + 4 * u) = o;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct FPlan {
+  int TH, TW, pitch, nTH, nTW, ntiles, XROWS, NBLK, XPOS, NST, grid, BW, padl;
+  uint32_t off_r, off_stage, off_w, off_misc, w_bytes, stage_bytes, smem, tmem_cols;
+  size_t o_inv, o_rsum, o_err, o_wp, o_hpart, o_fix, total;
+  int fix_cap;
+};
+
+bool fused_plan(const Geo& g, FPlan* P) {
+  if (g.nd != 2 || g.transposed || g.kD != 1 || g.sH != 1 || g.sW != 1) return false;
+  if (!((g.Cin == 16 || g.Cin == 32) && (g.Cout == 16 || g.Cout == 32))) return false;
+  if (g.kH > 3 || g.kW > 3 || g.iW % 4 != 0) return false;
+  static const int want = [] { const char* e = getenv("HEBB_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (!want) return false;
+  FPlan& q = *P;
+  const int sms = num_sms();
+  const int XB = g.Cin * 4, RB = g.Cout * 4;
+  q.nTW = (int)cdiv(g.oW, 128);
+  q.TW = (int)(cdiv(cdiv(g.oW, q.nTW), 4) * 4);          // tile columns start on multiples of 4 floats
+  q.nTW = (int)cdiv(g.oW, q.TW);
+  q.pitch = (int)((q.TW + g.kW - 1 + 3) / 4 * 4);
+  // The TMA box starts padl = round_up(pW, 4) columns left of the tile, so that its first byte is 16-byte aligned in
+  // global memory (HEBB_FUSED_ALIGN=0: start exactly pW columns left; profiling / debugging aid)
+  static const int want_align = [] { const char* e = getenv("HEBB_FUSED_ALIGN"); return (e && e[0] == '0') ? 0 : 1; }();
+  q.padl = want_align ? (g.pW + 3) / 4 * 4 : g.pW;
+  q.BW = (q.pitch + (q.padl - g.pW) + 3) / 4 * 4;
+  if (q.BW > 256) return false;
+  q.NST = 4;
+  q.stage_bytes = (uint32_t)align_up((size_t)q.BW * 16 * 4, 128);
+  q.w_bytes = (uint32_t)((g.Cin / 16) * g.taps * 4 * g.Cout * 16);
+  const uint32_t misc = (uint32_t)(12 * g.Cout * 4 + 8 * (16 + 2 * kMaxRows + 2 + 2 + 3 + 2) + 64);
+  const uint32_t r_bytes = 3u * kRSlotPos * RB;
+  bool found = false;
+  const long long tiles_w = (long long)g.B * q.nTW;
+  for (int th = 16; th >= 1 && !found; --th) {
+    if (th + g.kH - 1 > kMaxRows) continue;
+    if (th > g.oH && th > 1) continue;
+    // enough tiles to balance the persistent CTAs (unless the layer is too small anyway)
+    const long long tiles = tiles_w * cdiv(g.oH, th);
+    if (th > 1 && tiles < 4LL * sms && tiles_w * g.oH >= 4LL * sms) continue;
+    const int nblk = (int)cdiv((long long)th * q.pitch, 128);
+    // the kh copies of an update instruction reach (copies-1) rows (accumulator 0) resp. kH-1 rows (accumulator 1) past a block
+    const int copies = 128 / (2 * g.Cin);
+    const int reach = (copies - 1) > (g.kH - 1) ? (copies - 1) : (g.kH - 1);
+    const int xpos = nblk * 128 + reach * q.pitch + 8;
+    const uint32_t x_bytes = (uint32_t)align_up((size_t)xpos * XB, 1024);
+    const uint32_t tot = x_bytes + (uint32_t)align_up(r_bytes, 1024) + q.NST * q.stage_bytes + (uint32_t)align_up(q.w_bytes, 128) + misc + 1024;
+    if (tot > (uint32_t)kSmemLimitF) continue;
+    q.TH = th; q.NBLK = nblk; q.XPOS = xpos; q.XROWS = th + g.kH - 1;
+    q.off_r = x_bytes;
+    q.off_stage = q.off_r + (uint32_t)align_up(r_bytes, 1024);
+    q.off_w = q.off_stage + q.NST * q.stage_bytes;
+    q.off_misc = q.off_w + (uint32_t)align_up(q.w_bytes, 128);
+    q.smem = tot;
+    found = true;
+  }
+  if (!found) return false;
+  q.nTH = (int)cdiv(g.oH, q.TH);
+  q.ntiles = g.B * q.nTH * q.nTW;
+  q.grid = q.ntiles < sms ? q.ntiles : sms;
+  const int copies = 128 / (2 * g.Cin);
+  const int nacc = (g.kH + copies - 1) / copies;
+  const int cols = 2 * g.Cout + nacc * g.kW * 2 * g.Cout;
+  uint32_t tc = 32; while ((int)tc < cols) tc <<= 1;
+  if (tc > 512) return false;
+  q.tmem_cols = tc;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  q.o_inv = take(sizeof(float) * g.Cout);
+  q.o_rsum = take(sizeof(float) * g.Cout);
+  q.o_err = take(256);
+  q.o_wp = take(q.w_bytes);
+  q.o_hpart = take((size_t)q.grid * 2 * g.taps * g.Cin * g.Cout * sizeof(float));
+  const long long px = (long long)g.B * g.outS;
+  q.fix_cap = (int)(px < (1LL << 18) ? px : (1LL << 18));
+  q.o_fix = take(sizeof(int) * (size_t)q.fix_cap);
+  q.total = off;
+  return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+}  // namespace
+
+bool fused_supported(const Geo& g, int prec, unsigned flags) {
+  if (prec != HEBB_PREC_BF16X3 && prec != HEBB_PREC_BF16) return false;
+  if (flags & (HEBB_F_RULE_HPCA | HEBB_F_WGRAD_INTERNAL | HEBB_F_ONLY_PACK | HEBB_F_ONLY_FWD | HEBB_F_ONLY_DW)) return false;
+  FPlan P;
+  return fused_plan(g, &P) && encode_fn() != nullptr;
+}
+
+size_t fused_workspace_bytes(const Geo& g) {
+  FPlan P;
+  return fused_plan(g, &P) ? P.total : 0;
+}
+
+int fused_describe_plan(const Geo& g, int* out, int n) {
+  FPlan P;
+  if (!fused_plan(g, &P)) return 0;
+  const int v[] = {P.TH, P.TW, P.pitch, P.ntiles, P.NBLK, P.XROWS, (int)P.smem, (int)P.tmem_cols, P.grid};
+  const int m = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < n && i < m; ++i) out[i] = v[i];
+  return m;
+}
+
+int fused_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y, int32_t* winner,
+                    float* delta_w, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st, double* ystats,
+                    int* ystats_written) {
+  if (ystats_written) *ystats_written = 0;
+  FPlan P;
+  if (!fused_plan(g, &P)) return HEBB_ESHAPE;
+  if (!ws || ws_bytes < P.total) return HEBB_EWS;
+  if (reinterpret_cast<uintptr_t>(x) & 15) return HEBB_EALIGN;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return HEBB_ECUDA;
+  char* base = static_cast<char*>(ws);
+  float* inv = reinterpret_cast<float*>(base + P.o_inv);
+  float* rsum = reinterpret_cast<float*>(base + P.o_rsum);
+  int* err = reinterpret_cast<int*>(base + P.o_err);
+  const bool upd = (flags & HEBB_F_UPDATE) != 0;
+  HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, P.o_wp - P.o_rsum, st));      // rsum, error word, near-tie counter
+  if (flags & HEBB_F_WNRM) HEBB_TRY(launch_wnorm(W, nullptr, inv, g.Cout, g.K, 1, 0, g.K, st));
+  HEBB_TRY(tc_launch_pack_w(W, base + P.o_wp, g.Cin, g.Cout, g.taps, g.Cin / 16, g.Cout, st));
+
+  CUtensorMap tm;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.iW, (cuuint64_t)g.iH, (cuuint64_t)g.B * g.Cin};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.iW * 4, (cuuint64_t)g.iW * g.iH * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)P.BW, 1u, 16u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return HEBB_ESHAPE;
+
+  FusedParams f;
+  f.y = y; f.winner = winner; f.inv = (flags & HEBB_F_WNRM) ? inv : nullptr; f.bias = bias; f.rsum = rsum;
+  f.ystats = ystats; f.hpart = reinterpret_cast<float*>(base + P.o_hpart);
+  f.err = watchdog_word() ? watchdog_word() : err;
+  static const float tie_rel = [] { const char* e = getenv("HEBB_TIE_REL"); return e ? (float)atof(e) : 2.5e-4f; }();
+  f.fix_list = reinterpret_cast<int*>(base + P.o_fix); f.fix_count = err + 4; f.fix_cap = P.fix_cap; f.tie_rel = tie_rel;
+  f.wp = reinterpret_cast<const uint4*>(base + P.o_wp);
+  f.B = g.B; f.oH = g.oH; f.oW = g.oW; f.kH = g.kH; f.kW = g.kW; f.pH = g.pH; f.pW = g.pW; f.taps = g.taps;
+  f.TH = P.TH; f.TW = P.TW; f.pitch = P.pitch; f.nTH = P.nTH; f.nTW = P.nTW; f.ntiles = P.ntiles; f.XROWS = P.XROWS;
+  f.NBLK = P.NBLK; f.XPOS = P.XPOS; f.NST = P.NST; f.BW = P.BW; f.padl = P.padl;
+  f.kinv = kinv; f.update = upd ? 1 : 0;
+  f.off_r = P.off_r; f.off_stage = P.off_stage; f.off_w = P.off_w; f.off_misc = P.off_misc; f.w_bytes = P.w_bytes;
+  f.stage_bytes = P.stage_bytes; f.tmem_cols = P.tmem_cols;
+  if (ystats) {
+    HEBB_CUDA_TRY(cudaMemsetAsync(ystats, 0, sizeof(double) * 2 * (size_t)g.Cout, st));
+    if (ystats_written) *ystats_written = 1;
+  }
+#define HEBB_FUSED_LAUNCH(CI, CO)                                                                                         \
+  do {                                                                                                                    \
+    HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
+    fused_small_kernel<CI, CO><<<P.grid, kThreadsF, kSmemLimitF, st>>>(tm, f);                                            \
+  } while (0)
+  if (g.Cin == 16 && g.Cout == 16) HEBB_FUSED_LAUNCH(16, 16);
+  else if (g.Cin == 16 && g.Cout == 32) HEBB_FUSED_LAUNCH(16, 32);
+  else if (g.Cin == 32 && g.Cout == 16) HEBB_FUSED_LAUNCH(32, 16);
+  else HEBB_FUSED_LAUNCH(32, 32);
+#undef HEBB_FUSED_LAUNCH
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  if (winner && tie_rel > 0.f)
+    HEBB_TRY(launch_winner_fixup(g, x, W, (flags & HEBB_F_WNRM) ? inv : nullptr, bias, winner, f.fix_list, f.fix_count, P.fix_cap, st));
+  if (upd)
+    HEBB_TRY(tc_launch_finalize(f.hpart, rsum, W, delta_w, P.grid * 2, g.taps, g.Cin, g.Cin, g.Cout, st));
+  return HEBB_OK;
+}
+
+}  // namespace hebb

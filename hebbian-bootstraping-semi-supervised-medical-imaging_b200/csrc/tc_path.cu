@@ -364,30 +364,6 @@ struct FwdParams {
   uint32_t tmem_cols;
 };
 
-template <int CH>
-__device__ __forceinline__ float lane_col_sum(float (&v)[CH], int lane) {
-  // returns in lane l the sum over the 32 lanes of v[l % CH]
-  if (CH == 16) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
-  }
-#pragma unroll
-  for (int off = CH / 2; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = upper ? v[i] : v[i + off];
-      const float keep = upper ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
-template <int CH> struct TmemLd;
-template <> struct TmemLd<32> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[32]) { tmem_ld32(a, v); } };
-template <> struct TmemLd<16> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) { tmem_ld16(a, v); } };
-
 // Loads CH accumulator columns; with the stacked forward the x*w_lo partial lives `second` columns further on.
 template <int CH>
 __device__ __forceinline__ void ld_acc(uint32_t a, int second, uint32_t (&v)[CH]) {
@@ -2199,6 +2175,25 @@ static int launch_dw(const Plan& P, const Geo& g, const uint4* xp0, const uint4*
   return HEBB_OK;
 }
 
+// Launch wrappers for the fused small-channel path (fused_path.cu), which shares the weight packing and the
+// deterministic finalize pass with the kernels above.
+int tc_launch_pack_w(const float* W, void* wp, int Cin, int Cout, int taps, int NSLAB, int CT, cudaStream_t st) {
+  const long long n = (long long)NSLAB * taps * 2 * 2 * Cout;
+  pack_w_kernel<<<ew_grid(n), 256, 0, st>>>(W, reinterpret_cast<uint4*>(wp), Cin, Cout, taps, NSLAB, 2, CT, 0, 0, nullptr);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
+int tc_launch_finalize(const float* hpart, const float* rsum, const float* W, float* dw, int n_part, int taps, int Cin,
+                       int CinP, int Cout, cudaStream_t st) {
+  long long gx = cdiv((long long)taps * Cin * Cout, 32);
+  const long long cap = (long long)num_sms() * 32;
+  if (gx > cap) gx = cap;
+  tc_finalize_kernel<<<(unsigned)gx, 256, 0, st>>>(hpart, rsum, W, dw, n_part, taps, Cin, CinP, Cout);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
 int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bias, float kinv, float* y,
                  int32_t* winner, float* delta_w, void* ws, size_t ws_bytes, unsigned flags, int prec,
                  cudaStream_t st, int aux, double* ystats, int* ystats_written) {
@@ -2212,7 +2207,8 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   char* base = static_cast<char*>(ws);
   float* inv = reinterpret_cast<float*>(base + P.o_inv);
   float* rsum = reinterpret_cast<float*>(base + P.o_rsum);
-  int* err = reinterpret_cast<int*>(base + P.o_err);
+  int* err = reinterpret_cast<int*>(base + P.o_err);       // the near-tie counter sits 16 bytes after this word
+  int* wd = watchdog_word() ? watchdog_word() : err;       // where a timed-out wait leaves its code (pinned host memory)
   uint4* xp0 = reinterpret_cast<uint4*>(base + P.o_xp[0]);
   uint4* xp1 = reinterpret_cast<uint4*>(base + P.o_xp[1]);
   uint4* rp0 = reinterpret_cast<uint4*>(base + P.o_rp[0]);
@@ -2295,7 +2291,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   // ---- forward ----
   FwdParams f;
   f.xp[0] = xp0; f.xp[1] = xp1; f.wp = wp; f.rp[0] = rp0; f.rp[1] = rp1;
-  f.y = y; f.winner = winner; f.inv = ((flags & HEBB_F_WNRM) && !tr) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = err;
+  f.y = y; f.winner = winner; f.inv = ((flags & HEBB_F_WNRM) && !tr) ? inv : nullptr; f.bias = bias; f.rsum = rsum; f.err = wd;
   // BatchNorm statistics of y ride along when the layer is one channel tile of a plain convolution
   f.ystats = (ystats && do_fwd && !tr && P.n_ct == 1) ? ystats : nullptr;
   if (f.ystats) {
@@ -2377,7 +2373,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
   // ---- dW ----
-  HEBB_TRY(launch_dw(P, g, xp0, xp1, rp0, rp1, hpart, err, P.PA, P.PRS, st, rsw));
+  HEBB_TRY(launch_dw(P, g, xp0, xp1, rp0, rp1, hpart, wd, P.PA, P.PRS, st, rsw));
   const int n_part = rsw ? P.rs_PS * (P.rs_stackM ? 2 : 1) : P.PS * P.Q;           // partial planes the finalize pass sums
   const int cin_p = rsw ? P.rs_CinP : P.CinP;
   {
@@ -2419,7 +2415,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     float* G = reinterpret_cast<float*>(base + P.o_gram);
     float* hpart2 = reinterpret_cast<float*>(base + P.o_hpart2);
     HEBB_CUDA_TRY(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)g.Cout * g.Cout, st));
-    HEBB_TRY(launch_dw(P2, g2, rp0, rp1, rp0, rp1, hpart2, err, P.PRS, P.PRS, st));
+    HEBB_TRY(launch_dw(P2, g2, rp0, rp1, rp0, rp1, hpart2, wd, P.PRS, P.PRS, st));
     long long gx = cdiv((long long)g.Cout * g.Cout, 32);
     const long long cap = (long long)num_sms() * 32;
     if (gx > cap) gx = cap;

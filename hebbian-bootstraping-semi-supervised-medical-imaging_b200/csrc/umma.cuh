@@ -189,6 +189,33 @@ __device__ __host__ __forceinline__ uint32_t idesc_bf16(int m, int n, int a_mn_m
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---- warp helpers of the epilogues ----
+template <int CH>
+__device__ __forceinline__ float lane_col_sum(float (&v)[CH], int lane) {
+  // returns in lane l the sum over the 32 lanes of v[l % CH]
+  if (CH == 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+  }
+#pragma unroll
+  for (int off = CH / 2; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+
+template <int CH> struct TmemLd;
+template <> struct TmemLd<32> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[32]) { tmem_ld32(a, v); } };
+template <> struct TmemLd<16> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) { tmem_ld16(a, v); } };
+
+
 // ---- fp32 -> bf16 hi/lo split (round to nearest even) ----
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);

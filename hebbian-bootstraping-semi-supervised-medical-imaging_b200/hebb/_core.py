@@ -301,6 +301,8 @@ class _HebbianConvNd(nn.Module):
         if self.mode not in valid:
             raise NotImplementedError("Learning mode {} unavailable for {} layer".format(self.mode, self.__class__.__name__))
         native = self.MODE_SWTA_T if self._transposed else self.MODE_SWTA
+        if self._transposed and self.mode == self.MODE_HPCA_T:
+            return                      # hebb.py:266-277: see _hpca_t_update
         if self.mode == self.MODE_HPCA and self.patchwise:
             return                      # HPCA: tcgen05 kernels for plain convs; transposed layers (the conv rule
                                         # with x and y exchanged, hebb.py:243-246) on the fp32 CUDA-core kernels
@@ -318,6 +320,43 @@ class _HebbianConvNd(nn.Module):
                 "Learning mode {} (patchwise={}) of {} is not built into libhebb_sm100 yet; the sm_100 library "
                 "implements the pretraining path ('{}', patchwise=True) and has no PyTorch fallback".format(
                     self.mode, self.patchwise, self.__class__.__name__, native))
+
+    def _hpca_t_update(self, x, y):
+        """mode 'hpca_t' of the transposed layers (hebb.py:266-277, hebb3d.py:291-305): for every kernel offset t the
+        responses are the outputs y at offset t of each (non-overlapping) patch,
+            delta_w[ci, co, t] += sum_p y_t[co, p] x[ci, p] - sum_t' sum_{co' <= co} (y_t' y_t'^T)[co, co'] W[ci, co', t']
+        (the decay is summed over the offsets for patchwise=True, per offset otherwise).  A rule off the pretraining path
+        (SURVEY 8f row 1): the forward runs on the sm_100 kernels, the update is a few batched GEMMs through torch on
+        the same device.  The 3-D reference evaluates the triangular decay in chunks of 32 output channels
+        (PARALLEL_CHANNELS, hebb3d.py:12,293-305); that is kept."""
+        nd = self._nd
+        ks, st = self.kernel_size, self.stride
+        if tuple(ks) != tuple(st) or any(v != 0 for v in self._pad_list()):
+            raise NotImplementedError('hpca_t is built for kernel_size == stride and padding 0 (the layers makehebbian produces)')
+        with torch.no_grad():
+            B, C = y.shape[0], y.shape[1]
+            sp = x.shape[2:]
+            taps = math.prod(ks)
+            shape = [B, C]
+            for n, k in zip(sp, ks):
+                shape += [n, k]
+            yv = y.detach().reshape(shape)
+            k_axes = [3 + 2 * i for i in range(nd)]
+            s_axes = [2 + 2 * i for i in range(nd)]
+            r = yv.permute(*k_axes, 1, 0, *s_axes).reshape(taps, C, -1)                  # [taps, Cout, B * P]
+            xf = x.detach().permute(0, *range(2, nd + 2), 1).reshape(-1, x.shape[1])     # [B * P, Cin]
+            w = self.weight.detach()                                                      # (Cin, Cout, k...) view
+            wp = w.permute(*range(2, nd + 2), 1, 0).reshape(taps, C, -1)                  # [taps, Cout, Cin]
+            step = 32 if nd == 3 else C
+            for c0 in range(0, C, step):
+                c1 = min(C, c0 + step)
+                ri = r[:, c0:c1]
+                tri = torch.tril(torch.ones(c1 - c0, c1 - c0, device=x.device, dtype=x.dtype))
+                dec = (ri.matmul(ri.transpose(-2, -1)) * tri.unsqueeze(0)).matmul(wp[:, c0:c1])
+                if self.patchwise:
+                    dec = dec.sum(dim=0, keepdim=True)
+                upd = (ri.matmul(xf.unsqueeze(0)) - dec).permute(2, 1, 0)                 # [Cin, chunk, taps]
+                self.delta_w[:, c0:c1] += upd.reshape(self.delta_w[:, c0:c1].shape)
 
     def _act_is_identity(self):
         return self.act is None or isinstance(self.act, nn.Identity)
@@ -349,6 +388,10 @@ class _HebbianConvNd(nn.Module):
         update = bool(self.training and self.alpha != 0)
         if update:
             self._check_mode()
+        if update and self._transposed and self.mode == self.MODE_HPCA_T:
+            y = self.act(self._forward_no_update(x))
+            self._hpca_t_update(x, y)
+            return y
         if update and not self._act_is_identity() and self.mode != self.MODE_CONTRASTIVE:
             y = self.act(self._forward_no_update(x))
             self._update_through_act(x, y)
@@ -401,6 +444,8 @@ class _HebbianConvNd(nn.Module):
         """Accumulate the plasticity update for an already padded x into delta_w (y is recomputed
         on chip; the argument is accepted for signature compatibility)."""
         self._check_mode()
+        if self._transposed and self.mode == self.MODE_HPCA_T:
+            return self._hpca_t_update(x, y)
         if not self._act_is_identity() and self.mode != self.MODE_CONTRASTIVE:
             return self._update_through_act(x, y, pad=False)
         self._launch(x, self.weight, self.bias, update=True, pad=False)

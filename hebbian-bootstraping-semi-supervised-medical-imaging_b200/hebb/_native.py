@@ -26,6 +26,8 @@ EXPORTS = [
     'hebb_workspace_bytes', 'hebb_wnorm', 'hebb_conv_swta_step', 'hebb_convT_swta_step',
     'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
     'hebb_debug_umma_rate', 'hebb_debug_umma_rate_shared_a', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_upsample2x_bilinear',
+    'hebb_layer_path', 'hebb_debug_fused_plan', 'hebb_watchdog_code', 'hebb_conv_swta_step_stats', 'hebb_bn_act_from_stats', 'hebb_conv_wgrad', 'hebb_maxpool2x',
+    'hebb_bias_relu_dropout', 'hebb_mask_scale',
 ]
 
 
@@ -87,6 +89,8 @@ def load():
         lib.hebb_mask_scale.argtypes = [vp, vp, vp, i64, f32, vp]
         lib.hebb_debug_launch_count.restype = ctypes.c_ulonglong
         lib.hebb_uses_tensor_cores.argtypes = [ctypes.POINTER(HebbDesc), i32]
+        lib.hebb_layer_path.argtypes = [ctypes.POINTER(HebbDesc), i32, ctypes.c_uint]
+        lib.hebb_debug_fused_plan.argtypes = [ctypes.POINTER(HebbDesc), ctypes.POINTER(ctypes.c_int), i32]
         for name in EXPORTS:
             getattr(lib, name)      # fail loudly if a declared symbol is missing
         _lib = lib
@@ -100,6 +104,10 @@ def check(status: int, what: str = ''):
         extra = ''
         if status == -5:
             extra = f' (cudaError {lib.hebb_last_cuda_error()})'
+            wd = lib.hebb_watchdog_code()
+            if wd:                       # a kernel's bounded wait timed out and trapped: HEBB_EKERNEL
+                msg = lib.hebb_status_str(-7).decode()
+                extra += f' (watchdog code {wd})'
         raise RuntimeError(f'libhebb_sm100: {what}: {msg}{extra}')
 
 
@@ -386,6 +394,22 @@ def mask_scale(gout, mask, scale: float):
 
 def launch_count() -> int:
     return int(load().hebb_debug_launch_count())
+
+
+PATH_SIMT, PATH_TC, PATH_FUSED = 0, 1, 2
+FUSED_PLAN_FIELDS = ['TH', 'TW', 'pitch', 'tiles', 'blocks_per_tile', 'x_rows', 'smem', 'tmem_cols', 'grid']
+
+
+def layer_path(desc: HebbDesc, prec: int, flags: int = 0) -> int:
+    """Which kernels a step of this layer runs on: PATH_SIMT (fp32 CUDA cores), PATH_TC (pack + forward + update
+    tcgen05 kernels) or PATH_FUSED (the one-kernel small-channel path)."""
+    return int(load().hebb_layer_path(ctypes.byref(desc), int(prec), int(flags)))
+
+
+def fused_plan(desc: HebbDesc):
+    out = (ctypes.c_int * 16)()
+    n = load().hebb_debug_fused_plan(ctypes.byref(desc), out, 16)
+    return dict(zip(FUSED_PLAN_FIELDS, list(out)[:n])) if n else None
 
 
 def uses_tensor_cores(desc: HebbDesc, prec: int) -> bool:

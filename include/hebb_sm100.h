@@ -76,6 +76,10 @@ int hebb_query(int* sm_major, int* sm_minor, int* num_sms);
 const char* hebb_status_str(int status);
 /* cudaError_t of the last failing runtime call seen by this thread (0 if none). */
 int hebb_last_cuda_error(void);
+/* Code left by a kernel whose bounded mbarrier wait timed out (0 = none).  Such a kernel traps, the CUDA context is
+ * lost and every later call returns HEBB_ECUDA; the word is kept in pinned host memory so it stays readable.  The Python
+ * binding reports it as HEBB_EKERNEL.  Codes 1-6: forward kernel, 11-13: update kernel, 20-28: fused kernel. */
+int hebb_watchdog_code(void);
 const char* hebb_version(void);
 
 /* Output extent (D,H,W) of the layer described by d. */
@@ -189,6 +193,16 @@ unsigned long long hebb_debug_launch_count(void);
 
 /* 1 if (d, prec) runs on the tcgen05 kernels, 0 if on the CUDA-core kernels. */
 int hebb_uses_tensor_cores(const HebbDesc* d, int prec);
+
+/* Which kernels a step of (d, prec, flags) runs on: 0 = fp32 CUDA-core kernels, 1 = tcgen05 pack / forward / update
+ * kernels, 2 = the fused small-channel kernel (2-D, Cin and Cout in {16, 32}, stride 1, kernel <= 3x3: forward, soft-WTA
+ * and update in ONE launch fed by TMA tensor-map loads of the fp32 NCHW input -- SURVEY 8b `hebb_fwd_dw_fused`; reached
+ * through hebb_conv_swta_step / hebb_conv_swta_step_stats, hebb/hebb.py:87-115); -1 for an invalid descriptor. */
+int hebb_layer_path(const HebbDesc* d, int prec, unsigned flags);
+
+/* Tile plan of the fused kernel (0 if the layer does not take it): {TH, TW, tile row pitch, tiles, 128-position blocks
+ * per tile, x rows per tile, shared memory, TMEM columns, grid}; returns the number of fields. */
+int hebb_debug_fused_plan(const HebbDesc* d, int* out, int n);
 
 /* Tile plan the tensor-core path would use (0 if it would not run there): fills out[0..n) with
  * {MB, fwd SEGLEN, XST, WST, NACC, fwd TMEM cols, fwd tiles, fwd smem, dW by_kh, CM, CN, BLK, ST, dW SEGLEN,

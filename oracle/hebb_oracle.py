@@ -223,6 +223,39 @@ def contrastive_delta(xp, weight, bias, stride, contrast=1., perm=None, w_nrm=Tr
     return grads[0], (grads[1] if b is not None else None)
 
 
+def hpca_t_delta(x, y, weight, stride, patchwise=True, nd=None):
+    """mode 'hpca_t' of the transposed layers (hebb/hebb.py:266-277, hebb/hebb3d.py:291-305), kernel == stride, no
+    padding.  weight: the (Cin, Cout, k...) view.  For each kernel offset t the responses are y at offset t of every
+    input position's output patch; delta[ci, co, t] = sum_p y_t[co,p] x[ci,p] - sum_{co'<=co} (y_t y_t^T)[co,co'] W[ci,co',t]
+    with the decay summed over t when patchwise.  The 3-D reference applies the triangular mask inside chunks of 32
+    output channels (PARALLEL_CHANNELS, hebb3d.py:12)."""
+    nd = x.dim() - 2 if nd is None else nd
+    ks = tuple(weight.shape[2:])
+    B, C = y.shape[0], y.shape[1]
+    taps = 1
+    for k in ks:
+        taps *= k
+    shape = [B, C]
+    for n, k in zip(x.shape[2:], ks):
+        shape += [n, k]
+    k_axes = [3 + 2 * i for i in range(nd)]
+    s_axes = [2 + 2 * i for i in range(nd)]
+    r = y.reshape(shape).permute(*k_axes, 1, 0, *s_axes).reshape(taps, C, -1)
+    xf = x.permute(0, *range(2, nd + 2), 1).reshape(-1, x.shape[1])
+    wp = weight.permute(*range(2, nd + 2), 1, 0).reshape(taps, C, -1)
+    out = torch.zeros(weight.shape, dtype=weight.dtype)
+    step = 32 if nd == 3 else C
+    for c0 in range(0, C, step):
+        c1 = min(C, c0 + step)
+        ri = r[:, c0:c1]
+        tri = torch.tril(torch.ones(c1 - c0, c1 - c0, dtype=x.dtype))
+        dec = (ri.matmul(ri.transpose(-2, -1)) * tri).matmul(wp[:, c0:c1])
+        if patchwise:
+            dec = dec.sum(dim=0, keepdim=True)
+        out[:, c0:c1] = (ri.matmul(xf.unsqueeze(0)) - dec).permute(2, 1, 0).reshape(out[:, c0:c1].shape)
+    return out
+
+
 # --------------------------------------------------------------------------
 # a8  local_update()                     hebb/hebb.py:174-192, hebb/hebb3d.py:198-216
 # --------------------------------------------------------------------------

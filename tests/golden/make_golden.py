@@ -355,7 +355,12 @@ def round2_goldens():
             layer = cls(64, 64, 3, padding=1, bias=False, k=50., alpha=1.)
             with torch.no_grad():
                 layer.weight.copy_(w0)
-            opt = (torch.optim.SGD([layer.weight], lr=1e-3) if opt_name == 'sgd' else torch.optim.Adam([layer.weight], lr=1e-3))
+            # SGD: lr 1e-3 (the weights move by ~10 % of their norm in 100 steps).  Adam: lr 1e-5 = the reference's 3-D setting
+            # (reproduce_hebbian_unsupervised_pretraining_3d.sh; 10x its 2-D one) -- Adam makes every element move by ~lr per
+            # step whatever the update's size, so at lr 1e-3 the weights would travel further than their own magnitude and any
+            # two fp32 evaluation orders diverge chaotically
+            lr = 1e-3 if opt_name == 'sgd' else 1e-5
+            opt = (torch.optim.SGD([layer.weight], lr=lr) if opt_name == 'sgd' else torch.optim.Adam([layer.weight], lr=lr))
             layer.train()
             w1 = None
             for step in range(100):
@@ -369,7 +374,7 @@ def round2_goldens():
             out[name + '/w1'] = w1.reshape(-1)[idx].numpy()
             out[name + '/w100'] = layer.weight.detach().reshape(-1)[idx].numpy()
             out[name + '/norms'] = np.array([float(w1.norm()), float(layer.weight.detach().norm())])
-            meta[name] = dict(kind='drift64', nd=nd, opt=opt_name, lr=1e-3, k=50., steps=100, spatial=list(sp), B=B)
+            meta[name] = dict(kind='drift64', nd=nd, opt=opt_name, lr=lr, k=50., steps=100, spatial=list(sp), B=B)
 
     # a layer with a non-Identity activation: the plasticity rule is applied to act(y)
     for (name, Cin, Cout, sp) in [('act_relu_16_16', 16, 16, (12, 10)), ('act_relu_32_64', 32, 64, (9, 11))]:
@@ -383,6 +388,20 @@ def round2_goldens():
         out[name + '/x'], out[name + '/w'], out[name + '/b'] = x.numpy(), layer.weight.detach().numpy(), layer.bias.detach().numpy()
         out[name + '/y'], out[name + '/dw1'] = y.detach().numpy(), layer.delta_w.clone().numpy()
         meta[name] = dict(kind='act', Cin=Cin, Cout=Cout, spatial=list(sp), k=5., act='relu')
+    # mode 'hpca_t' of the transposed layers (hebb.py:266-277, hebb3d.py:291-305); 40 output channels cross the 3-D
+    # reference's 32-channel chunking of the triangular decay
+    for (name, nd, B, Cin, Cout, sp) in [('hpca_t2d_6_4', 2, 2, 6, 4, (5, 7)), ('hpca_t3d_8_4', 3, 1, 8, 4, (3, 4, 5)),
+                                         ('hpca_t3d_6_40', 3, 1, 6, 40, (2, 3, 3))]:
+        cls = ref.HebbianConvTranspose2d if nd == 2 else ref.HebbianConvTranspose3d
+        layer = cls(Cin, Cout, 2, stride=2, padding=0, bias=False, w_nrm=True, mode='hpca_t', k=1., patchwise=True, alpha=1.)
+        with torch.no_grad():
+            layer.weight.copy_(rnd(*layer.weight.shape, scale=0.3))
+        layer.train()
+        x = rnd(B, Cin, *sp)
+        y = layer(x)
+        out[name + '/x'], out[name + '/w'] = x.numpy(), layer.weight.detach().contiguous().numpy()
+        out[name + '/y'], out[name + '/dw1'] = y.detach().numpy(), layer.delta_w.clone().contiguous().numpy()
+        meta[name] = dict(kind='hpca_t', nd=nd, B=B, Cin=Cin, Cout=Cout, spatial=list(sp))
     np.savez_compressed(os.path.join(HERE, 'hebb_golden_r2.npz'), **out)
 
     with contextlib.redirect_stdout(io.StringIO()):

@@ -3,7 +3,7 @@ import torch
 
 
 def digest_err(t, dg):
-    t = t.detach().contiguous().reshape(-1).double()
+    t = t.detach().contiguous().reshape(-1).double().cpu()
     idx = torch.tensor(dg['idx'])
     val = torch.tensor(dg['val'], dtype=torch.float64)
     scale = max(dg['norm'] / max(t.numel(), 1) ** 0.5, 1e-30)

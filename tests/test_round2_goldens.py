@@ -35,7 +35,8 @@ def test_oracle_drift64_matches_reference(nd, opt_name):
     layer = O.OracleHebbConv(nd, 64, 64, 3, padding=1, bias=False, k=50., alpha=1.)
     with torch.no_grad():
         layer.weight.copy_(torch.from_numpy(G2[f'drift64_{nd}d/w0']))
-    opt = torch.optim.SGD([layer.weight], lr=1e-3) if opt_name == 'sgd' else torch.optim.Adam([layer.weight], lr=1e-3)
+    lr = STEPS['meta'][f'drift64_{nd}d_{opt_name}']['lr']
+    opt = torch.optim.SGD([layer.weight], lr=lr) if opt_name == 'sgd' else torch.optim.Adam([layer.weight], lr=lr)
     layer.train()
     idx = G2[f'drift64_{nd}d/idx']
     for step in range(100):
@@ -60,6 +61,17 @@ def test_oracle_nonidentity_act_matches_reference(name):
     assert float((y - torch.from_numpy(G2[name + '/y'])).norm() / torch.from_numpy(G2[name + '/y']).norm()) < 1e-6
     ref = torch.from_numpy(G2[name + '/dw1'])
     assert float((layer.delta_w - ref).norm() / ref.norm()) < 1e-5
+
+
+@pytest.mark.parametrize('name', ['hpca_t2d_6_4', 'hpca_t3d_8_4', 'hpca_t3d_6_40'])
+def test_oracle_hpca_t_matches_reference(name):
+    m = STEPS['meta'][name]
+    x, w = torch.from_numpy(G2[name + '/x']), torch.from_numpy(G2[name + '/w'])
+    y = O.convT_activation(x, w, None, (2,) * m['nd'])
+    assert float((y - torch.from_numpy(G2[name + '/y'])).norm() / torch.from_numpy(G2[name + '/y']).norm()) < 1e-6
+    dw = O.hpca_t_delta(x, y, w, (2,) * m['nd'])
+    ref = torch.from_numpy(G2[name + '/dw1'])
+    assert float((dw - ref).norm() / ref.norm()) < 1e-5
 
 
 def build_oracle_net(name):
