@@ -39,7 +39,12 @@ constexpr int kSmemLimitF = 227 * 1024;
 constexpr int kRLead = 8;                 // zero / carried-over positions in front of every response slot
 constexpr int kRSlotPos = kRLead + 128;
 constexpr int kMaxRows = 18;              // x tile rows (TH + kH - 1) a CTA keeps barriers for
-constexpr int kThreadsF = 448;
+constexpr int kMaxStages = 10;            // fp32 staging ring (TMA boxes in flight)
+constexpr int kDwLag = 2;                 // the update MMAs of a block are issued this many blocks after its forward MMAs
+constexpr int kRSlots = kDwLag + 2;       // response ring: slots of kRSlotPos positions
+constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxRows + 2 + 2 + 2 * kRSlots + 2;
+constexpr int kThreadsF = 416;            // warps: 0 TMA producer, 1 forward issuer, 2 update issuer, 3-4 converter, 5-8 / 9-12 the two epilogue sets
+constexpr int kConvWarps = 2;             // (384 threads leave 168 registers per thread: a 32-channel row + its sums fit)
 
 struct FusedParams {
   float* y; int32_t* winner; const float* inv; const float* bias; float* rsum; double* ystats; float* hpart; int* err;
@@ -49,6 +54,9 @@ struct FusedParams {
   int TH, TW, pitch, nTH, nTW, ntiles, XROWS, NBLK, XPOS, NST;
   int BW, padl;                // TMA box width (floats) and left pad of the box start: staging column = tile column + padl - pW
   float kinv; int update;
+  long long* prof;             // HEBB_FUSED_PROF=1: per CTA [32] cycles spent in each bounded wait (index = code - 16) + totals
+  int dbg;                     // HEBB_FUSED_DBG (profiling only): 1 one forward MMA per block, 2 no update MMAs, 4 no epilogue math,
+                               // 8 no conversion, 16 no y stores
   uint32_t off_r, off_stage, off_w, off_misc, w_bytes, stage_bytes, tmem_cols;
 };
 
@@ -86,7 +94,19 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int CIN, int COUT>
+// bounded wait; with PROF the cycles spent in it are accumulated per wait code (20..28)
+#define FWAIT(bar, par, code)                                                        \
+  do {                                                                               \
+    if (PROF) {                                                                      \
+      const long long _t = clock64();                                                \
+      mbar_wait(bar, par, p.err, code);                                              \
+      prof_acc[(code) - 20] += clock64() - _t;                                       \
+    } else {                                                                         \
+      mbar_wait(bar, par, p.err, code);                                              \
+    }                                                                                \
+  } while (0)
+
+template <int CIN, int COUT, int KS, bool PROF>
 __global__ void __launch_bounds__(kThreadsF, 1)
 fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
   constexpr int XB = CIN * 4;              // bytes per position of the x image: [hi Cin | lo Cin] bf16
@@ -95,25 +115,31 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   constexpr uint32_t XLAY = (XB == 128) ? 2u : 4u, RLAY = (RB == 128) ? 2u : 4u;     // SWIZZLE_128B : SWIZZLE_64B
   constexpr int NSL = CIN / 16;            // 16-channel slabs (K steps of the forward)
   constexpr int COPIES = 128 / (2 * CIN);  // kh copies of the x tile in the M = 128 rows of an update instruction
+  constexpr int FCOLS = 2 * COUT;          // forward accumulator: [x w_hi (+ x_lo w_hi) | x_hi w_lo]
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  long long prof_acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) prof_acc[i] = 0;
+  const long long prof_t0 = PROF ? clock64() : 0;
 
   float* s_inv = reinterpret_cast<float*>(smem + p.off_misc);
   float* s_bias = s_inv + COUT;
   float* s_rs = s_bias + COUT;               // [8 warps][COUT]
   float* s_ys = s_rs + 8 * COUT;
   float* s_yq = s_ys + COUT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_yq + COUT);
+  float* s_tab = s_yq + COUT;                 // 2 x 32 ints: per-block row tables of the issuing warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + 64);
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t st_full = bar0, st_empty = st_full + 8 * 8;
-  const uint32_t xr_full = st_empty + 8 * 8, xr_empty = xr_full + 8 * kMaxRows;
+  const uint32_t st_full = bar0, st_empty = st_full + 8 * kMaxStages;
+  const uint32_t xr_full = st_empty + 8 * kMaxStages, xr_empty = xr_full + 8 * kMaxRows;
   const uint32_t tf_full = xr_empty + 8 * kMaxRows, tf_empty = tf_full + 16;
-  const uint32_t r_full = tf_empty + 16, w_full = r_full + 24, done = w_full + 8;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16 + 2 * kMaxRows + 2 + 2 + 3 + 2);
+  const uint32_t r_full = tf_empty + 16, r_empty = r_full + 8 * kRSlots, w_full = r_empty + 8 * kRSlots, done = w_full + 8;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int NACC = (p.kH + COPIES - 1) / COPIES;          // update accumulators actually used (at most 2)
   // accumulator 1 re-reads the last COPIES kernel rows (kh = kH-COPIES ..), so that no copy reaches past kh = kH-1
@@ -128,19 +154,28 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     s_bias[i] = p.bias ? p.bias[i] : 0.f;
   }
   for (int i = threadIdx.x; i < 10 * COUT; i += blockDim.x) s_rs[i] = 0.f;     // rs, ys, yq
+  if ((int)threadIdx.x < p.NBLK && threadIdx.x < 32) {
+    const int kb = threadIdx.x;
+    int need = ((kb + 1) * 128 - 1 + (p.kH - 1) * p.pitch + (p.kW - 1)) / p.pitch + 1;
+    if (need > p.XROWS) need = p.XROWS;
+    int free_to = (kb == p.NBLK - 1) ? p.XROWS : ((kb + 1) * 128) / p.pitch;
+    if (free_to > p.XROWS) free_to = p.XROWS;
+    reinterpret_cast<int*>(s_tab)[kb] = need;
+    reinterpret_cast<int*>(s_tab)[32 + kb] = free_to;
+  }
   {
     // x image beyond the converted rows (read by the wasted kh copies / the last block) and the response ring
     const uint32_t x_tail = (uint32_t)p.XROWS * p.pitch * XB, x_end = (uint32_t)p.XPOS * XB;
     for (uint32_t a = x_tail + threadIdx.x * 16; a < x_end; a += blockDim.x * 16) st_shared_v4(xb + a, 0, 0, 0, 0);
-    const uint32_t r_end = 3u * kRSlotPos * RB;
+    const uint32_t r_end = (uint32_t)kRSlots * kRSlotPos * RB;
     for (uint32_t a = threadIdx.x * 16; a < r_end; a += blockDim.x * 16) st_shared_v4(rb + a, 0, 0, 0, 0);
   }
   fence_proxy_async();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, 4); }
-    for (int i = 0; i < kMaxRows; ++i) { mbar_init(xr_full + 8 * i, 4 * NSL); mbar_init(xr_empty + 8 * i, 1); }
+    for (int i = 0; i < p.NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, kConvWarps); }
+    for (int i = 0; i < kMaxRows; ++i) { mbar_init(xr_full + 8 * i, kConvWarps * NSL); mbar_init(xr_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tf_full + 8 * i, 1); mbar_init(tf_empty + 8 * i, 4); }
-    for (int i = 0; i < 3; ++i) mbar_init(r_full + 8 * i, 4);
+    for (int i = 0; i < kRSlots; ++i) { mbar_init(r_full + 8 * i, 4); mbar_init(r_empty + 8 * i, 1); }
     mbar_init(w_full, 1); mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -149,9 +184,10 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t tmem_f = tmem_base;                      // 2 forward accumulators of COUT columns
-  const uint32_t tmem_d = tmem_base + 2 * COUT;           // NACC update accumulators of NW columns
+  const uint32_t tmem_f = tmem_base;                      // 2 forward accumulators of FCOLS columns
+  const uint32_t tmem_d = tmem_base + 2 * FCOLS;          // NACC update accumulators of NW columns
   const int per_img = p.nTH * p.nTW;
+  const int my_tiles = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -166,115 +202,142 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int h0 = th * p.TH - p.pH, w0 = tw * p.TW - p.padl;      // box start: a multiple of 4 floats (16 bytes)
         for (int r = 0; r < p.XROWS; ++r)
           for (int cg = 0; cg < NSL; ++cg) {
-            mbar_wait(st_empty + 8 * s, ph ^ 1, p.err, 21);
+            FWAIT(st_empty + 8 * s, ph ^ 1, 21);
             mbar_expect_tx(st_full + 8 * s, row_bytes);
             tma_load_3d(sbase + p.off_stage + s * p.stage_bytes, &tmap, w0, h0 + r, b * CIN + cg * 16, st_full + 8 * s);
             if (++s == p.NST) { s = 0; ph ^= 1; }
           }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc_f = idesc_bf16(128, COUT, 0, 0);
-    const uint32_t idesc_d = idesc_bf16(128, NW, 1, 1);
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: warp 1 forward, warp 2 update =====================
+    // The issuing thread is the critical resource of this kernel (26-50 instructions per 128 positions, each worth
+    // ~45 cycles of tensor-pipe time): everything it needs per instruction is a compile-time constant or sits in a
+    // register before the loop -- tap offsets, weight descriptors, per-block row counts -- so that an issue is one or
+    // two integer adds plus the tcgen05.mma itself, and the loop nest is warp-uniform (descriptors in uniform registers).
+    constexpr int TAPS = KS * KS;
+    const uint32_t idesc_f1 = idesc_bf16(128, 2 * COUT, 0, 0);     // x_hi * [w_hi | w_lo]
+    const uint32_t idesc_f2 = idesc_bf16(128, COUT, 0, 0);         // x_lo * w_hi
+    const uint32_t idesc_d = idesc_bf16(128, KS * 2 * COUT, 1, 1);
     // forward A: K-major swizzled rows of XB bytes, 8-row groups 8*XB apart (LBO unused: K = 32 bytes < row)
     const uint32_t fa_hi = ((8u * XB) >> 4) | (1u << 14) | (XLAY << 29);
-    // forward B: SWIZZLE_NONE K-major packed weights [k-chunk][hi|lo][COUT rows][16 B]
+    // forward B: SWIZZLE_NONE K-major packed weights [k-chunk][hi|lo][COUT rows][16 B]: for one k-chunk the w_hi rows are
+    // directly followed by the w_lo rows, so N = 2 COUT rows from the w_hi start are [w_hi | w_lo]
     const uint32_t fb_hi = (128u >> 4) | (1u << 14);
-    const uint32_t fb_lbo = ((2u * COUT * 16u) >> 4) << 16;
+    const uint32_t fb_base = (((2u * COUT * 16u) >> 4) << 16) | (((sbase + p.off_w) >> 4) & 0x3FFFu);
     // update A: MN-major swizzled, atoms (kh copies) one tile row apart, 8-position groups 8*XB apart
     const uint32_t da_hi = ((8u * XB) >> 4) | (1u << 14) | (XLAY << 29);
-    const uint32_t da_lbo = (((uint32_t)p.pitch * XB) >> 4) << 16;
+    const uint32_t da_base = ((((uint32_t)p.pitch * XB) >> 4) << 16) | ((xb >> 4) & 0x3FFFu);
     // update B: MN-major swizzled response image, atoms (kw copies) ONE position apart
     const uint32_t db_hi = ((8u * RB) >> 4) | (1u << 14) | (RLAY << 29);
-    const uint32_t db_lbo = ((uint32_t)RB >> 4) << 16;
-    const uint32_t wb = sbase + p.off_w;
-    mbar_wait(w_full, 0, p.err, 20);
-    uint32_t kk = 0;               // blocks issued by this CTA so far
-    uint32_t d_acc = 0;            // 0 until the update accumulators hold something
-    int it = 0;
-    // update MMAs of block j of the current tile (kkj = its running index), then release the x rows it was last to read
-    auto dw_block = [&](int j, uint32_t kkj, int& rows_freed, bool last) {
-      const uint32_t slot = kkj % 3u;
-      mbar_wait(r_full + 8 * slot, (kkj / 3u) & 1u, p.err, 24);
-      tc_fence_after();
-      int free_to = last ? p.XROWS : (int)(((j + 1) * 128) / p.pitch);
-      if (free_to > p.XROWS) free_to = p.XROWS;
-      if (elect_one()) {
-        uint32_t a = da_lbo | (((xb + (uint32_t)(j * 128) * XB) >> 4) & 0x3FFFu);
-        uint32_t b = db_lbo | (((rb + slot * (kRSlotPos * RB) + (uint32_t)(kRLead - (p.kW - 1)) * RB) >> 4) & 0x3FFFu);
-        const uint32_t a2 = (uint32_t)(kh_base1 * p.pitch * XB) >> 4;    // second accumulator: kh copies kH-COPIES ..
-#pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks, a += XB, b += RB) {              // 16 positions per instruction
-          umma_rt(tmem_d, a, da_hi, b, db_hi, idesc_d, d_acc);
-          if (NACC > 1) umma_rt(tmem_d + NW, a + a2, da_hi, b, db_hi, idesc_d, d_acc);
-          d_acc = 1u;
-        }
-        for (int r = rows_freed; r < free_to; ++r) umma_commit(xr_empty + 8 * r);
-      }
-      __syncwarp();
-      d_acc = 1u;
-      rows_freed = free_to > rows_freed ? free_to : rows_freed;
-    };
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const uint32_t db_base = (((uint32_t)RB >> 4) << 16) | (((rb + (uint32_t)(kRLead - (KS - 1)) * RB) >> 4) & 0x3FFFu);
+    const uint32_t fa_base = (xb >> 4) & 0x3FFFu;
+    uint32_t toff[TAPS];                      // tap -> start offset of the A operand, in 16-byte units
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) toff[t] = (uint32_t)(((t / KS) * p.pitch + (t % KS)) * XB) >> 4;
+    const uint32_t a2 = (uint32_t)(kh_base1 * p.pitch * XB) >> 4;    // second update accumulator: kh copies kH-COPIES ..
+    const int* s_need = reinterpret_cast<const int*>(s_tab);          // rows the forward of block k needs converted
+    const int* s_free = s_need + 32;                                  // rows free once the update of block k is done
+    const int total = my_tiles * p.NBLK;
+    if (warp == 1) {
+      // ---------- forward issuer: block g as soon as its x rows are converted and its TMEM buffer has been drained ----------
+      FWAIT(w_full, 0, 20);
       int rows_ready = 0, rows_freed = 0;
-      for (int k = 0; k < p.NBLK; ++k, ++kk) {
-        int need = ((k + 1) * 128 - 1 + (p.kH - 1) * p.pitch + (p.kW - 1)) / p.pitch + 1;
-        if (need > p.XROWS) need = p.XROWS;
-        for (; rows_ready < need; ++rows_ready) mbar_wait(xr_full + 8 * rows_ready, it & 1, p.err, 22);
-        const uint32_t acc = kk & 1u;
-        mbar_wait(tf_empty + 8 * acc, ((kk >> 1) & 1u) ^ 1u, p.err, 23);
+      int k = 0, it = 0;                        // block within the tile, tile count
+      for (int g = 0; g < total; ++g) {
+        if (k == 0) rows_ready = 0;
+        const int need = s_need[k];
+        for (; rows_ready < need; ++rows_ready) FWAIT(xr_full + 8 * rows_ready, it & 1, 22);
+        const uint32_t acc = (uint32_t)g & 1u;
+        FWAIT(tf_empty + 8 * acc, (((uint32_t)g >> 1) & 1u) ^ 1u, 23);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d = tmem_f + acc * COUT;
-          bool first = true;
-          for (int kh = 0; kh < p.kH; ++kh)
-            for (int kw = 0; kw < p.kW; ++kw) {
-              const int tap = kh * p.kW + kw;
-              const uint32_t qa = xb + (uint32_t)(k * 128 + kh * p.pitch + kw) * XB;
+          const uint32_t d = tmem_f + acc * FCOLS;
+          const uint32_t ablk = fa_base + (uint32_t)k * (128u * XB >> 4);
+          const int ntap = (p.dbg & 1) ? 1 : TAPS;
+#pragma unroll
+          for (int t = 0; t < TAPS; ++t) {
+            if (t < ntap) {
 #pragma unroll
               for (int s = 0; s < NSL; ++s) {
-                const uint32_t ah = ((qa + 32u * s) >> 4) & 0x3FFFu, al = ((qa + 2u * CIN + 32u * s) >> 4) & 0x3FFFu;
-                const uint32_t wa = wb + (uint32_t)((s * p.taps + tap) * 4 * COUT) * 16u;
-                const uint32_t bh = fb_lbo | ((wa >> 4) & 0x3FFFu), bl = fb_lbo | (((wa + COUT * 16u) >> 4) & 0x3FFFu);
-                if (first) umma_lo<1, 0>(d, ah, fa_hi, bl, fb_hi, idesc_f);
-                else umma_lo<1, 1>(d, ah, fa_hi, bl, fb_hi, idesc_f);
-                umma_lo<3, 1>(d, ah, fa_hi, bh, fb_hi, idesc_f);
-                umma_lo<0, 1>(d, al, fa_hi, bh, fb_hi, idesc_f);
-                first = false;
+                const uint32_t ah = ablk + toff[t] + 2u * s, al = ah + (2u * CIN >> 4);
+                const uint32_t bh = fb_base + (uint32_t)((s * TAPS + t) * 4 * COUT);
+                if (t == 0 && s == 0) umma_lo<0, 0>(d, ah, fa_hi, bh, fb_hi, idesc_f1);
+                else umma_lo<0, 1>(d, ah, fa_hi, bh, fb_hi, idesc_f1);
+                umma_lo<0, 1>(d, al, fa_hi, bh, fb_hi, idesc_f2);
               }
             }
+          }
           umma_commit(tf_full + 8 * acc);
         }
         __syncwarp();
-        if (p.update) {
-          if (k > 0) dw_block(k - 1, kk - 1, rows_freed, false);
-        } else {
+        if (!p.update) {
           // forward only: rows are free once the blocks that read them have been issued
-          int free_to = (k == p.NBLK - 1) ? p.XROWS : (int)(((k + 1) * 128) / p.pitch);
-          if (free_to > p.XROWS) free_to = p.XROWS;
+          if (k == 0) rows_freed = 0;
+          const int free_to = s_free[k];
           if (elect_one())
             for (int r = rows_freed; r < free_to; ++r) umma_commit(xr_empty + 8 * r);
           __syncwarp();
           rows_freed = free_to > rows_freed ? free_to : rows_freed;
         }
+        if (++k == p.NBLK) { k = 0; ++it; }
       }
-      if (p.update) dw_block(p.NBLK - 1, kk - 1, rows_freed, true);
+    } else if (p.update) {
+      // ---------- update issuer: block g once its responses are in the ring (i.e. after its forward has completed and
+      // been through the epilogue).  It runs on its own warp so that its waits overlap the forward issue; the tensor
+      // pipe takes both instruction streams.  A tcgen05.commit only tracks the MMAs of its own thread: the x rows it
+      // releases are last read by forward blocks <= g, which have completed by the time r_full(g) is set. ----------
+      int rows_freed = 0;
+      int jd = 0; uint32_t slot_d = 0, ph_d = 0;   // block within its tile, response slot, its phase
+      bool d_first = true;
+      for (int g = 0; g < total; ++g) {
+        if (jd == 0) rows_freed = 0;
+        FWAIT(r_full + 8 * slot_d, ph_d, 24);
+        tc_fence_after();
+        const int free_to = s_free[jd];
+        if (elect_one()) {
+          uint32_t a = da_base + (uint32_t)jd * (128u * XB >> 4);
+          uint32_t b = db_base + slot_d * ((uint32_t)(kRSlotPos * RB) >> 4);
+          const uint32_t nks = (p.dbg & 2) ? 0u : 8u;
+          if (nks) {
+            if (d_first) {
+              umma_lo<0, 0>(tmem_d, a, da_hi, b, db_hi, idesc_d);
+              if (NACC > 1) umma_lo<0, 0>(tmem_d + NW, a + a2, da_hi, b, db_hi, idesc_d);
+            } else {
+              umma_lo<0, 1>(tmem_d, a, da_hi, b, db_hi, idesc_d);
+              if (NACC > 1) umma_lo<0, 1>(tmem_d + NW, a + a2, da_hi, b, db_hi, idesc_d);
+            }
+#pragma unroll
+            for (int ks = 1; ks < 8; ++ks) {                  // 16 positions per instruction
+              a += XB; b += RB;
+              umma_lo<0, 1>(tmem_d, a, da_hi, b, db_hi, idesc_d);
+              if (NACC > 1) umma_lo<0, 1>(tmem_d + NW, a + a2, da_hi, b, db_hi, idesc_d);
+            }
+          }
+          umma_commit(r_empty + 8 * slot_d);             // the response slot (and the lead it shares) may be rewritten
+          for (int r = rows_freed; r < free_to; ++r) umma_commit(xr_empty + 8 * r);
+        }
+        __syncwarp();
+        d_first = false;
+        rows_freed = free_to > rows_freed ? free_to : rows_freed;
+        if (++jd == p.NBLK) jd = 0;
+        if (++slot_d == kRSlots) { slot_d = 0; ph_d ^= 1u; }
+      }
+      if (elect_one()) umma_commit(done);
+      __syncwarp();
     }
-    if (elect_one()) umma_commit(done);
-    __syncwarp();
-  } else if (warp < 6) {
-    // ===================== converter (warps 2..5) =====================
-    const int t = threadIdx.x - 64;
+  } else if (warp < 3 + kConvWarps) {
+    // ===================== converter (warps 3..4) =====================
+    const int t = threadIdx.x - 96;
     int s = 0; uint32_t ph = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       for (int r = 0; r < p.XROWS; ++r)
         for (int cg = 0; cg < NSL; ++cg) {
-          mbar_wait(st_full + 8 * s, ph, p.err, 25);
-          if (cg == 0) mbar_wait(xr_empty + 8 * r, (it & 1) ^ 1, p.err, 26);      // the previous tile no longer reads this row
+          FWAIT(st_full + 8 * s, ph, 25);
+          if (cg == 0) FWAIT(xr_empty + 8 * r, (it & 1) ^ 1, 26);      // the previous tile no longer reads this row
           const float* st = reinterpret_cast<const float*>(smem + p.off_stage + s * p.stage_bytes) + (p.padl - p.pW);
-          for (int c = t; c < p.pitch; c += 128) {
+          for (int c = t; c < ((p.dbg & 8) ? 0 : p.pitch); c += 32 * kConvWarps) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = st[i * p.BW + c];
@@ -298,15 +361,21 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
     }
   } else {
-    // ===================== epilogue warps 6..13: two sets of four alternate blocks =====================
+    // ===================== epilogue warps 5..12: two sets of four alternate blocks =====================
     const int quad = warp & 3;
-    const int ew = warp - 6;
+    const int ew = warp - 5;
     const int eset = ew >> 2;
     float* my_rs = s_rs + ew * COUT;
     const long long outS = (long long)p.oH * p.oW;
-    float racc[COUT], ysacc[COUT], yqacc[COUT];
+    // BatchNorm sums of y: 16-channel rows keep per-thread running sums, 32-channel rows fold every block with a
+    // butterfly (96 more live registers would not fit next to the row itself)
+    constexpr bool YACC = COUT <= 16;
+    constexpr int NY = YACC ? COUT : 1;
+    float racc[COUT], ysacc[NY], yqacc[NY];
 #pragma unroll
-    for (int i = 0; i < COUT; ++i) { racc[i] = 0.f; ysacc[i] = 0.f; yqacc[i] = 0.f; }
+    for (int i = 0; i < COUT; ++i) racc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NY; ++i) { ysacc[i] = 0.f; yqacc[i] = 0.f; }
     const bool want_ys = p.ystats != nullptr;
     const float k2 = p.kinv * 1.4426950408889634f;      // exp(k y) = 2^(k2 y)
     uint32_t kk = 0;
@@ -318,33 +387,47 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       for (int k = 0; k < p.NBLK; ++k, ++kk) {
         if ((int)(kk & 1u) != eset) continue;
         const uint32_t acc = kk & 1u;
-        mbar_wait(tf_full + 8 * acc, (kk >> 1) & 1u, p.err, 27);
+        FWAIT(tf_full + 8 * acc, (kk >> 1) & 1u, 27);
         tc_fence_after();
-        uint32_t v[COUT];
-        TmemLd<COUT>::ld(tmem_f + (static_cast<uint32_t>(quad * 32) << 16) + acc * COUT, v);
+        uint32_t v[COUT], v2[COUT];
+        const uint32_t ta = tmem_f + (static_cast<uint32_t>(quad * 32) << 16) + acc * FCOLS;
+        TmemLd<COUT>::ld(ta, v);
+        TmemLd<COUT>::ld(ta + COUT, v2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tf_empty + 8 * acc);        // the accumulator is in registers: hand the buffer back
+        if (p.dbg & 4) {
+          if (p.update) { fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(r_full + 8 * (kk % kRSlots)); }
+          continue;
+        }
         const int loc = quad * 32 + lane;
         const int q = k * 128 + loc;
         const int r_ = q / p.pitch, c_ = q - r_ * p.pitch;
         const bool valid = r_ < THv && c_ < TWv;
         float f[COUT];
 #pragma unroll
-        for (int i = 0; i < COUT; ++i) f[i] = fmaf(__uint_as_float(v[i]), s_inv[i], s_bias[i]);
+        for (int i = 0; i < COUT; ++i) f[i] = fmaf(__uint_as_float(v[i]) + __uint_as_float(v2[i]), s_inv[i], s_bias[i]);
         const long long pix = (long long)(h0 + r_) * p.oW + (w0 + c_);
         float* yb = p.y + (long long)b * COUT * outS + pix;
         float best = -INFINITY;
         int bi = 0;
 #pragma unroll
         for (int i = 0; i < COUT; ++i) {
-          if (valid) yb[(long long)i * outS] = f[i];
+          if (valid && !(p.dbg & 16)) yb[(long long)i * outS] = f[i];
           if (f[i] > best) { best = f[i]; bi = i; }            // strict: the lowest index wins ties
         }
         if (want_ys) {
+          if constexpr (YACC) {
 #pragma unroll
-          for (int i = 0; i < COUT; ++i) { const float tt = valid ? f[i] : 0.f; ysacc[i] += tt; yqacc[i] = fmaf(tt, tt, yqacc[i]); }
+            for (int i = 0; i < COUT; ++i) { const float tt = valid ? f[i] : 0.f; ysacc[i] += tt; yqacc[i] = fmaf(tt, tt, yqacc[i]); }
+          } else {
+            float t1[COUT], t2[COUT];
+#pragma unroll
+            for (int i = 0; i < COUT; ++i) { t1[i] = valid ? f[i] : 0.f; t2[i] = t1[i] * t1[i]; }
+            const float a1 = lane_col_sum<COUT>(t1, lane), a2 = lane_col_sum<COUT>(t2, lane);
+            atomicAdd(s_ys + lane, a1); atomicAdd(s_yq + lane, a2);
+          }
         }
         if (p.winner && valid) {
           p.winner[(long long)b * outS + pix] = bi;
@@ -366,9 +449,12 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           f[i] = e; sum += e;
         }
         const float rinv = valid ? (1.f / sum) : 0.f;
-        const uint32_t slot = kk % 3u, nslot = (kk + 1u) % 3u;
+        const uint32_t slot = kk % kRSlots, nslot = (kk + 1u) % kRSlots;
+        // this block writes its own slot (last read by the update of block kk-kRSlots) and the lead of the next slot
+        // (block kk-kRSlots+1): the update issuer works in order, so one wait on the younger of the two covers both
+        if (kk >= kRSlots - 1) FWAIT(r_empty + 8 * nslot, ((kk - (kRSlots - 1)) / kRSlots) & 1u, 29);
         const uint32_t row = rb + slot * (kRSlotPos * RB) + (uint32_t)(kRLead + loc) * RB;
-        // the last kW-1 positions of a block are also the lead of the next block's slot (zeros at a tile's end)
+        // the last positions of a block are also the lead of the next block's slot (zeros at a tile's end)
         const bool carry = loc >= 128 - kRLead;
         const uint32_t lrow = rb + nslot * (kRSlotPos * RB) + (uint32_t)(loc - (128 - kRLead)) * RB;
         const bool tile_end = (k == p.NBLK - 1);
@@ -416,26 +502,24 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       for (int c = lane; c < COUT; c += 32) atomicAdd(p.rsum + c, my_rs[c]);
     }
     if (want_ys) {
-      constexpr int CHF = COUT >= 32 ? 32 : 16;
+      if constexpr (YACC) {
+        float t1[COUT], t2[COUT];
 #pragma unroll
-      for (int ck = 0; ck < COUT / CHF; ++ck) {
-        float t1[CHF], t2[CHF];
-#pragma unroll
-        for (int i = 0; i < CHF; ++i) { t1[i] = ysacc[ck * CHF + i]; t2[i] = yqacc[ck * CHF + i]; }
-        const float a1 = lane_col_sum<CHF>(t1, lane), a2 = lane_col_sum<CHF>(t2, lane);
-        if (lane < CHF) { atomicAdd(s_ys + ck * CHF + lane, a1); atomicAdd(s_yq + ck * CHF + lane, a2); }
+        for (int i = 0; i < COUT; ++i) { t1[i] = ysacc[i]; t2[i] = yqacc[i]; }
+        const float a1 = lane_col_sum<COUT>(t1, lane), a2 = lane_col_sum<COUT>(t2, lane);
+        if (lane < COUT) { atomicAdd(s_ys + lane, a1); atomicAdd(s_yq + lane, a2); }
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");        // the 8 epilogue warps
-      for (int c = (int)threadIdx.x - 192; c < COUT; c += 256) {
+      for (int c = (int)threadIdx.x - 160; c < COUT; c += 256) {
         atomicAdd(p.ystats + 2 * c, (double)s_ys[c]);
         atomicAdd(p.ystats + 2 * c + 1, (double)s_yq[c]);
       }
     }
     // ---- the update accumulators: one partial per CTA and hi/lo half of x; set s drains accumulator s ----
     if (p.update) {
-      mbar_wait(done, 0, p.err, 28);
+      FWAIT(done, 0, 28);
       tc_fence_after();
-      const bool have = (int)blockIdx.x < p.ntiles;
+      const bool have = my_tiles > 0;
       if (eset < NACC) {
         const int rowi = quad * 32 + lane;
         const int jj = rowi / (2 * CIN), rr = rowi - jj * (2 * CIN);
@@ -468,23 +552,30 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
     }
   }
+  if (PROF && p.prof && lane == 0) {
+    long long* dst = p.prof + ((long long)blockIdx.x * 13 + warp) * 11;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) dst[i] = prof_acc[i];
+    dst[10] = clock64() - prof_t0;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
+#undef FWAIT
 
 // ---------------------------------------------------------------------------------------------------------------
 struct FPlan {
   int TH, TW, pitch, nTH, nTW, ntiles, XROWS, NBLK, XPOS, NST, grid, BW, padl;
   uint32_t off_r, off_stage, off_w, off_misc, w_bytes, stage_bytes, smem, tmem_cols;
-  size_t o_inv, o_rsum, o_err, o_wp, o_hpart, o_fix, total;
+  size_t o_inv, o_rsum, o_err, o_wp, o_hpart, o_fix, o_prof, total;
   int fix_cap;
 };
 
 bool fused_plan(const Geo& g, FPlan* P) {
   if (g.nd != 2 || g.transposed || g.kD != 1 || g.sH != 1 || g.sW != 1) return false;
   if (!((g.Cin == 16 || g.Cin == 32) && (g.Cout == 16 || g.Cout == 32))) return false;
-  if (g.kH > 3 || g.kW > 3 || g.iW % 4 != 0) return false;
+  if (!((g.kH == 1 && g.kW == 1) || (g.kH == 3 && g.kW == 3)) || g.iW % 4 != 0) return false;
   static const int want = [] { const char* e = getenv("HEBB_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
   if (!want) return false;
   FPlan& q = *P;
@@ -500,42 +591,56 @@ bool fused_plan(const Geo& g, FPlan* P) {
   q.padl = want_align ? (g.pW + 3) / 4 * 4 : g.pW;
   q.BW = (q.pitch + (q.padl - g.pW) + 3) / 4 * 4;
   if (q.BW > 256) return false;
-  q.NST = 4;
-  q.stage_bytes = (uint32_t)align_up((size_t)q.BW * 16 * 4, 128);
   q.w_bytes = (uint32_t)((g.Cin / 16) * g.taps * 4 * g.Cout * 16);
-  const uint32_t misc = (uint32_t)(12 * g.Cout * 4 + 8 * (16 + 2 * kMaxRows + 2 + 2 + 3 + 2) + 64);
-  const uint32_t r_bytes = 3u * kRSlotPos * RB;
+  const uint32_t stage = (uint32_t)align_up((size_t)q.BW * 16 * 4, 128);
+  q.stage_bytes = stage;
+  const uint32_t misc = (uint32_t)(12 * g.Cout * 4 + 64 * 4 + 8 * kNumBars + 64);
+  const uint32_t r_bytes = (uint32_t)kRSlots * kRSlotPos * RB;
+  const uint32_t fixed = (uint32_t)align_up(r_bytes, 1024) + (uint32_t)align_up(q.w_bytes, 128) + misc + 1024;
   bool found = false;
+  double best = 1e300, best_waste = 1e300;
   const long long tiles_w = (long long)g.B * q.nTW;
-  for (int th = 16; th >= 1 && !found; --th) {
+  const int copies = 128 / (2 * g.Cin);
+  const int reach = (copies - 1) > (g.kH - 1) ? (copies - 1) : (g.kH - 1);
+  // Tile height: the kernel is bound by tcgen05.mma issue, so the positions the 128-wide blocks compute beyond the real
+  // pixels (row pitch > TW, the block that overhangs the tile, the last tile row of the image) cost time one to one; the
+  // re-converted halo rows cost a little; and the fp32 staging ring must keep ~48 KB of TMA boxes in flight per SM to
+  // cover the DRAM latency (measured: with 4 x 8 KB in flight the bare pipeline took 0.1 ms per 2304 tiles).
+  for (int th = 16; th >= 1; --th) {
     if (th + g.kH - 1 > kMaxRows) continue;
     if (th > g.oH && th > 1) continue;
-    // enough tiles to balance the persistent CTAs (unless the layer is too small anyway)
+    // the update of a block is issued kDwLag blocks late: the rows the next tile's first block waits for (kH) must have
+    // been released by then, which needs TH - 1 >= kH (see the issuing warp)
+    if (th < g.kH + 1) continue;
     const long long tiles = tiles_w * cdiv(g.oH, th);
-    if (th > 1 && tiles < 4LL * sms && tiles_w * g.oH >= 4LL * sms) continue;
+    if (th > g.kH + 1 && tiles < 4LL * sms && tiles_w * g.oH >= 4LL * sms) continue;      // enough tiles to balance the CTAs
     const int nblk = (int)cdiv((long long)th * q.pitch, 128);
-    // the kh copies of an update instruction reach (copies-1) rows (accumulator 0) resp. kH-1 rows (accumulator 1) past a block
-    const int copies = 128 / (2 * g.Cin);
-    const int reach = (copies - 1) > (g.kH - 1) ? (copies - 1) : (g.kH - 1);
     const int xpos = nblk * 128 + reach * q.pitch + 8;
     const uint32_t x_bytes = (uint32_t)align_up((size_t)xpos * XB, 1024);
-    const uint32_t tot = x_bytes + (uint32_t)align_up(r_bytes, 1024) + q.NST * q.stage_bytes + (uint32_t)align_up(q.w_bytes, 128) + misc + 1024;
-    if (tot > (uint32_t)kSmemLimitF) continue;
-    q.TH = th; q.NBLK = nblk; q.XPOS = xpos; q.XROWS = th + g.kH - 1;
-    q.off_r = x_bytes;
-    q.off_stage = q.off_r + (uint32_t)align_up(r_bytes, 1024);
-    q.off_w = q.off_stage + q.NST * q.stage_bytes;
-    q.off_misc = q.off_w + (uint32_t)align_up(q.w_bytes, 128);
-    q.smem = tot;
-    found = true;
+    if (x_bytes + fixed + 3 * stage > (uint32_t)kSmemLimitF) continue;
+    int nst = (int)(((uint32_t)kSmemLimitF - x_bytes - fixed) / stage);
+    if (nst > kMaxStages) nst = kMaxStages;
+    const double waste = (double)nblk * 128.0 / ((double)th * q.TW) * ((double)cdiv(g.oH, th) * th / g.oH);
+    const double halo = (double)(th + g.kH - 1) / th;
+    double fl = (double)nst * stage / 49152.0; if (fl > 1.0) fl = 1.0;
+    const double cost = waste * (0.8 + 0.2 * halo) / (0.5 + 0.5 * fl);
+    if (cost < best) {
+      best = cost; best_waste = waste * (0.8 + 0.2 * halo); found = true;
+      q.TH = th; q.NBLK = nblk; q.XPOS = xpos; q.XROWS = th + g.kH - 1; q.NST = nst;
+      q.off_r = x_bytes;
+      q.off_stage = q.off_r + (uint32_t)align_up(r_bytes, 1024);
+      q.off_w = q.off_stage + nst * stage;
+      q.off_misc = q.off_w + (uint32_t)align_up(q.w_bytes, 128);
+      q.smem = x_bytes + fixed + nst * stage;
+    }
   }
-  if (!found) return false;
+  // a tile that wastes this much (tiny TH for the 128-byte-per-position images) is slower than the two-kernel path
+  if (!found || best_waste > 1.6) return false;
   q.nTH = (int)cdiv(g.oH, q.TH);
   q.ntiles = g.B * q.nTH * q.nTW;
   q.grid = q.ntiles < sms ? q.ntiles : sms;
-  const int copies = 128 / (2 * g.Cin);
   const int nacc = (g.kH + copies - 1) / copies;
-  const int cols = 2 * g.Cout + nacc * g.kW * 2 * g.Cout;
+  const int cols = 4 * g.Cout + nacc * g.kW * 2 * g.Cout;      // 2 forward accumulators of 2 Cout columns + the update's
   uint32_t tc = 32; while ((int)tc < cols) tc <<= 1;
   if (tc > 512) return false;
   q.tmem_cols = tc;
@@ -549,6 +654,7 @@ bool fused_plan(const Geo& g, FPlan* P) {
   const long long px = (long long)g.B * g.outS;
   q.fix_cap = (int)(px < (1LL << 18) ? px : (1LL << 18));
   q.o_fix = take(sizeof(int) * (size_t)q.fix_cap);
+  q.o_prof = take(sizeof(long long) * (size_t)sms * 13 * 11);
   q.total = off;
   return true;
 }
@@ -572,6 +678,9 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
+static long long* g_last_prof = nullptr;
+static int g_last_prof_n = 0;
+
 bool fused_supported(const Geo& g, int prec, unsigned flags) {
   if (prec != HEBB_PREC_BF16X3 && prec != HEBB_PREC_BF16) return false;
   if (flags & (HEBB_F_RULE_HPCA | HEBB_F_WGRAD_INTERNAL | HEBB_F_ONLY_PACK | HEBB_F_ONLY_FWD | HEBB_F_ONLY_DW)) return false;
@@ -587,7 +696,7 @@ size_t fused_workspace_bytes(const Geo& g) {
 int fused_describe_plan(const Geo& g, int* out, int n) {
   FPlan P;
   if (!fused_plan(g, &P)) return 0;
-  const int v[] = {P.TH, P.TW, P.pitch, P.ntiles, P.NBLK, P.XROWS, (int)P.smem, (int)P.tmem_cols, P.grid};
+  const int v[] = {P.TH, P.TW, P.pitch, P.ntiles, P.NBLK, P.XROWS, (int)P.smem, (int)P.tmem_cols, P.grid, P.NST};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < m; ++i) out[i] = v[i];
   return m;
@@ -632,21 +741,32 @@ int fused_conv_step(const Geo& g, const float* x, const float* W, const float* b
   f.TH = P.TH; f.TW = P.TW; f.pitch = P.pitch; f.nTH = P.nTH; f.nTW = P.nTW; f.ntiles = P.ntiles; f.XROWS = P.XROWS;
   f.NBLK = P.NBLK; f.XPOS = P.XPOS; f.NST = P.NST; f.BW = P.BW; f.padl = P.padl;
   f.kinv = kinv; f.update = upd ? 1 : 0;
+  static const int fdbg = [] { const char* e = getenv("HEBB_FUSED_DBG"); return e ? atoi(e) : 0; }();
+  f.dbg = fdbg;
+  static const int fprof = [] { const char* e = getenv("HEBB_FUSED_PROF"); return (e && e[0] == '1') ? 1 : 0; }();
+  f.prof = fprof ? reinterpret_cast<long long*>(base + P.o_prof) : nullptr;
+  g_last_prof = f.prof; g_last_prof_n = P.grid * 13 * 11;
   f.off_r = P.off_r; f.off_stage = P.off_stage; f.off_w = P.off_w; f.off_misc = P.off_misc; f.w_bytes = P.w_bytes;
   f.stage_bytes = P.stage_bytes; f.tmem_cols = P.tmem_cols;
   if (ystats) {
     HEBB_CUDA_TRY(cudaMemsetAsync(ystats, 0, sizeof(double) * 2 * (size_t)g.Cout, st));
     if (ystats_written) *ystats_written = 1;
   }
+#define HEBB_FUSED_LAUNCH2(CI, CO, K, PR)                                                                                 \
+  do {                                                                                                                    \
+    HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CI, CO, K, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
+    fused_small_kernel<CI, CO, K, PR><<<P.grid, kThreadsF, kSmemLimitF, st>>>(tm, f);                                     \
+  } while (0)
 #define HEBB_FUSED_LAUNCH(CI, CO)                                                                                         \
   do {                                                                                                                    \
-    HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
-    fused_small_kernel<CI, CO><<<P.grid, kThreadsF, kSmemLimitF, st>>>(tm, f);                                            \
+    if (g.kH == 3) { if (f.prof) HEBB_FUSED_LAUNCH2(CI, CO, 3, true); else HEBB_FUSED_LAUNCH2(CI, CO, 3, false); }        \
+    else { f.prof = nullptr; HEBB_FUSED_LAUNCH2(CI, CO, 1, false); }                                                      \
   } while (0)
   if (g.Cin == 16 && g.Cout == 16) HEBB_FUSED_LAUNCH(16, 16);
   else if (g.Cin == 16 && g.Cout == 32) HEBB_FUSED_LAUNCH(16, 32);
   else if (g.Cin == 32 && g.Cout == 16) HEBB_FUSED_LAUNCH(32, 16);
   else HEBB_FUSED_LAUNCH(32, 32);
+#undef HEBB_FUSED_LAUNCH2
 #undef HEBB_FUSED_LAUNCH
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   if (winner && tie_rel > 0.f)
@@ -657,3 +777,12 @@ int fused_conv_step(const Geo& g, const float* x, const float* W, const float* b
 }
 
 }  // namespace hebb
+
+// Profiling aid (HEBB_FUSED_PROF=1): copies the wait-cycle table of the last fused launch to the host: per CTA and warp
+// 9 wait accumulators (codes 20..28) + the warp's total cycles.  Synchronises the device.
+extern "C" int hebb_debug_fused_prof(long long* out, int n) {
+  if (!hebb::g_last_prof || !out) return 0;
+  const int m = n < hebb::g_last_prof_n ? n : hebb::g_last_prof_n;
+  if (cudaMemcpy(out, hebb::g_last_prof, sizeof(long long) * (size_t)m, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return m;
+}

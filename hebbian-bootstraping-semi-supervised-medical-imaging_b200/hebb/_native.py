@@ -26,7 +26,7 @@ EXPORTS = [
     'hebb_workspace_bytes', 'hebb_wnorm', 'hebb_conv_swta_step', 'hebb_convT_swta_step',
     'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
     'hebb_debug_umma_rate', 'hebb_debug_umma_rate_shared_a', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_upsample2x_bilinear',
-    'hebb_layer_path', 'hebb_debug_fused_plan', 'hebb_watchdog_code', 'hebb_conv_swta_step_stats', 'hebb_bn_act_from_stats', 'hebb_conv_wgrad', 'hebb_maxpool2x',
+    'hebb_layer_path', 'hebb_debug_fused_plan', 'hebb_watchdog_code', 'hebb_debug_fused_prof', 'hebb_conv_swta_step_stats', 'hebb_bn_act_from_stats', 'hebb_conv_wgrad', 'hebb_maxpool2x',
     'hebb_bias_relu_dropout', 'hebb_mask_scale',
 ]
 
@@ -397,7 +397,7 @@ def launch_count() -> int:
 
 
 PATH_SIMT, PATH_TC, PATH_FUSED = 0, 1, 2
-FUSED_PLAN_FIELDS = ['TH', 'TW', 'pitch', 'tiles', 'blocks_per_tile', 'x_rows', 'smem', 'tmem_cols', 'grid']
+FUSED_PLAN_FIELDS = ['TH', 'TW', 'pitch', 'tiles', 'blocks_per_tile', 'x_rows', 'smem', 'tmem_cols', 'grid', 'stages']
 
 
 def layer_path(desc: HebbDesc, prec: int, flags: int = 0) -> int:

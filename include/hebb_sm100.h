@@ -204,6 +204,11 @@ int hebb_layer_path(const HebbDesc* d, int prec, unsigned flags);
  * per tile, x rows per tile, shared memory, TMEM columns, grid}; returns the number of fields. */
 int hebb_debug_fused_plan(const HebbDesc* d, int* out, int n);
 
+/* Profiling aid: with HEBB_FUSED_PROF=1 in the environment the fused kernel accumulates, per CTA and warp, the cycles
+ * spent in each of its bounded waits (10 counters, codes 20..29) and the warp's total cycles; this copies the table of
+ * the last launch ([grid][13 warps][11]) to the host buffer `out` (n entries) and returns the count.  Synchronises. */
+int hebb_debug_fused_prof(long long* out, int n);
+
 /* Tile plan the tensor-core path would use (0 if it would not run there): fills out[0..n) with
  * {MB, fwd SEGLEN, XST, WST, NACC, fwd TMEM cols, fwd tiles, fwd smem, dW by_kh, CM, CN, BLK, ST, dW SEGLEN,
  *  tap groups, cin tiles, cout tiles, position splits, position blocks, dW TMEM cols, dW smem, dW HL, ws MiB,
