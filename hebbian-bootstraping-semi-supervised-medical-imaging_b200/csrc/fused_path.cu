@@ -43,8 +43,9 @@ constexpr int kMaxStages = 10;            // fp32 staging ring (TMA boxes in fli
 constexpr int kDwLag = 2;                 // the update MMAs of a block are issued this many blocks after its forward MMAs
 constexpr int kRSlots = kDwLag + 2;       // response ring: slots of kRSlotPos positions
 constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxRows + 2 + 2 + 2 * kRSlots + 2;
-constexpr int kThreadsF = 416;            // warps: 0 TMA producer, 1 forward issuer, 2 update issuer, 3-4 converter, 5-8 / 9-12 the two epilogue sets
-constexpr int kConvWarps = 2;             // (384 threads leave 168 registers per thread: a 32-channel row + its sums fit)
+// warps: 0 TMA producer, 1 forward issuer, 2 update issuer, 3 .. 2+NCW converter, then the two epilogue sets of four.
+// NCW = 2 converter warps for the plain layers (13 warps: the issuing warps then share their scheduler with epilogue
+// warps only -- with a converter warp on every scheduler the same kernel ran 25 % slower), 4 for the patch gather.
 
 struct FusedParams {
   float* y; int32_t* winner; const float* inv; const float* bias; float* rsum; double* ystats; float* hpart; int* err;
@@ -52,6 +53,9 @@ struct FusedParams {
   const uint4* wp;
   int B, oH, oW, kH, kW, pH, pW, taps;
   int TH, TW, pitch, nTH, nTW, ntiles, XROWS, NBLK, XPOS, NST;
+  unsigned pitch_magic;        // ceil(2^32 / pitch): q / pitch == umulhi(q, pitch_magic) for the q < 2^16 of a tile
+  int gather, gcin, gk, srows; // few-input-channel layers: the converter gathers the gk x gk patch of the gcin real channels into
+                               // gcin*gk*gk pseudo-channels of a 1x1 layer (srows = TH + gk - 1 staged input rows per tile)
   int BW, padl;                // TMA box width (floats) and left pad of the box start: staging column = tile column + padl - pW
   float kinv; int update;
   long long* prof;             // HEBB_FUSED_PROF=1: per CTA [32] cycles spent in each bounded wait (index = code - 16) + totals
@@ -106,8 +110,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     }                                                                                \
   } while (0)
 
-template <int CIN, int COUT, int KS, bool PROF>
-__global__ void __launch_bounds__(kThreadsF, 1)
+template <int CIN, int COUT, int KS, bool PROF, int NCW>
+__global__ void __launch_bounds__(32 * (3 + NCW + 8), 1)
 fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
   constexpr int XB = CIN * 4;              // bytes per position of the x image: [hi Cin | lo Cin] bf16
   constexpr int RB = COUT * 4;             // ... of the response image
@@ -172,8 +176,8 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   }
   fence_proxy_async();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, kConvWarps); }
-    for (int i = 0; i < kMaxRows; ++i) { mbar_init(xr_full + 8 * i, kConvWarps * NSL); mbar_init(xr_empty + 8 * i, 1); }
+    for (int i = 0; i < p.NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, NCW); }
+    for (int i = 0; i < kMaxRows; ++i) { mbar_init(xr_full + 8 * i, NCW * NSL); mbar_init(xr_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tf_full + 8 * i, 1); mbar_init(tf_empty + 8 * i, 4); }
     for (int i = 0; i < kRSlots; ++i) { mbar_init(r_full + 8 * i, 4); mbar_init(r_empty + 8 * i, 1); }
     mbar_init(w_full, 1); mbar_init(done, 1);
@@ -200,6 +204,15 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int b = tile / per_img, rem = tile - b * per_img;
         const int th = rem / p.nTW, tw = rem - th * p.nTW;
         const int h0 = th * p.TH - p.pH, w0 = tw * p.TW - p.padl;      // box start: a multiple of 4 floats (16 bytes)
+        if (p.gather) {
+          for (int r = 0; r < p.srows; ++r) {          // one box per input row: [gcin channels][1 row][BW]
+            FWAIT(st_empty + 8 * s, ph ^ 1, 21);
+            mbar_expect_tx(st_full + 8 * s, (uint32_t)p.BW * p.gcin * 4);
+            tma_load_3d(sbase + p.off_stage + s * p.stage_bytes, &tmap, w0, h0 + r, b * p.gcin, st_full + 8 * s);
+            if (++s == p.NST) { s = 0; ph ^= 1; }
+          }
+          continue;
+        }
         for (int r = 0; r < p.XROWS; ++r)
           for (int cg = 0; cg < NSL; ++cg) {
             FWAIT(st_empty + 8 * s, ph ^ 1, 21);
@@ -326,18 +339,91 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       if (elect_one()) umma_commit(done);
       __syncwarp();
     }
-  } else if (warp < 3 + kConvWarps) {
-    // ===================== converter (warps 3..4) =====================
+  } else if (warp < 3 + NCW) {
+    // ===================== converter (warps 3 .. 2+NCW) =====================
     const int t = threadIdx.x - 96;
+    const int conv_ntiles = p.ntiles;
     int s = 0; uint32_t ph = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    if constexpr (CIN == 32 && KS == 1 && NCW == 4) {
+      if (p.gather) {
+        // ---- patch gather (first layers: 1-4 real channels, gk x gk kernel): image row r of the 1x1 layer holds, per
+        // output pixel, the gcin*gk*gk patch values (zero-padded to 32 pseudo-channels) as [hi 32 | lo 32] ----
+        // staged input rows: `cons` = rows waited for so far (stage cs, phase cph), `rel` = rows released (stage rs);
+        // s0 = stage of the first input row under the current image row.  All indices advance incrementally: a
+        // run-time modulo per element made this loop 500 instructions long.
+        int cons = 0, cs = 0, rel = 0, rs = 0, s0 = 0;
+        uint32_t cph = 0;
+        const int off = p.padl - p.pW;
+        for (int tile = blockIdx.x; tile < conv_ntiles; tile += gridDim.x, ++it) {
+          const int base = it * p.srows;
+          for (int r = 0; r < p.XROWS; ++r) {
+            for (; cons <= base + r + 2; ++cons) {
+              FWAIT(st_full + 8 * cs, cph, 25);
+              if (++cs == p.NST) { cs = 0; cph ^= 1u; }
+            }
+            FWAIT(xr_empty + 8 * r, (it & 1) ^ 1, 26);
+            const int s1 = (s0 + 1 == p.NST) ? 0 : s0 + 1, s2 = (s1 + 1 == p.NST) ? 0 : s1 + 1;
+            const float* row0 = reinterpret_cast<const float*>(smem + p.off_stage + s0 * p.stage_bytes) + off;
+            const float* row1 = reinterpret_cast<const float*>(smem + p.off_stage + s1 * p.stage_bytes) + off;
+            const float* row2 = reinterpret_cast<const float*>(smem + p.off_stage + s2 * p.stage_bytes) + off;
+            for (int c = t; c < ((p.dbg & 8) ? 0 : p.pitch); c += 32 * NCW) {
+              float vv[32];                      // pseudo-channel ci*9 + kh*3 + kw; zero beyond the real channels
+#pragma unroll
+              for (int i = 27; i < 32; ++i) vv[i] = 0.f;
+#pragma unroll
+              for (int ci = 0; ci < 3; ++ci) {
+                if (ci < p.gcin) {
+                  const float* q0 = row0 + ci * p.BW + c;
+                  const float* q1 = row1 + ci * p.BW + c;
+                  const float* q2 = row2 + ci * p.BW + c;
+#pragma unroll
+                  for (int kw = 0; kw < 3; ++kw) { vv[ci * 9 + kw] = q0[kw]; vv[ci * 9 + 3 + kw] = q1[kw]; vv[ci * 9 + 6 + kw] = q2[kw]; }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 9; ++i) vv[ci * 9 + i] = 0.f;
+                }
+              }
+              uint32_t hp[16], lp[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp[i]) : "f"(vv[2 * i + 1]), "f"(vv[2 * i]));
+                const float h0 = __uint_as_float(hp[i] << 16), h1 = __uint_as_float(hp[i] & 0xffff0000u);
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp[i]) : "f"(vv[2 * i + 1] - h1), "f"(vv[2 * i] - h0));
+              }
+              const uint32_t row = xb + (uint32_t)(r * p.pitch + c) * XB;
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                st_shared_v4(swz<XCH>(row, ch), hp[4 * ch], hp[4 * ch + 1], hp[4 * ch + 2], hp[4 * ch + 3]);
+                st_shared_v4(swz<XCH>(row, 4 + ch), lp[4 * ch], lp[4 * ch + 1], lp[4 * ch + 2], lp[4 * ch + 3]);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              for (int a = 0; a < NSL; ++a) mbar_arrive(xr_full + 8 * r);
+              mbar_arrive(st_empty + 8 * rs);               // input row base + r is no longer needed
+            }
+            ++rel;
+            if (++rs == p.NST) rs = 0;
+            s0 = s1;
+          }
+          for (; rel < base + p.srows; ++rel) {             // the trailing gk-1 input rows of the tile
+            if (lane == 0) mbar_arrive(st_empty + 8 * rs);
+            if (++rs == p.NST) rs = 0;
+            s0 = (s0 + 1 == p.NST) ? 0 : s0 + 1;
+          }
+        }
+        goto converter_done;
+      }
+    }
+    for (int tile = blockIdx.x; tile < conv_ntiles; tile += gridDim.x, ++it) {
       for (int r = 0; r < p.XROWS; ++r)
         for (int cg = 0; cg < NSL; ++cg) {
           FWAIT(st_full + 8 * s, ph, 25);
           if (cg == 0) FWAIT(xr_empty + 8 * r, (it & 1) ^ 1, 26);      // the previous tile no longer reads this row
           const float* st = reinterpret_cast<const float*>(smem + p.off_stage + s * p.stage_bytes) + (p.padl - p.pW);
-          for (int c = t; c < ((p.dbg & 8) ? 0 : p.pitch); c += 32 * kConvWarps) {
+          for (int c = t; c < ((p.dbg & 8) ? 0 : p.pitch); c += 32 * NCW) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = st[i * p.BW + c];
@@ -360,10 +446,11 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           if (++s == p.NST) { s = 0; ph ^= 1; }
         }
     }
+  converter_done:;
   } else {
-    // ===================== epilogue warps 5..12: two sets of four alternate blocks =====================
+    // ===================== epilogue warps 3+NCW .. 10+NCW: two sets of four alternate blocks =====================
     const int quad = warp & 3;
-    const int ew = warp - 5;
+    const int ew = warp - (3 + NCW);
     const int eset = ew >> 2;
     float* my_rs = s_rs + ew * COUT;
     const long long outS = (long long)p.oH * p.oW;
@@ -389,6 +476,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t acc = kk & 1u;
         FWAIT(tf_full + 8 * acc, (kk >> 1) & 1u, 27);
         tc_fence_after();
+        long long tq0 = PROF ? clock64() : 0;
         uint32_t v[COUT], v2[COUT];
         const uint32_t ta = tmem_f + (static_cast<uint32_t>(quad * 32) << 16) + acc * FCOLS;
         TmemLd<COUT>::ld(ta, v);
@@ -397,25 +485,37 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tf_empty + 8 * acc);        // the accumulator is in registers: hand the buffer back
+        if (PROF) { const long long tq = clock64(); prof_acc[0] += tq - tq0; tq0 = tq; }      // [0] TMEM load
         if (p.dbg & 4) {
           if (p.update) { fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(r_full + 8 * (kk % kRSlots)); }
           continue;
         }
         const int loc = quad * 32 + lane;
         const int q = k * 128 + loc;
-        const int r_ = q / p.pitch, c_ = q - r_ * p.pitch;
+        const int r_ = (int)__umulhi((unsigned)q, p.pitch_magic), c_ = q - r_ * p.pitch;      // q / pitch (q < 2^16)
         const bool valid = r_ < THv && c_ < TWv;
         float f[COUT];
 #pragma unroll
-        for (int i = 0; i < COUT; ++i) f[i] = fmaf(__uint_as_float(v[i]) + __uint_as_float(v2[i]), s_inv[i], s_bias[i]);
+        for (int i4 = 0; i4 < COUT; i4 += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_inv + i4);
+          const float4 bs = *reinterpret_cast<const float4*>(s_bias + i4);
+          f[i4 + 0] = fmaf(__uint_as_float(v[i4 + 0]) + __uint_as_float(v2[i4 + 0]), sc.x, bs.x);
+          f[i4 + 1] = fmaf(__uint_as_float(v[i4 + 1]) + __uint_as_float(v2[i4 + 1]), sc.y, bs.y);
+          f[i4 + 2] = fmaf(__uint_as_float(v[i4 + 2]) + __uint_as_float(v2[i4 + 2]), sc.z, bs.z);
+          f[i4 + 3] = fmaf(__uint_as_float(v[i4 + 3]) + __uint_as_float(v2[i4 + 3]), sc.w, bs.w);
+        }
         const long long pix = (long long)(h0 + r_) * p.oW + (w0 + c_);
-        float* yb = p.y + (long long)b * COUT * outS + pix;
+        if (valid && !(p.dbg & 16)) {          // ONE branch around all the stores (a condition per store costs a
+          float* yp = p.y + (long long)b * COUT * outS + pix;      // reconvergence region each: measured 11 % of the kernel)
+#pragma unroll
+          for (int i = 0; i < COUT; ++i) { *yp = f[i]; yp += outS; }
+        }
         float best = -INFINITY;
         int bi = 0;
+        if (p.winner) {
 #pragma unroll
-        for (int i = 0; i < COUT; ++i) {
-          if (valid && !(p.dbg & 16)) yb[(long long)i * outS] = f[i];
-          if (f[i] > best) { best = f[i]; bi = i; }            // strict: the lowest index wins ties
+          for (int i = 0; i < COUT; ++i)
+            if (f[i] > best) { best = f[i]; bi = i; }            // strict: the lowest index wins ties
         }
         if (want_ys) {
           if constexpr (YACC) {
@@ -436,6 +536,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           for (int i = 0; i < COUT; ++i) { second = fmaxf(second, i == bi ? -INFINITY : f[i]); amax = fmaxf(amax, fabsf(f[i])); }
           if (best - second <= p.tie_rel * amax) flag_tie_f(p.fix_list, p.fix_count, p.fix_cap, (long long)b * outS + pix);
         }
+        if (PROF) { const long long tq = clock64(); prof_acc[1] += tq - tq0; tq0 = tq; }      // [1] y, winner, sums
         if (!p.update) continue;
         // ---- responses: r = softmax_c(k y), bf16 hi/lo, into this block's slot of the response ring ----
         float mx2 = -INFINITY;
@@ -481,9 +582,11 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             st_shared_v4(swz<RCH>(lrow, RCH / 2 + g8), ol4[0], ol4[1], ol4[2], ol4[3]);
           }
         }
+        if (PROF) { const long long tq = clock64(); prof_acc[2] += tq - tq0; tq0 = tq; }      // [2] softmax, split, response stores
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(r_full + 8 * slot);
+        if (PROF) { const long long tq = clock64(); prof_acc[3] += tq - tq0; tq0 = tq; }      // [3] proxy fence + arrive
       }
     }
     // ---- fold the per-thread running sums ----
@@ -510,7 +613,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         if (lane < COUT) { atomicAdd(s_ys + lane, a1); atomicAdd(s_yq + lane, a2); }
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");        // the 8 epilogue warps
-      for (int c = (int)threadIdx.x - 160; c < COUT; c += 256) {
+      for (int c = (int)threadIdx.x - 32 * (3 + NCW); c < COUT; c += 256) {
         atomicAdd(p.ystats + 2 * c, (double)s_ys[c]);
         atomicAdd(p.ystats + 2 * c + 1, (double)s_yq[c]);
       }
@@ -553,7 +656,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
   }
   if (PROF && p.prof && lane == 0) {
-    long long* dst = p.prof + ((long long)blockIdx.x * 13 + warp) * 11;
+    long long* dst = p.prof + ((long long)blockIdx.x * 15 + warp) * 11;      // (15 = the widest layout)
 #pragma unroll
     for (int i = 0; i < 10; ++i) dst[i] = prof_acc[i];
     dst[10] = clock64() - prof_t0;
@@ -564,9 +667,58 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 }
 #undef FWAIT
 
+// One launch that prepares a layer call: 1/|W_c| per filter (hebb.py:10-13), the packed bf16 hi/lo weight image of the
+// forward B operand ([slab][tap][k-chunk][hi|lo][Cout] x 16 bytes, as pack_w_kernel writes it), and the zeroing of the
+// per-call accumulators (sum_p r, error word, near-tie counter, BatchNorm sums).  One block per filter.
+__global__ void __launch_bounds__(128)
+fused_prep_kernel(const float* __restrict__ W, uint4* __restrict__ wp, float* __restrict__ inv, uint32_t* __restrict__ zero32,
+                  int nzero32, double* __restrict__ ystats, int Cin, int NSLAB, int Cout, int taps, int wnrm) {
+  const int c = blockIdx.x, K = Cin * taps;
+  const float* w = W + (long long)c * K;
+  if (wnrm) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) { const float v = __ldg(w + i); acc = fmaf(v, v, acc); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ float part[4];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float nrm = sqrtf(part[0] + part[1] + part[2] + part[3]);
+      inv[c] = nrm == 0.f ? 1.f : 1.f / nrm;                 // hebb.py:12: zero norms divide by 1
+    }
+  }
+  const int items = NSLAB * taps * 4;                         // (slab, tap, k-chunk, hi|lo); channels >= Cin are zero
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int hl = it & 1, c2 = (it >> 1) & 1, st = it >> 2;
+    const int tap = st % taps, slab = st / taps;
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat16 e[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int ci = (slab * 2 + c2) * 8 + 2 * i + j;
+        const float v = ci < Cin ? __ldg(w + ci * taps + tap) : 0.f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        e[j] = hl ? lo : hi;
+      }
+      o[i] = pack_bf16x2(e[0], e[1]);
+    }
+    wp[((((long long)slab * taps + tap) * 2 + c2) * 2 + hl) * Cout + c] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (c == 0) {
+    for (int i = threadIdx.x; i < nzero32; i += blockDim.x) zero32[i] = 0u;
+    if (ystats)
+      for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x) ystats[i] = 0.0;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 struct FPlan {
   int TH, TW, pitch, nTH, nTW, ntiles, XROWS, NBLK, XPOS, NST, grid, BW, padl;
+  int gather, eCin, ek, etaps, srows;    // gather: few-channel 3x3 layer run as a 1x1 layer on eCin = 32 pseudo-channels
   uint32_t off_r, off_stage, off_w, off_misc, w_bytes, stage_bytes, smem, tmem_cols;
   size_t o_inv, o_rsum, o_err, o_wp, o_hpart, o_fix, o_prof, total;
   int fix_cap;
@@ -574,25 +726,32 @@ struct FPlan {
 
 bool fused_plan(const Geo& g, FPlan* P) {
   if (g.nd != 2 || g.transposed || g.kD != 1 || g.sH != 1 || g.sW != 1) return false;
-  if (!((g.Cin == 16 || g.Cin == 32) && (g.Cout == 16 || g.Cout == 32))) return false;
-  if (!((g.kH == 1 && g.kW == 1) || (g.kH == 3 && g.kW == 3)) || g.iW % 4 != 0) return false;
+  if (!(g.Cout == 16 || g.Cout == 32) || g.iW % 4 != 0) return false;
+  // Few input channels (the first layer: 3 -> 16): the converter gathers the 3x3 patch of the real channels into
+  // Cin*9 <= 32 pseudo-channels, and the layer runs as a 1x1 layer with 32 input channels over the output grid
+  // ([Cout][Cin][3][3] already is that layer's weight) -- 4 forward instructions per block instead of 18
+  const bool gather = g.Cin <= 3 && g.kH == 3 && g.kW == 3;
+  if (!gather && !((g.Cin == 16 || g.Cin == 32) && ((g.kH == 1 && g.kW == 1) || (g.kH == 3 && g.kW == 3)))) return false;
   static const int want = [] { const char* e = getenv("HEBB_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
   if (!want) return false;
   FPlan& q = *P;
   const int sms = num_sms();
-  const int XB = g.Cin * 4, RB = g.Cout * 4;
+  const int eCin = gather ? 32 : g.Cin, ekH = gather ? 1 : g.kH, ekW = gather ? 1 : g.kW;      // what the MMA side sees
+  q.gather = gather ? 1 : 0; q.eCin = eCin; q.ek = ekH; q.etaps = ekH * ekW;
+  const int XB = eCin * 4, RB = g.Cout * 4;
   q.nTW = (int)cdiv(g.oW, 128);
   q.TW = (int)(cdiv(cdiv(g.oW, q.nTW), 4) * 4);          // tile columns start on multiples of 4 floats
   q.nTW = (int)cdiv(g.oW, q.TW);
-  q.pitch = (int)((q.TW + g.kW - 1 + 3) / 4 * 4);
+  q.pitch = (int)((q.TW + ekW - 1 + 3) / 4 * 4);
   // The TMA box starts padl = round_up(pW, 4) columns left of the tile, so that its first byte is 16-byte aligned in
-  // global memory (HEBB_FUSED_ALIGN=0: start exactly pW columns left; profiling / debugging aid)
+  // global memory: a box whose first element is not 16-byte aligned raises an illegal-instruction fault on sm_100
+  // (HEBB_FUSED_ALIGN=0 reproduces it)
   static const int want_align = [] { const char* e = getenv("HEBB_FUSED_ALIGN"); return (e && e[0] == '0') ? 0 : 1; }();
   q.padl = want_align ? (g.pW + 3) / 4 * 4 : g.pW;
-  q.BW = (q.pitch + (q.padl - g.pW) + 3) / 4 * 4;
+  q.BW = (q.pitch + (gather ? g.kW - 1 : 0) + (q.padl - g.pW) + 3) / 4 * 4;
   if (q.BW > 256) return false;
-  q.w_bytes = (uint32_t)((g.Cin / 16) * g.taps * 4 * g.Cout * 16);
-  const uint32_t stage = (uint32_t)align_up((size_t)q.BW * 16 * 4, 128);
+  q.w_bytes = (uint32_t)((eCin / 16) * q.etaps * 4 * g.Cout * 16);
+  const uint32_t stage = (uint32_t)align_up((size_t)q.BW * (gather ? g.Cin : 16) * 4, 128);
   q.stage_bytes = stage;
   const uint32_t misc = (uint32_t)(12 * g.Cout * 4 + 64 * 4 + 8 * kNumBars + 64);
   const uint32_t r_bytes = (uint32_t)kRSlots * kRSlotPos * RB;
@@ -600,33 +759,34 @@ bool fused_plan(const Geo& g, FPlan* P) {
   bool found = false;
   double best = 1e300, best_waste = 1e300;
   const long long tiles_w = (long long)g.B * q.nTW;
-  const int copies = 128 / (2 * g.Cin);
-  const int reach = (copies - 1) > (g.kH - 1) ? (copies - 1) : (g.kH - 1);
-  // Tile height: the kernel is bound by tcgen05.mma issue, so the positions the 128-wide blocks compute beyond the real
-  // pixels (row pitch > TW, the block that overhangs the tile, the last tile row of the image) cost time one to one; the
-  // re-converted halo rows cost a little; and the fp32 staging ring must keep ~48 KB of TMA boxes in flight per SM to
-  // cover the DRAM latency (measured: with 4 x 8 KB in flight the bare pipeline took 0.1 ms per 2304 tiles).
+  const int copies = 128 / (2 * eCin);
+  const int reach = (copies - 1) > (ekH - 1) ? (copies - 1) : (ekH - 1);
+  // Tile height: the kernel is bound by the tensor pipe's operand fetches, so the positions the 128-wide blocks compute
+  // beyond the real pixels (row pitch > TW, the block that overhangs the tile, the last tile row of the image) cost time
+  // one to one; the re-converted halo rows cost a little; and the fp32 staging ring must keep ~48 KB of TMA boxes in
+  // flight per SM to cover the DRAM latency (measured: with 4 x 8 KB in flight the bare pipeline took 0.1 ms per 2304 tiles).
   for (int th = 16; th >= 1; --th) {
-    if (th + g.kH - 1 > kMaxRows) continue;
+    if (th + ekH - 1 > kMaxRows) continue;
     if (th > g.oH && th > 1) continue;
-    // the update of a block is issued kDwLag blocks late: the rows the next tile's first block waits for (kH) must have
-    // been released by then, which needs TH - 1 >= kH (see the issuing warp)
-    if (th < g.kH + 1) continue;
+    // the update of a block is issued after its responses went through the epilogue: the rows the next tile's first block
+    // waits for (kH) must have been released by the updates that can have been issued by then, which needs TH - 1 >= kH
+    if (th < ekH + 1) continue;
     const long long tiles = tiles_w * cdiv(g.oH, th);
-    if (th > g.kH + 1 && tiles < 4LL * sms && tiles_w * g.oH >= 4LL * sms) continue;      // enough tiles to balance the CTAs
+    if (th > ekH + 1 && tiles < 4LL * sms && tiles_w * g.oH >= 4LL * sms) continue;      // enough tiles to balance the CTAs
     const int nblk = (int)cdiv((long long)th * q.pitch, 128);
     const int xpos = nblk * 128 + reach * q.pitch + 8;
     const uint32_t x_bytes = (uint32_t)align_up((size_t)xpos * XB, 1024);
-    if (x_bytes + fixed + 3 * stage > (uint32_t)kSmemLimitF) continue;
+    const int min_st = gather ? 4 : 3;                  // the gather keeps 3 staged rows open at a time
+    if (x_bytes + fixed + min_st * stage > (uint32_t)kSmemLimitF) continue;
     int nst = (int)(((uint32_t)kSmemLimitF - x_bytes - fixed) / stage);
     if (nst > kMaxStages) nst = kMaxStages;
     const double waste = (double)nblk * 128.0 / ((double)th * q.TW) * ((double)cdiv(g.oH, th) * th / g.oH);
     const double halo = (double)(th + g.kH - 1) / th;
-    double fl = (double)nst * stage / 49152.0; if (fl > 1.0) fl = 1.0;
+    double fl = gather ? 1.0 : (double)nst * stage / 49152.0; if (fl > 1.0) fl = 1.0;
     const double cost = waste * (0.8 + 0.2 * halo) / (0.5 + 0.5 * fl);
     if (cost < best) {
       best = cost; best_waste = waste * (0.8 + 0.2 * halo); found = true;
-      q.TH = th; q.NBLK = nblk; q.XPOS = xpos; q.XROWS = th + g.kH - 1; q.NST = nst;
+      q.TH = th; q.NBLK = nblk; q.XPOS = xpos; q.XROWS = th + ekH - 1; q.NST = nst; q.srows = th + g.kH - 1;
       q.off_r = x_bytes;
       q.off_stage = q.off_r + (uint32_t)align_up(r_bytes, 1024);
       q.off_w = q.off_stage + nst * stage;
@@ -639,8 +799,8 @@ bool fused_plan(const Geo& g, FPlan* P) {
   q.nTH = (int)cdiv(g.oH, q.TH);
   q.ntiles = g.B * q.nTH * q.nTW;
   q.grid = q.ntiles < sms ? q.ntiles : sms;
-  const int nacc = (g.kH + copies - 1) / copies;
-  const int cols = 4 * g.Cout + nacc * g.kW * 2 * g.Cout;      // 2 forward accumulators of 2 Cout columns + the update's
+  const int nacc = (ekH + copies - 1) / copies;
+  const int cols = 4 * g.Cout + nacc * ekW * 2 * g.Cout;      // 2 forward accumulators of 2 Cout columns + the update's
   uint32_t tc = 32; while ((int)tc < cols) tc <<= 1;
   if (tc > 512) return false;
   q.tmem_cols = tc;
@@ -650,11 +810,11 @@ bool fused_plan(const Geo& g, FPlan* P) {
   q.o_rsum = take(sizeof(float) * g.Cout);
   q.o_err = take(256);
   q.o_wp = take(q.w_bytes);
-  q.o_hpart = take((size_t)q.grid * 2 * g.taps * g.Cin * g.Cout * sizeof(float));
+  q.o_hpart = take((size_t)q.grid * 2 * q.etaps * eCin * g.Cout * sizeof(float));
   const long long px = (long long)g.B * g.outS;
   q.fix_cap = (int)(px < (1LL << 18) ? px : (1LL << 18));
   q.o_fix = take(sizeof(int) * (size_t)q.fix_cap);
-  q.o_prof = take(sizeof(long long) * (size_t)sms * 13 * 11);
+  q.o_prof = take(sizeof(long long) * (size_t)sms * 15 * 11);
   q.total = off;
   return true;
 }
@@ -717,14 +877,16 @@ int fused_conv_step(const Geo& g, const float* x, const float* W, const float* b
   float* rsum = reinterpret_cast<float*>(base + P.o_rsum);
   int* err = reinterpret_cast<int*>(base + P.o_err);
   const bool upd = (flags & HEBB_F_UPDATE) != 0;
-  HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, P.o_wp - P.o_rsum, st));      // rsum, error word, near-tie counter
-  if (flags & HEBB_F_WNRM) HEBB_TRY(launch_wnorm(W, nullptr, inv, g.Cout, g.K, 1, 0, g.K, st));
-  HEBB_TRY(tc_launch_pack_w(W, base + P.o_wp, g.Cin, g.Cout, g.taps, g.Cin / 16, g.Cout, st));
+  // one launch: filter norms, packed weights, zeroed per-call accumulators (sum_p r, error word, near-tie counter, BatchNorm sums)
+  const int pCin = P.gather ? g.Cin * g.taps : g.Cin;          // the gathered layer's weight is [Cout][Cin*9] of a 1x1 layer
+  fused_prep_kernel<<<g.Cout, 128, 0, st>>>(W, reinterpret_cast<uint4*>(base + P.o_wp), inv, reinterpret_cast<uint32_t*>(base + P.o_rsum),
+                                            (int)((P.o_wp - P.o_rsum) / 4), ystats, pCin, P.eCin / 16, g.Cout, P.etaps, (flags & HEBB_F_WNRM) ? 1 : 0);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
 
   CUtensorMap tm;
-  const cuuint64_t dims[3] = {(cuuint64_t)g.iW, (cuuint64_t)g.iH, (cuuint64_t)g.B * g.Cin};
+  const cuuint64_t dims[3] = {(cuuint64_t)g.iW, (cuuint64_t)g.iH, (cuuint64_t)g.B * g.Cin};      // (the REAL channels)
   const cuuint64_t strides[2] = {(cuuint64_t)g.iW * 4, (cuuint64_t)g.iW * g.iH * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)P.BW, 1u, 16u};
+  const cuuint32_t box[3] = {(cuuint32_t)P.BW, 1u, (cuuint32_t)(P.gather ? g.Cin : 16)};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -737,34 +899,38 @@ int fused_conv_step(const Geo& g, const float* x, const float* W, const float* b
   static const float tie_rel = [] { const char* e = getenv("HEBB_TIE_REL"); return e ? (float)atof(e) : 2.5e-4f; }();
   f.fix_list = reinterpret_cast<int*>(base + P.o_fix); f.fix_count = err + 4; f.fix_cap = P.fix_cap; f.tie_rel = tie_rel;
   f.wp = reinterpret_cast<const uint4*>(base + P.o_wp);
-  f.B = g.B; f.oH = g.oH; f.oW = g.oW; f.kH = g.kH; f.kW = g.kW; f.pH = g.pH; f.pW = g.pW; f.taps = g.taps;
+  f.B = g.B; f.oH = g.oH; f.oW = g.oW; f.kH = P.ek; f.kW = P.ek; f.pH = g.pH; f.pW = g.pW; f.taps = P.etaps;
+  f.gather = P.gather; f.gcin = g.Cin; f.gk = g.kH; f.srows = P.srows;
   f.TH = P.TH; f.TW = P.TW; f.pitch = P.pitch; f.nTH = P.nTH; f.nTW = P.nTW; f.ntiles = P.ntiles; f.XROWS = P.XROWS;
   f.NBLK = P.NBLK; f.XPOS = P.XPOS; f.NST = P.NST; f.BW = P.BW; f.padl = P.padl;
+  f.pitch_magic = (unsigned)((0x100000000ULL + (unsigned)P.pitch - 1) / (unsigned)P.pitch);
+
   f.kinv = kinv; f.update = upd ? 1 : 0;
   static const int fdbg = [] { const char* e = getenv("HEBB_FUSED_DBG"); return e ? atoi(e) : 0; }();
   f.dbg = fdbg;
   static const int fprof = [] { const char* e = getenv("HEBB_FUSED_PROF"); return (e && e[0] == '1') ? 1 : 0; }();
   f.prof = fprof ? reinterpret_cast<long long*>(base + P.o_prof) : nullptr;
-  g_last_prof = f.prof; g_last_prof_n = P.grid * 13 * 11;
+  g_last_prof = f.prof; g_last_prof_n = P.grid * 15 * 11;
   f.off_r = P.off_r; f.off_stage = P.off_stage; f.off_w = P.off_w; f.off_misc = P.off_misc; f.w_bytes = P.w_bytes;
   f.stage_bytes = P.stage_bytes; f.tmem_cols = P.tmem_cols;
-  if (ystats) {
-    HEBB_CUDA_TRY(cudaMemsetAsync(ystats, 0, sizeof(double) * 2 * (size_t)g.Cout, st));
-    if (ystats_written) *ystats_written = 1;
-  }
-#define HEBB_FUSED_LAUNCH2(CI, CO, K, PR)                                                                                 \
+  if (ystats && ystats_written) *ystats_written = 1;           // (zeroed by the prep kernel)
+#define HEBB_FUSED_LAUNCH2(CI, CO, K, PR, NC)                                                                             \
   do {                                                                                                                    \
-    HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CI, CO, K, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
-    fused_small_kernel<CI, CO, K, PR><<<P.grid, kThreadsF, kSmemLimitF, st>>>(tm, f);                                     \
+    HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CI, CO, K, PR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
+    fused_small_kernel<CI, CO, K, PR, NC><<<P.grid, 32 * (3 + NC + 8), kSmemLimitF, st>>>(tm, f);                         \
   } while (0)
 #define HEBB_FUSED_LAUNCH(CI, CO)                                                                                         \
   do {                                                                                                                    \
-    if (g.kH == 3) { if (f.prof) HEBB_FUSED_LAUNCH2(CI, CO, 3, true); else HEBB_FUSED_LAUNCH2(CI, CO, 3, false); }        \
-    else { f.prof = nullptr; HEBB_FUSED_LAUNCH2(CI, CO, 1, false); }                                                      \
+    if (P.ek == 3) { if (f.prof) HEBB_FUSED_LAUNCH2(CI, CO, 3, true, 2); else HEBB_FUSED_LAUNCH2(CI, CO, 3, false, 2); }  \
+    else { f.prof = nullptr; HEBB_FUSED_LAUNCH2(CI, CO, 1, false, 2); }                                                   \
   } while (0)
-  if (g.Cin == 16 && g.Cout == 16) HEBB_FUSED_LAUNCH(16, 16);
-  else if (g.Cin == 16 && g.Cout == 32) HEBB_FUSED_LAUNCH(16, 32);
-  else if (g.Cin == 32 && g.Cout == 16) HEBB_FUSED_LAUNCH(32, 16);
+  if (P.gather) {
+    if (g.Cout == 16) { if (f.prof) HEBB_FUSED_LAUNCH2(32, 16, 1, true, 4); else HEBB_FUSED_LAUNCH2(32, 16, 1, false, 4); }
+    else { f.prof = nullptr; HEBB_FUSED_LAUNCH2(32, 32, 1, false, 4); }
+  }
+  else if (P.eCin == 16 && g.Cout == 16) HEBB_FUSED_LAUNCH(16, 16);
+  else if (P.eCin == 16 && g.Cout == 32) HEBB_FUSED_LAUNCH(16, 32);
+  else if (P.eCin == 32 && g.Cout == 16) HEBB_FUSED_LAUNCH(32, 16);
   else HEBB_FUSED_LAUNCH(32, 32);
 #undef HEBB_FUSED_LAUNCH2
 #undef HEBB_FUSED_LAUNCH
@@ -772,7 +938,7 @@ int fused_conv_step(const Geo& g, const float* x, const float* W, const float* b
   if (winner && tie_rel > 0.f)
     HEBB_TRY(launch_winner_fixup(g, x, W, (flags & HEBB_F_WNRM) ? inv : nullptr, bias, winner, f.fix_list, f.fix_count, P.fix_cap, st));
   if (upd)
-    HEBB_TRY(tc_launch_finalize(f.hpart, rsum, W, delta_w, P.grid * 2, g.taps, g.Cin, g.Cin, g.Cout, st));
+    HEBB_TRY(tc_launch_finalize(f.hpart, rsum, W, delta_w, P.grid * 2, P.etaps, pCin, P.eCin, g.Cout, st));
   return HEBB_OK;
 }
 

@@ -206,7 +206,7 @@ int hebb_debug_fused_plan(const HebbDesc* d, int* out, int n);
 
 /* Profiling aid: with HEBB_FUSED_PROF=1 in the environment the fused kernel accumulates, per CTA and warp, the cycles
  * spent in each of its bounded waits (10 counters, codes 20..29) and the warp's total cycles; this copies the table of
- * the last launch ([grid][13 warps][11]) to the host buffer `out` (n entries) and returns the count.  Synchronises. */
+ * the last launch ([grid][15 warps][11]) to the host buffer `out` (n entries) and returns the count.  Synchronises. */
 int hebb_debug_fused_prof(long long* out, int n);
 
 /* Tile plan the tensor-core path would use (0 if it would not run there): fills out[0..n) with

@@ -27,14 +27,20 @@ if os.environ.get('HEBB_FUSED_PROF') == '1':
     import ctypes
     import numpy as np
     grid = _native.fused_plan(desc)['grid']
-    buf = (ctypes.c_longlong * (grid * 143))()
+    buf = (ctypes.c_longlong * (grid * 165))()
     lib = _native.load()
     lib.hebb_debug_fused_prof.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
-    n = lib.hebb_debug_fused_prof(buf, grid * 143)
-    t = np.array(buf[:n], dtype=np.float64).reshape(grid, 13, 11)
+    n = lib.hebb_debug_fused_prof(buf, grid * 165)
+    t = np.array(buf[:n], dtype=np.float64).reshape(grid, 15, 11)
     names = {0: 'w_full', 1: 'st_empty', 2: 'xr_full', 3: 'tf_empty', 4: 'r_full', 5: 'st_full', 6: 'xr_empty', 7: 'tf_full', 8: 'done', 9: 'r_empty'}
-    roles = {0: 'producer', 1: 'mma.fwd', 2: 'mma.dw', 3: 'conv0', 4: 'conv1', 5: 'epi0.a', 9: 'epi1.a'}
+    roles = {0: 'producer', 1: 'mma.fwd', 2: 'mma.dw', 3: 'conv0', 6: 'conv3', 7: 'epi0.a', 11: 'epi1.a'}
     m = t.mean(axis=0)
+    if Cin <= 3:
+        roles = {0: 'producer', 1: 'mma.fwd', 2: 'mma.dw', 3: 'conv0', 6: 'conv3', 7: 'epi0.a', 11: 'epi1.a'}
+    else:
+        roles = {0: 'producer', 1: 'mma.fwd', 2: 'mma.dw', 3: 'conv0', 4: 'conv1', 5: 'epi0.a', 9: 'epi1.a'}
+    ep = 7 if Cin <= 3 else 5
+    print('   epilogue sections (kcyc): tmem-load %.1f  y/winner/sums %.1f  softmax/split/stores %.1f  fence+arrive %.1f' % tuple(m[ep, i] / 1e3 for i in range(4)))
     for w, rn in roles.items():
         tot = m[w, 10]
         print(f'   {rn:9s} total {tot / 1e3:8.1f} kcyc | ' + '  '.join(f'{names[i]} {m[w, i] / 1e3:.1f}' for i in range(10) if m[w, i] > 0.005 * tot))

@@ -7,7 +7,7 @@ import hebb
 from hebb import _native
 from oracle import hebb_oracle as O
 
-cases = [(2, 16, 16, 3, 0, (20, 24), 5.0, False), (2, 16, 16, 3, 0, (20, 24), 5.0, True), (2, 16, 16, 3, 1, (20, 24), 5.0, True), (2, 16, 16, 3, 1, (20, 24), 5.0, False), (2, 32, 32, 3, 1, (20, 24), 5.0, True),
+cases = [(4, 3, 16, 3, 1, (40, 36), 50.0, True), (2, 1, 32, 3, 1, (21, 44), 20.0, True), (2, 3, 16, 3, 1, (64, 256), 50.0, True), (2, 16, 16, 3, 0, (20, 24), 5.0, False), (2, 16, 16, 3, 0, (20, 24), 5.0, True), (2, 16, 16, 3, 1, (20, 24), 5.0, True), (2, 16, 16, 3, 1, (20, 24), 5.0, False), (2, 32, 32, 3, 1, (20, 24), 5.0, True),
          (3, 16, 32, 3, 1, (40, 36), 50.0, True), (2, 32, 16, 1, 0, (24, 28), 10.0, True), (1, 16, 16, 3, 1, (19, 256), 50.0, True)]
 only = int(sys.argv[1]) if len(sys.argv) > 1 else -1
 for i, (B, Cin, Cout, k, pad, sp, kinv, upd) in enumerate(cases):

@@ -164,6 +164,9 @@ TC_CASES = [
     ('f2d_32_16_1x1', 2, 3, 32, 16, 1, 0, (24, 28), 10.0),
     ('f2d_16_16_1x1', 2, 2, 16, 16, 1, 0, (9, 132), 5.0),
     ('f2d_32_32_tall', 2, 1, 32, 32, 3, 1, (150, 12), 50.0),
+    ('f2d_3_16_gather', 2, 4, 3, 16, 3, 1, (40, 36), 50.0),       # few input channels: patch gathered in the kernel
+    ('f2d_1_32_gather', 2, 2, 1, 32, 3, 1, (21, 44), 20.0),
+    ('f2d_2_16_gather_nopad', 2, 2, 2, 16, 3, 0, (30, 52), 10.0),
     ('c2d_64_128', 2, 8, 64, 128, 3, 1, (16, 16), 20.0),
     ('c2d_128_64', 2, 8, 128, 64, 3, 1, (16, 16), 50.0),
     ('c2d_256_256', 2, 4, 256, 256, 3, 1, (8, 8), 50.0),
@@ -203,7 +206,7 @@ def test_tensor_core_shapes_vs_oracle(case, prec):
     layer.prec = prec
     layer.record_winners = True
     layer = layer.to(DEV).train()
-    if name.startswith('f2d_') and prec != 'fp32':
+    if name.startswith('f2d_') and prec != 'fp32' and '32_32' not in name:      # (32 -> 32 does not fit shared memory: two-kernel path)
         assert _native.layer_path(layer._desc(x.shape, True), _native.parse_prec(prec), _native.F_UPDATE | _native.F_WNRM) == _native.PATH_FUSED
     y = layer(x.to(DEV))
     # the forward error is ~4e-6 relative; near-ties below that are listed by the epilogue and resolved exactly
@@ -908,7 +911,7 @@ def test_stepper_cuda_graph_replay_matches_eager():
     assert relerr(net2[0].weight, net[0].weight) < 1e-6
 
 
-@pytest.mark.parametrize('shape', [(16, 16, 256, 256, 8), (32, 16, 256, 256, 4), (32, 32, 128, 128, 8)])
+@pytest.mark.parametrize('shape', [(16, 16, 256, 256, 8), (32, 16, 256, 256, 4), (16, 32, 128, 128, 8), (3, 16, 256, 256, 8)])
 def test_fused_kernel_at_size_vs_two_kernel_path(shape):
     """The fused small-channel kernel at the BASELINE C2 image sizes (many tiles per persistent CTA, two tile columns)
     against the independent pack / forward / update kernels (HEBB_FUSED=0 is read once per process, so the two-kernel
