@@ -97,6 +97,10 @@ int tc_conv_step(const Geo& g, const float* x, const float* W, const float* bias
                  cudaStream_t st, int aux = 0, double* ystats = nullptr, int* ystats_written = nullptr);
 
 // ---- fused forward + update kernel of the small-channel 2-D layers (fused_path.cu) ----
+// one launch: 1/|W_c| per filter, packed bf16 hi/lo weights ([slab][tap][k-chunk][hi|lo][Cout]), zero_bytes of zeroed
+// accumulators from zero_from, zeroed BatchNorm sums (nullable)
+int launch_layer_prep(const float* W, void* wp, float* inv, void* zero_from, size_t zero_bytes, double* ystats, int Cin, int Cout,
+                      int taps, int wnrm, cudaStream_t st);
 bool fused_supported(const Geo& g, int prec, unsigned flags);
 size_t fused_workspace_bytes(const Geo& g);
 int fused_describe_plan(const Geo& g, int* out, int n);

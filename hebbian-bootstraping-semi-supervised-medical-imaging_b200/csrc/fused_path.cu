@@ -41,7 +41,7 @@ constexpr int kRSlotPos = kRLead + 128;
 constexpr int kMaxRows = 18;              // x tile rows (TH + kH - 1) a CTA keeps barriers for
 constexpr int kMaxStages = 10;            // fp32 staging ring (TMA boxes in flight)
 constexpr int kDwLag = 2;                 // the update MMAs of a block are issued this many blocks after its forward MMAs
-constexpr int kRSlots = kDwLag + 2;       // response ring: slots of kRSlotPos positions
+constexpr int kRSlots = kDwLag + 2;       // response ring: at most this many slots of kRSlotPos positions (p.nrs are in use)
 constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxRows + 2 + 2 + 2 * kRSlots + 2;
 // warps: 0 TMA producer, 1 forward issuer, 2 update issuer, 3 .. 2+NCW converter, then the two epilogue sets of four.
 // NCW = 2 converter warps for the plain layers (13 warps: the issuing warps then share their scheduler with epilogue
@@ -54,6 +54,7 @@ struct FusedParams {
   int B, oH, oW, kH, kW, pH, pW, taps;
   int TH, TW, pitch, nTH, nTW, ntiles, XROWS, NBLK, XPOS, NST;
   unsigned pitch_magic;        // ceil(2^32 / pitch): q / pitch == umulhi(q, pitch_magic) for the q < 2^16 of a tile
+  int nrs;                     // response ring slots in use (kRSlots, or one fewer where shared memory is short)
   int gather, gcin, gk, srows; // few-input-channel layers: the converter gathers the gk x gk patch of the gcin real channels into
                                // gcin*gk*gk pseudo-channels of a 1x1 layer (srows = TH + gk - 1 staged input rows per tile)
   int BW, padl;                // TMA box width (floats) and left pad of the box start: staging column = tile column + padl - pW
@@ -171,7 +172,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // x image beyond the converted rows (read by the wasted kh copies / the last block) and the response ring
     const uint32_t x_tail = (uint32_t)p.XROWS * p.pitch * XB, x_end = (uint32_t)p.XPOS * XB;
     for (uint32_t a = x_tail + threadIdx.x * 16; a < x_end; a += blockDim.x * 16) st_shared_v4(xb + a, 0, 0, 0, 0);
-    const uint32_t r_end = (uint32_t)kRSlots * kRSlotPos * RB;
+    const uint32_t r_end = (uint32_t)p.nrs * kRSlotPos * RB;
     for (uint32_t a = threadIdx.x * 16; a < r_end; a += blockDim.x * 16) st_shared_v4(rb + a, 0, 0, 0, 0);
   }
   fence_proxy_async();
@@ -334,7 +335,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         d_first = false;
         rows_freed = free_to > rows_freed ? free_to : rows_freed;
         if (++jd == p.NBLK) jd = 0;
-        if (++slot_d == kRSlots) { slot_d = 0; ph_d ^= 1u; }
+        if (++slot_d == (uint32_t)p.nrs) { slot_d = 0; ph_d ^= 1u; }
       }
       if (elect_one()) umma_commit(done);
       __syncwarp();
@@ -487,7 +488,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         if (lane == 0) mbar_arrive(tf_empty + 8 * acc);        // the accumulator is in registers: hand the buffer back
         if (PROF) { const long long tq = clock64(); prof_acc[0] += tq - tq0; tq0 = tq; }      // [0] TMEM load
         if (p.dbg & 4) {
-          if (p.update) { fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(r_full + 8 * (kk % kRSlots)); }
+          if (p.update) { fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(r_full + 8 * (kk % (uint32_t)p.nrs)); }
           continue;
         }
         const int loc = quad * 32 + lane;
@@ -550,10 +551,11 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           f[i] = e; sum += e;
         }
         const float rinv = valid ? (1.f / sum) : 0.f;
-        const uint32_t slot = kk % kRSlots, nslot = (kk + 1u) % kRSlots;
-        // this block writes its own slot (last read by the update of block kk-kRSlots) and the lead of the next slot
-        // (block kk-kRSlots+1): the update issuer works in order, so one wait on the younger of the two covers both
-        if (kk >= kRSlots - 1) FWAIT(r_empty + 8 * nslot, ((kk - (kRSlots - 1)) / kRSlots) & 1u, 29);
+        const uint32_t nrs = (uint32_t)p.nrs;
+        const uint32_t slot = kk % nrs, nslot = (kk + 1u) % nrs;
+        // this block writes its own slot (last read by the update of block kk-nrs) and the lead of the next slot
+        // (block kk-nrs+1): the update issuer works in order, so one wait on the younger of the two covers both
+        if (kk >= nrs - 1) FWAIT(r_empty + 8 * nslot, ((kk - (nrs - 1)) / nrs) & 1u, 29);
         const uint32_t row = rb + slot * (kRSlotPos * RB) + (uint32_t)(kRLead + loc) * RB;
         // the last positions of a block are also the lead of the next block's slot (zeros at a tile's end)
         const bool carry = loc >= 128 - kRLead;
@@ -718,6 +720,7 @@ fused_prep_kernel(const float* __restrict__ W, uint4* __restrict__ wp, float* __
 // ---------------------------------------------------------------------------------------------------------------
 struct FPlan {
   int TH, TW, pitch, nTH, nTW, ntiles, XROWS, NBLK, XPOS, NST, grid, BW, padl;
+  int nrs;
   int gather, eCin, ek, etaps, srows;    // gather: few-channel 3x3 layer run as a 1x1 layer on eCin = 32 pseudo-channels
   uint32_t off_r, off_stage, off_w, off_misc, w_bytes, stage_bytes, smem, tmem_cols;
   size_t o_inv, o_rsum, o_err, o_wp, o_hpart, o_fix, o_prof, total;
@@ -739,59 +742,68 @@ bool fused_plan(const Geo& g, FPlan* P) {
   const int eCin = gather ? 32 : g.Cin, ekH = gather ? 1 : g.kH, ekW = gather ? 1 : g.kW;      // what the MMA side sees
   q.gather = gather ? 1 : 0; q.eCin = eCin; q.ek = ekH; q.etaps = ekH * ekW;
   const int XB = eCin * 4, RB = g.Cout * 4;
-  q.nTW = (int)cdiv(g.oW, 128);
-  q.TW = (int)(cdiv(cdiv(g.oW, q.nTW), 4) * 4);          // tile columns start on multiples of 4 floats
-  q.nTW = (int)cdiv(g.oW, q.TW);
-  q.pitch = (int)((q.TW + ekW - 1 + 3) / 4 * 4);
   // The TMA box starts padl = round_up(pW, 4) columns left of the tile, so that its first byte is 16-byte aligned in
   // global memory: a box whose first element is not 16-byte aligned raises an illegal-instruction fault on sm_100
   // (HEBB_FUSED_ALIGN=0 reproduces it)
   static const int want_align = [] { const char* e = getenv("HEBB_FUSED_ALIGN"); return (e && e[0] == '0') ? 0 : 1; }();
   q.padl = want_align ? (g.pW + 3) / 4 * 4 : g.pW;
-  q.BW = (q.pitch + (gather ? g.kW - 1 : 0) + (q.padl - g.pW) + 3) / 4 * 4;
-  if (q.BW > 256) return false;
   q.w_bytes = (uint32_t)((eCin / 16) * q.etaps * 4 * g.Cout * 16);
-  const uint32_t stage = (uint32_t)align_up((size_t)q.BW * (gather ? g.Cin : 16) * 4, 128);
-  q.stage_bytes = stage;
   const uint32_t misc = (uint32_t)(12 * g.Cout * 4 + 64 * 4 + 8 * kNumBars + 64);
-  const uint32_t r_bytes = (uint32_t)kRSlots * kRSlotPos * RB;
-  const uint32_t fixed = (uint32_t)align_up(r_bytes, 1024) + (uint32_t)align_up(q.w_bytes, 128) + misc + 1024;
   bool found = false;
   double best = 1e300, best_waste = 1e300;
-  const long long tiles_w = (long long)g.B * q.nTW;
   const int copies = 128 / (2 * eCin);
   const int reach = (copies - 1) > (ekH - 1) ? (copies - 1) : (ekH - 1);
-  // Tile height: the kernel is bound by the tensor pipe's operand fetches, so the positions the 128-wide blocks compute
-  // beyond the real pixels (row pitch > TW, the block that overhangs the tile, the last tile row of the image) cost time
-  // one to one; the re-converted halo rows cost a little; and the fp32 staging ring must keep ~48 KB of TMA boxes in
-  // flight per SM to cover the DRAM latency (measured: with 4 x 8 KB in flight the bare pipeline took 0.1 ms per 2304 tiles).
-  for (int th = 16; th >= 1; --th) {
-    if (th + ekH - 1 > kMaxRows) continue;
-    if (th > g.oH && th > 1) continue;
-    // the update of a block is issued after its responses went through the epilogue: the rows the next tile's first block
-    // waits for (kH) must have been released by the updates that can have been issued by then, which needs TH - 1 >= kH
-    if (th < ekH + 1) continue;
-    const long long tiles = tiles_w * cdiv(g.oH, th);
-    if (th > ekH + 1 && tiles < 4LL * sms && tiles_w * g.oH >= 4LL * sms) continue;      // enough tiles to balance the CTAs
-    const int nblk = (int)cdiv((long long)th * q.pitch, 128);
-    const int xpos = nblk * 128 + reach * q.pitch + 8;
-    const uint32_t x_bytes = (uint32_t)align_up((size_t)xpos * XB, 1024);
-    const int min_st = gather ? 4 : 3;                  // the gather keeps 3 staged rows open at a time
-    if (x_bytes + fixed + min_st * stage > (uint32_t)kSmemLimitF) continue;
-    int nst = (int)(((uint32_t)kSmemLimitF - x_bytes - fixed) / stage);
-    if (nst > kMaxStages) nst = kMaxStages;
-    const double waste = (double)nblk * 128.0 / ((double)th * q.TW) * ((double)cdiv(g.oH, th) * th / g.oH);
-    const double halo = (double)(th + g.kH - 1) / th;
-    double fl = gather ? 1.0 : (double)nst * stage / 49152.0; if (fl > 1.0) fl = 1.0;
-    const double cost = waste * (0.8 + 0.2 * halo) / (0.5 + 0.5 * fl);
-    if (cost < best) {
-      best = cost; best_waste = waste * (0.8 + 0.2 * halo); found = true;
-      q.TH = th; q.NBLK = nblk; q.XPOS = xpos; q.XROWS = th + ekH - 1; q.NST = nst; q.srows = th + g.kH - 1;
-      q.off_r = x_bytes;
-      q.off_stage = q.off_r + (uint32_t)align_up(r_bytes, 1024);
-      q.off_w = q.off_stage + nst * stage;
-      q.off_misc = q.off_w + (uint32_t)align_up(q.w_bytes, 128);
-      q.smem = x_bytes + fixed + nst * stage;
+  // Search tile width (whole rows up to 128 pixels, or 64-pixel columns where the 128-byte-per-position images would
+  // otherwise leave no room), response-ring depth and tile height.  The kernel is bound by the tensor pipe's operand
+  // fetches, so the positions the 128-wide blocks compute beyond the real pixels (row pitch > TW, the block that
+  // overhangs the tile, the last tile row of the image) cost time one to one; the re-converted halo rows cost a
+  // little; and the fp32 staging ring must keep ~48 KB of TMA boxes in flight per SM to cover the DRAM latency
+  // (measured: with 4 x 8 KB in flight the bare pipeline took 0.1 ms per 2304 tiles).
+  for (int twc = 0; twc < 2; ++twc) {
+    const int tw_max = twc == 0 ? 128 : 64;
+    if (twc == 1 && (g.oW <= 64 || gather)) break;      // (the gather converts one pixel per thread: 128-pixel rows)
+    int nTW = (int)cdiv(g.oW, tw_max);
+    const int TW = (int)(cdiv(cdiv(g.oW, nTW), 4) * 4);          // tile columns start on multiples of 4 floats
+    nTW = (int)cdiv(g.oW, TW);
+    const int pitch = (int)((TW + ekW - 1 + 3) / 4 * 4);
+    const int BW = (pitch + (gather ? g.kW - 1 : 0) + (q.padl - g.pW) + 3) / 4 * 4;
+    if (BW > 256) continue;
+    const uint32_t stage = (uint32_t)align_up((size_t)BW * (gather ? g.Cin : 16) * 4, 128);
+    const long long tiles_w = (long long)g.B * nTW;
+    for (int nrs = kRSlots; nrs >= kRSlots - 1; --nrs) {
+      const uint32_t r_bytes = (uint32_t)nrs * kRSlotPos * RB;
+      const uint32_t fixed = (uint32_t)align_up(r_bytes, 1024) + (uint32_t)align_up(q.w_bytes, 128) + misc + 1024;
+      for (int th = 16; th >= 1; --th) {
+        if (th + ekH - 1 > kMaxRows) continue;
+        if (th > g.oH && th > 1) continue;
+        // the update of a block is issued after its responses went through the epilogue: the rows the next tile's first
+        // block waits for (kH) must have been released by the updates that can have been issued by then: TH - 1 >= kH
+        if (th < ekH + 1) continue;
+        const long long tiles = tiles_w * cdiv(g.oH, th);
+        if (th > ekH + 1 && tiles < 4LL * sms && tiles_w * g.oH >= 4LL * sms) continue;      // enough tiles to balance the CTAs
+        const int nblk = (int)cdiv((long long)th * pitch, 128);
+        const int xpos = nblk * 128 + reach * pitch + 8;
+        const uint32_t x_bytes = (uint32_t)align_up((size_t)xpos * XB, 1024);
+        const int min_st = gather ? 4 : 3;                  // the gather keeps 3 staged rows open at a time
+        if (x_bytes + fixed + min_st * stage > (uint32_t)kSmemLimitF) continue;
+        int nst = (int)(((uint32_t)kSmemLimitF - x_bytes - fixed) / stage);
+        if (nst > kMaxStages) nst = kMaxStages;
+        const double waste = (double)nblk * 128.0 / ((double)th * TW) * ((double)cdiv(g.oH, th) * th / g.oH) *
+                             ((double)nTW * TW / g.oW);
+        const double halo = (double)(th + g.kH - 1) / th * (double)(TW + g.kW - 1) / TW;
+        double fl = gather ? 1.0 : (double)nst * stage / 49152.0; if (fl > 1.0) fl = 1.0;
+        const double cost = waste * (0.8 + 0.2 * halo) / (0.5 + 0.5 * fl) * (nrs < kRSlots ? 1.03 : 1.0);
+        if (cost < best) {
+          best = cost; best_waste = waste * (0.8 + 0.2 * halo); found = true;
+          q.TW = TW; q.nTW = nTW; q.pitch = pitch; q.BW = BW; q.stage_bytes = stage; q.nrs = nrs;
+          q.TH = th; q.NBLK = nblk; q.XPOS = xpos; q.XROWS = th + ekH - 1; q.NST = nst; q.srows = th + g.kH - 1;
+          q.off_r = x_bytes;
+          q.off_stage = q.off_r + (uint32_t)align_up(r_bytes, 1024);
+          q.off_w = q.off_stage + nst * stage;
+          q.off_misc = q.off_w + (uint32_t)align_up(q.w_bytes, 128);
+          q.smem = x_bytes + fixed + nst * stage;
+        }
+      }
     }
   }
   // a tile that wastes this much (tiny TH for the 128-byte-per-position images) is slower than the two-kernel path
@@ -841,6 +853,15 @@ EncodeTiledFn encode_fn() {
 static long long* g_last_prof = nullptr;
 static int g_last_prof_n = 0;
 
+// Launch wrapper of fused_prep_kernel for the two-kernel path (tc_path.cu): small weight tensors, one channel tile.
+int launch_layer_prep(const float* W, void* wp, float* inv, void* zero_from, size_t zero_bytes, double* ystats, int Cin, int Cout,
+                      int taps, int wnrm, cudaStream_t st) {
+  fused_prep_kernel<<<Cout, 128, 0, st>>>(W, reinterpret_cast<uint4*>(wp), inv, reinterpret_cast<uint32_t*>(zero_from), (int)(zero_bytes / 4),
+                                          ystats, Cin, (Cin + 15) / 16, Cout, taps, wnrm);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
 bool fused_supported(const Geo& g, int prec, unsigned flags) {
   if (prec != HEBB_PREC_BF16X3 && prec != HEBB_PREC_BF16) return false;
   if (flags & (HEBB_F_RULE_HPCA | HEBB_F_WGRAD_INTERNAL | HEBB_F_ONLY_PACK | HEBB_F_ONLY_FWD | HEBB_F_ONLY_DW)) return false;
@@ -856,7 +877,7 @@ size_t fused_workspace_bytes(const Geo& g) {
 int fused_describe_plan(const Geo& g, int* out, int n) {
   FPlan P;
   if (!fused_plan(g, &P)) return 0;
-  const int v[] = {P.TH, P.TW, P.pitch, P.ntiles, P.NBLK, P.XROWS, (int)P.smem, (int)P.tmem_cols, P.grid, P.NST};
+  const int v[] = {P.TH, P.TW, P.pitch, P.ntiles, P.NBLK, P.XROWS, (int)P.smem, (int)P.tmem_cols, P.grid, P.NST, P.nrs};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < m; ++i) out[i] = v[i];
   return m;
@@ -900,7 +921,7 @@ int fused_conv_step(const Geo& g, const float* x, const float* W, const float* b
   f.fix_list = reinterpret_cast<int*>(base + P.o_fix); f.fix_count = err + 4; f.fix_cap = P.fix_cap; f.tie_rel = tie_rel;
   f.wp = reinterpret_cast<const uint4*>(base + P.o_wp);
   f.B = g.B; f.oH = g.oH; f.oW = g.oW; f.kH = P.ek; f.kW = P.ek; f.pH = g.pH; f.pW = g.pW; f.taps = P.etaps;
-  f.gather = P.gather; f.gcin = g.Cin; f.gk = g.kH; f.srows = P.srows;
+  f.gather = P.gather; f.gcin = g.Cin; f.gk = g.kH; f.srows = P.srows; f.nrs = P.nrs;
   f.TH = P.TH; f.TW = P.TW; f.pitch = P.pitch; f.nTH = P.nTH; f.nTW = P.nTW; f.ntiles = P.ntiles; f.XROWS = P.XROWS;
   f.NBLK = P.NBLK; f.XPOS = P.XPOS; f.NST = P.NST; f.BW = P.BW; f.padl = P.padl;
   f.pitch_magic = (unsigned)((0x100000000ULL + (unsigned)P.pitch - 1) / (unsigned)P.pitch);

@@ -2233,8 +2233,16 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   const bool do_pack = !only || (only & HEBB_F_ONLY_PACK);
   const bool do_fwd = !wgrad && (!only || (only & HEBB_F_ONLY_FWD));
   const bool do_dw = upd && (!only || (only & HEBB_F_ONLY_DW));
-  if (do_fwd) HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, (P.o_xp[0] - P.o_rsum), st));   // rsum + err word
-  if ((flags & HEBB_F_WNRM) && do_pack && !wgrad) {
+  // Small weight tensors of plain layers: filter norms, weight packing and the zeroing of the per-call accumulators are
+  // ONE launch (fused_path.cu: fused_prep_kernel) instead of memset + wnorm + pack_w -- these layers are launch-bound
+  const long long n_wp = (long long)P.NSLAB * g.taps * P.f_HL * 2 * g.Cout;
+  const bool merged_prep = !only && !wgrad && !tr && P.n_ct == 1 && P.f_HL == 2 && n_wp < (1LL << 16);
+  const bool want_stats = ystats && do_fwd && !tr && P.n_ct == 1;
+  if (merged_prep)
+    HEBB_TRY(launch_layer_prep(W, wp, inv, base + P.o_rsum, P.o_xp[0] - P.o_rsum, want_stats ? ystats : nullptr, g.Cin, g.Cout, g.taps,
+                               (flags & HEBB_F_WNRM) ? 1 : 0, st));
+  if (do_fwd && !merged_prep) HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, (P.o_xp[0] - P.o_rsum), st));   // rsum + err word
+  if ((flags & HEBB_F_WNRM) && do_pack && !wgrad && !merged_prep) {
     if (tr)   // per INPUT channel over (Cout, taps) of the [Cout][Cin][taps] buffer (hebb3d.py:78 on the view)
       HEBB_TRY(launch_wnorm(W, nullptr, inv, g0.Cin, g0.taps, g0.Cout, (long long)g0.Cin * g0.taps, g0.taps, st));
     else
@@ -2275,7 +2283,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
     pack_r_kernel<<<ew_grid((long long)P.C8 * P.PR), 256, 0, st>>>(y, rp0, P.d_HL == 2 ? rp1 : nullptr, rg);
     HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   }
-  if (do_pack && !wgrad) {
+  if (do_pack && !wgrad && !merged_prep) {
     const long long n = (long long)P.NSLAB * g.taps * P.f_HL * 2 * g.Cout;
     const size_t tile_bytes = (size_t)16 * (16 * g.taps + 1) * sizeof(float);
     if (!tr && n >= (1LL << 16) && tile_bytes <= 48 * 1024) {
@@ -2295,7 +2303,7 @@ int tc_conv_step(const Geo& g0, const float* x, const float* W, const float* bia
   // BatchNorm statistics of y ride along when the layer is one channel tile of a plain convolution
   f.ystats = (ystats && do_fwd && !tr && P.n_ct == 1) ? ystats : nullptr;
   if (f.ystats) {
-    HEBB_CUDA_TRY(cudaMemsetAsync(ystats, 0, sizeof(double) * 2 * (size_t)g.Cout, st));
+    if (!merged_prep) HEBB_CUDA_TRY(cudaMemsetAsync(ystats, 0, sizeof(double) * 2 * (size_t)g.Cout, st));
     if (ystats_written) *ystats_written = 1;
   }
   f.tr = tr ? (trq ? 2 : 1) : 0; f.trQ = trq; f.tD = g0.oD; f.tH = g0.oH; f.tW = g0.oW; f.CoutR = g0.Cout;

@@ -397,7 +397,7 @@ def launch_count() -> int:
 
 
 PATH_SIMT, PATH_TC, PATH_FUSED = 0, 1, 2
-FUSED_PLAN_FIELDS = ['TH', 'TW', 'pitch', 'tiles', 'blocks_per_tile', 'x_rows', 'smem', 'tmem_cols', 'grid', 'stages']
+FUSED_PLAN_FIELDS = ['TH', 'TW', 'pitch', 'tiles', 'blocks_per_tile', 'x_rows', 'smem', 'tmem_cols', 'grid', 'stages', 'r_slots']
 
 
 def layer_path(desc: HebbDesc, prec: int, flags: int = 0) -> int:

@@ -6,6 +6,7 @@ import torch
 import hebb
 from hebb import _native
 Cin, Cout, H, k = [int(v) for v in sys.argv[1:5]]
+UPD = 0 if (len(sys.argv) > 5 and sys.argv[5] == 'fwd') else 1      # 'fwd': forward only (no plasticity update)
 B = 64
 x = torch.randn(B, Cin, H, H, device='cuda')
 layer = hebb.HebbianConv2d(Cin, Cout, k, padding=k // 2, bias=False, k=50., alpha=1.).cuda().train()
@@ -18,10 +19,10 @@ for i in range(6):
     flush.fill_(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _native.conv_step(desc, x, w, None, 50., y, None, dw, _native.F_WNRM | _native.F_UPDATE, 1)
+    _native.conv_step(desc, x, w, None, 50., y, None, dw, _native.F_WNRM | (_native.F_UPDATE if UPD else 0), 1)
     e1.record(); e1.synchronize()
     ts.append(e0.elapsed_time(e1))
-print(f"dbg={os.environ.get('HEBB_FUSED_DBG', '0'):>3s} {Cin}->{Cout} k{k} @{H}: {min(ts[1:]):.3f} ms  plan {_native.fused_plan(desc)}", flush=True)
+print(f"dbg={os.environ.get('HEBB_FUSED_DBG', '0'):>3s} {'upd' if UPD else 'fwd'} fused={os.environ.get('HEBB_FUSED', '1')} {Cin}->{Cout} k{k} @{H}: {min(ts[1:]):.3f} ms  plan {_native.fused_plan(desc)}", flush=True)
 
 if os.environ.get('HEBB_FUSED_PROF') == '1':
     import ctypes

@@ -192,7 +192,8 @@ TC_CASES = [
 @pytest.mark.parametrize('case', TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_tensor_core_shapes_vs_oracle(case, prec):
     name, nd, B, Cin, Cout, k, pad, spatial, kinv = case
-    g = torch.Generator().manual_seed(hash(name) % 1000)
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)      # (hash() of a str differs per process)
     x = torch.randn(B, Cin, *spatial, generator=g)
     cls = hebb.HebbianConv2d if nd == 2 else hebb.HebbianConv3d
     layer = cls(Cin, Cout, k, stride=1, padding=pad, bias=True, w_nrm=True, mode='swta', k=kinv, alpha=1.)
@@ -217,8 +218,9 @@ def test_tensor_core_shapes_vs_oracle(case, prec):
     assert nbad == 0
     # One stated exception to the 1e-4 bound: c3d_256_512 (64 pixels x 512 channels, K = 6912, k = 50).  The split
     # operands carry 16 mantissa bits, so y is exact to ~1e-5 relative; r = softmax(k*y) amplifies that by k = 50 and
-    # with only 64 pixels nothing averages out: measured 1.2e-4 (the reference's own fp32-vs-fp64 noise on this case is
-    # 1.7e-6, i.e. this IS our rounding, bounded here at 2e-4; every layer of the BASELINE workloads has >= 1440 pixels)
+    # with only 64 pixels nothing averages out: measured 4e-5 .. 1.2e-4 depending on the draw (the reference's own
+    # fp32-vs-fp64 noise on this case is 1.7e-6, i.e. this IS our rounding, bounded here at 2e-4; every layer of the
+    # BASELINE workloads has >= 1440 pixels)
     tol = TOL_DW[prec] * (2.0 if (name == 'c3d_256_512' and prec != 'bf16') else 1.0)
     assert relerr(layer.delta_w, dw_ref) < tol, (name, prec)
 
@@ -808,8 +810,8 @@ def test_training_loop_vs_reference_after_1_and_n_steps(name):
         assert worst_w < 1e-4, (name, step, worst_w)               # W within 1e-4 (north-star)
         if gold['opt'] == 'sgd':
             # movement / lr = -(sum of the updates): deep layers inherit the upstream rounding through BatchNorm on a
-            # 2-sample batch (same bound as test_network_vs_reference_golden)
-            assert worst_m < 2e-2, (name, step, worst_m)
+            # 2-sample batch (measured 4e-3 after 5 steps)
+            assert worst_m < 1e-2, (name, step, worst_m)
 
 
 def _nccl_rank(rank, world, port, q):
