@@ -53,7 +53,8 @@ def parse_args():
     ap.add_argument('--head-nchw', action='store_true', help='keep the stock back-prop head in NCHW (default: channels_last)')
     ap.add_argument('--cudnn-benchmark', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the companions of the default line (3-D workload, plain drop-in, GPU-eager reference, element-wise kernels)')
-    ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph (HebbianStepper(capture=True); single GPU)')
+    ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph (HebbianStepper(capture=True))')
+    ap.add_argument('--fused-adam', action='store_true', help='torch.optim.Adam(fused=True): one multi-tensor kernel for the optimiser step')
     return ap.parse_args()
 
 
@@ -343,7 +344,7 @@ def measure(args, workload, prec, B, steps, warmup, dev, world, rank, fuse=True,
         model.out_conv.register_forward_pre_hook(lambda mod, a: (a[0].contiguous(memory_format=torch.channels_last),))
     lr = 1e-6 if workload != 'c4' else 1e-5
     params = [p for p in model.parameters()]
-    opt = torch.optim.Adam(params, lr=lr, capturable=bool(capture)) if params else None
+    opt = torch.optim.Adam(params, lr=lr, capturable=bool(capture), fused=bool(args.fused_adam) or None) if params else None
     stepper = HebbianStepper(model, opt, crit, capture=capture)
     x_host, m_host = make_batch(B, 100 + rank, 'cpu')
     x_pin = x_host.pin_memory()
@@ -365,7 +366,7 @@ def measure(args, workload, prec, B, steps, warmup, dev, world, rank, fuse=True,
     sync_all()
 
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    n0 = _native.launch_count()
+    n0, g0 = _native.launch_count(), stepper.graph_launches
     with ClockSampler(dev.index or 0) as clk:
         sync_all()
         t_wall0 = time.perf_counter()
@@ -376,7 +377,7 @@ def measure(args, workload, prec, B, steps, warmup, dev, world, rank, fuse=True,
             e1.record()
         sync_all()
         t_wall = time.perf_counter() - t_wall0
-    launches = _native.launch_count() - n0
+    launches = _native.launch_count() - n0 + (stepper.graph_launches - g0)
     dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -603,7 +604,7 @@ def run_ours(args):
             'data': 'synthetic',
             'config': {'workload': f'{args.workload}: {desc}', 'per_gpu_batch': B, 'global_batch': B * world,
                        'hebb_params': HEBB_PARAMS if args.workload != 'c1' else {'mode': 'swta', 'k': 3.0, 'alpha': 1.0},
-                       'optimizer': f'adam lr={lr}', 'precision_mode': args.prec,
+                       'optimizer': f'adam lr={lr}' + (' (fused=True)' if args.fused_adam else ''), 'precision_mode': args.prec,
                        'fused_norm_act_upsample': (not args.no_fuse) and args.workload != 'c1',
                        'fused_ops': 'BatchNorm(train)+act with statistics from the conv epilogue, 2x up-sampling, 2x max pooling, bias+ReLU+dropout of the back-prop head (own Philox dropout stream)' if ((not args.no_fuse) and args.workload != 'c1') else 'none',
                        'head_weight_gradient': ('hebb_conv_wgrad (bf16x3) for <= %d filters' % args.head_wgrad) if ((not args.no_fuse) and args.head_wgrad and args.workload != 'c1') else 'cuDNN',

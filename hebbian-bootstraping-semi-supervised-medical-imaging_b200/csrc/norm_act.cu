@@ -169,11 +169,15 @@ maxpool2x_kernel(const float* __restrict__ in, float* __restrict__ out, long lon
 __global__ void __launch_bounds__(256)
 bias_relu_dropout_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ out,
                              uint8_t* __restrict__ mask, long long n, int C, long long inner, float p, float scale,
-                             unsigned long long seed) {
+                             unsigned long long seed, const unsigned long long* __restrict__ state) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nth = (long long)gridDim.x * blockDim.x;
   curandStatePhilox4_32_10_t rng;
-  curand_init(seed, (unsigned long long)tid, 0, &rng);
+  // device-resident stream state {seed, launches so far}: each launch skips 2^24 draws per thread ahead of the last one
+  // (a thread draws n / threads values), so a replayed CUDA graph still gets a fresh mask every time
+  unsigned long long off = 0;
+  if (state) { seed = state[0]; off = state[1] << 24; }
+  curand_init(seed, (unsigned long long)tid, off, &rng);
   const bool vec = ((n & 3) == 0) && ((inner & 3) == 0 || (inner == 1 && (C & 3) == 0)) &&
                    (((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(mask) & 3) == 0);
@@ -206,6 +210,8 @@ bias_relu_dropout_fwd_kernel(const float* __restrict__ z, const float* __restric
     }
   }
 }
+
+__global__ void dropout_state_bump_kernel(unsigned long long* state) { state[1] += 1; }
 
 // gz = gout * mask * scale
 __global__ void __launch_bounds__(256)
@@ -292,8 +298,8 @@ int hebb_bn_act_from_stats(const float* y, float* out, const double* y_stats, co
   return HEBB_OK;
 }
 
-int hebb_bias_relu_dropout(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
-                           int64_t inner, float p, uint64_t seed, void* stream) {
+static int bias_relu_dropout_impl(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
+                                  int64_t inner, float p, uint64_t seed, uint64_t* state, void* stream) {
   HEBB_TRY(device_ok());
   if (!z || !bias || !out || !mask) return HEBB_EARG;
   if (n <= 0 || C <= 0 || inner <= 0 || !(p >= 0.f && p < 1.f)) return HEBB_ESHAPE;
@@ -301,10 +307,25 @@ int hebb_bias_relu_dropout(const float* z, const float* bias, float* out, uint8_
   const long long cap = (long long)num_sms() * 16;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  bias_relu_dropout_fwd_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(z, bias, out, mask, n, (int)C, inner, p,
-                                                                              1.f / (1.f - p), seed);
+  bias_relu_dropout_fwd_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(
+      z, bias, out, mask, n, (int)C, inner, p, 1.f / (1.f - p), seed, reinterpret_cast<const unsigned long long*>(state));
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  if (state) {
+    dropout_state_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(state));
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  }
   return HEBB_OK;
+}
+
+int hebb_bias_relu_dropout(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
+                           int64_t inner, float p, uint64_t seed, void* stream) {
+  return bias_relu_dropout_impl(z, bias, out, mask, n, C, inner, p, seed, nullptr, stream);
+}
+
+int hebb_bias_relu_dropout_state(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
+                                 int64_t inner, float p, uint64_t* state, void* stream) {
+  if (!state) return HEBB_EARG;
+  return bias_relu_dropout_impl(z, bias, out, mask, n, C, inner, p, 0, state, stream);
 }
 
 int hebb_mask_scale(const float* gout, const uint8_t* mask, float* gz, int64_t n, float scale, void* stream) {

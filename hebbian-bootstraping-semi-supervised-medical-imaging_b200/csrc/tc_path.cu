@@ -1790,7 +1790,8 @@ static bool plan_layer_search(const Geo& g, int prec, Plan* P, int trq, bool gra
   for (int mb = 4; mb >= 1 && !found; mb >>= 1) {
     if (mb > 1 && mb * fcw > 256) continue;
     // do not make tiles so large that the grid cannot fill the machine
-    if (mb > 1 && cdiv(q.PTOT, 128LL * mb) < 2LL * sms) continue;
+    static const double mb_waves = [] { const char* e = getenv("HEBB_MB_WAVES"); return e ? atof(e) : 2.0; }();
+    if (mb > 1 && (double)cdiv(q.PTOT, 128LL * mb) < mb_waves * sms) continue;
     const int seglen = round_up_i(128 * mb + halo, 8);
     const uint32_t xst = (uint32_t)q.f_HL * 2 * seglen * 16;
     for (int nx = 3; nx >= 2 && !found; --nx) {

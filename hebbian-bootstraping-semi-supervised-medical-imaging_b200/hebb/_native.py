@@ -27,7 +27,7 @@ EXPORTS = [
     'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
     'hebb_debug_umma_rate', 'hebb_debug_umma_rate_shared_a', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_upsample2x_bilinear',
     'hebb_layer_path', 'hebb_debug_fused_plan', 'hebb_watchdog_code', 'hebb_debug_fused_prof', 'hebb_conv_swta_step_stats', 'hebb_bn_act_from_stats', 'hebb_conv_wgrad', 'hebb_maxpool2x',
-    'hebb_bias_relu_dropout', 'hebb_mask_scale',
+    'hebb_bias_relu_dropout', 'hebb_bias_relu_dropout_state', 'hebb_mask_scale',
 ]
 
 
@@ -86,6 +86,7 @@ def load():
         lib.hebb_upsample2x_bilinear.argtypes = [vp, vp, i64, i64, i64, vp]
         lib.hebb_maxpool2x.argtypes = [vp, vp, i64, i64, i64, i64, i32, vp]
         lib.hebb_bias_relu_dropout.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, ctypes.c_uint64, vp]
+        lib.hebb_bias_relu_dropout_state.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, vp, vp]
         lib.hebb_mask_scale.argtypes = [vp, vp, vp, i64, f32, vp]
         lib.hebb_debug_launch_count.restype = ctypes.c_ulonglong
         lib.hebb_uses_tensor_cores.argtypes = [ctypes.POINTER(HebbDesc), i32]
@@ -370,17 +371,44 @@ def _dense_channel_inner(t):
     return None
 
 
+_dropout_state = {}
+
+
+def dropout_state(device, reseed: bool = False):
+    """The device-resident Philox state {seed, launches so far} of hebb_bias_relu_dropout_state on `device`.  The seed
+    is drawn once from torch's CPU generator (so torch.manual_seed() before the first use, or reseed=True after a
+    later manual_seed(), governs the masks); the launch counter lives on the device, which is what lets a captured
+    step draw a new mask on every replay."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _dropout_state.get(key)
+    if st is None or reseed:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        new = torch.tensor([seed, 0], dtype=torch.int64, device=torch.device('cuda', key))
+        if st is None:
+            _dropout_state[key] = st = new
+        else:
+            st.copy_(new)                          # keep the address: a captured graph may hold it
+    return st
+
+
 @_device_guard(0)
-def bias_relu_dropout(z, bias, p: float, seed: int):
-    """(out, mask) = hebb_bias_relu_dropout on z's dense storage (NCHW or channels_last; out keeps z's layout)."""
+def bias_relu_dropout(z, bias, p: float, seed=None):
+    """(out, mask) = hebb_bias_relu_dropout on z's dense storage (NCHW or channels_last; out keeps z's layout).
+    seed=None takes the stream from dropout_state(z.device) (no host value in the launch: graph-capturable)."""
     _require_cuda(z, 'input')
     inner = _dense_channel_inner(z)
     if inner is None:
         raise RuntimeError('bias_relu_dropout needs a dense NCHW or channels_last tensor')
     out = torch.empty_like(z)                      # preserves the memory format
     mask = torch.empty_like(z, dtype=torch.uint8)
-    check(load().hebb_bias_relu_dropout(z.data_ptr(), bias.data_ptr(), out.data_ptr(), mask.data_ptr(), z.numel(), z.shape[1],
-                                        inner, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream_ptr(z.device)), 'bias_relu_dropout')
+    if seed is None:
+        st = dropout_state(z.device)
+        check(load().hebb_bias_relu_dropout_state(z.data_ptr(), bias.data_ptr(), out.data_ptr(), mask.data_ptr(), z.numel(),
+                                                  z.shape[1], inner, float(p), st.data_ptr(), _stream_ptr(z.device)),
+              'bias_relu_dropout_state')
+    else:
+        check(load().hebb_bias_relu_dropout(z.data_ptr(), bias.data_ptr(), out.data_ptr(), mask.data_ptr(), z.numel(), z.shape[1],
+                                            inner, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream_ptr(z.device)), 'bias_relu_dropout')
     return out, mask
 
 

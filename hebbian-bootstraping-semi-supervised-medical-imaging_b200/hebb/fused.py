@@ -201,8 +201,7 @@ class FastWgradConv3d(_FastWgradMixin, nn.Conv3d):
 class _BiasReluDropoutFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, bias, p):
-        seed = int(torch.empty((), dtype=torch.int64).random_().item())      # torch.manual_seed() governs it
-        out, mask = _native.bias_relu_dropout(z.detach(), bias.detach(), p, seed)
+        out, mask = _native.bias_relu_dropout(z.detach(), bias.detach(), p)   # stream state on the device (_native.dropout_state)
         ctx.save_for_backward(mask)
         ctx.scale = 1.0 / (1.0 - p)
         return out
@@ -219,12 +218,17 @@ class _BiasReluDropoutFn(torch.autograd.Function):
 
 
 class _NoBiasConvMixin:
-    """The bias add moves into the fused activation kernel that follows (see FusedBiasReluDropout)."""
+    """The bias add moves into the fused activation kernel that follows (see FusedBiasReluDropout).  The convolution
+    alone decides, per call, whether it leaves the bias out, and records that on the follower; the follower acts on
+    the record (it never re-derives the decision from its own input, which may differ in dtype under autocast)."""
 
     def forward(self, x):
         follower = self.__dict__.get('_bias_follower')
-        if follower is not None and follower[0]._takes_bias(x):
-            return self._conv_forward(x, self.weight, None)
+        if follower is not None:
+            omit = follower[0]._wants_bias(x)
+            follower[0]._bias_pending = omit
+            if omit:
+                return self._conv_forward(x, self.weight, None)
         return super().forward(x)
 
 
@@ -237,16 +241,19 @@ class FusedBiasReluDropout(nn.ReLU):
     convolution's bias, applies ReLU and dropout in one pass (hebb_bias_relu_dropout).  Parameter-free, so the
     state_dict is unchanged; eval mode, CPU tensors and odd layouts take the stock ops."""
 
-    def _takes_bias(self, x):
+    _bias_pending = False
+
+    def _wants_bias(self, x):
         return self.training and x.is_cuda and x.dtype == torch.float32 and 0.0 <= self._p < 1.0
 
     def forward(self, z):
         conv = self.__dict__['_conv'][0]
-        if self._takes_bias(z) and _native._dense_channel_inner(z) is not None:
+        owes_bias, self._bias_pending = self._bias_pending, False
+        if owes_bias and z.is_cuda and z.dtype == torch.float32 and _native._dense_channel_inner(z) is not None:
             return _BiasReluDropoutFn.apply(z, conv.bias, self._p)
-        # stock path: the convolution added its bias itself unless it saw a training-mode CUDA input
-        if self._takes_bias(z):
-            z = z + conv.bias.view(1, -1, *([1] * (z.dim() - 2)))
+        # stock path; the bias is added here exactly when the convolution reported that it left it out
+        if owes_bias:
+            z = z + conv.bias.to(z.dtype).view(1, -1, *([1] * (z.dim() - 2)))
         return F.dropout(F.relu(z), self._p, self.training)
 
 

@@ -123,9 +123,10 @@ class HebbianStepper:
 
     process_group / allreduce: the data-parallel exchange (default: on iff torch.distributed is initialised with
     more than one rank).  overlap: issue the delta_w all-reduce asynchronously after the forward pass.
-    capture: record the step (zero gradients, forward, loss, backward, local_update, optimiser step) into a CUDA
-    graph on first use and replay it afterwards; needs static input buffers (step() copies into them), a
-    capturable optimiser and no collective inside (single-process use)."""
+    capture: record the step (zero gradients, forward, both collectives, loss, backward, local_update, optimiser
+    step) into a CUDA graph on first use and replay it afterwards; needs static input buffers (step() copies into
+    them) and a capturable optimiser.  `graph_launches` counts the library's kernel launches replayed so far (the
+    library's own counter only sees the launches made while recording)."""
 
     def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, criterion=None,
                  process_group=None, allreduce: Optional[bool] = None, overlap: bool = True, capture: bool = False):
@@ -146,9 +147,11 @@ class HebbianStepper:
         self.flat_grad = flatten_grads(self.bp_params)
         self._grad_views = [p.grad for p in self.bp_params] if self.flat_grad is not None else []
         self._pending = None
-        self.capture = capture and not allreduce
+        self.capture = capture
         self._graph = None
         self._static = None
+        self.graph_launches = 0
+        self._launches_per_replay = 0
 
     # ------------------------------------------------------------------ data-parallel exchange
     def exchange_begin(self):
@@ -219,15 +222,24 @@ class HebbianStepper:
                     m.weight.grad = torch.zeros_like(m.delta_w)
             self._keep_hebb_grads = True
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            n0 = _native.launch_count()
+            # thread_local: the NCCL watchdog thread polls events while we record
+            with torch.cuda.graph(g, capture_error_mode='thread_local' if self.allreduce else 'global'):
                 self._out = self._captured_body(sx, st)
+            self._launches_per_replay = _native.launch_count() - n0
             self._graph = g
         sx, st = self._static
-        sx.copy_(x, non_blocking=True)
-        if st is not None:
+        if x.data_ptr() != sx.data_ptr():
+            sx.copy_(x, non_blocking=True)
+        if st is not None and target.data_ptr() != st.data_ptr():
             st.copy_(target, non_blocking=True)
         self._graph.replay()
+        self.graph_launches += self._launches_per_replay
         return self._out
+
+    def static_inputs(self):
+        """(x, target) buffers the captured step reads; a caller may fill them directly to save the copy in step()."""
+        return self._static
 
     def _captured_body(self, x, target):
         # like _step_body, but the fully Hebbian weights keep one persistent gradient tensor that local_update
@@ -235,11 +247,13 @@ class HebbianStepper:
         if self.flat_grad is not None:
             self.flat_grad.zero_()
         out = self.model(x)
+        self.exchange_begin()
         loss = None
         if self.criterion is not None and target is not None:
             loss = self.criterion(out, target)
             if loss.requires_grad:
                 loss.backward()
+        self.exchange_end()
         grads, dws, alphas, had = [], [], [], []
         hebb_only = {id(m) for m in self.hebb_only}
         for m in self.layers:

@@ -184,6 +184,11 @@ int hebb_maxpool2x(const float* in, float* out, int64_t N, int64_t D, int64_t H,
  * hebb_mask_scale is its backward: gz = gout * mask * scale.  Opt-in (hebb.fused.fuse_norm_act). */
 int hebb_bias_relu_dropout(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
                            int64_t inner, float p, uint64_t seed, void* stream);
+/* Same, with the stream state on the device: state[0] = seed, state[1] = launches so far (incremented by the call,
+ * on `stream`).  No host value enters the launch, so the call can be recorded into a CUDA graph and every replay
+ * draws a new mask. */
+int hebb_bias_relu_dropout_state(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
+                                 int64_t inner, float p, uint64_t* state, void* stream);
 int hebb_mask_scale(const float* gout, const uint8_t* mask, float* gz, int64_t n, float scale, void* stream);
 
 /* ---- exported for tests and profiling ---- */

@@ -831,8 +831,9 @@ def _nccl_rank(rank, world, port, q):
         g = torch.Generator().manual_seed(5)
         x, t = torch.randn(8, 16, 24, 24, generator=g).to(dev), torch.randn(8, 2, 24, 24, generator=g).to(dev)
         ref_dw = ref_w = None
+        import copy
+        net_g = copy.deepcopy(net)
         if rank == 0:
-            import copy
             single = copy.deepcopy(net)
             single[0](x)
             ref_dw = single[0].delta_w.clone()
@@ -853,11 +854,18 @@ def _nccl_rank(rank, world, port, q):
         gathered = [[torch.zeros_like(p) for _ in range(world)] for p in mine]
         for p, lst in zip(mine, gathered):
             dist.all_gather(lst, p)
+        # the same three steps with the step (both collectives included) recorded into a CUDA graph: the first call
+        # warms up with two eager steps and replays once
+        sg = HebbianStepper(net_g, torch.optim.SGD(net_g.parameters(), lr=1e-2), crit, capture=True)
+        sg.step(x[rank * h:(rank + 1) * h], t[rank * h:(rank + 1) * h])
+        torch.cuda.synchronize()
+        e_g = max(float((a.detach() - b).norm() / b.norm().clamp_min(1e-30)) for a, b in zip(net_g.parameters(), mine))
+        assert sg._graph is not None and sg.graph_launches > 0
         if rank == 0:
             same = all(torch.equal(lst[0], l2) for lst in gathered for l2 in lst[1:])
             e_dw = float((dw_sum - ref_dw).norm() / ref_dw.norm())
             e_w = max(float((a - b).norm() / b.norm().clamp_min(1e-30)) for a, b in zip(mine, ref_w))
-            q.put((same, e_dw, e_w))
+            q.put((same, e_dw, e_w, e_g))
     finally:
         dist.destroy_process_group()
 
@@ -876,10 +884,10 @@ def test_data_parallel_step_nccl_two_gpus():
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    same, e_dw, e_w = q.get(timeout=5)
-    record('data_parallel_nccl', 'world2', dw_sum_vs_full=e_dw, w_vs_single=e_w, replicas_identical=int(same))
+    same, e_dw, e_w, e_g = q.get(timeout=5)
+    record('data_parallel_nccl', 'world2', dw_sum_vs_full=e_dw, w_vs_single=e_w, replicas_identical=int(same), graph_vs_eager=e_g)
     assert same
-    assert e_dw < 1e-4 and e_w < 1e-4
+    assert e_dw < 1e-4 and e_w < 1e-4 and e_g < 1e-5
 
 
 def test_modules_follow_their_tensors_device_not_the_current_device():
@@ -911,6 +919,62 @@ def test_stepper_cuda_graph_replay_matches_eager():
         b.step(x)
     torch.cuda.synchronize()
     assert relerr(net2[0].weight, net[0].weight) < 1e-6
+
+
+def test_stepper_cuda_graph_full_network_matches_eager():
+    """The whole 2-D UNet step (fused-kernel layers, tcgen05 layers, BatchNorm statistics from the epilogues, the fused
+    bias+ReLU+dropout of the head, native head weight gradient, Adam) replayed from a CUDA graph against eager."""
+    import copy
+    from hebb.fused import fuse_norm_act
+    net = _build_net('unet2d')
+    with contextlib.redirect_stdout(io.StringIO()):
+        fuse_norm_act(net)
+    net2 = copy.deepcopy(net)
+    gg = torch.Generator().manual_seed(11)
+    xs = [torch.randn(2, 3, 64, 64, generator=gg).to(DEV) for _ in range(3)]
+    ms = [torch.randint(0, 2, (2, 64, 64), generator=gg).to(DEV) for _ in range(3)]
+    a = HebbianStepper(net, torch.optim.SGD(net.parameters(), lr=1e-3), workloads.dice_loss)
+    b = HebbianStepper(net2, torch.optim.SGD(net2.parameters(), lr=1e-3), workloads.dice_loss, capture=True)
+    a.step(xs[0], ms[0]); a.step(xs[0], ms[0])
+    for x, m in zip(xs, ms):
+        _, la = a.step(x, m)
+        _, lb = b.step(x, m)
+        assert abs(float(la) - float(lb)) < 1e-5
+    torch.cuda.synchronize()
+    assert b._graph is not None and b.graph_launches == 3 * b._launches_per_replay > 0
+    worst = max(relerr(p2, p1) for p1, p2 in zip(net.parameters(), net2.parameters()))
+    record('cuda_graph_step', 'unet2d', w_vs_eager=worst, launches_per_replay=b._launches_per_replay)
+    assert worst < 1e-5
+
+
+def test_dropout_state_lives_on_the_device_and_advances_under_graph_replay():
+    """hebb_bias_relu_dropout_state: the Philox state is device-resident, so a recorded launch draws a NEW mask on every
+    replay (a host seed would be frozen into the graph), and torch.manual_seed() + reseed reproduces the stream."""
+    z = torch.randn(2, 8, 32, 32, device=DEV).abs() + 0.1
+    bias = torch.zeros(8, device=DEV)
+    torch.manual_seed(5)
+    _native.dropout_state(DEV, reseed=True)
+    o1, _ = _native.bias_relu_dropout(z, bias, 0.5)
+    o2, _ = _native.bias_relu_dropout(z, bias, 0.5)
+    assert not torch.equal(o1 != 0, o2 != 0)
+    torch.manual_seed(5)
+    _native.dropout_state(DEV, reseed=True)
+    o1b, _ = _native.bias_relu_dropout(z, bias, 0.5)
+    assert torch.equal(o1, o1b)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _native.bias_relu_dropout(z, bias, 0.5)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out, mask = _native.bias_relu_dropout(z, bias, 0.5)
+    masks = []
+    for _ in range(3):
+        g.replay()
+        masks.append(mask.clone())
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+    assert abs(float(masks[2].float().mean()) - 0.5) < 0.02
 
 
 @pytest.mark.parametrize('shape', [(16, 16, 256, 256, 8), (32, 16, 256, 256, 4), (16, 32, 128, 128, 8), (3, 16, 256, 256, 8)])
