@@ -53,8 +53,10 @@ def parse_args():
     ap.add_argument('--head-nchw', action='store_true', help='keep the stock back-prop head in NCHW (default: channels_last)')
     ap.add_argument('--cudnn-benchmark', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the companions of the default line (3-D workload, plain drop-in, GPU-eager reference, element-wise kernels)')
-    ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph (HebbianStepper(capture=True))')
-    ap.add_argument('--fused-adam', action='store_true', help='torch.optim.Adam(fused=True): one multi-tensor kernel for the optimiser step')
+    ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph (HebbianStepper(capture=True)); the default for c1/c2/c4')
+    ap.add_argument('--no-graph', action='store_true', help='launch every step eagerly')
+    ap.add_argument('--fused-adam', action='store_true', help='(default) torch.optim.Adam(fused=True): one multi-tensor kernel for the optimiser step')
+    ap.add_argument('--no-fused-adam', action='store_true', help='torch.optim.Adam with its default (for-each) implementation')
     return ap.parse_args()
 
 
@@ -326,7 +328,7 @@ def roofline_from_rows(rows, prec, pk):
 
 
 def measure(args, workload, prec, B, steps, warmup, dev, world, rank, fuse=True, head_nchw=False, e2e=True, profile=True,
-            capture=False, layers_out=''):
+            capture=False, layers_out='', fused_adam=None):
     """Build the workload on `dev`, time `steps` steps (HBM-resident inputs, CUDA events per step, L2 flushed between
     steps, max over ranks) and, optionally, the end-to-end loop (pinned host batch in, loss out) and the per-layer profile."""
     import torch.distributed as dist
@@ -344,7 +346,9 @@ def measure(args, workload, prec, B, steps, warmup, dev, world, rank, fuse=True,
         model.out_conv.register_forward_pre_hook(lambda mod, a: (a[0].contiguous(memory_format=torch.channels_last),))
     lr = 1e-6 if workload != 'c4' else 1e-5
     params = [p for p in model.parameters()]
-    opt = torch.optim.Adam(params, lr=lr, capturable=bool(capture), fused=bool(args.fused_adam) or None) if params else None
+    if fused_adam is None:
+        fused_adam = not args.no_fused_adam
+    opt = torch.optim.Adam(params, lr=lr, capturable=bool(capture), fused=True if fused_adam else None) if params else None
     stepper = HebbianStepper(model, opt, crit, capture=capture)
     x_host, m_host = make_batch(B, 100 + rank, 'cpu')
     x_pin = x_host.pin_memory()
@@ -384,7 +388,8 @@ def measure(args, workload, prec, B, steps, warmup, dev, world, rank, fuse=True,
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     res = dict(workload=f'{workload}: {desc}', prec=prec, B=B, lr=lr, value=B * world * steps / (dev_ms / 1e3), ms_per_step=dev_ms / steps,
-               launches=int(launches), clocks=clk.summary(), wall_s=t_wall, steps=steps)
+               launches=int(launches), clocks=clk.summary(), wall_s=t_wall, steps=steps,
+               graph=stepper._graph is not None, fused_adam=bool(fused_adam))
 
     if e2e:
         # The public-API loop a user writes: every step's batch is copied from pinned host memory (on a side
@@ -445,6 +450,7 @@ def measure(args, workload, prec, B, steps, warmup, dev, world, rank, fuse=True,
         if layers_out:
             with open(layers_out, 'w') as f:
                 json.dump(dict(workload=workload, prec=prec, batch=B, layers=rows), f, indent=1)
+    stepper.release()
     del stepper, model, opt, x, m, flush_buf
     _native.release_workspaces()
     torch.cuda.empty_cache()
@@ -549,8 +555,23 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = time_cpu_port(args.workload, cpu_b, 2 if args.workload != 'c4' else 1, 1 if args.workload != 'c4' else 0)
 
-    main = measure(args, args.workload, args.prec, B, args.steps, args.warmup, dev, world, rank, fuse=not args.no_fuse,
-                   head_nchw=args.head_nchw, e2e=True, profile=not args.no_layer_profile, capture=args.graph, layers_out=args.layers_out)
+    def want_graph(workload):
+        return bool(args.graph or (not args.no_graph and workload in ('c1', 'c2', 'c4')))
+
+    graph_error = None
+    try:
+        main = measure(args, args.workload, args.prec, B, args.steps, args.warmup, dev, world, rank, fuse=not args.no_fuse,
+                       head_nchw=args.head_nchw, e2e=True, profile=not args.no_layer_profile, capture=want_graph(args.workload),
+                       layers_out=args.layers_out)
+    except Exception as e:
+        if not want_graph(args.workload):
+            raise
+        # recording the step failed: say so and measure the eagerly launched step instead
+        graph_error = f'{type(e).__name__}: {str(e)[:300]}'
+        print(f'[bench] CUDA-graph capture failed ({graph_error}); falling back to eager launches', file=sys.stderr, flush=True)
+        torch.cuda.synchronize()
+        main = measure(args, args.workload, args.prec, B, args.steps, args.warmup, dev, world, rank, fuse=not args.no_fuse,
+                       head_nchw=args.head_nchw, e2e=True, profile=not args.no_layer_profile, capture=False, layers_out=args.layers_out)
 
     # ---- companions of the headline (single GPU, default workload only): the 3-D half of BASELINE's metric, the plain
     # drop-in number, the reference formulation on this GPU, the element-wise kernels ----
@@ -558,19 +579,20 @@ def run_ours(args):
     if world == 1 and rank == 0 and args.workload == 'c2' and not args.no_extras:
         pk = peaks()
         try:
-            plain = measure(args, 'c2', args.prec, B, 3, 3, dev, world, rank, fuse=False, head_nchw=True, e2e=False, profile=False)
+            plain = measure(args, 'c2', args.prec, B, 3, 3, dev, world, rank, fuse=False, head_nchw=True, e2e=False, profile=False,
+                            capture=False, fused_adam=False)
             extras['value_plain_dropin'] = dict(value=plain['value'], ms_per_step=plain['ms_per_step'], unit='samples/s',
-                                                note='same step with the stock module tree: no hebb.fused pass, back-prop head in NCHW (bench.py --no-fuse --head-nchw)')
+                                                note='same step with the stock module tree, launched eagerly: no hebb.fused pass, back-prop head in NCHW, for-each Adam (bench.py --no-fuse --head-nchw --no-graph --no-fused-adam)')
         except Exception as e:          # an extra must never take the headline down
             extras['value_plain_dropin'] = dict(error=str(e)[:200])
         c4 = {}
         for prec in ('bf16x3', 'bf16'):
             try:
-                r = measure(args, 'c4', prec, WORKLOADS['c4'][1], 3, 3, dev, world, rank, e2e=True, profile=True,
+                r = measure(args, 'c4', prec, WORKLOADS['c4'][1], 3, 3, dev, world, rank, e2e=True, profile=True, capture=want_graph('c4'),
                             layers_out=(args.layers_out.replace('.json', f'_c4_{prec}.json') if args.layers_out else ''))
                 roof = r['roofline'] or {}
                 c4[prec] = dict(value=r['value'], unit='samples/s', ms_per_step=r['ms_per_step'], e2e=r.get('e2e'), clocks=r['clocks'],
-                                gpu_launches=r['launches'], steps=r['steps'],
+                                gpu_launches=r['launches'], steps=r['steps'], cuda_graph=r['graph'],
                                 roofline=dict(per_stage=roof.get('per_stage'), per_kernel={k: dict(achieved=v['achieved'], unit=v['unit'], frac=v['frac'], ms=v['ms'])
                                                                                              for k, v in (roof.get('per_kernel') or {}).items()},
                                               peak=pk['tf'], peak_source=pk['source'] + ' bf16 burst',
@@ -604,13 +626,15 @@ def run_ours(args):
             'data': 'synthetic',
             'config': {'workload': f'{args.workload}: {desc}', 'per_gpu_batch': B, 'global_batch': B * world,
                        'hebb_params': HEBB_PARAMS if args.workload != 'c1' else {'mode': 'swta', 'k': 3.0, 'alpha': 1.0},
-                       'optimizer': f'adam lr={lr}' + (' (fused=True)' if args.fused_adam else ''), 'precision_mode': args.prec,
+                       'optimizer': f'adam lr={lr}' + (' (torch.optim.Adam(fused=True))' if main['fused_adam'] else ''), 'precision_mode': args.prec,
                        'fused_norm_act_upsample': (not args.no_fuse) and args.workload != 'c1',
                        'fused_ops': 'BatchNorm(train)+act with statistics from the conv epilogue, 2x up-sampling, 2x max pooling, bias+ReLU+dropout of the back-prop head (own Philox dropout stream)' if ((not args.no_fuse) and args.workload != 'c1') else 'none',
                        'head_weight_gradient': ('hebb_conv_wgrad (bf16x3) for <= %d filters' % args.head_wgrad) if ((not args.no_fuse) and args.head_wgrad and args.workload != 'c1') else 'cuDNN',
                        'backward': 'stock ATen' if args.aten_backward else 'native dgrad/wgrad on the tcgen05 kernels where the planner takes the layer',
                        'backprop_head_memory_format': 'nchw' if (args.head_nchw or args.workload != 'c2') else 'channels_last (input converted once, by a forward pre-hook)', 'l2': 'flushed between timed steps (256 MB fill)',
-                       'cuda_graph': bool(args.graph),
+                       'cuda_graph': bool(main['graph']),
+                       'cuda_graph_note': ('the whole step (zero-grad, forward, both all-reduces, loss, backward, local_update, Adam) is recorded once by HebbianStepper(capture=True) and replayed; gpu_launches counts the replayed kernel nodes of this library'
+                                           if main['graph'] else (f'capture failed: {graph_error}' if graph_error else 'eager launches')),
                        'parallelism': f'dp{world} (batch shards; delta_w summed by one all-reduce issued after the forward, back-prop gradients of the head averaged by a second one)'},
             'e2e': main.get('e2e'),
             'gpu_launches': main['launches'],

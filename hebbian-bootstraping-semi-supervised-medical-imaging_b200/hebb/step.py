@@ -74,9 +74,20 @@ def backprop_parameters(model: nn.Module, layers: Optional[List[nn.Module]] = No
     return out
 
 
+def _dense_permutation(t: torch.Tensor) -> bool:
+    """True if t's elements tile its storage extent exactly once (a permuted contiguous tensor)."""
+    dims = sorted((st, sz) for st, sz in zip(t.stride(), t.shape) if sz > 1)
+    run = 1
+    for st, sz in dims:
+        if st != run:
+            return False
+        run *= sz
+    return True
+
+
 def flatten_grads(params: List[nn.Parameter], align: int = 64) -> Optional[torch.Tensor]:
     """Point the .grad of every parameter into one flat zero-initialised buffer (dense parameters keep their
-    strides; anything else gets a contiguous gradient).  autograd accumulates in place into an existing .grad,
+    strides, whatever the dimension order; anything else gets a contiguous gradient).  autograd accumulates in place into an existing .grad,
     so the buffer IS the gradient after backward()."""
     if not params:
         return None
@@ -87,12 +98,12 @@ def flatten_grads(params: List[nn.Parameter], align: int = 64) -> Optional[torch
     flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
     for p, o in zip(params, offs):
         n = p.numel()
-        if p.is_contiguous():
+        if p.is_contiguous() or not _dense_permutation(p):
             g = flat[o:o + n].view(p.shape)
-        elif p.dim() >= 2 and p.transpose(0, 1).is_contiguous():        # the transposed-view weights of HebbianConvTranspose
-            g = flat[o:o + n].view(p.shape[1], p.shape[0], *p.shape[2:]).transpose(0, 1)
         else:
-            g = flat[o:o + n].view(p.shape)
+            # same strides as the parameter (channels_last head weights, the transposed-view weights of
+            # HebbianConvTranspose): what autograd would allocate, and what fused optimisers insist on
+            g = flat[o:o + n].as_strided(p.shape, p.stride())
         p.grad = g
     return flat
 
@@ -236,6 +247,14 @@ class HebbianStepper:
         self._graph.replay()
         self.graph_launches += self._launches_per_replay
         return self._out
+
+    def release(self):
+        """Drop the recorded graph (the next step() records a new one).  Call it before
+        torch.distributed.destroy_process_group(): NCCL keeps a communicator alive -- and its destruction waiting --
+        for as long as a CUDA graph holds one of its collectives."""
+        self._graph = None
+        self._out = None
+        self._static = None
 
     def static_inputs(self):
         """(x, target) buffers the captured step reads; a caller may fill them directly to save the copy in step()."""
