@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c4', 'c5', 'c6'])
-    ap.add_argument('--head-wgrad', type=int, default=16, help='weight gradients of back-prop head convolutions with at most this many filters through hebb_conv_wgrad (0: all cuDNN)')
+    ap.add_argument('--head-wgrad', type=int, default=64, help='weight gradients of back-prop head convolutions with at most this many filters through hebb_conv_wgrad (0: all cuDNN)')
     ap.add_argument('--aten-backward', action='store_true', help='c6: differentiate with stock ATen ops instead of the native dgrad/wgrad kernels')
     ap.add_argument('--prec', default=os.environ.get('HEBB_PREC', 'bf16x3'), choices=['fp32', 'bf16x3', 'bf16'])
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (0 = the workload default)')
@@ -83,7 +83,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------
-def build_model(workload, impl_ours, device, fuse=False, head_wgrad=16):
+def build_model(workload, impl_ours, device, fuse=False, head_wgrad=64):
     """Returns (model, make_batch(batch, seed, device), criterion)."""
     if workload == 'c1':
         if impl_ours:
@@ -629,7 +629,7 @@ def run_ours(args):
                        'optimizer': f'adam lr={lr}' + (' (torch.optim.Adam(fused=True))' if main['fused_adam'] else ''), 'precision_mode': args.prec,
                        'fused_norm_act_upsample': (not args.no_fuse) and args.workload != 'c1',
                        'fused_ops': 'BatchNorm(train)+act with statistics from the conv epilogue, 2x up-sampling, 2x max pooling, bias+ReLU+dropout of the back-prop head (own Philox dropout stream)' if ((not args.no_fuse) and args.workload != 'c1') else 'none',
-                       'head_weight_gradient': ('hebb_conv_wgrad (bf16x3) for <= %d filters' % args.head_wgrad) if ((not args.no_fuse) and args.head_wgrad and args.workload != 'c1') else 'cuDNN',
+                       'head_weight_gradient': ('hebb_conv_wgrad (fp32-equivalent split) for <= %d filters: the fused kernel in weight-gradient mode for 16->64 and 64->32, the tcgen05 update kernel for the 2-class layer' % args.head_wgrad) if ((not args.no_fuse) and args.head_wgrad and args.workload != 'c1') else 'cuDNN',
                        'backward': 'stock ATen' if args.aten_backward else 'native dgrad/wgrad on the tcgen05 kernels where the planner takes the layer',
                        'backprop_head_memory_format': 'nchw' if (args.head_nchw or args.workload != 'c2') else 'channels_last (input converted once, by a forward pre-hook)', 'l2': 'flushed between timed steps (256 MB fill)',
                        'cuda_graph': bool(main['graph']),

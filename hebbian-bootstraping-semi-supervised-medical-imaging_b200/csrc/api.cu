@@ -143,7 +143,11 @@ int hebb_workspace_bytes(const HebbDesc* d, int prec, size_t* bytes) {
   // the CUDA-core scratch is also what the HPCA rule uses, whatever the precision mode
   const size_t a = use_tc(g, prec) ? tc_workspace_bytes(g, prec) : 0, b = simt_workspace_bytes(g);
   const size_t c = (prec != HEBB_PREC_FP32 && fused_supported(g, prec, 0)) ? fused_workspace_bytes(g) : 0;
-  *bytes = a > b ? (a > c ? a : c) : (b > c ? b : c);
+  const size_t e = (prec != HEBB_PREC_FP32 && !g.transposed) ? fused_wgrad_workspace_bytes(g) : 0;      // hebb_conv_wgrad
+  size_t m = a > b ? a : b;
+  if (c > m) m = c;
+  if (e > m) m = e;
+  *bytes = m;
   return HEBB_OK;
 }
 
@@ -158,6 +162,14 @@ int hebb_layer_path(const HebbDesc* d, int prec, unsigned flags) {
   Geo g;
   if (resolve_geo(d, &g) != HEBB_OK) return -1;
   if (prec != HEBB_PREC_FP32 && !g.transposed && fused_supported(g, prec, flags & 0xFFFFu)) return 2;
+  return use_tc(g, prec) ? 1 : 0;
+}
+
+int hebb_wgrad_path(const HebbDesc* d, int prec) {
+  Geo g;
+  if (resolve_geo(d, &g) != HEBB_OK) return -1;
+  if (g.transposed || prec == HEBB_PREC_FP32) return 0;
+  if (fused_wgrad_supported(g)) return 2;
   return use_tc(g, prec) ? 1 : 0;
 }
 
@@ -235,6 +247,9 @@ int hebb_conv_wgrad(const HebbDesc* d, const float* x, const float* grad_y, floa
   if (prec != HEBB_PREC_BF16X3 && prec != HEBB_PREC_BF16) return HEBB_EARG;
   if (gy_channels < 0 || gy_channels > g.Cout) return HEBB_EARG;
   if (!aligned16(ws)) return HEBB_EALIGN;
+  // few-channel layers reduced over many pixels (the back-prop head): the fused kernel with dL/dy as the responses
+  if ((gy_channels == 0 || gy_channels == g.Cout) && fused_wgrad_supported(g))
+    return fused_conv_wgrad(g, x, grad_y, grad_w, channels_last, ws, ws_bytes, (cudaStream_t)stream);
   if (!use_tc(g, prec)) return HEBB_ESHAPE;          // shapes outside the tcgen05 planner: caller's choice what to do
   if (channels_last && g.Cin <= 4 && g.taps > 1) return HEBB_ESHAPE;   // the patch-gathering pack reads NCHW only
   const int aux = (gy_channels & 0xFFFF) | ((channels_last ? 1 : 0) << 16);

@@ -107,5 +107,11 @@ int fused_describe_plan(const Geo& g, int* out, int n);
 int fused_conv_step(const Geo& g, const float* x, const float* W, const float* bias, float kinv, float* y, int32_t* winner,
                     float* delta_w, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st, double* ystats = nullptr,
                     int* ystats_written = nullptr);
+// hebb_conv_wgrad on the fused kernel (dL/dy in place of the responses): channel counts that split into at most two
+// passes of (16|32) x (16|32) channels; x and gy dense NCHW or dense channels_last; gw[Cout][Cin][taps] +=
+bool fused_wgrad_supported(const Geo& g);
+size_t fused_wgrad_workspace_bytes(const Geo& g);
+int fused_conv_wgrad(const Geo& g, const float* x, const float* gy, float* gw, int channels_last, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
 
 }  // namespace hebb

@@ -59,6 +59,11 @@ struct FusedParams {
                                // gcin*gk*gk pseudo-channels of a 1x1 layer (srows = TH + gk - 1 staged input rows per tile)
   int BW, padl;                // TMA box width (floats) and left pad of the box start: staging column = tile column + padl - pW
   float kinv; int update;
+  // weight-gradient mode (hebb_conv_wgrad on this kernel): dL/dy takes the place of the responses -- no forward MMAs, no
+  // softmax; the "epilogue" warps read gy[b][co][pixel] (element strides gy_sb / gy_sc / gy_sp) and feed the response ring
+  const float* gy; long long gy_sb, gy_sc, gy_sp;
+  int xcl;                     // x is channels_last: boxes [BW pixels][16 channels] through a 4-D tensor map
+  int cin_tot, ci_off;         // channels of the tensor behind the map, first channel of this launch (channel passes)
   long long* prof;             // HEBB_FUSED_PROF=1: per CTA [32] cycles spent in each bounded wait (index = code - 16) + totals
   int dbg;                     // HEBB_FUSED_DBG (profiling only): 1 one forward MMA per block, 2 no update MMAs, 4 no epilogue math,
                                // 8 no conversion, 16 no y stores
@@ -74,6 +79,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
 // tcgen05.mma with a run-time accumulate flag (the update accumulators are overwritten exactly once per kernel)
@@ -111,7 +126,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     }                                                                                \
   } while (0)
 
-template <int CIN, int COUT, int KS, bool PROF, int NCW>
+template <int CIN, int COUT, int KS, bool PROF, int NCW, bool WG = false>
 __global__ void __launch_bounds__(32 * (3 + NCW + 8), 1)
 fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
   constexpr int XB = CIN * 4;              // bytes per position of the x image: [hi Cin | lo Cin] bf16
@@ -197,8 +212,10 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(w_full, p.w_bytes);
-      bulk_g2s(sbase + p.off_w, p.wp, p.w_bytes, w_full);
+      if (!WG) {
+        mbar_expect_tx(w_full, p.w_bytes);
+        bulk_g2s(sbase + p.off_w, p.wp, p.w_bytes, w_full);
+      }
       int s = 0; uint32_t ph = 0;
       const uint32_t row_bytes = (uint32_t)p.BW * 16 * 4;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -218,7 +235,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           for (int cg = 0; cg < NSL; ++cg) {
             FWAIT(st_empty + 8 * s, ph ^ 1, 21);
             mbar_expect_tx(st_full + 8 * s, row_bytes);
-            tma_load_3d(sbase + p.off_stage + s * p.stage_bytes, &tmap, w0, h0 + r, b * CIN + cg * 16, st_full + 8 * s);
+            if (WG && p.xcl) tma_load_4d(sbase + p.off_stage + s * p.stage_bytes, &tmap, p.ci_off + cg * 16, w0, h0 + r, b, st_full + 8 * s);
+            else if (WG) tma_load_3d(sbase + p.off_stage + s * p.stage_bytes, &tmap, w0, h0 + r, b * p.cin_tot + p.ci_off + cg * 16, st_full + 8 * s);
+            else tma_load_3d(sbase + p.off_stage + s * p.stage_bytes, &tmap, w0, h0 + r, b * CIN + cg * 16, st_full + 8 * s);
             if (++s == p.NST) { s = 0; ph ^= 1; }
           }
       }
@@ -255,6 +274,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const int total = my_tiles * p.NBLK;
     if (warp == 1) {
       // ---------- forward issuer: block g as soon as its x rows are converted and its TMEM buffer has been drained ----------
+      if (!WG) {
       FWAIT(w_full, 0, 20);
       int rows_ready = 0, rows_freed = 0;
       int k = 0, it = 0;                        // block within the tile, tile count
@@ -296,6 +316,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
         if (++k == p.NBLK) { k = 0; ++it; }
       }
+      }
     } else if (p.update) {
       // ---------- update issuer: block g once its responses are in the ring (i.e. after its forward has completed and
       // been through the epilogue).  It runs on its own warp so that its waits overlap the forward issue; the tensor
@@ -303,9 +324,14 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       // releases are last read by forward blocks <= g, which have completed by the time r_full(g) is set. ----------
       int rows_freed = 0;
       int jd = 0; uint32_t slot_d = 0, ph_d = 0;   // block within its tile, response slot, its phase
+      int rows_ready = 0, itd = 0;                  // weight-gradient mode: nobody in front of this warp waited for the x rows
       bool d_first = true;
       for (int g = 0; g < total; ++g) {
-        if (jd == 0) rows_freed = 0;
+        if (jd == 0) { rows_freed = 0; rows_ready = 0; }
+        if (WG) {
+          const int need = s_need[jd];
+          for (; rows_ready < need; ++rows_ready) FWAIT(xr_full + 8 * rows_ready, itd & 1, 22);
+        }
         FWAIT(r_full + 8 * slot_d, ph_d, 24);
         tc_fence_after();
         const int free_to = s_free[jd];
@@ -334,7 +360,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         __syncwarp();
         d_first = false;
         rows_freed = free_to > rows_freed ? free_to : rows_freed;
-        if (++jd == p.NBLK) jd = 0;
+        if (++jd == p.NBLK) { jd = 0; ++itd; }
         if (++slot_d == (uint32_t)p.nrs) { slot_d = 0; ph_d ^= 1u; }
       }
       if (elect_one()) umma_commit(done);
@@ -423,8 +449,24 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         for (int cg = 0; cg < NSL; ++cg) {
           FWAIT(st_full + 8 * s, ph, 25);
           if (cg == 0) FWAIT(xr_empty + 8 * r, (it & 1) ^ 1, 26);      // the previous tile no longer reads this row
+          if (WG && p.xcl) {
+            // channels_last box: [pixel][16 channels] fp32; four lanes share a pixel (one float4 = 4 channels each)
+            const float4* st4 = reinterpret_cast<const float4*>(smem + p.off_stage + s * p.stage_bytes) + (p.padl - p.pW) * 4;
+            for (int idx = t; idx < p.pitch * 4; idx += 32 * NCW) {
+              const int c = idx >> 2, j = idx & 3;
+              const float4 v = st4[idx];
+              uint32_t h0, h1, l0, l1;
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v.y), "f"(v.x));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v.w), "f"(v.z));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l0) : "f"(v.y - __uint_as_float(h0 & 0xffff0000u)), "f"(v.x - __uint_as_float(h0 << 16)));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l1) : "f"(v.w - __uint_as_float(h1 & 0xffff0000u)), "f"(v.z - __uint_as_float(h1 << 16)));
+              const uint32_t row = xb + (uint32_t)(r * p.pitch + c) * XB;
+              st_shared_v2(swz<XCH>(row, 2 * cg + (j >> 1)) + (uint32_t)(j & 1) * 8u, h0, h1);
+              st_shared_v2(swz<XCH>(row, XCH / 2 + 2 * cg + (j >> 1)) + (uint32_t)(j & 1) * 8u, l0, l1);
+            }
+          }
           const float* st = reinterpret_cast<const float*>(smem + p.off_stage + s * p.stage_bytes) + (p.padl - p.pW);
-          for (int c = t; c < ((p.dbg & 8) ? 0 : p.pitch); c += 32 * NCW) {
+          for (int c = t; c < (((p.dbg & 8) || (WG && p.xcl)) ? 0 : p.pitch); c += 32 * NCW) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = st[i * p.BW + c];
@@ -474,10 +516,38 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       const int THv = min(p.TH, p.oH - h0), TWv = min(p.TW, p.oW - w0);
       for (int k = 0; k < p.NBLK; ++k, ++kk) {
         if ((int)(kk & 1u) != eset) continue;
+        const int loc = quad * 32 + lane;
+        float f[COUT];
+        float rinv;
+        long long tq0 = PROF ? clock64() : 0;
+        if constexpr (WG) {
+          // weight-gradient mode: this pixel's dL/dy row takes the place of the responses
+          const int q = k * 128 + loc;
+          const int r_ = (int)__umulhi((unsigned)q, p.pitch_magic), c_ = q - r_ * p.pitch;      // q / pitch (q < 2^16)
+          const bool valid = r_ < THv && c_ < TWv;
+          const long long pix = (long long)(h0 + r_) * p.oW + (w0 + c_);
+          if (valid) {
+            const float* gp = p.gy + (long long)b * p.gy_sb + pix * p.gy_sp;
+            if (p.gy_sc == 1) {
+#pragma unroll
+              for (int i4 = 0; i4 < COUT; i4 += 4) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gp + i4));
+                f[i4] = g4.x; f[i4 + 1] = g4.y; f[i4 + 2] = g4.z; f[i4 + 3] = g4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < COUT; ++i) { f[i] = __ldg(gp); gp += p.gy_sc; }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < COUT; ++i) f[i] = 0.f;
+          }
+          rinv = 1.f;
+        } else {
         const uint32_t acc = kk & 1u;
         FWAIT(tf_full + 8 * acc, (kk >> 1) & 1u, 27);
         tc_fence_after();
-        long long tq0 = PROF ? clock64() : 0;
+        tq0 = PROF ? clock64() : 0;
         uint32_t v[COUT], v2[COUT];
         const uint32_t ta = tmem_f + (static_cast<uint32_t>(quad * 32) << 16) + acc * FCOLS;
         TmemLd<COUT>::ld(ta, v);
@@ -491,11 +561,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           if (p.update) { fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(r_full + 8 * (kk % (uint32_t)p.nrs)); }
           continue;
         }
-        const int loc = quad * 32 + lane;
         const int q = k * 128 + loc;
         const int r_ = (int)__umulhi((unsigned)q, p.pitch_magic), c_ = q - r_ * p.pitch;      // q / pitch (q < 2^16)
         const bool valid = r_ < THv && c_ < TWv;
-        float f[COUT];
 #pragma unroll
         for (int i4 = 0; i4 < COUT; i4 += 4) {
           const float4 sc = *reinterpret_cast<const float4*>(s_inv + i4);
@@ -550,7 +618,8 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(f[i] - mx2));
           f[i] = e; sum += e;
         }
-        const float rinv = valid ? (1.f / sum) : 0.f;
+        rinv = valid ? (1.f / sum) : 0.f;
+        }
         const uint32_t nrs = (uint32_t)p.nrs;
         const uint32_t slot = kk % nrs, nslot = (kk + 1u) % nrs;
         // this block writes its own slot (last read by the update of block kk-nrs) and the lead of the next slot
@@ -714,6 +783,25 @@ fused_prep_kernel(const float* __restrict__ W, uint4* __restrict__ wp, float* __
     for (int i = threadIdx.x; i < nzero32; i += blockDim.x) zero32[i] = 0u;
     if (ystats)
       for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x) ystats[i] = 0.0;
+  }
+}
+
+// Weight-gradient mode: gw[co_off + co][ci_off + ci][tap] += the per-CTA partials, summed in a fixed order.
+__global__ void __launch_bounds__(256)
+fused_wgrad_finalize_kernel(const float* __restrict__ hpart, float* __restrict__ gw, int n_part, int taps, int CI, int CO,
+                            int cin_tot, int ci_off, int co_off) {
+  const int n = taps * CI * CO;
+  const int idx = blockIdx.x * (blockDim.x / 8) + (threadIdx.x >> 3);      // 8 threads per output element
+  const int sub = threadIdx.x & 7;
+  float acc = 0.f;
+  if (idx < n)
+    for (int part = sub; part < n_part; part += 8) acc += __ldg(hpart + (long long)part * n + idx);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (idx < n && sub == 0) {
+    const int co = idx % CO, ci = (idx / CO) % CI, tap = idx / (CO * CI);
+    gw[((long long)(co_off + co) * cin_tot + ci_off + ci) * taps + tap] += acc;
   }
 }
 
@@ -927,6 +1015,7 @@ int fused_conv_step(const Geo& g, const float* x, const float* W, const float* b
   f.pitch_magic = (unsigned)((0x100000000ULL + (unsigned)P.pitch - 1) / (unsigned)P.pitch);
 
   f.kinv = kinv; f.update = upd ? 1 : 0;
+  f.gy = nullptr; f.gy_sb = f.gy_sc = f.gy_sp = 0; f.xcl = 0; f.cin_tot = g.Cin; f.ci_off = 0;
   static const int fdbg = [] { const char* e = getenv("HEBB_FUSED_DBG"); return e ? atoi(e) : 0; }();
   f.dbg = fdbg;
   static const int fprof = [] { const char* e = getenv("HEBB_FUSED_PROF"); return (e && e[0] == '1') ? 1 : 0; }();
@@ -960,6 +1049,108 @@ int fused_conv_step(const Geo& g, const float* x, const float* W, const float* b
     HEBB_TRY(launch_winner_fixup(g, x, W, (flags & HEBB_F_WNRM) ? inv : nullptr, bias, winner, f.fix_list, f.fix_count, P.fix_cap, st));
   if (upd)
     HEBB_TRY(tc_launch_finalize(f.hpart, rsum, W, delta_w, P.grid * 2, P.etaps, pCin, P.eCin, g.Cout, st));
+  return HEBB_OK;
+}
+
+// ---- hebb_conv_wgrad on the fused kernel ("the wgrad kernel is a6 with dL/dy in place of r") ----
+// Channel counts that are multiples of 16 run as passes of (16|32) x (16|32) channels: every pass re-reads one of the
+// two tensors, so only layers that need at most kMaxWgradPasses passes are taken (the back-prop head of the 2-D
+// network: 16 -> 64 and 64 -> 32; its tall-skinny reduction over 4 M pixels is the shape this kernel was built for).
+static bool fused_wgrad_split(const Geo& g, Geo* sub, int* cip, int* cop) {
+  if (g.nd != 2 || g.transposed) return false;
+  if (g.Cin % 16 != 0 || g.Cout % 16 != 0) return false;
+  static const int want = [] { const char* e = getenv("HEBB_FUSED_WGRAD"); return (e && e[0] == '0') ? 0 : 1; }();
+  static const int max_passes = [] { const char* e = getenv("HEBB_FUSED_WGRAD_PASSES"); return e ? atoi(e) : 2; }();
+  if (!want) return false;
+  const int ci = (g.Cin % 32 == 0) ? 32 : 16, co = (g.Cout % 32 == 0) ? 32 : 16;
+  if ((g.Cin / ci) * (g.Cout / co) > max_passes) return false;
+  *sub = g;
+  sub->Cin = ci; sub->Cout = co;
+  *cip = ci; *cop = co;
+  return true;
+}
+
+bool fused_wgrad_supported(const Geo& g) {
+  Geo sub; int ci, co; FPlan P;
+  return fused_wgrad_split(g, &sub, &ci, &co) && fused_plan(sub, &P) && !P.gather && encode_fn() != nullptr;
+}
+
+size_t fused_wgrad_workspace_bytes(const Geo& g) {
+  Geo sub; int ci, co; FPlan P;
+  return (fused_wgrad_split(g, &sub, &ci, &co) && fused_plan(sub, &P)) ? P.total : 0;
+}
+
+int fused_conv_wgrad(const Geo& g, const float* x, const float* gy, float* gw, int channels_last, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  Geo sub; int CI, CO; FPlan P;
+  if (!fused_wgrad_split(g, &sub, &CI, &CO) || !fused_plan(sub, &P) || P.gather) return HEBB_ESHAPE;
+  if (!ws || ws_bytes < P.total) return HEBB_EWS;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return HEBB_EALIGN;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return HEBB_ECUDA;
+  char* base = static_cast<char*>(ws);
+  float* rsum = reinterpret_cast<float*>(base + P.o_rsum);
+  int* err = reinterpret_cast<int*>(base + P.o_err);
+
+  CUtensorMap tm;
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult rc;
+  if (channels_last) {
+    const cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.iW, (cuuint64_t)g.iH, (cuuint64_t)g.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 4, (cuuint64_t)g.iW * g.Cin * 4, (cuuint64_t)g.iH * g.iW * g.Cin * 4};
+    const cuuint32_t box[4] = {16u, (cuuint32_t)P.BW, 1u, 1u};
+    rc = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[3] = {(cuuint64_t)g.iW, (cuuint64_t)g.iH, (cuuint64_t)g.B * g.Cin};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.iW * 4, (cuuint64_t)g.iW * g.iH * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)P.BW, 1u, 16u};
+    rc = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (rc != CUDA_SUCCESS) return HEBB_ESHAPE;
+
+  FusedParams f;
+  memset(&f, 0, sizeof(f));
+  f.rsum = rsum; f.hpart = reinterpret_cast<float*>(base + P.o_hpart);
+  f.err = watchdog_word() ? watchdog_word() : err;
+  f.fix_list = reinterpret_cast<int*>(base + P.o_fix); f.fix_count = err + 4; f.fix_cap = P.fix_cap;
+  f.B = g.B; f.oH = g.oH; f.oW = g.oW; f.kH = P.ek; f.kW = P.ek; f.pH = g.pH; f.pW = g.pW; f.taps = P.etaps;
+  f.gcin = CI; f.gk = g.kH; f.srows = P.srows; f.nrs = P.nrs;
+  f.TH = P.TH; f.TW = P.TW; f.pitch = P.pitch; f.nTH = P.nTH; f.nTW = P.nTW; f.ntiles = P.ntiles; f.XROWS = P.XROWS;
+  f.NBLK = P.NBLK; f.XPOS = P.XPOS; f.NST = P.NST; f.BW = P.BW; f.padl = P.padl;
+  f.pitch_magic = (unsigned)((0x100000000ULL + (unsigned)P.pitch - 1) / (unsigned)P.pitch);
+  f.kinv = 1.f; f.update = 1;
+  f.off_r = P.off_r; f.off_stage = P.off_stage; f.off_w = P.off_w; f.off_misc = P.off_misc; f.w_bytes = 0;
+  f.stage_bytes = P.stage_bytes; f.tmem_cols = P.tmem_cols;
+  f.xcl = channels_last ? 1 : 0; f.cin_tot = g.Cin;
+  if (channels_last) { f.gy_sb = g.outS * g.Cout; f.gy_sc = 1; f.gy_sp = g.Cout; }
+  else { f.gy_sb = g.outS * g.Cout; f.gy_sc = g.outS; f.gy_sp = 1; }
+  const int n_out = P.etaps * CI * CO;
+  for (int co0 = 0; co0 < g.Cout; co0 += CO)
+    for (int ci0 = 0; ci0 < g.Cin; ci0 += CI) {
+      HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, P.o_wp - P.o_rsum, st));      // sum of gy, error word
+      f.gy = gy + (long long)co0 * f.gy_sc;
+      f.ci_off = ci0;
+#define HEBB_FUSED_WG(CIv, COv)                                                                                          \
+  do {                                                                                                                    \
+    if (P.ek == 3) {                                                                                                      \
+      HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CIv, COv, 3, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
+      fused_small_kernel<CIv, COv, 3, false, 2, true><<<P.grid, 32 * 13, kSmemLimitF, st>>>(tm, f);                             \
+    } else {                                                                                                              \
+      HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CIv, COv, 1, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
+      fused_small_kernel<CIv, COv, 1, false, 2, true><<<P.grid, 32 * 13, kSmemLimitF, st>>>(tm, f);                             \
+    }                                                                                                                     \
+  } while (0)
+      if (CI == 16 && CO == 16) HEBB_FUSED_WG(16, 16);
+      else if (CI == 16 && CO == 32) HEBB_FUSED_WG(16, 32);
+      else if (CI == 32 && CO == 16) HEBB_FUSED_WG(32, 16);
+      else HEBB_FUSED_WG(32, 32);
+#undef HEBB_FUSED_WG
+      HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+      fused_wgrad_finalize_kernel<<<(unsigned)cdiv(n_out, 32), 256, 0, st>>>(f.hpart, gw, P.grid * 2, P.etaps, CI, CO, g.Cin, ci0, co0);
+      HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+    }
   return HEBB_OK;
 }
 

@@ -26,7 +26,7 @@ EXPORTS = [
     'hebb_workspace_bytes', 'hebb_wnorm', 'hebb_conv_swta_step', 'hebb_convT_swta_step',
     'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
     'hebb_debug_umma_rate', 'hebb_debug_umma_rate_shared_a', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_upsample2x_bilinear',
-    'hebb_layer_path', 'hebb_debug_fused_plan', 'hebb_watchdog_code', 'hebb_debug_fused_prof', 'hebb_conv_swta_step_stats', 'hebb_bn_act_from_stats', 'hebb_conv_wgrad', 'hebb_maxpool2x',
+    'hebb_layer_path', 'hebb_wgrad_path', 'hebb_debug_fused_plan', 'hebb_watchdog_code', 'hebb_debug_fused_prof', 'hebb_conv_swta_step_stats', 'hebb_bn_act_from_stats', 'hebb_conv_wgrad', 'hebb_maxpool2x',
     'hebb_bias_relu_dropout', 'hebb_bias_relu_dropout_state', 'hebb_mask_scale',
 ]
 
@@ -91,6 +91,7 @@ def load():
         lib.hebb_debug_launch_count.restype = ctypes.c_ulonglong
         lib.hebb_uses_tensor_cores.argtypes = [ctypes.POINTER(HebbDesc), i32]
         lib.hebb_layer_path.argtypes = [ctypes.POINTER(HebbDesc), i32, ctypes.c_uint]
+        lib.hebb_wgrad_path.argtypes = [ctypes.POINTER(HebbDesc), i32]
         lib.hebb_debug_fused_plan.argtypes = [ctypes.POINTER(HebbDesc), ctypes.POINTER(ctypes.c_int), i32]
         for name in EXPORTS:
             getattr(lib, name)      # fail loudly if a declared symbol is missing
@@ -268,7 +269,7 @@ def conv_wgrad(desc: HebbDesc, x, grad_y, prec: int, gy_channels: int = 0, chann
     """grad_w[Cout][Cin][taps] of a stride-1 convolution on the tcgen05 contraction kernel (hebb_conv_wgrad).
     x / grad_y: dense NCHW (default) or dense channels_last storage.  Returns None when the layer is outside
     the tensor-core planner (the caller then uses ATen)."""
-    if desc.transposed or prec == PREC_FP32 or not uses_tensor_cores(desc, prec):
+    if desc.transposed or prec == PREC_FP32 or wgrad_path(desc, prec) <= 0:
         return None
     taps = desc.k[0] * desc.k[1] * desc.k[2]
     if channels_last and desc.Cin <= 4 and taps > 1:
@@ -432,6 +433,11 @@ def layer_path(desc: HebbDesc, prec: int, flags: int = 0) -> int:
     """Which kernels a step of this layer runs on: PATH_SIMT (fp32 CUDA cores), PATH_TC (pack + forward + update
     tcgen05 kernels) or PATH_FUSED (the one-kernel small-channel path)."""
     return int(load().hebb_layer_path(ctypes.byref(desc), int(prec), int(flags)))
+
+
+def wgrad_path(desc: HebbDesc, prec: int) -> int:
+    """Which kernels conv_wgrad runs on: 0 none, PATH_TC, or PATH_FUSED (the fused kernel with dL/dy as the responses)."""
+    return int(load().hebb_wgrad_path(ctypes.byref(desc), int(prec)))
 
 
 def fused_plan(desc: HebbDesc):

@@ -9,9 +9,10 @@ and every `nn.Upsample(scale_factor=2, bilinear, align_corners=True)` so it runs
 as `hebb_maxpool2x`; the stock convolutions a Hebbian network keeps for back-prop (makehebbian's `exclude` list)
 have their `Conv -> ReLU -> Dropout` runs turned into convolution-without-bias + one `hebb_bias_relu_dropout`
 pass (`fuse_head_act=True`; statistically the same dropout, its own Philox stream), and can get their weight
-gradient from `hebb_conv_wgrad` (`head_wgrad=N`: convolutions with at most N filters, default 16 — the 2-class
-output layer, whose cuDNN weight gradient costs 1.7 ms against 0.9 ms here, fp32-equivalent instead of TF32; for
-the wider head layers the packing passes eat the gain).
+gradient from `hebb_conv_wgrad` (`head_wgrad=N`: convolutions with at most N filters, default 64 — the 2-class
+output layer, whose cuDNN weight gradient costs 1.7 ms against 0.9 ms here, fp32-equivalent instead of TF32; the
+16 -> 64 and 64 -> 32 layers of the 2-D head where the fused kernel takes them in weight-gradient mode, i.e. reads
+x and dL/dy once per channel pass instead of packing them first; other wide layers stay with cuDNN).
 Numerics follow torch (biased variance for normalisation, unbiased for the running estimate, momentum update, num_batches_tracked).  Anything the kernels do not cover —
 eval mode, inputs or affine parameters that require grad, CPU tensors, cumulative-average momentum —
 takes the stock torch path of the parent class, so the pass is always safe to apply.
@@ -173,6 +174,8 @@ class _FastWgradMixin:
         cpad = (cout + 15) // 16 * 16          # the kernel works on multiples of 16 filters; the extra rows are zero
         desc = _native.make_desc(nd, x.shape[0], self.in_channels, cpad, x.shape[2:], self.kernel_size, (1,) * nd,
                                  self.padding, self.padding, False)
+        if cout > 16 and _native.wgrad_path(desc, prec) != _native.PATH_FUSED:
+            return None                        # wider layers only where the fused kernel takes them (else cuDNN is as fast)
         gw = _native.conv_wgrad(desc, x, gy, prec, gy_channels=cout, channels_last=cl)
         if gw is None:
             return None
@@ -181,11 +184,13 @@ class _FastWgradMixin:
             gw = gw.contiguous(memory_format=cl_fmt)
         return gw
 
+    def _fast_ok(self, x):
+        return (self.padding_mode == 'zeros' and isinstance(self.padding, tuple) and self.groups == 1
+                and all(s == 1 for s in self.stride) and all(d == 1 for d in self.dilation)
+                and x.is_cuda and torch.is_grad_enabled() and self.weight.requires_grad)
+
     def forward(self, x):
-        ok = (self.padding_mode == 'zeros' and isinstance(self.padding, tuple) and self.groups == 1
-              and all(s == 1 for s in self.stride) and all(d == 1 for d in self.dilation)
-              and x.is_cuda and torch.is_grad_enabled() and self.weight.requires_grad)
-        if not ok:
+        if not self._fast_ok(x):
             return super().forward(x)
         return _ConvWgradFn.apply(x, self.weight, self.bias, self)
 
@@ -222,18 +227,32 @@ class _NoBiasConvMixin:
     alone decides, per call, whether it leaves the bias out, and records that on the follower; the follower acts on
     the record (it never re-derives the decision from its own input, which may differ in dtype under autocast)."""
 
-    def forward(self, x):
+    def _omit_bias(self, x):
         follower = self.__dict__.get('_bias_follower')
-        if follower is not None:
-            omit = follower[0]._wants_bias(x)
-            follower[0]._bias_pending = omit
-            if omit:
-                return self._conv_forward(x, self.weight, None)
+        if follower is None:
+            return False
+        omit = follower[0]._wants_bias(x)
+        follower[0]._bias_pending = omit
+        return omit
+
+    def forward(self, x):
+        if self._omit_bias(x):
+            return self._conv_forward(x, self.weight, None)
         return super().forward(x)
 
 
 class NoBiasConv2d(_NoBiasConvMixin, nn.Conv2d):
     pass
+
+
+class NoBiasFastWgradConv2d(_NoBiasConvMixin, _FastWgradMixin, nn.Conv2d):
+    """Both: the bias add lives in the fused activation that follows, the weight gradient in hebb_conv_wgrad."""
+
+    def forward(self, x):
+        bias = None if self._omit_bias(x) else self.bias
+        if self._fast_ok(x):
+            return _ConvWgradFn.apply(x, self.weight, bias, self)
+        return self._conv_forward(x, self.weight, bias)
 
 
 class FusedBiasReluDropout(nn.ReLU):
@@ -265,7 +284,7 @@ def _slope_of(m):
     return None
 
 
-def fuse_norm_act(model: nn.Module, head_wgrad: int = 16, fuse_stats: bool = True, fuse_head_act: bool = True) -> nn.Module:
+def fuse_norm_act(model: nn.Module, head_wgrad: int = 64, fuse_stats: bool = True, fuse_head_act: bool = True) -> nn.Module:
     n_bn = n_up = n_pool = n_head = n_act = 0
     for mod in model.modules():
         if isinstance(mod, nn.Sequential):
@@ -306,8 +325,9 @@ def fuse_norm_act(model: nn.Module, head_wgrad: int = 16, fuse_stats: bool = Tru
             elif type(m) is nn.MaxPool3d and _pool_is_2x(m, 3):
                 m.__class__ = FastMaxPool3d
                 n_pool += 1
-            elif head_wgrad and type(m) in (nn.Conv2d, nn.Conv3d) and m.weight.requires_grad and m.out_channels <= int(head_wgrad):
-                m.__class__ = FastWgradConv2d if type(m) is nn.Conv2d else FastWgradConv3d
+            elif (head_wgrad and type(m) in (nn.Conv2d, nn.Conv3d, NoBiasConv2d) and m.weight.requires_grad
+                  and m.out_channels <= int(head_wgrad)):
+                m.__class__ = {nn.Conv2d: FastWgradConv2d, nn.Conv3d: FastWgradConv3d, NoBiasConv2d: NoBiasFastWgradConv2d}[type(m)]
                 n_head += 1
     model._hebb_fused = dict(bn_act=n_bn, upsample=n_up, maxpool=n_pool, head_wgrad=n_head, bias_relu_dropout=n_act)
     return model

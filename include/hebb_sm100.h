@@ -205,6 +205,12 @@ int hebb_uses_tensor_cores(const HebbDesc* d, int prec);
  * through hebb_conv_swta_step / hebb_conv_swta_step_stats, hebb/hebb.py:87-115); -1 for an invalid descriptor. */
 int hebb_layer_path(const HebbDesc* d, int prec, unsigned flags);
 
+/* Which kernels hebb_conv_wgrad(d, ...) runs on: 0 = not taken (HEBB_ESHAPE), 1 = the tcgen05 pack + update kernels,
+ * 2 = the fused kernel in weight-gradient mode (2-D, stride 1, kernel <= 3x3, Cin and Cout multiples of 16 that split
+ * into at most two (16|32) x (16|32) channel passes: x through TMA tensor maps -- NCHW or channels_last --, dL/dy read
+ * once per pass in place of the responses); -1 for an invalid descriptor. */
+int hebb_wgrad_path(const HebbDesc* d, int prec);
+
 /* Tile plan of the fused kernel (0 if the layer does not take it): {TH, TW, tile row pitch, tiles, 128-position blocks
  * per tile, x rows per tile, shared memory, TMEM columns, grid}; returns the number of fields. */
 int hebb_debug_fused_plan(const HebbDesc* d, int* out, int n);

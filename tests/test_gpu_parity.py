@@ -500,11 +500,45 @@ def test_fast_wgrad_conv_matches_stock_conv(case, fmt):
     n0 = N.launch_count()
     xf = x.clone().requires_grad_(True)
     (fast(xf) * t).sum().backward()
-    assert N.launch_count() - n0 >= 3                # pack x, pack dL/dy, contraction, finalize
+    assert N.launch_count() - n0 >= 2                # pack x, pack dL/dy, contraction, finalize -- or the fused kernel + finalize
     record('fast_wgrad_conv', f'{Cin}x{Cout}k{k}/{fmt}', gw=relerr(fast.weight.grad, ref.weight.grad))
     assert relerr(fast.weight.grad, ref.weight.grad) < 1e-4
     assert relerr(fast.bias.grad, ref.bias.grad) < 1e-5
     assert relerr(xf.grad, xr.grad) < 2e-3           # cuDNN dgrad (TF32 by default) on both sides
+
+
+@pytest.mark.parametrize('fmt', ['nchw', 'channels_last'])
+@pytest.mark.parametrize('case', [(16, 64, 3, 4, 40, 36), (64, 32, 3, 3, 24, 28), (32, 32, 3, 2, 64, 64), (16, 16, 1, 3, 20, 24),
+                                  (32, 16, 3, 2, 130, 200), (16, 64, 3, 8, 256, 256)])
+def test_wgrad_on_the_fused_kernel(case, fmt):
+    """hebb_conv_wgrad in the fused kernel's weight-gradient mode (dL/dy in place of the responses, x through TMA tensor
+    maps in either layout, channel passes for 64-channel sides) against the fp64 weight gradient; SURVEY 8f row 3."""
+    Cin, Cout, k, B, H, W = case
+    g = torch.Generator().manual_seed(Cin * 3 + Cout + H)
+    x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+    gy = torch.randn(B, Cout, H, W, generator=g).to(DEV)
+    desc = _native.make_desc(2, B, Cin, Cout, (H, W), (k, k), (1, 1), (k // 2, k // 2), (k // 2, k // 2), False)
+    assert _native.wgrad_path(desc, _native.PREC_BF16X3) == _native.PATH_FUSED
+    cl = fmt == 'channels_last'
+    xs = x.contiguous(memory_format=torch.channels_last) if cl else x
+    gs = gy.contiguous(memory_format=torch.channels_last) if cl else gy
+    n0 = _native.launch_count()
+    gw = _native.conv_wgrad(desc, xs, gs, _native.PREC_BF16X3, gy_channels=Cout, channels_last=cl)
+    passes = (Cin // (32 if Cin % 32 == 0 else 16)) * (Cout // (32 if Cout % 32 == 0 else 16))
+    assert _native.launch_count() - n0 == 2 * passes          # the fused kernel + its finalize, per channel pass
+    if B * H * W <= 1 << 16:
+        ref = torch.nn.grad.conv2d_weight(x.double(), (Cout, Cin, k, k), gy.double(), padding=k // 2)
+    else:                                                     # at size: the cuDNN fp32 gradient (TF32 off) is the cheaper reference
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, k, k), gy, padding=k // 2)
+        torch.backends.cudnn.allow_tf32 = old
+    err = relerr(gw.reshape(Cout, Cin, k, k), ref)
+    record('fused_wgrad', f'{Cin}x{Cout}k{k}@{H}x{W}/{fmt}', gw=err)
+    assert err < 1e-4
+    # accumulates into gw (+=): a second call on zeros of the same tensors gives the same result again
+    gw2 = _native.conv_wgrad(desc, xs, gs, _native.PREC_BF16X3, gy_channels=Cout, channels_last=cl)
+    assert torch.equal(gw, gw2)                               # deterministic: fixed summation order
 
 
 @pytest.mark.parametrize('x_fmt,gy_fmt', [('channels_last', 'nchw'), ('nchw', 'channels_last')])
@@ -589,7 +623,7 @@ def test_fuse_pass_keeps_network_output_and_state():
     ref = copy.deepcopy(net).to(DEV).train()
     keys = list(net.state_dict().keys())
     fuse_norm_act(net)
-    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4, 'head_wgrad': 1, 'bias_relu_dropout': 2}
+    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4, 'head_wgrad': 3, 'bias_relu_dropout': 2}
     net = net.to(DEV).train()
     x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(5)).to(DEV)
     a, b = ref(x), net(x)
