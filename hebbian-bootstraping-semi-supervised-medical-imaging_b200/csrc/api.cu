@@ -248,8 +248,8 @@ int hebb_conv_wgrad(const HebbDesc* d, const float* x, const float* grad_y, floa
   if (gy_channels < 0 || gy_channels > g.Cout) return HEBB_EARG;
   if (!aligned16(ws)) return HEBB_EALIGN;
   // few-channel layers reduced over many pixels (the back-prop head): the fused kernel with dL/dy as the responses
-  if ((gy_channels == 0 || gy_channels == g.Cout) && fused_wgrad_supported(g))
-    return fused_conv_wgrad(g, x, grad_y, grad_w, channels_last, ws, ws_bytes, (cudaStream_t)stream);
+  if (fused_wgrad_supported(g))
+    return fused_conv_wgrad(g, x, grad_y, grad_w, gy_channels, channels_last, ws, ws_bytes, (cudaStream_t)stream);
   if (!use_tc(g, prec)) return HEBB_ESHAPE;          // shapes outside the tcgen05 planner: caller's choice what to do
   if (channels_last && g.Cin <= 4 && g.taps > 1) return HEBB_ESHAPE;   // the patch-gathering pack reads NCHW only
   const int aux = (gy_channels & 0xFFFF) | ((channels_last ? 1 : 0) << 16);

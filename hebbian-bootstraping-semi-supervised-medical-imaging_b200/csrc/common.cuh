@@ -111,7 +111,7 @@ int fused_conv_step(const Geo& g, const float* x, const float* W, const float* b
 // passes of (16|32) x (16|32) channels; x and gy dense NCHW or dense channels_last; gw[Cout][Cin][taps] +=
 bool fused_wgrad_supported(const Geo& g);
 size_t fused_wgrad_workspace_bytes(const Geo& g);
-int fused_conv_wgrad(const Geo& g, const float* x, const float* gy, float* gw, int channels_last, void* ws, size_t ws_bytes,
-                     cudaStream_t st);
+int fused_conv_wgrad(const Geo& g, const float* x, const float* gy, float* gw, int gy_channels, int channels_last, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
 
 }  // namespace hebb

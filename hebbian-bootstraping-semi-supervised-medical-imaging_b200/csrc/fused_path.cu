@@ -62,6 +62,7 @@ struct FusedParams {
   // weight-gradient mode (hebb_conv_wgrad on this kernel): dL/dy takes the place of the responses -- no forward MMAs, no
   // softmax; the "epilogue" warps read gy[b][co][pixel] (element strides gy_sb / gy_sc / gy_sp) and feed the response ring
   const float* gy; long long gy_sb, gy_sc, gy_sp;
+  int gy_nc;                   // channels of this pass present in gy (< COUT: a 2-class layer padded to 16 filters; the rest read 0)
   int xcl;                     // x is channels_last: boxes [BW pixels][16 channels] through a 4-D tensor map
   int cin_tot, ci_off;         // channels of the tensor behind the map, first channel of this launch (channel passes)
   long long* prof;             // HEBB_FUSED_PROF=1: per CTA [32] cycles spent in each bounded wait (index = code - 16) + totals
@@ -528,7 +529,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           const long long pix = (long long)(h0 + r_) * p.oW + (w0 + c_);
           if (valid) {
             const float* gp = p.gy + (long long)b * p.gy_sb + pix * p.gy_sp;
-            if (p.gy_sc == 1) {
+            if (p.gy_sc == 1 && p.gy_nc == COUT) {
 #pragma unroll
               for (int i4 = 0; i4 < COUT; i4 += 4) {
                 const float4 g4 = __ldg(reinterpret_cast<const float4*>(gp + i4));
@@ -536,7 +537,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < COUT; ++i) { f[i] = __ldg(gp); gp += p.gy_sc; }
+              for (int i = 0; i < COUT; ++i) { f[i] = i < p.gy_nc ? __ldg(gp) : 0.f; gp += p.gy_sc; }
             }
           } else {
 #pragma unroll
@@ -1080,10 +1081,11 @@ size_t fused_wgrad_workspace_bytes(const Geo& g) {
   return (fused_wgrad_split(g, &sub, &ci, &co) && fused_plan(sub, &P)) ? P.total : 0;
 }
 
-int fused_conv_wgrad(const Geo& g, const float* x, const float* gy, float* gw, int channels_last, void* ws, size_t ws_bytes,
-                     cudaStream_t st) {
+int fused_conv_wgrad(const Geo& g, const float* x, const float* gy, float* gw, int gy_channels, int channels_last, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
   Geo sub; int CI, CO; FPlan P;
   if (!fused_wgrad_split(g, &sub, &CI, &CO) || !fused_plan(sub, &P) || P.gather) return HEBB_ESHAPE;
+  const int gyC = gy_channels > 0 ? gy_channels : g.Cout;      // channels stored in gy; filters gyC.. get a zero gradient
   if (!ws || ws_bytes < P.total) return HEBB_EWS;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return HEBB_EALIGN;
   EncodeTiledFn enc = encode_fn();
@@ -1124,13 +1126,14 @@ int fused_conv_wgrad(const Geo& g, const float* x, const float* gy, float* gw, i
   f.off_r = P.off_r; f.off_stage = P.off_stage; f.off_w = P.off_w; f.off_misc = P.off_misc; f.w_bytes = 0;
   f.stage_bytes = P.stage_bytes; f.tmem_cols = P.tmem_cols;
   f.xcl = channels_last ? 1 : 0; f.cin_tot = g.Cin;
-  if (channels_last) { f.gy_sb = g.outS * g.Cout; f.gy_sc = 1; f.gy_sp = g.Cout; }
-  else { f.gy_sb = g.outS * g.Cout; f.gy_sc = g.outS; f.gy_sp = 1; }
+  if (channels_last) { f.gy_sb = g.outS * gyC; f.gy_sc = 1; f.gy_sp = gyC; }
+  else { f.gy_sb = g.outS * gyC; f.gy_sc = g.outS; f.gy_sp = 1; }
   const int n_out = P.etaps * CI * CO;
   for (int co0 = 0; co0 < g.Cout; co0 += CO)
     for (int ci0 = 0; ci0 < g.Cin; ci0 += CI) {
       HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, P.o_wp - P.o_rsum, st));      // sum of gy, error word
       f.gy = gy + (long long)co0 * f.gy_sc;
+      f.gy_nc = gyC - co0 < CO ? (gyC - co0 > 0 ? gyC - co0 : 0) : CO;
       f.ci_off = ci0;
 #define HEBB_FUSED_WG(CIv, COv)                                                                                          \
   do {                                                                                                                    \

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence for profiles/: the driver's own test command, smoke, both bench arms (the default line carries the C4
-# sub-lines, the plain drop-in, the GPU-eager reference and the element-wise kernels), C1 with and without CUDA-graph replay,
+# sub-lines, the plain drop-in, the GPU-eager reference and the element-wise kernels), the eagerly launched variants, C1, C5, C6,
 # the ncu launch list and DRAM-traffic capture of the bench command, full ncu captures of the fused kernel and of the two
 # tcgen05 kernels on a tensor-bound 3-D layer.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
@@ -11,21 +11,24 @@ python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 python bench.py --layers-out gpurun_out/layers_c2_bf16x3.json > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench rc=$?"
 HEBB_FUSED=0 python bench.py --no-cpu-baseline --no-extras --layers-out gpurun_out/layers_c2_bf16x3_nofused.json > gpurun_out/bench_c2_nofused.json 2> gpurun_out/bench_c2_nofused.err; echo "bench nofused rc=$?"
-python bench.py --workload c1 --steps 50 --warmup 5 > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err; echo "c1 rc=$?"
-python bench.py --workload c1 --steps 50 --warmup 5 --no-cpu-baseline --graph > gpurun_out/bench_c1_graph.json 2> gpurun_out/bench_c1_graph.err; echo "c1 graph rc=$?"
+python bench.py --no-cpu-baseline --no-extras --no-layer-profile --no-graph --no-fused-adam --head-wgrad 16 > gpurun_out/bench_c2_eager.json 2> gpurun_out/bench_c2_eager.err; echo "bench eager (no graph, for-each Adam, cuDNN head wgrad) rc=$?"
+python bench.py --workload c1 --steps 50 --warmup 5 > gpurun_out/bench_c1_graph.json 2> gpurun_out/bench_c1_graph.err; echo "c1 (graph) rc=$?"
+python bench.py --workload c1 --steps 50 --warmup 5 --no-cpu-baseline --no-graph --no-fused-adam > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err; echo "c1 eager rc=$?"
+python bench.py --workload c6 --steps 5 --warmup 3 --no-cpu-baseline --no-layer-profile > gpurun_out/bench_c6.json 2> gpurun_out/bench_c6.err; echo "c6 rc=$?"
 python bench.py --workload c5 --steps 10 --warmup 3 --no-layer-profile > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "c5 rc=$?"
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-layer-profile --no-extras"
+# (the profiler passes launch the step eagerly: the same kernels as the replayed graph, a known launch count per step)
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-layer-profile --no-extras --no-graph"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c2.csv $CMD > gpurun_out/ncu_ll.log 2>&1; echo "launchlist rc=$?"
 # DRAM traffic of our kernels over the whole run (7 steps: 3 warm-up, 2 timed, 2 end-to-end)
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'swta|pack_x|pack_w|tc_finalize|wnorm_kernel|fused_small|fused_prep' --csv --log-file gpurun_out/traffic_c2.csv $CMD > gpurun_out/ncu_tr.log 2>&1; echo "traffic rc=$?"
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'swta|pack_x|pack_w|tc_finalize|wnorm_kernel|fused_small|fused_prep|fused_wgrad' --csv --log-file gpurun_out/traffic_c2.csv $CMD > gpurun_out/ncu_tr.log 2>&1; echo "traffic rc=$?"
 # the fused small-channel kernel: 16->16 3x3 @256x256, batch 64
 python scripts/fused_breakdown.py 16 16 256 3 > gpurun_out/pl_fused.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:fused_small_kernel -s 2 -c 1 -f -o gpurun_out/r2_fused_16x16 python scripts/fused_breakdown.py 16 16 256 3 > gpurun_out/ncu_fused.log 2>&1; echo "ncu fused rc=$?"; cat gpurun_out/pl_fused.log | cut -c1-80
 # tensor-bound layer of the 3-D network: 128->128 3x3x3 @48x48x40, batch 8
 python scripts/profile_layer.py 128 128 3 48 40 8 bf16 48 > gpurun_out/pl_bf16.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'dw_swta|fwd_swta' -s 6 -c 2 -f -o gpurun_out/r2_c4_128x128_bf16 python scripts/profile_layer.py 128 128 3 48 40 8 bf16 48 > gpurun_out/ncu_bf16.log 2>&1; echo "ncu c4 rc=$?"; cat gpurun_out/pl_bf16.log
-for f in gpurun_out/bench_c2.json gpurun_out/bench_c2_nofused.json gpurun_out/bench_c1.json gpurun_out/bench_c1_graph.json gpurun_out/bench_c5.json gpurun_out/bench_ref.json; do
+for f in gpurun_out/bench_c2.json gpurun_out/bench_c2_nofused.json gpurun_out/bench_c2_eager.json gpurun_out/bench_c6.json gpurun_out/bench_c1.json gpurun_out/bench_c1_graph.json gpurun_out/bench_c5.json gpurun_out/bench_ref.json; do
 python - "$f" <<'PY'
 import json, sys
 try:

@@ -541,6 +541,24 @@ def test_wgrad_on_the_fused_kernel(case, fmt):
     assert torch.equal(gw, gw2)                               # deterministic: fixed summation order
 
 
+@pytest.mark.parametrize('fmt', ['nchw', 'channels_last'])
+def test_wgrad_on_the_fused_kernel_with_fewer_gy_channels_than_filters(fmt):
+    """The 2-class output layer: descriptor padded to 16 filters, dL/dy holds 2 channels; rows 2..15 of grad_w stay 0."""
+    B, Cin, H, W = 3, 32, 72, 64
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+    gy = torch.randn(B, 2, H, W, generator=g).to(DEV)
+    desc = _native.make_desc(2, B, Cin, 16, (H, W), (3, 3), (1, 1), (1, 1), (1, 1), False)
+    assert _native.wgrad_path(desc, _native.PREC_BF16X3) == _native.PATH_FUSED
+    cl = fmt == 'channels_last'
+    xs = x.contiguous(memory_format=torch.channels_last) if cl else x
+    gs = gy.contiguous(memory_format=torch.channels_last) if cl else gy
+    gw = _native.conv_wgrad(desc, xs, gs, _native.PREC_BF16X3, gy_channels=2, channels_last=cl)
+    ref = torch.nn.grad.conv2d_weight(x.double(), (2, Cin, 3, 3), gy.double(), padding=1)
+    assert relerr(gw[:2].reshape(2, Cin, 3, 3), ref) < 1e-4
+    assert float(gw[2:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize('x_fmt,gy_fmt', [('channels_last', 'nchw'), ('nchw', 'channels_last')])
 def test_fast_wgrad_mixed_layouts_copy_the_smaller_tensor(x_fmt, gy_fmt):
     """The 2-class output layer of the benchmark head: saved input channels_last, dL/dy NCHW (from the softmax
