@@ -137,6 +137,10 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   constexpr int NSL = CIN / 16;            // 16-channel slabs (K steps of the forward)
   constexpr int COPIES = 128 / (2 * CIN);  // kh copies of the x tile in the M = 128 rows of an update instruction
   constexpr int FCOLS = 2 * COUT;          // forward accumulator: [x w_hi (+ x_lo w_hi) | x_hi w_lo]
+  // converter warps own whole stages in turn instead of sharing every stage's pixels (see the converter): in weight-
+  // gradient mode and in the plain forward + update kernels (32->16 @256^2 0.415 -> 0.374 ms, 32->32 @128^2 0.194 -> 0.181,
+  // 16->32 @128^2 0.105 -> 0.101); the patch-gather variant keeps its own loop
+  constexpr bool OWN = WG || NCW == 2;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -193,8 +197,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   }
   fence_proxy_async();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, NCW); }
-    for (int i = 0; i < kMaxRows; ++i) { mbar_init(xr_full + 8 * i, NCW * NSL); mbar_init(xr_empty + 8 * i, 1); }
+    // (weight-gradient mode: one converter warp per stage, see the converter)
+    for (int i = 0; i < p.NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, OWN ? 1 : NCW); }
+    for (int i = 0; i < kMaxRows; ++i) { mbar_init(xr_full + 8 * i, OWN ? NSL : NCW * NSL); mbar_init(xr_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tf_full + 8 * i, 1); mbar_init(tf_empty + 8 * i, 4); }
     for (int i = 0; i < kRSlots; ++i) { mbar_init(r_full + 8 * i, 4); mbar_init(r_empty + 8 * i, 1); }
     mbar_init(w_full, 1); mbar_init(done, 1);
@@ -373,6 +378,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const int conv_ntiles = p.ntiles;
     int s = 0; uint32_t ph = 0;
     int it = 0;
+    constexpr int CSTEP = OWN ? 32 : 32 * NCW;
+    const int t0 = OWN ? lane : t;
+    int own = 0;
     if constexpr (CIN == 32 && KS == 1 && NCW == 4) {
       if (p.gather) {
         // ---- patch gather (first layers: 1-4 real channels, gk x gk kernel): image row r of the 1x1 layer holds, per
@@ -445,29 +453,83 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         goto converter_done;
       }
     }
+    // Weight-gradient mode: a converter warp owns WHOLE stages in turn (stage n belongs to warp n mod NCW) instead of a
+    // share of every stage's pixels -- with nothing but the update behind it the converter is the critical path, and the
+    // per-stage fixed cost (two barrier polls, the proxy fence, two arrives: ~300 of 450 cycles for a 68-pixel row) is
+    // then paid by four warps in parallel
     for (int tile = blockIdx.x; tile < conv_ntiles; tile += gridDim.x, ++it) {
       for (int r = 0; r < p.XROWS; ++r)
         for (int cg = 0; cg < NSL; ++cg) {
+          if constexpr (OWN) {
+            const bool mine = own == warp - 3;
+            own = (own + 1 == NCW) ? 0 : own + 1;
+            if (!mine) {
+              if (++s == p.NST) { s = 0; ph ^= 1; }
+              continue;
+            }
+          }
           FWAIT(st_full + 8 * s, ph, 25);
-          if (cg == 0) FWAIT(xr_empty + 8 * r, (it & 1) ^ 1, 26);      // the previous tile no longer reads this row
+          if (OWN || cg == 0) FWAIT(xr_empty + 8 * r, (it & 1) ^ 1, 26);      // the previous tile no longer reads this row
           if (WG && p.xcl) {
             // channels_last box: [pixel][16 channels] fp32; four lanes share a pixel (one float4 = 4 channels each)
             const float4* st4 = reinterpret_cast<const float4*>(smem + p.off_stage + s * p.stage_bytes) + (p.padl - p.pW) * 4;
-            for (int idx = t; idx < p.pitch * 4; idx += 32 * NCW) {
-              const int c = idx >> 2, j = idx & 3;
-              const float4 v = st4[idx];
-              uint32_t h0, h1, l0, l1;
-              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v.y), "f"(v.x));
-              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v.w), "f"(v.z));
-              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l0) : "f"(v.y - __uint_as_float(h0 & 0xffff0000u)), "f"(v.x - __uint_as_float(h0 << 16)));
-              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l1) : "f"(v.w - __uint_as_float(h1 & 0xffff0000u)), "f"(v.z - __uint_as_float(h1 << 16)));
-              const uint32_t row = xb + (uint32_t)(r * p.pitch + c) * XB;
-              st_shared_v2(swz<XCH>(row, 2 * cg + (j >> 1)) + (uint32_t)(j & 1) * 8u, h0, h1);
-              st_shared_v2(swz<XCH>(row, XCH / 2 + 2 * cg + (j >> 1)) + (uint32_t)(j & 1) * 8u, l0, l1);
+            // four pixels-quarters per lane and round: the loads first (the shared-memory stores are ordered asm
+            // statements, so the compiler cannot overlap one item's load with the previous item's stores by itself)
+            const int n_items = p.pitch * 4;
+            for (int base = t0; base < n_items; base += 4 * CSTEP) {
+              float4 v4[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * CSTEP;
+                v4[u] = idx < n_items ? st4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * CSTEP;
+                if (idx < n_items) {
+                  const int c = idx >> 2, j = idx & 3;
+                  const float4 v = v4[u];
+                  uint32_t h0, h1, l0, l1;
+                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v.y), "f"(v.x));
+                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v.w), "f"(v.z));
+                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l0) : "f"(v.y - __uint_as_float(h0 & 0xffff0000u)), "f"(v.x - __uint_as_float(h0 << 16)));
+                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l1) : "f"(v.w - __uint_as_float(h1 & 0xffff0000u)), "f"(v.z - __uint_as_float(h1 << 16)));
+                  const uint32_t row = xb + (uint32_t)(r * p.pitch + c) * XB;
+                  st_shared_v2(swz<XCH>(row, 2 * cg + (j >> 1)) + (uint32_t)(j & 1) * 8u, h0, h1);
+                  st_shared_v2(swz<XCH>(row, XCH / 2 + 2 * cg + (j >> 1)) + (uint32_t)(j & 1) * 8u, l0, l1);
+                }
+              }
             }
           }
           const float* st = reinterpret_cast<const float*>(smem + p.off_stage + s * p.stage_bytes) + (p.padl - p.pW);
-          for (int c = t; c < (((p.dbg & 8) || (WG && p.xcl)) ? 0 : p.pitch); c += 32 * NCW) {
+          if constexpr (WG) {
+            if (!p.xcl) {
+              // NCHW box, two pixels per lane and round (loads of both first, see above)
+              for (int c = t0; c < p.pitch; c += 2 * CSTEP) {
+                float v[2][16];
+                const bool two = c + CSTEP < p.pitch;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { v[0][i] = st[i * p.BW + c]; v[1][i] = two ? st[i * p.BW + c + CSTEP] : 0.f; }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  if (u == 1 && !two) break;
+                  uint32_t hp[8], lp[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp[i]) : "f"(v[u][2 * i + 1]), "f"(v[u][2 * i]));
+                    const float h0 = __uint_as_float(hp[i] << 16), h1 = __uint_as_float(hp[i] & 0xffff0000u);
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp[i]) : "f"(v[u][2 * i + 1] - h1), "f"(v[u][2 * i] - h0));
+                  }
+                  const uint32_t row = xb + (uint32_t)(r * p.pitch + c + u * CSTEP) * XB;
+                  st_shared_v4(swz<XCH>(row, 2 * cg), hp[0], hp[1], hp[2], hp[3]);
+                  st_shared_v4(swz<XCH>(row, 2 * cg + 1), hp[4], hp[5], hp[6], hp[7]);
+                  st_shared_v4(swz<XCH>(row, XCH / 2 + 2 * cg), lp[0], lp[1], lp[2], lp[3]);
+                  st_shared_v4(swz<XCH>(row, XCH / 2 + 2 * cg + 1), lp[4], lp[5], lp[6], lp[7]);
+                }
+              }
+            }
+          }
+          for (int c = t0; c < (((p.dbg & 8) || WG) ? 0 : p.pitch); c += CSTEP) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = st[i * p.BW + c];
@@ -1129,27 +1191,45 @@ int fused_conv_wgrad(const Geo& g, const float* x, const float* gy, float* gw, i
   if (channels_last) { f.gy_sb = g.outS * gyC; f.gy_sc = 1; f.gy_sp = gyC; }
   else { f.gy_sb = g.outS * gyC; f.gy_sc = g.outS; f.gy_sp = 1; }
   const int n_out = P.etaps * CI * CO;
+  // converter warps of the weight-gradient mode: 6 (measured on the head's layers, channels_last: 2 -> 4 -> 6 warps with whole-
+  // stage ownership: 2.31 -> 1.58 -> 1.50 ms for the three of them); HEBB_FUSED_WG_NCW=4 selects the profiled 4-warp build
+  static const int wg_ncw = [] { const char* e = getenv("HEBB_FUSED_WG_NCW"); return e ? atoi(e) : 6; }();
+  static const int wprof = [] { const char* e = getenv("HEBB_FUSED_PROF"); return (e && e[0] == '1') ? 1 : 0; }();
+  f.prof = (wprof && CI == 32 && P.ek == 3) ? reinterpret_cast<long long*>(base + P.o_prof) : nullptr;
+  if (f.prof) { g_last_prof = f.prof; g_last_prof_n = P.grid * 15 * 11; }
   for (int co0 = 0; co0 < g.Cout; co0 += CO)
     for (int ci0 = 0; ci0 < g.Cin; ci0 += CI) {
       HEBB_CUDA_TRY(cudaMemsetAsync(base + P.o_rsum, 0, P.o_wp - P.o_rsum, st));      // sum of gy, error word
       f.gy = gy + (long long)co0 * f.gy_sc;
       f.gy_nc = gyC - co0 < CO ? (gyC - co0 > 0 ? gyC - co0 : 0) : CO;
       f.ci_off = ci0;
+#define HEBB_FUSED_WG2(CIv, COv, Kv, NCv)                                                                                \
+  do {                                                                                                                    \
+    HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CIv, COv, Kv, false, NCv, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
+    fused_small_kernel<CIv, COv, Kv, false, NCv, true><<<P.grid, 32 * (3 + NCv + 8), kSmemLimitF, st>>>(tm, f);           \
+  } while (0)
 #define HEBB_FUSED_WG(CIv, COv)                                                                                          \
   do {                                                                                                                    \
     if (P.ek == 3) {                                                                                                      \
-      HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CIv, COv, 3, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
-      fused_small_kernel<CIv, COv, 3, false, 2, true><<<P.grid, 32 * 13, kSmemLimitF, st>>>(tm, f);                             \
+      if (wg_ncw == 4) HEBB_FUSED_WG2(CIv, COv, 3, 4);                                                                    \
+      else HEBB_FUSED_WG2(CIv, COv, 3, 6);                                                                                \
     } else {                                                                                                              \
-      HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<CIv, COv, 1, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF)); \
-      fused_small_kernel<CIv, COv, 1, false, 2, true><<<P.grid, 32 * 13, kSmemLimitF, st>>>(tm, f);                             \
+      HEBB_FUSED_WG2(CIv, COv, 1, 2);                                                                                     \
     }                                                                                                                     \
   } while (0)
-      if (CI == 16 && CO == 16) HEBB_FUSED_WG(16, 16);
+      if (f.prof && CO == 16) {          // (the wait-cycle table exists for the 4-converter-warp layout)
+        HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<32, 16, 3, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF));
+        fused_small_kernel<32, 16, 3, true, 4, true><<<P.grid, 32 * 15, kSmemLimitF, st>>>(tm, f);
+      } else if (f.prof) {
+        HEBB_CUDA_TRY(cudaFuncSetAttribute(fused_small_kernel<32, 32, 3, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimitF));
+        fused_small_kernel<32, 32, 3, true, 4, true><<<P.grid, 32 * 15, kSmemLimitF, st>>>(tm, f);
+      }
+      else if (CI == 16 && CO == 16) HEBB_FUSED_WG(16, 16);
       else if (CI == 16 && CO == 32) HEBB_FUSED_WG(16, 32);
       else if (CI == 32 && CO == 16) HEBB_FUSED_WG(32, 16);
       else HEBB_FUSED_WG(32, 32);
 #undef HEBB_FUSED_WG
+#undef HEBB_FUSED_WG2
       HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
       fused_wgrad_finalize_kernel<<<(unsigned)cdiv(n_out, 32), 256, 0, st>>>(f.hpart, gw, P.grid * 2, P.etaps, CI, CO, g.Cin, ci0, co0);
       HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
