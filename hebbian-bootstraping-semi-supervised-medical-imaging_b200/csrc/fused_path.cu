@@ -137,10 +137,6 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   constexpr int NSL = CIN / 16;            // 16-channel slabs (K steps of the forward)
   constexpr int COPIES = 128 / (2 * CIN);  // kh copies of the x tile in the M = 128 rows of an update instruction
   constexpr int FCOLS = 2 * COUT;          // forward accumulator: [x w_hi (+ x_lo w_hi) | x_hi w_lo]
-  // converter warps own whole stages in turn instead of sharing every stage's pixels (see the converter): in weight-
-  // gradient mode and in the plain forward + update kernels (32->16 @256^2 0.415 -> 0.374 ms, 32->32 @128^2 0.194 -> 0.181,
-  // 16->32 @128^2 0.105 -> 0.101); the patch-gather variant keeps its own loop
-  constexpr bool OWN = WG || NCW == 2;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -197,9 +193,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   }
   fence_proxy_async();
   if (threadIdx.x == 0) {
-    // (weight-gradient mode: one converter warp per stage, see the converter)
-    for (int i = 0; i < p.NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, OWN ? 1 : NCW); }
-    for (int i = 0; i < kMaxRows; ++i) { mbar_init(xr_full + 8 * i, OWN ? NSL : NCW * NSL); mbar_init(xr_empty + 8 * i, 1); }
+    // (one converter warp per stage, see the converter; the patch gather releases a staged input row three times)
+    for (int i = 0; i < p.NST; ++i) { mbar_init(st_full + 8 * i, 1); mbar_init(st_empty + 8 * i, p.gather ? 3 : 1); }
+    for (int i = 0; i < kMaxRows; ++i) { mbar_init(xr_full + 8 * i, NSL); mbar_init(xr_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tf_full + 8 * i, 1); mbar_init(tf_empty + 8 * i, 4); }
     for (int i = 0; i < kRSlots; ++i) { mbar_init(r_full + 8 * i, 4); mbar_init(r_empty + 8 * i, 1); }
     mbar_init(w_full, 1); mbar_init(done, 1);
@@ -374,36 +370,43 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
   } else if (warp < 3 + NCW) {
     // ===================== converter (warps 3 .. 2+NCW) =====================
-    const int t = threadIdx.x - 96;
     const int conv_ntiles = p.ntiles;
     int s = 0; uint32_t ph = 0;
     int it = 0;
-    constexpr int CSTEP = OWN ? 32 : 32 * NCW;
-    const int t0 = OWN ? lane : t;
+    constexpr int CSTEP = 32;
+    const int t0 = lane;
     int own = 0;
     if constexpr (CIN == 32 && KS == 1 && NCW == 4) {
       if (p.gather) {
         // ---- patch gather (first layers: 1-4 real channels, gk x gk kernel): image row r of the 1x1 layer holds, per
         // output pixel, the gcin*gk*gk patch values (zero-padded to 32 pseudo-channels) as [hi 32 | lo 32] ----
-        // staged input rows: `cons` = rows waited for so far (stage cs, phase cph), `rel` = rows released (stage rs);
-        // s0 = stage of the first input row under the current image row.  All indices advance incrementally: a
-        // run-time modulo per element made this loop 500 instructions long.
-        int cons = 0, cs = 0, rel = 0, rs = 0, s0 = 0;
-        uint32_t cph = 0;
+        // A converter warp owns whole image rows in turn (global row n belongs to warp n mod NCW): the per-row fixed cost
+        // (barrier polls, proxy fence, arrives) is paid by the four warps in parallel instead of by each of them for a
+        // quarter of the pixels.  Staged input row j serves image rows j-2 .. j: its st_empty barrier counts 3 arrivals,
+        // and the rows at a tile's edge make up for the neighbours they do not have.
+        const int cw = warp - 3;
         const int off = p.padl - p.pW;
+        int grow = 0;
+        int cons = 0, cs = 0;                // staged input rows observed so far, and the ring slot of the next one
+        uint32_t cph = 0;
+        int s0 = 0;                          // ring slot of the first input row under the current image row
         for (int tile = blockIdx.x; tile < conv_ntiles; tile += gridDim.x, ++it) {
           const int base = it * p.srows;
-          for (int r = 0; r < p.XROWS; ++r) {
+          for (int r = 0; r < p.XROWS; ++r, ++grow) {
+            // every warp observes every barrier phase in order (see the plain converter below); the owner converts
             for (; cons <= base + r + 2; ++cons) {
               FWAIT(st_full + 8 * cs, cph, 25);
               if (++cs == p.NST) { cs = 0; cph ^= 1u; }
             }
             FWAIT(xr_empty + 8 * r, (it & 1) ^ 1, 26);
-            const int s1 = (s0 + 1 == p.NST) ? 0 : s0 + 1, s2 = (s1 + 1 == p.NST) ? 0 : s1 + 1;
-            const float* row0 = reinterpret_cast<const float*>(smem + p.off_stage + s0 * p.stage_bytes) + off;
-            const float* row1 = reinterpret_cast<const float*>(smem + p.off_stage + s1 * p.stage_bytes) + off;
-            const float* row2 = reinterpret_cast<const float*>(smem + p.off_stage + s2 * p.stage_bytes) + off;
-            for (int c = t; c < ((p.dbg & 8) ? 0 : p.pitch); c += 32 * NCW) {
+            int sl[3];
+            sl[0] = s0; sl[1] = (s0 + 1 == p.NST) ? 0 : s0 + 1; sl[2] = (sl[1] + 1 == p.NST) ? 0 : sl[1] + 1;
+            s0 = sl[1];
+            if ((grow & (NCW - 1)) != cw) continue;
+            const float* row0 = reinterpret_cast<const float*>(smem + p.off_stage + sl[0] * p.stage_bytes) + off;
+            const float* row1 = reinterpret_cast<const float*>(smem + p.off_stage + sl[1] * p.stage_bytes) + off;
+            const float* row2 = reinterpret_cast<const float*>(smem + p.off_stage + sl[2] * p.stage_bytes) + off;
+            for (int c = lane; c < ((p.dbg & 8) ? 0 : p.pitch); c += 32) {
               float vv[32];                      // pseudo-channel ci*9 + kh*3 + kw; zero beyond the real channels
 #pragma unroll
               for (int i = 27; i < 32; ++i) vv[i] = 0.f;
@@ -438,29 +441,31 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             __syncwarp();
             if (lane == 0) {
               for (int a = 0; a < NSL; ++a) mbar_arrive(xr_full + 8 * r);
-              mbar_arrive(st_empty + 8 * rs);               // input row base + r is no longer needed
+              const int top = r == 0 ? 1 : 0, bot = r == p.XROWS - 1 ? 1 : 0;
+              for (int a = 0; a < 1 + 2 * top; ++a) mbar_arrive(st_empty + 8 * sl[0]);
+              for (int a = 0; a < 1 + top + bot; ++a) mbar_arrive(st_empty + 8 * sl[1]);
+              for (int a = 0; a < 1 + 2 * bot; ++a) mbar_arrive(st_empty + 8 * sl[2]);
             }
-            ++rel;
-            if (++rs == p.NST) rs = 0;
-            s0 = s1;
           }
-          for (; rel < base + p.srows; ++rel) {             // the trailing gk-1 input rows of the tile
-            if (lane == 0) mbar_arrive(st_empty + 8 * rs);
-            if (++rs == p.NST) rs = 0;
-            s0 = (s0 + 1 == p.NST) ? 0 : s0 + 1;
-          }
+          for (int j = 0; j < p.srows - p.XROWS; ++j) s0 = (s0 + 1 == p.NST) ? 0 : s0 + 1;      // the trailing gk-1 input rows
         }
         goto converter_done;
       }
     }
-    // Weight-gradient mode: a converter warp owns WHOLE stages in turn (stage n belongs to warp n mod NCW) instead of a
-    // share of every stage's pixels -- with nothing but the update behind it the converter is the critical path, and the
-    // per-stage fixed cost (two barrier polls, the proxy fence, two arrives: ~300 of 450 cycles for a 68-pixel row) is
-    // then paid by four warps in parallel
+    // A converter warp owns WHOLE stages in turn (stage n belongs to warp n mod NCW) instead of a share of every stage's
+    // pixels: the per-stage fixed cost (two barrier polls, the proxy fence, two arrives: ~300 of 450 cycles for a 68-pixel
+    // row) is then paid by the warps in parallel.  In weight-gradient mode, where nothing but the update runs behind it,
+    // the converter is the critical path (six warps: 2.31 -> 1.50 ms for the 2-D head's three layers); the forward +
+    // update kernels gained 2-10 % (32->16 @256^2 0.415 -> 0.374 ms, 32->32 @128^2 0.194 -> 0.181, 16->32 0.105 -> 0.101)
     for (int tile = blockIdx.x; tile < conv_ntiles; tile += gridDim.x, ++it) {
       for (int r = 0; r < p.XROWS; ++r)
         for (int cg = 0; cg < NSL; ++cg) {
-          if constexpr (OWN) {
+          // EVERY warp observes every barrier phase in order (a parity wait cannot tell a phase from the one two
+          // completions earlier: a warp that skipped ahead to its own stage could pass on a stale phase); only the
+          // conversion, the proxy fence and the arrives belong to the owner
+          FWAIT(st_full + 8 * s, ph, 25);
+          if (cg == 0) FWAIT(xr_empty + 8 * r, (it & 1) ^ 1, 26);      // the previous tile no longer reads this row
+          {
             const bool mine = own == warp - 3;
             own = (own + 1 == NCW) ? 0 : own + 1;
             if (!mine) {
@@ -468,8 +473,6 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
               continue;
             }
           }
-          FWAIT(st_full + 8 * s, ph, 25);
-          if (OWN || cg == 0) FWAIT(xr_empty + 8 * r, (it & 1) ^ 1, 26);      // the previous tile no longer reads this row
           if (WG && p.xcl) {
             // channels_last box: [pixel][16 channels] fp32; four lanes share a pixel (one float4 = 4 channels each)
             const float4* st4 = reinterpret_cast<const float4*>(smem + p.off_stage + s * p.stage_bytes) + (p.padl - p.pW) * 4;

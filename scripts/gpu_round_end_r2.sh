@@ -28,6 +28,9 @@ ncu --set full --clock-control none --import-source on -k regex:fused_small_kern
 # tensor-bound layer of the 3-D network: 128->128 3x3x3 @48x48x40, batch 8
 python scripts/profile_layer.py 128 128 3 48 40 8 bf16 48 > gpurun_out/pl_bf16.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'dw_swta|fwd_swta' -s 6 -c 2 -f -o gpurun_out/r2_c4_128x128_bf16 python scripts/profile_layer.py 128 128 3 48 40 8 bf16 48 > gpurun_out/ncu_bf16.log 2>&1; echo "ncu c4 rc=$?"; cat gpurun_out/pl_bf16.log
+# hebb_conv_wgrad on the fused kernel against cuDNN on the 2-D head's layers, and its wait-cycle table (4-converter-warp build)
+python scripts/wgrad_bench.py 64 > gpurun_out/wgrad_bench.txt 2>&1; echo "wgrad bench rc=$?"; tail -5 gpurun_out/wgrad_bench.txt | cut -c1-160
+HEBB_FUSED_PROF=1 HEBB_FUSED_WG_NCW=4 python scripts/wgrad_breakdown.py 32 32 nhwc > gpurun_out/wgrad_prof.txt 2>&1; echo "wgrad prof rc=$?"
 for f in gpurun_out/bench_c2.json gpurun_out/bench_c2_nofused.json gpurun_out/bench_c2_eager.json gpurun_out/bench_c6.json gpurun_out/bench_c1.json gpurun_out/bench_c1_graph.json gpurun_out/bench_c5.json gpurun_out/bench_ref.json; do
 python - "$f" <<'PY'
 import json, sys

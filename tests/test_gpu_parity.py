@@ -509,7 +509,10 @@ def test_fast_wgrad_conv_matches_stock_conv(case, fmt):
 
 @pytest.mark.parametrize('fmt', ['nchw', 'channels_last'])
 @pytest.mark.parametrize('case', [(16, 64, 3, 4, 40, 36), (64, 32, 3, 3, 24, 28), (32, 32, 3, 2, 64, 64), (16, 16, 1, 3, 20, 24),
-                                  (32, 16, 3, 2, 130, 200), (16, 64, 3, 8, 256, 256)])
+                                  (32, 16, 3, 2, 130, 200), (16, 64, 3, 8, 256, 256),
+                                  # the fine-tuning network's layers (many tiles per CTA, short staging rings, 1x1 kernels)
+                                  (32, 64, 3, 8, 128, 128), (64, 32, 3, 8, 128, 128), (32, 16, 1, 16, 128, 128), (16, 32, 3, 16, 128, 128),
+                                  (32, 32, 3, 16, 128, 128), (64, 32, 1, 8, 128, 128)])
 def test_wgrad_on_the_fused_kernel(case, fmt):
     """hebb_conv_wgrad in the fused kernel's weight-gradient mode (dL/dy in place of the responses, x through TMA tensor
     maps in either layout, channel passes for 64-channel sides) against the fp64 weight gradient; SURVEY 8f row 3."""
@@ -518,7 +521,9 @@ def test_wgrad_on_the_fused_kernel(case, fmt):
     x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
     gy = torch.randn(B, Cout, H, W, generator=g).to(DEV)
     desc = _native.make_desc(2, B, Cin, Cout, (H, W), (k, k), (1, 1), (k // 2, k // 2), (k // 2, k // 2), False)
-    assert _native.wgrad_path(desc, _native.PREC_BF16X3) == _native.PATH_FUSED
+    if _native.wgrad_path(desc, _native.PREC_BF16X3) != _native.PATH_FUSED:
+        assert B >= 8 and H <= 128, 'the head-sized layers must take the fused kernel'
+        pytest.skip('the planner keeps this layer on the pack + update kernels')
     cl = fmt == 'channels_last'
     xs = x.contiguous(memory_format=torch.channels_last) if cl else x
     gs = gy.contiguous(memory_format=torch.channels_last) if cl else gy
