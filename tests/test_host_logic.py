@@ -281,3 +281,48 @@ def test_reference_checkpoint_interchange():
         twin = makehebbian(Net(), exclude=ck['excluded_layers'], hebb_params=hp)
     twin.load_state_dict(net.state_dict())
     assert all(torch.equal(a, b) for a, b in zip(twin.state_dict().values(), net.state_dict().values()))
+
+
+def test_fused_head_bias_is_added_exactly_once_whoever_takes_it():
+    """hebb.fused: the convolution alone decides whether it leaves its bias to the fused activation that follows and
+    records that per call; the follower acts on the record (round-1 advisor finding: the two used to re-derive the
+    decision from different tensors, and a disagreement dropped the bias silently)."""
+    import copy
+    from hebb.fused import fuse_norm_act, FusedBiasReluDropout, NoBiasFastWgradConv2d
+    torch.manual_seed(0)
+    net = nn.Module()
+    net.head = nn.Sequential(nn.Conv2d(4, 8, 3, padding=1), nn.ReLU(), nn.Dropout(0.0), nn.Conv2d(8, 2, 1))
+    ref = copy.deepcopy(net.head)
+    keys = list(net.state_dict().keys())
+    fuse_norm_act(net)
+    assert list(net.state_dict().keys()) == keys
+    conv, act = net.head[0], net.head[1]
+    assert isinstance(conv, NoBiasFastWgradConv2d) and isinstance(act, FusedBiasReluDropout)
+    x = torch.randn(2, 4, 6, 6)
+    net.train(); ref.train()
+    # CPU input: the convolution keeps its bias, the follower takes the stock ops and owes nothing
+    assert torch.allclose(net.head(x), ref(x), atol=1e-6) and act._bias_pending is False
+    # the convolution leaves its bias out (what it does for CUDA fp32 training inputs) while the follower's own input
+    # cannot take the fused kernel (here: a CPU tensor): the follower adds the bias itself, once
+    act._wants_bias = lambda t: True
+    assert torch.allclose(net.head(x), ref(x), atol=1e-6) and act._bias_pending is False
+    # and a follower that is called without its convolution having run first adds nothing
+    z = torch.randn(2, 8, 6, 6)
+    assert torch.allclose(act(z), torch.relu(z))
+
+
+def test_flat_gradient_buffer_keeps_each_parameters_dimension_order():
+    """HebbianStepper: the gradients of the back-prop parameters alias ONE flat buffer and keep their parameter's
+    strides (channels_last head weights, transposed-view weights) -- fused optimisers insist on matching layouts."""
+    from hebb.step import flatten_grads
+    a = nn.Parameter(torch.randn(8, 4, 3, 3).contiguous(memory_format=torch.channels_last))
+    b = nn.Parameter(torch.randn(6, 5, 2, 2).transpose(0, 1))
+    c = nn.Parameter(torch.randn(7))
+    flat = flatten_grads([a, b, c])
+    for p in (a, b, c):
+        assert p.grad.shape == p.shape and p.grad.stride() == p.stride()
+        assert p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+    (a.sum() * 2 + (b * b.detach()).sum() + c.sum() * 3).backward()
+    assert torch.equal(a.grad, torch.full_like(a, 2.0)) and torch.equal(c.grad, torch.full_like(c, 3.0))
+    assert torch.allclose(b.grad, b.detach())
+    assert float(flat.abs().sum()) > 0
