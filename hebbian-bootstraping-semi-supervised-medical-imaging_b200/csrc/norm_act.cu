@@ -233,6 +233,44 @@ mask_scale_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict_
   }
 }
 
+// gz = gout * mask * scale for channels_last storage (element i belongs to channel i % C), plus the per-channel sums of gz
+// (the bias gradient of the convolution in front: it would otherwise be one more full pass over gz).  The grid stride is
+// a multiple of C, so a thread meets the same four channels in every round: register sums, one fixed-order fold per
+// block into partial[block][C], one fixed-order fold over the blocks by bias_partial_fold_kernel -- deterministic.
+__global__ void __launch_bounds__(256)
+mask_scale_gb_cl_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ mask, float* __restrict__ gz,
+                        float* __restrict__ partial, long long n, int C, float scale) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (long long i = tid * 4; i < n; i += nth * 4) {
+    const float4 g = *reinterpret_cast<const float4*>(gout + i);
+    const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + i);
+    const float4 o = make_float4((m & 0xffu) ? g.x * scale : 0.f, (m & 0xff00u) ? g.y * scale : 0.f,
+                                 (m & 0xff0000u) ? g.z * scale : 0.f, (m & 0xff000000u) ? g.w * scale : 0.f);
+    *reinterpret_cast<float4*>(gz + i) = o;
+    a0 += o.x; a1 += o.y; a2 += o.z; a3 += o.w;
+  }
+  __shared__ float4 s[256];
+  s[threadIdx.x] = make_float4(a0, a1, a2, a3);
+  __syncthreads();
+  const int q = C >> 2;                       // channel quads; 256 % q == 0: thread t holds quad t % q
+  if ((int)threadIdx.x < q) {
+    float4 acc = s[threadIdx.x];
+    for (int t = threadIdx.x + q; t < 256; t += q) { const float4 v = s[t]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * C + 4 * threadIdx.x) = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bias_partial_fold_kernel(const float* __restrict__ partial, float* __restrict__ gb, int rows, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; ++r) acc += __ldg(partial + (long long)r * C + c);
+  gb[c] = acc;
+}
+
 }  // namespace hebb
 
 using namespace hebb;
@@ -337,6 +375,27 @@ int hebb_mask_scale(const float* gout, const uint8_t* mask, float* gz, int64_t n
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   mask_scale_bwd_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(gout, mask, gz, n, scale);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
+int hebb_mask_scale_gb(const float* gout, const uint8_t* mask, float* gz, float* gb, int64_t n, int64_t C, float scale,
+                       float* partial, int64_t partial_rows, void* stream) {
+  HEBB_TRY(device_ok());
+  if (!gout || !mask || !gz || !gb || !partial) return HEBB_EARG;
+  if (n <= 0 || C < 4 || C > 1024 || (C & (C - 1)) != 0 || n % C != 0 || partial_rows < 1) return HEBB_ESHAPE;
+  if (((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(gz) | reinterpret_cast<uintptr_t>(partial)) & 15) ||
+      (reinterpret_cast<uintptr_t>(mask) & 3))
+    return HEBB_EALIGN;
+  long long gx = cdiv(n, 256 * 4 * 2);
+  const long long cap = (long long)num_sms() * 8;
+  if (gx > cap) gx = cap;
+  if (gx > partial_rows) gx = partial_rows;
+  if (gx < 1) gx = 1;
+  // (256 threads x 4 channels per round and block: the grid stride gx * 1024 is a multiple of every power-of-two C <= 1024)
+  mask_scale_gb_cl_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(gout, mask, gz, partial, n, (int)C, scale);
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  bias_partial_fold_kernel<<<(unsigned)cdiv(C, 256), 256, 0, (cudaStream_t)stream>>>(partial, gb, (int)gx, (int)C);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   return HEBB_OK;
 }

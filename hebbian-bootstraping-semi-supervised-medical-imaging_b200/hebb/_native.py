@@ -27,7 +27,7 @@ EXPORTS = [
     'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
     'hebb_debug_umma_rate', 'hebb_debug_umma_rate_shared_a', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_upsample2x_bilinear',
     'hebb_layer_path', 'hebb_wgrad_path', 'hebb_debug_fused_plan', 'hebb_watchdog_code', 'hebb_debug_fused_prof', 'hebb_conv_swta_step_stats', 'hebb_bn_act_from_stats', 'hebb_conv_wgrad', 'hebb_maxpool2x',
-    'hebb_bias_relu_dropout', 'hebb_bias_relu_dropout_state', 'hebb_mask_scale',
+    'hebb_bias_relu_dropout', 'hebb_bias_relu_dropout_state', 'hebb_mask_scale', 'hebb_mask_scale_gb',
 ]
 
 
@@ -87,6 +87,7 @@ def load():
         lib.hebb_maxpool2x.argtypes = [vp, vp, i64, i64, i64, i64, i32, vp]
         lib.hebb_bias_relu_dropout.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, ctypes.c_uint64, vp]
         lib.hebb_bias_relu_dropout_state.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, vp, vp]
+        lib.hebb_mask_scale_gb.argtypes = [vp, vp, vp, vp, i64, i64, f32, vp, i64, vp]
         lib.hebb_mask_scale.argtypes = [vp, vp, vp, i64, f32, vp]
         lib.hebb_debug_launch_count.restype = ctypes.c_ulonglong
         lib.hebb_uses_tensor_cores.argtypes = [ctypes.POINTER(HebbDesc), i32]
@@ -419,6 +420,30 @@ def mask_scale(gout, mask, scale: float):
     check(load().hebb_mask_scale(gout.data_ptr(), mask.data_ptr(), gz.data_ptr(), gout.numel(), float(scale),
                                  _stream_ptr(gout.device)), 'mask_scale')
     return gz
+
+
+_sm_count = {}
+
+
+@_device_guard(0)
+def mask_scale_gb(gout, mask, scale: float):
+    """(gz, gb): hebb_mask_scale plus the per-channel sums of gz in the same pass, for dense channels_last tensors whose
+    channel count is a power of two (4..1024); None when the tensors do not qualify (the caller then sums gz itself)."""
+    C = mask.shape[1]
+    if (_dense_channel_inner(mask) != 1 or gout.stride() != mask.stride() or C < 4 or C > 1024 or (C & (C - 1))
+            or gout.dtype != torch.float32):
+        return None
+    dev = mask.device
+    sms = _sm_count.get(dev.index)
+    if sms is None:
+        sms = _sm_count[dev.index] = torch.cuda.get_device_properties(dev).multi_processor_count
+    rows = sms * 8
+    gz = torch.empty_like(mask, dtype=torch.float32)
+    gb = torch.empty(C, dtype=torch.float32, device=dev)
+    partial = torch.empty(rows * C, dtype=torch.float32, device=dev)
+    check(load().hebb_mask_scale_gb(gout.data_ptr(), mask.data_ptr(), gz.data_ptr(), gb.data_ptr(), gout.numel(), C, float(scale),
+                                    partial.data_ptr(), rows, _stream_ptr(dev)), 'mask_scale_gb')
+    return gz, gb
 
 
 def launch_count() -> int:

@@ -217,6 +217,10 @@ class _BiasReluDropoutFn(torch.autograd.Function):
         if gout.stride() != mask.stride():          # bring dL/dout into the layout the mask was written in
             cl = mask.dim() == 4 and _native._dense_channel_inner(mask) == 1
             gout = gout.contiguous(memory_format=torch.channels_last) if cl else gout.contiguous()
+        if ctx.needs_input_grad[1]:
+            both = _native.mask_scale_gb(gout, mask, ctx.scale)      # channels_last: bias gradient out of the same pass
+            if both is not None:
+                return both[0], both[1], None
         gz = _native.mask_scale(gout, mask, ctx.scale)
         gb = gz.sum(dim=(0, *range(2, gz.dim()))) if ctx.needs_input_grad[1] else None
         return gz, gb, None

@@ -190,6 +190,13 @@ int hebb_bias_relu_dropout(const float* z, const float* bias, float* out, uint8_
 int hebb_bias_relu_dropout_state(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
                                  int64_t inner, float p, uint64_t* state, void* stream);
 int hebb_mask_scale(const float* gout, const uint8_t* mask, float* gz, int64_t n, float scale, void* stream);
+/* hebb_mask_scale for channels_last storage (element i belongs to channel i % C; C a power of two, 4..1024) that also
+ * returns gb[c] = sum over the pixels of gz[., c] -- the bias gradient of the convolution in front of the fused
+ * activation (reference: autograd of `Conv -> ReLU -> Dropout`, models/networks_2d/unet.py:449-457), saving one more
+ * pass over gz.  partial: caller-owned scratch of partial_rows x C floats (the launch uses at most partial_rows blocks);
+ * sums are folded in a fixed order (deterministic). */
+int hebb_mask_scale_gb(const float* gout, const uint8_t* mask, float* gz, float* gb, int64_t n, int64_t C, float scale,
+                       float* partial, int64_t partial_rows, void* stream);
 
 /* ---- exported for tests and profiling ---- */
 
