@@ -473,6 +473,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
               continue;
             }
           }
+          const long long tc0 = PROF ? clock64() : 0;
           if (WG && p.xcl) {
             // channels_last box: [pixel][16 channels] fp32; four lanes share a pixel (one float4 = 4 channels each)
             const float4* st4 = reinterpret_cast<const float4*>(smem + p.off_stage + s * p.stage_bytes) + (p.padl - p.pW) * 4;
@@ -549,9 +550,11 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             st_shared_v4(swz<XCH>(row, XCH / 2 + 2 * cg), lp[0], lp[1], lp[2], lp[3]);
             st_shared_v4(swz<XCH>(row, XCH / 2 + 2 * cg + 1), lp[4], lp[5], lp[6], lp[7]);
           }
+          const long long tc1 = PROF ? clock64() : 0;
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) { mbar_arrive(xr_full + 8 * r); mbar_arrive(st_empty + 8 * s); }
+          if (PROF) { prof_acc[0] += tc1 - tc0; prof_acc[1] += clock64() - tc1; }      // [0] conversion, [1] fence + arrives
           if (++s == p.NST) { s = 0; ph ^= 1; }
         }
     }

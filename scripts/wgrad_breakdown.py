@@ -37,7 +37,8 @@ if os.environ.get('HEBB_FUSED_PROF') == '1':
     names = {0: 'w_full', 1: 'st_empty', 2: 'xr_full', 3: 'tf_empty', 4: 'r_full', 5: 'st_full', 6: 'xr_empty', 7: 'tf_full', 8: 'done', 9: 'r_empty'}
     roles = {0: 'producer', 2: 'mma.dw', 3: 'conv0', 6: 'conv3', 7: 'epi0.a', 11: 'epi1.a'}
     print('   gy-loader sections (kcyc): load+split+stores %.1f  fence+arrive %.1f' % (m[7, 2] / 1e3, m[7, 3] / 1e3))
+    print('   converter sections (kcyc, conv0): conversion loop %.1f  fence+arrives %.1f' % (m[3, 0] / 1e3, m[3, 1] / 1e3))
     for w, rn in roles.items():
         tot = m[w, 10]
-        skip = (0, 1, 2, 3) if w >= 7 else ()
+        skip = (0, 1, 2, 3) if w >= 7 else ((0, 1) if w >= 3 else ())
         print(f'   {rn:9s} total {tot / 1e3:8.1f} kcyc | ' + '  '.join(f'{names[i]} {m[w, i] / 1e3:.1f}' for i in range(10) if i not in skip and m[w, i] > 0.005 * tot))
