@@ -7,23 +7,28 @@
 // loads (out-of-bounds zero fill materialises the zero halo of hebb.py:83-85), converted to bf16 hi/lo in shared
 // memory, y is written once, and the responses r = softmax_c(k y) never leave the SM.
 //
-//   persistent CTA (one per SM), work item = (image b, TH x TW output tile); per CTA:
-//   warp 0      TMA producer: per padded tile row and 16-channel group one 3-D box  [16 ch][1 row][pitch] fp32
-//   warps 2-5   converter: fp32 [ch][pos] staging -> x image [pos][hi Cin | lo Cin] bf16, 16-byte chunks XOR-swizzled
-//               on absolute address bits (SWIZZLE_64B for Cin = 16, SWIZZLE_128B for Cin = 32)
-//   warp 1      tcgen05.mma issuer, per 128-position block:
-//                 forward  D[pos, co] += x[pos + tap][ci] W[tap][ci][co]: A = the x image read K-major (a tap is a
-//                          start-address offset of whole rows, hi/lo halves are 32-byte offsets), B = packed weights;
-//                          3 products (hi*lo, hi*hi, lo*hi) per tap and 16-channel slab into one fp32 accumulator
-//                 update   H[(kh, hl, ci), (kw, hl', co)] += x[q + kh*pitch] r[q - kw]: the SAME x image read MN-major
-//                          with an atom stride of one tile row (M = 128 rows = kh copies x [hi; lo] x Cin), the response
-//                          image read with an atom stride of ONE position (N = kW copies x [hi | lo] x Cout): ONE
-//                          instruction per 16 positions covers all taps and all four hi/lo products
-//                          (tests/test_umma_probe.py pins these descriptor forms on hardware)
-//   warps 6-13  epilogue (two sets alternate blocks): TMEM -> y = acc/|w| + b -> global; winner (+ near-tie list);
-//               BatchNorm sums; r = softmax -> bf16 hi/lo -> response image in shared memory; running sums of r
+//   persistent CTA (one per SM), work item = (image b, TH x TW output tile); per CTA (NCW converter warps):
+//   warp 0        TMA producer: per padded tile row and 16-channel group one 3-D box  [16 ch][1 row][pitch] fp32
+//                 (weight-gradient mode on channels_last tensors: 4-D boxes [pitch pixels][16 ch])
+//   warp 1        tcgen05.mma issuer of the forward, per 128-position block:
+//                   D[pos, co] += x[pos + tap][ci] W[tap][ci][co]: A = the x image read K-major (a tap is a start-address
+//                   offset of whole rows, hi/lo halves are 32-byte offsets), B = packed weights [w_hi | w_lo] stacked along
+//                   N for x_hi, w_hi for x_lo: 2 instructions per tap and 16-channel slab into one fp32 accumulator
+//   warp 2        tcgen05.mma issuer of the update, lagging until a block's responses are through the epilogue:
+//                   H[(kh, hl, ci), (kw, hl', co)] += x[q + kh*pitch] r[q - kw]: the SAME x image read MN-major with an
+//                   atom stride of one tile row (M = 128 rows = kh copies x [hi; lo] x Cin), the response image read with
+//                   an atom stride of ONE position (N = kW copies x [hi | lo] x Cout): ONE instruction per 16 positions
+//                   covers all taps and all four hi/lo products (tests/test_umma_probe.py pins these descriptor forms)
+//   warps 3..2+NCW  converter: fp32 staging -> x image [pos][hi Cin | lo Cin] bf16, 16-byte chunks XOR-swizzled on absolute
+//                 address bits (SWIZZLE_64B for Cin = 16, SWIZZLE_128B for Cin = 32); a warp owns whole stages in turn
+//                 (NCW = 2; 4 for the patch gather of the 3-channel first layer; 6 in weight-gradient mode)
+//   last 8 warps  epilogue (two sets alternate blocks): TMEM -> y = acc/|w| + b -> global; winner (+ near-tie list);
+//                 BatchNorm sums; r = softmax -> bf16 hi/lo -> response image in shared memory; running sums of r.
+//                 Weight-gradient mode (template flag WG, hebb_conv_wgrad): no forward, no softmax -- these warps read
+//                 dL/dy[b, co, pixel] from global memory and split it into the response ring instead.
 //   The update accumulators stay in TMEM for the whole kernel; each CTA writes ONE partial [taps][Cin][Cout] (x2 for the
-//   hi/lo rows of x), summed in a fixed order by tc_finalize_kernel together with the decay term -(sum_p r) W.
+//   hi/lo rows of x), summed in a fixed order by tc_finalize_kernel together with the decay term -(sum_p r) W
+//   (fused_wgrad_finalize_kernel in weight-gradient mode: no decay, += into grad_w).
 #include "common.cuh"
 #include "umma.cuh"
 #include <cuda.h>
@@ -45,7 +50,8 @@ constexpr int kRSlots = kDwLag + 2;       // response ring: at most this many sl
 constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxRows + 2 + 2 + 2 * kRSlots + 2;
 // warps: 0 TMA producer, 1 forward issuer, 2 update issuer, 3 .. 2+NCW converter, then the two epilogue sets of four.
 // NCW = 2 converter warps for the plain layers (13 warps: the issuing warps then share their scheduler with epilogue
-// warps only -- with a converter warp on every scheduler the same kernel ran 25 % slower), 4 for the patch gather.
+// warps only -- with a converter warp on every scheduler the same kernel ran 25 % slower), 4 for the patch gather, 6 in
+// weight-gradient mode (no forward issuer to disturb; the converter is the critical path there).
 
 struct FusedParams {
   float* y; int32_t* winner; const float* inv; const float* bias; float* rsum; double* ystats; float* hpart; int* err;
