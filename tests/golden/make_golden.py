@@ -447,8 +447,42 @@ def round2_goldens():
     print('round-2 goldens written:', os.path.getsize(os.path.join(HERE, 'hebb_golden_r2.npz')) // 1024, 'KiB')
 
 
+def round2b_goldens():
+    """hebb_golden_r2b.npz: anisotropic 3-D kernels / paddings as `unet3d_urpc` builds its blocks
+    (models/networks_3d/unet3d_urpc.py:32: kernel (3,3,1), padding (1,1,0)) -- SURVEY 8f row 4.  The reference hands the
+    padding tuple to F.pad (hebb3d.py:82-84), which pads from the LAST dimension backwards: (1,1,0) pads W and H by 1 and D
+    by 0 while the kernel spans 3 along D and 1 along W, so the output is (D-2, H, W+2).  Parity means reproducing that."""
+    ref, mk = load_reference()
+    out, meta = {}, {}
+    g = torch.Generator().manual_seed(20261020)
+
+    def rnd(*shape, scale=1.0):
+        return torch.randn(*shape, generator=g) * scale
+
+    for (name, Cin, Cout, kern, pad, sp) in [('aniso3d_8_16', 8, 16, (3, 3, 1), (1, 1, 0), (7, 9, 10)),
+                                             ('aniso3d_32_64', 32, 64, (3, 3, 1), (1, 1, 0), (6, 8, 10)),
+                                             ('aniso3d_16_32_k133', 16, 32, (1, 3, 3), (1, 1, 0), (5, 8, 9))]:
+        layer = ref.HebbianConv3d(Cin, Cout, kern, padding=pad, bias=True, w_nrm=True, mode='swta', k=5., alpha=1.)
+        with torch.no_grad():
+            layer.weight.copy_(rnd(*layer.weight.shape, scale=0.3))
+            layer.bias.copy_(rnd(Cout, scale=0.1))
+        layer.train()
+        x = rnd(2, Cin, *sp)
+        y = layer(x)
+        out[name + '/x'], out[name + '/w'], out[name + '/b'] = x.numpy(), layer.weight.detach().numpy(), layer.bias.detach().numpy()
+        out[name + '/y'], out[name + '/dw1'] = y.detach().numpy(), layer.delta_w.clone().numpy()
+        meta[name] = dict(kind='aniso3d', Cin=Cin, Cout=Cout, kernel=list(kern), padding=list(pad), spatial=list(sp), k=5.,
+                          out_shape=list(y.shape))
+    np.savez_compressed(os.path.join(HERE, 'hebb_golden_r2b.npz'), **out)
+    with open(os.path.join(HERE, 'hebb_golden_r2b_meta.json'), 'w') as f:
+        json.dump(meta, f, indent=1)
+    print('wrote hebb_golden_r2b.npz', {k: v['out_shape'] for k, v in meta.items()})
+
+
 if __name__ == '__main__':
-    if '--round2' in sys.argv:
+    if '--round2b' in sys.argv:
+        round2b_goldens()
+    elif '--round2' in sys.argv:
         round2_goldens()
     else:
         main()

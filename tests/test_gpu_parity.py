@@ -803,6 +803,30 @@ def test_hundred_step_drift_tensor_core_layer(nd, opt_name, prec):
     assert e1 < TOL_DW[prec] and e100 < TOL_DW[prec]
 
 
+_G2B = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'hebb_golden_r2b.npz'))
+_META2B = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'hebb_golden_r2b_meta.json')))
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16x3'])
+@pytest.mark.parametrize('name', sorted(_META2B))
+def test_anisotropic_3d_kernels_vs_reference_golden(name, prec):
+    """HebbianConv3d with kernel (3,3,1) / padding (1,1,0) as in unet3d_urpc, incl. the reference's
+    F.pad ordering of the padding tuple (hebb3d.py:82-84): output shape, y and delta_w against the reference run."""
+    m = _META2B[name]
+    layer = hebb.HebbianConv3d(m['Cin'], m['Cout'], tuple(m['kernel']), padding=tuple(m['padding']), bias=True, w_nrm=True,
+                               mode='swta', k=m['k'], alpha=1.)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(_G2B[name + '/w']))
+        layer.bias.copy_(torch.from_numpy(_G2B[name + '/b']))
+    layer.prec = prec
+    layer = layer.to(DEV).train()
+    y = layer(torch.from_numpy(_G2B[name + '/x']).to(DEV))
+    assert list(y.shape) == m['out_shape']
+    ey, edw = relerr(y, _G2B[name + '/y']), relerr(layer.delta_w, _G2B[name + '/dw1'])
+    record('anisotropic_3d_vs_reference_golden', f'{name}/{prec}', y=ey, dw=edw)
+    assert ey < 1e-4 and edw < 1e-4
+
+
 @pytest.mark.parametrize('prec', ['bf16x3', 'bf16'])
 @pytest.mark.parametrize('name', ['act_relu_16_16', 'act_relu_32_64'])
 def test_nonidentity_act_vs_reference_golden(name, prec):

@@ -20,6 +20,8 @@ from helpers import digest_err
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G2 = np.load(os.path.join(ROOT, 'tests', 'golden', 'hebb_golden_r2.npz'))
 STEPS = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'network_steps_golden.json')))
+G2B = np.load(os.path.join(ROOT, 'tests', 'golden', 'hebb_golden_r2b.npz'))
+META2B = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'hebb_golden_r2b_meta.json')))
 
 
 def sampled_relerr(w, idx, ref_samples):
@@ -60,6 +62,23 @@ def test_oracle_nonidentity_act_matches_reference(name):
     y = layer(torch.from_numpy(G2[name + '/x']))
     assert float((y - torch.from_numpy(G2[name + '/y'])).norm() / torch.from_numpy(G2[name + '/y']).norm()) < 1e-6
     ref = torch.from_numpy(G2[name + '/dw1'])
+    assert float((layer.delta_w - ref).norm() / ref.norm()) < 1e-5
+
+
+@pytest.mark.parametrize('name', sorted(META2B))
+def test_oracle_anisotropic_3d_kernels_match_reference(name):
+    """Kernel (3,3,1) / padding (1,1,0) as unet3d_urpc builds its blocks: the reference hands the padding
+    tuple to F.pad, which pads from the last dimension backwards -- the output shape is part of the fixture."""
+    m = META2B[name]
+    layer = O.OracleHebbConv(3, m['Cin'], m['Cout'], tuple(m['kernel']), padding=tuple(m['padding']), bias=True, k=m['k'], alpha=1.)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(G2B[name + '/w']))
+        layer.bias.copy_(torch.from_numpy(G2B[name + '/b']))
+    layer.train()
+    y = layer(torch.from_numpy(G2B[name + '/x']))
+    assert list(y.shape) == m['out_shape']
+    assert float((y - torch.from_numpy(G2B[name + '/y'])).norm() / torch.from_numpy(G2B[name + '/y']).norm()) < 1e-6
+    ref = torch.from_numpy(G2B[name + '/dw1'])
     assert float((layer.delta_w - ref).norm() / ref.norm()) < 1e-5
 
 
