@@ -628,7 +628,7 @@ def run_ours(args):
                        'hebb_params': HEBB_PARAMS if args.workload != 'c1' else {'mode': 'swta', 'k': 3.0, 'alpha': 1.0},
                        'optimizer': f'adam lr={lr}' + (' (torch.optim.Adam(fused=True))' if main['fused_adam'] else ''), 'precision_mode': args.prec,
                        'fused_norm_act_upsample': (not args.no_fuse) and args.workload != 'c1',
-                       'fused_ops': 'BatchNorm(train)+act with statistics from the conv epilogue, 2x up-sampling, 2x max pooling, bias+ReLU+dropout of the back-prop head (own Philox dropout stream)' if ((not args.no_fuse) and args.workload != 'c1') else 'none',
+                       'fused_ops': 'BatchNorm(train)+act(+the Dropout behind it) with statistics from the conv epilogue, 2x up-sampling, 2x max pooling, bias+ReLU+dropout of the back-prop head (own Philox dropout stream)' if ((not args.no_fuse) and args.workload != 'c1') else 'none',
                        'head_weight_gradient': ('hebb_conv_wgrad (fp32-equivalent split) for <= %d filters: the fused kernel in weight-gradient mode for 16->64 and 64->32, the tcgen05 update kernel for the 2-class layer' % args.head_wgrad) if ((not args.no_fuse) and args.head_wgrad and args.workload != 'c1') else 'cuDNN',
                        'backward': 'stock ATen' if args.aten_backward else 'native dgrad/wgrad on the tcgen05 kernels where the planner takes the layer',
                        'backprop_head_memory_format': 'nchw' if (args.head_nchw or args.workload != 'c2') else 'channels_last (input converted once, by a forward pre-hook)', 'l2': 'flushed between timed steps (256 MB fill)',

@@ -67,6 +67,41 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
   }
 }
 
+// out = dropout_p(act(y * scale[c] + shift[c])): the normalise + activate pass with the nn.Dropout that follows it in the
+// networks' blocks (models/networks_2d/unet.py:53-61) folded in.  No mask is kept: the pass is only taken where nothing
+// back-propagates through it.  Philox stream as in bias_relu_dropout_fwd_kernel (device-resident {seed, launches} state).
+__global__ void __launch_bounds__(256)
+bn_act_dropout_apply_kernel(const float* __restrict__ y, float* __restrict__ out, const float* __restrict__ scale_shift,
+                            int C, long long S, long long total, float slope, float p, float keep_scale,
+                            const unsigned long long* __restrict__ state) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  curandStatePhilox4_32_10_t rng;
+  curand_init(state[0], (unsigned long long)tid, state[1] << 24, &rng);
+  const bool vec = ((S & 3) == 0) && (((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+  if (vec) {
+    for (long long i = tid * 4; i < total; i += nth * 4) {
+      const int c = (int)((i / S) % C);
+      const float sc = __ldg(scale_shift + 2 * c), sh = __ldg(scale_shift + 2 * c + 1);
+      const float4 u = curand_uniform4(&rng);
+      float4 v = *reinterpret_cast<const float4*>(y + i);
+      v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh); v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+      v.x = v.x >= 0.f ? v.x : v.x * slope; v.y = v.y >= 0.f ? v.y : v.y * slope;
+      v.z = v.z >= 0.f ? v.z : v.z * slope; v.w = v.w >= 0.f ? v.w : v.w * slope;
+      v.x = u.x > p ? v.x * keep_scale : 0.f; v.y = u.y > p ? v.y * keep_scale : 0.f;      // curand_uniform is in (0, 1]
+      v.z = u.z > p ? v.z * keep_scale : 0.f; v.w = u.w > p ? v.w * keep_scale : 0.f;
+      *reinterpret_cast<float4*>(out + i) = v;
+    }
+  } else {
+    for (long long i = tid; i < total; i += nth) {
+      const int c = (int)((i / S) % C);
+      float v = fmaf(y[i], scale_shift[2 * c], scale_shift[2 * c + 1]);
+      v = v >= 0.f ? v : v * slope;
+      out[i] = curand_uniform(&rng) > p ? v * keep_scale : 0.f;
+    }
+  }
+}
+
 // out = act(y * scale[c] + shift[c]), act(v) = v >= 0 ? v : slope * v   (slope 0 -> ReLU, 1 -> identity)
 __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const float* __restrict__ y, float* __restrict__ out, const float* __restrict__ scale_shift,
@@ -275,11 +310,67 @@ bias_partial_fold_kernel(const float* __restrict__ partial, float* __restrict__ 
 
 using namespace hebb;
 
+// the normalise + activate (+ dropout) pass shared by the two BatchNorm entry points
+static int launch_bn_apply(const float* y, float* out, const float* ss, int64_t C, int64_t S, long long total, float slope, float p,
+                           uint64_t* state, cudaStream_t st) {
+  long long gx = cdiv(total, 256 * 4 * 4);
+  const long long cap = (long long)num_sms() * 16;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  if (p > 0.f) {
+    if (!state) return HEBB_EARG;
+    if (!(p < 1.f)) return HEBB_ESHAPE;
+    bn_act_dropout_apply_kernel<<<(unsigned)gx, 256, 0, st>>>(y, out, ss, (int)C, S, total, slope, p, 1.f / (1.f - p),
+                                                             reinterpret_cast<const unsigned long long*>(state));
+    HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+    dropout_state_bump_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(state));
+  } else {
+    bn_act_apply_kernel<<<(unsigned)gx, 256, 0, st>>>(y, out, ss, (int)C, S, total, slope);
+  }
+  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
+  return HEBB_OK;
+}
+
+static int bn_act_train_impl(const float* y, float* out, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, int64_t B, int64_t C, int64_t S, float eps, float momentum, float slope,
+                             float p, uint64_t* state, void* ws, size_t ws_bytes, void* stream);
+static int bn_act_from_stats_impl(const float* y, float* out, const double* y_stats, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, int64_t B, int64_t C, int64_t S, float eps,
+                                  float momentum, float slope, float p, uint64_t* state, void* ws, size_t ws_bytes, void* stream);
+
 extern "C" {
 
 int hebb_bn_act_train(const float* y, float* out, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, int64_t B, int64_t C, int64_t S, float eps, float momentum, float slope,
                       void* ws, size_t ws_bytes, void* stream) {
+  return bn_act_train_impl(y, out, gamma, beta, running_mean, running_var, B, C, S, eps, momentum, slope, 0.f, nullptr, ws, ws_bytes, stream);
+}
+
+int hebb_bn_act_train_dropout(const float* y, float* out, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, int64_t B, int64_t C, int64_t S, float eps, float momentum, float slope,
+                              float p, uint64_t* state, void* ws, size_t ws_bytes, void* stream) {
+  return bn_act_train_impl(y, out, gamma, beta, running_mean, running_var, B, C, S, eps, momentum, slope, p, state, ws, ws_bytes, stream);
+}
+
+int hebb_bn_act_from_stats(const float* y, float* out, const double* y_stats, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, int64_t B, int64_t C, int64_t S, float eps,
+                           float momentum, float slope, void* ws, size_t ws_bytes, void* stream) {
+  return bn_act_from_stats_impl(y, out, y_stats, gamma, beta, running_mean, running_var, B, C, S, eps, momentum, slope, 0.f, nullptr, ws,
+                                ws_bytes, stream);
+}
+
+int hebb_bn_act_from_stats_dropout(const float* y, float* out, const double* y_stats, const float* gamma, const float* beta,
+                                   float* running_mean, float* running_var, int64_t B, int64_t C, int64_t S, float eps,
+                                   float momentum, float slope, float p, uint64_t* state, void* ws, size_t ws_bytes, void* stream) {
+  return bn_act_from_stats_impl(y, out, y_stats, gamma, beta, running_mean, running_var, B, C, S, eps, momentum, slope, p, state, ws,
+                                ws_bytes, stream);
+}
+
+}  // extern "C"
+
+static int bn_act_train_impl(const float* y, float* out, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, int64_t B, int64_t C, int64_t S, float eps, float momentum, float slope,
+                             float p, uint64_t* state, void* ws, size_t ws_bytes, void* stream) {
   HEBB_TRY(device_ok());
   if (!y || !out || !ws) return HEBB_EARG;
   if (B <= 0 || C <= 0 || S <= 0 || C > 65535) return HEBB_ESHAPE;
@@ -303,19 +394,12 @@ int hebb_bn_act_train(const float* y, float* out, const float* gamma, const floa
   bn_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(sums, gamma, beta, ss, running_mean, running_var, (int)C,
                                                              (double)BS, eps, momentum);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-  const long long total = B * C * S;
-  long long gx = cdiv(total, 256 * 4 * 4);
-  const long long cap = (long long)num_sms() * 16;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  bn_act_apply_kernel<<<(unsigned)gx, 256, 0, st>>>(y, out, ss, (int)C, S, total, slope);
-  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-  return HEBB_OK;
+  return launch_bn_apply(y, out, ss, C, S, B * C * S, slope, p, state, st);
 }
 
-int hebb_bn_act_from_stats(const float* y, float* out, const double* y_stats, const float* gamma, const float* beta,
-                           float* running_mean, float* running_var, int64_t B, int64_t C, int64_t S, float eps,
-                           float momentum, float slope, void* ws, size_t ws_bytes, void* stream) {
+static int bn_act_from_stats_impl(const float* y, float* out, const double* y_stats, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, int64_t B, int64_t C, int64_t S, float eps,
+                                  float momentum, float slope, float p, uint64_t* state, void* ws, size_t ws_bytes, void* stream) {
   HEBB_TRY(device_ok());
   if (!y || !out || !ws || !y_stats) return HEBB_EARG;
   if (B <= 0 || C <= 0 || S <= 0 || C > 65535) return HEBB_ESHAPE;
@@ -326,14 +410,7 @@ int hebb_bn_act_from_stats(const float* y, float* out, const double* y_stats, co
   bn_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(y_stats, gamma, beta, ss, running_mean, running_var, (int)C,
                                                              (double)(B * S), eps, momentum);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-  const long long total = B * C * S;
-  long long gx = cdiv(total, 256 * 4 * 4);
-  const long long cap = (long long)num_sms() * 16;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  bn_act_apply_kernel<<<(unsigned)gx, 256, 0, st>>>(y, out, ss, (int)C, S, total, slope);
-  HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-  return HEBB_OK;
+  return launch_bn_apply(y, out, ss, C, S, B * C * S, slope, p, state, st);
 }
 
 static int bias_relu_dropout_impl(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
@@ -354,6 +431,8 @@ static int bias_relu_dropout_impl(const float* z, const float* bias, float* out,
   }
   return HEBB_OK;
 }
+
+extern "C" {
 
 int hebb_bias_relu_dropout(const float* z, const float* bias, float* out, uint8_t* mask, int64_t n, int64_t C,
                            int64_t inner, float p, uint64_t seed, void* stream) {

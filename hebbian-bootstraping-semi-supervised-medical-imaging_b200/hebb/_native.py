@@ -25,7 +25,7 @@ EXPORTS = [
     'hebb_query', 'hebb_status_str', 'hebb_last_cuda_error', 'hebb_version', 'hebb_out_shape',
     'hebb_workspace_bytes', 'hebb_wnorm', 'hebb_conv_swta_step', 'hebb_convT_swta_step',
     'hebb_local_update_multi', 'hebb_debug_umma_probe', 'hebb_debug_launch_count', 'hebb_uses_tensor_cores',
-    'hebb_debug_umma_rate', 'hebb_debug_umma_rate_shared_a', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_upsample2x_bilinear',
+    'hebb_debug_umma_rate', 'hebb_debug_umma_rate_shared_a', 'hebb_debug_plan', 'hebb_bn_act_train', 'hebb_bn_act_train_dropout', 'hebb_bn_act_from_stats_dropout', 'hebb_upsample2x_bilinear',
     'hebb_layer_path', 'hebb_wgrad_path', 'hebb_debug_fused_plan', 'hebb_watchdog_code', 'hebb_debug_fused_prof', 'hebb_conv_swta_step_stats', 'hebb_bn_act_from_stats', 'hebb_conv_wgrad', 'hebb_maxpool2x',
     'hebb_bias_relu_dropout', 'hebb_bias_relu_dropout_state', 'hebb_mask_scale', 'hebb_mask_scale_gb',
 ]
@@ -72,6 +72,7 @@ def load():
         lib.hebb_convT_swta_step.argtypes = step
         lib.hebb_conv_swta_step_stats.argtypes = step[:-1] + [vp, ctypes.POINTER(i32), vp]
         lib.hebb_bn_act_from_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, vp, ctypes.c_size_t, vp]
+        lib.hebb_bn_act_from_stats_dropout.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, f32, vp, vp, ctypes.c_size_t, vp]
         lib.hebb_conv_wgrad.argtypes = [ctypes.POINTER(HebbDesc), vp, vp, vp, i32, i32, vp, ctypes.c_size_t, i32, vp]
         lib.hebb_local_update_multi.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
                                                 ctypes.POINTER(f32), ctypes.POINTER(ctypes.c_int32), vp]
@@ -83,6 +84,7 @@ def load():
         lib.hebb_debug_umma_rate_shared_a.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
                                                       ctypes.c_uint32, ctypes.c_uint32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
         lib.hebb_bn_act_train.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, vp, ctypes.c_size_t, vp]
+        lib.hebb_bn_act_train_dropout.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, f32, vp, vp, ctypes.c_size_t, vp]
         lib.hebb_upsample2x_bilinear.argtypes = [vp, vp, i64, i64, i64, vp]
         lib.hebb_maxpool2x.argtypes = [vp, vp, i64, i64, i64, i64, i32, vp]
         lib.hebb_bias_relu_dropout.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, ctypes.c_uint64, vp]
@@ -251,14 +253,22 @@ def conv_step_stats(desc: HebbDesc, x, W, bias, kinv: float, y, winner, delta_w,
 
 
 @_device_guard(0)
-def bn_act_from_stats(y, stats, gamma, beta, running_mean, running_var, eps, momentum, slope):
-    """BatchNorm(train) + activation of y from precomputed per-channel (sum, sum of squares) (hebb_bn_act_from_stats)."""
+def bn_act_from_stats(y, stats, gamma, beta, running_mean, running_var, eps, momentum, slope, drop_p: float = 0.0):
+    """BatchNorm(train) + activation of y from precomputed per-channel (sum, sum of squares) (hebb_bn_act_from_stats);
+    drop_p > 0 folds the nn.Dropout(drop_p) that follows into the same pass (hebb_bn_act_from_stats_dropout)."""
     _require_cuda(y, 'input')
     B, C = y.shape[0], y.shape[1]
     S = y.numel() // (B * C)
     out = torch.empty_like(y)
     ws = workspace(y.device, C * 8 + 64)
     ptr = lambda t: t.data_ptr() if t is not None else None
+    if drop_p > 0.0:
+        st = dropout_state(y.device)
+        check(load().hebb_bn_act_from_stats_dropout(y.data_ptr(), out.data_ptr(), stats.data_ptr(), ptr(gamma), ptr(beta),
+                                                    ptr(running_mean), ptr(running_var), B, C, S, float(eps), float(momentum),
+                                                    float(slope), float(drop_p), st.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                    _stream_ptr(y.device)), 'bn_act_from_stats_dropout')
+        return out
     check(load().hebb_bn_act_from_stats(y.data_ptr(), out.data_ptr(), stats.data_ptr(), ptr(gamma), ptr(beta), ptr(running_mean),
                                         ptr(running_var), B, C, S, float(eps), float(momentum), float(slope), ws.data_ptr(),
                                         ws.numel(), _stream_ptr(y.device)), 'bn_act_from_stats')
@@ -323,8 +333,9 @@ def plan(desc: HebbDesc, prec: int):
 
 
 @_device_guard(0)
-def bn_act_train(y, gamma, beta, running_mean, running_var, eps, momentum, slope, out=None):
-    """BatchNorm(train) + (Leaky)ReLU on a contiguous [B, C, *spatial] fp32 CUDA tensor (hebb_bn_act_train)."""
+def bn_act_train(y, gamma, beta, running_mean, running_var, eps, momentum, slope, out=None, drop_p: float = 0.0):
+    """BatchNorm(train) + (Leaky)ReLU on a contiguous [B, C, *spatial] fp32 CUDA tensor (hebb_bn_act_train); drop_p > 0
+    folds the nn.Dropout(drop_p) that follows into the same pass (hebb_bn_act_train_dropout)."""
     _require_cuda(y, 'input')
     B, C = y.shape[0], y.shape[1]
     S = y.numel() // (B * C)
@@ -332,6 +343,12 @@ def bn_act_train(y, gamma, beta, running_mean, running_var, eps, momentum, slope
         out = torch.empty_like(y)
     ws = workspace(y.device, C * 24 + 64)
     ptr = lambda t: t.data_ptr() if t is not None else None
+    if drop_p > 0.0:
+        st = dropout_state(y.device)
+        check(load().hebb_bn_act_train_dropout(y.data_ptr(), out.data_ptr(), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                               B, C, S, float(eps), float(momentum), float(slope), float(drop_p), st.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), _stream_ptr(y.device)), 'bn_act_train_dropout')
+        return out
     check(load().hebb_bn_act_train(y.data_ptr(), out.data_ptr(), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
                                    B, C, S, float(eps), float(momentum), float(slope), ws.data_ptr(), ws.numel(),
                                    _stream_ptr(y.device)), 'bn_act_train')

@@ -35,11 +35,14 @@ def _fast_ok(x, mod):
 class _FusedBNActMixin:
     """Mixed into a BatchNorm instance by fuse_norm_act(); `_act_slope` is the fused activation."""
 
+    _drop_p = 0.0          # > 0: the nn.Dropout that followed the activation lives in this module too (fuse_norm_act)
+
     def forward(self, x):
         if not (self.training and self.track_running_stats and self.momentum is not None and _fast_ok(x, self)):
             y = super().forward(x)
             s = self._act_slope
-            return y if s == 1.0 else (F.relu(y) if s == 0.0 else F.leaky_relu(y, s))
+            y = y if s == 1.0 else (F.relu(y) if s == 0.0 else F.leaky_relu(y, s))
+            return F.dropout(y, self._drop_p, self.training) if self._drop_p > 0.0 else y
         self._check_input_dim(x)
         if self.num_batches_tracked is not None:
             self.num_batches_tracked.add_(1)
@@ -50,9 +53,9 @@ class _FusedBNActMixin:
             # the producing Hebbian layer already summed y and y^2 in its epilogue: skip the statistics pass
             src._y_stats = None
             return _native.bn_act_from_stats(x, held[1], self.weight, self.bias, self.running_mean, self.running_var,
-                                             self.eps, self.momentum, self._act_slope)
+                                             self.eps, self.momentum, self._act_slope, drop_p=self._drop_p)
         return _native.bn_act_train(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
-                                    self.momentum, self._act_slope)
+                                    self.momentum, self._act_slope, drop_p=self._drop_p)
 
 
 class FusedBatchNormAct2d(_FusedBNActMixin, nn.BatchNorm2d):
@@ -288,8 +291,9 @@ def _slope_of(m):
     return None
 
 
-def fuse_norm_act(model: nn.Module, head_wgrad: int = 64, fuse_stats: bool = True, fuse_head_act: bool = True) -> nn.Module:
-    n_bn = n_up = n_pool = n_head = n_act = 0
+def fuse_norm_act(model: nn.Module, head_wgrad: int = 64, fuse_stats: bool = True, fuse_head_act: bool = True,
+                  fuse_dropout: bool = True) -> nn.Module:
+    n_bn = n_up = n_pool = n_head = n_act = n_drop = 0
     for mod in model.modules():
         if isinstance(mod, nn.Sequential):
             items = list(mod._modules.items())
@@ -304,6 +308,13 @@ def fuse_norm_act(model: nn.Module, head_wgrad: int = 64, fuse_stats: bool = Tru
                         m.__dict__['_src_conv'] = (conv,)            # plain attribute, not a sub-module: no state_dict entry
                     if slope is not None:
                         mod._modules[items[i + 1][0]] = nn.Identity()     # activation now lives in the fused module
+                        # ... and so does the Dropout behind it (Conv -> BN -> LeakyReLU -> Dropout -> Conv blocks)
+                        if fuse_dropout and i + 2 < len(items) and type(items[i + 2][1]) is nn.Dropout:
+                            d = items[i + 2][1]
+                            if 0.0 < d.p < 1.0 and not d.inplace:
+                                m._drop_p = float(d.p)
+                                mod._modules[items[i + 2][0]] = nn.Identity()
+                                n_drop += 1
                     n_bn += 1
         if fuse_head_act and isinstance(mod, nn.Sequential):
             items = list(mod._modules.items())
@@ -333,5 +344,5 @@ def fuse_norm_act(model: nn.Module, head_wgrad: int = 64, fuse_stats: bool = Tru
                   and m.out_channels <= int(head_wgrad)):
                 m.__class__ = {nn.Conv2d: FastWgradConv2d, nn.Conv3d: FastWgradConv3d, NoBiasConv2d: NoBiasFastWgradConv2d}[type(m)]
                 n_head += 1
-    model._hebb_fused = dict(bn_act=n_bn, upsample=n_up, maxpool=n_pool, head_wgrad=n_head, bias_relu_dropout=n_act)
+    model._hebb_fused = dict(bn_act=n_bn, upsample=n_up, maxpool=n_pool, head_wgrad=n_head, bias_relu_dropout=n_act, bn_act_dropout=n_drop)
     return model

@@ -166,6 +166,19 @@ int hebb_bn_act_from_stats(const float* y, float* out, const double* y_stats, co
                            float* running_mean, float* running_var, int64_t B, int64_t C, int64_t S, float eps,
                            float momentum, float slope, void* ws, size_t ws_bytes, void* stream);
 
+/* The two calls above with the nn.Dropout(p) that follows BatchNorm + activation inside the networks' blocks
+ * (models/networks_2d/unet.py:53-61: Conv -> BatchNorm -> LeakyReLU -> Dropout -> Conv ...) folded into the same pass:
+ * out = dropout_p(act(bn(y))), kept values scaled by 1/(1-p); no mask is returned (the pass is for tensors nothing
+ * back-propagates through).  state: the device-resident Philox state {seed, launches so far} of
+ * hebb_bias_relu_dropout_state (incremented on `stream`).  0 <= p < 1; p = 0 is the plain call. */
+int hebb_bn_act_train_dropout(const float* y, float* out, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, int64_t B, int64_t C, int64_t S, float eps, float momentum, float slope,
+                              float p, uint64_t* state, void* ws, size_t ws_bytes, void* stream);
+int hebb_bn_act_from_stats_dropout(const float* y, float* out, const double* y_stats, const float* gamma, const float* beta,
+                                   float* running_mean, float* running_var, int64_t B, int64_t C, int64_t S, float eps,
+                                   float momentum, float slope, float p, uint64_t* state, void* ws, size_t ws_bytes,
+                                   void* stream);
+
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) — models/networks_2d/unet.py:171-172.
  * in: [N][H][W], out: [N][2H][2W] fp32, N = batch*channels. */
 int hebb_upsample2x_bilinear(const float* in, float* out, int64_t N, int64_t H, int64_t W, void* stream);

@@ -634,6 +634,39 @@ def test_fused_bias_relu_dropout(fmt, p):
         assert relerr(out, want) < 1e-7
 
 
+@pytest.mark.parametrize('from_stats', [False, True])
+def test_fused_bn_act_dropout(from_stats):
+    """hebb_bn_act_{train,from_stats}_dropout: the Dropout behind BatchNorm + LeakyReLU in the networks' blocks folded into
+    the normalise pass -- every output is either 0 or the un-dropped value / (1-p), the kept fraction is 1-p, eval mode and
+    p = 0 are the plain pass, and the fuse pass moves the module's p into the fused BatchNorm."""
+    import copy
+    from hebb.fused import fuse_norm_act
+    torch.manual_seed(3)
+    p = 0.3
+    blk = torch.nn.Sequential(hebb.HebbianConv2d(16, 32, 3, padding=1, bias=False, k=5., alpha=1.), torch.nn.BatchNorm2d(32),
+                              torch.nn.LeakyReLU(), torch.nn.Dropout(p))
+    for q in blk[1].parameters():
+        q.requires_grad_(False)
+    ref = copy.deepcopy(blk)
+    ref[3].p = 0.0
+    net = torch.nn.Module()
+    net.blk = blk
+    fuse_norm_act(net, fuse_stats=from_stats)
+    assert net._hebb_fused['bn_act_dropout'] == 1 and type(blk[3]) is torch.nn.Identity and blk[1]._drop_p == p
+    net, ref = net.to(DEV).train(), ref.to(DEV).train()
+    x = torch.randn(4, 16, 40, 36, device=DEV)
+    out, want = blk(x), ref(x)
+    kept = out != 0
+    assert relerr(out[kept], (want / (1.0 - p))[kept]) < 1e-5
+    frac = float(kept.sum()) / float((want != 0).sum())
+    assert abs(frac - (1.0 - p)) < 0.01
+    out2 = blk(x)
+    ref(x)                                                        # (keep the running statistics of the twin in step)
+    assert not torch.equal(out2 != 0, kept)                       # a new mask per call (device-resident stream state)
+    net.eval(); ref.eval()
+    assert relerr(blk(x), ref(x)) < 1e-5                          # eval: no dropout, stock path
+
+
 def test_fuse_pass_keeps_network_output_and_state():
     from hebb.fused import fuse_norm_act
     torch.manual_seed(0)
@@ -646,7 +679,7 @@ def test_fuse_pass_keeps_network_output_and_state():
     ref = copy.deepcopy(net).to(DEV).train()
     keys = list(net.state_dict().keys())
     fuse_norm_act(net)
-    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4, 'head_wgrad': 3, 'bias_relu_dropout': 2}
+    assert list(net.state_dict().keys()) == keys and net._hebb_fused == {'bn_act': 18, 'upsample': 4, 'maxpool': 4, 'head_wgrad': 3, 'bias_relu_dropout': 2, 'bn_act_dropout': 0}
     net = net.to(DEV).train()
     x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(5)).to(DEV)
     a, b = ref(x), net(x)
