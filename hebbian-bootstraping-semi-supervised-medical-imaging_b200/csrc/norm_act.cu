@@ -129,37 +129,45 @@ bn_act_apply_kernel(const float* __restrict__ y, float* __restrict__ out, const 
 }
 
 // nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) on [N][H][W] planes (N = B*C).
-// One thread per output pixel pair; source coordinate = o * (in-1)/(out-1), like ATen's
-// area_pixel_compute_source_index(align_corners=true).
+// Source coordinate = o * (in-1)/(out-1), like ATen's area_pixel_compute_source_index(align_corners=true).
+// A block works on whole output rows (256 / W of them at a time; a thread owns the output columns 2w, 2w+1 of its row and
+// keeps their horizontal taps in registers), so the only integer division left is one 32-bit one per row: the first
+// version decoded a flat 64-bit index per output pair and ran at a quarter of the HBM rate.
 __global__ void __launch_bounds__(256)
-upsample2x_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, long long N, int H, int W) {
+upsample2x_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, unsigned rows, int H, int W) {
   const int OH = 2 * H, OW = 2 * W;
   const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
   const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
-  const long long total = N * OH * (long long)W;      // each thread: output columns 2*w, 2*w+1
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(i % W);
-    const long long t = i / W;
-    const int oy = (int)(t % OH);
-    const long long n = t / OH;
-    const float fy = ry * oy;
-    const int y0 = (int)fy;
-    const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
-    const float ly = fy - y0, hy = 1.f - ly;
-    const float* r0 = in + (n * H + y0) * (long long)W;
-    const float* r1 = in + (n * H + y1) * (long long)W;
-    float o2[2];
+  const int rpb = W < 256 ? 256 / W : 1;                 // output rows per block and round
+  const int lr = W < 256 ? (int)threadIdx.x / W : 0;
+  if (lr >= rpb) return;
+  const int w0 = W < 256 ? (int)threadIdx.x - lr * W : (int)threadIdx.x;
+  for (int w = w0; w < W; w += 256) {
+    int x0[2], x1[2]; float lx[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const int ox = 2 * w + k;
-      const float fx = rx * ox;
-      const int x0 = (int)fx;
-      const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
-      const float lx = fx - x0, hx = 1.f - lx;
-      o2[k] = hy * (hx * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) + ly * (hx * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
+      const float fx = rx * (float)(2 * w + k);
+      x0[k] = (int)fx;
+      x1[k] = x0[k] + (x0[k] < W - 1 ? 1 : 0);
+      lx[k] = fx - (float)x0[k];
     }
-    *reinterpret_cast<float2*>(out + (n * OH + oy) * (long long)OW + 2 * w) = make_float2(o2[0], o2[1]);
+    for (unsigned row = blockIdx.x * (unsigned)rpb + (unsigned)lr; row < rows; row += gridDim.x * (unsigned)rpb) {
+      const unsigned n = row / (unsigned)OH;
+      const int oy = (int)(row - n * (unsigned)OH);
+      const float fy = ry * (float)oy;
+      const int y0 = (int)fy;
+      const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
+      const float ly = fy - (float)y0, hy = 1.f - ly;
+      const float* r0 = in + ((long long)n * H + y0) * W;
+      const float* r1 = in + ((long long)n * H + y1) * W;
+      float o2[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float hx = 1.f - lx[k];
+        o2[k] = hy * (hx * __ldg(r0 + x0[k]) + lx[k] * __ldg(r0 + x1[k])) + ly * (hx * __ldg(r1 + x0[k]) + lx[k] * __ldg(r1 + x1[k]));
+      }
+      *reinterpret_cast<float2*>(out + (long long)row * OW + 2 * w) = make_float2(o2[0], o2[1]);
+    }
   }
 }
 
@@ -297,13 +305,21 @@ mask_scale_gb_cl_kernel(const float* __restrict__ gout, const uint8_t* __restric
   }
 }
 
-__global__ void __launch_bounds__(256)
+// gb[c] = sum over the blocks' partial rows, in a fixed order: 1024 / C row groups each sum every (1024 / C)-th row, then
+// one thread per channel folds the groups (a single thread per channel walking all ~1200 rows took 0.1 ms)
+__global__ void __launch_bounds__(1024)
 bias_partial_fold_kernel(const float* __restrict__ partial, float* __restrict__ gb, int rows, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float s[1024];
+  const int G = 1024 / C;                       // C is a power of two <= 1024
+  const int c = threadIdx.x % C, g = threadIdx.x / C;
   float acc = 0.f;
-  for (int r = 0; r < rows; ++r) acc += __ldg(partial + (long long)r * C + c);
-  gb[c] = acc;
+  for (int r = g; r < rows; r += G) acc += __ldg(partial + (long long)r * C + c);
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  if (g == 0) {
+    for (int k = 1; k < G; ++k) acc += s[k * C + c];
+    gb[c] = acc;
+  }
 }
 
 }  // namespace hebb
@@ -474,7 +490,7 @@ int hebb_mask_scale_gb(const float* gout, const uint8_t* mask, float* gz, float*
   // (256 threads x 4 channels per round and block: the grid stride gx * 1024 is a multiple of every power-of-two C <= 1024)
   mask_scale_gb_cl_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(gout, mask, gz, partial, n, (int)C, scale);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
-  bias_partial_fold_kernel<<<(unsigned)cdiv(C, 256), 256, 0, (cudaStream_t)stream>>>(partial, gb, (int)gx, (int)C);
+  bias_partial_fold_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partial, gb, (int)gx, (int)C);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   return HEBB_OK;
 }
@@ -483,12 +499,14 @@ int hebb_upsample2x_bilinear(const float* in, float* out, int64_t N, int64_t H, 
   HEBB_TRY(device_ok());
   if (!in || !out) return HEBB_EARG;
   if (N <= 0 || H <= 0 || W <= 0 || H > (1 << 20) || W > (1 << 20)) return HEBB_ESHAPE;
-  const long long total = N * 2 * H * W;
-  long long gx = cdiv(total, 256 * 2);
+  const long long rows = N * 2 * H;                       // output rows
+  if (rows >= (1LL << 31)) return HEBB_ESHAPE;
+  const long long rpb = W < 256 ? 256 / W : 1;
+  long long gx = cdiv(rows, rpb * 4);                     // ~4 rounds per block
   const long long cap = (long long)num_sms() * 16;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  upsample2x_bilinear_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(in, out, N, (int)H, (int)W);
+  upsample2x_bilinear_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(in, out, (unsigned)rows, (int)H, (int)W);
   HEBB_CUDA_TRY(cudaGetLastError()); HEBB_LAUNCHED();
   return HEBB_OK;
 }
